@@ -1,0 +1,462 @@
+/*
+ * lwse.h — C ABI of the B200 reconcile-and-placement engine ("lwse") for the
+ * LeaderWorkerSet / DisaggregatedSet controllers.
+ *
+ * This is the drop-in boundary for the hot path named in BASELINE.json:
+ * a cgo (or any FFI) caller hands fixed-width record tables to the engine and
+ * reads fixed-width result tables back.  Plain pointers and sizes only; no
+ * CUDA, torch or C++ types cross this boundary.
+ *
+ * The reference (kubernetes-sigs/lws @ 1d9204a2) has no FFI for this path —
+ * every hot function is package-private Go.  Each entry point below therefore
+ * cites the reference function(s) whose arithmetic it replaces
+ * (paths relative to the reference root):
+ *
+ *   lwse_sweep_lws_*   pkg/controllers/leaderworkerset_controller.go:280-373
+ *                      (rollingUpdateParameters), :414-509 (updateConditions),
+ *                      :576-641 (getReplicaStates), :643-708 (partition math),
+ *                      :811-830 (stsMaxUnavailable);
+ *                      pkg/controllers/pod_controller.go:100-172 (worker-sts
+ *                      gating), :204-266 (handleRestartPolicy), :268-295
+ *                      (workerPodBelongsToLeader), :315-336
+ *                      (topologyValueFromPod), :338-362 (pendingPodsInGroup),
+ *                      :434-443 (worker ordinals);
+ *                      pkg/schedulerprovider/volcano_provider.go:72-83 (MinMember)
+ *   lwse_place_*       build-defined placement spec over the constraints of
+ *                      pkg/webhooks/pod_webhook.go:185-227 (exclusive affinity /
+ *                      anti-affinity per topology domain) — the reference has no
+ *                      node scoring; see DESIGN.md "Placement (parity unpinned)"
+ *   lwse_sweep_ds_*    pkg/controllers/disaggregatedset/planner.go:61-352,
+ *                      executor.go:199-302 (planner state / config / stability),
+ *                      :330-398 (scaleDownOld), disaggregatedset_controller.go:
+ *                      203-236 (cleanup predicate), service_manager.go:57-89
+ *   lwse_group_keys_*  pkg/webhooks/pod_webhook.go:180-182 + pkg/utils/utils.go:39-43
+ *                      (SHA-1 group / subgroup keys), :249-255 (getSubGroupIndex)
+ *
+ * Conventions
+ *   - All records are little-endian plain-old-data with explicit padding; every
+ *     table base must be 16-byte aligned.
+ *   - Every function returns LWSE_OK (0) or a negative lwse_status.  Nothing
+ *     aborts.  lwse_last_cuda_error() returns the cudaError_t behind
+ *     LWSE_ERR_CUDA.
+ *   - The caller owns every host buffer (cgo: C.malloc / pinned pool — the
+ *     engine never retains a host pointer past the call).  The engine owns its
+ *     device staging memory.
+ *   - An engine handle is bound to one CUDA device and runs one sweep at a time
+ *     (internal mutex).  Create one per GPU.
+ *   - There is no CPU fallback: if no CUDA device is usable lwse_create fails
+ *     with LWSE_ERR_NO_DEVICE.
+ */
+#ifndef LWSE_H_
+#define LWSE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LWSE_ABI_VERSION 1u
+
+#if defined(__GNUC__)
+#define LWSE_API __attribute__((visibility("default")))
+#else
+#define LWSE_API
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* Status codes                                                              */
+/* ------------------------------------------------------------------------- */
+typedef enum lwse_status {
+  LWSE_OK = 0,
+  LWSE_ERR_INVALID_ARG = -1, /* NULL / misaligned pointer, bad count            */
+  LWSE_ERR_NO_DEVICE = -2,   /* no usable CUDA device (no CPU fallback exists)  */
+  LWSE_ERR_CUDA = -3,        /* a CUDA call failed; see lwse_last_cuda_error    */
+  LWSE_ERR_OOM = -4,         /* device or pinned allocation failed              */
+  LWSE_ERR_BAD_TABLE = -5,   /* a base/count in a record points outside a table */
+  LWSE_ERR_NOT_READY = -6,   /* e.g. lwse_place_* before lwse_upload_nodes      */
+  LWSE_ERR_UNSUPPORTED = -7  /* e.g. more than LWSE_DS_MAX_ROLES roles          */
+} lwse_status;
+
+/* ------------------------------------------------------------------------- */
+/* Input records                                                             */
+/* ------------------------------------------------------------------------- */
+
+#define LWSE_NONE 0xFFFFFFFFu           /* "no index" (unscheduled, no domain, …) */
+#define LWSE_NODE_NOT_FOUND 0xFFFFFFFEu /* leader.spec.nodeName set, Node object missing */
+
+/* One LeaderWorkerSet object (64 B). */
+typedef struct lwse_lws_rec {
+  uint64_t uid_hash;  /* hash of metadata.uid: shard key, placement priority     */
+  uint64_t rev_hash;  /* hash of the revisionKey handed to the reconciler
+                         (leaderworkerset_controller.go:159,:196)                */
+  int32_t replicas;   /* *spec.replicas                                          */
+  int32_t size;       /* *spec.leaderWorkerTemplate.size                         */
+  int32_t partition;  /* *spec.rolloutStrategy.rollingUpdateConfiguration.partition */
+  int32_t max_surge;  /* IntVal, or the percent number when ..._IS_PERCENT       */
+  int32_t max_unavailable;
+  uint32_t flags;     /* LWSE_LWS_* */
+  int32_t sts_replicas;            /* leader sts *spec.replicas                  */
+  int32_t sts_partition;           /* leader sts rollingUpdate.partition         */
+  int32_t sts_replicas_annotation; /* Atoi(leaderworkerset.sigs.k8s.io/replicas) */
+  int32_t subgroup_size;           /* 0 = no subGroupPolicy                      */
+  uint32_t group_base;             /* first row of this object in the group table */
+  uint32_t group_count;            /* rows = group indices 0..group_count-1      */
+} lwse_lws_rec;
+
+#define LWSE_LWS_SURGE_IS_PERCENT (1u << 0)
+#define LWSE_LWS_UNAVAIL_IS_PERCENT (1u << 1)
+#define LWSE_LWS_STS_EXISTS (1u << 2)       /* leader StatefulSet found (:293)            */
+#define LWSE_LWS_UPDATED (1u << 3)          /* leaderWorkerSetUpdated argument (:325)     */
+#define LWSE_LWS_ANNOT_VALID (1u << 4)      /* strconv.Atoi of the annotation ok (:351)   */
+#define LWSE_LWS_RESTART_SHIFT 5            /* 2 bits: lwse_restart_policy                */
+#define LWSE_LWS_RESTART_MASK (3u << 5)
+#define LWSE_LWS_RECREATE_AFTER_START_ANNOT (1u << 7) /* pod_controller.go:220            */
+#define LWSE_LWS_STARTUP_LEADER_READY (1u << 8)       /* spec.startupPolicy == LeaderReady */
+#define LWSE_LWS_EXCLUSIVE_TOPOLOGY (1u << 9) /* exclusive-topology annotation present    */
+#define LWSE_LWS_SUBGROUP_LEADER_EXCLUDED (1u << 10)
+#define LWSE_LWS_GROUP_LABEL_INVALID (1u << 11) /* a leader pod's group-index label fails
+                                                   Atoi → updateConditions error (:434)   */
+#define LWSE_LWS_INTSTR_INVALID (1u << 12)  /* maxSurge/maxUnavailable string not "N%"    */
+#define LWSE_LWS_IRREGULAR (1u << 13)       /* encoder could not express the object
+                                               (see DESIGN.md "Encoder invariants")       */
+
+typedef enum lwse_restart_policy {
+  LWSE_RESTART_NONE = 0,          /* "None", "Default", anything else            */
+  LWSE_RESTART_ON_POD_RESTART = 1,/* RecreateGroupOnPodRestart                   */
+  LWSE_RESTART_AFTER_START = 2    /* RecreateGroupAfterStart                     */
+} lwse_restart_policy;
+
+/* One pod group = leader pod slot + its worker StatefulSet (64 B).
+ * Row r of an object describes group index r. */
+typedef struct lwse_group_rec {
+  uint64_t leader_rev_hash;   /* leader pod template-revision-hash label          */
+  uint64_t wsts_rev_hash;     /* worker sts template-revision-hash label          */
+  int32_t wsts_spec_replicas; /* worker sts *spec.replicas                        */
+  int32_t wsts_avail_replicas;/* worker sts status.availableReplicas              */
+  uint32_t leader_uid_hash;   /* leader pod metadata.uid                          */
+  uint32_t wsts_uid_hash;     /* worker sts metadata.uid                          */
+  uint32_t wsts_owner_uid_hash; /* controller ownerRef.uid of the worker sts      */
+  uint32_t leader_node;       /* node-table row, LWSE_NONE, or LWSE_NODE_NOT_FOUND */
+  uint32_t pod_base;          /* first row of this group in the pod table         */
+  uint32_t pod_count;         /* pods carrying (set name, group index) labels     */
+  uint32_t lws_index;         /* row of the owning object in the LWS table        */
+  uint32_t flags;             /* LWSE_GRP_* */
+  uint32_t reserved[2];
+} lwse_group_rec;
+
+#define LWSE_GRP_POD_PRESENT (1u << 0)    /* a leader pod with this group-index label exists */
+#define LWSE_GRP_POD_NAME_MATCH (1u << 1) /* its name == "<lws>-<idx>" (:609)                 */
+#define LWSE_GRP_POD_RUNNING (1u << 2)    /* status.phase == Running                          */
+#define LWSE_GRP_POD_READY (1u << 3)      /* Ready condition == True                          */
+#define LWSE_GRP_POD_DELETING (1u << 4)   /* deletionTimestamp != nil                         */
+#define LWSE_GRP_WSTS_LABEL_NAME_MATCH (1u << 5) /* sts with this group-index label is named
+                                                    "<lws>-<idx>" (:611)                      */
+#define LWSE_GRP_WSTS_FOUND (1u << 6)     /* Get(sts named like the leader pod) succeeded     */
+#define LWSE_GRP_WSTS_REV_SETTLED (1u << 7) /* status.currentRevision == status.updateRevision */
+#define LWSE_GRP_WSTS_OWNER_IS_POD (1u << 8)
+#define LWSE_GRP_WSTS_OWNER_NAME_MATCH (1u << 9) /* sts ownerRef.name == leader pod name      */
+#define LWSE_GRP_MISTAKEN_ANNOTATION (1u << 10)  /* leader carries leader-name annotation     */
+#define LWSE_GRP_REVISION_EXISTS (1u << 11)      /* ControllerRevision for leader's key found */
+
+/* One pod (16 B). */
+typedef struct lwse_pod_rec {
+  uint64_t rev_hash;       /* template-revision-hash label                        */
+  uint32_t owner_uid_hash; /* controller ownerRef.uid                             */
+  uint32_t bits;           /* LWSE_POD_* | node << LWSE_POD_NODE_SHIFT            */
+} lwse_pod_rec;
+
+#define LWSE_POD_PHASE_MASK 3u       /* 0 other, 1 Pending, 2 Running              */
+#define LWSE_POD_PHASE_PENDING 1u
+#define LWSE_POD_PHASE_RUNNING 2u
+#define LWSE_POD_ANY_RESTART (1u << 2) /* some (init)containerStatus.restartCount > 0 */
+#define LWSE_POD_DELETING (1u << 3)
+#define LWSE_POD_OWNER_SHIFT 4       /* 2 bits: 0 none, 1 Pod, 2 StatefulSet, 3 other */
+#define LWSE_POD_OWNER_MASK (3u << 4)
+#define LWSE_POD_OWNER_NAME_MATCH (1u << 6) /* ownerRef.name == "<lws>-<group>"    */
+#define LWSE_POD_IS_LEADER (1u << 7) /* worker-index label == "0"                  */
+#define LWSE_POD_NAME_OK (1u << 8)   /* GetParentNameAndOrdinal ordinal != -1      */
+#define LWSE_POD_SCHEDULED (1u << 9) /* node field below is valid                  */
+#define LWSE_POD_NODE_SHIFT 10       /* 22-bit node-table row                      */
+#define LWSE_POD_NODE_MAX ((1u << 22) - 1u)
+
+/* One node (16 B). */
+typedef struct lwse_node_rec {
+  uint64_t topo_value_hash; /* hash of node.labels[topologyKey]                   */
+  uint32_t domain_id;       /* dense id of that label value, or LWSE_NONE         */
+  uint16_t capacity;        /* pod slots available to LWS pods                    */
+  uint16_t flags;           /* LWSE_NODE_* */
+} lwse_node_rec;
+
+#define LWSE_NODE_HAS_TOPOLOGY (1u << 0) /* label present (pod_controller.go:330) */
+#define LWSE_NODE_SCHEDULABLE (1u << 1)
+
+/* ------------------------------------------------------------------------- */
+/* Output records                                                            */
+/* ------------------------------------------------------------------------- */
+
+/* Per LeaderWorkerSet (32 B). */
+typedef struct lwse_lws_out {
+  int32_t sts_partition;      /* rollingUpdateParameters → stsPartition           */
+  int32_t sts_replicas;       /* rollingUpdateParameters → replicas               */
+  int32_t sts_max_unavailable;/* constructLeaderStatefulSetApplyConfiguration     */
+  int32_t ready_replicas;     /* status.readyReplicas                             */
+  int32_t updated_replicas;   /* status.updatedReplicas                           */
+  int32_t min_member;         /* PodGroup spec.minMember                          */
+  uint32_t flags;             /* LWSE_LOUT_* */
+  int32_t unready_replicas;   /* calculateLWSUnreadyReplicas (diagnostic; 0 when
+                                 the reference does not compute it)               */
+} lwse_lws_out;
+
+#define LWSE_LOUT_RUP_ERROR (1u << 0)     /* rollingUpdateParameters returned err  */
+#define LWSE_LOUT_STATUS_ERROR (1u << 1)  /* updateConditions returned err         */
+#define LWSE_LOUT_COND_SHIFT 2            /* 2 bits: lwse_condition                */
+#define LWSE_LOUT_COND_MASK (3u << 2)
+#define LWSE_LOUT_UPDATE_DONE (1u << 4)
+#define LWSE_LOUT_EVENT_SHIFT 5           /* 2 bits: lwse_surge_event              */
+#define LWSE_LOUT_EVENT_MASK (3u << 5)
+#define LWSE_LOUT_IRREGULAR (1u << 7)
+
+typedef enum lwse_condition {
+  LWSE_COND_PROGRESSING = 0,
+  LWSE_COND_AVAILABLE = 1,
+  LWSE_COND_UPDATE_IN_PROGRESS = 2 /* UpdateInProgress + Progressing              */
+} lwse_condition;
+
+typedef enum lwse_surge_event {
+  LWSE_EVENT_NONE = 0,
+  LWSE_EVENT_DELETE_ONE = 1,  /* "deleting surge replica %s-%d" (:314)            */
+  LWSE_EVENT_DELETE_RANGE = 2 /* "deleting surge replicas from … to …" (:316)     */
+} lwse_surge_event;
+
+/* Per pod group (16 B). */
+typedef struct lwse_group_out {
+  uint32_t flags;           /* LWSE_GOUT_* */
+  uint32_t first_trigger;   /* pod row (relative to pod_base) of the first pod
+                               whose reconcile would recreate the group, or NONE  */
+  int32_t worker_replicas;  /* worker sts replicas (= size-1, ordinals start at 1)
+                               when LWSE_GOUT_CREATE_WSTS, else 0                 */
+  uint32_t domain_id;       /* nodeSelector topology domain of the workers
+                               (topologyValueFromPod), or LWSE_NONE               */
+} lwse_group_out;
+
+#define LWSE_GOUT_STATE_READY (1u << 0)    /* getReplicaStates ready  (name-checked)   */
+#define LWSE_GOUT_STATE_UPDATED (1u << 1)  /* getReplicaStates updated                 */
+#define LWSE_GOUT_COUNTED (1u << 2)        /* leader pod visited by updateConditions   */
+#define LWSE_GOUT_COND_READY (1u << 3)     /* updateConditions ready                   */
+#define LWSE_GOUT_COND_UPDATED (1u << 4)   /* updateConditions updated                 */
+#define LWSE_GOUT_PENDING (1u << 5)        /* pendingPodsInGroup                       */
+#define LWSE_GOUT_DELETE_LEADER (1u << 6)  /* some pod's reconcile issues Delete(leader) */
+#define LWSE_GOUT_LEADER_DELETING (1u << 7)/* …returns true because it is already going  */
+#define LWSE_GOUT_RESTART_ERROR (1u << 8)  /* worker name failed to parse (:231)       */
+#define LWSE_GOUT_CREATE_WSTS (1u << 9)    /* leader reconcile reaches Create(worker sts) */
+#define LWSE_GOUT_WAIT_SCHEDULE (1u << 10) /* exclusive topology, leader unscheduled   */
+#define LWSE_GOUT_TOPOLOGY_ERROR (1u << 11)/* node lacks the topology label (:331)     */
+#define LWSE_GOUT_REQUEUE_REVISION (1u << 12) /* revision missing → requeue 1s (:152)  */
+#define LWSE_GOUT_CREATE_PODGROUP (1u << 13)  /* SchedulerProvider.CreatePodGroupIfNotExists reached */
+
+/* ------------------------------------------------------------------------- */
+/* Table bundles                                                             */
+/* ------------------------------------------------------------------------- */
+
+/* The same bundle is used with host pointers (lwse_sweep_lws_host) and with
+ * device pointers (lwse_sweep_lws_device). */
+typedef struct lwse_lws_tables {
+  const lwse_lws_rec* lws;
+  uint32_t n_lws;
+  const lwse_group_rec* groups;
+  uint32_t n_groups;
+  const lwse_pod_rec* pods;
+  uint64_t n_pods;
+  lwse_lws_out* lws_out;     /* n_lws rows   */
+  lwse_group_out* group_out; /* n_groups rows */
+  uint32_t* node_occupancy;  /* optional: n_nodes counters, pods per node (this
+                                call ADDS into the host buffer's zeroed copy);
+                                NULL to skip                                      */
+  uint32_t flags;            /* LWSE_SWEEP_* */
+} lwse_lws_tables;
+
+#define LWSE_SWEEP_GANG (1u << 0) /* a SchedulerProvider is configured (min_member,
+                                     CREATE_PODGROUP are meaningful)              */
+
+typedef struct lwse_config {
+  uint32_t abi_version; /* LWSE_ABI_VERSION */
+  int32_t device;       /* CUDA device ordinal */
+  uint32_t flags;       /* reserved, 0 */
+  uint32_t reserved;
+} lwse_config;
+
+typedef struct lwse_engine lwse_engine;
+
+/* ------------------------------------------------------------------------- */
+/* Lifecycle                                                                 */
+/* ------------------------------------------------------------------------- */
+LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out);
+LWSE_API void lwse_destroy(lwse_engine* e);
+LWSE_API const char* lwse_strerror(int status);
+LWSE_API int lwse_last_cuda_error(const lwse_engine* e);
+LWSE_API uint32_t lwse_abi_version(void);
+/* The CUDA stream (cudaStream_t) all of this engine's work is issued on. */
+LWSE_API void* lwse_stream(const lwse_engine* e);
+/* Number of kernels this engine has launched since creation. */
+LWSE_API uint64_t lwse_launch_count(const lwse_engine* e);
+
+/* Shard an object onto one of n engines (Go: hash(LWS.UID) mod nGPU; DS-owned
+ * LWS pass the DS uid hash so a DS and its children co-reside). */
+LWSE_API uint32_t lwse_shard_of(uint64_t uid_hash, uint32_t n_shards);
+/* The 64-bit string hash the encoders use for revision keys / label values /
+ * UIDs (FNV-1a 64; 32-bit fields take the low word xor the high word). */
+LWSE_API uint64_t lwse_hash64(const void* bytes, size_t len);
+
+/* ------------------------------------------------------------------------- */
+/* Node table                                                                */
+/* ------------------------------------------------------------------------- */
+/* Copies n node rows to the device; they stay resident across sweeps. */
+LWSE_API int lwse_upload_nodes(lwse_engine* e, const lwse_node_rec* nodes, uint32_t n_nodes,
+                               uint32_t n_domains);
+
+/* ------------------------------------------------------------------------- */
+/* LWS sweep                                                                 */
+/* ------------------------------------------------------------------------- */
+/* Host buffers in, host buffers out: H2D of the three tables, the sweep
+ * kernels, D2H of the two result tables, then a stream synchronize. */
+LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* host_tables);
+/* All pointers are device pointers on the engine's device; kernels are
+ * enqueued on `stream` (cudaStream_t; NULL = the engine's stream) and the call
+ * returns without synchronizing. */
+LWSE_API int lwse_sweep_lws_device(lwse_engine* e, const lwse_lws_tables* dev_tables, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Placement (build-defined spec — the reference has no node scoring)        */
+/* ------------------------------------------------------------------------- */
+
+/* One placement request per pod group of an exclusive-topology object (32 B). */
+typedef struct lwse_place_req {
+  uint64_t priority;    /* total order: smaller wins (uid_hash-derived)          */
+  uint64_t group_key;   /* first 8 bytes of the SHA-1 group key: preference salt */
+  uint32_t group;       /* caller's group id, echoed back                        */
+  uint32_t ns;          /* dense namespace id: exclusivity is per namespace      */
+  int32_t size;         /* pods that must fit in the domain                      */
+  uint32_t leader_node; /* node row if the leader is scheduled, else LWSE_NONE   */
+} lwse_place_req;
+
+typedef struct lwse_place_out {
+  uint32_t domain_id;   /* claimed domain or LWSE_NONE                           */
+  uint32_t leader_node; /* chosen (or given) node for the leader, or LWSE_NONE   */
+  uint32_t flags;       /* LWSE_PLACE_* */
+  uint32_t score;       /* score of the winning (group, node) pair               */
+} lwse_place_out;
+
+#define LWSE_PLACE_PLACED (1u << 0)
+#define LWSE_PLACE_PINNED (1u << 1)        /* domain came from a scheduled leader */
+#define LWSE_PLACE_CONFLICT (1u << 2)      /* pinned domain already held by a
+                                              higher-priority group              */
+#define LWSE_PLACE_UNSCHEDULABLE (1u << 3) /* no feasible domain left            */
+
+/* occupancy: pods per node (n_nodes counters, host memory) already summed over
+ * every shard; NULL = all zero. */
+LWSE_API int lwse_place_host(lwse_engine* e, const lwse_place_req* reqs, uint32_t n_reqs,
+                             const uint32_t* occupancy, uint32_t n_namespaces,
+                             lwse_place_out* out, uint32_t* rounds_out);
+LWSE_API int lwse_place_device(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
+                               const uint32_t* d_occupancy, uint32_t n_namespaces,
+                               lwse_place_out* d_out, uint32_t* rounds_out, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* DisaggregatedSet sweep                                                    */
+/* ------------------------------------------------------------------------- */
+#define LWSE_DS_MAX_ROLES 10u /* api/disaggregatedset/v1: 2..10 roles             */
+
+/* One DisaggregatedSet (32 B). */
+typedef struct lwse_ds_rec {
+  uint64_t uid_hash;
+  uint32_t role_base;  /* first row in the role table                            */
+  uint32_t n_roles;    /* spec roles first, then removed roles (executor.go:140) */
+  uint32_t n_spec_roles;
+  uint32_t rev_base;   /* first row in the revision-role table                   */
+  uint32_t n_old_revs; /* old revisions, each n_roles consecutive rows; the new
+                          revision's n_roles rows follow them                    */
+  uint32_t flags;      /* LWSE_DS_* */
+} lwse_ds_rec;
+
+#define LWSE_DS_HAS_NEW_REVISION (1u << 0) /* GetRevisionRolesList newRevision != nil */
+
+/* One role of a DS (16 B). */
+typedef struct lwse_ds_role_rec {
+  int32_t target_replicas; /* getTargetReplicas (nil → 1)                        */
+  int32_t max_surge;
+  int32_t max_unavailable;
+  uint32_t flags;          /* LWSE_ROLE_* */
+} lwse_ds_role_rec;
+
+#define LWSE_ROLE_SURGE_IS_PERCENT (1u << 0)
+#define LWSE_ROLE_UNAVAIL_IS_PERCENT (1u << 1)
+#define LWSE_ROLE_HAS_ROLLING_CONFIG (1u << 2) /* rollingUpdateConfiguration != nil */
+#define LWSE_ROLE_IN_SPEC (1u << 3)
+#define LWSE_ROLE_SURGE_INVALID (1u << 4)   /* intstr error (ignored → 0, executor.go:249) */
+#define LWSE_ROLE_UNAVAIL_INVALID (1u << 5)
+
+/* One (revision, role) LWS child of a DS (16 B). */
+typedef struct lwse_ds_revrole_rec {
+  int32_t replicas;         /* getLWSReplicas (nil → 1)                           */
+  int32_t initial_replicas; /* initial-replicas annotation, or -1 when absent/unparsable */
+  int32_t ready_replicas;   /* status.readyReplicas                               */
+  uint32_t flags;           /* LWSE_RR_* */
+} lwse_ds_revrole_rec;
+
+#define LWSE_RR_EXISTS (1u << 0)
+
+/* Per DS (16 B). */
+typedef struct lwse_ds_out {
+  uint32_t flags;      /* LWSE_DOUT_* */
+  uint32_t drained_revs; /* bit r set: old revision r has every role at 0 → delete */
+  uint32_t reserved[2];
+} lwse_ds_out;
+
+#define LWSE_DOUT_ROLLING (1u << 0)      /* some old revision still has replicas  */
+#define LWSE_DOUT_STABLE (1u << 1)       /* isRevisionStable(newRevision)         */
+#define LWSE_DOUT_STEP (1u << 2)         /* ComputeNextStep returned a step       */
+#define LWSE_DOUT_COMPLETE (1u << 3)     /* planner returned nil                  */
+#define LWSE_DOUT_INIT (1u << 4)         /* no new revision yet → initRollingUpdate */
+#define LWSE_DOUT_NEW_READY (1u << 5)    /* service_manager readiness of the new revision */
+
+/* Per role (8 B): the planner step. */
+typedef struct lwse_ds_role_out {
+  int32_t next_old; /* UpdateStep.Past[i] */
+  int32_t next_new; /* UpdateStep.New[i]  */
+} lwse_ds_role_out;
+
+/* Per (revision, role): replicas after scaleUpNew / scaleDownOld (4 B). */
+typedef int32_t lwse_ds_revrole_out;
+
+typedef struct lwse_ds_tables {
+  const lwse_ds_rec* ds;
+  uint32_t n_ds;
+  const lwse_ds_role_rec* roles;
+  uint32_t n_roles;
+  const lwse_ds_revrole_rec* revroles;
+  uint32_t n_revroles;
+  lwse_ds_out* ds_out;              /* n_ds       */
+  lwse_ds_role_out* role_out;       /* n_roles    */
+  lwse_ds_revrole_out* revrole_out; /* n_revroles */
+} lwse_ds_tables;
+
+LWSE_API int lwse_sweep_ds_host(lwse_engine* e, const lwse_ds_tables* host_tables);
+LWSE_API int lwse_sweep_ds_device(lwse_engine* e, const lwse_ds_tables* dev_tables, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Group / subgroup keys (SHA-1) and subgroup indices                        */
+/* ------------------------------------------------------------------------- */
+/* keys: n strings, string i = bytes[offsets[i] .. offsets[i+1]) (the caller
+ * formats "<ns>/<podName>" or "<leaderName>/<subIdx>"); digests: n x 20 bytes. */
+LWSE_API int lwse_group_keys_host(lwse_engine* e, const uint8_t* bytes, const uint32_t* offsets,
+                                  uint32_t n, uint8_t* digests);
+LWSE_API int lwse_group_keys_device(lwse_engine* e, const uint8_t* d_bytes,
+                                    const uint32_t* d_offsets, uint32_t n, uint8_t* d_digests,
+                                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LWSE_H_ */

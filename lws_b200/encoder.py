@@ -1,0 +1,334 @@
+"""Objects → fixed-width records (the host side of the boundary).
+
+The encoder performs the string / label / lookup work that the reference does
+with informer-cache ``List``/``Get`` calls and leaves every comparison and
+count that decides an output to the device:
+
+* label-selector lists + ``SortByIndex`` (pkg/utils/utils.go:53-71) become the
+  row order of the group table (row r of an object = group index r);
+* names are reduced to the *NAME_MATCH* flags the reference checks at
+  pkg/controllers/leaderworkerset_controller.go:609-612;
+* revision keys, UIDs and topology label values become hashes (compared for
+  equality on the device);
+* ``GetParentNameAndOrdinal`` (pkg/utils/statefulset/statefulset_utils.go:27-45)
+  is evaluated here (it is a regex over a string) and reduced to ``NAME_OK``.
+
+Objects the fixed-width form cannot express exactly (two leader pods with the
+same group index, a worker whose name does not derive from its group's leader,
+a leader pod whose name is not ``<lws>-<index>`` …) get ``LWS_IRREGULAR`` so
+that the caller reconciles them through the stock path; see DESIGN.md.
+"""
+from __future__ import annotations
+
+import re
+from dataclasses import dataclass, field
+from typing import Iterable, Optional
+
+import numpy as np
+
+from . import api
+from . import records as R
+
+_STATEFUL_POD_RE = re.compile(r"(.*)-([0-9]+)$", re.S)
+
+
+def get_parent_name_and_ordinal(name: str) -> tuple[str, int]:
+    """pkg/utils/statefulset/statefulset_utils.go:33-45."""
+    m = _STATEFUL_POD_RE.match(name)
+    if not m:
+        return "", -1
+    parent, digits = m.group(1), m.group(2)
+    try:
+        v = int(digits)
+    except ValueError:  # pragma: no cover
+        return parent, -1
+    if v > 0x7FFFFFFF:  # strconv.ParseInt(..., 10, 32) overflows → err → ordinal stays -1
+        return parent, -1
+    return parent, v
+
+
+def atoi(s: Optional[str]) -> Optional[int]:
+    """strconv.Atoi: optional sign, decimal digits only; None on error."""
+    if s is None or not re.fullmatch(r"[+-]?[0-9]+", s):
+        return None
+    v = int(s)
+    if not -(1 << 63) <= v < (1 << 63):
+        return None
+    return v
+
+
+def parse_int_or_percent(v: api.IntOrString) -> tuple[int, bool, bool]:
+    """→ (value, is_percent, valid), as intstr.GetScaledValueFromIntOrPercent parses."""
+    if isinstance(v, int):
+        return v, False, True
+    if isinstance(v, str) and v.endswith("%"):
+        n = atoi(v[:-1])
+        if n is not None:
+            return n, True, True
+    return 0, False, False
+
+
+@dataclass
+class LwsItem:
+    """Everything ``Reconcile`` looks at for one LeaderWorkerSet."""
+
+    lws: api.LeaderWorkerSet
+    revision_key: str  # revisionutils.GetRevisionKey(updatedRevision)
+    lws_updated: bool = False  # leaderWorkerSetUpdated
+    leader_sts: Optional[api.StatefulSet] = None
+    existing_revisions: Optional[set] = None  # ControllerRevision keys; None = all exist
+
+
+@dataclass
+class Cluster:
+    """The slice of the informer cache the path reads."""
+
+    pods: list = field(default_factory=list)
+    statefulsets: list = field(default_factory=list)
+    nodes: list = field(default_factory=list)
+
+
+@dataclass
+class LwsTables:
+    lws: np.ndarray
+    groups: np.ndarray
+    pods: np.ndarray
+    nodes: np.ndarray
+    n_domains: int
+    domain_values: list  # domain id → topology label value
+    node_names: list
+    # bookkeeping for reading results back by name
+    lws_names: list
+    group_pod_names: list  # per group row: names of its pod rows
+
+
+def encode_nodes(nodes: Iterable[api.Node], topology_key: Optional[str]):
+    nodes = list(nodes)
+    rec = R.aligned_empty(len(nodes), R.NODE_REC)
+    domains: dict[str, int] = {}
+    for i, n in enumerate(nodes):
+        flags = R.NODE_SCHEDULABLE if n.schedulable else 0
+        dom = R.NONE
+        h = 0
+        if topology_key is not None and topology_key in n.labels:
+            val = n.labels[topology_key]
+            flags |= R.NODE_HAS_TOPOLOGY
+            dom = domains.setdefault(val, len(domains))
+            h = R.hash64(val)
+        rec[i] = (h, dom, min(n.capacity, 0xFFFF), flags)
+    values = [None] * len(domains)
+    for v, d in domains.items():
+        values[d] = v
+    return rec, values, {n.name: i for i, n in enumerate(nodes)}
+
+
+def encode_lws(items: Iterable[LwsItem], cluster: Cluster, topology_key: Optional[str] = None) -> LwsTables:
+    items = list(items)
+    node_rec, domain_values, node_index = encode_nodes(cluster.nodes, topology_key)
+
+    pods_by_ns_set: dict[tuple, list] = {}
+    for p in cluster.pods:
+        key = (p.namespace, p.labels.get(api.SetNameLabelKey))
+        pods_by_ns_set.setdefault(key, []).append(p)
+    sts_by_ns_set: dict[tuple, list] = {}
+    sts_by_name: dict[tuple, api.StatefulSet] = {}
+    for s in cluster.statefulsets:
+        sts_by_ns_set.setdefault((s.namespace, s.labels.get(api.SetNameLabelKey)), []).append(s)
+        sts_by_name[(s.namespace, s.name)] = s
+
+    lws_rows, group_rows, pod_rows = [], [], []
+    group_pod_names: list = []
+
+    for li, it in enumerate(items):
+        lws = it.lws
+        irregular = False
+        flags = 0
+        surge, surge_pct, surge_ok = parse_int_or_percent(lws.rollingUpdate.maxSurge)
+        unav, unav_pct, unav_ok = parse_int_or_percent(lws.rollingUpdate.maxUnavailable)
+        if surge_pct:
+            flags |= R.LWS_SURGE_IS_PERCENT
+        if unav_pct:
+            flags |= R.LWS_UNAVAIL_IS_PERCENT
+        if not (surge_ok and unav_ok):
+            flags |= R.LWS_INTSTR_INVALID
+        sts = it.leader_sts
+        sts_replicas = sts_partition = annot = 0
+        if sts is not None:
+            flags |= R.LWS_STS_EXISTS
+            sts_replicas, sts_partition = sts.replicas, sts.partition
+            a = atoi(sts.annotations.get(api.ReplicasAnnotationKey, ""))
+            if a is not None:
+                flags |= R.LWS_ANNOT_VALID
+                annot = a
+        if it.lws_updated:
+            flags |= R.LWS_UPDATED
+        policy = {
+            api.RecreateGroupOnPodRestart: R.RESTART_ON_POD_RESTART,
+            api.RecreateGroupAfterStart: R.RESTART_AFTER_START,
+        }.get(lws.restartPolicy, R.RESTART_NONE)
+        flags |= policy << R.LWS_RESTART_SHIFT
+        if api.RecreateGroupAfterStartAnnotationKey in lws.annotations:
+            flags |= R.LWS_RECREATE_AFTER_START_ANNOT
+        if lws.startupPolicy == api.LeaderReadyStartupPolicy:
+            flags |= R.LWS_STARTUP_LEADER_READY
+        if api.ExclusiveKeyAnnotationKey in lws.annotations:
+            flags |= R.LWS_EXCLUSIVE_TOPOLOGY
+            if lws.annotations[api.ExclusiveKeyAnnotationKey] != topology_key:
+                irregular = True  # one topology key per node table
+        if lws.subGroupPolicyType == api.SubGroupPolicyTypeLeaderExcluded:
+            flags |= R.LWS_SUBGROUP_LEADER_EXCLUDED
+
+        all_pods = pods_by_ns_set.get((lws.namespace, lws.name), [])
+        all_sts = sts_by_ns_set.get((lws.namespace, lws.name), [])
+
+        # List(leader pods) + SortByIndex (leaderworkerset_controller.go:584-593)
+        leader_by_idx: dict[int, api.Pod] = {}
+        for p in all_pods:
+            if p.labels.get(api.WorkerIndexLabelKey) != "0":
+                continue
+            idx = atoi(p.labels.get(api.GroupIndexLabelKey, ""))
+            if idx is None:
+                flags |= R.LWS_GROUP_LABEL_INVALID  # :434-437 (SortByIndex merely drops it)
+                continue
+            if idx < 0:
+                irregular = True
+                continue
+            if idx in leader_by_idx:
+                irregular = True  # two leader pods, one slot
+            leader_by_idx[idx] = p  # last writer wins (utils.go:68)
+        # List(sts) + SortByIndex (:595-603); the leader sts has no group-index label
+        sts_by_idx: dict[int, api.StatefulSet] = {}
+        for s in all_sts:
+            idx = atoi(s.labels.get(api.GroupIndexLabelKey, ""))
+            if idx is None or idx < 0:
+                continue
+            sts_by_idx[idx] = s
+        # pods per group (pod_controller.go:338-349 selects by the label *string*)
+        pods_by_idx: dict[int, list] = {}
+        for p in all_pods:
+            gi = p.labels.get(api.GroupIndexLabelKey)
+            idx = atoi(gi if gi is not None else "")
+            if idx is None or idx < 0 or str(idx) != gi:
+                if gi is not None:
+                    irregular = True
+                continue
+            pods_by_idx.setdefault(idx, []).append(p)
+
+        n_groups = 1 + max([-1, *leader_by_idx, *sts_by_idx, *pods_by_idx])
+        group_base = len(group_rows)
+        for idx in range(n_groups):
+            nominated = f"{lws.name}-{idx}"
+            gflags = 0
+            pod = leader_by_idx.get(idx)
+            leader_rev = wsts_rev = 0
+            leader_uid = wsts_uid = wsts_owner_uid = 0
+            wsts_spec = wsts_avail = 0
+            leader_node = R.NONE
+            wsts = None
+            if pod is not None:
+                gflags |= R.GRP_POD_PRESENT
+                if pod.name == nominated:
+                    gflags |= R.GRP_POD_NAME_MATCH
+                else:
+                    irregular = True
+                if pod.phase == "Running":
+                    gflags |= R.GRP_POD_RUNNING
+                if pod.readyCondition:
+                    gflags |= R.GRP_POD_READY
+                if pod.deletionTimestamp:
+                    gflags |= R.GRP_POD_DELETING
+                if pod.annotations.get(api.LeaderPodNameAnnotationKey, "") != "":
+                    gflags |= R.GRP_MISTAKEN_ANNOTATION
+                leader_rev = R.hash64(pod.labels.get(api.RevisionKey, ""))
+                leader_uid = R.hash32(pod.uid)
+                if it.existing_revisions is None or pod.labels.get(api.RevisionKey, "") in it.existing_revisions:
+                    gflags |= R.GRP_REVISION_EXISTS
+                if pod.nodeName != "":
+                    leader_node = node_index.get(pod.nodeName, R.NODE_NOT_FOUND)
+                wsts = sts_by_name.get((lws.namespace, pod.name))
+            label_sts = sts_by_idx.get(idx)
+            if label_sts is not None and label_sts.name == nominated:
+                gflags |= R.GRP_WSTS_LABEL_NAME_MATCH
+            if wsts is not None:
+                gflags |= R.GRP_WSTS_FOUND
+                wsts_rev = R.hash64(wsts.labels.get(api.RevisionKey, ""))
+                wsts_uid = R.hash32(wsts.uid)
+                wsts_spec, wsts_avail = wsts.replicas, wsts.availableReplicas
+                if wsts.currentRevision == wsts.updateRevision:
+                    gflags |= R.GRP_WSTS_REV_SETTLED
+                owner = api.controller_of(wsts)
+                if owner is not None and owner.kind == "Pod":
+                    gflags |= R.GRP_WSTS_OWNER_IS_POD
+                    wsts_owner_uid = R.hash32(owner.uid)
+                    if pod is not None and owner.name == pod.name:
+                        gflags |= R.GRP_WSTS_OWNER_NAME_MATCH
+
+            gpods = pods_by_idx.get(idx, [])
+            pod_base = len(pod_rows)
+            names = []
+            for p in gpods:
+                bits = {"Pending": R.POD_PHASE_PENDING, "Running": R.POD_PHASE_RUNNING}.get(p.phase, 0)
+                if any(c > 0 for c in p.initContainerRestartCounts) or any(
+                    c > 0 for c in p.containerRestartCounts
+                ):
+                    bits |= R.POD_ANY_RESTART
+                if p.deletionTimestamp:
+                    bits |= R.POD_DELETING
+                owner = api.controller_of(p)
+                owner_uid = 0
+                if owner is not None:
+                    kind = {"Pod": R.POD_OWNER_POD, "StatefulSet": R.POD_OWNER_STS}.get(
+                        owner.kind, R.POD_OWNER_OTHER
+                    )
+                    bits |= kind << R.POD_OWNER_SHIFT
+                    owner_uid = R.hash32(owner.uid)
+                    if owner.name == nominated:
+                        bits |= R.POD_OWNER_NAME_MATCH
+                    elif kind == R.POD_OWNER_STS:
+                        irregular = True  # would Get() a foreign StatefulSet
+                if p.labels.get(api.WorkerIndexLabelKey) == "0":
+                    bits |= R.POD_IS_LEADER
+                    bits |= R.POD_NAME_OK
+                else:
+                    parent, ordinal = get_parent_name_and_ordinal(p.name)
+                    if ordinal != -1:
+                        bits |= R.POD_NAME_OK
+                        if parent != nominated:
+                            irregular = True  # leader lookup would hit another group
+                if p.nodeName != "" and p.nodeName in node_index:
+                    ni = node_index[p.nodeName]
+                    if ni <= R.POD_NODE_MAX:
+                        bits |= R.POD_SCHEDULED | (ni << R.POD_NODE_SHIFT)
+                pod_rows.append((R.hash64(p.labels.get(api.RevisionKey, "")), owner_uid, bits))
+                names.append(p.name)
+            group_pod_names.append(names)
+            group_rows.append(
+                (leader_rev, wsts_rev, wsts_spec, wsts_avail, leader_uid, wsts_uid, wsts_owner_uid,
+                 leader_node, pod_base, len(gpods), li, gflags, (0, 0))
+            )
+
+        if irregular:
+            flags |= R.LWS_IRREGULAR
+        lws_rows.append(
+            (R.hash64(lws.uid), R.hash64(it.revision_key), lws.replicas, lws.size,
+             lws.rollingUpdate.partition, surge, unav, flags, sts_replicas, sts_partition, annot,
+             lws.subGroupSize or 0, group_base, n_groups)
+        )
+
+    def table(rows, dtype):
+        t = R.aligned_empty(len(rows), dtype)
+        for i, r in enumerate(rows):
+            t[i] = r
+        return t
+
+    return LwsTables(
+        lws=table(lws_rows, R.LWS_REC),
+        groups=table(group_rows, R.GROUP_REC),
+        pods=table(pod_rows, R.POD_REC),
+        nodes=node_rec,
+        n_domains=len(domain_values),
+        domain_values=domain_values,
+        node_names=[n.name for n in cluster.nodes],
+        lws_names=[it.lws.name for it in items],
+        group_pod_names=group_pod_names,
+    )

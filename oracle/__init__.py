@@ -1,0 +1,90 @@
+"""ctypes loader for the CPU oracle (``oracle/lwse_oracle*.c`` → ``liblwso.so``).
+
+TEST INFRASTRUCTURE ONLY — see the header of ``lwse_oracle.c``.  Only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs
+of ``bench.py`` import this package.  Nothing under ``lws_b200/`` does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from lws_b200 import records as R
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_DIR, "liblwso.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement with gcc (seconds)."""
+    srcs = [os.path.join(_DIR, f) for f in os.listdir(_DIR) if f.endswith(".c")]
+    deps = srcs + [os.path.join(_DIR, "..", "include", "lwse.h"), os.path.join(_DIR, "Makefile")]
+    if (
+        force
+        or not os.path.exists(_LIB_PATH)
+        or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(d) for d in deps)
+    ):
+        subprocess.run(["make", "-C", _DIR, "-B", "all"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.lwso_sweep_lws.argtypes = [C.POINTER(R.LwsTables), C.c_void_p, C.c_uint32, C.c_int]
+        _lib.lwso_sweep_lws.restype = C.c_int
+        _lib.lwso_calculate_rolling_update_replicas.argtypes = [C.c_int32] * 4
+        _lib.lwso_calculate_rolling_update_replicas.restype = C.c_int32
+        _lib.lwso_scaled_value.argtypes = [C.c_int32, C.c_int, C.c_int, C.c_int]
+        _lib.lwso_scaled_value.restype = C.c_int
+        _lib.lwso_sub_group_index.argtypes = [C.c_int] * 3
+        _lib.lwso_sub_group_index.restype = C.c_int
+        for name, args, res in _OPTIONAL:
+            if hasattr(_lib, name):
+                fn = getattr(_lib, name)
+                fn.argtypes, fn.restype = args, res
+    return _lib
+
+
+_OPTIONAL = [
+    (
+        "lwso_place",
+        [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p],
+        C.c_int,
+    ),
+    ("lwso_sweep_ds", [C.POINTER(R.DsTables)], C.c_int),
+    ("lwso_sha1", [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p], C.c_int),
+    (
+        "lwso_ds_compute_next_step",
+        [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+        C.c_int,
+    ),
+    (
+        "lwso_ds_scale_down_old",
+        [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+        C.c_int,
+    ),
+]
+
+
+def sweep_lws(lws, groups, pods, nodes=None, flags=0, want_occupancy=False, threads=1):
+    """Run the restatement over record tables → (lws_out, group_out, occupancy|None)."""
+    n_nodes = 0 if nodes is None else len(nodes)
+    lws_out = R.aligned_empty(len(lws), R.LWS_OUT)
+    group_out = R.aligned_empty(len(groups), R.GROUP_OUT)
+    occ = np.zeros(max(n_nodes, 1), dtype=np.uint32) if want_occupancy else None
+    t = R.LwsTables(
+        R.ptr(lws), len(lws), R.ptr(groups), len(groups), R.ptr(pods), len(pods),
+        R.ptr(lws_out), R.ptr(group_out), R.ptr(occ), flags,
+    )
+    rc = lib().lwso_sweep_lws(C.byref(t), R.ptr(nodes) if n_nodes else None, n_nodes, threads)
+    if rc != 0:
+        raise RuntimeError(f"lwso_sweep_lws failed: {rc}")
+    return lws_out, group_out, (occ[:n_nodes] if occ is not None else None)

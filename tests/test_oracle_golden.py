@@ -1,0 +1,67 @@
+"""Pins the CPU oracle (oracle/lwse_oracle.c) to the reference's own test vectors.
+
+Sources (paths relative to the reference root):
+  pkg/controllers/leaderworkerset_controller_test.go:818-885, :887-1011
+  test/integration/controllers/leaderworkerset_test.go (traces, see traces.py)
+"""
+import pytest
+
+import oracle
+from lws_b200 import api, encoder
+from lws_b200 import records as R
+from sim import LwsSim
+from traces import TRACES, make_lws
+
+
+# pkg/controllers/leaderworkerset_controller_test.go:818-885
+@pytest.mark.parametrize(
+    "lws_replicas,max_surge,max_unavailable,unready,want",
+    [(1, 1, 0, 1, 2), (4, 2, 1, 2, 5), (2, 2, 1, 2, 3), (1, 1, 0, 0, 1), (1, 1, 1, 1, 1), (3, 0, 0, 1, 3)],
+)
+def test_calculate_rolling_update_replicas(lws_replicas, max_surge, max_unavailable, unready, want):
+    got = oracle.lib().lwso_calculate_rolling_update_replicas(lws_replicas, max_surge, max_unavailable, unready)
+    assert got == want
+
+
+# pkg/controllers/leaderworkerset_controller_test.go:887-1011
+@pytest.mark.parametrize(
+    "replicas,mu,ms,updated,want",
+    [(3, 0, 1, False, (0, 3)), (3, 0, 1, True, (2, 3)), (2, 1, 2, True, (2, 3))],
+)
+def test_rolling_update_parameters_kats(oracle_sweep, replicas, mu, ms, updated, want):
+    lws = api.LeaderWorkerSet(
+        name="test-sample", replicas=replicas, size=1,
+        rollingUpdate=api.RollingUpdateConfiguration(partition=0, maxUnavailable=mu, maxSurge=ms),
+    )
+    sts = api.StatefulSet(name=lws.name, replicas=2, partition=0, annotations={api.ReplicasAnnotationKey: "2"})
+    item = encoder.LwsItem(lws=lws, revision_key="rev-new", lws_updated=updated, leader_sts=sts)
+    t = encoder.encode_lws([item], encoder.Cluster())
+    lws_out, _ = oracle_sweep(t)
+    assert not lws_out[0]["flags"] & R.LOUT_RUP_ERROR
+    assert (lws_out[0]["sts_partition"], lws_out[0]["sts_replicas"]) == want
+
+
+# k8s.io/apimachinery intstr.GetScaledValueFromIntOrPercent, pinned by
+# pkg/controllers/disaggregatedset/executor_test.go:685-760 and
+# pkg/controllers/leaderworkerset_controller_test.go:672-740
+@pytest.mark.parametrize(
+    "val,pct,total,up,want",
+    [(50, 1, 4, 1, 2), (25, 1, 4, 1, 1), (25, 1, 10, 1, 3), (25, 1, 10, 0, 2), (100, 1, 5, 1, 5),
+     (50, 1, 2, 0, 1), (3, 0, 10, 1, 3), (10, 1, 16, 1, 2), (10, 1, 16, 0, 1)],
+)
+def test_scaled_value(val, pct, total, up, want):
+    assert oracle.lib().lwso_scaled_value(val, pct, total, up) == want
+
+
+@pytest.mark.parametrize("name", sorted(TRACES))
+def test_integration_trace(oracle_sweep, name):
+    cfg, steps = TRACES[name]
+    sim = LwsSim(make_lws(cfg), oracle_sweep)
+    sim.settle()
+    sim.create_leader_pods(0, cfg["replicas"])
+    for i, (action, want) in enumerate(steps):
+        action(sim)
+        got = sim.state() + (sim.status["condition"],)
+        for k, (g, w) in enumerate(zip(got, want)):
+            if w is not None:
+                assert g == w, f"{name} step {i}: field {k} got {got} want {want}"
