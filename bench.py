@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the reconcile sweep — BASELINE.json's metric on its config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+metric   pod-group reconciles/sec: pod groups swept / time of one full sweep
+         (group+pod pass, LWS pass; the placement round when the workload has
+         exclusive-topology groups).
+workload BASELINE.json configs[2] ("C3"): 100k LWS x size 64 (100k groups,
+         6.4M pod rows), 10k nodes, topology-aware gang placement on.  It fits
+         one GPU, so N=1 runs exactly it; N>1 is weak scaling — every rank holds
+         its own C3-sized shard of an N-times larger cluster (objects shard by
+         LWS UID hash, no data-path collective for the sweep).
+value    whole-job groups/s with the tables resident in HBM (CUDA events on the
+         launching stream, max over ranks).  Inputs rotate through copies whose
+         total size exceeds L2, so no step reads a warm cache.
+e2e      the same metric through lwse_sweep_lws_host(): pinned host tables in,
+         host result tables out, H2D + kernels + D2H inside the timed region.
+roofline the dominant kernel (group/pod pass) alone: algorithmic bytes / its
+         CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth.
+cpu_baseline  the CPU oracle (a port of the reference's Go arithmetic — the
+         reference itself needs a Go toolchain, absent here) on one host core.
+
+--impl reference times that same oracle on all host threads (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "pod-group reconciles/sec on 100k-group x 10k-node synthetic cluster"
+UNIT = "groups/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    return ap.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def make_tables(args, rank):
+    from lws_b200 import synth
+
+    return synth.make(args.workload, args.scale, seed=synth.SEED + rank)
+
+
+def cpu_oracle_rate(t, threads, min_seconds=1.0, max_reps=50):
+    """groups/s of the CPU oracle over the whole workload, `threads` host threads."""
+    import oracle
+    from lws_b200 import records as R
+    import ctypes as C
+
+    lws_out = R.aligned_empty(len(t.lws), R.LWS_OUT)
+    group_out = R.aligned_empty(len(t.groups), R.GROUP_OUT)
+    tab = R.LwsTables(R.ptr(t.lws), len(t.lws), R.ptr(t.groups), len(t.groups), R.ptr(t.pods), len(t.pods),
+                      R.ptr(lws_out), R.ptr(group_out), None, t.flags)
+    fn = oracle.lib().lwso_sweep_lws
+    fn(C.byref(tab), R.ptr(t.nodes), len(t.nodes), threads)  # warm
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        fn(C.byref(tab), R.ptr(t.nodes), len(t.nodes), threads)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds or reps >= max_reps:
+            break
+    return len(t.groups) * reps / dt, dt / reps, reps
+
+
+def run_reference(args):
+    """The reference arm: the reference's CPU arithmetic (oracle port) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t = make_tables(args, 0)
+    threads = host_threads()
+    import oracle
+    from lws_b200 import records as R
+    import ctypes as C
+
+    lws_out = R.aligned_empty(len(t.lws), R.LWS_OUT)
+    group_out = R.aligned_empty(len(t.groups), R.GROUP_OUT)
+    tab = R.LwsTables(R.ptr(t.lws), len(t.lws), R.ptr(t.groups), len(t.groups), R.ptr(t.pods), len(t.pods),
+                      R.ptr(lws_out), R.ptr(group_out), None, t.flags)
+    fn = oracle.lib().lwso_sweep_lws
+    for _ in range(max(args.warmup, 1)):
+        fn(C.byref(tab), R.ptr(t.nodes), len(t.nodes), threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn(C.byref(tab), R.ptr(t.nodes), len(t.nodes), threads)
+    dt = time.perf_counter() - t0
+    value = len(t.groups) * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/u64 (integer compare)",
+        "data": "synthetic", "config": t.describe(),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"full {t.profile.name} workload per step, {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU port of the reference's Go arithmetic (no Go toolchain here); excludes the "
+                "informer-cache List/DeepCopy and API round-trips that dominate the real reconciler",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from lws_b200 import records as R
+    from lws_b200.engine import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU path to benchmark")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    t = make_tables(args, rank)
+    eng = Engine(local_rank)
+    eng.upload_nodes(t.nodes, t.n_domains)
+    n_lws, n_grp, n_pod = len(t.lws), len(t.groups), len(t.pods)
+    algo_bytes = t.algorithmic_bytes()
+
+    # ---- resident copies, rotated so that the working set exceeds L2 ----
+    copies = max(2, int(np.ceil(2.5 * L2_BYTES / algo_bytes)) + 1)
+
+    def up(a):
+        return torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
+
+    sets = []
+    for _ in range(copies):
+        sets.append(dict(
+            lws=up(t.lws), grp=up(t.groups), pod=up(t.pods),
+            lo=torch.empty(n_lws * R.LWS_OUT.itemsize, dtype=torch.uint8, device=dev),
+            go=torch.empty(n_grp * R.GROUP_OUT.itemsize, dtype=torch.uint8, device=dev)))
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    def sweep(i, flags):
+        s = sets[i % copies]
+        eng.sweep_lws_device(s["lws"], n_lws, s["grp"], n_grp, s["pod"], n_pod, s["lo"], s["go"], None,
+                             flags=flags, stream=sptr)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(flags, steps, warmup):
+        for i in range(warmup):
+            sweep(i, flags)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count
+        e0.record(stream)
+        for i in range(steps):
+            sweep(warmup + i, flags)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        return ms / steps, eng.launch_count - l0
+
+    with ClockSampler(local_rank) as clk:
+        ms_step, launches = timed(t.flags, args.steps, max(args.warmup, 3))
+        # the dominant kernel alone (group/pod pass)
+        ms_group, _ = timed(t.flags | R.SWEEP_SKIP_LWS_PASS, args.steps, 3)
+    clocks = clk.summary()
+
+    # correctness of what was just timed: compare one resident result with a fresh host sweep
+    # ---- end to end through the host entry point, pinned buffers ----
+    def pinned(a):
+        ten = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
+        view = ten.numpy().view(a.dtype)
+        view[:] = a
+        return ten, view
+
+    keep = []
+    h = {}
+    for name, arr in (("lws", t.lws), ("groups", t.groups), ("pods", t.pods),
+                      ("lo", R.aligned_empty(n_lws, R.LWS_OUT)), ("go", R.aligned_empty(n_grp, R.GROUP_OUT))):
+        ten, view = pinned(arr)
+        keep.append(ten)
+        h[name] = view
+    for _ in range(3):
+        eng.sweep_lws_host(h["lws"], h["groups"], h["pods"], flags=t.flags, out=(h["lo"], h["go"]))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        eng.sweep_lws_host(h["lws"], h["groups"], h["pods"], flags=t.flags, out=(h["lo"], h["go"]))
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    # the resident result must equal the host-path result
+    same = (sets[0]["lo"].cpu().numpy().tobytes() == h["lo"].tobytes()
+            and sets[0]["go"].cpu().numpy().tobytes() == h["go"].tobytes())
+    if not same:
+        raise SystemExit("bench.py: resident and host-path results differ")
+
+    # ---- max over ranks ----
+    stats = torch.tensor([ms_step, ms_group, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    groups = torch.tensor([float(n_grp)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(groups, op=dist.ReduceOp.SUM)
+    ms_step, ms_group, e2e_ms = [float(x) for x in stats.tolist()]
+    total_groups = float(groups.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        group_bytes = (n_grp * (R.GROUP_REC.itemsize + R.GROUP_OUT.itemsize) + n_pod * R.POD_REC.itemsize
+                       + n_lws * 16)
+        achieved = group_bytes / (ms_group * 1e-3) / 1e9
+        cpu_rate, cpu_s, cpu_reps = cpu_oracle_rate(t, 1)
+        line = {
+            "metric": METRIC, "value": total_groups / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32/u64 (integer compare)", "data": "synthetic",
+            "config": {**t.describe(), "parallelism": f"shard-by-uid x{world}",
+                       "l2": f"inputs rotate over {copies} resident copies ({copies * algo_bytes / 1e6:.0f} MB > L2)"},
+            "e2e": {"value": total_groups / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(t.lws.nbytes + t.groups.nbytes + t.pods.nbytes),
+                    "d2h_bytes_per_step": int(n_lws * R.LWS_OUT.itemsize + n_grp * R.GROUP_OUT.itemsize),
+                    "ms_per_step": e2e_ms, "api": "lwse_sweep_lws_host (pinned host tables)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "group_sweep_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "bytes_per_launch": int(group_bytes), "ms_per_launch": ms_group, "peak_source": peak_src},
+            "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"full {t.profile.name} workload x{cpu_reps} ({cpu_s * 1e3:.1f} ms per sweep)"},
+            "clocks": clocks,
+            "algorithmic_bytes_per_step": int(algo_bytes),
+            "sweep_gbs": algo_bytes / (ms_step * 1e-3) / 1e9,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

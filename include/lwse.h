@@ -86,21 +86,22 @@ typedef enum lwse_status {
 #define LWSE_NONE 0xFFFFFFFFu           /* "no index" (unscheduled, no domain, …) */
 #define LWSE_NODE_NOT_FOUND 0xFFFFFFFEu /* leader.spec.nodeName set, Node object missing */
 
-/* One LeaderWorkerSet object (64 B). */
+/* One LeaderWorkerSet object (64 B).  The first 16 bytes are everything the
+ * per-group kernel needs from its owner. */
 typedef struct lwse_lws_rec {
-  uint64_t uid_hash;  /* hash of metadata.uid: shard key, placement priority     */
   uint64_t rev_hash;  /* hash of the revisionKey handed to the reconciler
                          (leaderworkerset_controller.go:159,:196)                */
-  int32_t replicas;   /* *spec.replicas                                          */
   int32_t size;       /* *spec.leaderWorkerTemplate.size                         */
+  uint32_t flags;     /* LWSE_LWS_* */
+  int32_t replicas;   /* *spec.replicas                                          */
   int32_t partition;  /* *spec.rolloutStrategy.rollingUpdateConfiguration.partition */
   int32_t max_surge;  /* IntVal, or the percent number when ..._IS_PERCENT       */
   int32_t max_unavailable;
-  uint32_t flags;     /* LWSE_LWS_* */
   int32_t sts_replicas;            /* leader sts *spec.replicas                  */
   int32_t sts_partition;           /* leader sts rollingUpdate.partition         */
   int32_t sts_replicas_annotation; /* Atoi(leaderworkerset.sigs.k8s.io/replicas) */
   int32_t subgroup_size;           /* 0 = no subGroupPolicy                      */
+  uint64_t uid_hash;  /* hash of metadata.uid: shard key, placement priority     */
   uint32_t group_base;             /* first row of this object in the group table */
   uint32_t group_count;            /* rows = group indices 0..group_count-1      */
 } lwse_lws_rec;
@@ -217,6 +218,7 @@ typedef struct lwse_lws_out {
 #define LWSE_LOUT_EVENT_SHIFT 5           /* 2 bits: lwse_surge_event              */
 #define LWSE_LOUT_EVENT_MASK (3u << 5)
 #define LWSE_LOUT_IRREGULAR (1u << 7)
+#define LWSE_LOUT_BAD_TABLE (1u << 8)     /* group_base/group_count outside the group table */
 
 typedef enum lwse_condition {
   LWSE_COND_PROGRESSING = 0,
@@ -255,6 +257,7 @@ typedef struct lwse_group_out {
 #define LWSE_GOUT_TOPOLOGY_ERROR (1u << 11)/* node lacks the topology label (:331)     */
 #define LWSE_GOUT_REQUEUE_REVISION (1u << 12) /* revision missing → requeue 1s (:152)  */
 #define LWSE_GOUT_CREATE_PODGROUP (1u << 13)  /* SchedulerProvider.CreatePodGroupIfNotExists reached */
+#define LWSE_GOUT_BAD_TABLE (1u << 14)     /* lws_index / pod_base+pod_count outside a table  */
 
 /* ------------------------------------------------------------------------- */
 /* Table bundles                                                             */
@@ -279,6 +282,9 @@ typedef struct lwse_lws_tables {
 
 #define LWSE_SWEEP_GANG (1u << 0) /* a SchedulerProvider is configured (min_member,
                                      CREATE_PODGROUP are meaningful)              */
+#define LWSE_SWEEP_SKIP_GROUP_PASS (1u << 1) /* profiling: run only the LWS-level pass
+                                                (group_out must hold a previous result) */
+#define LWSE_SWEEP_SKIP_LWS_PASS (1u << 2)   /* profiling: run only the group/pod pass   */
 
 typedef struct lwse_config {
   uint32_t abi_version; /* LWSE_ABI_VERSION */

@@ -1,0 +1,450 @@
+// C-ABI implementation of include/lwse.h: engine lifecycle, device staging,
+// host- and device-pointer entry points.  No CPU compute path exists in this
+// library: every sweep is a CUDA kernel launch or the call fails.
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <new>
+
+#include "lwse_device.cuh"
+
+namespace lwse {
+// lwse_lws_kernels.cu
+int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
+                     int sm_count, cudaStream_t s, int* cuda_err);
+// lwse_place_kernels.cu
+int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_domains,
+                 const lwse_place_req* d_reqs, uint32_t n_reqs, const uint32_t* d_occupancy,
+                 uint32_t n_namespaces, lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes,
+                 uint32_t* h_rounds, int sm_count, cudaStream_t s, int* cuda_err);
+size_t place_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces);
+// lwse_ds_kernels.cu
+int launch_ds_sweep(const lwse_ds_tables* t, int sm_count, cudaStream_t s, int* cuda_err);
+// lwse_sha1_kernels.cu
+int launch_sha1(const uint8_t* d_bytes, const uint32_t* d_offsets, uint32_t n, uint8_t* d_digests,
+                int sm_count, cudaStream_t s, int* cuda_err);
+}  // namespace lwse
+
+namespace {
+
+// A device buffer that only grows (sweeps reuse their staging memory).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct lwse_engine {
+  int device = 0;
+  int sm_count = lwse::kSmCount;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  int last_cuda_error = 0;
+  uint64_t launches = 0;
+  // resident node table
+  DevBuf nodes;
+  uint32_t n_nodes = 0, n_domains = 0;
+  // staging for the *_host entry points
+  DevBuf lws, groups, pods, lws_out, group_out, occupancy;
+  DevBuf place_reqs, place_out, place_occ, place_scratch;
+  DevBuf ds, ds_roles, ds_revroles, ds_out, ds_role_out, ds_revrole_out;
+  DevBuf sha_bytes, sha_offsets, sha_digests;
+  uint32_t* h_rounds = nullptr;  // pinned
+};
+
+namespace {
+
+int fail_cuda(lwse_engine* e, cudaError_t err) {
+  e->last_cuda_error = (int)err;
+  (void)cudaGetLastError();  // clear the sticky-free error state
+  return err == cudaErrorMemoryAllocation ? LWSE_ERR_OOM : LWSE_ERR_CUDA;
+}
+
+#define LWSE_CUDA(e, call)                                \
+  do {                                                    \
+    cudaError_t err__ = (call);                           \
+    if (err__ != cudaSuccess) return fail_cuda(e, err__); \
+  } while (0)
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int check_lws_tables(const lwse_lws_tables* t) {
+  if (!t) return LWSE_ERR_INVALID_ARG;
+  if (t->n_lws && (!t->lws || !t->lws_out)) return LWSE_ERR_INVALID_ARG;
+  if (t->n_groups && (!t->groups || !t->group_out)) return LWSE_ERR_INVALID_ARG;
+  if (t->n_pods && !t->pods) return LWSE_ERR_INVALID_ARG;
+  if (!aligned16(t->lws) || !aligned16(t->groups) || !aligned16(t->pods) || !aligned16(t->lws_out) ||
+      !aligned16(t->group_out))
+    return LWSE_ERR_INVALID_ARG;
+  return LWSE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+LWSE_API uint32_t lwse_abi_version(void) { return LWSE_ABI_VERSION; }
+
+LWSE_API const char* lwse_strerror(int status) {
+  switch (status) {
+    case LWSE_OK: return "ok";
+    case LWSE_ERR_INVALID_ARG: return "invalid argument (NULL or misaligned table, bad count)";
+    case LWSE_ERR_NO_DEVICE: return "no usable CUDA device (this engine has no CPU fallback)";
+    case LWSE_ERR_CUDA: return "CUDA call failed (see lwse_last_cuda_error)";
+    case LWSE_ERR_OOM: return "device or pinned memory allocation failed";
+    case LWSE_ERR_BAD_TABLE: return "a base/count in a record points outside its table";
+    case LWSE_ERR_NOT_READY: return "engine not ready for this call (upload the node table first)";
+    case LWSE_ERR_UNSUPPORTED: return "unsupported input";
+    default: return "unknown lwse status";
+  }
+}
+
+LWSE_API uint64_t lwse_hash64(const void* bytes, size_t len) {
+  const uint8_t* b = static_cast<const uint8_t*>(bytes);
+  uint64_t h = 0xCBF29CE484222325ull;
+  for (size_t i = 0; i < len; i++) h = (h ^ b[i]) * 0x100000001B3ull;
+  return h;
+}
+
+LWSE_API uint32_t lwse_shard_of(uint64_t uid_hash, uint32_t n_shards) {
+  if (n_shards <= 1) return 0;
+  // finalizer of splitmix64 so that weak uid hashes still spread
+  uint64_t x = uid_hash;
+  x ^= x >> 30;
+  x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27;
+  x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (uint32_t)(x % n_shards);
+}
+
+LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
+  if (!cfg || !out) return LWSE_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (cfg->abi_version != LWSE_ABI_VERSION) return LWSE_ERR_INVALID_ARG;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || cfg->device < 0 || cfg->device >= n) {
+    (void)cudaGetLastError();
+    return LWSE_ERR_NO_DEVICE;
+  }
+  lwse_engine* e = new (std::nothrow) lwse_engine();
+  if (!e) return LWSE_ERR_OOM;
+  e->device = cfg->device;
+  DeviceGuard guard(e->device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, e->device) != cudaSuccess) {
+    delete e;
+    return LWSE_ERR_NO_DEVICE;
+  }
+  if (prop.major < 10) {  // the kernels are built for sm_100a only
+    delete e;
+    return LWSE_ERR_NO_DEVICE;
+  }
+  e->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost(reinterpret_cast<void**>(&e->h_rounds), 64) != cudaSuccess) {
+    (void)cudaGetLastError();
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return LWSE_ERR_CUDA;
+  }
+  *out = e;
+  return LWSE_OK;
+}
+
+LWSE_API void lwse_destroy(lwse_engine* e) {
+  if (!e) return;
+  {
+    DeviceGuard guard(e->device);
+    cudaStreamSynchronize(e->stream);
+    DevBuf* bufs[] = {&e->nodes,      &e->lws,         &e->groups,     &e->pods,        &e->lws_out,
+                      &e->group_out,  &e->occupancy,   &e->place_reqs, &e->place_out,   &e->place_occ,
+                      &e->place_scratch, &e->ds,       &e->ds_roles,   &e->ds_revroles, &e->ds_out,
+                      &e->ds_role_out, &e->ds_revrole_out, &e->sha_bytes, &e->sha_offsets, &e->sha_digests};
+    for (DevBuf* b : bufs) b->release();
+    if (e->h_rounds) cudaFreeHost(e->h_rounds);
+    cudaStreamDestroy(e->stream);
+  }
+  delete e;
+}
+
+LWSE_API int lwse_last_cuda_error(const lwse_engine* e) { return e ? e->last_cuda_error : 0; }
+LWSE_API void* lwse_stream(const lwse_engine* e) { return e ? (void*)e->stream : nullptr; }
+LWSE_API uint64_t lwse_launch_count(const lwse_engine* e) { return e ? e->launches : 0; }
+
+LWSE_API int lwse_upload_nodes(lwse_engine* e, const lwse_node_rec* nodes, uint32_t n_nodes,
+                               uint32_t n_domains) {
+  if (!e || (n_nodes && !nodes) || !aligned16(nodes)) return LWSE_ERR_INVALID_ARG;
+  if (n_nodes > LWSE_POD_NODE_MAX) return LWSE_ERR_UNSUPPORTED;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  LWSE_CUDA(e, e->nodes.reserve((size_t)n_nodes * sizeof(lwse_node_rec) + 16));
+  if (n_nodes)
+    LWSE_CUDA(e, cudaMemcpyAsync(e->nodes.p, nodes, (size_t)n_nodes * sizeof(lwse_node_rec),
+                                 cudaMemcpyHostToDevice, e->stream));
+  LWSE_CUDA(e, cudaStreamSynchronize(e->stream));
+  e->n_nodes = n_nodes;
+  e->n_domains = n_domains;
+  return LWSE_OK;
+}
+
+// ---------------------------------------------------------------------------
+// LWS sweep
+// ---------------------------------------------------------------------------
+LWSE_API int lwse_sweep_lws_device(lwse_engine* e, const lwse_lws_tables* t, void* stream) {
+  if (!e) return LWSE_ERR_INVALID_ARG;
+  int rc = check_lws_tables(t);
+  if (rc != LWSE_OK) return rc;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  int cuda_err = 0;
+  int launched = lwse::launch_lws_sweep(t, (const lwse_node_rec*)e->nodes.p, e->n_nodes,
+                                        e->sm_count, s, &cuda_err);
+  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+  e->launches += (uint64_t)launched;
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* h) {
+  if (!e) return LWSE_ERR_INVALID_ARG;
+  int rc = check_lws_tables(h);
+  if (rc != LWSE_OK) return rc;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  cudaStream_t s = e->stream;
+  const size_t b_lws = (size_t)h->n_lws * sizeof(lwse_lws_rec);
+  const size_t b_grp = (size_t)h->n_groups * sizeof(lwse_group_rec);
+  const size_t b_pod = (size_t)h->n_pods * sizeof(lwse_pod_rec);
+  const size_t b_lo = (size_t)h->n_lws * sizeof(lwse_lws_out);
+  const size_t b_go = (size_t)h->n_groups * sizeof(lwse_group_out);
+  LWSE_CUDA(e, e->lws.reserve(b_lws + 16));
+  LWSE_CUDA(e, e->groups.reserve(b_grp + 16));
+  LWSE_CUDA(e, e->pods.reserve(b_pod + 16));
+  LWSE_CUDA(e, e->lws_out.reserve(b_lo + 16));
+  LWSE_CUDA(e, e->group_out.reserve(b_go + 16));
+  const bool want_occ = h->node_occupancy != nullptr && e->n_nodes > 0;
+  if (want_occ) {
+    LWSE_CUDA(e, e->occupancy.reserve((size_t)e->n_nodes * 4 + 16));
+    LWSE_CUDA(e, cudaMemsetAsync(e->occupancy.p, 0, (size_t)e->n_nodes * 4, s));
+  }
+  if (b_lws) LWSE_CUDA(e, cudaMemcpyAsync(e->lws.p, h->lws, b_lws, cudaMemcpyHostToDevice, s));
+  if (b_grp) LWSE_CUDA(e, cudaMemcpyAsync(e->groups.p, h->groups, b_grp, cudaMemcpyHostToDevice, s));
+  if (b_pod) LWSE_CUDA(e, cudaMemcpyAsync(e->pods.p, h->pods, b_pod, cudaMemcpyHostToDevice, s));
+
+  lwse_lws_tables d = *h;
+  d.lws = (const lwse_lws_rec*)e->lws.p;
+  d.groups = (const lwse_group_rec*)e->groups.p;
+  d.pods = (const lwse_pod_rec*)e->pods.p;
+  d.lws_out = (lwse_lws_out*)e->lws_out.p;
+  d.group_out = (lwse_group_out*)e->group_out.p;
+  d.node_occupancy = want_occ ? (uint32_t*)e->occupancy.p : nullptr;
+  int cuda_err = 0;
+  int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes, e->sm_count,
+                                        s, &cuda_err);
+  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+  e->launches += (uint64_t)launched;
+
+  if (b_lo) LWSE_CUDA(e, cudaMemcpyAsync(h->lws_out, e->lws_out.p, b_lo, cudaMemcpyDeviceToHost, s));
+  if (b_go) LWSE_CUDA(e, cudaMemcpyAsync(h->group_out, e->group_out.p, b_go, cudaMemcpyDeviceToHost, s));
+  if (want_occ)
+    LWSE_CUDA(e, cudaMemcpyAsync(h->node_occupancy, e->occupancy.p, (size_t)e->n_nodes * 4,
+                                 cudaMemcpyDeviceToHost, s));
+  LWSE_CUDA(e, cudaStreamSynchronize(s));
+  return LWSE_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Placement
+// ---------------------------------------------------------------------------
+LWSE_API int lwse_place_device(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
+                               const uint32_t* d_occupancy, uint32_t n_namespaces,
+                               lwse_place_out* d_out, uint32_t* rounds_out, void* stream) {
+  if (!e || (n_reqs && (!d_reqs || !d_out)) || n_namespaces == 0) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (e->n_nodes == 0 || e->n_domains == 0) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  const size_t scratch = lwse::place_scratch_bytes(e->n_nodes, e->n_domains, n_reqs, n_namespaces);
+  LWSE_CUDA(e, e->place_scratch.reserve(scratch));
+  int cuda_err = 0;
+  int launched = lwse::launch_place((const lwse_node_rec*)e->nodes.p, e->n_nodes, e->n_domains, d_reqs,
+                                    n_reqs, d_occupancy, n_namespaces, d_out, e->place_scratch.p,
+                                    scratch, e->h_rounds, e->sm_count, s, &cuda_err);
+  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+  e->launches += (uint64_t)launched;
+  if (rounds_out) *rounds_out = e->h_rounds[0];
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_place_host(lwse_engine* e, const lwse_place_req* reqs, uint32_t n_reqs,
+                             const uint32_t* occupancy, uint32_t n_namespaces, lwse_place_out* out,
+                             uint32_t* rounds_out) {
+  if (!e || (n_reqs && (!reqs || !out)) || n_namespaces == 0) return LWSE_ERR_INVALID_ARG;
+  uint32_t n_nodes;
+  {
+    std::lock_guard<std::mutex> lock(e->mu);
+    if (e->n_nodes == 0 || e->n_domains == 0) return LWSE_ERR_NOT_READY;
+    n_nodes = e->n_nodes;
+    DeviceGuard guard(e->device);
+    LWSE_CUDA(e, e->place_reqs.reserve((size_t)n_reqs * sizeof(lwse_place_req) + 16));
+    LWSE_CUDA(e, e->place_out.reserve((size_t)n_reqs * sizeof(lwse_place_out) + 16));
+    LWSE_CUDA(e, e->place_occ.reserve((size_t)n_nodes * 4 + 16));
+    if (n_reqs)
+      LWSE_CUDA(e, cudaMemcpyAsync(e->place_reqs.p, reqs, (size_t)n_reqs * sizeof(lwse_place_req),
+                                   cudaMemcpyHostToDevice, e->stream));
+    if (occupancy)
+      LWSE_CUDA(e, cudaMemcpyAsync(e->place_occ.p, occupancy, (size_t)n_nodes * 4,
+                                   cudaMemcpyHostToDevice, e->stream));
+    else
+      LWSE_CUDA(e, cudaMemsetAsync(e->place_occ.p, 0, (size_t)n_nodes * 4, e->stream));
+  }
+  int rc = lwse_place_device(e, (const lwse_place_req*)e->place_reqs.p, n_reqs,
+                             (const uint32_t*)e->place_occ.p, n_namespaces,
+                             (lwse_place_out*)e->place_out.p, rounds_out, nullptr);
+  if (rc != LWSE_OK) return rc;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  if (n_reqs)
+    LWSE_CUDA(e, cudaMemcpyAsync(out, e->place_out.p, (size_t)n_reqs * sizeof(lwse_place_out),
+                                 cudaMemcpyDeviceToHost, e->stream));
+  LWSE_CUDA(e, cudaStreamSynchronize(e->stream));
+  return LWSE_OK;
+}
+
+// ---------------------------------------------------------------------------
+// DisaggregatedSet sweep
+// ---------------------------------------------------------------------------
+static int check_ds_tables(const lwse_ds_tables* t) {
+  if (!t) return LWSE_ERR_INVALID_ARG;
+  if (t->n_ds && (!t->ds || !t->ds_out)) return LWSE_ERR_INVALID_ARG;
+  if (t->n_roles && (!t->roles || !t->role_out)) return LWSE_ERR_INVALID_ARG;
+  if (t->n_revroles && (!t->revroles || !t->revrole_out)) return LWSE_ERR_INVALID_ARG;
+  if (!aligned16(t->ds) || !aligned16(t->roles) || !aligned16(t->revroles)) return LWSE_ERR_INVALID_ARG;
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_sweep_ds_device(lwse_engine* e, const lwse_ds_tables* t, void* stream) {
+  if (!e) return LWSE_ERR_INVALID_ARG;
+  int rc = check_ds_tables(t);
+  if (rc != LWSE_OK) return rc;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  int cuda_err = 0;
+  int launched = lwse::launch_ds_sweep(t, e->sm_count, s, &cuda_err);
+  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+  e->launches += (uint64_t)launched;
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_sweep_ds_host(lwse_engine* e, const lwse_ds_tables* h) {
+  if (!e) return LWSE_ERR_INVALID_ARG;
+  int rc = check_ds_tables(h);
+  if (rc != LWSE_OK) return rc;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  cudaStream_t s = e->stream;
+  const size_t b_ds = (size_t)h->n_ds * sizeof(lwse_ds_rec), b_ro = (size_t)h->n_roles * sizeof(lwse_ds_role_rec),
+               b_rr = (size_t)h->n_revroles * sizeof(lwse_ds_revrole_rec);
+  const size_t o_ds = (size_t)h->n_ds * sizeof(lwse_ds_out), o_ro = (size_t)h->n_roles * sizeof(lwse_ds_role_out),
+               o_rr = (size_t)h->n_revroles * sizeof(lwse_ds_revrole_out);
+  LWSE_CUDA(e, e->ds.reserve(b_ds + 16));
+  LWSE_CUDA(e, e->ds_roles.reserve(b_ro + 16));
+  LWSE_CUDA(e, e->ds_revroles.reserve(b_rr + 16));
+  LWSE_CUDA(e, e->ds_out.reserve(o_ds + 16));
+  LWSE_CUDA(e, e->ds_role_out.reserve(o_ro + 16));
+  LWSE_CUDA(e, e->ds_revrole_out.reserve(o_rr + 16));
+  if (b_ds) LWSE_CUDA(e, cudaMemcpyAsync(e->ds.p, h->ds, b_ds, cudaMemcpyHostToDevice, s));
+  if (b_ro) LWSE_CUDA(e, cudaMemcpyAsync(e->ds_roles.p, h->roles, b_ro, cudaMemcpyHostToDevice, s));
+  if (b_rr) LWSE_CUDA(e, cudaMemcpyAsync(e->ds_revroles.p, h->revroles, b_rr, cudaMemcpyHostToDevice, s));
+  lwse_ds_tables d = *h;
+  d.ds = (const lwse_ds_rec*)e->ds.p;
+  d.roles = (const lwse_ds_role_rec*)e->ds_roles.p;
+  d.revroles = (const lwse_ds_revrole_rec*)e->ds_revroles.p;
+  d.ds_out = (lwse_ds_out*)e->ds_out.p;
+  d.role_out = (lwse_ds_role_out*)e->ds_role_out.p;
+  d.revrole_out = (lwse_ds_revrole_out*)e->ds_revrole_out.p;
+  int cuda_err = 0;
+  int launched = lwse::launch_ds_sweep(&d, e->sm_count, s, &cuda_err);
+  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+  e->launches += (uint64_t)launched;
+  if (o_ds) LWSE_CUDA(e, cudaMemcpyAsync(h->ds_out, e->ds_out.p, o_ds, cudaMemcpyDeviceToHost, s));
+  if (o_ro) LWSE_CUDA(e, cudaMemcpyAsync(h->role_out, e->ds_role_out.p, o_ro, cudaMemcpyDeviceToHost, s));
+  if (o_rr) LWSE_CUDA(e, cudaMemcpyAsync(h->revrole_out, e->ds_revrole_out.p, o_rr, cudaMemcpyDeviceToHost, s));
+  LWSE_CUDA(e, cudaStreamSynchronize(s));
+  return LWSE_OK;
+}
+
+// ---------------------------------------------------------------------------
+// SHA-1 group keys
+// ---------------------------------------------------------------------------
+LWSE_API int lwse_group_keys_device(lwse_engine* e, const uint8_t* d_bytes, const uint32_t* d_offsets,
+                                    uint32_t n, uint8_t* d_digests, void* stream) {
+  if (!e || (n && (!d_offsets || !d_digests))) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  int cuda_err = 0;
+  int launched = lwse::launch_sha1(d_bytes, d_offsets, n, d_digests, e->sm_count, s, &cuda_err);
+  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+  e->launches += (uint64_t)launched;
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_group_keys_host(lwse_engine* e, const uint8_t* bytes, const uint32_t* offsets,
+                                  uint32_t n, uint8_t* digests) {
+  if (!e || (n && (!offsets || !digests))) return LWSE_ERR_INVALID_ARG;
+  if (n == 0) return LWSE_OK;
+  const size_t total = offsets[n];
+  if (total && !bytes) return LWSE_ERR_INVALID_ARG;
+  {
+    std::lock_guard<std::mutex> lock(e->mu);
+    DeviceGuard guard(e->device);
+    LWSE_CUDA(e, e->sha_bytes.reserve(total + 64));
+    LWSE_CUDA(e, e->sha_offsets.reserve((size_t)(n + 1) * 4 + 16));
+    LWSE_CUDA(e, e->sha_digests.reserve((size_t)n * 20 + 16));
+    if (total) LWSE_CUDA(e, cudaMemcpyAsync(e->sha_bytes.p, bytes, total, cudaMemcpyHostToDevice, e->stream));
+    LWSE_CUDA(e, cudaMemcpyAsync(e->sha_offsets.p, offsets, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice,
+                                 e->stream));
+  }
+  int rc = lwse_group_keys_device(e, (const uint8_t*)e->sha_bytes.p, (const uint32_t*)e->sha_offsets.p, n,
+                                  (uint8_t*)e->sha_digests.p, nullptr);
+  if (rc != LWSE_OK) return rc;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  LWSE_CUDA(e, cudaMemcpyAsync(digests, e->sha_digests.p, (size_t)n * 20, cudaMemcpyDeviceToHost, e->stream));
+  LWSE_CUDA(e, cudaStreamSynchronize(e->stream));
+  return LWSE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,521 @@
+// LWS sweep kernels (sm_100a): one pass over the group + pod tables, then one
+// pass over the LWS table.
+//
+//   group_sweep_kernel<W>  one W-lane tile per pod group.  Streams the group's
+//                          pod rows with 128-bit loads (lane i takes pods i,
+//                          i+W, …), folds the per-pod restart predicate
+//                          (pod_controller.go:204-295,338-362) into a flag word
+//                          and reduces it across the tile with redux.sync
+//                          (__reduce_or_sync / __reduce_min_sync), then
+//                          evaluates the per-group state bits
+//                          (leaderworkerset_controller.go:608-638, :433-476)
+//                          and the leader pod's worker-sts gating
+//                          (pod_controller.go:100-198).  16 B out per group.
+//   lws_sweep_kernel<W>    one W-lane tile per LeaderWorkerSet.  Lanes stride
+//                          over the object's group_out flag words; counters via
+//                          redux.sync; rollingUpdateParameters' five cases, the
+//                          partition walk (:643-673) done as three reductions
+//                          instead of three loops.  32 B out per object.
+//
+// Both kernels are pure integer/compare work bound by HBM traffic: see
+// DESIGN.md for the algorithmic bytes and the roofline.
+#include "lwse_device.cuh"
+
+namespace lwse {
+
+struct GroupSweepArgs {
+  const lwse_lws_rec* lws;
+  const lwse_group_rec* groups;
+  const lwse_pod_rec* pods;
+  const lwse_node_rec* nodes;
+  lwse_group_out* out;
+  uint32_t* occupancy;  // nullable
+  uint64_t n_pods;
+  uint32_t n_lws;
+  uint32_t n_groups;
+  uint32_t n_nodes;
+  uint32_t sweep_flags;
+};
+
+// bits of the per-lane accumulator
+constexpr uint32_t ACC_PENDING = 1u << 0;
+constexpr uint32_t ACC_TRIG_DELETE = 1u << 1;    // trigger, leader not yet deleting → Delete()
+constexpr uint32_t ACC_TRIG_DELETING = 1u << 2;  // trigger, leader already deleting
+constexpr uint32_t ACC_ERROR = 1u << 3;          // worker name unparsable
+constexpr uint32_t ACC_LEADER_TRIG = 1u << 4;    // the leader pod's own event triggered
+
+struct GroupCtx {
+  uint32_t leader_rev_lo, leader_rev_hi;
+  uint32_t leader_uid, wsts_uid;
+  bool policy_on;     // RecreateGroupOnPodRestart | RecreateGroupAfterStart
+  bool leader_found;  // Get(leader by parsed name) succeeds (pod_controller.go:233)
+  bool wsts_chain_ok; // sts found ∧ owned by this leader (:281-294)
+  bool leader_deleting;
+};
+
+__device__ __forceinline__ void fold_pod(const uint4 p, const uint32_t idx, const GroupCtx& c,
+                                         uint32_t& acc, uint32_t& first, uint32_t* occupancy,
+                                         uint32_t n_nodes) {
+  const uint32_t bits = p.w;
+  const uint32_t phase = bits & LWSE_POD_PHASE_MASK;
+  if (phase == LWSE_POD_PHASE_PENDING) acc |= ACC_PENDING;  // pendingPodsInGroup :356
+  if (occupancy != nullptr && (bits & LWSE_POD_SCHEDULED)) {
+    const uint32_t node = bits >> LWSE_POD_NODE_SHIFT;
+    if (node < n_nodes) atomicAdd(occupancy + node, 1u);
+  }
+  // ContainerRestarted (pod_utils.go:29-45) || PodDeleted (:48)
+  const bool restarted = (phase - 1u) < 2u && (bits & LWSE_POD_ANY_RESTART);
+  const bool ev = restarted || (bits & LWSE_POD_DELETING);
+  if (ev && c.policy_on) {
+    bool cand, deleting;
+    if (bits & LWSE_POD_IS_LEADER) {
+      cand = true;  // leader = pod (:251)
+      deleting = bits & LWSE_POD_DELETING;
+    } else if (!(bits & LWSE_POD_NAME_OK)) {
+      acc |= ACC_ERROR;  // :230
+      return;
+    } else {
+      const uint32_t kind = (bits & LWSE_POD_OWNER_MASK) >> LWSE_POD_OWNER_SHIFT;
+      const bool name_match = bits & LWSE_POD_OWNER_NAME_MATCH;
+      // workerPodBelongsToLeader :268-295
+      const bool belongs = name_match && ((kind == 1u && p.z == c.leader_uid) ||
+                                          (kind == 2u && p.z == c.wsts_uid && c.wsts_chain_ok));
+      cand = c.leader_found && p.x == c.leader_rev_lo && p.y == c.leader_rev_hi && belongs;
+      deleting = c.leader_deleting;
+    }
+    if (cand) {
+      acc |= deleting ? ACC_TRIG_DELETING : ACC_TRIG_DELETE;
+      if (bits & LWSE_POD_IS_LEADER) acc |= ACC_LEADER_TRIG;
+      first = min(first, idx);
+    }
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) group_sweep_kernel(const GroupSweepArgs a) {
+  constexpr uint32_t kTilesPerBlock = 256 / W;
+  const uint32_t lane = threadIdx.x & (W - 1);
+  const uint32_t n_tiles = gridDim.x * kTilesPerBlock;
+  uint32_t g = blockIdx.x * kTilesPerBlock + threadIdx.x / W;
+  if (g >= a.n_groups) return;  // whole tiles leave together
+
+  const uint4* grows = reinterpret_cast<const uint4*>(a.groups);
+  uint4 ra = ldg_stream(grows + 4ull * g + 0), rb = ldg_stream(grows + 4ull * g + 1),
+        rc = ldg_stream(grows + 4ull * g + 2), rd = ldg_stream(grows + 4ull * g + 3);
+
+  while (true) {
+    // ---- unpack the current row, prefetch the next one ----
+    const uint32_t g_next = g + n_tiles;
+    const bool has_next = g_next < a.n_groups;
+    const uint4 ca = ra, cb = rb, cc = rc, cd = rd;
+    if (has_next) {
+      ra = ldg_stream(grows + 4ull * g_next + 0);
+      rb = ldg_stream(grows + 4ull * g_next + 1);
+      rc = ldg_stream(grows + 4ull * g_next + 2);
+      rd = ldg_stream(grows + 4ull * g_next + 3);
+    }
+    const uint32_t pod_base = cc.z, pod_count = cc.w, lws_index = cd.x, gflags = cd.y;
+    const bool bad = lws_index >= a.n_lws || (uint64_t)pod_base + pod_count > a.n_pods;
+
+    uint32_t oflags = 0, first_out = LWSE_NONE, domain = LWSE_NONE;
+    int32_t worker_replicas = 0;
+    if (bad) {
+      oflags = LWSE_GOUT_BAD_TABLE;
+    } else {
+      // owner row: only its first 16 bytes (rev_hash, size, flags)
+      const uint4 L = ldg_cached(reinterpret_cast<const uint4*>(a.lws + lws_index));
+      const int32_t size = (int32_t)L.z;
+      const uint32_t lflags = L.w;
+      const uint32_t policy = (lflags & LWSE_LWS_RESTART_MASK) >> LWSE_LWS_RESTART_SHIFT;
+
+      GroupCtx c;
+      c.leader_rev_lo = ca.x;
+      c.leader_rev_hi = ca.y;
+      c.leader_uid = cb.z;
+      c.wsts_uid = cb.w;
+      c.policy_on = policy == LWSE_RESTART_ON_POD_RESTART || policy == LWSE_RESTART_AFTER_START;
+      c.leader_found = (gflags & (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH)) ==
+                       (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH);
+      constexpr uint32_t kChain =
+          LWSE_GRP_WSTS_FOUND | LWSE_GRP_WSTS_OWNER_IS_POD | LWSE_GRP_WSTS_OWNER_NAME_MATCH;
+      c.wsts_chain_ok = (gflags & kChain) == kChain && cc.x == cb.z;  // sts ownerRef.uid == leader.uid
+      c.leader_deleting = gflags & LWSE_GRP_POD_DELETING;
+
+      // ---- stream the pod rows: two 128-bit loads in flight per lane ----
+      const uint4* prows = reinterpret_cast<const uint4*>(a.pods) + pod_base;
+      uint32_t acc = 0, first = LWSE_NONE;
+      for (uint32_t i = lane; i < pod_count; i += 2 * W) {
+        const uint32_t j = i + W;
+        const bool two = j < pod_count;
+        const uint4 p0 = ldg_stream(prows + i);
+        uint4 p1 = make_uint4(0, 0, 0, 0);
+        if (two) p1 = ldg_stream(prows + j);
+        fold_pod(p0, i, c, acc, first, a.occupancy, a.n_nodes);
+        if (two) fold_pod(p1, j, c, acc, first, a.occupancy, a.n_nodes);
+      }
+      acc = tile_or<W>(acc);
+      const bool any_trig = acc & (ACC_TRIG_DELETE | ACC_TRIG_DELETING);
+      if (any_trig) first = tile_min<W>(first);  // tile-uniform branch
+
+      // pendingPodsInGroup :338-362
+      const bool pending = (uint32_t)size != pod_count || (acc & ACC_PENDING);
+      // :222 skip when pending ∧ (AfterStart ∨ annotation)
+      const bool suppressed =
+          pending && (policy == LWSE_RESTART_AFTER_START || (lflags & LWSE_LWS_RECREATE_AFTER_START_ANNOT));
+      if (pending) oflags |= LWSE_GOUT_PENDING;
+      bool leader_deleted = false;
+      if (!suppressed) {
+        if (acc & ACC_TRIG_DELETE) oflags |= LWSE_GOUT_DELETE_LEADER;
+        if (acc & ACC_TRIG_DELETING) oflags |= LWSE_GOUT_LEADER_DELETING;
+        if (acc & ACC_ERROR) oflags |= LWSE_GOUT_RESTART_ERROR;
+        if (any_trig) first_out = first;
+        leader_deleted = acc & ACC_LEADER_TRIG;
+      }
+
+      // ---- per-replica state bits (consumed by lws_sweep_kernel) ----
+      const bool no_wsts = size == 1;
+      const uint64_t rev = u64_of(L.x, L.y);
+      const bool leader_updated = u64_of(ca.x, ca.y) == rev;
+      const bool wsts_updated = u64_of(ca.z, ca.w) == rev;
+      const bool leader_ready = (gflags & (LWSE_GRP_POD_RUNNING | LWSE_GRP_POD_READY)) ==
+                                (LWSE_GRP_POD_RUNNING | LWSE_GRP_POD_READY);  // PodRunningAndReady
+      const bool wsts_ready = cb.x == cb.y && (gflags & LWSE_GRP_WSTS_REV_SETTLED);  // StatefulsetReady
+      const bool ready = leader_ready && (no_wsts || wsts_ready);
+      const bool updated = leader_updated && (no_wsts || wsts_updated);
+      // getReplicaStates :609-617 — names decide whether the slot is live
+      const bool named = (gflags & LWSE_GRP_POD_NAME_MATCH) &&
+                         (no_wsts || (gflags & LWSE_GRP_WSTS_LABEL_NAME_MATCH));
+      if (named && ready) oflags |= LWSE_GOUT_STATE_READY;
+      if (named && updated) oflags |= LWSE_GOUT_STATE_UPDATED;
+      // updateConditions :433-476 — existing leader pods whose worker sts is found
+      const bool counted = (gflags & LWSE_GRP_POD_PRESENT) && (no_wsts || (gflags & LWSE_GRP_WSTS_FOUND));
+      if (counted) {
+        oflags |= LWSE_GOUT_COUNTED;
+        if (ready) oflags |= LWSE_GOUT_COND_READY;
+        if (updated) oflags |= LWSE_GOUT_COND_UPDATED;
+      }
+
+      // ---- the leader pod's own Reconcile tail, pod_controller.go:95-198 ----
+      bool go_on = (gflags & LWSE_GRP_POD_PRESENT) && !leader_deleted &&
+                   !(gflags & (LWSE_GRP_MISTAKEN_ANNOTATION | LWSE_GRP_POD_DELETING));
+      if (go_on) {
+        if (a.sweep_flags & LWSE_SWEEP_GANG) oflags |= LWSE_GOUT_CREATE_PODGROUP;  // :130
+        go_on = !no_wsts &&                                                          // :138
+                !((lflags & LWSE_LWS_STARTUP_LEADER_READY) && !(gflags & LWSE_GRP_POD_READY));  // :143
+      }
+      if (go_on && !(gflags & LWSE_GRP_REVISION_EXISTS)) {  // :152
+        oflags |= LWSE_GOUT_REQUEUE_REVISION;
+        go_on = false;
+      }
+      if (go_on && (lflags & LWSE_LWS_EXCLUSIVE_TOPOLOGY)) {  // :162
+        const uint32_t node = cc.y;
+        if (node == LWSE_NONE) {  // :164
+          oflags |= LWSE_GOUT_WAIT_SCHEDULE;
+          go_on = false;
+        } else if (node != LWSE_NODE_NOT_FOUND && node < a.n_nodes) {
+          const uint4 nr = ldg_cached(reinterpret_cast<const uint4*>(a.nodes + node));
+          const uint32_t nflags = nr.w >> 16;
+          if (!(nflags & LWSE_NODE_HAS_TOPOLOGY)) {  // :330
+            oflags |= LWSE_GOUT_TOPOLOGY_ERROR;
+            go_on = false;
+          } else {
+            domain = nr.z;
+          }
+        }  // Node NotFound → empty value, nil error (:327)
+      }
+      if (go_on && !(gflags & LWSE_GRP_WSTS_FOUND)) {  // :188-192
+        oflags |= LWSE_GOUT_CREATE_WSTS;
+        worker_replicas = size - 1;  // :437; ordinals start at 1 (:440)
+      }
+    }
+    if (lane == 0)
+      stg_stream(a.out + g, make_uint4(oflags, first_out, (uint32_t)worker_replicas, domain));
+
+    if (!has_next) break;
+    g = g_next;
+  }
+}
+
+// --------------------------------------------------------------------------
+// LWS-level pass
+// --------------------------------------------------------------------------
+struct LwsSweepArgs {
+  const lwse_lws_rec* lws;
+  const lwse_group_out* gout;
+  lwse_lws_out* out;
+  uint32_t n_lws;
+  uint32_t n_groups;
+  uint32_t sweep_flags;
+};
+
+__device__ __forceinline__ int32_t want_replicas(int32_t lws_replicas, int32_t surge, int32_t mu,
+                                                 int32_t unready, int32_t sts_replicas,
+                                                 uint32_t& event) {
+  // calculateRollingUpdateReplicas :685-696
+  int32_t fin;
+  if (unready <= surge) {
+    fin = lws_replicas + max(0, unready - mu);
+  } else {
+    fin = lws_replicas + surge;
+  }
+  if (fin == sts_replicas - 1)  // :313
+    event = LWSE_EVENT_DELETE_ONE;
+  else if (fin < sts_replicas)  // :315
+    event = LWSE_EVENT_DELETE_RANGE;
+  return fin;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) lws_sweep_kernel(const LwsSweepArgs a) {
+  constexpr uint32_t kTilesPerBlock = 256 / W;
+  const uint32_t lane = threadIdx.x & (W - 1);
+  const uint32_t n_tiles = gridDim.x * kTilesPerBlock;
+  for (uint32_t i = blockIdx.x * kTilesPerBlock + threadIdx.x / W; i < a.n_lws; i += n_tiles) {
+    const uint4* row = reinterpret_cast<const uint4*>(a.lws + i);
+    const uint4 r0 = ldg_stream(row + 0), r1 = ldg_stream(row + 1), r2 = ldg_stream(row + 2),
+                r3 = ldg_stream(row + 3);
+    const int32_t size = (int32_t)r0.z;
+    const uint32_t lflags = r0.w;
+    const int32_t R = (int32_t)r1.x, P = (int32_t)r1.y;
+    const int32_t n = (int32_t)r2.x;  // sts replicas
+    const int32_t cur_partition = (int32_t)r2.y, annot = (int32_t)r2.z;
+    const uint32_t gbase = r3.z, gc = r3.w;
+
+    uint32_t oflags = 0, event = LWSE_EVENT_NONE;
+    int32_t o_partition = 0, o_replicas = 0, o_mu = 0, o_ready = 0, o_updated = 0, o_unready = 0,
+            o_min_member = 0;
+
+    if ((uint64_t)gbase + gc > a.n_groups) {
+      oflags = LWSE_LOUT_BAD_TABLE;
+    } else {
+      const lwse_group_out* go = a.gout + gbase;
+      const bool sts_exists = lflags & LWSE_LWS_STS_EXISTS;
+      const bool intstr_bad = lflags & LWSE_LWS_INTSTR_INVALID;
+      int32_t mu = scaled_value((int32_t)r1.w, lflags & LWSE_LWS_UNAVAIL_IS_PERCENT, R, false);
+      int32_t surge = scaled_value((int32_t)r1.z, lflags & LWSE_LWS_SURGE_IS_PERCENT, R, true);
+      if (surge > R) surge = R;  // :307
+      const int32_t burst = R + surge;
+
+      // ---- pass A: counters over every group slot of the object ----
+      // updateConditions counters (:450-475) and, for slots below the leader
+      // sts's replica count, the getReplicaStates view.
+      int32_t c_ready = 0, c_updated = 0, c_cur_nb = 0, c_upd_nb = 0, c_ready_nb = 0, c_upd_rdy = 0;
+      int32_t c_ok_below_R = 0;  // slots < min(R, n) that are ready ∧ updated
+      int32_t max_bad = -1;      // highest slot < n that is not (ready ∧ updated)
+      const int32_t n_live = min(n, (int32_t)min(gc, 0x7FFFFFFFu));
+      for (uint32_t idx = lane; idx < gc; idx += W) {
+        const uint32_t f = __ldg(&go[idx].flags);
+        const int32_t ix = (int32_t)idx;
+        const bool in_nb = ix < R && ix >= P;
+        if (f & LWSE_GOUT_COUNTED) {
+          const bool rd = f & LWSE_GOUT_COND_READY, up = f & LWSE_GOUT_COND_UPDATED;
+          c_ready += rd;
+          c_updated += up;
+          c_cur_nb += in_nb;
+          c_upd_nb += in_nb && up;
+          c_ready_nb += (ix < R) && rd;
+          c_upd_rdy += in_nb && rd && up;
+        }
+        if (ix < n_live) {
+          const bool ok = (f & (LWSE_GOUT_STATE_READY | LWSE_GOUT_STATE_UPDATED)) ==
+                          (LWSE_GOUT_STATE_READY | LWSE_GOUT_STATE_UPDATED);
+          if (ok && ix < R) c_ok_below_R++;
+          if (!ok) max_bad = ix;  // idx ascends per lane
+        }
+      }
+      // pack the six small counters pairwise to halve the reductions
+      c_ready = tile_add<W>(c_ready);
+      c_updated = tile_add<W>(c_updated);
+      c_cur_nb = tile_add<W>(c_cur_nb);
+      c_upd_nb = tile_add<W>(c_upd_nb);
+      c_ready_nb = tile_add<W>(c_ready_nb);
+      c_upd_rdy = tile_add<W>(c_upd_rdy);
+      c_ok_below_R = tile_add<W>(c_ok_below_R);
+      max_bad = tile_max<W>(max_bad);
+      if (n > n_live) max_bad = n - 1;  // slots without any object are zero-valued states
+
+      // ---- status / conditions (:478-501) ----
+      if (lflags & LWSE_LWS_GROUP_LABEL_INVALID) {
+        oflags |= LWSE_LOUT_STATUS_ERROR;  // :434-437
+      } else {
+        o_ready = c_ready;
+        o_updated = c_updated;
+        uint32_t cond;
+        if (c_upd_nb < c_cur_nb)
+          cond = LWSE_COND_UPDATE_IN_PROGRESS;
+        else if (c_ready_nb == R && c_upd_rdy == c_cur_nb)
+          cond = LWSE_COND_AVAILABLE;
+        else
+          cond = LWSE_COND_PROGRESSING;
+        oflags |= cond << LWSE_LOUT_COND_SHIFT;
+        if (P == 0 && c_upd_rdy == R) oflags |= LWSE_LOUT_UPDATE_DONE;
+      }
+
+      // ---- rollingUpdateParameters (:280-373) ----
+      bool err = false;
+      if (!sts_exists) {  // Case 1
+        o_partition = 0;
+        o_replicas = R;
+      } else if (intstr_bad) {
+        err = true;
+      } else if (lflags & LWSE_LWS_UPDATED) {  // Case 2
+        o_partition = min(R, n);
+        o_replicas = n < R ? R : want_replicas(R, surge, mu, R, n, event);
+      } else if (cur_partition == 0 && n == R) {  // Case 3
+        o_partition = 0;
+        o_replicas = R;
+      } else if (n < R) {
+        o_partition = cur_partition;
+        o_replicas = R;
+      } else {
+        // calculateLWSUnreadyReplicas :675-683 (R >= 0 here because n >= R is not implied; clamp)
+        const int32_t unready = max(R, 0) - c_ok_below_R;
+        o_unready = unready;
+        if (!(lflags & LWSE_LWS_ANNOT_VALID)) {
+          err = true;  // :351-354
+        } else if (annot != R) {  // Case 4
+          o_partition = min(cur_partition, burst);
+          o_replicas = want_replicas(R, surge, mu, unready, n, event);
+        } else {  // Case 5
+          const int32_t step = mu + surge - (burst - n);  // :366-369
+          // rollingUpdatePartition :643-673
+          const int32_t cont_ready = n - 1 - max_bad;  // calculateContinuousReadyReplicas
+          const int32_t rsp = max(0, n - cont_ready - step);
+          // pass B: unavailable = #{idx < rsp : !ready}
+          int32_t unavail = 0;
+          const int32_t rsp_live = min(rsp, n_live);
+          for (int32_t idx = (int32_t)lane; idx < rsp_live; idx += W)
+            unavail += !(__ldg(&go[idx].flags) & LWSE_GOUT_STATE_READY);
+          unavail = tile_add<W>(unavail) + (rsp - rsp_live);
+          int32_t part = rsp + unavail;
+          const int32_t hi = min(part, n - 1);
+          if (hi >= rsp) {
+            // pass C: the walk stops at the highest idx in [rsp, hi] that is ready ∧ ¬updated
+            int32_t blocker = -1;
+            const int32_t hi_live = min(hi, n_live - 1);
+            for (int32_t idx = rsp + (int32_t)lane; idx <= hi_live; idx += W) {
+              const uint32_t f = __ldg(&go[idx].flags);
+              if ((f & LWSE_GOUT_STATE_READY) && !(f & LWSE_GOUT_STATE_UPDATED)) blocker = idx;
+            }
+            blocker = tile_max<W>(blocker);
+            if (blocker < 0)
+              part = rsp;
+            else if (blocker < hi)
+              part = blocker + 1;
+            // blocker == hi: the first probe breaks, partition keeps rsp + unavail
+          }
+          o_partition = min(part, cur_partition);
+          o_replicas = want_replicas(R, surge, mu, unready, n, event);
+        }
+      }
+      if (err) {
+        oflags |= LWSE_LOUT_RUP_ERROR;
+        o_partition = 0;
+        o_replicas = 0;
+        event = LWSE_EVENT_NONE;
+      }
+      o_partition = max(o_partition, P);  // deferred clamp :285-288
+      oflags |= event << LWSE_LOUT_EVENT_SHIFT;
+
+      // stsMaxUnavailable :811-830
+      if (!intstr_bad) o_mu = max(1, mu + surge);
+      // PodGroup MinMember, volcano_provider.go:72,81-83
+      if (a.sweep_flags & LWSE_SWEEP_GANG)
+        o_min_member = (lflags & LWSE_LWS_STARTUP_LEADER_READY) ? 1 : size;
+      if (lflags & LWSE_LWS_IRREGULAR) oflags |= LWSE_LOUT_IRREGULAR;
+    }
+    if (lane == 0) {
+      uint4* o = reinterpret_cast<uint4*>(a.out + i);
+      stg_stream(o + 0, make_uint4((uint32_t)o_partition, (uint32_t)o_replicas, (uint32_t)o_mu,
+                                   (uint32_t)o_ready));
+      stg_stream(o + 1, make_uint4((uint32_t)o_updated, (uint32_t)o_min_member, oflags,
+                                   (uint32_t)o_unready));
+    }
+  }
+}
+
+// --------------------------------------------------------------------------
+// launchers
+// --------------------------------------------------------------------------
+static int pick_tile(uint64_t items, uint64_t owners) {
+  // lanes per owner: next power of two >= average items per owner, in [1, 32]
+  if (owners == 0) return 1;
+  const uint64_t avg = (items + owners - 1) / owners;
+  int w = 1;
+  while (w < 32 && (uint64_t)w < avg) w <<= 1;
+  return w;
+}
+
+// Persistent-style grids: exactly as many CTAs as are resident at once
+// (SM count x occupancy), each tile striding over its share of the rows.
+template <typename K>
+static uint32_t resident_ctas(K kernel, int sm_count) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 4;
+  return (uint32_t)sm_count * (uint32_t)per_sm;
+}
+
+template <int W>
+static cudaError_t launch_group(const GroupSweepArgs& a, int sm_count, cudaStream_t s) {
+  constexpr uint32_t kTilesPerBlock = 256 / W;
+  static uint32_t resident = 0;
+  if (resident == 0) resident = resident_ctas(group_sweep_kernel<W>, sm_count);
+  const uint32_t want = (a.n_groups + kTilesPerBlock - 1) / kTilesPerBlock;
+  group_sweep_kernel<W><<<want < resident ? want : resident, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <int W>
+static cudaError_t launch_lws(const LwsSweepArgs& a, int sm_count, cudaStream_t s) {
+  constexpr uint32_t kTilesPerBlock = 256 / W;
+  static uint32_t resident = 0;
+  if (resident == 0) resident = resident_ctas(lws_sweep_kernel<W>, sm_count);
+  const uint32_t want = (a.n_lws + kTilesPerBlock - 1) / kTilesPerBlock;
+  lws_sweep_kernel<W><<<want < resident ? want : resident, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+// Returns the number of kernels launched (>=0) or a negative cudaError_t.
+int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
+                     int sm_count, cudaStream_t s, int* cuda_err) {
+  *cuda_err = 0;
+  int launches = 0;
+  cudaError_t e = cudaSuccess;
+  if (t->n_groups && !(t->flags & LWSE_SWEEP_SKIP_GROUP_PASS)) {
+    GroupSweepArgs a{t->lws,        t->groups,  t->pods,  d_nodes,     t->group_out, t->node_occupancy,
+                     t->n_pods,     t->n_lws,   t->n_groups, n_nodes, t->flags};
+    switch (pick_tile(t->n_pods, t->n_groups)) {
+      case 1: e = launch_group<1>(a, sm_count, s); break;
+      case 2: e = launch_group<2>(a, sm_count, s); break;
+      case 4: e = launch_group<4>(a, sm_count, s); break;
+      case 8: e = launch_group<8>(a, sm_count, s); break;
+      case 16: e = launch_group<16>(a, sm_count, s); break;
+      default: e = launch_group<32>(a, sm_count, s); break;
+    }
+    if (e != cudaSuccess) {
+      *cuda_err = (int)e;
+      return -1;
+    }
+    launches++;
+  }
+  if (t->n_lws && !(t->flags & LWSE_SWEEP_SKIP_LWS_PASS)) {
+    LwsSweepArgs a{t->lws, t->group_out, t->lws_out, t->n_lws, t->n_groups, t->flags};
+    switch (pick_tile(t->n_groups, t->n_lws)) {
+      case 1: e = launch_lws<1>(a, sm_count, s); break;
+      case 2: e = launch_lws<2>(a, sm_count, s); break;
+      case 4: e = launch_lws<4>(a, sm_count, s); break;
+      case 8: e = launch_lws<8>(a, sm_count, s); break;
+      case 16: e = launch_lws<16>(a, sm_count, s); break;
+      default: e = launch_lws<32>(a, sm_count, s); break;
+    }
+    if (e != cudaSuccess) {
+      *cuda_err = (int)e;
+      return -1;
+    }
+    launches++;
+  }
+  return launches;
+}
+
+}  // namespace lwse

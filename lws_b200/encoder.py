@@ -310,15 +310,23 @@ def encode_lws(items: Iterable[LwsItem], cluster: Cluster, topology_key: Optiona
         if irregular:
             flags |= R.LWS_IRREGULAR
         lws_rows.append(
-            (R.hash64(lws.uid), R.hash64(it.revision_key), lws.replicas, lws.size,
-             lws.rollingUpdate.partition, surge, unav, flags, sts_replicas, sts_partition, annot,
-             lws.subGroupSize or 0, group_base, n_groups)
+            dict(
+                rev_hash=R.hash64(it.revision_key), size=lws.size, flags=flags, replicas=lws.replicas,
+                partition=lws.rollingUpdate.partition, max_surge=surge, max_unavailable=unav,
+                sts_replicas=sts_replicas, sts_partition=sts_partition, sts_replicas_annotation=annot,
+                subgroup_size=lws.subGroupSize or 0, uid_hash=R.hash64(lws.uid),
+                group_base=group_base, group_count=n_groups,
+            )
         )
 
     def table(rows, dtype):
         t = R.aligned_empty(len(rows), dtype)
         for i, r in enumerate(rows):
-            t[i] = r
+            if isinstance(r, dict):
+                for k, v in r.items():
+                    t[i][k] = v
+            else:
+                t[i] = r
         return t
 
     return LwsTables(

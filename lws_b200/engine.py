@@ -1,0 +1,205 @@
+"""ctypes binding of ``liblwse.so`` (the C ABI of ``include/lwse.h``).
+
+This is the only way Python reaches the engine, and it is the same set of
+symbols a cgo shim binds.  There is no fallback: if the
+library is missing or no sm_100 device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import records as R
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblwse.so")
+_lib = None
+
+# every symbol include/lwse.h declares: name → (argtypes, restype)
+SYMBOLS = {
+    "lwse_create": ([C.POINTER(R.Config), C.POINTER(C.c_void_p)], C.c_int),
+    "lwse_destroy": ([C.c_void_p], None),
+    "lwse_strerror": ([C.c_int], C.c_char_p),
+    "lwse_last_cuda_error": ([C.c_void_p], C.c_int),
+    "lwse_abi_version": ([], C.c_uint32),
+    "lwse_stream": ([C.c_void_p], C.c_void_p),
+    "lwse_launch_count": ([C.c_void_p], C.c_uint64),
+    "lwse_shard_of": ([C.c_uint64, C.c_uint32], C.c_uint32),
+    "lwse_hash64": ([C.c_void_p, C.c_size_t], C.c_uint64),
+    "lwse_upload_nodes": ([C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32], C.c_int),
+    "lwse_sweep_lws_host": ([C.c_void_p, C.POINTER(R.LwsTables)], C.c_int),
+    "lwse_sweep_lws_device": ([C.c_void_p, C.POINTER(R.LwsTables), C.c_void_p], C.c_int),
+    "lwse_place_host": (
+        [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)],
+        C.c_int,
+    ),
+    "lwse_place_device": (
+        [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p],
+        C.c_int,
+    ),
+    "lwse_sweep_ds_host": ([C.c_void_p, C.POINTER(R.DsTables)], C.c_int),
+    "lwse_sweep_ds_device": ([C.c_void_p, C.POINTER(R.DsTables), C.c_void_p], C.c_int),
+    "lwse_group_keys_host": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p], C.c_int),
+    "lwse_group_keys_device": (
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p],
+        C.c_int,
+    ),
+}
+
+
+class LwseError(RuntimeError):
+    def __init__(self, status: int, cuda_error: int = 0):
+        self.status, self.cuda_error = status, cuda_error
+        msg = lib().lwse_strerror(status).decode()
+        if cuda_error:
+            msg += f" [cudaError {cuda_error}]"
+        super().__init__(f"lwse: {msg} ({status})")
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Load liblwse.so; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise FileNotFoundError(
+                f"{_LIB_PATH} is missing: build it with `python -m lws_b200.build` "
+                "(the engine has no CPU fallback)"
+            )
+        _lib = C.CDLL(_LIB_PATH)
+        for name, (args, res) in SYMBOLS.items():
+            fn = getattr(_lib, name)  # AttributeError = ABI drift, fail loudly
+            fn.argtypes, fn.restype = args, res
+    return _lib
+
+
+def shard_of(uid_hash: int, n_shards: int) -> int:
+    return lib().lwse_shard_of(uid_hash, n_shards)
+
+
+class Engine:
+    """One engine per GPU (``lwse_create``)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        cfg = R.Config(R.ABI_VERSION, device, 0, 0)
+        rc = lib().lwse_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise LwseError(rc)
+        self.device = device
+        self.n_nodes = 0
+        self.n_domains = 0
+
+    def close(self):
+        if self._h:
+            lib().lwse_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise LwseError(rc, lib().lwse_last_cuda_error(self._h))
+
+    @property
+    def stream(self) -> int:
+        return lib().lwse_stream(self._h) or 0
+
+    @property
+    def launch_count(self) -> int:
+        return lib().lwse_launch_count(self._h)
+
+    # ------------------------------------------------------------------ nodes
+    def upload_nodes(self, nodes: np.ndarray, n_domains: int):
+        assert nodes.dtype == R.NODE_REC
+        self._check(lib().lwse_upload_nodes(self._h, R.ptr(nodes) if len(nodes) else None, len(nodes), n_domains))
+        self.n_nodes, self.n_domains = len(nodes), n_domains
+
+    # -------------------------------------------------------------- LWS sweep
+    def sweep_lws_host(self, lws, groups, pods, flags=0, want_occupancy=False, out=None):
+        """Host tables in → (lws_out, group_out, occupancy|None) host tables out."""
+        assert lws.dtype == R.LWS_REC and groups.dtype == R.GROUP_REC and pods.dtype == R.POD_REC
+        if out is None:
+            lws_out = R.aligned_empty(len(lws), R.LWS_OUT)
+            group_out = R.aligned_empty(len(groups), R.GROUP_OUT)
+        else:
+            lws_out, group_out = out
+        occ = np.zeros(max(self.n_nodes, 1), dtype=np.uint32) if want_occupancy else None
+        t = R.LwsTables(
+            R.ptr(lws), len(lws), R.ptr(groups), len(groups), R.ptr(pods), len(pods),
+            R.ptr(lws_out), R.ptr(group_out), R.ptr(occ), flags,
+        )
+        self._check(lib().lwse_sweep_lws_host(self._h, C.byref(t)))
+        return lws_out, group_out, (occ[: self.n_nodes] if occ is not None else None)
+
+    def sweep_lws_device(self, d_lws, n_lws, d_groups, n_groups, d_pods, n_pods, d_lws_out, d_group_out,
+                         d_occupancy=None, flags=0, stream=None):
+        """Device pointers (ints / tensors) in; kernels are enqueued, no synchronize."""
+        t = R.LwsTables(
+            R.ptr(d_lws), n_lws, R.ptr(d_groups), n_groups, R.ptr(d_pods), n_pods,
+            R.ptr(d_lws_out), R.ptr(d_group_out), R.ptr(d_occupancy), flags,
+        )
+        self._check(lib().lwse_sweep_lws_device(self._h, C.byref(t), stream))
+
+    # -------------------------------------------------------------- placement
+    def place_host(self, reqs: np.ndarray, occupancy=None, n_namespaces=1):
+        assert reqs.dtype == R.PLACE_REQ
+        out = R.aligned_empty(len(reqs), R.PLACE_OUT)
+        rounds = C.c_uint32(0)
+        if occupancy is not None:
+            occupancy = np.ascontiguousarray(occupancy, dtype=np.uint32)
+        self._check(
+            lib().lwse_place_host(self._h, R.ptr(reqs), len(reqs), R.ptr(occupancy), n_namespaces,
+                                  R.ptr(out), C.byref(rounds))
+        )
+        return out, rounds.value
+
+    def place_device(self, d_reqs, n_reqs, d_occupancy, n_namespaces, d_out, stream=None):
+        rounds = C.c_uint32(0)
+        self._check(
+            lib().lwse_place_device(self._h, R.ptr(d_reqs), n_reqs, R.ptr(d_occupancy), n_namespaces,
+                                    R.ptr(d_out), C.byref(rounds), stream)
+        )
+        return rounds.value
+
+    # --------------------------------------------------------------------- DS
+    def sweep_ds_host(self, ds, roles, revroles):
+        assert ds.dtype == R.DS_REC and roles.dtype == R.DS_ROLE_REC and revroles.dtype == R.DS_REVROLE_REC
+        ds_out = R.aligned_empty(len(ds), R.DS_OUT)
+        role_out = R.aligned_empty(len(roles), R.DS_ROLE_OUT)
+        revrole_out = R.aligned_empty(len(revroles), R.DS_REVROLE_OUT)
+        t = R.DsTables(
+            R.ptr(ds), len(ds), R.ptr(roles), len(roles), R.ptr(revroles), len(revroles),
+            R.ptr(ds_out), R.ptr(role_out), R.ptr(revrole_out),
+        )
+        self._check(lib().lwse_sweep_ds_host(self._h, C.byref(t)))
+        return ds_out, role_out, revrole_out
+
+    def sweep_ds_device(self, d_ds, n_ds, d_roles, n_roles, d_revroles, n_revroles, d_ds_out, d_role_out,
+                        d_revrole_out, stream=None):
+        t = R.DsTables(
+            R.ptr(d_ds), n_ds, R.ptr(d_roles), n_roles, R.ptr(d_revroles), n_revroles,
+            R.ptr(d_ds_out), R.ptr(d_role_out), R.ptr(d_revrole_out),
+        )
+        self._check(lib().lwse_sweep_ds_device(self._h, C.byref(t), stream))
+
+    # ------------------------------------------------------------- group keys
+    def group_keys_host(self, strings) -> np.ndarray:
+        """SHA-1 of each string → (n, 20) uint8."""
+        enc = [s.encode() if isinstance(s, str) else bytes(s) for s in strings]
+        offsets = np.zeros(len(enc) + 1, dtype=np.uint32)
+        offsets[1:] = np.cumsum([len(b) for b in enc], dtype=np.uint64).astype(np.uint32)
+        blob = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8)
+        digests = np.zeros((len(enc), 20), dtype=np.uint8)
+        self._check(
+            lib().lwse_group_keys_host(self._h, R.ptr(blob), R.ptr(offsets), len(enc), R.ptr(digests))
+        )
+        return digests

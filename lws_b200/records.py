@@ -20,18 +20,18 @@ NODE_NOT_FOUND = 0xFFFFFFFE
 # --------------------------------------------------------------------------- #
 LWS_REC = np.dtype(
     [
-        ("uid_hash", "<u8"),
         ("rev_hash", "<u8"),
-        ("replicas", "<i4"),
         ("size", "<i4"),
+        ("flags", "<u4"),
+        ("replicas", "<i4"),
         ("partition", "<i4"),
         ("max_surge", "<i4"),
         ("max_unavailable", "<i4"),
-        ("flags", "<u4"),
         ("sts_replicas", "<i4"),
         ("sts_partition", "<i4"),
         ("sts_replicas_annotation", "<i4"),
         ("subgroup_size", "<i4"),
+        ("uid_hash", "<u8"),
         ("group_base", "<u4"),
         ("group_count", "<u4"),
     ],
@@ -143,6 +143,7 @@ LOUT_UPDATE_DONE = 1 << 4
 LOUT_EVENT_SHIFT = 5
 LOUT_EVENT_MASK = 3 << 5
 LOUT_IRREGULAR = 1 << 7
+LOUT_BAD_TABLE = 1 << 8
 COND_PROGRESSING, COND_AVAILABLE, COND_UPDATE_IN_PROGRESS = 0, 1, 2
 EVENT_NONE, EVENT_DELETE_ONE, EVENT_DELETE_RANGE = 0, 1, 2
 
@@ -166,8 +167,11 @@ GOUT_WAIT_SCHEDULE = 1 << 10
 GOUT_TOPOLOGY_ERROR = 1 << 11
 GOUT_REQUEUE_REVISION = 1 << 12
 GOUT_CREATE_PODGROUP = 1 << 13
+GOUT_BAD_TABLE = 1 << 14
 
 SWEEP_GANG = 1 << 0
+SWEEP_SKIP_GROUP_PASS = 1 << 1
+SWEEP_SKIP_LWS_PASS = 1 << 2
 
 # --------------------------------------------------------------------------- #
 # placement

@@ -35,8 +35,7 @@ def build(force: bool = False) -> str:
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
-            build()
+        build()  # no-op when liblwso.so is newer than its sources
         _lib = C.CDLL(_LIB_PATH)
         _lib.lwso_sweep_lws.argtypes = [C.POINTER(R.LwsTables), C.c_void_p, C.c_uint32, C.c_int]
         _lib.lwso_sweep_lws.restype = C.c_int

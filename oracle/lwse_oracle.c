@@ -465,11 +465,14 @@ static void reconcile_group(const lwse_lws_rec* l, const lwse_group_rec* g,
 /* whole-table sweep                                                         */
 /* ------------------------------------------------------------------------- */
 
-static void sweep_one_lws(const lwse_lws_tables* t, const lwse_node_rec* nodes, uint32_t n_nodes,
-                          uint32_t i) {
+static void sweep_one_lws(const lwse_lws_tables* t, uint32_t i) {
   const lwse_lws_rec* l = &t->lws[i];
   lwse_lws_out* o = &t->lws_out[i];
   memset(o, 0, sizeof(*o));
+  if ((uint64_t)l->group_base + l->group_count > t->n_groups) {
+    o->flags = LWSE_LOUT_BAD_TABLE;
+    return;
+  }
   uint32_t event = 0;
   int32_t unready = 0;
   if (rolling_update_parameters(l, t->groups, &o->sts_partition, &o->sts_replicas, &event, &unready))
@@ -482,25 +485,36 @@ static void sweep_one_lws(const lwse_lws_tables* t, const lwse_node_rec* nodes, 
   if (t->flags & LWSE_SWEEP_GANG)
     o->min_member = (l->flags & LWSE_LWS_STARTUP_LEADER_READY) ? 1 : l->size;
   if (l->flags & LWSE_LWS_IRREGULAR) o->flags |= LWSE_LOUT_IRREGULAR;
-  for (uint32_t r = 0; r < l->group_count; r++) {
-    const lwse_group_rec* g = &t->groups[l->group_base + r];
-    reconcile_group(l, g, t->pods, nodes, n_nodes, t->flags, &t->group_out[l->group_base + r]);
+}
+
+static void sweep_one_group(const lwse_lws_tables* t, const lwse_node_rec* nodes, uint32_t n_nodes,
+                            uint32_t r) {
+  const lwse_group_rec* g = &t->groups[r];
+  lwse_group_out* o = &t->group_out[r];
+  if (g->lws_index >= t->n_lws || (uint64_t)g->pod_base + g->pod_count > t->n_pods) {
+    o->flags = LWSE_GOUT_BAD_TABLE;
+    o->first_trigger = LWSE_NONE;
+    o->worker_replicas = 0;
+    o->domain_id = LWSE_NONE;
+    return;
   }
+  reconcile_group(&t->lws[g->lws_index], g, t->pods, nodes, n_nodes, t->flags, o);
 }
 
 /* Sweep every object, one at a time (the reference runs one reconcile worker
- * per controller).  threads > 1 splits the object range over pthreads — used
+ * per controller).  threads > 1 splits the row ranges over pthreads — used
  * only by bench.py's all-cores baseline. */
 typedef struct {
   const lwse_lws_tables* t;
   const lwse_node_rec* nodes;
   uint32_t n_nodes;
-  uint32_t begin, end;
+  uint32_t lws_begin, lws_end, grp_begin, grp_end;
 } sweep_job;
 
 static void* sweep_range(void* arg) {
   sweep_job* j = (sweep_job*)arg;
-  for (uint32_t i = j->begin; i < j->end; i++) sweep_one_lws(j->t, j->nodes, j->n_nodes, i);
+  for (uint32_t i = j->lws_begin; i < j->lws_end; i++) sweep_one_lws(j->t, i);
+  for (uint32_t r = j->grp_begin; r < j->grp_end; r++) sweep_one_group(j->t, j->nodes, j->n_nodes, r);
   return NULL;
 }
 
@@ -509,19 +523,18 @@ LWSO_API int lwso_sweep_lws(const lwse_lws_tables* t, const lwse_node_rec* nodes
   if (!t) return LWSE_ERR_INVALID_ARG;
   if (threads < 1) threads = 1;
   if (threads > 256) threads = 256;
-  if (threads == 1 || t->n_lws < (uint32_t)threads * 4u) {
-    sweep_job j = {t, nodes, n_nodes, 0, t->n_lws};
+  if (threads == 1 || t->n_groups < (uint32_t)threads * 4u) {
+    sweep_job j = {t, nodes, n_nodes, 0, t->n_lws, 0, t->n_groups};
     sweep_range(&j);
   } else {
     pthread_t tid[256];
     sweep_job jobs[256];
-    /* split by pod rows so that threads get equal work */
-    uint64_t per = (t->n_lws + (uint32_t)threads - 1) / (uint32_t)threads;
     for (int k = 0; k < threads; k++) {
-      uint64_t b = per * (uint64_t)k, e = b + per;
-      if (b > t->n_lws) b = t->n_lws;
-      if (e > t->n_lws) e = t->n_lws;
-      jobs[k] = (sweep_job){t, nodes, n_nodes, (uint32_t)b, (uint32_t)e};
+      jobs[k] = (sweep_job){t, nodes, n_nodes,
+                            (uint32_t)((uint64_t)t->n_lws * (uint64_t)k / (uint64_t)threads),
+                            (uint32_t)((uint64_t)t->n_lws * (uint64_t)(k + 1) / (uint64_t)threads),
+                            (uint32_t)((uint64_t)t->n_groups * (uint64_t)k / (uint64_t)threads),
+                            (uint32_t)((uint64_t)t->n_groups * (uint64_t)(k + 1) / (uint64_t)threads)};
       pthread_create(&tid[k], NULL, sweep_range, &jobs[k]);
     }
     for (int k = 0; k < threads; k++) pthread_join(tid[k], NULL);

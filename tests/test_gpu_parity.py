@@ -1,0 +1,165 @@
+"""GPU parity: the CUDA engine, called through the C ABI, against the CPU oracle
+on the same seeded tables — bit-exact on every output field."""
+import numpy as np
+import pytest
+
+from lws_b200 import records as R
+from lws_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from lws_b200.engine import Engine
+
+    e = Engine(0)  # raises if liblwse.so or the GPU is missing — no fallback
+    yield e
+    e.close()
+
+
+def assert_same(got, want, what):
+    assert got.dtype == want.dtype and got.shape == want.shape
+    for name in got.dtype.names or [None]:
+        a = got[name] if name else got
+        b = want[name] if name else want
+        if not np.array_equal(a, b):
+            bad = np.flatnonzero(a != b)
+            i = int(bad[0])
+            raise AssertionError(
+                f"{what}.{name}: {len(bad)} rows differ; first row {i}: got {a[i]!r} want {b[i]!r}"
+            )
+
+
+def run_both(engine, t, occupancy=True):
+    import oracle
+
+    engine.upload_nodes(t.nodes, t.n_domains)
+    want = oracle.sweep_lws(t.lws, t.groups, t.pods, t.nodes, flags=t.flags, want_occupancy=occupancy)
+    got = engine.sweep_lws_host(t.lws, t.groups, t.pods, flags=t.flags, want_occupancy=occupancy)
+    assert_same(got[0], want[0], "lws_out")
+    assert_same(got[1], want[1], "group_out")
+    if occupancy:
+        assert np.array_equal(got[2], want[2]), "node occupancy"
+    return got
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_fuzz(engine, seed):
+    run_both(engine, synth.make("fuzz", 1.0, seed=seed))
+
+
+@pytest.mark.parametrize("size", [1, 2, 3, 5, 8, 13, 16, 31, 32, 33, 64, 100])
+def test_every_tile_width(engine, size):
+    """pods-per-group selects the tile width W of the group kernel (1..32)."""
+    p = synth.profile("fuzz", 0.2)
+    p.size_choices = (size,)
+    run_both(engine, synth.make(p, seed=size))
+
+
+@pytest.mark.parametrize("replicas", [(0,), (1,), (3,), (31, 32, 33), (200,), (1, 1000)])
+def test_every_lws_tile_width(engine, replicas):
+    p = synth.profile("fuzz", 0.1)
+    p.size_choices = (2,)
+    p.replicas_choices = replicas
+    run_both(engine, synth.make(p, seed=7))
+
+
+@pytest.mark.parametrize("name,scale", [("C1", 1.0), ("C2", 1.0), ("C3", 0.1), ("C5", 0.05)])
+def test_baseline_configs(engine, name, scale):
+    run_both(engine, synth.make(name, scale))
+
+
+def test_empty_tables(engine):
+    t = synth.make("C1")
+    engine.upload_nodes(t.nodes, t.n_domains)
+    e_lws = R.aligned_empty(0, R.LWS_REC)
+    e_grp = R.aligned_empty(0, R.GROUP_REC)
+    e_pod = R.aligned_empty(0, R.POD_REC)
+    lo, go, _ = engine.sweep_lws_host(e_lws, e_grp, e_pod)
+    assert len(lo) == 0 and len(go) == 0
+    # objects without any group rows
+    t.lws["group_count"] = 0
+    run_both(engine, synth.Tables(t.profile, t.lws, e_grp, e_pod, t.nodes, t.n_domains, t.flags))
+
+
+def test_bad_tables_are_flagged_not_fatal(engine):
+    t = synth.make("fuzz", 0.05, seed=11)
+    t.lws["group_base"][3] = len(t.groups) + 5
+    t.groups["lws_index"][7] = len(t.lws) + 1
+    t.groups["pod_base"][9] = len(t.pods)
+    t.groups["pod_count"][9] = 3
+    lo, go, _ = run_both(engine, t)
+    assert lo["flags"][3] & R.LOUT_BAD_TABLE
+    assert go["flags"][7] & R.GOUT_BAD_TABLE and go["flags"][9] & R.GOUT_BAD_TABLE
+
+
+def test_device_pointer_entry(engine):
+    """lwse_sweep_lws_device with torch-owned device memory on torch's stream."""
+    import torch
+    import oracle
+
+    t = synth.make("C5", 0.02)
+    engine.upload_nodes(t.nodes, t.n_domains)
+    dev = torch.device("cuda:0")
+
+    def up(a):
+        return torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
+
+    d_lws, d_grp, d_pod = up(t.lws), up(t.groups), up(t.pods)
+    d_lo = torch.zeros(len(t.lws) * R.LWS_OUT.itemsize, dtype=torch.uint8, device=dev)
+    d_go = torch.zeros(len(t.groups) * R.GROUP_OUT.itemsize, dtype=torch.uint8, device=dev)
+    d_occ = torch.zeros(len(t.nodes), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    before = engine.launch_count
+    engine.sweep_lws_device(d_lws, len(t.lws), d_grp, len(t.groups), d_pod, len(t.pods), d_lo, d_go,
+                            d_occ, flags=t.flags, stream=stream)
+    torch.cuda.synchronize()
+    assert engine.launch_count - before == 2
+    want = oracle.sweep_lws(t.lws, t.groups, t.pods, t.nodes, flags=t.flags, want_occupancy=True)
+    assert_same(d_lo.cpu().numpy().view(R.LWS_OUT), want[0], "lws_out")
+    assert_same(d_go.cpu().numpy().view(R.GROUP_OUT), want[1], "group_out")
+    assert np.array_equal(d_occ.cpu().numpy().astype(np.uint32), want[2])
+
+
+def test_reference_integration_traces_on_gpu(engine):
+    """The reference's own integration traces, reconciled by the CUDA engine."""
+    from sim import LwsSim
+    from traces import TRACES, make_lws
+
+    def sweep(tables, flags=0):
+        engine.upload_nodes(tables.nodes, tables.n_domains)
+        lo, go, _ = engine.sweep_lws_host(tables.lws, tables.groups, tables.pods, flags=flags)
+        return lo, go
+
+    for name, (cfg, steps) in sorted(TRACES.items()):
+        sim = LwsSim(make_lws(cfg), sweep)
+        sim.settle()
+        sim.create_leader_pods(0, cfg["replicas"])
+        for i, (action, want) in enumerate(steps):
+            action(sim)
+            got = sim.state() + (sim.status["condition"],)
+            for g, w in zip(got, want):
+                if w is not None:
+                    assert g == w, f"{name} step {i}: got {got} want {want}"
+
+
+def test_large_idempotent_and_order_independent(engine):
+    """Full-size property checks (no oracle needed): sweeping twice gives the same
+    bytes, and permuting the objects permutes the outputs."""
+    t = synth.make("C3", 0.25)
+    engine.upload_nodes(t.nodes, t.n_domains)
+    a = engine.sweep_lws_host(t.lws, t.groups, t.pods, flags=t.flags)
+    b = engine.sweep_lws_host(t.lws, t.groups, t.pods, flags=t.flags)
+    assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()
+    # reverse the LWS table (group rows keep their place; lws_index is remapped)
+    n = len(t.lws)
+    perm = np.arange(n)[::-1].copy()
+    lws2 = R.aligned_empty(n, R.LWS_REC)
+    lws2[:] = t.lws[perm]
+    grp2 = R.aligned_empty(len(t.groups), R.GROUP_REC)
+    grp2[:] = t.groups
+    grp2["lws_index"] = (n - 1 - t.groups["lws_index"].astype(np.int64)).astype(np.uint32)
+    c = engine.sweep_lws_host(lws2, grp2, t.pods, flags=t.flags)
+    assert c[0].tobytes() == a[0][perm].tobytes()
+    assert c[1].tobytes() == a[1].tobytes()
