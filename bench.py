@@ -222,8 +222,9 @@ def run_ours(args):
             lws=up(t.lws), grp=up(t.groups), pod=up(t.pods),
             lo=torch.empty(n_lws * R.LWS_OUT.itemsize, dtype=torch.uint8, device=dev),
             go=torch.empty(n_grp * R.GROUP_OUT.itemsize, dtype=torch.uint8, device=dev)))
-    stream = torch.cuda.current_stream()
-    sptr = stream.cuda_stream
+    # time on the stream the kernels are launched on: the engine's own stream
+    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+    sptr = eng.stream
 
     def sweep(i, flags):
         s = sets[i % copies]

@@ -403,29 +403,39 @@ typedef struct lwse_ds_role_rec {
 #define LWSE_ROLE_SURGE_INVALID (1u << 4)   /* intstr error (ignored → 0, executor.go:249) */
 #define LWSE_ROLE_UNAVAIL_INVALID (1u << 5)
 
-/* One (revision, role) LWS child of a DS (16 B). */
+/* One (revision, role) LWS child of a DS (16 B).  Rows of one DS: for each old
+ * revision (in List order) n_roles rows in role order, then n_roles rows for
+ * the new (target) revision. */
 typedef struct lwse_ds_revrole_rec {
-  int32_t replicas;         /* getLWSReplicas (nil → 1)                           */
+  int32_t replicas;         /* getLWSReplicas: *spec.replicas, nil → 1            */
   int32_t initial_replicas; /* initial-replicas annotation, or -1 when absent/unparsable */
   int32_t ready_replicas;   /* status.readyReplicas                               */
-  uint32_t flags;           /* LWSE_RR_* */
+  uint32_t flags;           /* LWSE_RR_* | creation rank << LWSE_RR_TS_SHIFT      */
 } lwse_ds_revrole_rec;
 
-#define LWSE_RR_EXISTS (1u << 0)
+#define LWSE_RR_EXISTS (1u << 0)       /* this revision has an LWS for this role   */
+#define LWSE_RR_REPLICAS_NIL (1u << 1) /* spec.replicas == nil (cleanup counts it as 0,
+                                          disaggregatedset_controller.go:222-225) */
+#define LWSE_RR_TS_SHIFT 2             /* 30-bit order-preserving rank of
+                                          metadata.creationTimestamp (executor.go:283-302) */
 
 /* Per DS (16 B). */
 typedef struct lwse_ds_out {
-  uint32_t flags;      /* LWSE_DOUT_* */
-  uint32_t drained_revs; /* bit r set: old revision r has every role at 0 → delete */
-  uint32_t reserved[2];
+  uint32_t flags;        /* LWSE_DOUT_* */
+  uint32_t drained_revs; /* bit r: old revision r has every role at 0 → delete its LWS */
+  uint32_t ready_revs;   /* bit r: old revision r is ready on all spec roles (its
+                            services are kept, service_manager.go:174-189)          */
+  uint32_t reserved;
 } lwse_ds_out;
 
-#define LWSE_DOUT_ROLLING (1u << 0)      /* some old revision still has replicas  */
-#define LWSE_DOUT_STABLE (1u << 1)       /* isRevisionStable(newRevision)         */
-#define LWSE_DOUT_STEP (1u << 2)         /* ComputeNextStep returned a step       */
-#define LWSE_DOUT_COMPLETE (1u << 3)     /* planner returned nil                  */
-#define LWSE_DOUT_INIT (1u << 4)         /* no new revision yet → initRollingUpdate */
-#define LWSE_DOUT_NEW_READY (1u << 5)    /* service_manager readiness of the new revision */
+#define LWSE_DOUT_ROLLING (1u << 0)   /* old revisions still hold replicas → rolling path */
+#define LWSE_DOUT_INIT (1u << 1)      /* …but no new revision yet → initRollingUpdate     */
+#define LWSE_DOUT_STABLE (1u << 2)    /* isRevisionStable(newRevision)                    */
+#define LWSE_DOUT_STEP (1u << 3)      /* ComputeNextStep returned a step                  */
+#define LWSE_DOUT_COMPLETE (1u << 4)  /* ComputeNextStep returned nil                     */
+#define LWSE_DOUT_NEW_READY (1u << 5) /* target revision ready on all roles → ensure services */
+#define LWSE_DOUT_BAD_TABLE (1u << 6)
+#define LWSE_DS_MAX_OLD_REVS 32u
 
 /* Per role (8 B): the planner step. */
 typedef struct lwse_ds_role_out {
@@ -433,7 +443,9 @@ typedef struct lwse_ds_role_out {
   int32_t next_new; /* UpdateStep.New[i]  */
 } lwse_ds_role_out;
 
-/* Per (revision, role): replicas after scaleUpNew / scaleDownOld (4 B). */
+/* Per (revision, role): spec.replicas after this reconcile — scaleUpNew /
+ * scaleDownOld / reconcileSimple — or -1 where no LWS exists and none is
+ * created (4 B). */
 typedef int32_t lwse_ds_revrole_out;
 
 typedef struct lwse_ds_tables {

@@ -142,3 +142,43 @@ def controller_of(obj) -> Optional[OwnerReference]:
         if ref.controller:
             return ref
     return None
+
+
+# --------------------------------------------------------------------------- #
+# DisaggregatedSet (api/disaggregatedset/v1/disaggregatedset_types.go:24-72)
+# --------------------------------------------------------------------------- #
+DSSetNameLabelKey = "disaggregatedset.x-k8s.io/name"
+DSRoleLabelKey = "disaggregatedset.x-k8s.io/role"
+DSRevisionLabelKey = "disaggregatedset.x-k8s.io/revision"
+DSInitialReplicasAnnotationKey = "disaggregatedset.x-k8s.io/initial-replicas"
+
+
+@dataclass
+class DisaggregatedRoleSpec:
+    name: str
+    replicas: Optional[int] = 1  # spec.replicas (nil → 1, executor.go:223-233)
+    rollingUpdate: Optional[RollingUpdateConfiguration] = None  # rolloutStrategy.rollingUpdateConfiguration
+
+
+@dataclass
+class DisaggregatedSet:
+    name: str
+    namespace: str = "default"
+    uid: str = ""
+    roles: list = field(default_factory=list)
+
+    def __post_init__(self):
+        if not self.uid:
+            self.uid = f"uid-ds-{self.namespace}-{self.name}"
+
+
+@dataclass
+class ChildLWS:
+    """A LeaderWorkerSet owned by a DisaggregatedSet (lws_manager.go:60-130)."""
+
+    role: str
+    revision: str
+    replicas: Optional[int] = 1  # spec.replicas, None = nil
+    readyReplicas: int = 0
+    creationTimestamp: float = 0.0
+    annotations: dict = field(default_factory=dict)

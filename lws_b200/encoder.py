@@ -340,3 +340,92 @@ def encode_lws(items: Iterable[LwsItem], cluster: Cluster, topology_key: Optiona
         lws_names=[it.lws.name for it in items],
         group_pod_names=group_pod_names,
     )
+
+
+# --------------------------------------------------------------------------- #
+# DisaggregatedSet
+# --------------------------------------------------------------------------- #
+@dataclass
+class DsItem:
+    ds: api.DisaggregatedSet
+    revision: str  # ComputeRevision(spec.roles) — the target revision
+    children: list = field(default_factory=list)  # api.ChildLWS, List order
+
+
+@dataclass
+class DsTablesHost:
+    ds: np.ndarray
+    roles: np.ndarray
+    revroles: np.ndarray
+    role_names: list  # per DS: allRoleNames
+    old_revisions: list  # per DS: old revision names in row order
+
+
+def get_initial_replicas(child: api.ChildLWS) -> int:
+    """pkg/utils/disaggregatedset/utils.go:33-46 → value or -1."""
+    v = child.annotations.get(api.DSInitialReplicasAnnotationKey)
+    if v is None or v == "":
+        return -1
+    n = atoi(v)
+    if n is None or not -(1 << 31) <= n < (1 << 31):  # strconv.ParseInt(value, 10, 32)
+        return -1
+    return n
+
+
+def encode_ds(items: Iterable[DsItem]) -> DsTablesHost:
+    items = list(items)
+    ds_rows, role_rows, rr_rows, names_out, revs_out = [], [], [], [], []
+    # one order-preserving rank table for all timestamps
+    stamps = sorted({c.creationTimestamp for it in items for c in it.children})
+    rank = {s: i + 1 for i, s in enumerate(stamps)}
+    for it in items:
+        spec_names = [r.name for r in it.ds.roles]
+        # GroupByRevision (utils.go:192-211); old revisions in first-seen order
+        by_rev: dict[str, dict[str, api.ChildLWS]] = {}
+        for c in it.children:
+            by_rev.setdefault(c.revision, {})[c.role] = c
+        old_revs = [r for r in by_rev if r != it.revision]
+        # allRoleNames = spec roles, then removed roles (executor.go:140,189-197); the
+        # reference ranges a Go map there — canonical order here is sorted
+        old_role_set = {role for r in old_revs for role in by_rev[r]}
+        removed = sorted(old_role_set - set(spec_names))
+        all_names = spec_names + removed
+        n = len(all_names)
+        role_base, rev_base = len(role_rows), len(rr_rows)
+        for i, name in enumerate(all_names):
+            flags, target, surge, unav = 0, 0, 0, 0
+            if i < len(spec_names):
+                spec = it.ds.roles[i]
+                flags |= R.ROLE_IN_SPEC
+                target = 1 if spec.replicas is None else spec.replicas
+                if spec.rollingUpdate is not None:
+                    flags |= R.ROLE_HAS_ROLLING_CONFIG
+                    surge, sp, sok = parse_int_or_percent(spec.rollingUpdate.maxSurge)
+                    unav, up, uok = parse_int_or_percent(spec.rollingUpdate.maxUnavailable)
+                    flags |= (R.ROLE_SURGE_IS_PERCENT if sp else 0) | (R.ROLE_UNAVAIL_IS_PERCENT if up else 0)
+                    flags |= (0 if sok else R.ROLE_SURGE_INVALID) | (0 if uok else R.ROLE_UNAVAIL_INVALID)
+            role_rows.append((target, surge, unav, flags))
+        for rev in old_revs + [it.revision]:
+            for name in all_names:
+                c = by_rev.get(rev, {}).get(name)
+                if c is None:
+                    rr_rows.append((0, -1, 0, 0))
+                    continue
+                flags = R.RR_EXISTS | (rank[c.creationTimestamp] << R.RR_TS_SHIFT)
+                if c.replicas is None:
+                    flags |= R.RR_REPLICAS_NIL
+                rr_rows.append((1 if c.replicas is None else c.replicas, get_initial_replicas(c),
+                                c.readyReplicas, flags))
+        ds_flags = R.DS_HAS_NEW_REVISION if it.revision in by_rev else 0
+        ds_rows.append((R.hash64(it.ds.uid), role_base, n, len(spec_names), rev_base, len(old_revs), ds_flags))
+        names_out.append(all_names)
+        revs_out.append(old_revs)
+
+    def table(rows, dtype):
+        t = R.aligned_empty(len(rows), dtype)
+        for i, r in enumerate(rows):
+            t[i] = r
+        return t
+
+    return DsTablesHost(table(ds_rows, R.DS_REC), table(role_rows, R.DS_ROLE_REC),
+                        table(rr_rows, R.DS_REVROLE_REC), names_out, revs_out)

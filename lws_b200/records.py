@@ -234,15 +234,21 @@ DS_REVROLE_REC = np.dtype(
 )
 assert DS_REVROLE_REC.itemsize == 16
 RR_EXISTS = 1 << 0
+RR_REPLICAS_NIL = 1 << 1
+RR_TS_SHIFT = 2
 
-DS_OUT = np.dtype([("flags", "<u4"), ("drained_revs", "<u4"), ("reserved", "<u4", (2,))], align=False)
+DS_OUT = np.dtype(
+    [("flags", "<u4"), ("drained_revs", "<u4"), ("ready_revs", "<u4"), ("reserved", "<u4")], align=False
+)
 assert DS_OUT.itemsize == 16
 DOUT_ROLLING = 1 << 0
-DOUT_STABLE = 1 << 1
-DOUT_STEP = 1 << 2
-DOUT_COMPLETE = 1 << 3
-DOUT_INIT = 1 << 4
+DOUT_INIT = 1 << 1
+DOUT_STABLE = 1 << 2
+DOUT_STEP = 1 << 3
+DOUT_COMPLETE = 1 << 4
 DOUT_NEW_READY = 1 << 5
+DOUT_BAD_TABLE = 1 << 6
+DS_MAX_OLD_REVS = 32
 
 DS_ROLE_OUT = np.dtype([("next_old", "<i4"), ("next_new", "<i4")], align=False)
 assert DS_ROLE_OUT.itemsize == 8

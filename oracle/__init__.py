@@ -87,3 +87,54 @@ def sweep_lws(lws, groups, pods, nodes=None, flags=0, want_occupancy=False, thre
     if rc != 0:
         raise RuntimeError(f"lwso_sweep_lws failed: {rc}")
     return lws_out, group_out, (occ[:n_nodes] if occ is not None else None)
+
+
+def sweep_ds(ds, roles, revroles):
+    ds_out = R.aligned_empty(len(ds), R.DS_OUT)
+    role_out = R.aligned_empty(len(roles), R.DS_ROLE_OUT)
+    revrole_out = R.aligned_empty(len(revroles), R.DS_REVROLE_OUT)
+    t = R.DsTables(R.ptr(ds), len(ds), R.ptr(roles), len(roles), R.ptr(revroles), len(revroles),
+                   R.ptr(ds_out), R.ptr(role_out), R.ptr(revrole_out))
+    rc = lib().lwso_sweep_ds(C.byref(t))
+    if rc != 0:
+        raise RuntimeError(f"lwso_sweep_ds failed: {rc}")
+    return ds_out, role_out, revrole_out
+
+
+def ds_compute_next_step(initial_old, current_old, current_new, target_new, max_surge, max_unavailable):
+    """planner.go:320 ComputeNextStep → (past, new) or None."""
+    n = len(initial_old)
+    arr = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+    a = [arr(x) for x in (initial_old, current_old, current_new, target_new, max_surge, max_unavailable)]
+    past, new = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    rc = lib().lwso_ds_compute_next_step(n, *[R.ptr(x) for x in a], R.ptr(past), R.ptr(new))
+    if rc < 0:
+        raise RuntimeError("lwso_ds_compute_next_step failed")
+    return (past.tolist(), new.tolist()) if rc else None
+
+
+def ds_compute_all_steps(initial_old, target, max_surge, max_unavailable):
+    """planner.go:355-385 ComputeAllSteps."""
+    n = len(initial_old)
+    cur_old, cur_new = list(initial_old), [0] * n
+    steps = [(list(initial_old), [0] * n)]
+    for _ in range(max(max(initial_old + target + [0]) * 2 + 10, 0)):
+        s = ds_compute_next_step(initial_old, cur_old, cur_new, target, max_surge, max_unavailable)
+        if s is None:
+            break
+        steps.append(s)
+        cur_old, cur_new = s
+    return steps
+
+
+def ds_scale_down_old(replicas, order, current, target):
+    """executor.go:330-398; replicas[r][i] (-1 = role missing) newest-first via order."""
+    n = len(current)
+    reps = np.ascontiguousarray(replicas, dtype=np.int32).reshape(-1)
+    o = np.ascontiguousarray(order, dtype=np.int32)
+    rc = lib().lwso_ds_scale_down_old(n, len(order), R.ptr(reps), R.ptr(o),
+                                      R.ptr(np.ascontiguousarray(current, np.int32)),
+                                      R.ptr(np.ascontiguousarray(target, np.int32)), None)
+    if rc != 0:
+        raise RuntimeError("lwso_ds_scale_down_old failed")
+    return reps.reshape(len(order), n).tolist()

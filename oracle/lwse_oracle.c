@@ -540,11 +540,16 @@ LWSO_API int lwso_sweep_lws(const lwse_lws_tables* t, const lwse_node_rec* nodes
     for (int k = 0; k < threads; k++) pthread_join(tid[k], NULL);
   }
   if (t->node_occupancy) {
-    for (uint64_t p = 0; p < t->n_pods; p++) {
-      uint32_t b = t->pods[p].bits;
-      if (b & LWSE_POD_SCHEDULED) {
-        uint32_t node = b >> LWSE_POD_NODE_SHIFT;
-        if (node < n_nodes) t->node_occupancy[node]++;
+    /* pods per node, over the pod rows of every well-formed group row */
+    for (uint32_t r = 0; r < t->n_groups; r++) {
+      const lwse_group_rec* g = &t->groups[r];
+      if (g->lws_index >= t->n_lws || (uint64_t)g->pod_base + g->pod_count > t->n_pods) continue;
+      for (uint32_t i = 0; i < g->pod_count; i++) {
+        uint32_t b = t->pods[g->pod_base + i].bits;
+        if (b & LWSE_POD_SCHEDULED) {
+          uint32_t node = b >> LWSE_POD_NODE_SHIFT;
+          if (node < n_nodes) t->node_occupancy[node]++;
+        }
       }
     }
   }
