@@ -132,9 +132,9 @@ def ds_scale_down_old(replicas, order, current, target):
     n = len(current)
     reps = np.ascontiguousarray(replicas, dtype=np.int32).reshape(-1)
     o = np.ascontiguousarray(order, dtype=np.int32)
-    rc = lib().lwso_ds_scale_down_old(n, len(order), R.ptr(reps), R.ptr(o),
-                                      R.ptr(np.ascontiguousarray(current, np.int32)),
-                                      R.ptr(np.ascontiguousarray(target, np.int32)), None)
+    cur = np.ascontiguousarray(current, dtype=np.int32)  # keep alive across the call
+    tgt = np.ascontiguousarray(target, dtype=np.int32)
+    rc = lib().lwso_ds_scale_down_old(n, len(order), R.ptr(reps), R.ptr(o), R.ptr(cur), R.ptr(tgt), None)
     if rc != 0:
         raise RuntimeError("lwso_ds_scale_down_old failed")
     return reps.reshape(len(order), n).tolist()

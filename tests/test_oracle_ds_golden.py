@@ -1,0 +1,241 @@
+"""Pins the DisaggregatedSet oracle (oracle/lwse_oracle_ds.c) to the reference's
+own vectors:
+  pkg/controllers/disaggregatedset/planner_test.go:106-505  22 exact sequences
+      (tests/golden/planner_sequences.json, extracted by extract_planner_vectors.py)
+  planner_test.go:507-672, :904-1055   completion + surge / unavailable invariants
+  planner_test.go:722-798              nil-when-done / abnormal-state vectors
+  executor_test.go:806-1014            scaleDownOld budget split (7 + 3 cases)
+  executor_test.go:685-804             extractRollingUpdateConfig percent scaling
+  executor_test.go:1151-1238           one ReconcileRollingUpdate call (3 rows)
+  executor_test.go:334-481             single-reconcile behaviours
+"""
+import json
+import os
+
+import pytest
+
+import oracle
+from lws_b200 import api, encoder
+from lws_b200 import records as R
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SEQ = json.load(open(os.path.join(HERE, "golden", "planner_sequences.json")))["cases"]
+
+
+def all_steps(initial_old, target, surge, unavail):
+    return oracle.ds_compute_all_steps(list(initial_old), list(target), list(surge), list(unavail))
+
+
+def completes(steps, target):
+    past, new = steps[-1]
+    return all(p == 0 for p in past) and new == list(target)
+
+
+@pytest.mark.parametrize("case", SEQ, ids=[c["name"] for c in SEQ])
+def test_exact_sequences(case):
+    surge = [c[0] for c in case["config"]]
+    unavail = [c[1] for c in case["config"]]
+    got = all_steps(case["source"], case["target"], surge, unavail)
+    assert [[p, n] for p, n in got] == case["steps"]
+
+
+N_ROLE = [  # planner_test.go:904-968
+    ([3, 3, 3], [3, 3, 3], [1, 1, 1], [0, 0, 0]), ([6, 3, 2], [6, 3, 2], [2, 1, 1], [0, 0, 0]),
+    ([4, 4, 4], [4, 4, 4], [2, 1, 3], [0, 0, 0]), ([2, 2, 2], [4, 4, 4], [1, 1, 1], [0, 0, 0]),
+    ([4, 4, 4], [2, 2, 2], [1, 1, 1], [0, 0, 0]), ([0, 0, 0], [3, 3, 3], [1, 1, 1], [0, 0, 0]),
+    ([4, 4, 4], [4, 4, 4], [0, 0, 0], [1, 1, 1]), ([4, 4, 4], [4, 4, 4], [1, 0, 2], [0, 1, 0]),
+    ([4, 4, 4, 4], [4, 4, 4, 4], [1, 1, 1, 1], [0, 0, 0, 0]), ([8, 4, 2, 1], [8, 4, 2, 1], [2, 2, 1, 1], [0, 0, 0, 0]),
+    ([1, 1, 1, 1], [3, 3, 3, 3], [1, 1, 1, 1], [0, 0, 0, 0]), ([5, 5, 5, 5], [2, 2, 2, 2], [1, 1, 1, 1], [0, 0, 0, 0]),
+    ([0, 0, 0, 0], [4, 4, 4, 4], [1, 1, 1, 1], [0, 0, 0, 0]),
+    ([5] * 5, [5] * 5, [1] * 5, [0] * 5), ([10, 5, 3, 2, 1], [10, 5, 3, 2, 1], [2, 2, 1, 1, 1], [0] * 5),
+    ([1] * 5, [2] * 5, [1] * 5, [0] * 5), ([6] * 5, [3] * 5, [1] * 5, [0] * 5), ([0] * 5, [5] * 5, [1] * 5, [0] * 5),
+    ([4, 4, 0], [4, 4, 4], [1, 1, 1], [0, 0, 0]), ([3, 3, 3, 0], [3, 3, 3, 3], [1] * 4, [0] * 4),
+    ([2, 2, 2, 2, 2, 0], [2] * 6, [1] * 6, [0] * 6),
+    ([4, 4, 4], [4, 4, 0], [1, 1, 1], [0, 0, 0]), ([3, 3, 3, 3], [3, 3, 3, 0], [1] * 4, [0] * 4),
+    ([10, 10, 10, 10, 0, 10], [10, 10, 10, 10, 10, 0], [1] * 6, [0] * 6),
+    ([10, 2], [6, 8], [2, 2], [0, 0]), ([10, 10], [4, 4], [2, 2], [0, 0]), ([8, 4], [3, 2], [1, 1], [0, 0]),
+    ([5, 2], [5, 2], [0, 0], [1, 1]),
+]
+
+
+@pytest.mark.parametrize("io,tg,su,un", N_ROLE)
+def test_n_role_rollout_completes(io, tg, su, un):
+    assert completes(all_steps(io, tg, su, un), tg)
+
+
+@pytest.mark.parametrize(
+    "io,tg,su",
+    [([3, 3, 3], [3, 3, 3], [1, 1, 1]), ([4] * 4, [4] * 4, [1] * 4), ([5] * 5, [5] * 5, [1] * 5),
+     ([10, 2], [6, 8], [2, 2]), ([10, 10], [4, 4], [2, 2]), ([8, 4], [3, 2], [1, 1])],
+)
+def test_n_role_surge_constraint(io, tg, su):  # planner_test.go:970-1012
+    for past, new in all_steps(io, tg, su, [0] * len(io)):
+        for i in range(len(tg)):
+            if new[i] == 0:
+                continue
+            assert past[i] + new[i] <= tg[i] + su[i]
+
+
+@pytest.mark.parametrize(
+    "io,tg,un", [([4, 4], [4, 4], [1, 1]), ([5, 2], [5, 2], [1, 1]), ([2, 5], [2, 5], [1, 1]), ([3, 3, 3], [3, 3, 3], [1, 1, 1])]
+)
+def test_n_role_unavailable_constraint(io, tg, un):  # planner_test.go:1014-1055
+    steps = all_steps(io, tg, [0] * len(io), un)
+    assert completes(steps, tg)
+    for past, new in steps:
+        for i in range(len(tg)):
+            if io[i] < tg[i]:
+                continue
+            assert past[i] + new[i] >= tg[i] - un[i]
+
+
+def test_unavailable_and_surge_priority():  # planner_test.go:507-672
+    def totals(steps):
+        return [sum(p) + sum(n) for p, n in steps]
+
+    s = all_steps([4, 4], [4, 4], [0, 0], [1, 1])
+    assert completes(s, [4, 4]) and min(totals(s)) < 8
+    s = all_steps([4, 4], [4, 4], [1, 1], [1, 1])
+    assert completes(s, [4, 4]) and min(totals(s)) >= 8
+    s = all_steps([6, 6], [6, 6], [2, 2], [0, 0])
+    assert completes(s, [6, 6]) and min(totals(s)) >= 12
+    s = all_steps([6, 6], [6, 6], [0, 0], [2, 2])
+    assert completes(s, [6, 6]) and min(totals(s)) < 12
+    s = all_steps([6, 6], [6, 6], [2, 2], [2, 2])
+    assert completes(s, [6, 6]) and min(totals(s)) >= 12
+    for cfg in (([1, 0], [0, 1]), ([0, 1], [1, 0])):
+        assert completes(all_steps([4, 4], [4, 4], *cfg), [4, 4])
+    for sp, sd in ((6, 2), (2, 6), (8, 4)):
+        assert completes(all_steps([sp, sd], [sp, sd], [1, 0], [0, 1]), [sp, sd])
+    assert completes(all_steps([2, 2], [4, 4], [0, 0], [1, 1]), [4, 4])
+    assert completes(all_steps([4, 4], [2, 2], [0, 0], [1, 1]), [2, 2])
+    assert completes(all_steps([0, 0], [4, 4], [0, 0], [1, 1]), [4, 4])
+    for size, un in ((4, 1), (6, 2), (10, 5)):
+        s = all_steps([size, size], [size, size], [0, 0], [un, un])
+        assert len(s) <= size * 4 and completes(s, [size, size])
+
+
+def test_next_step_nil_when_done_and_abnormal_state():  # planner_test.go:722-798
+    step = oracle.ds_compute_next_step
+    assert step([3, 3], [0, 0], [3, 3], [3, 3], [1, 1], [0, 0]) is None  # complete
+    assert step([0, 0], [0, 0], [0, 0], [0, 0], [1, 1], [0, 0]) is None  # totalSteps == 0
+    # correctAbnormalState: currentOld above initialOld is clamped first, new untouched
+    assert step([2, 2], [3, 2], [1, 1], [2, 2], [1, 1], [0, 0]) == ([2, 2], [1, 1])
+    # new at target → drain everything
+    assert step([3, 3], [2, 1], [3, 3], [3, 3], [1, 1], [0, 0]) == ([0, 0], [3, 3])
+
+
+SCALE_DOWN = [  # executor_test.go:806-918: (revisions oldest→newest, budget, expected)
+    ([(4, 4)], (2, 2), [(2, 2)]),
+    ([(2, 2), (2, 2)], (2, 2), [(2, 2), (0, 0)]),
+    ([(3, 2)], (1, 2), [(0, 0)]),
+    ([(6, 6)], (2, 2), [(4, 4)]),
+    ([(2, 2), (2, 2), (2, 2)], (4, 4), [(2, 2), (0, 0), (0, 0)]),
+    ([(1, 2), (3, 3)], (1, 1), [(1, 2), (2, 2)]),
+    ([(1, 1), (3, 3)], (2, 2), [(1, 1), (1, 1)]),
+]
+
+
+@pytest.mark.parametrize("revs,budget,want", SCALE_DOWN)
+def test_scale_down_old(revs, budget, want):
+    n = 2
+    current = [sum(r[i] for r in revs) for i in range(n)]
+    target = [current[i] - budget[i] for i in range(n)]
+    order = list(range(len(revs)))[::-1]  # newest first
+    got = oracle.ds_scale_down_old([list(r) for r in revs], order, current, target)
+    assert [tuple(r) for r in got] == want
+
+
+@pytest.mark.parametrize("budget,want", [((0, 1, 0), (4, 3)), ((1, 1, 0), (3, 3)), ((4, 0, 0), (0, 0))])
+def test_scale_down_old_with_missing_role(budget, want):  # executor_test.go:920-1014
+    current = [4, 4, 0]
+    target = [current[i] - budget[i] for i in range(3)]
+    got = oracle.ds_scale_down_old([[4, 4, -1]], [0], current, target)
+    assert tuple(got[0][:2]) == want
+
+
+def _ds(target=(4, 4), cfg=None):
+    roles = [api.DisaggregatedRoleSpec("prefill", target[0], cfg), api.DisaggregatedRoleSpec("decode", target[1], cfg)]
+    return api.DisaggregatedSet("test", roles=roles)
+
+
+def _child(role, rev, replicas, ts, initial=None, ready=None):
+    ann = {} if initial is None else {api.DSInitialReplicasAnnotationKey: str(initial)}
+    return api.ChildLWS(role, rev, replicas, replicas if ready is None else ready, ts, ann)
+
+
+@pytest.mark.parametrize(
+    "a,b,c,want",  # executor_test.go:1151-1238: target (4,4), default config, initial-replicas=2
+    [((2, 2), (2, 2), (0, 0), {"A": (2, 2), "B": (2, 2), "C": (1, 1)}),
+     (None, (2, 2), (2, 2), {"B": (2, 2), "C": (3, 3)}),
+     ((2, 2), (2, 2), (2, 2), {"A": (2, 2), "B": (1, 1), "C": (2, 2)})],
+)
+def test_reconcile_rolling_update_one_call(a, b, c, want):
+    children = []
+    for name, reps, ts in (("A", a, 1.0), ("B", b, 2.0), ("C", c, 3.0)):
+        if reps is None:
+            continue
+        initial = 2 if name != "C" else None
+        children += [_child("prefill", name, reps[0], ts, initial), _child("decode", name, reps[1], ts, initial)]
+    t = encoder.encode_ds([encoder.DsItem(_ds(), "C", children)])
+    ds_out, role_out, rr_out = oracle.sweep_ds(t.ds, t.roles, t.revroles)
+    assert ds_out[0]["flags"] & R.DOUT_ROLLING and ds_out[0]["flags"] & R.DOUT_STABLE
+    revs = t.old_revisions[0] + ["C"]
+    got = {rev: (int(rr_out[k * 2]), int(rr_out[k * 2 + 1])) for k, rev in enumerate(revs)}
+    assert got == want
+
+
+@pytest.mark.parametrize(
+    "surge,unavail,replicas,want",  # executor_test.go:685-804 (percent scaling, priority rule)
+    [("50%", 0, 4, (2, 0)), ("25%", 0, 4, (1, 0)), ("25%", "25%", 10, (3, 2)), ("100%", 0, 5, (5, 0)),
+     (0, 0, 4, (1, 0)), (0, 2, 4, (0, 2)), (3, 0, 4, (3, 0))],
+)
+def test_extract_rolling_update_config(surge, unavail, replicas, want):
+    """The config is only observable through the planner: compare with a run that is
+    handed the expected (surge, unavailable) directly."""
+    cfg = api.RollingUpdateConfiguration(maxSurge=surge, maxUnavailable=unavail)
+    ds = _ds((replicas, replicas), cfg)
+    children = [_child("prefill", "old", replicas, 1.0), _child("decode", "old", replicas, 1.0),
+                _child("prefill", "new", 0, 2.0), _child("decode", "new", 0, 2.0)]
+    t = encoder.encode_ds([encoder.DsItem(ds, "new", children)])
+    ds_out, role_out, _ = oracle.sweep_ds(t.ds, t.roles, t.revroles)
+    direct = oracle.ds_compute_next_step([replicas] * 2, [replicas] * 2, [0, 0], [replicas] * 2,
+                                         [want[0]] * 2, [want[1]] * 2)
+    assert ds_out[0]["flags"] & R.DOUT_STEP
+    assert [int(role_out[i]["next_old"]) for i in range(2)] == direct[0]
+    assert [int(role_out[i]["next_new"]) for i in range(2)] == direct[1]
+
+
+def test_reconciler_single_reconcile_behaviours():  # executor_test.go:334-481
+    # fully drained old revision is deleted
+    t = encoder.encode_ds([encoder.DsItem(_ds((2, 2)), "new", [
+        _child("prefill", "old", 0, 1.0), _child("decode", "old", 0, 1.0),
+        _child("prefill", "new", 2, 2.0), _child("decode", "new", 2, 2.0)])])
+    ds_out, _, rr = oracle.sweep_ds(t.ds, t.roles, t.revroles)
+    assert ds_out[0]["drained_revs"] == 1 and not ds_out[0]["flags"] & R.DOUT_ROLLING
+    # first reconcile of an update: no new revision yet → init, new LWS at 0
+    t = encoder.encode_ds([encoder.DsItem(_ds((2, 2)), "new", [
+        _child("prefill", "old", 2, 1.0), _child("decode", "old", 2, 1.0)])])
+    ds_out, _, rr = oracle.sweep_ds(t.ds, t.roles, t.revroles)
+    assert ds_out[0]["flags"] & R.DOUT_INIT and list(rr[2:4]) == [0, 0]
+    # no old scale-down while the new revision is not ready
+    t = encoder.encode_ds([encoder.DsItem(_ds((2, 2)), "new", [
+        _child("prefill", "old", 2, 1.0), _child("decode", "old", 2, 1.0),
+        _child("prefill", "new", 1, 2.0, ready=0), _child("decode", "new", 1, 2.0, ready=0)])])
+    ds_out, _, rr = oracle.sweep_ds(t.ds, t.roles, t.revroles)
+    assert not ds_out[0]["flags"] & R.DOUT_STABLE and list(rr) == [2, 2, 1, 1]
+    # old scales down once new is ready
+    t = encoder.encode_ds([encoder.DsItem(_ds((2, 2)), "new", [
+        _child("prefill", "old", 2, 1.0), _child("decode", "old", 2, 1.0),
+        _child("prefill", "new", 1, 2.0), _child("decode", "new", 1, 2.0)])])
+    ds_out, _, rr = oracle.sweep_ds(t.ds, t.roles, t.revroles)
+    assert ds_out[0]["flags"] & R.DOUT_STEP and list(rr) == [1, 1, 1, 1]
+
+
+def test_initial_replicas_annotation_rules():  # pkg/utils/disaggregatedset/utils_test.go:20-120
+    mk = lambda v: api.ChildLWS("r", "x", 3, annotations={} if v is None else {api.DSInitialReplicasAnnotationKey: v})
+    assert encoder.get_initial_replicas(mk(None)) == -1
+    assert encoder.get_initial_replicas(mk("")) == -1
+    assert encoder.get_initial_replicas(mk("abc")) == -1
+    assert encoder.get_initial_replicas(mk("5")) == 5
+    assert encoder.get_initial_replicas(mk("99999999999")) == -1
