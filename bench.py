@@ -136,7 +136,7 @@ def cpu_oracle_rate(t, threads, min_seconds=1.0, max_reps=50):
 
     lws_out = R.aligned_empty(len(t.lws), R.LWS_OUT)
     group_out = R.aligned_empty(len(t.groups), R.GROUP_OUT)
-    tab = R.LwsTables(R.ptr(t.lws), len(t.lws), R.ptr(t.groups), len(t.groups), R.ptr(t.pods), len(t.pods),
+    tab = R.LwsTables(R.ptr(t.lws), len(t.lws), R.ptr(t.groups), len(t.groups), R.ptr(t.pod_state), R.ptr(t.pod_ident), len(t.pod_state),
                       R.ptr(lws_out), R.ptr(group_out), None, t.flags)
     fn = oracle.lib().lwso_sweep_lws
     fn(C.byref(tab), R.ptr(t.nodes), len(t.nodes), threads)  # warm
@@ -163,7 +163,7 @@ def run_reference(args):
 
     lws_out = R.aligned_empty(len(t.lws), R.LWS_OUT)
     group_out = R.aligned_empty(len(t.groups), R.GROUP_OUT)
-    tab = R.LwsTables(R.ptr(t.lws), len(t.lws), R.ptr(t.groups), len(t.groups), R.ptr(t.pods), len(t.pods),
+    tab = R.LwsTables(R.ptr(t.lws), len(t.lws), R.ptr(t.groups), len(t.groups), R.ptr(t.pod_state), R.ptr(t.pod_ident), len(t.pod_state),
                       R.ptr(lws_out), R.ptr(group_out), None, t.flags)
     fn = oracle.lib().lwso_sweep_lws
     for _ in range(max(args.warmup, 1)):
@@ -207,11 +207,11 @@ def run_ours(args):
     t = make_tables(args, rank)
     eng = Engine(local_rank)
     eng.upload_nodes(t.nodes, t.n_domains)
-    n_lws, n_grp, n_pod = len(t.lws), len(t.groups), len(t.pods)
+    n_lws, n_grp, n_pod = len(t.lws), len(t.groups), len(t.pod_state)
     algo_bytes = t.algorithmic_bytes()
 
     # ---- resident copies, rotated so that the working set exceeds L2 ----
-    copies = max(2, int(np.ceil(2.5 * L2_BYTES / algo_bytes)) + 1)
+    copies = max(2, int(np.ceil(2.5 * L2_BYTES / algo_bytes)) + 1)  # bytes a sweep touches x copies > 2.5 x L2
 
     def up(a):
         return torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
@@ -219,7 +219,7 @@ def run_ours(args):
     sets = []
     for _ in range(copies):
         sets.append(dict(
-            lws=up(t.lws), grp=up(t.groups), pod=up(t.pods),
+            lws=up(t.lws), grp=up(t.groups), pst=up(t.pod_state), pid=up(t.pod_ident),
             lo=torch.empty(n_lws * R.LWS_OUT.itemsize, dtype=torch.uint8, device=dev),
             go=torch.empty(n_grp * R.GROUP_OUT.itemsize, dtype=torch.uint8, device=dev)))
     # time on the stream the kernels are launched on: the engine's own stream
@@ -228,7 +228,7 @@ def run_ours(args):
 
     def sweep(i, flags):
         s = sets[i % copies]
-        eng.sweep_lws_device(s["lws"], n_lws, s["grp"], n_grp, s["pod"], n_pod, s["lo"], s["go"], None,
+        eng.sweep_lws_device(s["lws"], n_lws, s["grp"], n_grp, s["pst"], s["pid"], n_pod, s["lo"], s["go"], None,
                              flags=flags, stream=sptr)
 
     def barrier():
@@ -251,10 +251,23 @@ def run_ours(args):
         ms = e0.elapsed_time(e1)
         return ms / steps, eng.launch_count - l0
 
+    SCAN_ONLY = R.SWEEP_SKIP_GROUP_PASS | R.SWEEP_SKIP_LWS_PASS
+    GROUP_ONLY = R.SWEEP_SKIP_POD_SCAN | R.SWEEP_SKIP_LWS_PASS
+    LWS_ONLY = R.SWEEP_SKIP_POD_SCAN | R.SWEEP_SKIP_GROUP_PASS
     with ClockSampler(local_rank) as clk:
         ms_step, launches = timed(t.flags, args.steps, max(args.warmup, 3))
-        # the dominant kernel alone (group/pod pass)
-        ms_group, _ = timed(t.flags | R.SWEEP_SKIP_LWS_PASS, args.steps, 3)
+        # each pass alone (same rotating inputs), for the per-kernel roofline
+        ms_scan, _ = timed(t.flags | SCAN_ONLY, args.steps, 3)
+        ms_group, _ = timed(t.flags | GROUP_ONLY, args.steps, 3)
+        ms_lws, _ = timed(t.flags | LWS_ONLY, args.steps, 3)
+        # keep the GPU under the same load long enough for nvidia-smi to sample clocks
+        t_end = time.perf_counter() + 1.0
+        i = 0
+        while time.perf_counter() < t_end:
+            for _ in range(200):
+                sweep(i, t.flags)
+                i += 1
+            torch.cuda.synchronize()
     clocks = clk.summary()
 
     # correctness of what was just timed: compare one resident result with a fresh host sweep
@@ -267,17 +280,17 @@ def run_ours(args):
 
     keep = []
     h = {}
-    for name, arr in (("lws", t.lws), ("groups", t.groups), ("pods", t.pods),
+    for name, arr in (("lws", t.lws), ("groups", t.groups), ("pst", t.pod_state), ("pid", t.pod_ident),
                       ("lo", R.aligned_empty(n_lws, R.LWS_OUT)), ("go", R.aligned_empty(n_grp, R.GROUP_OUT))):
         ten, view = pinned(arr)
         keep.append(ten)
         h[name] = view
     for _ in range(3):
-        eng.sweep_lws_host(h["lws"], h["groups"], h["pods"], flags=t.flags, out=(h["lo"], h["go"]))
+        eng.sweep_lws_host(h["lws"], h["groups"], h["pst"], h["pid"], flags=t.flags, out=(h["lo"], h["go"]))
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        eng.sweep_lws_host(h["lws"], h["groups"], h["pods"], flags=t.flags, out=(h["lo"], h["go"]))
+        eng.sweep_lws_host(h["lws"], h["groups"], h["pst"], h["pid"], flags=t.flags, out=(h["lo"], h["go"]))
     e2e_s = (time.perf_counter() - t0) / args.e2e_steps
     # the resident result must equal the host-path result
     same = (sets[0]["lo"].cpu().numpy().tobytes() == h["lo"].tobytes()
@@ -286,19 +299,28 @@ def run_ours(args):
         raise SystemExit("bench.py: resident and host-path results differ")
 
     # ---- max over ranks ----
-    stats = torch.tensor([ms_step, ms_group, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms_step, ms_group, e2e_s * 1e3, ms_scan, ms_lws], dtype=torch.float64, device=dev)
     groups = torch.tensor([float(n_grp)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(groups, op=dist.ReduceOp.SUM)
-    ms_step, ms_group, e2e_ms = [float(x) for x in stats.tolist()]
+    ms_step, ms_group, e2e_ms, ms_scan, ms_lws = [float(x) for x in stats.tolist()]
     total_groups = float(groups.item())
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        group_bytes = (n_grp * (R.GROUP_REC.itemsize + R.GROUP_OUT.itemsize) + n_pod * R.POD_REC.itemsize
-                       + n_lws * 16)
-        achieved = group_bytes / (ms_group * 1e-3) / 1e9
+        ev = t.event_pods()
+        words = (n_pod + 31) // 32
+        passes = {
+            # algorithmic bytes per launch: rows read once + rows written once
+            "pod_scan_kernel": (n_pod * 4 + 2 * words * 4, ms_scan),
+            "group_sweep_kernel": (n_grp * (R.GROUP_REC.itemsize + R.GROUP_OUT.itemsize) + n_lws * 16
+                                   + 2 * words * 4 + ev * (4 + R.POD_IDENT.itemsize), ms_group),
+            "lws_sweep_kernel": (n_lws * (R.LWS_REC.itemsize + R.LWS_OUT.itemsize) + n_grp * 4, ms_lws),
+        }
+        dom = max(passes, key=lambda k: passes[k][1])
+        dom_bytes, dom_ms = passes[dom]
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         cpu_rate, cpu_s, cpu_reps = cpu_oracle_rate(t, 1)
         line = {
             "metric": METRIC, "value": total_groups / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -308,13 +330,15 @@ def run_ours(args):
             "config": {**t.describe(), "parallelism": f"shard-by-uid x{world}",
                        "l2": f"inputs rotate over {copies} resident copies ({copies * algo_bytes / 1e6:.0f} MB > L2)"},
             "e2e": {"value": total_groups / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(t.lws.nbytes + t.groups.nbytes + t.pods.nbytes),
+                    "h2d_bytes_per_step": int(t.table_bytes()),
                     "d2h_bytes_per_step": int(n_lws * R.LWS_OUT.itemsize + n_grp * R.GROUP_OUT.itemsize),
                     "ms_per_step": e2e_ms, "api": "lwse_sweep_lws_host (pinned host tables)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "group_sweep_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "bytes_per_launch": int(group_bytes), "ms_per_launch": ms_group, "peak_source": peak_src},
+                         "bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms, "peak_source": peak_src,
+                         "passes": {k: {"bytes": int(v[0]), "ms": v[1], "gbs": v[0] / (v[1] * 1e-3) / 1e9,
+                                        "frac": v[0] / (v[1] * 1e-3) / 1e9 / peak} for k, v in passes.items()}},
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"full {t.profile.name} workload x{cpu_reps} ({cpu_s * 1e3:.1f} ms per sweep)"},
             "clocks": clocks,

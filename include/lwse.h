@@ -140,7 +140,7 @@ typedef struct lwse_group_rec {
   uint32_t wsts_uid_hash;     /* worker sts metadata.uid                          */
   uint32_t wsts_owner_uid_hash; /* controller ownerRef.uid of the worker sts      */
   uint32_t leader_node;       /* node-table row, LWSE_NONE, or LWSE_NODE_NOT_FOUND */
-  uint32_t pod_base;          /* first row of this group in the pod table         */
+  uint32_t pod_base;          /* first row of this group in the pod columns       */
   uint32_t pod_count;         /* pods carrying (set name, group index) labels     */
   uint32_t lws_index;         /* row of the owning object in the LWS table        */
   uint32_t flags;             /* LWSE_GRP_* */
@@ -161,12 +161,16 @@ typedef struct lwse_group_rec {
 #define LWSE_GRP_MISTAKEN_ANNOTATION (1u << 10)  /* leader carries leader-name annotation     */
 #define LWSE_GRP_REVISION_EXISTS (1u << 11)      /* ControllerRevision for leader's key found */
 
-/* One pod (16 B). */
-typedef struct lwse_pod_rec {
-  uint64_t rev_hash;       /* template-revision-hash label                        */
-  uint32_t owner_uid_hash; /* controller ownerRef.uid                             */
-  uint32_t bits;           /* LWSE_POD_* | node << LWSE_POD_NODE_SHIFT            */
-} lwse_pod_rec;
+/* Pods are stored column-split: the per-sweep-hot state word (4 B, changes
+ * with every status update) and the cold identity (12 B, fixed at pod
+ * creation, read only for pods that have a restart / deletion event). */
+typedef uint32_t lwse_pod_state; /* LWSE_POD_* | node << LWSE_POD_NODE_SHIFT */
+
+typedef struct lwse_pod_ident { /* 12 B */
+  uint32_t rev_hash_lo; /* template-revision-hash label (hash64, two halves) */
+  uint32_t rev_hash_hi;
+  uint32_t owner_uid_hash; /* controller ownerRef.uid */
+} lwse_pod_ident;
 
 #define LWSE_POD_PHASE_MASK 3u       /* 0 other, 1 Pending, 2 Running              */
 #define LWSE_POD_PHASE_PENDING 1u
@@ -270,13 +274,14 @@ typedef struct lwse_lws_tables {
   uint32_t n_lws;
   const lwse_group_rec* groups;
   uint32_t n_groups;
-  const lwse_pod_rec* pods;
+  const lwse_pod_state* pod_state; /* n_pods words  */
+  const lwse_pod_ident* pod_ident; /* n_pods rows   */
   uint64_t n_pods;
   lwse_lws_out* lws_out;     /* n_lws rows   */
   lwse_group_out* group_out; /* n_groups rows */
-  uint32_t* node_occupancy;  /* optional: n_nodes counters, pods per node (this
-                                call ADDS into the host buffer's zeroed copy);
-                                NULL to skip                                      */
+  uint32_t* node_occupancy;  /* optional: n_nodes counters, scheduled pods per node
+                                over the whole pod table (the call overwrites
+                                them); NULL to skip                               */
   uint32_t flags;            /* LWSE_SWEEP_* */
 } lwse_lws_tables;
 
@@ -284,7 +289,9 @@ typedef struct lwse_lws_tables {
                                      CREATE_PODGROUP are meaningful)              */
 #define LWSE_SWEEP_SKIP_GROUP_PASS (1u << 1) /* profiling: run only the LWS-level pass
                                                 (group_out must hold a previous result) */
-#define LWSE_SWEEP_SKIP_LWS_PASS (1u << 2)   /* profiling: run only the group/pod pass   */
+#define LWSE_SWEEP_SKIP_LWS_PASS (1u << 2)   /* profiling: skip the LWS-level pass       */
+#define LWSE_SWEEP_SKIP_POD_SCAN (1u << 3)   /* profiling: skip the pod-state scan (its
+                                                bitmaps must hold a previous result)     */
 
 typedef struct lwse_config {
   uint32_t abi_version; /* LWSE_ABI_VERSION */

@@ -11,7 +11,8 @@
 namespace lwse {
 // lwse_lws_kernels.cu
 int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
-                     int sm_count, cudaStream_t s, int* cuda_err);
+                     void* scratch, int sm_count, cudaStream_t s, int* cuda_err);
+size_t lws_sweep_scratch_bytes(uint64_t n_pods);
 // lwse_place_kernels.cu
 int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_domains,
                  const lwse_place_req* d_reqs, uint32_t n_reqs, const uint32_t* d_occupancy,
@@ -61,7 +62,7 @@ struct lwse_engine {
   DevBuf nodes;
   uint32_t n_nodes = 0, n_domains = 0;
   // staging for the *_host entry points
-  DevBuf lws, groups, pods, lws_out, group_out, occupancy;
+  DevBuf lws, groups, pod_state, pod_ident, lws_out, group_out, occupancy, scan_scratch;
   DevBuf place_reqs, place_out, place_occ, place_scratch;
   DevBuf ds, ds_roles, ds_revroles, ds_out, ds_role_out, ds_revrole_out;
   DevBuf sha_bytes, sha_offsets, sha_digests;
@@ -101,9 +102,10 @@ int check_lws_tables(const lwse_lws_tables* t) {
   if (!t) return LWSE_ERR_INVALID_ARG;
   if (t->n_lws && (!t->lws || !t->lws_out)) return LWSE_ERR_INVALID_ARG;
   if (t->n_groups && (!t->groups || !t->group_out)) return LWSE_ERR_INVALID_ARG;
-  if (t->n_pods && !t->pods) return LWSE_ERR_INVALID_ARG;
-  if (!aligned16(t->lws) || !aligned16(t->groups) || !aligned16(t->pods) || !aligned16(t->lws_out) ||
-      !aligned16(t->group_out))
+  if (t->n_pods && (!t->pod_state || !t->pod_ident)) return LWSE_ERR_INVALID_ARG;
+  if (t->n_pods > 0xFFFFFFFFull) return LWSE_ERR_UNSUPPORTED;  // pod_base / pod_count are 32-bit
+  if (!aligned16(t->lws) || !aligned16(t->groups) || !aligned16(t->lws_out) || !aligned16(t->group_out) ||
+      (reinterpret_cast<uintptr_t>(t->pod_state) & 3u) || (reinterpret_cast<uintptr_t>(t->pod_ident) & 3u))
     return LWSE_ERR_INVALID_ARG;
   return LWSE_OK;
 }
@@ -186,7 +188,8 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
   {
     DeviceGuard guard(e->device);
     cudaStreamSynchronize(e->stream);
-    DevBuf* bufs[] = {&e->nodes,      &e->lws,         &e->groups,     &e->pods,        &e->lws_out,
+    DevBuf* bufs[] = {&e->nodes,      &e->lws,         &e->groups,     &e->pod_state,   &e->pod_ident,
+                      &e->scan_scratch, &e->lws_out,
                       &e->group_out,  &e->occupancy,   &e->place_reqs, &e->place_out,   &e->place_occ,
                       &e->place_scratch, &e->ds,       &e->ds_roles,   &e->ds_revroles, &e->ds_out,
                       &e->ds_role_out, &e->ds_revrole_out, &e->sha_bytes, &e->sha_offsets, &e->sha_digests};
@@ -227,9 +230,12 @@ LWSE_API int lwse_sweep_lws_device(lwse_engine* e, const lwse_lws_tables* t, voi
   std::lock_guard<std::mutex> lock(e->mu);
   DeviceGuard guard(e->device);
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  // the scan bitmaps live in engine-owned scratch; it only grows (a growth is a
+  // cudaMalloc, so size it with one warm-up call before capturing a graph)
+  LWSE_CUDA(e, e->scan_scratch.reserve(lwse::lws_sweep_scratch_bytes(t->n_pods)));
   int cuda_err = 0;
   int launched = lwse::launch_lws_sweep(t, (const lwse_node_rec*)e->nodes.p, e->n_nodes,
-                                        e->sm_count, s, &cuda_err);
+                                        e->scan_scratch.p, e->sm_count, s, &cuda_err);
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
   return LWSE_OK;
@@ -244,33 +250,39 @@ LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* h) {
   cudaStream_t s = e->stream;
   const size_t b_lws = (size_t)h->n_lws * sizeof(lwse_lws_rec);
   const size_t b_grp = (size_t)h->n_groups * sizeof(lwse_group_rec);
-  const size_t b_pod = (size_t)h->n_pods * sizeof(lwse_pod_rec);
+  const size_t b_pst = (size_t)h->n_pods * sizeof(lwse_pod_state);
+  const size_t b_pid = (size_t)h->n_pods * sizeof(lwse_pod_ident);
   const size_t b_lo = (size_t)h->n_lws * sizeof(lwse_lws_out);
   const size_t b_go = (size_t)h->n_groups * sizeof(lwse_group_out);
   LWSE_CUDA(e, e->lws.reserve(b_lws + 16));
   LWSE_CUDA(e, e->groups.reserve(b_grp + 16));
-  LWSE_CUDA(e, e->pods.reserve(b_pod + 16));
+  LWSE_CUDA(e, e->pod_state.reserve(b_pst + 16));
+  LWSE_CUDA(e, e->pod_ident.reserve(b_pid + 16));
+  LWSE_CUDA(e, e->scan_scratch.reserve(lwse::lws_sweep_scratch_bytes(h->n_pods)));
   LWSE_CUDA(e, e->lws_out.reserve(b_lo + 16));
   LWSE_CUDA(e, e->group_out.reserve(b_go + 16));
   const bool want_occ = h->node_occupancy != nullptr && e->n_nodes > 0;
   if (want_occ) {
     LWSE_CUDA(e, e->occupancy.reserve((size_t)e->n_nodes * 4 + 16));
-    LWSE_CUDA(e, cudaMemsetAsync(e->occupancy.p, 0, (size_t)e->n_nodes * 4, s));
   }
   if (b_lws) LWSE_CUDA(e, cudaMemcpyAsync(e->lws.p, h->lws, b_lws, cudaMemcpyHostToDevice, s));
   if (b_grp) LWSE_CUDA(e, cudaMemcpyAsync(e->groups.p, h->groups, b_grp, cudaMemcpyHostToDevice, s));
-  if (b_pod) LWSE_CUDA(e, cudaMemcpyAsync(e->pods.p, h->pods, b_pod, cudaMemcpyHostToDevice, s));
+  if (b_pst) {
+    LWSE_CUDA(e, cudaMemcpyAsync(e->pod_state.p, h->pod_state, b_pst, cudaMemcpyHostToDevice, s));
+    LWSE_CUDA(e, cudaMemcpyAsync(e->pod_ident.p, h->pod_ident, b_pid, cudaMemcpyHostToDevice, s));
+  }
 
   lwse_lws_tables d = *h;
   d.lws = (const lwse_lws_rec*)e->lws.p;
   d.groups = (const lwse_group_rec*)e->groups.p;
-  d.pods = (const lwse_pod_rec*)e->pods.p;
+  d.pod_state = (const lwse_pod_state*)e->pod_state.p;
+  d.pod_ident = (const lwse_pod_ident*)e->pod_ident.p;
   d.lws_out = (lwse_lws_out*)e->lws_out.p;
   d.group_out = (lwse_group_out*)e->group_out.p;
   d.node_occupancy = want_occ ? (uint32_t*)e->occupancy.p : nullptr;
   int cuda_err = 0;
-  int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes, e->sm_count,
-                                        s, &cuda_err);
+  int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes,
+                                        e->scan_scratch.p, e->sm_count, s, &cuda_err);
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
 

@@ -1,35 +1,100 @@
-// LWS sweep kernels (sm_100a): one pass over the group + pod tables, then one
-// pass over the LWS table.
+// LWS sweep kernels (sm_100a).  One sweep = three launches on one stream:
 //
-//   group_sweep_kernel<W>  one W-lane tile per pod group.  Streams the group's
-//                          pod rows with 128-bit loads (lane i takes pods i,
-//                          i+W, …), folds the per-pod restart predicate
-//                          (pod_controller.go:204-295,338-362) into a flag word
-//                          and reduces it across the tile with redux.sync
-//                          (__reduce_or_sync / __reduce_min_sync), then
-//                          evaluates the per-group state bits
-//                          (leaderworkerset_controller.go:608-638, :433-476)
-//                          and the leader pod's worker-sts gating
-//                          (pod_controller.go:100-198).  16 B out per group.
-//   lws_sweep_kernel<W>    one W-lane tile per LeaderWorkerSet.  Lanes stride
-//                          over the object's group_out flag words; counters via
-//                          redux.sync; rollingUpdateParameters' five cases, the
-//                          partition walk (:643-673) done as three reductions
-//                          instead of three loops.  32 B out per object.
+//   pod_scan_kernel<U>   pod-centric streaming pass over the 4-byte pod state
+//                        column: every lane takes U pods with coalesced loads
+//                        (all U loads in flight before the first use), derives
+//                        "Pending" (pod_controller.go:356) and "has a restart or
+//                        deletion event" (pod_utils.go:29-50) per pod and packs
+//                        them with __ballot_sync into two bitmaps (1 bit / pod).
+//                        No dependence on group rows → pure HBM streaming.
+//   group_sweep_kernel   one lane per pod group.  Reads its 64-byte group row,
+//                        the first 16 bytes of its owner row and the bitmap words
+//                        of its pod range; only pods whose event bit is set are
+//                        visited individually (state word + 12-byte identity row:
+//                        workerPodBelongsToLeader, pod_controller.go:268-295).
+//                        Emits the per-replica state bits
+//                        (leaderworkerset_controller.go:608-638, :433-476), the
+//                        restart verdict (pod_controller.go:204-266) and the
+//                        leader pod's worker-sts gating (:100-198).  16 B out.
+//   lws_sweep_kernel<W>  one W-lane tile per LeaderWorkerSet over its groups'
+//                        flag words: counters via redux.sync, the five cases of
+//                        rollingUpdateParameters, the partition walk (:643-673)
+//                        as three reductions.  32 B out per object.
 //
-// Both kernels are pure integer/compare work bound by HBM traffic: see
-// DESIGN.md for the algorithmic bytes and the roofline.
+// All three are integer/compare kernels bound by HBM traffic.
 #include "lwse_device.cuh"
 
 namespace lwse {
 
+// --------------------------------------------------------------------------
+// pod scan
+// --------------------------------------------------------------------------
+struct PodScanArgs {
+  const uint32_t* state;
+  uint32_t* pending_bits;  // ceil(n_pods / 32) words
+  uint32_t* event_bits;
+  uint32_t* occupancy;  // nullable: scheduled pods per node
+  uint64_t n_pods;
+  uint32_t n_nodes;
+};
+
+__device__ __forceinline__ bool pod_has_event(uint32_t bits) {
+  const uint32_t phase = bits & LWSE_POD_PHASE_MASK;
+  // ContainerRestarted (pod_utils.go:29-45) || PodDeleted (:48)
+  return ((phase - 1u) < 2u && (bits & LWSE_POD_ANY_RESTART)) || (bits & LWSE_POD_DELETING);
+}
+
+template <int U, bool OCC>
+__global__ void __launch_bounds__(256) pod_scan_kernel(const PodScanArgs a) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warp = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5);
+  const uint64_t n_warps = (uint64_t)gridDim.x * 8u;
+  const uint64_t n_words = (a.n_pods + 31u) >> 5;
+  constexpr uint64_t kPodsPerChunk = 32ull * U;
+  for (uint64_t base = warp * kPodsPerChunk; base < a.n_pods; base += n_warps * kPodsPerChunk) {
+    uint32_t bits[U];
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+      const uint64_t idx = base + (uint64_t)j * 32u + lane;
+      bits[j] = idx < a.n_pods ? __ldcs(a.state + idx) : 0u;  // streaming: evict-first
+    }
+    uint32_t my_pending = 0, my_event = 0;
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+      const uint32_t b = bits[j];
+      const uint32_t wp = __ballot_sync(0xFFFFFFFFu, (b & LWSE_POD_PHASE_MASK) == LWSE_POD_PHASE_PENDING);
+      const uint32_t we = __ballot_sync(0xFFFFFFFFu, pod_has_event(b));
+      if (lane == (uint32_t)j) {
+        my_pending = wp;
+        my_event = we;
+      }
+      if (OCC) {
+        if (b & LWSE_POD_SCHEDULED) {
+          const uint32_t node = b >> LWSE_POD_NODE_SHIFT;
+          if (node < a.n_nodes) atomicAdd(a.occupancy + node, 1u);
+        }
+      }
+    }
+    const uint64_t w = (base >> 5) + lane;
+    if (lane < (uint32_t)U && w < n_words) {
+      a.pending_bits[w] = my_pending;
+      a.event_bits[w] = my_event;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------
+// group pass
+// --------------------------------------------------------------------------
 struct GroupSweepArgs {
   const lwse_lws_rec* lws;
   const lwse_group_rec* groups;
-  const lwse_pod_rec* pods;
+  const uint32_t* pod_state;
+  const lwse_pod_ident* pod_ident;
+  const uint32_t* pending_bits;
+  const uint32_t* event_bits;
   const lwse_node_rec* nodes;
   lwse_group_out* out;
-  uint32_t* occupancy;  // nullable
   uint64_t n_pods;
   uint32_t n_lws;
   uint32_t n_groups;
@@ -37,89 +102,22 @@ struct GroupSweepArgs {
   uint32_t sweep_flags;
 };
 
-// bits of the per-lane accumulator
-constexpr uint32_t ACC_PENDING = 1u << 0;
-constexpr uint32_t ACC_TRIG_DELETE = 1u << 1;    // trigger, leader not yet deleting → Delete()
-constexpr uint32_t ACC_TRIG_DELETING = 1u << 2;  // trigger, leader already deleting
-constexpr uint32_t ACC_ERROR = 1u << 3;          // worker name unparsable
-constexpr uint32_t ACC_LEADER_TRIG = 1u << 4;    // the leader pod's own event triggered
-
-struct GroupCtx {
-  uint32_t leader_rev_lo, leader_rev_hi;
-  uint32_t leader_uid, wsts_uid;
-  bool policy_on;     // RecreateGroupOnPodRestart | RecreateGroupAfterStart
-  bool leader_found;  // Get(leader by parsed name) succeeds (pod_controller.go:233)
-  bool wsts_chain_ok; // sts found ∧ owned by this leader (:281-294)
-  bool leader_deleting;
-};
-
-__device__ __forceinline__ void fold_pod(const uint4 p, const uint32_t idx, const GroupCtx& c,
-                                         uint32_t& acc, uint32_t& first, uint32_t* occupancy,
-                                         uint32_t n_nodes) {
-  const uint32_t bits = p.w;
-  const uint32_t phase = bits & LWSE_POD_PHASE_MASK;
-  if (phase == LWSE_POD_PHASE_PENDING) acc |= ACC_PENDING;  // pendingPodsInGroup :356
-  if (occupancy != nullptr && (bits & LWSE_POD_SCHEDULED)) {
-    const uint32_t node = bits >> LWSE_POD_NODE_SHIFT;
-    if (node < n_nodes) atomicAdd(occupancy + node, 1u);
-  }
-  // ContainerRestarted (pod_utils.go:29-45) || PodDeleted (:48)
-  const bool restarted = (phase - 1u) < 2u && (bits & LWSE_POD_ANY_RESTART);
-  const bool ev = restarted || (bits & LWSE_POD_DELETING);
-  if (ev && c.policy_on) {
-    bool cand, deleting;
-    if (bits & LWSE_POD_IS_LEADER) {
-      cand = true;  // leader = pod (:251)
-      deleting = bits & LWSE_POD_DELETING;
-    } else if (!(bits & LWSE_POD_NAME_OK)) {
-      acc |= ACC_ERROR;  // :230
-      return;
-    } else {
-      const uint32_t kind = (bits & LWSE_POD_OWNER_MASK) >> LWSE_POD_OWNER_SHIFT;
-      const bool name_match = bits & LWSE_POD_OWNER_NAME_MATCH;
-      // workerPodBelongsToLeader :268-295
-      const bool belongs = name_match && ((kind == 1u && p.z == c.leader_uid) ||
-                                          (kind == 2u && p.z == c.wsts_uid && c.wsts_chain_ok));
-      cand = c.leader_found && p.x == c.leader_rev_lo && p.y == c.leader_rev_hi && belongs;
-      deleting = c.leader_deleting;
-    }
-    if (cand) {
-      acc |= deleting ? ACC_TRIG_DELETING : ACC_TRIG_DELETE;
-      if (bits & LWSE_POD_IS_LEADER) acc |= ACC_LEADER_TRIG;
-      first = min(first, idx);
-    }
-  }
+// bits [lo, hi) of a 32-bit word, 0 <= lo <= hi <= 32
+__device__ __forceinline__ uint32_t bit_range(uint32_t lo, uint32_t hi) {
+  const uint32_t upto_hi = hi >= 32u ? 0xFFFFFFFFu : ((1u << hi) - 1u);
+  return upto_hi & ~((1u << lo) - 1u) & (lo >= 32u ? 0u : 0xFFFFFFFFu);
 }
 
-template <int W>
 __global__ void __launch_bounds__(256) group_sweep_kernel(const GroupSweepArgs a) {
-  constexpr uint32_t kTilesPerBlock = 256 / W;
-  const uint32_t lane = threadIdx.x & (W - 1);
-  const uint32_t n_tiles = gridDim.x * kTilesPerBlock;
-  uint32_t g = blockIdx.x * kTilesPerBlock + threadIdx.x / W;
-  if (g >= a.n_groups) return;  // whole tiles leave together
-
-  const uint4* grows = reinterpret_cast<const uint4*>(a.groups);
-  uint4 ra = ldg_stream(grows + 4ull * g + 0), rb = ldg_stream(grows + 4ull * g + 1),
-        rc = ldg_stream(grows + 4ull * g + 2), rd = ldg_stream(grows + 4ull * g + 3);
-
-  while (true) {
-    // ---- unpack the current row, prefetch the next one ----
-    const uint32_t g_next = g + n_tiles;
-    const bool has_next = g_next < a.n_groups;
-    const uint4 ca = ra, cb = rb, cc = rc, cd = rd;
-    if (has_next) {
-      ra = ldg_stream(grows + 4ull * g_next + 0);
-      rb = ldg_stream(grows + 4ull * g_next + 1);
-      rc = ldg_stream(grows + 4ull * g_next + 2);
-      rd = ldg_stream(grows + 4ull * g_next + 3);
-    }
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < a.n_groups; g += stride) {
+    const uint4* row = reinterpret_cast<const uint4*>(a.groups + g);
+    const uint4 ca = ldg_cached(row + 0), cb = ldg_cached(row + 1), cc = ldg_cached(row + 2),
+                cd = ldg_cached(row + 3);
     const uint32_t pod_base = cc.z, pod_count = cc.w, lws_index = cd.x, gflags = cd.y;
-    const bool bad = lws_index >= a.n_lws || (uint64_t)pod_base + pod_count > a.n_pods;
-
     uint32_t oflags = 0, first_out = LWSE_NONE, domain = LWSE_NONE;
     int32_t worker_replicas = 0;
-    if (bad) {
+    if (lws_index >= a.n_lws || (uint64_t)pod_base + pod_count > a.n_pods) {
       oflags = LWSE_GOUT_BAD_TABLE;
     } else {
       // owner row: only its first 16 bytes (rev_hash, size, flags)
@@ -127,49 +125,68 @@ __global__ void __launch_bounds__(256) group_sweep_kernel(const GroupSweepArgs a
       const int32_t size = (int32_t)L.z;
       const uint32_t lflags = L.w;
       const uint32_t policy = (lflags & LWSE_LWS_RESTART_MASK) >> LWSE_LWS_RESTART_SHIFT;
+      const bool policy_on = policy == LWSE_RESTART_ON_POD_RESTART || policy == LWSE_RESTART_AFTER_START;
 
-      GroupCtx c;
-      c.leader_rev_lo = ca.x;
-      c.leader_rev_hi = ca.y;
-      c.leader_uid = cb.z;
-      c.wsts_uid = cb.w;
-      c.policy_on = policy == LWSE_RESTART_ON_POD_RESTART || policy == LWSE_RESTART_AFTER_START;
-      c.leader_found = (gflags & (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH)) ==
-                       (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH);
-      constexpr uint32_t kChain =
-          LWSE_GRP_WSTS_FOUND | LWSE_GRP_WSTS_OWNER_IS_POD | LWSE_GRP_WSTS_OWNER_NAME_MATCH;
-      c.wsts_chain_ok = (gflags & kChain) == kChain && cc.x == cb.z;  // sts ownerRef.uid == leader.uid
-      c.leader_deleting = gflags & LWSE_GRP_POD_DELETING;
-
-      // ---- stream the pod rows: two 128-bit loads in flight per lane ----
-      const uint4* prows = reinterpret_cast<const uint4*>(a.pods) + pod_base;
-      uint32_t acc = 0, first = LWSE_NONE;
-      for (uint32_t i = lane; i < pod_count; i += 2 * W) {
-        const uint32_t j = i + W;
-        const bool two = j < pod_count;
-        const uint4 p0 = ldg_stream(prows + i);
-        uint4 p1 = make_uint4(0, 0, 0, 0);
-        if (two) p1 = ldg_stream(prows + j);
-        fold_pod(p0, i, c, acc, first, a.occupancy, a.n_nodes);
-        if (two) fold_pod(p1, j, c, acc, first, a.occupancy, a.n_nodes);
+      // ---- pendingPodsInGroup :338-362 from the pending bitmap ----
+      const uint32_t pod_end = pod_base + pod_count;  // <= n_pods < 2^32 (checked by the entry points)
+      const uint32_t w_first = pod_base >> 5, w_last = pod_count ? ((pod_end - 1u) >> 5) : w_first;
+      bool any_pending = false, any_event = false;
+      if (pod_count) {
+        for (uint32_t w = w_first; w <= w_last; w++) {
+          const uint32_t lo = w == w_first ? (pod_base & 31u) : 0u;
+          const uint32_t hi = w == w_last ? (((pod_end - 1u) & 31u) + 1u) : 32u;
+          const uint32_t m = bit_range(lo, hi);
+          any_pending |= (__ldg(a.pending_bits + w) & m) != 0u;
+          any_event |= (__ldg(a.event_bits + w) & m) != 0u;
+        }
       }
-      acc = tile_or<W>(acc);
-      const bool any_trig = acc & (ACC_TRIG_DELETE | ACC_TRIG_DELETING);
-      if (any_trig) first = tile_min<W>(first);  // tile-uniform branch
-
-      // pendingPodsInGroup :338-362
-      const bool pending = (uint32_t)size != pod_count || (acc & ACC_PENDING);
+      const bool pending = (uint32_t)size != pod_count || any_pending;
+      if (pending) oflags |= LWSE_GOUT_PENDING;
       // :222 skip when pending ∧ (AfterStart ∨ annotation)
       const bool suppressed =
           pending && (policy == LWSE_RESTART_AFTER_START || (lflags & LWSE_LWS_RECREATE_AFTER_START_ANNOT));
-      if (pending) oflags |= LWSE_GOUT_PENDING;
+
+      // ---- handleRestartPolicy :204-266 for the pods that have an event ----
       bool leader_deleted = false;
-      if (!suppressed) {
-        if (acc & ACC_TRIG_DELETE) oflags |= LWSE_GOUT_DELETE_LEADER;
-        if (acc & ACC_TRIG_DELETING) oflags |= LWSE_GOUT_LEADER_DELETING;
-        if (acc & ACC_ERROR) oflags |= LWSE_GOUT_RESTART_ERROR;
-        if (any_trig) first_out = first;
-        leader_deleted = acc & ACC_LEADER_TRIG;
+      if (any_event && policy_on && !suppressed) {
+        const bool leader_found = (gflags & (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH)) ==
+                                  (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH);  // :233
+        constexpr uint32_t kChain =
+            LWSE_GRP_WSTS_FOUND | LWSE_GRP_WSTS_OWNER_IS_POD | LWSE_GRP_WSTS_OWNER_NAME_MATCH;
+        const bool wsts_chain_ok = (gflags & kChain) == kChain && cc.x == cb.z;  // sts owner uid == leader uid
+        for (uint32_t w = w_first; w <= w_last; w++) {
+          const uint32_t lo = w == w_first ? (pod_base & 31u) : 0u;
+          const uint32_t hi = w == w_last ? (((pod_end - 1u) & 31u) + 1u) : 32u;
+          uint32_t m = __ldg(a.event_bits + w) & bit_range(lo, hi);
+          while (m) {
+            const uint32_t bit = __ffs(m) - 1u;
+            m &= m - 1u;
+            const uint32_t p = (w << 5) + bit;  // pod row, ascending
+            const uint32_t bits = __ldg(a.pod_state + p);
+            bool cand, deleting;
+            if (bits & LWSE_POD_IS_LEADER) {
+              cand = true;  // leader = pod (:251)
+              deleting = bits & LWSE_POD_DELETING;
+            } else if (!(bits & LWSE_POD_NAME_OK)) {
+              oflags |= LWSE_GOUT_RESTART_ERROR;  // :230
+              continue;
+            } else {
+              const lwse_pod_ident id = a.pod_ident[p];
+              const uint32_t kind = (bits & LWSE_POD_OWNER_MASK) >> LWSE_POD_OWNER_SHIFT;
+              // workerPodBelongsToLeader :268-295
+              const bool belongs = (bits & LWSE_POD_OWNER_NAME_MATCH) &&
+                                   ((kind == 1u && id.owner_uid_hash == cb.z) ||
+                                    (kind == 2u && id.owner_uid_hash == cb.w && wsts_chain_ok));
+              cand = leader_found && id.rev_hash_lo == ca.x && id.rev_hash_hi == ca.y && belongs;  // :239
+              deleting = gflags & LWSE_GRP_POD_DELETING;
+            }
+            if (cand) {
+              oflags |= deleting ? LWSE_GOUT_LEADER_DELETING : LWSE_GOUT_DELETE_LEADER;  // :255 / :259
+              if (bits & LWSE_POD_IS_LEADER) leader_deleted = true;
+              if (first_out == LWSE_NONE) first_out = p - pod_base;
+            }
+          }
+        }
       }
 
       // ---- per-replica state bits (consumed by lws_sweep_kernel) ----
@@ -228,11 +245,7 @@ __global__ void __launch_bounds__(256) group_sweep_kernel(const GroupSweepArgs a
         worker_replicas = size - 1;  // :437; ordinals start at 1 (:440)
       }
     }
-    if (lane == 0)
-      stg_stream(a.out + g, make_uint4(oflags, first_out, (uint32_t)worker_replicas, domain));
-
-    if (!has_next) break;
-    g = g_next;
+    stg_stream(a.out + g, make_uint4(oflags, first_out, (uint32_t)worker_replicas, domain));
   }
 }
 
@@ -446,24 +459,14 @@ static int pick_tile(uint64_t items, uint64_t owners) {
   return w;
 }
 
-// Persistent-style grids: exactly as many CTAs as are resident at once
-// (SM count x occupancy), each tile striding over its share of the rows.
+// Persistent-style grids: as many CTAs as are resident at once (SM count x
+// occupancy), each thread/tile striding over its share of the rows.
 template <typename K>
 static uint32_t resident_ctas(K kernel, int sm_count) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1)
     per_sm = 4;
   return (uint32_t)sm_count * (uint32_t)per_sm;
-}
-
-template <int W>
-static cudaError_t launch_group(const GroupSweepArgs& a, int sm_count, cudaStream_t s) {
-  constexpr uint32_t kTilesPerBlock = 256 / W;
-  static uint32_t resident = 0;
-  if (resident == 0) resident = resident_ctas(group_sweep_kernel<W>, sm_count);
-  const uint32_t want = (a.n_groups + kTilesPerBlock - 1) / kTilesPerBlock;
-  group_sweep_kernel<W><<<want < resident ? want : resident, 256, 0, s>>>(a);
-  return cudaGetLastError();
 }
 
 template <int W>
@@ -476,27 +479,58 @@ static cudaError_t launch_lws(const LwsSweepArgs& a, int sm_count, cudaStream_t 
   return cudaGetLastError();
 }
 
-// Returns the number of kernels launched (>=0) or a negative cudaError_t.
+constexpr int kScanUnroll = 8;  // pods per lane per chunk: 8 x 128 B = 1 KB in flight per warp
+
+size_t lws_sweep_scratch_bytes(uint64_t n_pods) {
+  const uint64_t words = (n_pods + 31u) / 32u;
+  return (size_t)(2 * words * sizeof(uint32_t) + 256);
+}
+
+// Returns the number of kernels launched (>=0) or -1 with *cuda_err set.
+// scratch: lws_sweep_scratch_bytes(n_pods) bytes of device memory.
 int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
-                     int sm_count, cudaStream_t s, int* cuda_err) {
+                     void* scratch, int sm_count, cudaStream_t s, int* cuda_err) {
   *cuda_err = 0;
   int launches = 0;
   cudaError_t e = cudaSuccess;
-  if (t->n_groups && !(t->flags & LWSE_SWEEP_SKIP_GROUP_PASS)) {
-    GroupSweepArgs a{t->lws,        t->groups,  t->pods,  d_nodes,     t->group_out, t->node_occupancy,
-                     t->n_pods,     t->n_lws,   t->n_groups, n_nodes, t->flags};
-    switch (pick_tile(t->n_pods, t->n_groups)) {
-      case 1: e = launch_group<1>(a, sm_count, s); break;
-      case 2: e = launch_group<2>(a, sm_count, s); break;
-      case 4: e = launch_group<4>(a, sm_count, s); break;
-      case 8: e = launch_group<8>(a, sm_count, s); break;
-      case 16: e = launch_group<16>(a, sm_count, s); break;
-      default: e = launch_group<32>(a, sm_count, s); break;
+  const uint64_t words = (t->n_pods + 31u) / 32u;
+  uint32_t* pending_bits = static_cast<uint32_t*>(scratch);
+  uint32_t* event_bits = pending_bits + ((words + 31u) & ~(uint64_t)31u);
+  const bool group_pass = t->n_groups && !(t->flags & LWSE_SWEEP_SKIP_GROUP_PASS);
+
+  if (t->n_pods && (t->n_groups || t->node_occupancy) && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN)) {
+    if (t->node_occupancy) {
+      e = cudaMemsetAsync(t->node_occupancy, 0, (size_t)n_nodes * sizeof(uint32_t), s);
+      if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
     }
-    if (e != cudaSuccess) {
-      *cuda_err = (int)e;
-      return -1;
+    PodScanArgs a{t->pod_state, pending_bits, event_bits, t->node_occupancy, t->n_pods, n_nodes};
+    static uint32_t resident = 0, resident_occ = 0;
+    if (resident == 0) {
+      resident = resident_ctas(pod_scan_kernel<kScanUnroll, false>, sm_count);
+      resident_occ = resident_ctas(pod_scan_kernel<kScanUnroll, true>, sm_count);
     }
+    const uint64_t chunks = (t->n_pods + 32ull * kScanUnroll - 1) / (32ull * kScanUnroll);
+    const uint64_t want = (chunks + 7) / 8;
+    if (t->node_occupancy) {
+      const uint32_t grid = (uint32_t)(want < resident_occ ? want : resident_occ);
+      pod_scan_kernel<kScanUnroll, true><<<grid, 256, 0, s>>>(a);
+    } else {
+      const uint32_t grid = (uint32_t)(want < resident ? want : resident);
+      pod_scan_kernel<kScanUnroll, false><<<grid, 256, 0, s>>>(a);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
+    launches++;
+  }
+  if (group_pass) {
+    GroupSweepArgs a{t->lws,   t->groups, t->pod_state, t->pod_ident, pending_bits, event_bits, d_nodes,
+                     t->group_out, t->n_pods, t->n_lws, t->n_groups, n_nodes, t->flags};
+    static uint32_t resident = 0;
+    if (resident == 0) resident = resident_ctas(group_sweep_kernel, sm_count);
+    const uint32_t want = (t->n_groups + 255u) / 256u;
+    group_sweep_kernel<<<want < resident ? want : resident, 256, 0, s>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
     launches++;
   }
   if (t->n_lws && !(t->flags & LWSE_SWEEP_SKIP_LWS_PASS)) {
@@ -509,10 +543,7 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
       case 16: e = launch_lws<16>(a, sm_count, s); break;
       default: e = launch_lws<32>(a, sm_count, s); break;
     }
-    if (e != cudaSuccess) {
-      *cuda_err = (int)e;
-      return -1;
-    }
+    if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
     launches++;
   }
   return launches;

@@ -92,7 +92,8 @@ class Cluster:
 class LwsTables:
     lws: np.ndarray
     groups: np.ndarray
-    pods: np.ndarray
+    pod_state: np.ndarray
+    pod_ident: np.ndarray
     nodes: np.ndarray
     n_domains: int
     domain_values: list  # domain id → topology label value
@@ -100,6 +101,12 @@ class LwsTables:
     # bookkeeping for reading results back by name
     lws_names: list
     group_pod_names: list  # per group row: names of its pod rows
+
+
+def _state_column(pod_rows) -> np.ndarray:
+    col = R.aligned_empty(len(pod_rows), R.POD_STATE)
+    col[:] = np.array([r[2] for r in pod_rows], dtype=np.uint32)
+    return col
 
 
 def encode_nodes(nodes: Iterable[api.Node], topology_key: Optional[str]):
@@ -332,7 +339,10 @@ def encode_lws(items: Iterable[LwsItem], cluster: Cluster, topology_key: Optiona
     return LwsTables(
         lws=table(lws_rows, R.LWS_REC),
         groups=table(group_rows, R.GROUP_REC),
-        pods=table(pod_rows, R.POD_REC),
+        pod_state=_state_column(pod_rows),
+        pod_ident=R.pod_ident_table(
+            np.array([r[0] for r in pod_rows], dtype=np.uint64), np.array([r[1] for r in pod_rows], dtype=np.uint32)
+        ),
         nodes=node_rec,
         n_domains=len(domain_values),
         domain_values=domain_values,

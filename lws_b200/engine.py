@@ -124,9 +124,10 @@ class Engine:
         self.n_nodes, self.n_domains = len(nodes), n_domains
 
     # -------------------------------------------------------------- LWS sweep
-    def sweep_lws_host(self, lws, groups, pods, flags=0, want_occupancy=False, out=None):
+    def sweep_lws_host(self, lws, groups, pod_state, pod_ident, flags=0, want_occupancy=False, out=None):
         """Host tables in → (lws_out, group_out, occupancy|None) host tables out."""
-        assert lws.dtype == R.LWS_REC and groups.dtype == R.GROUP_REC and pods.dtype == R.POD_REC
+        assert lws.dtype == R.LWS_REC and groups.dtype == R.GROUP_REC
+        assert pod_state.dtype == R.POD_STATE and pod_ident.dtype == R.POD_IDENT and len(pod_state) == len(pod_ident)
         if out is None:
             lws_out = R.aligned_empty(len(lws), R.LWS_OUT)
             group_out = R.aligned_empty(len(groups), R.GROUP_OUT)
@@ -134,17 +135,17 @@ class Engine:
             lws_out, group_out = out
         occ = np.zeros(max(self.n_nodes, 1), dtype=np.uint32) if want_occupancy else None
         t = R.LwsTables(
-            R.ptr(lws), len(lws), R.ptr(groups), len(groups), R.ptr(pods), len(pods),
+            R.ptr(lws), len(lws), R.ptr(groups), len(groups), R.ptr(pod_state), R.ptr(pod_ident), len(pod_state),
             R.ptr(lws_out), R.ptr(group_out), R.ptr(occ), flags,
         )
         self._check(lib().lwse_sweep_lws_host(self._h, C.byref(t)))
         return lws_out, group_out, (occ[: self.n_nodes] if occ is not None else None)
 
-    def sweep_lws_device(self, d_lws, n_lws, d_groups, n_groups, d_pods, n_pods, d_lws_out, d_group_out,
-                         d_occupancy=None, flags=0, stream=None):
+    def sweep_lws_device(self, d_lws, n_lws, d_groups, n_groups, d_pod_state, d_pod_ident, n_pods, d_lws_out,
+                         d_group_out, d_occupancy=None, flags=0, stream=None):
         """Device pointers (ints / tensors) in; kernels are enqueued, no synchronize."""
         t = R.LwsTables(
-            R.ptr(d_lws), n_lws, R.ptr(d_groups), n_groups, R.ptr(d_pods), n_pods,
+            R.ptr(d_lws), n_lws, R.ptr(d_groups), n_groups, R.ptr(d_pod_state), R.ptr(d_pod_ident), n_pods,
             R.ptr(d_lws_out), R.ptr(d_group_out), R.ptr(d_occupancy), flags,
         )
         self._check(lib().lwse_sweep_lws_device(self._h, C.byref(t), stream))

@@ -91,8 +91,20 @@ GRP_WSTS_OWNER_NAME_MATCH = 1 << 9
 GRP_MISTAKEN_ANNOTATION = 1 << 10
 GRP_REVISION_EXISTS = 1 << 11
 
-POD_REC = np.dtype([("rev_hash", "<u8"), ("owner_uid_hash", "<u4"), ("bits", "<u4")], align=False)
-assert POD_REC.itemsize == 16
+POD_STATE = np.dtype("<u4")  # lwse_pod_state
+POD_IDENT = np.dtype([("rev_hash_lo", "<u4"), ("rev_hash_hi", "<u4"), ("owner_uid_hash", "<u4")], align=False)
+assert POD_IDENT.itemsize == 12
+
+
+def pod_ident_table(rev_hash: np.ndarray, owner_uid_hash: np.ndarray) -> np.ndarray:
+    """Build the identity column from 64-bit revision hashes and 32-bit owner uid hashes."""
+    t = aligned_empty(len(rev_hash), POD_IDENT)
+    rev = np.asarray(rev_hash, dtype=np.uint64)
+    t["rev_hash_lo"] = (rev & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    t["rev_hash_hi"] = (rev >> np.uint64(32)).astype(np.uint32)
+    t["owner_uid_hash"] = owner_uid_hash
+    return t
+
 
 POD_PHASE_MASK = 3
 POD_PHASE_PENDING = 1
@@ -172,6 +184,7 @@ GOUT_BAD_TABLE = 1 << 14
 SWEEP_GANG = 1 << 0
 SWEEP_SKIP_GROUP_PASS = 1 << 1
 SWEEP_SKIP_LWS_PASS = 1 << 2
+SWEEP_SKIP_POD_SCAN = 1 << 3
 
 # --------------------------------------------------------------------------- #
 # placement
@@ -264,7 +277,8 @@ class LwsTables(C.Structure):
         ("n_lws", C.c_uint32),
         ("groups", C.c_void_p),
         ("n_groups", C.c_uint32),
-        ("pods", C.c_void_p),
+        ("pod_state", C.c_void_p),
+        ("pod_ident", C.c_void_p),
         ("n_pods", C.c_uint64),
         ("lws_out", C.c_void_p),
         ("group_out", C.c_void_p),

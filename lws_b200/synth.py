@@ -88,7 +88,8 @@ class Tables:
     profile: Profile
     lws: np.ndarray
     groups: np.ndarray
-    pods: np.ndarray
+    pod_state: np.ndarray
+    pod_ident: np.ndarray
     nodes: np.ndarray
     n_domains: int
     flags: int
@@ -99,8 +100,22 @@ class Tables:
         return (
             len(self.lws) * (R.LWS_REC.itemsize + R.LWS_OUT.itemsize)
             + len(self.groups) * (R.GROUP_REC.itemsize + R.GROUP_OUT.itemsize)
-            + len(self.pods) * R.POD_REC.itemsize
+            + len(self.pod_state) * R.POD_STATE.itemsize
+            + self.event_pods() * R.POD_IDENT.itemsize
         )
+
+    def event_pods(self) -> int:
+        """Pods with a restart / deletion event: the only identity rows a sweep reads."""
+        b = self.pod_state
+        phase = b & R.POD_PHASE_MASK
+        ev = (((phase == R.POD_PHASE_PENDING) | (phase == R.POD_PHASE_RUNNING)) & ((b & R.POD_ANY_RESTART) != 0)) | (
+            (b & R.POD_DELETING) != 0
+        )
+        return int(ev.sum())
+
+    def table_bytes(self) -> int:
+        """Bytes of all input tables (what a full host→device upload moves)."""
+        return int(self.lws.nbytes + self.groups.nbytes + self.pod_state.nbytes + self.pod_ident.nbytes)
 
     def describe(self) -> dict:
         p = self.profile
@@ -108,7 +123,7 @@ class Tables:
             "workload": p.name,
             "lws": int(len(self.lws)),
             "groups": int(len(self.groups)),
-            "pods": int(len(self.pods)),
+            "pods": int(len(self.pod_state)),
             "nodes": int(len(self.nodes)),
             "domains": int(self.n_domains),
             "size": list(p.size_choices),
@@ -292,9 +307,8 @@ def make(name_or_profile, scale: float = 1.0, seed: int = SEED) -> Tables:
 
     pg = np.repeat(np.arange(G, dtype=np.int64), pod_count)  # pod → group
     within = np.arange(Pn, dtype=np.int64) - pod_base[pg]
-    pods = R.aligned_empty(Pn, R.POD_REC)
     same_rev = rng.random(Pn) > (0.02 + p.fuzz)
-    pods["rev_hash"] = np.where(same_rev, g["leader_rev_hash"][pg], g["leader_rev_hash"][pg] ^ np.uint64(1))
+    pod_rev = np.where(same_rev, g["leader_rev_hash"][pg], g["leader_rev_hash"][pg] ^ np.uint64(1))
     is_leader = within == 0
     if p.fuzz:
         is_leader &= rng.random(Pn) > p.fuzz / 2
@@ -311,7 +325,7 @@ def make(name_or_profile, scale: float = 1.0, seed: int = SEED) -> Tables:
         kind[k_other] = R.POD_OWNER_OTHER
     stale = rng.random(Pn) < (0.01 + p.fuzz)
     owner_uid = np.where(stale, _u32(rng, Pn), owner_uid)
-    pods["owner_uid_hash"] = owner_uid
+    pod_ident = R.pod_ident_table(pod_rev, owner_uid)
     phase = np.full(Pn, R.POD_PHASE_RUNNING, dtype=np.uint32)
     phase[rng.random(Pn) < p.p_pending] = R.POD_PHASE_PENDING
     if p.fuzz:
@@ -334,9 +348,10 @@ def make(name_or_profile, scale: float = 1.0, seed: int = SEED) -> Tables:
                        np.uint32(max(p.n_nodes - 1, 0)))
     p_sched = g_sched & (rng.random(Pn) > p.p_pending)
     bits |= np.where(p_sched, np.uint32(R.POD_SCHEDULED) | (pnode << np.uint32(R.POD_NODE_SHIFT)), 0).astype(np.uint32)
-    pods["bits"] = bits
+    pod_state = R.aligned_empty(Pn, R.POD_STATE)
+    pod_state[:] = bits
 
-    return Tables(profile=p, lws=lws, groups=g, pods=pods, nodes=nodes, n_domains=n_domains,
+    return Tables(profile=p, lws=lws, groups=g, pod_state=pod_state, pod_ident=pod_ident, nodes=nodes, n_domains=n_domains,
                   flags=R.SWEEP_GANG if p.gang else 0)
 
 

@@ -73,14 +73,14 @@ _OPTIONAL = [
 ]
 
 
-def sweep_lws(lws, groups, pods, nodes=None, flags=0, want_occupancy=False, threads=1):
+def sweep_lws(lws, groups, pod_state, pod_ident, nodes=None, flags=0, want_occupancy=False, threads=1):
     """Run the restatement over record tables → (lws_out, group_out, occupancy|None)."""
     n_nodes = 0 if nodes is None else len(nodes)
     lws_out = R.aligned_empty(len(lws), R.LWS_OUT)
     group_out = R.aligned_empty(len(groups), R.GROUP_OUT)
     occ = np.zeros(max(n_nodes, 1), dtype=np.uint32) if want_occupancy else None
     t = R.LwsTables(
-        R.ptr(lws), len(lws), R.ptr(groups), len(groups), R.ptr(pods), len(pods),
+        R.ptr(lws), len(lws), R.ptr(groups), len(groups), R.ptr(pod_state), R.ptr(pod_ident), len(pod_state),
         R.ptr(lws_out), R.ptr(group_out), R.ptr(occ), flags,
     )
     rc = lib().lwso_sweep_lws(C.byref(t), R.ptr(nodes) if n_nodes else None, n_nodes, threads)

@@ -317,8 +317,28 @@ static int update_conditions(const lwse_lws_rec* l, const lwse_group_rec* groups
 /* pod_controller.go                                                         */
 /* ------------------------------------------------------------------------- */
 
+/* one pod, assembled from the state and identity columns */
+typedef struct {
+  uint64_t rev_hash;
+  uint32_t owner_uid_hash;
+  uint32_t bits;
+} pod_view;
+
+typedef struct {
+  const lwse_pod_state* state;
+  const lwse_pod_ident* ident;
+} pod_cols;
+
+static pod_view get_pod(const pod_cols* c, uint64_t i) {
+  pod_view p;
+  p.rev_hash = (uint64_t)c->ident[i].rev_hash_lo | ((uint64_t)c->ident[i].rev_hash_hi << 32);
+  p.owner_uid_hash = c->ident[i].owner_uid_hash;
+  p.bits = c->state[i];
+  return p;
+}
+
 /* pkg/utils/pod/pod_utils.go:29-45 ContainerRestarted */
-static int container_restarted(const lwse_pod_rec* p) {
+static int container_restarted(const pod_view* p) {
   uint32_t phase = p->bits & LWSE_POD_PHASE_MASK;
   if (phase == LWSE_POD_PHASE_RUNNING || phase == LWSE_POD_PHASE_PENDING)
     return (p->bits & LWSE_POD_ANY_RESTART) != 0;
@@ -326,16 +346,16 @@ static int container_restarted(const lwse_pod_rec* p) {
 }
 
 /* :338-362 pendingPodsInGroup */
-static int pending_pods_in_group(const lwse_group_rec* g, const lwse_pod_rec* pods, int group_size) {
+static int pending_pods_in_group(const lwse_group_rec* g, const pod_cols* pods, int group_size) {
   if ((uint32_t)group_size != g->pod_count) return 1;
   for (uint32_t i = 0; i < g->pod_count; i++) {
-    if ((pods[g->pod_base + i].bits & LWSE_POD_PHASE_MASK) == LWSE_POD_PHASE_PENDING) return 1;
+    if ((pods->state[g->pod_base + i] & LWSE_POD_PHASE_MASK) == LWSE_POD_PHASE_PENDING) return 1;
   }
   return 0;
 }
 
 /* :268-295 workerPodBelongsToLeader */
-static int worker_pod_belongs_to_leader(const lwse_pod_rec* p, const lwse_group_rec* g) {
+static int worker_pod_belongs_to_leader(const pod_view* p, const lwse_group_rec* g) {
   uint32_t kind = (p->bits & LWSE_POD_OWNER_MASK) >> LWSE_POD_OWNER_SHIFT;
   if (kind == 0) return 0; /* owner == nil */
   if (kind == 1) /* Pod */
@@ -352,7 +372,7 @@ static int worker_pod_belongs_to_leader(const lwse_pod_rec* p, const lwse_group_
  * returns 1 = leaderDeleted (true,nil); 0 = (false,nil); -1 = (false,err).
  * *issued_delete = 1 when r.Delete(leader) would be called. */
 static int handle_restart_policy(const lwse_lws_rec* l, const lwse_group_rec* g,
-                                 const lwse_pod_rec* pods, const lwse_pod_rec* p,
+                                 const pod_cols* pods, const pod_view* p,
                                  int* issued_delete) {
   *issued_delete = 0;
   uint32_t policy = (l->flags & LWSE_LWS_RESTART_MASK) >> LWSE_LWS_RESTART_SHIFT;
@@ -380,7 +400,7 @@ static int handle_restart_policy(const lwse_lws_rec* l, const lwse_group_rec* g,
 /* One pod group: restart sweep over its pods (B1/B2), then the leader pod's
  * own Reconcile tail (:100-198) for worker-sts gating and topology (B3/B4). */
 static void reconcile_group(const lwse_lws_rec* l, const lwse_group_rec* g,
-                            const lwse_pod_rec* pods, const lwse_node_rec* nodes,
+                            const pod_cols* pods, const lwse_node_rec* nodes,
                             uint32_t n_nodes, uint32_t sweep_flags, lwse_group_out* o) {
   uint32_t f = 0;
   o->first_trigger = LWSE_NONE;
@@ -411,7 +431,8 @@ static void reconcile_group(const lwse_lws_rec* l, const lwse_group_rec* g,
 
   int leader_deleted = 0; /* result of handleRestartPolicy for the leader pod's own event */
   for (uint32_t i = 0; i < g->pod_count; i++) {
-    const lwse_pod_rec* p = &pods[g->pod_base + i];
+    const pod_view pv = get_pod(pods, (uint64_t)g->pod_base + i);
+    const pod_view* p = &pv;
     int issued = 0;
     int r = handle_restart_policy(l, g, pods, p, &issued);
     if (r < 0) {
@@ -498,7 +519,8 @@ static void sweep_one_group(const lwse_lws_tables* t, const lwse_node_rec* nodes
     o->domain_id = LWSE_NONE;
     return;
   }
-  reconcile_group(&t->lws[g->lws_index], g, t->pods, nodes, n_nodes, t->flags, o);
+  pod_cols cols = {t->pod_state, t->pod_ident};
+  reconcile_group(&t->lws[g->lws_index], g, &cols, nodes, n_nodes, t->flags, o);
 }
 
 /* Sweep every object, one at a time (the reference runs one reconcile worker
@@ -540,16 +562,13 @@ LWSO_API int lwso_sweep_lws(const lwse_lws_tables* t, const lwse_node_rec* nodes
     for (int k = 0; k < threads; k++) pthread_join(tid[k], NULL);
   }
   if (t->node_occupancy) {
-    /* pods per node, over the pod rows of every well-formed group row */
-    for (uint32_t r = 0; r < t->n_groups; r++) {
-      const lwse_group_rec* g = &t->groups[r];
-      if (g->lws_index >= t->n_lws || (uint64_t)g->pod_base + g->pod_count > t->n_pods) continue;
-      for (uint32_t i = 0; i < g->pod_count; i++) {
-        uint32_t b = t->pods[g->pod_base + i].bits;
-        if (b & LWSE_POD_SCHEDULED) {
-          uint32_t node = b >> LWSE_POD_NODE_SHIFT;
-          if (node < n_nodes) t->node_occupancy[node]++;
-        }
+    /* scheduled pods per node, over the whole pod table */
+    memset(t->node_occupancy, 0, sizeof(uint32_t) * (size_t)n_nodes);
+    for (uint64_t p = 0; p < t->n_pods; p++) {
+      uint32_t b = t->pod_state[p];
+      if (b & LWSE_POD_SCHEDULED) {
+        uint32_t node = b >> LWSE_POD_NODE_SHIFT;
+        if (node < n_nodes) t->node_occupancy[node]++;
       }
     }
   }

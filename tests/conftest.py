@@ -22,7 +22,7 @@ def oracle_sweep():
 
     def sweep(tables, flags=0):
         lws_out, group_out, _ = oracle.sweep_lws(
-            tables.lws, tables.groups, tables.pods, tables.nodes, flags=flags
+            tables.lws, tables.groups, tables.pod_state, tables.pod_ident, tables.nodes, flags=flags
         )
         return lws_out, group_out
 

@@ -50,7 +50,7 @@ def test_record_sizes_match_header():
     import tempfile
 
     structs = {
-        "lwse_lws_rec": R.LWS_REC, "lwse_group_rec": R.GROUP_REC, "lwse_pod_rec": R.POD_REC,
+        "lwse_lws_rec": R.LWS_REC, "lwse_group_rec": R.GROUP_REC, "lwse_pod_ident": R.POD_IDENT,
         "lwse_node_rec": R.NODE_REC, "lwse_lws_out": R.LWS_OUT, "lwse_group_out": R.GROUP_OUT,
         "lwse_place_req": R.PLACE_REQ, "lwse_place_out": R.PLACE_OUT, "lwse_ds_rec": R.DS_REC,
         "lwse_ds_role_rec": R.DS_ROLE_REC, "lwse_ds_revrole_rec": R.DS_REVROLE_REC,

@@ -35,8 +35,8 @@ def run_both(engine, t, occupancy=True):
     import oracle
 
     engine.upload_nodes(t.nodes, t.n_domains)
-    want = oracle.sweep_lws(t.lws, t.groups, t.pods, t.nodes, flags=t.flags, want_occupancy=occupancy)
-    got = engine.sweep_lws_host(t.lws, t.groups, t.pods, flags=t.flags, want_occupancy=occupancy)
+    want = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, flags=t.flags, want_occupancy=occupancy)
+    got = engine.sweep_lws_host(t.lws, t.groups, t.pod_state, t.pod_ident, flags=t.flags, want_occupancy=occupancy)
     assert_same(got[0], want[0], "lws_out")
     assert_same(got[1], want[1], "group_out")
     if occupancy:
@@ -75,19 +75,20 @@ def test_empty_tables(engine):
     engine.upload_nodes(t.nodes, t.n_domains)
     e_lws = R.aligned_empty(0, R.LWS_REC)
     e_grp = R.aligned_empty(0, R.GROUP_REC)
-    e_pod = R.aligned_empty(0, R.POD_REC)
-    lo, go, _ = engine.sweep_lws_host(e_lws, e_grp, e_pod)
+    e_pst = R.aligned_empty(0, R.POD_STATE)
+    e_pid = R.aligned_empty(0, R.POD_IDENT)
+    lo, go, _ = engine.sweep_lws_host(e_lws, e_grp, e_pst, e_pid)
     assert len(lo) == 0 and len(go) == 0
     # objects without any group rows
     t.lws["group_count"] = 0
-    run_both(engine, synth.Tables(t.profile, t.lws, e_grp, e_pod, t.nodes, t.n_domains, t.flags))
+    run_both(engine, synth.Tables(t.profile, t.lws, e_grp, e_pst, e_pid, t.nodes, t.n_domains, t.flags))
 
 
 def test_bad_tables_are_flagged_not_fatal(engine):
     t = synth.make("fuzz", 0.05, seed=11)
     t.lws["group_base"][3] = len(t.groups) + 5
     t.groups["lws_index"][7] = len(t.lws) + 1
-    t.groups["pod_base"][9] = len(t.pods)
+    t.groups["pod_base"][9] = len(t.pod_state)
     t.groups["pod_count"][9] = 3
     lo, go, _ = run_both(engine, t)
     assert lo["flags"][3] & R.LOUT_BAD_TABLE
@@ -106,17 +107,19 @@ def test_device_pointer_entry(engine):
     def up(a):
         return torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
 
-    d_lws, d_grp, d_pod = up(t.lws), up(t.groups), up(t.pods)
+    d_lws, d_grp, d_pst, d_pid = up(t.lws), up(t.groups), up(t.pod_state), up(t.pod_ident)
     d_lo = torch.zeros(len(t.lws) * R.LWS_OUT.itemsize, dtype=torch.uint8, device=dev)
     d_go = torch.zeros(len(t.groups) * R.GROUP_OUT.itemsize, dtype=torch.uint8, device=dev)
     d_occ = torch.zeros(len(t.nodes), dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    side = torch.cuda.Stream()  # a non-default torch stream (0 / NULL would mean "the engine's own stream")
+    side.wait_stream(torch.cuda.current_stream())
+    stream = side.cuda_stream
     before = engine.launch_count
-    engine.sweep_lws_device(d_lws, len(t.lws), d_grp, len(t.groups), d_pod, len(t.pods), d_lo, d_go,
+    engine.sweep_lws_device(d_lws, len(t.lws), d_grp, len(t.groups), d_pst, d_pid, len(t.pod_state), d_lo, d_go,
                             d_occ, flags=t.flags, stream=stream)
     torch.cuda.synchronize()
-    assert engine.launch_count - before == 2
-    want = oracle.sweep_lws(t.lws, t.groups, t.pods, t.nodes, flags=t.flags, want_occupancy=True)
+    assert engine.launch_count - before == 3
+    want = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, flags=t.flags, want_occupancy=True)
     assert_same(d_lo.cpu().numpy().view(R.LWS_OUT), want[0], "lws_out")
     assert_same(d_go.cpu().numpy().view(R.GROUP_OUT), want[1], "group_out")
     assert np.array_equal(d_occ.cpu().numpy().astype(np.uint32), want[2])
@@ -129,7 +132,7 @@ def test_reference_integration_traces_on_gpu(engine):
 
     def sweep(tables, flags=0):
         engine.upload_nodes(tables.nodes, tables.n_domains)
-        lo, go, _ = engine.sweep_lws_host(tables.lws, tables.groups, tables.pods, flags=flags)
+        lo, go, _ = engine.sweep_lws_host(tables.lws, tables.groups, tables.pod_state, tables.pod_ident, flags=flags)
         return lo, go
 
     for name, (cfg, steps) in sorted(TRACES.items()):
@@ -149,8 +152,8 @@ def test_large_idempotent_and_order_independent(engine):
     bytes, and permuting the objects permutes the outputs."""
     t = synth.make("C3", 0.25)
     engine.upload_nodes(t.nodes, t.n_domains)
-    a = engine.sweep_lws_host(t.lws, t.groups, t.pods, flags=t.flags)
-    b = engine.sweep_lws_host(t.lws, t.groups, t.pods, flags=t.flags)
+    a = engine.sweep_lws_host(t.lws, t.groups, t.pod_state, t.pod_ident, flags=t.flags)
+    b = engine.sweep_lws_host(t.lws, t.groups, t.pod_state, t.pod_ident, flags=t.flags)
     assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()
     # reverse the LWS table (group rows keep their place; lws_index is remapped)
     n = len(t.lws)
@@ -160,6 +163,6 @@ def test_large_idempotent_and_order_independent(engine):
     grp2 = R.aligned_empty(len(t.groups), R.GROUP_REC)
     grp2[:] = t.groups
     grp2["lws_index"] = (n - 1 - t.groups["lws_index"].astype(np.int64)).astype(np.uint32)
-    c = engine.sweep_lws_host(lws2, grp2, t.pods, flags=t.flags)
+    c = engine.sweep_lws_host(lws2, grp2, t.pod_state, t.pod_ident, flags=t.flags)
     assert c[0].tobytes() == a[0][perm].tobytes()
     assert c[1].tobytes() == a[1].tobytes()
