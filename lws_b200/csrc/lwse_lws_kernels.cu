@@ -108,9 +108,15 @@ __device__ __forceinline__ uint32_t bit_range(uint32_t lo, uint32_t hi) {
   return upto_hi & ~((1u << lo) - 1u) & (lo >= 32u ? 0u : 0xFFFFFFFFu);
 }
 
+// One W-lane tile per group: the lanes share the group's bitmap words (lane j
+// takes words j, j+W, …) so that the rare per-pod visits of one group run in
+// parallel; W = 1 for small groups.
+template <int W>
 __global__ void __launch_bounds__(256) group_sweep_kernel(const GroupSweepArgs a) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < a.n_groups; g += stride) {
+  constexpr uint32_t kTilesPerBlock = 256 / W;
+  const uint32_t lane = threadIdx.x & (W - 1);
+  const uint32_t stride = gridDim.x * kTilesPerBlock;
+  for (uint32_t g = blockIdx.x * kTilesPerBlock + threadIdx.x / W; g < a.n_groups; g += stride) {
     const uint4* row = reinterpret_cast<const uint4*>(a.groups + g);
     const uint4 ca = ldg_cached(row + 0), cb = ldg_cached(row + 1), cc = ldg_cached(row + 2),
                 cd = ldg_cached(row + 3);
@@ -130,17 +136,18 @@ __global__ void __launch_bounds__(256) group_sweep_kernel(const GroupSweepArgs a
       // ---- pendingPodsInGroup :338-362 from the pending bitmap ----
       const uint32_t pod_end = pod_base + pod_count;  // <= n_pods < 2^32 (checked by the entry points)
       const uint32_t w_first = pod_base >> 5, w_last = pod_count ? ((pod_end - 1u) >> 5) : w_first;
-      bool any_pending = false, any_event = false;
+      uint32_t any_bits = 0;  // bit0 pending, bit1 event
       if (pod_count) {
-        for (uint32_t w = w_first; w <= w_last; w++) {
+        for (uint32_t w = w_first + lane; w <= w_last; w += W) {
           const uint32_t lo = w == w_first ? (pod_base & 31u) : 0u;
           const uint32_t hi = w == w_last ? (((pod_end - 1u) & 31u) + 1u) : 32u;
           const uint32_t m = bit_range(lo, hi);
-          any_pending |= (__ldg(a.pending_bits + w) & m) != 0u;
-          any_event |= (__ldg(a.event_bits + w) & m) != 0u;
+          if (__ldg(a.pending_bits + w) & m) any_bits |= 1u;
+          if (__ldg(a.event_bits + w) & m) any_bits |= 2u;
         }
       }
-      const bool pending = (uint32_t)size != pod_count || any_pending;
+      any_bits = tile_or<W>(any_bits);
+      const bool pending = (uint32_t)size != pod_count || (any_bits & 1u);
       if (pending) oflags |= LWSE_GOUT_PENDING;
       // :222 skip when pending ∧ (AfterStart ∨ annotation)
       const bool suppressed =
@@ -148,45 +155,51 @@ __global__ void __launch_bounds__(256) group_sweep_kernel(const GroupSweepArgs a
 
       // ---- handleRestartPolicy :204-266 for the pods that have an event ----
       bool leader_deleted = false;
-      if (any_event && policy_on && !suppressed) {
+      if ((any_bits & 2u) && policy_on && !suppressed) {  // tile-uniform
         const bool leader_found = (gflags & (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH)) ==
                                   (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH);  // :233
         constexpr uint32_t kChain =
             LWSE_GRP_WSTS_FOUND | LWSE_GRP_WSTS_OWNER_IS_POD | LWSE_GRP_WSTS_OWNER_NAME_MATCH;
         const bool wsts_chain_ok = (gflags & kChain) == kChain && cc.x == cb.z;  // sts owner uid == leader uid
-        for (uint32_t w = w_first; w <= w_last; w++) {
+        uint32_t acc = 0, first = LWSE_NONE;
+        for (uint32_t w = w_first + lane; w <= w_last; w += W) {
           const uint32_t lo = w == w_first ? (pod_base & 31u) : 0u;
           const uint32_t hi = w == w_last ? (((pod_end - 1u) & 31u) + 1u) : 32u;
           uint32_t m = __ldg(a.event_bits + w) & bit_range(lo, hi);
           while (m) {
-            const uint32_t bit = __ffs(m) - 1u;
+            const uint32_t p = (w << 5) + (__ffs(m) - 1u);  // pod row, ascending within the lane
             m &= m - 1u;
-            const uint32_t p = (w << 5) + bit;  // pod row, ascending
+            // state and identity are independent loads: both in flight at once
             const uint32_t bits = __ldg(a.pod_state + p);
+            const uint32_t* idp = reinterpret_cast<const uint32_t*>(a.pod_ident + p);
+            const uint32_t id_lo = __ldg(idp), id_hi = __ldg(idp + 1), id_owner = __ldg(idp + 2);
             bool cand, deleting;
             if (bits & LWSE_POD_IS_LEADER) {
               cand = true;  // leader = pod (:251)
               deleting = bits & LWSE_POD_DELETING;
             } else if (!(bits & LWSE_POD_NAME_OK)) {
-              oflags |= LWSE_GOUT_RESTART_ERROR;  // :230
+              acc |= LWSE_GOUT_RESTART_ERROR;  // :230
               continue;
             } else {
-              const lwse_pod_ident id = a.pod_ident[p];
               const uint32_t kind = (bits & LWSE_POD_OWNER_MASK) >> LWSE_POD_OWNER_SHIFT;
               // workerPodBelongsToLeader :268-295
               const bool belongs = (bits & LWSE_POD_OWNER_NAME_MATCH) &&
-                                   ((kind == 1u && id.owner_uid_hash == cb.z) ||
-                                    (kind == 2u && id.owner_uid_hash == cb.w && wsts_chain_ok));
-              cand = leader_found && id.rev_hash_lo == ca.x && id.rev_hash_hi == ca.y && belongs;  // :239
+                                   ((kind == 1u && id_owner == cb.z) ||
+                                    (kind == 2u && id_owner == cb.w && wsts_chain_ok));
+              cand = leader_found && id_lo == ca.x && id_hi == ca.y && belongs;  // :239
               deleting = gflags & LWSE_GRP_POD_DELETING;
             }
             if (cand) {
-              oflags |= deleting ? LWSE_GOUT_LEADER_DELETING : LWSE_GOUT_DELETE_LEADER;  // :255 / :259
-              if (bits & LWSE_POD_IS_LEADER) leader_deleted = true;
-              if (first_out == LWSE_NONE) first_out = p - pod_base;
+              acc |= deleting ? LWSE_GOUT_LEADER_DELETING : LWSE_GOUT_DELETE_LEADER;  // :255 / :259
+              if (bits & LWSE_POD_IS_LEADER) acc |= 0x80000000u;
+              first = min(first, p - pod_base);
             }
           }
         }
+        acc = tile_or<W>(acc);
+        first_out = tile_min<W>(first);
+        leader_deleted = acc & 0x80000000u;
+        oflags |= acc & 0x7FFFFFFFu;
       }
 
       // ---- per-replica state bits (consumed by lws_sweep_kernel) ----
@@ -245,7 +258,7 @@ __global__ void __launch_bounds__(256) group_sweep_kernel(const GroupSweepArgs a
         worker_replicas = size - 1;  // :437; ordinals start at 1 (:440)
       }
     }
-    stg_stream(a.out + g, make_uint4(oflags, first_out, (uint32_t)worker_replicas, domain));
+    if (lane == 0) stg_stream(a.out + g, make_uint4(oflags, first_out, (uint32_t)worker_replicas, domain));
   }
 }
 
@@ -470,6 +483,16 @@ static uint32_t resident_ctas(K kernel, int sm_count) {
 }
 
 template <int W>
+static cudaError_t launch_group(const GroupSweepArgs& a, int sm_count, cudaStream_t s) {
+  constexpr uint32_t kTilesPerBlock = 256 / W;
+  static uint32_t resident = 0;
+  if (resident == 0) resident = resident_ctas(group_sweep_kernel<W>, sm_count);
+  const uint32_t want = (a.n_groups + kTilesPerBlock - 1) / kTilesPerBlock;
+  group_sweep_kernel<W><<<want < resident ? want : resident, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <int W>
 static cudaError_t launch_lws(const LwsSweepArgs& a, int sm_count, cudaStream_t s) {
   constexpr uint32_t kTilesPerBlock = 256 / W;
   static uint32_t resident = 0;
@@ -498,11 +521,11 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
   uint32_t* event_bits = pending_bits + ((words + 31u) & ~(uint64_t)31u);
   const bool group_pass = t->n_groups && !(t->flags & LWSE_SWEEP_SKIP_GROUP_PASS);
 
+  if (t->node_occupancy && n_nodes && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN)) {
+    e = cudaMemsetAsync(t->node_occupancy, 0, (size_t)n_nodes * sizeof(uint32_t), s);
+    if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
+  }
   if (t->n_pods && (t->n_groups || t->node_occupancy) && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN)) {
-    if (t->node_occupancy) {
-      e = cudaMemsetAsync(t->node_occupancy, 0, (size_t)n_nodes * sizeof(uint32_t), s);
-      if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
-    }
     PodScanArgs a{t->pod_state, pending_bits, event_bits, t->node_occupancy, t->n_pods, n_nodes};
     static uint32_t resident = 0, resident_occ = 0;
     if (resident == 0) {
@@ -525,11 +548,15 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
   if (group_pass) {
     GroupSweepArgs a{t->lws,   t->groups, t->pod_state, t->pod_ident, pending_bits, event_bits, d_nodes,
                      t->group_out, t->n_pods, t->n_lws, t->n_groups, n_nodes, t->flags};
-    static uint32_t resident = 0;
-    if (resident == 0) resident = resident_ctas(group_sweep_kernel, sm_count);
-    const uint32_t want = (t->n_groups + 255u) / 256u;
-    group_sweep_kernel<<<want < resident ? want : resident, 256, 0, s>>>(a);
-    e = cudaGetLastError();
+    // lanes per group: one per bitmap word of an average group, in {1, 2, 4, 8}
+    const uint64_t avg_pods = (t->n_pods + t->n_groups - 1) / t->n_groups;
+    const int w = avg_pods > 128 ? 8 : avg_pods > 48 ? 4 : avg_pods > 24 ? 2 : 1;
+    switch (w) {
+      case 8: e = launch_group<8>(a, sm_count, s); break;
+      case 4: e = launch_group<4>(a, sm_count, s); break;
+      case 2: e = launch_group<2>(a, sm_count, s); break;
+      default: e = launch_group<1>(a, sm_count, s); break;
+    }
     if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
     launches++;
   }
