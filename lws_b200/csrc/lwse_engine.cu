@@ -105,7 +105,7 @@ int check_lws_tables(const lwse_lws_tables* t) {
   if (t->n_pods && (!t->pod_state || !t->pod_ident)) return LWSE_ERR_INVALID_ARG;
   if (t->n_pods > 0xFFFFFFFFull) return LWSE_ERR_UNSUPPORTED;  // pod_base / pod_count are 32-bit
   if (!aligned16(t->lws) || !aligned16(t->groups) || !aligned16(t->lws_out) || !aligned16(t->group_out) ||
-      (reinterpret_cast<uintptr_t>(t->pod_state) & 3u) || (reinterpret_cast<uintptr_t>(t->pod_ident) & 3u))
+      !aligned16(t->pod_state) || (reinterpret_cast<uintptr_t>(t->pod_ident) & 3u))
     return LWSE_ERR_INVALID_ARG;
   return LWSE_OK;
 }

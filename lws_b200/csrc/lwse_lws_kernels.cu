@@ -44,41 +44,56 @@ __device__ __forceinline__ bool pod_has_event(uint32_t bits) {
   return ((phase - 1u) < 2u && (bits & LWSE_POD_ANY_RESTART)) || (bits & LWSE_POD_DELETING);
 }
 
+// 4 predicate bits of the 4 pods a lane holds, moved to the lane's nibble of its
+// 8-lane segment: OR-reducing over the segment yields one bitmap word (32 pods).
+__device__ __forceinline__ uint32_t seg8_or(uint32_t nibble, uint32_t lane) {
+  const uint32_t mask = 0xFFu << (lane & 24u);
+  return __reduce_or_sync(mask, nibble << ((lane & 7u) * 4u));
+}
+
 template <int U, bool OCC>
 __global__ void __launch_bounds__(256) pod_scan_kernel(const PodScanArgs a) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t warp = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5);
   const uint64_t n_warps = (uint64_t)gridDim.x * 8u;
   const uint64_t n_words = (a.n_pods + 31u) >> 5;
-  constexpr uint64_t kPodsPerChunk = 32ull * U;
+  constexpr uint64_t kPodsPerChunk = 128ull * U;  // 32 lanes x 4 pods x U
+  const uint4* vec = reinterpret_cast<const uint4*>(a.state);
   for (uint64_t base = warp * kPodsPerChunk; base < a.n_pods; base += n_warps * kPodsPerChunk) {
-    uint32_t bits[U];
+    uint4 v[U];
 #pragma unroll
-    for (int j = 0; j < U; j++) {
-      const uint64_t idx = base + (uint64_t)j * 32u + lane;
-      bits[j] = idx < a.n_pods ? __ldcs(a.state + idx) : 0u;  // streaming: evict-first
-    }
-    uint32_t my_pending = 0, my_event = 0;
-#pragma unroll
-    for (int j = 0; j < U; j++) {
-      const uint32_t b = bits[j];
-      const uint32_t wp = __ballot_sync(0xFFFFFFFFu, (b & LWSE_POD_PHASE_MASK) == LWSE_POD_PHASE_PENDING);
-      const uint32_t we = __ballot_sync(0xFFFFFFFFu, pod_has_event(b));
-      if (lane == (uint32_t)j) {
-        my_pending = wp;
-        my_event = we;
+    for (int j = 0; j < U; j++) {  // all U 128-bit loads in flight before the first use
+      const uint64_t idx = base + (uint64_t)j * 128u + lane * 4u;
+      if (idx + 3u < a.n_pods) {
+        v[j] = ldg_stream(vec + (idx >> 2));
+      } else {  // ragged tail of the column
+        v[j].x = idx + 0u < a.n_pods ? __ldg(a.state + idx + 0u) : 0u;
+        v[j].y = idx + 1u < a.n_pods ? __ldg(a.state + idx + 1u) : 0u;
+        v[j].z = idx + 2u < a.n_pods ? __ldg(a.state + idx + 2u) : 0u;
+        v[j].w = 0u;
       }
-      if (OCC) {
-        if (b & LWSE_POD_SCHEDULED) {
-          const uint32_t node = b >> LWSE_POD_NODE_SHIFT;
-          if (node < a.n_nodes) atomicAdd(a.occupancy + node, 1u);
+    }
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+      const uint32_t b[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+      uint32_t pend = 0, ev = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        pend |= ((b[k] & LWSE_POD_PHASE_MASK) == LWSE_POD_PHASE_PENDING ? 1u : 0u) << k;
+        ev |= (pod_has_event(b[k]) ? 1u : 0u) << k;
+        if (OCC) {
+          if (b[k] & LWSE_POD_SCHEDULED) {
+            const uint32_t node = b[k] >> LWSE_POD_NODE_SHIFT;
+            if (node < a.n_nodes) atomicAdd(a.occupancy + node, 1u);
+          }
         }
       }
-    }
-    const uint64_t w = (base >> 5) + lane;
-    if (lane < (uint32_t)U && w < n_words) {
-      a.pending_bits[w] = my_pending;
-      a.event_bits[w] = my_event;
+      const uint32_t wp = seg8_or(pend, lane), we = seg8_or(ev, lane);
+      const uint64_t w = ((base + (uint64_t)j * 128u) >> 5) + (lane >> 3);
+      if ((lane & 7u) == 0u && w < n_words) {
+        a.pending_bits[w] = wp;
+        a.event_bits[w] = we;
+      }
     }
   }
 }
@@ -487,8 +502,9 @@ static cudaError_t launch_group(const GroupSweepArgs& a, int sm_count, cudaStrea
   constexpr uint32_t kTilesPerBlock = 256 / W;
   static uint32_t resident = 0;
   if (resident == 0) resident = resident_ctas(group_sweep_kernel<W>, sm_count);
+  (void)resident;
   const uint32_t want = (a.n_groups + kTilesPerBlock - 1) / kTilesPerBlock;
-  group_sweep_kernel<W><<<want < resident ? want : resident, 256, 0, s>>>(a);
+  group_sweep_kernel<W><<<want < (1u << 20) ? want : (1u << 20), 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -502,7 +518,7 @@ static cudaError_t launch_lws(const LwsSweepArgs& a, int sm_count, cudaStream_t 
   return cudaGetLastError();
 }
 
-constexpr int kScanUnroll = 8;  // pods per lane per chunk: 8 x 128 B = 1 KB in flight per warp
+constexpr int kScanUnroll = 4;  // 128-bit loads per lane per chunk: 4 x 512 B = 2 KB in flight per warp
 
 size_t lws_sweep_scratch_bytes(uint64_t n_pods) {
   const uint64_t words = (n_pods + 31u) / 32u;
@@ -527,20 +543,15 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
   }
   if (t->n_pods && (t->n_groups || t->node_occupancy) && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN)) {
     PodScanArgs a{t->pod_state, pending_bits, event_bits, t->node_occupancy, t->n_pods, n_nodes};
-    static uint32_t resident = 0, resident_occ = 0;
-    if (resident == 0) {
-      resident = resident_ctas(pod_scan_kernel<kScanUnroll, false>, sm_count);
-      resident_occ = resident_ctas(pod_scan_kernel<kScanUnroll, true>, sm_count);
-    }
-    const uint64_t chunks = (t->n_pods + 32ull * kScanUnroll - 1) / (32ull * kScanUnroll);
+    // one chunk per warp: the kernel is a few microseconds long, so let the
+    // hardware CTA scheduler balance it instead of a persistent grid-stride loop
+    const uint64_t chunks = (t->n_pods + 128ull * kScanUnroll - 1) / (128ull * kScanUnroll);
     const uint64_t want = (chunks + 7) / 8;
-    if (t->node_occupancy) {
-      const uint32_t grid = (uint32_t)(want < resident_occ ? want : resident_occ);
+    const uint32_t grid = (uint32_t)(want < (1u << 20) ? want : (1u << 20));
+    if (t->node_occupancy)
       pod_scan_kernel<kScanUnroll, true><<<grid, 256, 0, s>>>(a);
-    } else {
-      const uint32_t grid = (uint32_t)(want < resident ? want : resident);
+    else
       pod_scan_kernel<kScanUnroll, false><<<grid, 256, 0, s>>>(a);
-    }
     e = cudaGetLastError();
     if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
     launches++;
@@ -550,7 +561,7 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
                      t->group_out, t->n_pods, t->n_lws, t->n_groups, n_nodes, t->flags};
     // lanes per group: one per bitmap word of an average group, in {1, 2, 4, 8}
     const uint64_t avg_pods = (t->n_pods + t->n_groups - 1) / t->n_groups;
-    const int w = avg_pods > 128 ? 8 : avg_pods > 48 ? 4 : avg_pods > 24 ? 2 : 1;
+    const int w = avg_pods > 2048 ? 8 : avg_pods > 1024 ? 4 : avg_pods > 512 ? 2 : 1;
     switch (w) {
       case 8: e = launch_group<8>(a, sm_count, s); break;
       case 4: e = launch_group<4>(a, sm_count, s); break;

@@ -49,10 +49,10 @@ def test_fuzz(engine, seed):
     run_both(engine, synth.make("fuzz", 1.0, seed=seed))
 
 
-@pytest.mark.parametrize("size", [1, 2, 3, 5, 8, 13, 16, 24, 25, 31, 32, 33, 48, 49, 64, 100, 128, 129, 300])
+@pytest.mark.parametrize("size", [1, 2, 3, 5, 8, 13, 31, 32, 33, 64, 100, 129, 513, 1025, 2049])
 def test_every_tile_width(engine, size):
     """pods-per-group selects the tile width W of the group kernel (1, 2, 4, 8)."""
-    p = synth.profile("fuzz", 0.2)
+    p = synth.profile("fuzz", 0.2 if size <= 100 else 0.01)
     p.size_choices = (size,)
     run_both(engine, synth.make(p, seed=size))
 
