@@ -34,15 +34,7 @@ def sources() -> list[str]:
 
 
 def defines() -> list[str]:
-    have = {os.path.basename(s) for s in sources()}
-    d = []
-    if "lwse_place_kernels.cu" in have:
-        d.append("-DLWSE_HAVE_PLACE")
-    if "lwse_ds_kernels.cu" in have:
-        d.append("-DLWSE_HAVE_DS")
-    if "lwse_sha1_kernels.cu" in have:
-        d.append("-DLWSE_HAVE_SHA1")
-    return d
+    return []
 
 
 def stale() -> bool:

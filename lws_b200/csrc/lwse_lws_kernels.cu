@@ -45,10 +45,16 @@ __device__ __forceinline__ bool pod_has_event(uint32_t bits) {
 }
 
 // 4 predicate bits of the 4 pods a lane holds, moved to the lane's nibble of its
-// 8-lane segment: OR-reducing over the segment yields one bitmap word (32 pods).
+// 8-lane segment; a 3-step xor butterfly ORs the segment into one bitmap word
+// (32 consecutive pods) that every lane of the segment ends up holding.
+// (__reduce_or_sync with a sub-warp mask compiles to a serialised per-segment
+// loop on sm_100a — measured slower — so the butterfly uses plain shuffles.)
 __device__ __forceinline__ uint32_t seg8_or(uint32_t nibble, uint32_t lane) {
-  const uint32_t mask = 0xFFu << (lane & 24u);
-  return __reduce_or_sync(mask, nibble << ((lane & 7u) * 4u));
+  uint32_t v = nibble << ((lane & 7u) * 4u);
+  v |= __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+  v |= __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+  v |= __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+  return v;
 }
 
 template <int U, bool OCC>

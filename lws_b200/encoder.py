@@ -439,3 +439,39 @@ def encode_ds(items: Iterable[DsItem]) -> DsTablesHost:
 
     return DsTablesHost(table(ds_rows, R.DS_REC), table(role_rows, R.DS_ROLE_REC),
                         table(rr_rows, R.DS_REVROLE_REC), names_out, revs_out)
+
+
+# --------------------------------------------------------------------------- #
+# Placement requests
+# --------------------------------------------------------------------------- #
+def encode_place_requests(lws: np.ndarray, groups: np.ndarray, ns_of_lws: Optional[np.ndarray] = None) -> np.ndarray:
+    """One request per pod group of an exclusive-topology object (vectorised).
+
+    priority  = mix(owner uid hash, group index): a total order that is stable
+                across sweeps and shards (smaller wins);
+    group_key = per-group salt of the preference hash (the reference's group key is
+                sha1("<ns>/<leader pod name>"), pkg/webhooks/pod_webhook.go:180-182 —
+                any stable per-group 64-bit value serves the spec);
+    leader_node = the group row's leader node (NONE → the engine chooses).
+    Only groups whose leader pod exists take part.
+    """
+    owner = groups["lws_index"].astype(np.int64)
+    excl = (lws["flags"][owner] & R.LWS_EXCLUSIVE_TOPOLOGY) != 0
+    present = (groups["flags"] & R.GRP_POD_PRESENT) != 0
+    sel = np.flatnonzero(excl & present)
+    reqs = R.aligned_empty(len(sel), R.PLACE_REQ)
+    o = owner[sel]
+    gidx = (sel - lws["group_base"][o].astype(np.int64)).astype(np.uint64)
+    uid = lws["uid_hash"][o]
+    with np.errstate(over="ignore"):
+        pr = (uid ^ (gidx * np.uint64(0x9E3779B97F4A7C15))) * np.uint64(0xBF58476D1CE4E5B9)
+        pr ^= pr >> np.uint64(31)
+        key = (uid + gidx) * np.uint64(0x94D049BB133111EB)
+        key ^= key >> np.uint64(29)
+    reqs["priority"] = pr
+    reqs["group_key"] = key
+    reqs["group"] = sel.astype(np.uint32)
+    reqs["ns"] = 0 if ns_of_lws is None else ns_of_lws[o]
+    reqs["size"] = lws["size"][o]
+    reqs["leader_node"] = groups["leader_node"][sel]
+    return reqs

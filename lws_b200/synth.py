@@ -358,3 +358,89 @@ def make(name_or_profile, scale: float = 1.0, seed: int = SEED) -> Tables:
 def _norm(ps):
     a = np.asarray(ps, dtype=np.float64)
     return a / a.sum()
+
+
+# --------------------------------------------------------------------------- #
+# DisaggregatedSet tables (BASELINE.json configs[3]: 2-role prefill/decode)
+# --------------------------------------------------------------------------- #
+@dataclass
+class DsTables:
+    ds: np.ndarray
+    roles: np.ndarray
+    revroles: np.ndarray
+
+    def algorithmic_bytes(self) -> int:
+        return (len(self.ds) * (R.DS_REC.itemsize + R.DS_OUT.itemsize)
+                + len(self.roles) * (R.DS_ROLE_REC.itemsize + R.DS_ROLE_OUT.itemsize)
+                + len(self.revroles) * (R.DS_REVROLE_REC.itemsize + 4))
+
+
+def make_ds(n_ds: int, n_roles_choices=(2,), max_old_revs=3, seed: int = SEED, fuzz: float = 0.0) -> DsTables:
+    """Random mid-rollout DisaggregatedSets.  C4: 2 roles (prefill:decode ratios from
+    {1:1, 2:1, 5:2, 10:1}, replicas <= 32), maxSurge in {1, 2, 25%}, 1-3 old revisions
+    with distinct creation stamps, some roles missing / drained / not yet ready."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n_roles = rng.choice(np.array(n_roles_choices), size=n_ds).astype(np.int64)
+    n_removed = np.where(rng.random(n_ds) < (0.1 + fuzz), 1, 0) * (n_roles < R.DS_MAX_ROLES)
+    n_all = n_roles + n_removed
+    n_old = rng.integers(0 if fuzz else 1, max_old_revs + 1, size=n_ds)
+    role_base = np.concatenate([[0], np.cumsum(n_all)[:-1]])
+    rr_count = (n_old + 1) * n_all
+    rev_base = np.concatenate([[0], np.cumsum(rr_count)[:-1]])
+    ds = R.aligned_empty(n_ds, R.DS_REC)
+    ds["uid_hash"] = _u64(rng, n_ds)
+    ds["role_base"], ds["n_roles"], ds["n_spec_roles"] = role_base, n_all, n_roles
+    ds["rev_base"], ds["n_old_revs"] = rev_base, n_old
+    ds["flags"] = np.where(rng.random(n_ds) < 0.9, R.DS_HAS_NEW_REVISION, 0)
+
+    NR = int(n_all.sum())
+    owner = np.repeat(np.arange(n_ds), n_all)
+    ridx = np.arange(NR) - role_base[owner]
+    in_spec = ridx < n_roles[owner]
+    roles = R.aligned_empty(NR, R.DS_ROLE_REC)
+    ratio = rng.choice(np.array([1, 2, 5, 10]), size=NR)
+    base = rng.integers(0 if fuzz else 1, 5, size=NR)
+    target = np.minimum(base * np.where(ridx == 0, ratio, rng.choice(np.array([1, 2]), size=NR)), 32)
+    roles["target_replicas"] = np.where(in_spec, target, 0)
+    kind = rng.integers(0, 6, size=NR)  # 0 none, 1 surge1, 2 surge2, 3 surge25%, 4 unavail1, 5 both
+    rflags = np.where(in_spec, R.ROLE_IN_SPEC, 0).astype(np.uint32)
+    rflags |= np.where(in_spec & (kind > 0), R.ROLE_HAS_ROLLING_CONFIG, 0).astype(np.uint32)
+    surge = np.select([kind == 1, kind == 2, kind == 3, kind == 5], [1, 2, 25, 1], 0)
+    rflags |= np.where(kind == 3, R.ROLE_SURGE_IS_PERCENT, 0).astype(np.uint32)
+    unav = np.select([kind == 4, kind == 5], [1, 2], 0)
+    if fuzz:
+        rflags |= np.where(rng.random(NR) < fuzz, R.ROLE_SURGE_INVALID, 0).astype(np.uint32)
+        rflags |= np.where(rng.random(NR) < fuzz, R.ROLE_UNAVAIL_IS_PERCENT, 0).astype(np.uint32)
+        unav = np.where(rng.random(NR) < fuzz, 50, unav)
+    roles["max_surge"], roles["max_unavailable"], roles["flags"] = surge, unav, rflags
+
+    NRR = int(rr_count.sum())
+    d_of = np.repeat(np.arange(n_ds), rr_count)
+    k = np.arange(NRR) - rev_base[d_of]
+    rev = k // n_all[d_of]
+    role = k % n_all[d_of]
+    is_new = rev == n_old[d_of]
+    tgt = roles["target_replicas"][role_base[d_of] + role].astype(np.int64)
+    rr = R.aligned_empty(NRR, R.DS_REVROLE_REC)
+    spec_role = role < n_roles[d_of]
+    exists = np.where(is_new, spec_role & (ds["flags"][d_of] & R.DS_HAS_NEW_REVISION != 0),
+                      rng.random(NRR) > (0.05 + fuzz))
+    # old revisions hold a random share of an initial count; the new one a random progress
+    initial = np.maximum(tgt + rng.integers(-2, 3, size=NRR), 0)
+    initial = np.where(spec_role, initial, rng.integers(1, 5, size=NRR))
+    progress = rng.random(NRR)
+    replicas = np.where(is_new, np.floor(progress * (tgt + 1)), np.ceil(progress * initial)).astype(np.int64)
+    replicas = np.where(rng.random(NRR) < 0.15, 0, replicas)
+    rr["replicas"] = np.where(exists, replicas, 0)
+    has_annot = rng.random(NRR) < 0.8
+    rr["initial_replicas"] = np.where(exists & ~is_new & has_annot, initial, -1)
+    not_ready = rng.random(NRR) < 0.1
+    rr["ready_replicas"] = np.where(exists, np.where(not_ready, np.maximum(replicas - 1, 0), replicas), 0)
+    stamp = (rev + 1) * 7 + (d_of % 5)  # distinct per revision within a DS
+    if fuzz:
+        stamp = np.where(rng.random(NRR) < fuzz, 3, stamp)  # equal stamps exercise the stable order
+    f = np.where(exists, R.RR_EXISTS, 0).astype(np.uint32) | (stamp.astype(np.uint32) << np.uint32(R.RR_TS_SHIFT))
+    f |= np.where(exists & (rng.random(NRR) < 0.02), R.RR_REPLICAS_NIL, 0).astype(np.uint32)
+    rr["replicas"] = np.where((f & R.RR_REPLICAS_NIL) != 0, 1, rr["replicas"])
+    rr["flags"] = np.where(exists, f, 0)
+    return DsTables(ds, roles, rr)

@@ -138,3 +138,28 @@ def ds_scale_down_old(replicas, order, current, target):
     if rc != 0:
         raise RuntimeError("lwso_ds_scale_down_old failed")
     return reps.reshape(len(order), n).tolist()
+
+
+def place(nodes, occupancy, n_domains, n_namespaces, reqs):
+    """Sequential statement of the placement spec (parity unpinned, build-defined)."""
+    out = R.aligned_empty(len(reqs), R.PLACE_OUT)
+    occ = None if occupancy is None else np.ascontiguousarray(occupancy, dtype=np.uint32)
+    rc = lib().lwso_place(R.ptr(nodes), len(nodes), R.ptr(occ), n_domains, n_namespaces, R.ptr(reqs), len(reqs),
+                          R.ptr(out))
+    if rc != 0:
+        raise RuntimeError(f"lwso_place failed: {rc}")
+    return out
+
+
+def sha1(strings) -> np.ndarray:
+    """SHA-1 of each string → (n, 20) uint8 (pkg/utils/utils.go:39-43 before hex encoding)."""
+    enc = [s.encode() if isinstance(s, str) else bytes(s) for s in strings]
+    offsets = np.zeros(len(enc) + 1, dtype=np.uint32)
+    if enc:
+        offsets[1:] = np.cumsum([len(b) for b in enc])
+    blob = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8)
+    digests = np.zeros((len(enc), 20), dtype=np.uint8)
+    rc = lib().lwso_sha1(R.ptr(blob), R.ptr(offsets), len(enc), R.ptr(digests))
+    if rc != 0:
+        raise RuntimeError("lwso_sha1 failed")
+    return digests

@@ -1,0 +1,158 @@
+/*
+ * lwse_oracle_place.c — sequential statement of the placement SPEC.
+ *
+ * TEST INFRASTRUCTURE ONLY (see lwse_oracle.c).
+ *
+ * PARITY UNPINNED: the reference has no node scoring.  It only emits the
+ * constraints — exclusive pod affinity / anti-affinity per topology domain
+ * (pkg/webhooks/pod_webhook.go:185-227, namespace-scoped: no Namespaces field
+ * on the terms), the workers' nodeSelector copied from the leader's node
+ * (pkg/controllers/pod_controller.go:297-336) and the PodGroup
+ * (pkg/schedulerprovider/volcano_provider.go:58-87); kube-scheduler / Volcano,
+ * whose sources are not part of the reference, do the actual filtering and
+ * scoring.  What follows is therefore this build's own specification of a
+ * placement round that honours those constraints, written sequentially; the
+ * CUDA kernels must reproduce it bit for bit (DESIGN.md "Placement").
+ *
+ * Spec
+ *   free[n]      = schedulable ∧ has-topology ? max(0, capacity[n] − occupancy[n]) : 0
+ *   dom_free[d]  = Σ free[n] over the nodes of domain d
+ *   key(r)       = unpinned(r) << 63 | (priority(r) >> 25) << 24 | index(r)     (smaller wins)
+ *   pinned r     (leader already scheduled on a node with a topology label) claims
+ *                its node's domain in its namespace; the smallest key among the
+ *                pinned claimants of a (namespace, domain) holds it (PLACED|PINNED),
+ *                the others get PINNED|CONFLICT.  Pinned claims are facts: they are
+ *                never displaced by unpinned requests (bit 63 of the key).
+ *   unpinned r   in ascending key order takes, among the (domain d, node n ∈ d) pairs
+ *                with   dom_free[d] ≥ size(r) ∧ free[n] ≥ 1 ∧ (ns(r), d) not held,
+ *                the pair with the largest score
+ *                   hi = (7 − min(7, (dom_free[d] − size)/size)) << 29 | mix(key_lo ^ d·φ) >> 3
+ *                   lo = min(free[n], 15) << 28 | mix(key_hi ^ n·ψ) >> 4
+ *                (best fit first, then a per-group rendezvous hash that spreads equal
+ *                candidates; ties → lower node index) and then holds (ns, d).
+ *                No feasible pair → UNSCHEDULABLE.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/lwse.h"
+
+#define LWSO_API __attribute__((visibility("default")))
+
+static uint32_t mix32(uint32_t x) { /* murmur3 finalizer */
+  x ^= x >> 16;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+
+uint64_t lwso_place_key(const lwse_place_req* r, uint32_t index, int pinned) {
+  return ((uint64_t)(pinned ? 0 : 1) << 63) | (((r->priority >> 25) & 0x7FFFFFFFFFull) << 24) |
+         (uint64_t)(index & 0xFFFFFFu);
+}
+
+typedef struct {
+  uint64_t key;
+  uint32_t idx;
+} order_ent;
+
+static int cmp_order(const void* a, const void* b) {
+  uint64_t x = ((const order_ent*)a)->key, y = ((const order_ent*)b)->key;
+  return x < y ? -1 : x > y ? 1 : 0;
+}
+
+LWSO_API int lwso_place(const lwse_node_rec* nodes, uint32_t n_nodes, const uint32_t* occupancy,
+                        uint32_t n_domains, uint32_t n_namespaces, const lwse_place_req* reqs,
+                        uint32_t n_reqs, lwse_place_out* out) {
+  if (n_reqs > 0xFFFFFFu) return LWSE_ERR_UNSUPPORTED;
+  uint32_t* free_ = (uint32_t*)calloc(n_nodes ? n_nodes : 1, sizeof(uint32_t));
+  uint32_t* dom_free = (uint32_t*)calloc(n_domains ? n_domains : 1, sizeof(uint32_t));
+  uint64_t* holder = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(n_namespaces * (uint64_t)n_domains + 1));
+  order_ent* order = (order_ent*)malloc(sizeof(order_ent) * (n_reqs ? n_reqs : 1));
+  memset(holder, 0xFF, sizeof(uint64_t) * (size_t)(n_namespaces * (uint64_t)n_domains + 1));
+  for (uint32_t n = 0; n < n_nodes; n++) {
+    const lwse_node_rec* nd = &nodes[n];
+    uint32_t occ = occupancy ? occupancy[n] : 0;
+    int usable = (nd->flags & LWSE_NODE_SCHEDULABLE) && (nd->flags & LWSE_NODE_HAS_TOPOLOGY) &&
+                 nd->domain_id < n_domains;
+    free_[n] = usable && nd->capacity > occ ? nd->capacity - occ : 0;
+    if (usable) dom_free[nd->domain_id] += free_[n];
+  }
+  /* classify, default outputs */
+  for (uint32_t i = 0; i < n_reqs; i++) {
+    const lwse_place_req* r = &reqs[i];
+    int pinned = r->leader_node != LWSE_NONE;
+    order[i].key = lwso_place_key(r, i, pinned);
+    order[i].idx = i;
+    out[i].domain_id = LWSE_NONE;
+    out[i].leader_node = pinned ? r->leader_node : LWSE_NONE;
+    out[i].flags = pinned ? LWSE_PLACE_PINNED : 0;
+    out[i].score = 0;
+  }
+  qsort(order, n_reqs, sizeof(order_ent), cmp_order);
+  for (uint32_t k = 0; k < n_reqs; k++) {
+    uint32_t i = order[k].idx;
+    const lwse_place_req* r = &reqs[i];
+    if (r->ns >= n_namespaces) {
+      out[i].flags |= LWSE_PLACE_UNSCHEDULABLE;
+      continue;
+    }
+    uint64_t* hold = holder + (size_t)r->ns * n_domains;
+    if (r->leader_node != LWSE_NONE) {
+      /* pinned: the leader's node decides */
+      if (r->leader_node >= n_nodes) continue; /* node object missing: no claim */
+      const lwse_node_rec* nd = &nodes[r->leader_node];
+      if (!(nd->flags & LWSE_NODE_HAS_TOPOLOGY) || nd->domain_id >= n_domains) continue;
+      out[i].domain_id = nd->domain_id;
+      if (hold[nd->domain_id] == ~0ull) {
+        hold[nd->domain_id] = order[k].key;
+        out[i].flags |= LWSE_PLACE_PLACED;
+      } else {
+        out[i].flags |= LWSE_PLACE_CONFLICT;
+      }
+      continue;
+    }
+    if (r->size < 1) {
+      out[i].flags |= LWSE_PLACE_UNSCHEDULABLE;
+      continue;
+    }
+    const uint32_t key_lo = (uint32_t)r->group_key, key_hi = (uint32_t)(r->group_key >> 32);
+    int found = 0;
+    uint64_t best = 0;
+    uint32_t best_n = 0;
+    for (uint32_t n = 0; n < n_nodes; n++) {
+      if (free_[n] < 1) continue;
+      uint32_t d = nodes[n].domain_id;
+      if (hold[d] != ~0ull) continue;
+      if (dom_free[d] < (uint32_t)r->size) continue;
+      uint32_t slack = (dom_free[d] - (uint32_t)r->size) / (uint32_t)r->size;
+      uint32_t bucket = slack > 7 ? 7 : slack;
+      uint32_t hi = ((7u - bucket) << 29) | (mix32(key_lo ^ (d * 0x9E3779B1u)) >> 3);
+      uint32_t lo = ((free_[n] > 15 ? 15u : free_[n]) << 28) | (mix32(key_hi ^ (n * 0x85EBCA77u)) >> 4);
+      uint64_t s = ((uint64_t)hi << 32) | lo;
+      if (!found || s > best) { /* ties keep the lower node index */
+        found = 1;
+        best = s;
+        best_n = n;
+      }
+    }
+    if (!found) {
+      out[i].flags |= LWSE_PLACE_UNSCHEDULABLE;
+      continue;
+    }
+    uint32_t d = nodes[best_n].domain_id;
+    hold[d] = order[k].key;
+    out[i].domain_id = d;
+    out[i].leader_node = best_n;
+    out[i].flags |= LWSE_PLACE_PLACED;
+    out[i].score = (uint32_t)(best >> 32);
+  }
+  free(free_);
+  free(dom_free);
+  free(holder);
+  free(order);
+  return LWSE_OK;
+}

@@ -1,0 +1,148 @@
+"""GPU parity for the placement round, the DisaggregatedSet sweep and the SHA-1
+group keys — CUDA engine through the C ABI vs the CPU oracle, bit-exact."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from lws_b200 import encoder, synth
+from lws_b200 import records as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from lws_b200.engine import Engine
+
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def same(got, want, what):
+    for name in got.dtype.names or [None]:
+        a, b = (got[name], want[name]) if name else (got, want)
+        if not np.array_equal(a, b):
+            i = int(np.flatnonzero(a != b)[0])
+            raise AssertionError(f"{what}.{name}: {int((a != b).sum())} rows differ; row {i}: got {a[i]} want {b[i]}")
+
+
+# ------------------------------------------------------------------ placement
+def place_case(n_lws, n_nodes, size, p_excl, p_unsched, seed, fuzz=False, capacity=4, nodes_per_domain=16):
+    p = synth.profile("fuzz" if fuzz else "C3", 1.0)
+    p.n_lws, p.n_nodes, p.size_choices, p.replicas_choices = n_lws, n_nodes, (size,), (1, 2)
+    p.p_exclusive, p.p_leader_unscheduled, p.node_capacity, p.nodes_per_domain = p_excl, p_unsched, capacity, nodes_per_domain
+    t = synth.make(p, seed=seed)
+    return t, encoder.encode_place_requests(t.lws, t.groups)
+
+
+@pytest.mark.parametrize(
+    "kw",
+    [dict(n_lws=300, n_nodes=3200, size=16, p_excl=0.6, p_unsched=0.5, seed=1),
+     dict(n_lws=2000, n_nodes=10000, size=64, p_excl=0.5, p_unsched=0.4, seed=2),
+     dict(n_lws=500, n_nodes=640, size=8, p_excl=0.9, p_unsched=0.7, seed=3),  # heavy contention
+     dict(n_lws=400, n_nodes=4096, size=4, p_excl=0.7, p_unsched=0.5, seed=4, fuzz=True),
+     dict(n_lws=50, n_nodes=60000, size=8, p_excl=1.0, p_unsched=0.5, seed=5, nodes_per_domain=100),  # node words in global
+     dict(n_lws=64, n_nodes=48, size=2, p_excl=1.0, p_unsched=1.0, seed=6, nodes_per_domain=2, capacity=1)],
+)
+def test_placement_matches_spec_oracle(engine, kw):
+    import oracle
+
+    t, reqs = place_case(**kw)
+    engine.upload_nodes(t.nodes, t.n_domains)
+    _, _, occ = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, want_occupancy=True)
+    for occupancy in (None, occ // 8):
+        want = oracle.place(t.nodes, occupancy, t.n_domains, 1, reqs)
+        got, rounds = engine.place_host(reqs, occupancy, 1)
+        same(got, want, "place_out")
+        assert rounds >= 1
+
+
+def test_placement_namespaces_and_empty(engine):
+    import oracle
+
+    t, reqs = place_case(n_lws=400, n_nodes=2048, size=8, p_excl=0.8, p_unsched=0.6, seed=8)
+    reqs["ns"] = np.arange(len(reqs)) % 3
+    reqs["ns"][5] = 7  # out of range → unschedulable
+    engine.upload_nodes(t.nodes, t.n_domains)
+    same(engine.place_host(reqs, None, 3)[0], oracle.place(t.nodes, None, t.n_domains, 3, reqs), "place_out")
+    empty = R.aligned_empty(0, R.PLACE_REQ)
+    assert len(engine.place_host(empty, None, 1)[0]) == 0
+
+
+def test_placement_occupancy_from_the_sweep(engine):
+    """The occupancy vector the LWS sweep counts feeds the placement round."""
+    import oracle
+
+    t, reqs = place_case(n_lws=1000, n_nodes=4096, size=16, p_excl=0.5, p_unsched=0.5, seed=11, capacity=40)
+    engine.upload_nodes(t.nodes, t.n_domains)
+    _, _, occ_gpu = engine.sweep_lws_host(t.lws, t.groups, t.pod_state, t.pod_ident, flags=t.flags, want_occupancy=True)
+    want = oracle.place(t.nodes, occ_gpu, t.n_domains, 1, reqs)
+    same(engine.place_host(reqs, occ_gpu, 1)[0], want, "place_out")
+
+
+# ------------------------------------------------------------------------- DS
+@pytest.mark.parametrize(
+    "kw",
+    [dict(n_ds=5000, n_roles_choices=(2,), seed=1), dict(n_ds=3000, n_roles_choices=(2, 3, 4, 5, 6, 9, 10), seed=2),
+     dict(n_ds=4000, n_roles_choices=(2, 3, 10), seed=3, fuzz=0.1), dict(n_ds=1, n_roles_choices=(2,), seed=4)],
+)
+def test_ds_sweep_matches_oracle(engine, kw):
+    import oracle
+
+    t = synth.make_ds(**kw)
+    want = oracle.sweep_ds(t.ds, t.roles, t.revroles)
+    got = engine.sweep_ds_host(t.ds, t.roles, t.revroles)
+    same(got[0], want[0], "ds_out")
+    same(got[1], want[1], "role_out")
+    same(got[2], want[2], "revrole_out")
+    flags = want[0]["flags"]
+    if kw["n_ds"] >= 1000:  # the generator reaches every branch
+        for bit in (R.DOUT_ROLLING, R.DOUT_INIT, R.DOUT_STABLE, R.DOUT_STEP, R.DOUT_NEW_READY):
+            assert (flags & bit).any(), f"no DS exercises flag {bit}"
+
+
+def test_ds_reference_sequences_on_gpu(engine):
+    """planner_test.go's 22 exact sequences, advanced step by step by the CUDA planner."""
+    import json
+    import os
+
+    from lws_b200 import api
+
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "planner_sequences.json")))["cases"]
+    for c in cases:
+        cfgs = [api.RollingUpdateConfiguration(maxSurge=ms, maxUnavailable=mu) for ms, mu in c["config"]]
+        ds = api.DisaggregatedSet("t", roles=[api.DisaggregatedRoleSpec(f"r{i}", c["target"][i], cfgs[i]) for i in range(2)])
+        old, new = list(c["source"]), [0, 0]
+        seq = [[old[:], new[:]]]
+        for _ in range(100):
+            ch = []
+            for i in range(2):
+                ch.append(api.ChildLWS(f"r{i}", "old", old[i], old[i], 1.0,
+                                       {api.DSInitialReplicasAnnotationKey: str(c["source"][i])}))
+                ch.append(api.ChildLWS(f"r{i}", "new", new[i], new[i], 2.0))
+            t = encoder.encode_ds([encoder.DsItem(ds, "new", ch)])
+            ds_out, role_out, _ = engine.sweep_ds_host(t.ds, t.roles, t.revroles)
+            if not ds_out[0]["flags"] & R.DOUT_STEP:
+                break
+            old = [int(role_out[i]["next_old"]) for i in range(2)]
+            new = [int(role_out[i]["next_new"]) for i in range(2)]
+            seq.append([old[:], new[:]])
+        # an all-zero old revision is not "rolling" any more: the reference sequence's tail
+        # (drain to zero) is the last step the rolling path can emit
+        assert seq == c["steps"][: len(seq)] and len(seq) >= len(c["steps"]) - 1, c["name"]
+
+
+# ---------------------------------------------------------------------- SHA-1
+def test_group_keys_kats_and_hashlib(engine):
+    kats = {"default/test-sample": "95e88034e460983f51a9952fe128729fbc0663b5",
+            "default/podName": "390b34ab671d29e9997d7d4252b8bbf8da02f5b7",
+            "leaderworkerset/test-sample": "39f5d7e9122b9d94d3932e3720b43fd3b56347e8"}
+    got = engine.group_keys_host(list(kats))
+    assert [d.tobytes().hex() for d in got] == list(kats.values())
+    msgs = [("x" * n).encode() + bytes([n % 251]) for n in range(0, 300)] + [b"", b"a" * 5000]
+    msgs += [f"ns-{i % 7}/lws-{i}-{i % 13}".encode() for i in range(20000)]
+    got = engine.group_keys_host(msgs)
+    for m, d in zip(msgs, got):
+        assert d.tobytes() == hashlib.sha1(m).digest()

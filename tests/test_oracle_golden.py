@@ -65,3 +65,29 @@ def test_integration_trace(oracle_sweep, name):
         for k, (g, w) in enumerate(zip(got, want)):
             if w is not None:
                 assert g == w, f"{name} step {i}: field {k} got {got} want {want}"
+
+
+# pkg/webhooks/pod_webhook_test.go:29-53 (genGroupUniqueKey) + hashlib cross-check
+@pytest.mark.parametrize(
+    "ns,pod,want",
+    [("default", "test-sample", "95e88034e460983f51a9952fe128729fbc0663b5"),
+     ("default", "podName", "390b34ab671d29e9997d7d4252b8bbf8da02f5b7"),
+     ("leaderworkerset", "test-sample", "39f5d7e9122b9d94d3932e3720b43fd3b56347e8")],
+)
+def test_group_unique_key_kats(ns, pod, want):
+    assert oracle.sha1([f"{ns}/{pod}"])[0].tobytes().hex() == want
+
+
+def test_sha1_against_hashlib_all_padding_lengths():
+    import hashlib
+
+    msgs = [("x" * n).encode() + bytes([n % 251]) for n in range(0, 200)] + [b"", b"a" * 1000]
+    got = oracle.sha1(msgs)
+    for m, d in zip(msgs, got):
+        assert d.tobytes() == hashlib.sha1(m).digest()
+
+
+# pkg/webhooks/pod_webhook_test.go:272-305 (getSubGroupIndex)
+@pytest.mark.parametrize("pod_count,sg,widx,want", [(4, 2, 2, 1), (5, 2, 2, 0), (9, 4, 8, 1), (8, 4, 7, 1), (8, 4, 3, 0)])
+def test_sub_group_index(pod_count, sg, widx, want):
+    assert oracle.lib().lwso_sub_group_index(pod_count, sg, widx) == want
