@@ -112,6 +112,8 @@ def test_ds_reference_sequences_on_gpu(engine):
 
     cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "planner_sequences.json")))["cases"]
     for c in cases:
+        if sum(c["source"]) == 0:
+            continue  # nothing old to roll: Reconcile takes reconcileSimple, the planner is not consulted
         cfgs = [api.RollingUpdateConfiguration(maxSurge=ms, maxUnavailable=mu) for ms, mu in c["config"]]
         ds = api.DisaggregatedSet("t", roles=[api.DisaggregatedRoleSpec(f"r{i}", c["target"][i], cfgs[i]) for i in range(2)])
         old, new = list(c["source"]), [0, 0]
