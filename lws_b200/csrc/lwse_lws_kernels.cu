@@ -22,6 +22,8 @@
 //                        as three reductions.  32 B out per object.
 //
 // All three are integer/compare kernels bound by HBM traffic.
+#include <cstdlib>
+
 #include "lwse_device.cuh"
 
 namespace lwse {
@@ -65,6 +67,8 @@ __global__ void __launch_bounds__(256) pod_scan_kernel(const PodScanArgs a) {
   const uint64_t n_words = (a.n_pods + 31u) >> 5;
   constexpr uint64_t kPodsPerChunk = 128ull * U;  // 32 lanes x 4 pods x U
   const uint4* vec = reinterpret_cast<const uint4*>(a.state);
+  pdl_launch_dependents();
+  bool waited = false;
   for (uint64_t base = warp * kPodsPerChunk; base < a.n_pods; base += n_warps * kPodsPerChunk) {
     uint4 v[U];
 #pragma unroll
@@ -78,6 +82,10 @@ __global__ void __launch_bounds__(256) pod_scan_kernel(const PodScanArgs a) {
         v[j].z = idx + 2u < a.n_pods ? __ldg(a.state + idx + 2u) : 0u;
         v[j].w = 0u;
       }
+    }
+    if (!waited) {  // the bitmaps (and counters) may still be read by the previous sweep's group pass
+      pdl_wait_prior();
+      waited = true;
     }
 #pragma unroll
     for (int j = 0; j < U; j++) {
@@ -137,6 +145,8 @@ __global__ void __launch_bounds__(256) group_sweep_kernel(const GroupSweepArgs a
   constexpr uint32_t kTilesPerBlock = 256 / W;
   const uint32_t lane = threadIdx.x & (W - 1);
   const uint32_t stride = gridDim.x * kTilesPerBlock;
+  pdl_launch_dependents();
+  bool waited = false;
   for (uint32_t g = blockIdx.x * kTilesPerBlock + threadIdx.x / W; g < a.n_groups; g += stride) {
     const uint4* row = reinterpret_cast<const uint4*>(a.groups + g);
     const uint4 ca = ldg_cached(row + 0), cb = ldg_cached(row + 1), cc = ldg_cached(row + 2),
@@ -144,11 +154,17 @@ __global__ void __launch_bounds__(256) group_sweep_kernel(const GroupSweepArgs a
     const uint32_t pod_base = cc.z, pod_count = cc.w, lws_index = cd.x, gflags = cd.y;
     uint32_t oflags = 0, first_out = LWSE_NONE, domain = LWSE_NONE;
     int32_t worker_replicas = 0;
-    if (lws_index >= a.n_lws || (uint64_t)pod_base + pod_count > a.n_pods) {
+    const bool bad = lws_index >= a.n_lws || (uint64_t)pod_base + pod_count > a.n_pods;
+    // owner row: only its first 16 bytes (rev_hash, size, flags)
+    uint4 L = make_uint4(0, 0, 0, 0);
+    if (!bad) L = ldg_cached(reinterpret_cast<const uint4*>(a.lws + lws_index));
+    if (!waited) {  // everything above is input; the scan's bitmaps and group_out come next
+      pdl_wait_prior();
+      waited = true;
+    }
+    if (bad) {
       oflags = LWSE_GOUT_BAD_TABLE;
     } else {
-      // owner row: only its first 16 bytes (rev_hash, size, flags)
-      const uint4 L = ldg_cached(reinterpret_cast<const uint4*>(a.lws + lws_index));
       const int32_t size = (int32_t)L.z;
       const uint32_t lflags = L.w;
       const uint32_t policy = (lflags & LWSE_LWS_RESTART_MASK) >> LWSE_LWS_RESTART_SHIFT;
@@ -183,40 +199,72 @@ __global__ void __launch_bounds__(256) group_sweep_kernel(const GroupSweepArgs a
             LWSE_GRP_WSTS_FOUND | LWSE_GRP_WSTS_OWNER_IS_POD | LWSE_GRP_WSTS_OWNER_NAME_MATCH;
         const bool wsts_chain_ok = (gflags & kChain) == kChain && cc.x == cb.z;  // sts owner uid == leader uid
         uint32_t acc = 0, first = LWSE_NONE;
+        // The pods to visit are collected four at a time so that their state and
+        // identity loads are all in flight together (one DRAM round trip per batch
+        // instead of one per pod).
+        auto visit = [&](const uint32_t* ev, int cnt) {
+          uint32_t bits[4], id_lo[4], id_hi[4], id_owner[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (k < cnt) {
+              const uint32_t p = ev[k];
+              bits[k] = __ldg(a.pod_state + p);
+              const uint32_t* idp = reinterpret_cast<const uint32_t*>(a.pod_ident + p);
+              id_lo[k] = __ldg(idp);
+              id_hi[k] = __ldg(idp + 1);
+              id_owner[k] = __ldg(idp + 2);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (k < cnt) {
+              const uint32_t b = bits[k];
+              bool cand, deleting;
+              if (b & LWSE_POD_IS_LEADER) {
+                cand = true;  // leader = pod (:251)
+                deleting = b & LWSE_POD_DELETING;
+              } else if (!(b & LWSE_POD_NAME_OK)) {
+                acc |= LWSE_GOUT_RESTART_ERROR;  // :230
+                cand = false;
+                deleting = false;
+              } else {
+                const uint32_t kind = (b & LWSE_POD_OWNER_MASK) >> LWSE_POD_OWNER_SHIFT;
+                // workerPodBelongsToLeader :268-295
+                const bool belongs = (b & LWSE_POD_OWNER_NAME_MATCH) &&
+                                     ((kind == 1u && id_owner[k] == cb.z) ||
+                                      (kind == 2u && id_owner[k] == cb.w && wsts_chain_ok));
+                cand = leader_found && id_lo[k] == ca.x && id_hi[k] == ca.y && belongs;  // :239
+                deleting = gflags & LWSE_GRP_POD_DELETING;
+              }
+              if (cand) {
+                acc |= deleting ? LWSE_GOUT_LEADER_DELETING : LWSE_GOUT_DELETE_LEADER;  // :255 / :259
+                if (b & LWSE_POD_IS_LEADER) acc |= 0x80000000u;
+                first = min(first, ev[k] - pod_base);
+              }
+            }
+          }
+        };
+        uint32_t ev[4];
+        int cnt = 0;
         for (uint32_t w = w_first + lane; w <= w_last; w += W) {
           const uint32_t lo = w == w_first ? (pod_base & 31u) : 0u;
           const uint32_t hi = w == w_last ? (((pod_end - 1u) & 31u) + 1u) : 32u;
           uint32_t m = __ldg(a.event_bits + w) & bit_range(lo, hi);
           while (m) {
-            const uint32_t p = (w << 5) + (__ffs(m) - 1u);  // pod row, ascending within the lane
+            const uint32_t p = (w << 5) + (__ffs(m) - 1u);
             m &= m - 1u;
-            // state and identity are independent loads: both in flight at once
-            const uint32_t bits = __ldg(a.pod_state + p);
-            const uint32_t* idp = reinterpret_cast<const uint32_t*>(a.pod_ident + p);
-            const uint32_t id_lo = __ldg(idp), id_hi = __ldg(idp + 1), id_owner = __ldg(idp + 2);
-            bool cand, deleting;
-            if (bits & LWSE_POD_IS_LEADER) {
-              cand = true;  // leader = pod (:251)
-              deleting = bits & LWSE_POD_DELETING;
-            } else if (!(bits & LWSE_POD_NAME_OK)) {
-              acc |= LWSE_GOUT_RESTART_ERROR;  // :230
-              continue;
-            } else {
-              const uint32_t kind = (bits & LWSE_POD_OWNER_MASK) >> LWSE_POD_OWNER_SHIFT;
-              // workerPodBelongsToLeader :268-295
-              const bool belongs = (bits & LWSE_POD_OWNER_NAME_MATCH) &&
-                                   ((kind == 1u && id_owner == cb.z) ||
-                                    (kind == 2u && id_owner == cb.w && wsts_chain_ok));
-              cand = leader_found && id_lo == ca.x && id_hi == ca.y && belongs;  // :239
-              deleting = gflags & LWSE_GRP_POD_DELETING;
-            }
-            if (cand) {
-              acc |= deleting ? LWSE_GOUT_LEADER_DELETING : LWSE_GOUT_DELETE_LEADER;  // :255 / :259
-              if (bits & LWSE_POD_IS_LEADER) acc |= 0x80000000u;
-              first = min(first, p - pod_base);
+            // fixed-slot insert keeps ev[] in registers
+            if (cnt == 0) ev[0] = p;
+            else if (cnt == 1) ev[1] = p;
+            else if (cnt == 2) ev[2] = p;
+            else ev[3] = p;
+            if (++cnt == 4) {
+              visit(ev, 4);
+              cnt = 0;
             }
           }
         }
+        if (cnt) visit(ev, cnt);
         acc = tile_or<W>(acc);
         first_out = tile_min<W>(first);
         leader_deleted = acc & 0x80000000u;
@@ -317,10 +365,16 @@ __global__ void __launch_bounds__(256) lws_sweep_kernel(const LwsSweepArgs a) {
   constexpr uint32_t kTilesPerBlock = 256 / W;
   const uint32_t lane = threadIdx.x & (W - 1);
   const uint32_t n_tiles = gridDim.x * kTilesPerBlock;
+  pdl_launch_dependents();
+  bool waited = false;
   for (uint32_t i = blockIdx.x * kTilesPerBlock + threadIdx.x / W; i < a.n_lws; i += n_tiles) {
     const uint4* row = reinterpret_cast<const uint4*>(a.lws + i);
     const uint4 r0 = ldg_stream(row + 0), r1 = ldg_stream(row + 1), r2 = ldg_stream(row + 2),
                 r3 = ldg_stream(row + 3);
+    if (!waited) {  // the object rows are input; the group pass's flag words come next
+      pdl_wait_prior();
+      waited = true;
+    }
     const int32_t size = (int32_t)r0.z;
     const uint32_t lflags = r0.w;
     const int32_t R = (int32_t)r1.x, P = (int32_t)r1.y;
@@ -484,6 +538,12 @@ __global__ void __launch_bounds__(256) lws_sweep_kernel(const LwsSweepArgs a) {
 // --------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------
+// LWSE_NO_PDL=1 turns programmatic dependent launch off (A/B measurements).
+static const bool g_pdl = [] {
+  const char* v = getenv("LWSE_NO_PDL");
+  return !(v && v[0] == '1');
+}();
+
 static int pick_tile(uint64_t items, uint64_t owners) {
   // lanes per owner: next power of two >= average items per owner, in [1, 32]
   if (owners == 0) return 1;
@@ -510,8 +570,7 @@ static cudaError_t launch_group(const GroupSweepArgs& a, int sm_count, cudaStrea
   if (resident == 0) resident = resident_ctas(group_sweep_kernel<W>, sm_count);
   (void)resident;
   const uint32_t want = (a.n_groups + kTilesPerBlock - 1) / kTilesPerBlock;
-  group_sweep_kernel<W><<<want < (1u << 20) ? want : (1u << 20), 256, 0, s>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(group_sweep_kernel<W>, dim3(want < (1u << 20) ? want : (1u << 20)), dim3(256), 0, s, g_pdl, a);
 }
 
 template <int W>
@@ -520,8 +579,7 @@ static cudaError_t launch_lws(const LwsSweepArgs& a, int sm_count, cudaStream_t 
   static uint32_t resident = 0;
   if (resident == 0) resident = resident_ctas(lws_sweep_kernel<W>, sm_count);
   const uint32_t want = (a.n_lws + kTilesPerBlock - 1) / kTilesPerBlock;
-  lws_sweep_kernel<W><<<want < resident ? want : resident, 256, 0, s>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(lws_sweep_kernel<W>, dim3(want < resident ? want : resident), dim3(256), 0, s, g_pdl, a);
 }
 
 constexpr int kScanUnroll = 4;  // 128-bit loads per lane per chunk: 4 x 512 B = 2 KB in flight per warp
@@ -555,10 +613,9 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
     const uint64_t want = (chunks + 7) / 8;
     const uint32_t grid = (uint32_t)(want < (1u << 20) ? want : (1u << 20));
     if (t->node_occupancy)
-      pod_scan_kernel<kScanUnroll, true><<<grid, 256, 0, s>>>(a);
+      e = launch_pdl(pod_scan_kernel<kScanUnroll, true>, dim3(grid), dim3(256), 0, s, false, a);  // follows a memset
     else
-      pod_scan_kernel<kScanUnroll, false><<<grid, 256, 0, s>>>(a);
-    e = cudaGetLastError();
+      e = launch_pdl(pod_scan_kernel<kScanUnroll, false>, dim3(grid), dim3(256), 0, s, g_pdl, a);
     if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
     launches++;
   }
