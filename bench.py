@@ -128,21 +128,42 @@ def make_tables(args, rank):
     return synth.make(args.workload, args.scale, seed=synth.SEED + rank)
 
 
-def cpu_oracle_rate(t, threads, min_seconds=1.0, max_reps=50):
-    """groups/s of the CPU oracle over the whole workload, `threads` host threads."""
-    import oracle
-    from lws_b200 import records as R
+def _cpu_step_fn(t, threads):
+    """One CPU step = the oracle's sweep over the whole workload (+ the placement spec
+    round when the workload has exclusive-topology groups)."""
     import ctypes as C
+
+    import oracle
+    from lws_b200 import encoder
+    from lws_b200 import records as R
 
     lws_out = R.aligned_empty(len(t.lws), R.LWS_OUT)
     group_out = R.aligned_empty(len(t.groups), R.GROUP_OUT)
-    tab = R.LwsTables(R.ptr(t.lws), len(t.lws), R.ptr(t.groups), len(t.groups), R.ptr(t.pod_state), R.ptr(t.pod_ident), len(t.pod_state),
-                      R.ptr(lws_out), R.ptr(group_out), None, t.flags)
-    fn = oracle.lib().lwso_sweep_lws
-    fn(C.byref(tab), R.ptr(t.nodes), len(t.nodes), threads)  # warm
+    tab = R.LwsTables(R.ptr(t.lws), len(t.lws), R.ptr(t.groups), len(t.groups), R.ptr(t.pod_state),
+                      R.ptr(t.pod_ident), len(t.pod_state), R.ptr(lws_out), R.ptr(group_out), None, t.flags)
+    reqs = encoder.encode_place_requests(t.lws, t.groups)
+    sched = (t.pod_state & R.POD_SCHEDULED) != 0
+    occ = np.bincount((t.pod_state[sched] >> R.POD_NODE_SHIFT).astype(np.int64), minlength=len(t.nodes)).astype(np.uint32)
+    pout = R.aligned_empty(len(reqs), R.PLACE_OUT)
+    lib = oracle.lib()
+    keep = (lws_out, group_out, reqs, occ, pout, tab)
+
+    def step():
+        lib.lwso_sweep_lws(C.byref(tab), R.ptr(t.nodes), len(t.nodes), threads)
+        if len(reqs):
+            lib.lwso_place(R.ptr(t.nodes), len(t.nodes), R.ptr(occ), t.n_domains, 1, R.ptr(reqs), len(reqs), R.ptr(pout))
+
+    step.keep = keep
+    return step
+
+
+def cpu_oracle_rate(t, threads, min_seconds=1.0, max_reps=50):
+    """groups/s of the CPU oracle over the whole workload, `threads` host threads."""
+    step = _cpu_step_fn(t, threads)
+    step()  # warm
     reps, t0 = 0, time.perf_counter()
     while True:
-        fn(C.byref(tab), R.ptr(t.nodes), len(t.nodes), threads)
+        step()
         reps += 1
         dt = time.perf_counter() - t0
         if dt >= min_seconds or reps >= max_reps:
@@ -157,20 +178,12 @@ def run_reference(args):
         return
     t = make_tables(args, 0)
     threads = host_threads()
-    import oracle
-    from lws_b200 import records as R
-    import ctypes as C
-
-    lws_out = R.aligned_empty(len(t.lws), R.LWS_OUT)
-    group_out = R.aligned_empty(len(t.groups), R.GROUP_OUT)
-    tab = R.LwsTables(R.ptr(t.lws), len(t.lws), R.ptr(t.groups), len(t.groups), R.ptr(t.pod_state), R.ptr(t.pod_ident), len(t.pod_state),
-                      R.ptr(lws_out), R.ptr(group_out), None, t.flags)
-    fn = oracle.lib().lwso_sweep_lws
+    step = _cpu_step_fn(t, threads)
     for _ in range(max(args.warmup, 1)):
-        fn(C.byref(tab), R.ptr(t.nodes), len(t.nodes), threads)
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        fn(C.byref(tab), R.ptr(t.nodes), len(t.nodes), threads)
+        step()
     dt = time.perf_counter() - t0
     value = len(t.groups) * args.steps / dt
     line = {
@@ -179,7 +192,8 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/u64 (integer compare)",
         "data": "synthetic", "config": t.describe(),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"full {t.profile.name} workload per step, {args.steps} steps"},
+                         "sample": f"full {t.profile.name} workload per step (sweep on {threads} threads + placement "
+                                   f"spec round), {args.steps} steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU port of the reference's Go arithmetic (no Go toolchain here); excludes the "
                 "informer-cache List/DeepCopy and API round-trips that dominate the real reconciler",
@@ -191,6 +205,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
+    from lws_b200 import encoder
     from lws_b200 import records as R
     from lws_b200.engine import Engine
 
@@ -207,14 +222,22 @@ def run_ours(args):
     t = make_tables(args, rank)
     eng = Engine(local_rank)
     eng.upload_nodes(t.nodes, t.n_domains)
-    n_lws, n_grp, n_pod = len(t.lws), len(t.groups), len(t.pod_state)
+    n_lws, n_grp, n_pod, n_nodes = len(t.lws), len(t.groups), len(t.pod_state), len(t.nodes)
     algo_bytes = t.algorithmic_bytes()
+    # placement: one request per group of an exclusive-topology object; the per-node
+    # occupancy of this shard's pods is a resident input column (the host maintains it
+    # incrementally from pod events; lwse can recount it)
+    reqs = encoder.encode_place_requests(t.lws, t.groups)
+    n_req = len(reqs)
+    place_on = n_req > 0
+    sched = (t.pod_state & R.POD_SCHEDULED) != 0
+    occ_host = np.bincount((t.pod_state[sched] >> R.POD_NODE_SHIFT).astype(np.int64), minlength=n_nodes).astype(np.uint32)
 
     # ---- resident copies, rotated so that the working set exceeds L2 ----
     copies = max(2, int(np.ceil(2.5 * L2_BYTES / algo_bytes)) + 1)  # bytes a sweep touches x copies > 2.5 x L2
 
     def up(a):
-        return torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
 
     sets = []
     for _ in range(copies):
@@ -222,6 +245,29 @@ def run_ours(args):
             lws=up(t.lws), grp=up(t.groups), pst=up(t.pod_state), pid=up(t.pod_ident),
             lo=torch.empty(n_lws * R.LWS_OUT.itemsize, dtype=torch.uint8, device=dev),
             go=torch.empty(n_grp * R.GROUP_OUT.itemsize, dtype=torch.uint8, device=dev)))
+    d_occ = torch.from_numpy(occ_host.view(np.int32)).to(dev)
+    d_reqs = up(reqs) if place_on else None
+    # multi-GPU placement: ONE all-gather of [occupancy | request count | requests] per step
+    req_cap = 0
+    if world > 1 and place_on is not None:
+        cap = torch.tensor([n_req], dtype=torch.int64, device=dev)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX)
+        req_cap = int(cap.item())
+        place_on = req_cap > 0
+    if world > 1 and place_on:
+        pack_words = n_nodes + 4 + req_cap * (R.PLACE_REQ.itemsize // 4)
+        send = torch.zeros(pack_words, dtype=torch.int32, device=dev)
+        send[:n_nodes] = d_occ
+        send[n_nodes] = n_req
+        if n_req:
+            send[n_nodes + 4: n_nodes + 4 + n_req * 8] = d_reqs.view(torch.int32)
+        gathered = torch.empty(world * pack_words, dtype=torch.int32, device=dev)
+        all_reqs = torch.zeros(world * req_cap * R.PLACE_REQ.itemsize, dtype=torch.uint8, device=dev)
+        all_occ = torch.empty(n_nodes, dtype=torch.int32, device=dev)
+        d_pout = torch.empty(max(world * req_cap, 1) * R.PLACE_OUT.itemsize, dtype=torch.uint8, device=dev)
+    else:
+        d_pout = torch.empty(max(n_req, 1) * R.PLACE_OUT.itemsize, dtype=torch.uint8, device=dev)
+
     # time on the stream the kernels are launched on: the engine's own stream
     stream = torch.cuda.ExternalStream(eng.stream, device=dev)
     sptr = eng.stream
@@ -231,80 +277,112 @@ def run_ours(args):
         eng.sweep_lws_device(s["lws"], n_lws, s["grp"], n_grp, s["pst"], s["pid"], n_pod, s["lo"], s["go"], None,
                              flags=flags, stream=sptr)
 
+    def place():
+        if not place_on:
+            return
+        if world == 1:
+            eng.place_device(d_reqs, n_req, d_occ, 1, d_pout, stream=sptr)
+            return
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(gathered, send)  # the single collective of a step
+            g = gathered.view(world, pack_words)
+            torch.sum(g[:, :n_nodes], dim=0, out=all_occ)  # occupancy of every shard
+            all_reqs.view(world, -1).copy_(g[:, n_nodes + 4:].contiguous().view(torch.uint8).view(world, -1))
+        # every rank solves the whole (small) placement problem: identical inputs, deterministic
+        # kernel → identical results, each rank keeps the rows of its own groups.  Padding rows are
+        # zero (size 0 → unschedulable, never claim a domain).
+        eng.place_device(all_reqs, world * req_cap, all_occ, 1, d_pout, stream=sptr)
+
+    def step(i, flags):
+        sweep(i, flags)
+        place()
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(flags, steps, warmup):
+    def timed(fn, steps, warmup):
         for i in range(warmup):
-            sweep(i, flags)
+            fn(i)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = eng.launch_count
         e0.record(stream)
         for i in range(steps):
-            sweep(warmup + i, flags)
+            fn(warmup + i)
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
-        return ms / steps, eng.launch_count - l0
+        return e0.elapsed_time(e1) / steps, eng.launch_count - l0
 
     SCAN_ONLY = R.SWEEP_SKIP_GROUP_PASS | R.SWEEP_SKIP_LWS_PASS
     GROUP_ONLY = R.SWEEP_SKIP_POD_SCAN | R.SWEEP_SKIP_LWS_PASS
     LWS_ONLY = R.SWEEP_SKIP_POD_SCAN | R.SWEEP_SKIP_GROUP_PASS
+    W = max(args.warmup, 3)
     with ClockSampler(local_rank) as clk:
-        ms_step, launches = timed(t.flags, args.steps, max(args.warmup, 3))
+        ms_step, launches = timed(lambda i: step(i, t.flags), args.steps, W)
         # each pass alone (same rotating inputs), for the per-kernel roofline
-        ms_scan, _ = timed(t.flags | SCAN_ONLY, args.steps, 3)
-        ms_group, _ = timed(t.flags | GROUP_ONLY, args.steps, 3)
-        ms_lws, _ = timed(t.flags | LWS_ONLY, args.steps, 3)
+        ms_sweep, _ = timed(lambda i: sweep(i, t.flags), args.steps, 3)
+        ms_scan, _ = timed(lambda i: sweep(i, t.flags | SCAN_ONLY), args.steps, 3)
+        ms_group, _ = timed(lambda i: sweep(i, t.flags | GROUP_ONLY), args.steps, 3)
+        ms_lws, _ = timed(lambda i: sweep(i, t.flags | LWS_ONLY), args.steps, 3)
+        ms_place = timed(lambda i: place(), args.steps, 3)[0] if place_on else 0.0
         # keep the GPU under the same load long enough for nvidia-smi to sample clocks
         t_end = time.perf_counter() + 1.0
         i = 0
         while time.perf_counter() < t_end:
-            for _ in range(200):
-                sweep(i, t.flags)
+            for _ in range(100):
+                step(i, t.flags)
                 i += 1
             torch.cuda.synchronize()
     clocks = clk.summary()
+    rounds = eng.place_device(d_reqs, n_req, d_occ, 1, d_pout, stream=sptr, want_rounds=True) if (place_on and world == 1) else None
 
-    # correctness of what was just timed: compare one resident result with a fresh host sweep
-    # ---- end to end through the host entry point, pinned buffers ----
+    # ---- end to end through the host entry points, pinned buffers ----
     def pinned(a):
-        ten = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
-        view = ten.numpy().view(a.dtype)
-        view[:] = a
+        ten = torch.empty(max(a.nbytes, 16), dtype=torch.uint8).pin_memory()
+        view = ten.numpy()[: a.nbytes].view(a.dtype)
+        view[...] = a
         return ten, view
 
-    keep = []
-    h = {}
+    keep, h = [], {}
     for name, arr in (("lws", t.lws), ("groups", t.groups), ("pst", t.pod_state), ("pid", t.pod_ident),
-                      ("lo", R.aligned_empty(n_lws, R.LWS_OUT)), ("go", R.aligned_empty(n_grp, R.GROUP_OUT))):
+                      ("lo", R.aligned_empty(n_lws, R.LWS_OUT)), ("go", R.aligned_empty(n_grp, R.GROUP_OUT)),
+                      ("reqs", reqs), ("occ", occ_host)):
         ten, view = pinned(arr)
         keep.append(ten)
         h[name] = view
-    for _ in range(3):
+
+    def e2e_step():
         eng.sweep_lws_host(h["lws"], h["groups"], h["pst"], h["pid"], flags=t.flags, out=(h["lo"], h["go"]))
+        if n_req and world == 1:
+            return eng.place_host(h["reqs"], h["occ"], 1)[0]
+        return None
+
+    for _ in range(3):
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        eng.sweep_lws_host(h["lws"], h["groups"], h["pst"], h["pid"], flags=t.flags, out=(h["lo"], h["go"]))
+        pout_host = e2e_step()
     e2e_s = (time.perf_counter() - t0) / args.e2e_steps
     # the resident result must equal the host-path result
     same = (sets[0]["lo"].cpu().numpy().tobytes() == h["lo"].tobytes()
             and sets[0]["go"].cpu().numpy().tobytes() == h["go"].tobytes())
+    if pout_host is not None:
+        same = same and d_pout.cpu().numpy()[: n_req * R.PLACE_OUT.itemsize].tobytes() == pout_host.tobytes()
     if not same:
         raise SystemExit("bench.py: resident and host-path results differ")
 
     # ---- max over ranks ----
-    stats = torch.tensor([ms_step, ms_group, e2e_s * 1e3, ms_scan, ms_lws], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms_step, ms_group, e2e_s * 1e3, ms_scan, ms_lws, ms_place, ms_sweep], dtype=torch.float64,
+                         device=dev)
     groups = torch.tensor([float(n_grp)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(groups, op=dist.ReduceOp.SUM)
-    ms_step, ms_group, e2e_ms, ms_scan, ms_lws = [float(x) for x in stats.tolist()]
+    ms_step, ms_group, e2e_ms, ms_scan, ms_lws, ms_place, ms_sweep = [float(x) for x in stats.tolist()]
     total_groups = float(groups.item())
 
     if rank == 0:
@@ -322,28 +400,34 @@ def run_ours(args):
         dom_bytes, dom_ms = passes[dom]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         cpu_rate, cpu_s, cpu_reps = cpu_oracle_rate(t, 1)
+        h2d = int(t.table_bytes() + (reqs.nbytes + occ_host.nbytes if world == 1 else 0))
+        d2h = int(n_lws * R.LWS_OUT.itemsize + n_grp * R.GROUP_OUT.itemsize
+                  + (n_req * R.PLACE_OUT.itemsize if world == 1 else 0))
         line = {
             "metric": METRIC, "value": total_groups / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32/u64 (integer compare)", "data": "synthetic",
             "config": {**t.describe(), "parallelism": f"shard-by-uid x{world}",
+                       "placement": {"requests_per_rank": int(n_req), "rounds": rounds,
+                                     "collective": "1 all_gather/step" if (world > 1 and place_on) else "none"},
+                       "step": "pod scan + group pass + LWS pass + placement round",
                        "l2": f"inputs rotate over {copies} resident copies ({copies * algo_bytes / 1e6:.0f} MB > L2)"},
-            "e2e": {"value": total_groups / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(t.table_bytes()),
-                    "d2h_bytes_per_step": int(n_lws * R.LWS_OUT.itemsize + n_grp * R.GROUP_OUT.itemsize),
-                    "ms_per_step": e2e_ms, "api": "lwse_sweep_lws_host (pinned host tables)"},
+            "e2e": {"value": total_groups / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                    "api": "lwse_sweep_lws_host + lwse_place_host (pinned host tables)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms, "peak_source": peak_src,
                          "passes": {k: {"bytes": int(v[0]), "ms": v[1], "gbs": v[0] / (v[1] * 1e-3) / 1e9,
                                         "frac": v[0] / (v[1] * 1e-3) / 1e9 / peak} for k, v in passes.items()}},
+            "ms_sweep_only": ms_sweep, "ms_placement_only": ms_place,
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": f"full {t.profile.name} workload x{cpu_reps} ({cpu_s * 1e3:.1f} ms per sweep)"},
+                             "sample": f"full {t.profile.name} step x{cpu_reps} ({cpu_s * 1e3:.1f} ms per step: sweep + placement spec round)"},
             "clocks": clocks,
             "algorithmic_bytes_per_step": int(algo_bytes),
-            "sweep_gbs": algo_bytes / (ms_step * 1e-3) / 1e9,
+            "sweep_gbs": algo_bytes / (ms_sweep * 1e-3) / 1e9,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

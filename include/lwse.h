@@ -372,6 +372,8 @@ typedef struct lwse_place_out {
 LWSE_API int lwse_place_host(lwse_engine* e, const lwse_place_req* reqs, uint32_t n_reqs,
                              const uint32_t* occupancy, uint32_t n_namespaces,
                              lwse_place_out* out, uint32_t* rounds_out);
+/* Device pointers; enqueued on `stream`.  rounds_out == NULL: no synchronize;
+ * otherwise the call waits for the round count. */
 LWSE_API int lwse_place_device(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
                                const uint32_t* d_occupancy, uint32_t n_namespaces,
                                lwse_place_out* d_out, uint32_t* rounds_out, void* stream);

@@ -311,7 +311,7 @@ LWSE_API int lwse_place_device(lwse_engine* e, const lwse_place_req* d_reqs, uin
   int cuda_err = 0;
   int launched = lwse::launch_place((const lwse_node_rec*)e->nodes.p, e->n_nodes, e->n_domains, d_reqs,
                                     n_reqs, d_occupancy, n_namespaces, d_out, e->place_scratch.p,
-                                    scratch, e->h_rounds, e->sm_count, s, &cuda_err);
+                                    scratch, rounds_out ? e->h_rounds : nullptr, e->sm_count, s, &cuda_err);
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
   if (rounds_out) *rounds_out = e->h_rounds[0];

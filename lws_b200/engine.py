@@ -163,13 +163,14 @@ class Engine:
         )
         return out, rounds.value
 
-    def place_device(self, d_reqs, n_reqs, d_occupancy, n_namespaces, d_out, stream=None):
+    def place_device(self, d_reqs, n_reqs, d_occupancy, n_namespaces, d_out, stream=None, want_rounds=False):
+        """Enqueue a placement round; synchronizes only when ``want_rounds``."""
         rounds = C.c_uint32(0)
         self._check(
             lib().lwse_place_device(self._h, R.ptr(d_reqs), n_reqs, R.ptr(d_occupancy), n_namespaces,
-                                    R.ptr(d_out), C.byref(rounds), stream)
+                                    R.ptr(d_out), C.byref(rounds) if want_rounds else None, stream)
         )
-        return rounds.value
+        return rounds.value if want_rounds else None
 
     # --------------------------------------------------------------------- DS
     def sweep_ds_host(self, ds, roles, revroles):
