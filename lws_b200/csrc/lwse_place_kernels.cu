@@ -2,17 +2,17 @@
 // and DESIGN.md "Placement (parity unpinned)".
 //
 // One cooperative, persistent kernel (one CTA per SM):
-//   phase 0  every CTA stages the node table through shared memory with TMA
-//            (cp.async.bulk + mbarrier, 64 KB chunks) and condenses it, with the
-//            occupancy vector, into a 4-byte/node word (free slots | domain) and
-//            the per-domain free capacity — both kept in shared memory for the
-//            whole kernel;
-//   phase 1  pinned requests (leader already scheduled) claim their domain with
-//            atomicMin on the 64-bit holder key;
+//   phase 0  the grid condenses the node table (16 B/node) and the occupancy
+//            vector into one word per node (free slots | domain) plus the
+//            per-domain free capacity, and pinned requests (leader already
+//            scheduled) claim their domain with atomicMin on the 64-bit holder
+//            key; one grid.sync;
+//   stage    every CTA pulls the condensed node table and the domain capacities
+//            into shared memory with TMA (cp.async.bulk + mbarrier);
 //   phase 2  deferred-acceptance rounds: every unplaced / displaced request is
-//            taken by one warp, whose lanes score every (request, node) pair
-//            against the shared-memory node words, arg-max across the warp, then
-//            atomicMin the holder of the winning domain.  Holder keys only ever
+//            taken by one CTA, whose threads score every (request, node) pair
+//            from shared memory, arg-max across the CTA, then atomicMin the
+//            holder of the winning domain; one grid.sync per round.  Holder keys only ever
 //            decrease, so the fixed point is unique and equals the sequential
 //            "ascending key takes its best free domain" statement of the oracle.
 #include <cooperative_groups.h>
@@ -31,14 +31,13 @@ struct PlaceArgs {
   unsigned long long* holder;  // n_namespaces x n_domains
   uint32_t* choice;            // per request: proposed node (or NONE)
   uint32_t* state;             // per request: 1 = unschedulable
-  uint32_t* counters;          // [0..2] proposals per round (rotating), [3] rounds
+  uint32_t* counters;          // [0..2] proposals per round (rotating), [3] rounds, [4] unpinned requests
   uint32_t* g_compact;         // fallback when the node words do not fit in shared memory
   uint32_t* g_dom_free;
   uint32_t n_nodes, n_domains, n_reqs, n_namespaces;
   uint32_t smem_nodes;  // 1: node words + domain capacities live in shared memory
 };
 
-constexpr uint32_t kStageRows = 4096;  // 64 KB TMA stage
 constexpr uint32_t kPlaceThreads = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -93,143 +92,169 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-  uint4* stage = reinterpret_cast<uint4*>(smem + 128);
-  uint32_t* s_words = reinterpret_cast<uint32_t*>(smem + 128 + kStageRows * sizeof(lwse_node_rec));
-  uint32_t* compact = a.smem_nodes ? s_words : a.g_compact;
-  uint32_t* dom_free = a.smem_nodes ? s_words + ((a.n_nodes + 31u) & ~31u) : a.g_dom_free;
-  const uint32_t tid = threadIdx.x, lane = tid & 31u;
-  const bool builder = a.smem_nodes || blockIdx.x == 0;  // who condenses the node table
+  unsigned long long* s_best = reinterpret_cast<unsigned long long*>(smem + 16);  // 16 warps
+  uint32_t* s_best_n = reinterpret_cast<uint32_t*>(smem + 16 + 16 * 8);
+  uint32_t* s_words = reinterpret_cast<uint32_t*>(smem + 256);
+  const uint32_t n_pad = (a.n_nodes + 31u) & ~31u;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t gtid = blockIdx.x * blockDim.x + tid, gsize = gridDim.x * blockDim.x;
 
-  // ---------------- phase 0: holders, node words, domain capacities ----------------
-  const uint64_t n_hold = (uint64_t)a.n_namespaces * a.n_domains;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + tid; i < n_hold; i += (uint64_t)gridDim.x * blockDim.x)
-    a.holder[i] = ~0ull;
-  if (blockIdx.x == 0 && tid < 4) a.counters[tid] = 0;
-  if (builder) {
-    for (uint32_t d = tid; d < a.n_domains; d += blockDim.x) dom_free[d] = 0;
-    if (tid == 0) {
-      mbar_init(bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  // ---------------- phase 0: node words, domain capacities, pinned claims ----------------
+  // (the host side zeroed g_dom_free / counters and set every holder to ~0 before the launch)
+  // Every CTA condenses its slice of the node table: 16-byte node row + occupancy →
+  // one word (free slots | domain); domain capacities accumulate with global atomics.
+  for (uint32_t n = gtid; n < n_pad; n += gsize) {
+    uint32_t word = kUnusable;
+    if (n < a.n_nodes) {
+      const uint4 nr = ldg_stream(reinterpret_cast<const uint4*>(a.nodes + n));
+      const uint32_t d = nr.z, cap = nr.w & 0xFFFFu, nflags = nr.w >> 16;
+      const uint32_t occ = a.occupancy ? __ldg(a.occupancy + n) : 0u;
+      const bool usable = (nflags & LWSE_NODE_SCHEDULABLE) && (nflags & LWSE_NODE_HAS_TOPOLOGY) && d < a.n_domains;
+      const uint32_t fr = usable && cap > occ ? cap - occ : 0u;
+      if (usable) word = (min(fr, 15u) << 28) | d;
+      if (usable && fr) atomicAdd(a.g_dom_free + d, fr);
     }
-    __syncthreads();
-    uint32_t parity = 0;
-    for (uint32_t base = 0; base < a.n_nodes; base += kStageRows) {
-      const uint32_t rows = min(kStageRows, a.n_nodes - base);
-      if (tid == 0) {
-        mbar_expect_tx(bar, rows * (uint32_t)sizeof(lwse_node_rec));
-        tma_bulk_g2s(stage, a.nodes + base, rows * (uint32_t)sizeof(lwse_node_rec), bar);
-      }
-      mbar_wait(bar, parity);
-      parity ^= 1u;
-      for (uint32_t i = tid; i < rows; i += blockDim.x) {
-        const uint4 nr = stage[i];
-        const uint32_t n = base + i, d = nr.z, cap = nr.w & 0xFFFFu, nflags = nr.w >> 16;
-        const uint32_t occ = a.occupancy ? __ldg(a.occupancy + n) : 0u;
-        const bool usable = (nflags & LWSE_NODE_SCHEDULABLE) && (nflags & LWSE_NODE_HAS_TOPOLOGY) &&
-                            d < a.n_domains;
-        const uint32_t fr = usable && cap > occ ? cap - occ : 0u;
-        compact[n] = usable ? ((min(fr, 15u) << 28) | d) : kUnusable;
-        if (usable && fr) atomicAdd(dom_free + d, fr);
-      }
-      __syncthreads();  // everyone is done with the stage before the next TMA overwrites it
-    }
+    a.g_compact[n] = word;
   }
-  __threadfence();
-  grid.sync();
-
-  // ---------------- phase 1: pinned claims ----------------
-  for (uint32_t r = blockIdx.x * blockDim.x + tid; r < a.n_reqs; r += gridDim.x * blockDim.x) {
+  uint32_t my_unpinned = 0;
+  for (uint32_t r = gtid; r < a.n_reqs; r += gsize) {
     const lwse_place_req rq = a.reqs[r];
     a.choice[r] = LWSE_NONE;
     a.state[r] = 0;
-    if (rq.leader_node != LWSE_NONE && rq.ns < a.n_namespaces && rq.leader_node < a.n_nodes) {
+    if (rq.leader_node == LWSE_NONE) {
+      my_unpinned++;
+    } else if (rq.ns < a.n_namespaces && rq.leader_node < a.n_nodes) {
       const uint4 nr = __ldg(reinterpret_cast<const uint4*>(a.nodes + rq.leader_node));
       const uint32_t d = nr.z;
       if (((nr.w >> 16) & LWSE_NODE_HAS_TOPOLOGY) && d < a.n_domains)
         atomicMin(a.holder + (uint64_t)rq.ns * a.n_domains + d, place_key(rq, r, true));
     }
   }
+  my_unpinned = __reduce_add_sync(0xFFFFFFFFu, my_unpinned);
+  if (lane == 0 && my_unpinned) atomicAdd(a.counters + 4, my_unpinned);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __threadfence();
   grid.sync();
 
-  // ---------------- phase 2: deferred-acceptance rounds for the unpinned ----------------
-  const uint32_t warps_per_grid = gridDim.x * (blockDim.x >> 5);
-  const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+  const uint32_t n_unpinned = __ldcg(a.counters + 4);
+  uint32_t* compact = a.g_compact;
+  uint32_t* dom_free = a.g_dom_free;
   uint32_t round = 0;
-  for (;; round++) {
-    // three rotating counters: the one for round k+1 is cleared during round k,
-    // when no CTA can still be reading it (it was last read after round k-2)
-    uint32_t* counter = a.counters + (round % 3u);
-    if (blockIdx.x == 0 && tid == 0) a.counters[(round + 1u) % 3u] = 0;
-    for (uint32_t r = warp_id; r < a.n_reqs; r += warps_per_grid) {
-      const lwse_place_req rq = a.reqs[r];
-      if (rq.leader_node != LWSE_NONE) continue;  // pinned
-      if (rq.ns >= a.n_namespaces || rq.size < 1) {
-        if (lane == 0) a.state[r] = 1;
-        continue;
+  if (n_unpinned) {
+    if (a.smem_nodes) {
+      // TMA-stage the condensed node table and the domain capacities into shared memory:
+      // every (request, node) pair below is scored from on-chip memory.
+      const uint32_t bytes_w = n_pad * 4u, bytes_d = ((a.n_domains + 3u) & ~3u) * 4u;
+      if (tid == 0) {
+        mbar_expect_tx(bar, bytes_w + bytes_d);
+        tma_bulk_g2s(s_words, a.g_compact, bytes_w, bar);
+        tma_bulk_g2s(s_words + n_pad, a.g_dom_free, bytes_d, bar);
       }
-      if (a.state[r]) continue;
-      const unsigned long long key = place_key(rq, r, false);
-      unsigned long long* hold = a.holder + (uint64_t)rq.ns * a.n_domains;
-      const uint32_t cur = a.choice[r];
-      if (cur != LWSE_NONE) {
-        const uint32_t cd = compact[cur] & 0x0FFFFFFFu;
-        if (__ldcg(hold + cd) == key) continue;  // still holding its domain
-      }
-      // score every (request, node) pair
-      const uint32_t key_lo = (uint32_t)rq.group_key, key_hi = (uint32_t)(rq.group_key >> 32);
-      const uint32_t size = (uint32_t)rq.size;
-      unsigned long long best = 0;
-      uint32_t best_n = LWSE_NONE;
-      for (uint32_t n = lane; n < a.n_nodes; n += 32u) {
-        const uint32_t w = compact[n];
-        if (w == kUnusable || (w >> 28) == 0u) continue;
-        const uint32_t d = w & 0x0FFFFFFFu;
-        const uint32_t df = dom_free[d];
-        if (df < size) continue;
-        if (__ldcg(hold + d) < key) continue;  // held by a higher-priority group (monotone: never frees)
-        const uint32_t slack = (df - size) / size;
-        const uint32_t bucket = slack > 7u ? 7u : slack;
-        const uint32_t hi = ((7u - bucket) << 29) | (mix32(key_lo ^ (d * 0x9E3779B1u)) >> 3);
-        const uint32_t lo = ((w >> 28) << 28) | (mix32(key_hi ^ (n * 0x85EBCA77u)) >> 4);
-        const unsigned long long s = ((unsigned long long)hi << 32) | lo;
-        if (best_n == LWSE_NONE || s > best) {  // n ascends per lane: ties keep the lower index
-          best = s;
-          best_n = n;
-        }
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const unsigned long long os = __shfl_xor_sync(0xFFFFFFFFu, best, off);
-        const uint32_t on = __shfl_xor_sync(0xFFFFFFFFu, best_n, off);
-        const bool take = on != LWSE_NONE && (best_n == LWSE_NONE || os > best || (os == best && on < best_n));
-        if (take) {
-          best = os;
-          best_n = on;
-        }
-      }
-      if (lane == 0) {
-        if (best_n == LWSE_NONE) {
-          a.state[r] = 1;  // nothing feasible now, and the feasible set only shrinks
-          a.choice[r] = LWSE_NONE;
-        } else {
-          const uint32_t d = compact[best_n] & 0x0FFFFFFFu;
-          atomicMin(hold + d, key);
-          a.choice[r] = best_n;
-          a.out[r].score = (uint32_t)(best >> 32);
-          atomicAdd(counter, 1u);
-        }
-      }
+      mbar_wait(bar, 0);
+      compact = s_words;
+      dom_free = s_words + n_pad;
     }
-    __threadfence();
-    grid.sync();
-    const uint32_t proposals = __ldcg(counter);
-    if (proposals == 0u || round > a.n_reqs + 2u) break;
+
+    // ---------------- phase 2: deferred-acceptance rounds, one CTA per request ----------------
+    for (;; round++) {
+      // three rotating counters: the one for round k+1 is cleared during round k,
+      // when no CTA can still be reading it (it was last read after round k-2)
+      uint32_t* counter = a.counters + (round % 3u);
+      if (blockIdx.x == 0 && tid == 0) a.counters[(round + 1u) % 3u] = 0;
+      for (uint32_t r = blockIdx.x; r < a.n_reqs; r += gridDim.x) {
+        const lwse_place_req rq = a.reqs[r];
+        if (rq.leader_node != LWSE_NONE) continue;  // pinned
+        if (rq.ns >= a.n_namespaces || rq.size < 1) {
+          if (tid == 0) a.state[r] = 1;
+          continue;
+        }
+        if (__ldcg(a.state + r)) continue;
+        const unsigned long long key = place_key(rq, r, false);
+        unsigned long long* hold = a.holder + (uint64_t)rq.ns * a.n_domains;
+        const uint32_t cur = __ldcg(a.choice + r);
+        if (cur != LWSE_NONE) {
+          const uint32_t cd = compact[cur] & 0x0FFFFFFFu;
+          if (__ldcg(hold + cd) == key) continue;  // still holding its domain (block-uniform)
+        }
+        // score every (request, node) pair: the CTA's threads stride over the node words
+        const uint32_t key_lo = (uint32_t)rq.group_key, key_hi = (uint32_t)(rq.group_key >> 32);
+        const uint32_t size = (uint32_t)rq.size;
+        unsigned long long best = 0;
+        uint32_t best_n = LWSE_NONE;
+        for (uint32_t n = tid; n < a.n_nodes; n += kPlaceThreads) {
+          const uint32_t w = compact[n];
+          if (w == kUnusable || (w >> 28) == 0u) continue;
+          const uint32_t d = w & 0x0FFFFFFFu;
+          const uint32_t df = dom_free[d];
+          if (df < size) continue;
+          if (__ldcg(hold + d) < key) continue;  // held by a higher-priority group (monotone: never frees)
+          const uint32_t slack = (df - size) / size;
+          const uint32_t bucket = slack > 7u ? 7u : slack;
+          const uint32_t hi = ((7u - bucket) << 29) | (mix32(key_lo ^ (d * 0x9E3779B1u)) >> 3);
+          const uint32_t lo = ((w >> 28) << 28) | (mix32(key_hi ^ (n * 0x85EBCA77u)) >> 4);
+          const unsigned long long s = ((unsigned long long)hi << 32) | lo;
+          if (best_n == LWSE_NONE || s > best) {  // n ascends per thread: ties keep the lower index
+            best = s;
+            best_n = n;
+          }
+        }
+        auto better = [](unsigned long long os, uint32_t on, unsigned long long s, uint32_t n) {
+          return on != LWSE_NONE && (n == LWSE_NONE || os > s || (os == s && on < n));
+        };
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const unsigned long long os = __shfl_xor_sync(0xFFFFFFFFu, best, off);
+          const uint32_t on = __shfl_xor_sync(0xFFFFFFFFu, best_n, off);
+          if (better(os, on, best, best_n)) {
+            best = os;
+            best_n = on;
+          }
+        }
+        if (lane == 0) {
+          s_best[warp] = best;
+          s_best_n[warp] = best_n;
+        }
+        __syncthreads();
+        if (warp == 0) {
+          best = lane < kPlaceThreads / 32 ? s_best[lane] : 0ull;
+          best_n = lane < kPlaceThreads / 32 ? s_best_n[lane] : LWSE_NONE;
+#pragma unroll
+          for (int off = 8; off > 0; off >>= 1) {
+            const unsigned long long os = __shfl_xor_sync(0xFFFFFFFFu, best, off);
+            const uint32_t on = __shfl_xor_sync(0xFFFFFFFFu, best_n, off);
+            if (better(os, on, best, best_n)) {
+              best = os;
+              best_n = on;
+            }
+          }
+          if (lane == 0) {
+            if (best_n == LWSE_NONE) {
+              a.state[r] = 1;  // nothing feasible now, and the feasible set only shrinks
+              a.choice[r] = LWSE_NONE;
+            } else {
+              const uint32_t d = compact[best_n] & 0x0FFFFFFFu;
+              atomicMin(hold + d, key);
+              a.choice[r] = best_n;
+              a.out[r].score = (uint32_t)(best >> 32);
+              atomicAdd(counter, 1u);
+            }
+          }
+        }
+        __syncthreads();  // s_best is reused by the CTA's next request
+      }
+      __threadfence();
+      grid.sync();
+      const uint32_t proposals = __ldcg(counter);
+      if (proposals == 0u || round > a.n_reqs + 2u) break;
+    }
   }
-  if (blockIdx.x == 0 && tid == 0) a.counters[3] = round + 1u;
+  if (blockIdx.x == 0 && tid == 0) a.counters[3] = n_unpinned ? round + 1u : 0u;
 
   // ---------------- results ----------------
-  for (uint32_t r = blockIdx.x * blockDim.x + tid; r < a.n_reqs; r += gridDim.x * blockDim.x) {
+  for (uint32_t r = gtid; r < a.n_reqs; r += gsize) {
     const lwse_place_req rq = a.reqs[r];
     lwse_place_out o;
     o.domain_id = LWSE_NONE;
@@ -251,11 +276,11 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
         }
       }
     } else {
-      const uint32_t cur = a.choice[r];
-      if (a.state[r] || cur == LWSE_NONE) {
+      const uint32_t cur = __ldcg(a.choice + r);
+      if (__ldcg(a.state + r) || cur == LWSE_NONE) {
         o.flags = LWSE_PLACE_UNSCHEDULABLE;
       } else {
-        o.domain_id = compact[cur] & 0x0FFFFFFFu;
+        o.domain_id = __ldcg(a.g_compact + cur) & 0x0FFFFFFFu;
         o.leader_node = cur;
         o.flags = LWSE_PLACE_PLACED;
         o.score = a.out[r].score;
@@ -267,9 +292,11 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// scratch layout: [holder | counters(256 B) | g_dom_free | choice | state | g_compact]; the first three
+// regions are contiguous so that two memsets initialise them.
 size_t place_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces) {
-  return align_up((size_t)n_namespaces * n_domains * 8, 256) + align_up((size_t)n_reqs * 4, 256) * 2 + 256 +
-         align_up((size_t)n_nodes * 4, 256) + align_up((size_t)n_domains * 4, 256) + 1024;
+  return align_up((size_t)n_namespaces * n_domains * 8, 256) + 256 + align_up((size_t)n_domains * 4 + 16, 256) +
+         align_up((size_t)n_reqs * 4, 256) * 2 + align_up((size_t)n_nodes * 4 + 128, 256) + 1024;
 }
 
 int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_domains,
@@ -277,11 +304,8 @@ int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_doma
                  uint32_t n_namespaces, lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes,
                  uint32_t* h_rounds, int sm_count, cudaStream_t s, int* cuda_err) {
   *cuda_err = 0;
-  if (n_reqs > 0xFFFFFFu) {
-    *cuda_err = (int)cudaErrorInvalidValue;
-    return -1;
-  }
-  if (scratch_bytes < place_scratch_bytes(n_nodes, n_domains, n_reqs, n_namespaces)) {
+  if (n_reqs > 0xFFFFFFu || n_domains >= (1u << 28) ||
+      scratch_bytes < place_scratch_bytes(n_nodes, n_domains, n_reqs, n_namespaces)) {
     *cuda_err = (int)cudaErrorInvalidValue;
     return -1;
   }
@@ -291,36 +315,42 @@ int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_doma
   a.reqs = d_reqs;
   a.occupancy = d_occupancy;
   a.out = d_out;
+  const size_t holder_bytes = align_up((size_t)n_namespaces * n_domains * 8, 256);
+  const size_t zero_bytes = 256 + align_up((size_t)n_domains * 4 + 16, 256);
   a.holder = reinterpret_cast<unsigned long long*>(p);
-  p += align_up((size_t)n_namespaces * n_domains * 8, 256);
+  p += holder_bytes;
+  a.counters = reinterpret_cast<uint32_t*>(p);
+  a.g_dom_free = reinterpret_cast<uint32_t*>(p + 256);
+  p += zero_bytes;
   a.choice = reinterpret_cast<uint32_t*>(p);
   p += align_up((size_t)n_reqs * 4, 256);
   a.state = reinterpret_cast<uint32_t*>(p);
   p += align_up((size_t)n_reqs * 4, 256);
-  a.counters = reinterpret_cast<uint32_t*>(p);
-  p += 256;
   a.g_compact = reinterpret_cast<uint32_t*>(p);
-  p += align_up((size_t)n_nodes * 4, 256);
-  a.g_dom_free = reinterpret_cast<uint32_t*>(p);
   a.n_nodes = n_nodes;
   a.n_domains = n_domains;
   a.n_reqs = n_reqs;
   a.n_namespaces = n_namespaces;
 
-  const size_t stage_bytes = 128 + (size_t)kStageRows * sizeof(lwse_node_rec);
-  const size_t words_bytes = ((size_t)((n_nodes + 31u) & ~31u) + n_domains) * 4;
-  size_t smem = stage_bytes + words_bytes;
+  const size_t words_bytes = ((size_t)((n_nodes + 31u) & ~31u) + ((n_domains + 3u) & ~3u)) * 4;
+  size_t smem = 256 + words_bytes;
   a.smem_nodes = smem <= 227u * 1024u ? 1u : 0u;
-  if (!a.smem_nodes) smem = stage_bytes;
-  cudaError_t e = cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (!a.smem_nodes) smem = 256;
+  static size_t smem_set = 0;
+  cudaError_t e = cudaSuccess;
+  if (smem > smem_set) {
+    e = cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      *cuda_err = (int)e;
+      return -1;
+    }
+    smem_set = smem;
+  }
+  // holders ← ~0, counters and domain capacities ← 0
+  e = cudaMemsetAsync(a.holder, 0xFF, holder_bytes, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(a.counters, 0, zero_bytes, s);
   if (e != cudaSuccess) {
     *cuda_err = (int)e;
-    return -1;
-  }
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, place_kernel, (int)kPlaceThreads, smem);
-  if (e != cudaSuccess || per_sm < 1) {
-    *cuda_err = (int)(e != cudaSuccess ? e : cudaErrorLaunchOutOfResources);
     return -1;
   }
   void* params[] = {&a};

@@ -64,7 +64,7 @@ def profile(name: str, scale: float = 1.0) -> Profile:
                        f_mid_update=0.10)
     if name == "C3":  # 100k LWS x size 64, 10k nodes, topology-aware gang placement on
         return Profile("C3", s(100_000), size_choices=(64,), replicas_choices=(1,), n_nodes=10_000,
-                       nodes_per_domain=16, node_capacity=4, p_exclusive=0.01, f_mid_update=0.10)
+                       nodes_per_domain=16, node_capacity=650, p_exclusive=0.01, f_mid_update=0.10)
     if name == "C5":  # 100k LWS rolling update maxSurge=10% + restart sweep
         return Profile("C5", s(100_000), size_choices=(8,), replicas_choices=(16,), n_nodes=10_000,
                        max_surge=((10, True),), max_unavailable=((1, False),), f_no_sts=0.02,
