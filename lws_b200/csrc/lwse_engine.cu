@@ -17,7 +17,8 @@ size_t lws_sweep_scratch_bytes(uint64_t n_pods);
 int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_domains,
                  const lwse_place_req* d_reqs, uint32_t n_reqs, const uint32_t* d_occupancy,
                  uint32_t n_namespaces, lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes,
-                 uint32_t* h_rounds, int sm_count, cudaStream_t s, int* cuda_err);
+                 uint32_t* h_rounds, int sm_count, cudaStream_t s, int* cuda_err, uint32_t call_index,
+                 bool fresh);
 size_t place_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces);
 // lwse_ds_kernels.cu
 int launch_ds_sweep(const lwse_ds_tables* t, int sm_count, cudaStream_t s, int* cuda_err);
@@ -64,6 +65,8 @@ struct lwse_engine {
   // staging for the *_host entry points
   DevBuf lws, groups, pod_state, pod_ident, lws_out, group_out, occupancy, scan_scratch;
   DevBuf place_reqs, place_out, place_occ, place_scratch;
+  uint32_t place_calls = 0;          // selects the scratch half
+  uint64_t place_geometry = 0;       // (n_reqs, n_namespaces, nodes, domains) the scratch was laid out for
   DevBuf ds, ds_roles, ds_revroles, ds_out, ds_role_out, ds_revrole_out;
   DevBuf sha_bytes, sha_offsets, sha_digests;
   uint32_t* h_rounds = nullptr;  // pinned
@@ -307,11 +310,18 @@ LWSE_API int lwse_place_device(lwse_engine* e, const lwse_place_req* d_reqs, uin
   DeviceGuard guard(e->device);
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
   const size_t scratch = lwse::place_scratch_bytes(e->n_nodes, e->n_domains, n_reqs, n_namespaces);
+  const void* before = e->place_scratch.p;
   LWSE_CUDA(e, e->place_scratch.reserve(scratch));
+  // the two scratch halves are laid out for one geometry; any change re-initialises them
+  const uint64_t geometry = ((uint64_t)n_reqs << 40) ^ ((uint64_t)n_namespaces << 56) ^ ((uint64_t)e->n_nodes << 16) ^
+                            (uint64_t)e->n_domains ^ 0x8000000000000000ull;
+  const bool fresh = before != e->place_scratch.p || geometry != e->place_geometry;
+  e->place_geometry = geometry;
   int cuda_err = 0;
   int launched = lwse::launch_place((const lwse_node_rec*)e->nodes.p, e->n_nodes, e->n_domains, d_reqs,
                                     n_reqs, d_occupancy, n_namespaces, d_out, e->place_scratch.p,
-                                    scratch, rounds_out ? e->h_rounds : nullptr, e->sm_count, s, &cuda_err);
+                                    scratch, rounds_out ? e->h_rounds : nullptr, e->sm_count, s, &cuda_err,
+                                    e->place_calls++, fresh);
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
   if (rounds_out) *rounds_out = e->h_rounds[0];

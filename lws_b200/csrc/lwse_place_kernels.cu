@@ -32,8 +32,12 @@ struct PlaceArgs {
   uint32_t* choice;            // per request: proposed node (or NONE)
   uint32_t* state;             // per request: 1 = unschedulable
   uint32_t* counters;          // [0..2] proposals per round (rotating), [3] rounds, [4] unpinned requests
-  uint32_t* g_compact;         // fallback when the node words do not fit in shared memory
+  uint32_t* g_compact;         // condensed node words (global copy, TMA source)
   uint32_t* g_dom_free;
+  uint32_t* unpinned;          // indices of the unpinned requests (built in phase 0)
+  unsigned long long* next_holder;  // the scratch half the NEXT call will use: reset here
+  uint32_t* next_zero;         // its counters + domain capacities
+  uint32_t next_zero_words;
   uint32_t n_nodes, n_domains, n_reqs, n_namespaces;
   uint32_t smem_nodes;  // 1: node words + domain capacities live in shared memory
 };
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
   const uint32_t gtid = blockIdx.x * blockDim.x + tid, gsize = gridDim.x * blockDim.x;
 
   // ---------------- phase 0: node words, domain capacities, pinned claims ----------------
-  // (the host side zeroed g_dom_free / counters and set every holder to ~0 before the launch)
+  // (this scratch half was left clean — holders ~0, counters and capacities 0 — by the previous call)
   // Every CTA condenses its slice of the node table: 16-byte node row + occupancy →
   // one word (free slots | domain); domain capacities accumulate with global atomics.
   for (uint32_t n = gtid; n < n_pad; n += gsize) {
@@ -116,13 +120,18 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
     }
     a.g_compact[n] = word;
   }
-  uint32_t my_unpinned = 0;
+  // leave the other scratch half clean for the next call (it is idle: calls are stream-ordered)
+  {
+    const uint64_t n_hold = (uint64_t)a.n_namespaces * a.n_domains;
+    for (uint64_t i = gtid; i < n_hold; i += gsize) a.next_holder[i] = ~0ull;
+    for (uint32_t i = gtid; i < a.next_zero_words; i += gsize) a.next_zero[i] = 0u;
+  }
   for (uint32_t r = gtid; r < a.n_reqs; r += gsize) {
     const lwse_place_req rq = a.reqs[r];
     a.choice[r] = LWSE_NONE;
     a.state[r] = 0;
     if (rq.leader_node == LWSE_NONE) {
-      my_unpinned++;
+      a.unpinned[atomicAdd(a.counters + 4, 1u)] = r;  // order is irrelevant: the fixed point is unique
     } else if (rq.ns < a.n_namespaces && rq.leader_node < a.n_nodes) {
       const uint4 nr = __ldg(reinterpret_cast<const uint4*>(a.nodes + rq.leader_node));
       const uint32_t d = nr.z;
@@ -130,8 +139,6 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
         atomicMin(a.holder + (uint64_t)rq.ns * a.n_domains + d, place_key(rq, r, true));
     }
   }
-  my_unpinned = __reduce_add_sync(0xFFFFFFFFu, my_unpinned);
-  if (lane == 0 && my_unpinned) atomicAdd(a.counters + 4, my_unpinned);
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -164,9 +171,9 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
       // when no CTA can still be reading it (it was last read after round k-2)
       uint32_t* counter = a.counters + (round % 3u);
       if (blockIdx.x == 0 && tid == 0) a.counters[(round + 1u) % 3u] = 0;
-      for (uint32_t r = blockIdx.x; r < a.n_reqs; r += gridDim.x) {
+      for (uint32_t k = blockIdx.x; k < n_unpinned; k += gridDim.x) {
+        const uint32_t r = __ldcg(a.unpinned + k);
         const lwse_place_req rq = a.reqs[r];
-        if (rq.leader_node != LWSE_NONE) continue;  // pinned
         if (rq.ns >= a.n_namespaces || rq.size < 1) {
           if (tid == 0) a.state[r] = 1;
           continue;
@@ -191,9 +198,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
           const uint32_t df = dom_free[d];
           if (df < size) continue;
           if (__ldcg(hold + d) < key) continue;  // held by a higher-priority group (monotone: never frees)
-          const uint32_t slack = (df - size) / size;
-          const uint32_t bucket = slack > 7u ? 7u : slack;
-          const uint32_t hi = ((7u - bucket) << 29) | (mix32(key_lo ^ (d * 0x9E3779B1u)) >> 3);
+          const uint32_t hi = mix32(key_lo ^ (d * 0x9E3779B1u));  // per-group rendezvous hash of the domain
           const uint32_t lo = ((w >> 28) << 28) | (mix32(key_hi ^ (n * 0x85EBCA77u)) >> 4);
           const unsigned long long s = ((unsigned long long)hi << 32) | lo;
           if (best_n == LWSE_NONE || s > best) {  // n ascends per thread: ties keep the lower index
@@ -292,39 +297,66 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// scratch layout: [holder | counters(256 B) | g_dom_free | choice | state | g_compact]; the first three
-// regions are contiguous so that two memsets initialise them.
-size_t place_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces) {
+// scratch: two identical halves used alternately by successive calls; each half is
+// [holder | counters(256 B) | g_dom_free | choice | state | unpinned | g_compact].  A call resets the
+// holders / counters / capacities of the *other* half, so no memset sits on the critical path
+// (the engine zero-fills the whole scratch once, when it allocates it).
+static size_t place_half_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces) {
   return align_up((size_t)n_namespaces * n_domains * 8, 256) + 256 + align_up((size_t)n_domains * 4 + 16, 256) +
-         align_up((size_t)n_reqs * 4, 256) * 2 + align_up((size_t)n_nodes * 4 + 128, 256) + 1024;
+         align_up((size_t)n_reqs * 4, 256) * 3 + align_up((size_t)n_nodes * 4 + 128, 256);
+}
+size_t place_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces) {
+  return 2 * place_half_bytes(n_nodes, n_domains, n_reqs, n_namespaces) + 1024;
 }
 
+// `fresh`: the scratch was (re)allocated or its geometry changed → initialise both halves first.
 int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_domains,
                  const lwse_place_req* d_reqs, uint32_t n_reqs, const uint32_t* d_occupancy,
                  uint32_t n_namespaces, lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes,
-                 uint32_t* h_rounds, int sm_count, cudaStream_t s, int* cuda_err) {
+                 uint32_t* h_rounds, int sm_count, cudaStream_t s, int* cuda_err, uint32_t call_index,
+                 bool fresh) {
   *cuda_err = 0;
   if (n_reqs > 0xFFFFFFu || n_domains >= (1u << 28) ||
       scratch_bytes < place_scratch_bytes(n_nodes, n_domains, n_reqs, n_namespaces)) {
     *cuda_err = (int)cudaErrorInvalidValue;
     return -1;
   }
-  uint8_t* p = static_cast<uint8_t*>(d_scratch);
+  const size_t half = place_half_bytes(n_nodes, n_domains, n_reqs, n_namespaces);
+  const size_t holder_bytes = align_up((size_t)n_namespaces * n_domains * 8, 256);
+  const size_t zero_bytes = 256 + align_up((size_t)n_domains * 4 + 16, 256);
+  uint8_t* base = static_cast<uint8_t*>(d_scratch);
+  uint8_t* p = base + (call_index & 1u) * half;
+  uint8_t* q = base + ((call_index + 1u) & 1u) * half;
+  cudaError_t e = cudaSuccess;
+  if (fresh) {
+    for (int h = 0; h < 2 && e == cudaSuccess; h++) {
+      e = cudaMemsetAsync(base + h * half, 0xFF, holder_bytes, s);
+      if (e == cudaSuccess) e = cudaMemsetAsync(base + h * half + holder_bytes, 0, zero_bytes, s);
+    }
+    if (e != cudaSuccess) {
+      *cuda_err = (int)e;
+      return -1;
+    }
+  }
   PlaceArgs a{};
   a.nodes = d_nodes;
   a.reqs = d_reqs;
   a.occupancy = d_occupancy;
   a.out = d_out;
-  const size_t holder_bytes = align_up((size_t)n_namespaces * n_domains * 8, 256);
-  const size_t zero_bytes = 256 + align_up((size_t)n_domains * 4 + 16, 256);
   a.holder = reinterpret_cast<unsigned long long*>(p);
+  a.next_holder = reinterpret_cast<unsigned long long*>(q);
   p += holder_bytes;
+  q += holder_bytes;
   a.counters = reinterpret_cast<uint32_t*>(p);
   a.g_dom_free = reinterpret_cast<uint32_t*>(p + 256);
+  a.next_zero = reinterpret_cast<uint32_t*>(q);
+  a.next_zero_words = (uint32_t)(zero_bytes / 4);
   p += zero_bytes;
   a.choice = reinterpret_cast<uint32_t*>(p);
   p += align_up((size_t)n_reqs * 4, 256);
   a.state = reinterpret_cast<uint32_t*>(p);
+  p += align_up((size_t)n_reqs * 4, 256);
+  a.unpinned = reinterpret_cast<uint32_t*>(p);
   p += align_up((size_t)n_reqs * 4, 256);
   a.g_compact = reinterpret_cast<uint32_t*>(p);
   a.n_nodes = n_nodes;
@@ -337,7 +369,6 @@ int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_doma
   a.smem_nodes = smem <= 227u * 1024u ? 1u : 0u;
   if (!a.smem_nodes) smem = 256;
   static size_t smem_set = 0;
-  cudaError_t e = cudaSuccess;
   if (smem > smem_set) {
     e = cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -345,13 +376,6 @@ int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_doma
       return -1;
     }
     smem_set = smem;
-  }
-  // holders ← ~0, counters and domain capacities ← 0
-  e = cudaMemsetAsync(a.holder, 0xFF, holder_bytes, s);
-  if (e == cudaSuccess) e = cudaMemsetAsync(a.counters, 0, zero_bytes, s);
-  if (e != cudaSuccess) {
-    *cuda_err = (int)e;
-    return -1;
   }
   void* params[] = {&a};
   e = cudaLaunchCooperativeKernel((const void*)place_kernel, dim3((unsigned)sm_count), dim3(kPlaceThreads), params,
