@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--graph", action="store_true",
+                    help="replay CUDA graphs instead of eager launches (measured slower: programmatic "
+                         "dependent launch does not span graph replays)")
     return ap.parse_args()
 
 
@@ -271,6 +274,10 @@ def run_ours(args):
     # time on the stream the kernels are launched on: the engine's own stream
     stream = torch.cuda.ExternalStream(eng.stream, device=dev)
     sptr = eng.stream
+    # the placement round reads only inputs (requests, occupancy, node table), never the sweep's
+    # outputs: it runs on its own stream, concurrently with the sweep kernels
+    pstream = torch.cuda.Stream(device=dev)
+    pptr = pstream.cuda_stream
 
     def sweep(i, flags):
         s = sets[i % copies]
@@ -281,9 +288,9 @@ def run_ours(args):
         if not place_on:
             return
         if world == 1:
-            eng.place_device(d_reqs, n_req, d_occ, 1, d_pout, stream=sptr)
+            eng.place_device(d_reqs, n_req, d_occ, 1, d_pout, stream=pptr)
             return
-        with torch.cuda.stream(stream):
+        with torch.cuda.stream(pstream):
             dist.all_gather_into_tensor(gathered, send)  # the single collective of a step
             g = gathered.view(world, pack_words)
             torch.sum(g[:, :n_nodes], dim=0, out=all_occ)  # occupancy of every shard
@@ -291,11 +298,20 @@ def run_ours(args):
         # every rank solves the whole (small) placement problem: identical inputs, deterministic
         # kernel → identical results, each rank keeps the rows of its own groups.  Padding rows are
         # zero (size 0 → unschedulable, never claim a domain).
-        eng.place_device(all_reqs, world * req_cap, all_occ, 1, d_pout, stream=sptr)
+        eng.place_device(all_reqs, world * req_cap, all_occ, 1, d_pout, stream=pptr)
 
     def step(i, flags):
+        if place_on:
+            pstream.wait_stream(stream)  # fork: placement starts with the sweep …
+            place()
         sweep(i, flags)
+        if place_on:
+            stream.wait_stream(pstream)  # … join: the step ends when both are done
+
+    def place_alone():
+        pstream.wait_stream(stream)
         place()
+        stream.wait_stream(pstream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -303,31 +319,67 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    use_graph = args.graph and world == 1
+
     def timed(fn, steps, warmup):
+        """ms per call of fn(i) over `steps` calls.  Single GPU: the calls for each rotating input
+        set are captured once into a CUDA graph and replayed (launch overhead off the device
+        timeline); multi GPU: eager (the step contains a NCCL collective)."""
         for i in range(warmup):
             fn(i)
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = eng.launch_count
-        e0.record(stream)
-        for i in range(steps):
-            fn(warmup + i)
-        e1.record(stream)
+        graphs = None
+        if use_graph:
+            try:
+                graphs = []
+                for k in range(copies):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=stream, capture_error_mode="relaxed"):
+                        fn(k)
+                    graphs.append(g)
+            except Exception as exc:  # pragma: no cover
+                print(f"bench.py: graph capture failed ({exc}); timing eager launches", file=sys.stderr)
+                graphs = None
+                torch.cuda.synchronize()
+        run = (lambda i: graphs[i % copies].replay()) if graphs else fn
+        with torch.cuda.stream(stream):
+            for i in range(3):
+                run(i)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = eng.launch_count
+            e0.record(stream)
+            for i in range(steps):
+                run(i)
+            e1.record(stream)
         barrier()
-        return e0.elapsed_time(e1) / steps, eng.launch_count - l0
+        launched = eng.launch_count - l0
+        if graphs:  # replays do not pass through the engine's counter: kernels per captured call x calls
+            launched = timed.per_call.get(fn, 0) * steps
+        return e0.elapsed_time(e1) / steps, launched
+
+    timed.per_call = {}
+
+    def count_launches(fn):
+        l0 = eng.launch_count
+        fn(0)
+        torch.cuda.synchronize()
+        timed.per_call[fn] = eng.launch_count - l0
 
     SCAN_ONLY = R.SWEEP_SKIP_GROUP_PASS | R.SWEEP_SKIP_LWS_PASS
     GROUP_ONLY = R.SWEEP_SKIP_POD_SCAN | R.SWEEP_SKIP_LWS_PASS
     LWS_ONLY = R.SWEEP_SKIP_POD_SCAN | R.SWEEP_SKIP_GROUP_PASS
     W = max(args.warmup, 3)
+    full_step = lambda i: step(i, t.flags)  # noqa: E731
+    count_launches(full_step)
     with ClockSampler(local_rank) as clk:
-        ms_step, launches = timed(lambda i: step(i, t.flags), args.steps, W)
+        ms_step, launches = timed(full_step, args.steps, W)
         # each pass alone (same rotating inputs), for the per-kernel roofline
         ms_sweep, _ = timed(lambda i: sweep(i, t.flags), args.steps, 3)
         ms_scan, _ = timed(lambda i: sweep(i, t.flags | SCAN_ONLY), args.steps, 3)
         ms_group, _ = timed(lambda i: sweep(i, t.flags | GROUP_ONLY), args.steps, 3)
         ms_lws, _ = timed(lambda i: sweep(i, t.flags | LWS_ONLY), args.steps, 3)
-        ms_place = timed(lambda i: place(), args.steps, 3)[0] if place_on else 0.0
+        ms_place = timed(lambda i: place_alone(), args.steps, 3)[0] if place_on else 0.0
         # keep the GPU under the same load long enough for nvidia-smi to sample clocks
         t_end = time.perf_counter() + 1.0
         i = 0
@@ -337,7 +389,9 @@ def run_ours(args):
                 i += 1
             torch.cuda.synchronize()
     clocks = clk.summary()
-    rounds = eng.place_device(d_reqs, n_req, d_occ, 1, d_pout, stream=sptr, want_rounds=True) if (place_on and world == 1) else None
+    torch.cuda.synchronize()
+    rounds = eng.place_device(d_reqs, n_req, d_occ, 1, d_pout, stream=pptr, want_rounds=True) if (place_on and world == 1) else None
+    torch.cuda.synchronize()
 
     # ---- end to end through the host entry points, pinned buffers ----
     def pinned(a):
@@ -411,7 +465,8 @@ def run_ours(args):
             "config": {**t.describe(), "parallelism": f"shard-by-uid x{world}",
                        "placement": {"requests_per_rank": int(n_req), "rounds": rounds,
                                      "collective": "1 all_gather/step" if (world > 1 and place_on) else "none"},
-                       "step": "pod scan + group pass + LWS pass + placement round",
+                       "launch": "CUDA graph replay" if use_graph else "eager",
+                       "step": "pod scan + group pass + LWS pass, placement round concurrently on a second stream",
                        "l2": f"inputs rotate over {copies} resident copies ({copies * algo_bytes / 1e6:.0f} MB > L2)"},
             "e2e": {"value": total_groups / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,

@@ -17,6 +17,8 @@
 //            "ascending key takes its best free domain" statement of the oracle.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "lwse_device.cuh"
 
 namespace cg = cooperative_groups;
@@ -378,8 +380,16 @@ int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_doma
     smem_set = smem;
   }
   void* params[] = {&a};
-  e = cudaLaunchCooperativeKernel((const void*)place_kernel, dim3((unsigned)sm_count), dim3(kPlaceThreads), params,
-                                  smem, s);
+  // one CTA per SM at most; a grid barrier costs more the more CTAs take part, and a round
+  // needs no more CTAs than there are requests
+  static const int env_ctas = [] {
+    const char* v = getenv("LWSE_PLACE_CTAS");
+    return v ? atoi(v) : 0;
+  }();
+  unsigned ctas = (unsigned)sm_count;
+  if (n_reqs < ctas) ctas = n_reqs < 16u ? 16u : n_reqs;
+  if (env_ctas > 0 && (unsigned)env_ctas < ctas) ctas = (unsigned)env_ctas;
+  e = cudaLaunchCooperativeKernel((const void*)place_kernel, dim3(ctas), dim3(kPlaceThreads), params, smem, s);
   if (e != cudaSuccess) {
     *cuda_err = (int)e;
     return -1;
