@@ -258,15 +258,11 @@ def run_ours(args):
         req_cap = int(cap.item())
         place_on = req_cap > 0
     if world > 1 and place_on:
-        pack_words = n_nodes + 4 + req_cap * (R.PLACE_REQ.itemsize // 4)
-        send = torch.zeros(pack_words, dtype=torch.int32, device=dev)
-        send[:n_nodes] = d_occ
-        send[n_nodes] = n_req
-        if n_req:
-            send[n_nodes + 4: n_nodes + 4 + n_req * 8] = d_reqs.view(torch.int32)
-        gathered = torch.empty(world * pack_words, dtype=torch.int32, device=dev)
-        all_reqs = torch.zeros(world * req_cap * R.PLACE_REQ.itemsize, dtype=torch.uint8, device=dev)
-        all_occ = torch.empty(n_nodes, dtype=torch.int32, device=dev)
+        from lws_b200 import distributed as D
+
+        part_stride, reqs_off = D.part_layout(n_nodes, req_cap)
+        send = torch.from_numpy(D.pack_part(occ_host, reqs, req_cap)).to(dev)  # [occupancy | requests]
+        gathered = torch.empty(world * part_stride, dtype=torch.uint8, device=dev)
         d_pout = torch.empty(max(world * req_cap, 1) * R.PLACE_OUT.itemsize, dtype=torch.uint8, device=dev)
     else:
         d_pout = torch.empty(max(n_req, 1) * R.PLACE_OUT.itemsize, dtype=torch.uint8, device=dev)
@@ -292,13 +288,9 @@ def run_ours(args):
             return
         with torch.cuda.stream(pstream):
             dist.all_gather_into_tensor(gathered, send)  # the single collective of a step
-            g = gathered.view(world, pack_words)
-            torch.sum(g[:, :n_nodes], dim=0, out=all_occ)  # occupancy of every shard
-            all_reqs.view(world, -1).copy_(g[:, n_nodes + 4:].contiguous().view(torch.uint8).view(world, -1))
-        # every rank solves the whole (small) placement problem: identical inputs, deterministic
-        # kernel → identical results, each rank keeps the rows of its own groups.  Padding rows are
-        # zero (size 0 → unschedulable, never claim a domain).
-        eng.place_device(all_reqs, world * req_cap, all_occ, 1, d_pout, stream=pptr)
+        # every rank solves the whole (small) placement problem on the gathered parts: identical
+        # inputs, deterministic kernel → identical results; each rank keeps the rows of its own part
+        eng.place_gathered_device(gathered, world, part_stride, reqs_off, req_cap, 1, d_pout, stream=pptr)
 
     def step(i, flags):
         if place_on:

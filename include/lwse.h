@@ -378,6 +378,17 @@ LWSE_API int lwse_place_device(lwse_engine* e, const lwse_place_req* d_reqs, uin
                                const uint32_t* d_occupancy, uint32_t n_namespaces,
                                lwse_place_out* d_out, uint32_t* rounds_out, void* stream);
 
+/* Multi-GPU form: `d_parts` is the result of ONE all-gather over the ranks; part p
+ * (rank p, at d_parts + p * part_stride_bytes) holds that shard's per-node occupancy
+ * (n_nodes uint32 counters) followed, at reqs_offset_bytes, by reqs_per_part request
+ * rows (unused rows: leader_node = LWSE_NONE, size = 0).  Node occupancy is summed over
+ * the parts; request r = p * reqs_per_part + j; d_out has n_parts * reqs_per_part rows.
+ * Every rank solves the same problem and keeps the rows of its own part. */
+LWSE_API int lwse_place_gathered_device(lwse_engine* e, const void* d_parts, uint32_t n_parts,
+                                        uint64_t part_stride_bytes, uint64_t reqs_offset_bytes,
+                                        uint32_t reqs_per_part, uint32_t n_namespaces,
+                                        lwse_place_out* d_out, uint32_t* rounds_out, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* DisaggregatedSet sweep                                                    */
 /* ------------------------------------------------------------------------- */

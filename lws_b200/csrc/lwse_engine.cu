@@ -18,7 +18,7 @@ int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_doma
                  const lwse_place_req* d_reqs, uint32_t n_reqs, const uint32_t* d_occupancy,
                  uint32_t n_namespaces, lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes,
                  uint32_t* h_rounds, int sm_count, cudaStream_t s, int* cuda_err, uint32_t call_index,
-                 bool fresh);
+                 bool fresh, uint32_t n_parts, uint32_t reqs_per_part, uint64_t part_stride_bytes);
 size_t place_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces);
 // lwse_ds_kernels.cu
 int launch_ds_sweep(const lwse_ds_tables* t, int sm_count, cudaStream_t s, int* cuda_err);
@@ -301,9 +301,10 @@ LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* h) {
 // ---------------------------------------------------------------------------
 // Placement
 // ---------------------------------------------------------------------------
-LWSE_API int lwse_place_device(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
-                               const uint32_t* d_occupancy, uint32_t n_namespaces,
-                               lwse_place_out* d_out, uint32_t* rounds_out, void* stream) {
+static int place_common(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
+                        const uint32_t* d_occupancy, uint32_t n_namespaces, lwse_place_out* d_out,
+                        uint32_t* rounds_out, void* stream, uint32_t n_parts, uint32_t reqs_per_part,
+                        uint64_t part_stride_bytes) {
   if (!e || (n_reqs && (!d_reqs || !d_out)) || n_namespaces == 0) return LWSE_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(e->mu);
   if (e->n_nodes == 0 || e->n_domains == 0) return LWSE_ERR_NOT_READY;
@@ -321,11 +322,30 @@ LWSE_API int lwse_place_device(lwse_engine* e, const lwse_place_req* d_reqs, uin
   int launched = lwse::launch_place((const lwse_node_rec*)e->nodes.p, e->n_nodes, e->n_domains, d_reqs,
                                     n_reqs, d_occupancy, n_namespaces, d_out, e->place_scratch.p,
                                     scratch, rounds_out ? e->h_rounds : nullptr, e->sm_count, s, &cuda_err,
-                                    e->place_calls++, fresh);
+                                    e->place_calls++, fresh, n_parts, reqs_per_part, part_stride_bytes);
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
   if (rounds_out) *rounds_out = e->h_rounds[0];
   return LWSE_OK;
+}
+
+LWSE_API int lwse_place_device(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
+                               const uint32_t* d_occupancy, uint32_t n_namespaces,
+                               lwse_place_out* d_out, uint32_t* rounds_out, void* stream) {
+  return place_common(e, d_reqs, n_reqs, d_occupancy, n_namespaces, d_out, rounds_out, stream, 1, n_reqs, 0);
+}
+
+LWSE_API int lwse_place_gathered_device(lwse_engine* e, const void* d_parts, uint32_t n_parts,
+                                        uint64_t part_stride_bytes, uint64_t reqs_offset_bytes,
+                                        uint32_t reqs_per_part, uint32_t n_namespaces,
+                                        lwse_place_out* d_out, uint32_t* rounds_out, void* stream) {
+  if (!d_parts || n_parts == 0 || (part_stride_bytes & 15u) || (reqs_offset_bytes & 15u) ||
+      (uint64_t)n_parts * reqs_per_part > 0xFFFFFFull)
+    return LWSE_ERR_INVALID_ARG;
+  const uint8_t* base = static_cast<const uint8_t*>(d_parts);
+  return place_common(e, reinterpret_cast<const lwse_place_req*>(base + reqs_offset_bytes), n_parts * reqs_per_part,
+                      reinterpret_cast<const uint32_t*>(base), n_namespaces, d_out, rounds_out, stream, n_parts,
+                      reqs_per_part, part_stride_bytes);
 }
 
 LWSE_API int lwse_place_host(lwse_engine* e, const lwse_place_req* reqs, uint32_t n_reqs,

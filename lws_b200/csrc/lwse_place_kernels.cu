@@ -42,6 +42,11 @@ struct PlaceArgs {
   uint32_t next_zero_words;
   uint32_t n_nodes, n_domains, n_reqs, n_namespaces;
   uint32_t smem_nodes;  // 1: node words + domain capacities live in shared memory
+  // gathered form (multi-GPU): `reqs` / `occupancy` point into part 0 of n_parts equally laid out
+  // parts (one per rank, as all-gathered); request r lives in part r / reqs_per_part, and the
+  // occupancy of a node is the sum over the parts
+  uint32_t n_parts, reqs_per_part;
+  uint64_t part_stride_bytes;
 };
 
 constexpr uint32_t kPlaceThreads = 512;
@@ -91,6 +96,35 @@ __device__ __forceinline__ unsigned long long place_key(const lwse_place_req& r,
          (unsigned long long)(index & 0xFFFFFFu);
 }
 
+__device__ __forceinline__ lwse_place_req load_req(const PlaceArgs& a, uint32_t r) {
+  const lwse_place_req* p = a.reqs;
+  if (a.n_parts > 1u) {
+    const uint32_t part = r / a.reqs_per_part, j = r - part * a.reqs_per_part;
+    p = reinterpret_cast<const lwse_place_req*>(reinterpret_cast<const uint8_t*>(a.reqs) +
+                                                (uint64_t)part * a.part_stride_bytes) + j;
+  } else {
+    p += r;
+  }
+  const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p)), hi = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  lwse_place_req q;
+  q.priority = u64_of(lo.x, lo.y);
+  q.group_key = u64_of(lo.z, lo.w);
+  q.group = hi.x;
+  q.ns = hi.y;
+  q.size = (int32_t)hi.z;
+  q.leader_node = hi.w;
+  return q;
+}
+
+__device__ __forceinline__ uint32_t load_occupancy(const PlaceArgs& a, uint32_t n) {
+  if (!a.occupancy) return 0u;
+  uint32_t occ = 0;
+  for (uint32_t p = 0; p < a.n_parts; p++)
+    occ += __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(a.occupancy) +
+                                                    (uint64_t)p * a.part_stride_bytes) + n);
+  return occ;
+}
+
 constexpr uint32_t kUnusable = 0xFFFFFFFFu;
 // node word: min(free,15) << 28 | domain (28 bits); the exact free count only feeds dom_free
 
@@ -114,7 +148,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
     if (n < a.n_nodes) {
       const uint4 nr = ldg_stream(reinterpret_cast<const uint4*>(a.nodes + n));
       const uint32_t d = nr.z, cap = nr.w & 0xFFFFu, nflags = nr.w >> 16;
-      const uint32_t occ = a.occupancy ? __ldg(a.occupancy + n) : 0u;
+      const uint32_t occ = load_occupancy(a, n);
       const bool usable = (nflags & LWSE_NODE_SCHEDULABLE) && (nflags & LWSE_NODE_HAS_TOPOLOGY) && d < a.n_domains;
       const uint32_t fr = usable && cap > occ ? cap - occ : 0u;
       if (usable) word = (min(fr, 15u) << 28) | d;
@@ -129,7 +163,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
     for (uint32_t i = gtid; i < a.next_zero_words; i += gsize) a.next_zero[i] = 0u;
   }
   for (uint32_t r = gtid; r < a.n_reqs; r += gsize) {
-    const lwse_place_req rq = a.reqs[r];
+    const lwse_place_req rq = load_req(a, r);
     a.choice[r] = LWSE_NONE;
     a.state[r] = 0;
     if (rq.leader_node == LWSE_NONE) {
@@ -175,7 +209,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
       if (blockIdx.x == 0 && tid == 0) a.counters[(round + 1u) % 3u] = 0;
       for (uint32_t k = blockIdx.x; k < n_unpinned; k += gridDim.x) {
         const uint32_t r = __ldcg(a.unpinned + k);
-        const lwse_place_req rq = a.reqs[r];
+        const lwse_place_req rq = load_req(a, r);
         if (rq.ns >= a.n_namespaces || rq.size < 1) {
           if (tid == 0) a.state[r] = 1;
           continue;
@@ -262,7 +296,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
 
   // ---------------- results ----------------
   for (uint32_t r = gtid; r < a.n_reqs; r += gsize) {
-    const lwse_place_req rq = a.reqs[r];
+    const lwse_place_req rq = load_req(a, r);
     lwse_place_out o;
     o.domain_id = LWSE_NONE;
     o.leader_node = LWSE_NONE;
@@ -316,7 +350,7 @@ int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_doma
                  const lwse_place_req* d_reqs, uint32_t n_reqs, const uint32_t* d_occupancy,
                  uint32_t n_namespaces, lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes,
                  uint32_t* h_rounds, int sm_count, cudaStream_t s, int* cuda_err, uint32_t call_index,
-                 bool fresh) {
+                 bool fresh, uint32_t n_parts, uint32_t reqs_per_part, uint64_t part_stride_bytes) {
   *cuda_err = 0;
   if (n_reqs > 0xFFFFFFu || n_domains >= (1u << 28) ||
       scratch_bytes < place_scratch_bytes(n_nodes, n_domains, n_reqs, n_namespaces)) {
@@ -365,6 +399,9 @@ int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_doma
   a.n_domains = n_domains;
   a.n_reqs = n_reqs;
   a.n_namespaces = n_namespaces;
+  a.n_parts = n_parts ? n_parts : 1u;
+  a.reqs_per_part = reqs_per_part ? reqs_per_part : n_reqs;
+  a.part_stride_bytes = part_stride_bytes;
 
   const size_t words_bytes = ((size_t)((n_nodes + 31u) & ~31u) + ((n_domains + 3u) & ~3u)) * 4;
   size_t smem = 256 + words_bytes;

@@ -38,6 +38,11 @@ SYMBOLS = {
         [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p],
         C.c_int,
     ),
+    "lwse_place_gathered_device": (
+        [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p,
+         C.POINTER(C.c_uint32), C.c_void_p],
+        C.c_int,
+    ),
     "lwse_sweep_ds_host": ([C.c_void_p, C.POINTER(R.DsTables)], C.c_int),
     "lwse_sweep_ds_device": ([C.c_void_p, C.POINTER(R.DsTables), C.c_void_p], C.c_int),
     "lwse_group_keys_host": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p], C.c_int),
@@ -169,6 +174,17 @@ class Engine:
         self._check(
             lib().lwse_place_device(self._h, R.ptr(d_reqs), n_reqs, R.ptr(d_occupancy), n_namespaces,
                                     R.ptr(d_out), C.byref(rounds) if want_rounds else None, stream)
+        )
+        return rounds.value if want_rounds else None
+
+    def place_gathered_device(self, d_parts, n_parts, part_stride_bytes, reqs_offset_bytes, reqs_per_part,
+                              n_namespaces, d_out, stream=None, want_rounds=False):
+        """Placement over the all-gathered [occupancy | requests] parts of every rank."""
+        rounds = C.c_uint32(0)
+        self._check(
+            lib().lwse_place_gathered_device(self._h, R.ptr(d_parts), n_parts, part_stride_bytes, reqs_offset_bytes,
+                                             reqs_per_part, n_namespaces, R.ptr(d_out),
+                                             C.byref(rounds) if want_rounds else None, stream)
         )
         return rounds.value if want_rounds else None
 
