@@ -148,3 +148,32 @@ def test_group_keys_kats_and_hashlib(engine):
     got = engine.group_keys_host(msgs)
     for m, d in zip(msgs, got):
         assert d.tobytes() == hashlib.sha1(m).digest()
+
+
+def test_placement_gathered_parts_matches_oracle(engine):
+    """lwse_place_gathered_device over the payloads of three (simulated) ranks."""
+    import torch
+    import oracle
+    from lws_b200 import distributed as D
+
+    p = synth.profile("C3", 0.03)
+    p.p_exclusive, p.p_leader_unscheduled, p.node_capacity, p.size_choices, p.n_nodes = 0.4, 0.5, 40, (8,), 3000
+    t = synth.make(p, seed=21)
+    world = 3
+    shards = D.shard_lws_tables(t.lws, t.groups, t.pod_state, t.pod_ident, world)
+    engine.upload_nodes(t.nodes, t.n_domains)
+    parts, caps = [], []
+    for lws, grp, pst, pid, _, _ in shards:
+        _, _, occ = oracle.sweep_lws(lws, grp, pst, pid, t.nodes, want_occupancy=True)
+        parts.append((occ, encoder.encode_place_requests(lws, grp)))
+    cap = max(len(r) for _, r in parts)
+    blob = np.concatenate([D.pack_part(o, r, cap) for o, r in parts])
+    stride, off = D.part_layout(len(t.nodes), cap)
+    occ_all, reqs_all = D.unpack_parts(blob, world, len(t.nodes), cap)
+    want = oracle.place(t.nodes, occ_all, t.n_domains, 1, reqs_all)
+    d_blob = torch.from_numpy(blob).cuda()
+    d_out = torch.zeros(world * cap * R.PLACE_OUT.itemsize, dtype=torch.uint8, device="cuda")
+    rounds = engine.place_gathered_device(d_blob, world, stride, off, cap, 1, d_out, want_rounds=True)
+    got = d_out.cpu().numpy().view(R.PLACE_OUT)
+    same(got, want, "place_out(gathered)")
+    assert rounds >= 1 and ((want["flags"] & R.PLACE_PLACED) != 0).sum() > 0
