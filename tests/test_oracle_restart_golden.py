@@ -1,0 +1,113 @@
+"""Restart-policy vectors of the reference, run through encoder + oracle.
+
+  pkg/controllers/pod_controller_test.go:427-532   current vs stale worker-sts owner
+  test/integration/controllers/leaderworkerset_test.go:408-563   None / OnPodRestart /
+      annotation+pending / AfterStart pending / AfterStart running (workers owned by the
+      leader Pod, test/testutils/util.go:58-88)
+  pkg/utils/pod/pod_utils_test.go:28-101            ContainerRestarted
+  pkg/utils/statefulset/statefulset_utils_test.go:26-153  GetParentNameAndOrdinal, StatefulsetReady
+"""
+import pytest
+
+from lws_b200 import api, encoder
+from lws_b200 import records as R
+
+
+def labels(lws, group, worker, rev="revision-1"):
+    return {api.SetNameLabelKey: lws.name, api.WorkerIndexLabelKey: str(worker), api.GroupIndexLabelKey: str(group),
+            api.RevisionKey: rev}
+
+
+def group_flags(oracle_sweep, lws, pods, stss):
+    item = encoder.LwsItem(lws=lws, revision_key="revision-1",
+                           leader_sts=api.StatefulSet(name=lws.name, replicas=lws.replicas,
+                                                      annotations={api.ReplicasAnnotationKey: str(lws.replicas)}))
+    t = encoder.encode_lws([item], encoder.Cluster(pods=pods, statefulsets=stss))
+    assert not t.lws[0]["flags"] & R.LWS_IRREGULAR
+    _, go = oracle_sweep(t)
+    return int(go[0]["flags"]), int(go[0]["first_trigger"]), t
+
+
+# pod_controller_test.go:427-532
+@pytest.mark.parametrize("owner_uid,want_deleted", [("sts-current", True), ("sts-stale", False)])
+def test_handle_restart_policy_uses_current_worker_ownership(oracle_sweep, owner_uid, want_deleted):
+    lws = api.LeaderWorkerSet("test-sample", replicas=1, size=2, restartPolicy=api.RecreateGroupOnPodRestart)
+    leader = api.Pod("test-sample-0", uid="leader-current", labels=labels(lws, 0, 0))
+    sts = api.StatefulSet("test-sample-0", uid="sts-current", labels={api.SetNameLabelKey: lws.name, api.GroupIndexLabelKey: "0"},
+                          ownerReferences=[api.OwnerReference("Pod", leader.name, leader.uid)])
+    worker = api.Pod("test-sample-0-1", labels=labels(lws, 0, 1), deletionTimestamp=True,
+                     ownerReferences=[api.OwnerReference("StatefulSet", "test-sample-0", owner_uid)])
+    flags, first, t = group_flags(oracle_sweep, lws, [leader, worker], [sts])
+    assert bool(flags & R.GOUT_DELETE_LEADER) == want_deleted
+    assert not flags & (R.GOUT_LEADER_DELETING | R.GOUT_RESTART_ERROR)
+    if want_deleted:
+        assert t.group_pod_names[0][first] == "test-sample-0-1"
+
+
+def _group_of_four(lws, pending=None, running=False, deleting="test-sample-0-1"):
+    leader = api.Pod("test-sample-0", labels=labels(lws, 0, 0), phase="Running" if running else "")
+    pods = [leader]
+    for i in range(1, 4):
+        name = f"test-sample-0-{i}"
+        pods.append(api.Pod(name, labels=labels(lws, 0, i), phase="Pending" if name == pending else ("Running" if running else ""),
+                            deletionTimestamp=(name == deleting),
+                            ownerReferences=[api.OwnerReference("Pod", leader.name, leader.uid)]))
+    return pods
+
+
+# test/integration/controllers/leaderworkerset_test.go:408-563
+@pytest.mark.parametrize(
+    "policy,annot,pending,running,want",
+    [(api.NoneRestartPolicy, False, None, False, False),
+     (api.RecreateGroupOnPodRestart, False, None, False, True),
+     (api.RecreateGroupOnPodRestart, True, "test-sample-0-2", False, False),
+     (api.RecreateGroupAfterStart, False, "test-sample-0-2", False, False),
+     (api.RecreateGroupAfterStart, False, None, True, True)],
+)
+def test_integration_restart_policies(oracle_sweep, policy, annot, pending, running, want):
+    lws = api.LeaderWorkerSet("test-sample", replicas=1, size=4, restartPolicy=policy,
+                              annotations={api.RecreateGroupAfterStartAnnotationKey: "true"} if annot else {})
+    flags, first, t = group_flags(oracle_sweep, lws, _group_of_four(lws, pending, running), [])
+    assert bool(flags & R.GOUT_DELETE_LEADER) == want
+    if want:  # "Worker pod test-sample-0-1 failed, deleted leader pod test-sample-0 to recreate group 0"
+        assert t.group_pod_names[0][first] == "test-sample-0-1"
+    assert bool(flags & R.GOUT_PENDING) == (pending is not None)
+
+
+def test_leader_already_deleting_returns_true_without_delete(oracle_sweep):
+    """pod_controller.go:255-257."""
+    lws = api.LeaderWorkerSet("test-sample", replicas=1, size=4)
+    pods = _group_of_four(lws)
+    pods[0].deletionTimestamp = True
+    flags, _, _ = group_flags(oracle_sweep, lws, pods, [])
+    assert flags & R.GOUT_LEADER_DELETING and not flags & R.GOUT_DELETE_LEADER
+    assert not flags & R.GOUT_CREATE_WSTS  # :125 leader deleting → no worker sts
+
+
+# pkg/utils/pod/pod_utils_test.go:28-101 ContainerRestarted
+@pytest.mark.parametrize(
+    "phase,init,main,want",
+    [("Running", [], [1], True), ("Pending", [2], [0], True), ("Running", [], [0], False),
+     ("Failed", [], [3], False), ("Succeeded", [1], [1], False)],
+)
+def test_container_restarted(oracle_sweep, phase, init, main, want):
+    lws = api.LeaderWorkerSet("test-sample", replicas=1, size=2)
+    leader = api.Pod("test-sample-0", labels=labels(lws, 0, 0), phase="Running")
+    worker = api.Pod("test-sample-0-1", labels=labels(lws, 0, 1), phase=phase, initContainerRestartCounts=init,
+                     containerRestartCounts=main, ownerReferences=[api.OwnerReference("Pod", leader.name, leader.uid)])
+    flags, _, _ = group_flags(oracle_sweep, lws, [leader, worker], [])
+    assert bool(flags & R.GOUT_DELETE_LEADER) == want
+
+
+# pkg/utils/statefulset/statefulset_utils_test.go:26-153
+@pytest.mark.parametrize(
+    "name,parent,ordinal",
+    [  # the reference's 7 cases (statefulset_utils_test.go:26-75) …
+     ("lws-samples-132", "lws-samples", 132), ("lws-samples-132-u", "", -1), ("lws-samples-", "", -1),
+     ("lws-samples-0", "lws-samples", 0), ("lws-samples--1", "lws-samples-", 1), ("lws-samples1", "", -1),
+     ("lws-samples-1-0", "lws-samples-1", 0),
+     # … plus the int32 overflow rule of strconv.ParseInt(…, 10, 32)
+     ("x-99999999999999", "x", -1)],
+)
+def test_get_parent_name_and_ordinal(name, parent, ordinal):
+    assert encoder.get_parent_name_and_ordinal(name) == (parent, ordinal)

@@ -82,6 +82,17 @@ def del_surge(s):
     s.delete_leader_pods_above_replicas()
 
 
+def replicas_then(n, *fns):
+    """UpdateReplicaCount followed by more helper calls in the same lwsUpdateFn."""
+
+    def run(s):
+        s.set_replicas(n)
+        for f in fns:
+            f(s)
+
+    return run
+
+
 TRACES = {
     # :631-727 leaderTemplate changed with default strategy
     "T1": (_lws(4), [
@@ -125,6 +136,61 @@ TRACES = {
         (rdy(2), (0, 5, 5, 3, UP)),
         (seq(rdy(1), del_surge), (0, 4, 4, 3, UP)),
         (rdy(0), (0, 4, 4, 4, AV)),
+    ]),
+    # :856-914 rolling update with both worker template and number of replicas changed
+    "T4": (_lws(4), [
+        (all_rdy, (0, 4, 4, 4, AV)),
+        (seq(update_and_replicas(6), create_stale(4, 6)), (4, 6, 4, 0, UP)),
+        (all_rdy, (0, 6, 6, 6, AV)),
+    ]),
+    # :916-1006 replicas increases during rolling update
+    "T5": (_lws(4), [
+        (all_rdy, (0, 4, 4, 4, AV)),
+        (update, (3, 4, 4, 0, UP)),
+        (rdy(3), (2, 4, 4, 1, UP)),
+        (replicas_then(6, create(4, 6), rdy(4), rdy(5)), (2, 6, 6, 3, UP)),
+        (all_rdy, (0, 6, 6, 6, AV)),
+    ]),
+    # :1008-1086 replicas decreases during rolling update
+    "T6": (_lws(6), [
+        (all_rdy, (0, 6, 6, 6, AV)),
+        (update, (5, 6, 6, 0, UP)),
+        (replicas_then(3, del_surge), (2, 3, 3, 0, UP)),
+        (all_rdy, (0, 3, 3, 3, AV)),
+    ]),
+    # :1326-1402 rolling update with maxUnavailable and maxSurge set
+    "T9": (_lws(4, mu=2, ms=2), [
+        (all_rdy, (0, 4, 4, 4, AV)),
+        (seq(update, create_stale(4, 6)), (2, 6, 4, 0, UP)),
+        (seq(rdy(3), rdy(2), delete(4, 6)), (0, 4, 4, 2, None)),
+        (rdy(1, 0), (0, 4, 4, 4, AV)),
+    ]),
+    # :1766-1876 multiple rolling update with maxSurge set
+    "T14": (_lws(4, ms=2), [
+        (all_rdy, (0, 4, 4, 4, AV)),
+        (seq(update, create_stale(4, 6)), (3, 6, 4, 0, UP)),
+        (rdy(5, 4), (1, 6, 6, 2, UP)),
+        (update, (3, 6, 6, 0, UP)),
+        (all_rdy, (None, None, None, None, AV)),
+        (del_surge, (0, 4, 4, 4, AV)),
+    ]),
+    # :2199-2275 rolling update with no ready replicas
+    "T16": (_lws(2, mu=1), [
+        (all_rdy, (0, 2, 2, 2, AV)),
+        (unready(0), (0, None, None, None, PR)),
+        (unready(1), (0, None, None, None, PR)),
+        (update, (1, 2, 0, 0, UP)),
+        (rdy(1), (0, None, None, None, None)),
+        (rdy(0), (None, None, None, None, AV)),
+    ]),
+    # :2408-2496 rolling update with the partition and maxSurge setting
+    "T18": (_lws(3, ms=1, partition=2), [
+        (all_rdy, (2, 3, 3, 3, AV)),
+        (update, (2, 4, 3, 0, UP)),
+        (seq(create(3, 4), rdy(3), rdy(2)), (2, 4, 4, 2, AV)),
+        (partition(0), (0, 4, 4, 2, UP)),
+        (rdy(1, 0), (0, 3, 4, 4, AV)),
+        (delete(3, 4), (0, 3, 3, 3, AV)),
     ]),
     # :2132-2197 unready replica below the partition counts as unavailable
     "T15": (_lws(4, mu=2), [
