@@ -290,6 +290,10 @@ typedef struct lwse_lws_tables {
 #define LWSE_SWEEP_SKIP_GROUP_PASS (1u << 1) /* profiling: run only the LWS-level pass
                                                 (group_out must hold a previous result) */
 #define LWSE_SWEEP_SKIP_LWS_PASS (1u << 2)   /* profiling: skip the LWS-level pass       */
+#define LWSE_SWEEP_REUSE_POD_IDENT (1u << 4) /* host entry point only: the pod identity column
+                                                (revision hash, owner uid — fixed at pod creation)
+                                                is unchanged since this engine's previous host
+                                                sweep with the same n_pods; skip its upload     */
 #define LWSE_SWEEP_SKIP_POD_SCAN (1u << 3)   /* profiling: skip the pod-state scan (its
                                                 bitmaps must hold a previous result)     */
 

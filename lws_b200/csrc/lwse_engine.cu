@@ -27,6 +27,8 @@ int launch_sha1(const uint8_t* d_bytes, const uint32_t* d_offsets, uint32_t n, u
                 int sm_count, cudaStream_t s, int* cuda_err);
 }  // namespace lwse
 
+const uint32_t* g_last_place_counters = nullptr;
+
 namespace {
 
 // A device buffer that only grows (sweeps reuse their staging memory).
@@ -65,6 +67,7 @@ struct lwse_engine {
   // staging for the *_host entry points
   DevBuf lws, groups, pod_state, pod_ident, lws_out, group_out, occupancy, scan_scratch;
   DevBuf place_reqs, place_out, place_occ, place_scratch;
+  uint64_t ident_rows = ~0ull;       // rows of the identity column resident from the last host sweep
   uint32_t place_calls = 0;          // selects the scratch half
   uint64_t place_geometry = 0;       // (n_reqs, n_namespaces, nodes, domains) the scratch was laid out for
   DevBuf ds, ds_roles, ds_revroles, ds_out, ds_role_out, ds_revrole_out;
@@ -260,7 +263,9 @@ LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* h) {
   LWSE_CUDA(e, e->lws.reserve(b_lws + 16));
   LWSE_CUDA(e, e->groups.reserve(b_grp + 16));
   LWSE_CUDA(e, e->pod_state.reserve(b_pst + 16));
+  const void* ident_before = e->pod_ident.p;
   LWSE_CUDA(e, e->pod_ident.reserve(b_pid + 16));
+  const bool ident_moved = ident_before != e->pod_ident.p;
   LWSE_CUDA(e, e->scan_scratch.reserve(lwse::lws_sweep_scratch_bytes(h->n_pods)));
   LWSE_CUDA(e, e->lws_out.reserve(b_lo + 16));
   LWSE_CUDA(e, e->group_out.reserve(b_go + 16));
@@ -272,7 +277,10 @@ LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* h) {
   if (b_grp) LWSE_CUDA(e, cudaMemcpyAsync(e->groups.p, h->groups, b_grp, cudaMemcpyHostToDevice, s));
   if (b_pst) {
     LWSE_CUDA(e, cudaMemcpyAsync(e->pod_state.p, h->pod_state, b_pst, cudaMemcpyHostToDevice, s));
-    LWSE_CUDA(e, cudaMemcpyAsync(e->pod_ident.p, h->pod_ident, b_pid, cudaMemcpyHostToDevice, s));
+    // the identity column only changes when pods are created or deleted
+    const bool reuse = (h->flags & LWSE_SWEEP_REUSE_POD_IDENT) && e->ident_rows == h->n_pods && !ident_moved;
+    if (!reuse) LWSE_CUDA(e, cudaMemcpyAsync(e->pod_ident.p, h->pod_ident, b_pid, cudaMemcpyHostToDevice, s));
+    e->ident_rows = h->n_pods;
   }
 
   lwse_lws_tables d = *h;
@@ -346,6 +354,21 @@ LWSE_API int lwse_place_gathered_device(lwse_engine* e, const void* d_parts, uin
   return place_common(e, reinterpret_cast<const lwse_place_req*>(base + reqs_offset_bytes), n_parts * reqs_per_part,
                       reinterpret_cast<const uint32_t*>(base), n_namespaces, d_out, rounds_out, stream, n_parts,
                       reqs_per_part, part_stride_bytes);
+}
+
+// Tuning aid (not part of lwse.h): phase timestamps of the most recent placement kernel.
+extern "C" __attribute__((visibility("default"))) int lwse_debug_place_trace(lwse_engine* e, uint64_t* out16) {
+  if (!e || !out16 || !e->place_scratch.p || e->place_calls == 0) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  cudaDeviceSynchronize();
+  // the half used by the last call: layout [holder | counters …]; holder size is unknown here, so the
+  // launcher recorded the counters pointer
+  if (!g_last_place_counters) return LWSE_ERR_NOT_READY;
+  uint32_t raw[32];
+  if (cudaMemcpy(raw, g_last_place_counters + 16, sizeof(raw), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return LWSE_ERR_CUDA;
+  for (int k = 0; k < 16; k++) out16[k] = (uint64_t)raw[2 * k] | ((uint64_t)raw[2 * k + 1] << 32);
+  return LWSE_OK;
 }
 
 LWSE_API int lwse_place_host(lwse_engine* e, const lwse_place_req* reqs, uint32_t n_reqs,

@@ -89,13 +89,18 @@ __global__ void __launch_bounds__(256) pod_scan_kernel(const PodScanArgs a) {
     }
 #pragma unroll
     for (int j = 0; j < U; j++) {
-      const uint32_t b[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-      uint32_t pend = 0, ev = 0;
+      // SWAR over the 4 pods of this lane: byte k of X = low byte of pod k's state word
+      // (phase bits 0-1, any-restart bit 2, deleting bit 3), both predicates evaluated on the
+      // four bytes at once, then the four bit-0s are gathered into a nibble with one multiply.
+      const uint32_t X = __byte_perm(__byte_perm(v[j].x, v[j].y, 0x0040), __byte_perm(v[j].z, v[j].w, 0x0040), 0x5410);
+      const uint32_t y = X >> 1, z = X >> 2, w3 = X >> 3;
+      const uint32_t P = X & ~y & 0x01010101u;                  // phase == Pending (bit0 ∧ ¬bit1)
+      const uint32_t E = (((X ^ y) & z) | w3) & 0x01010101u;    // (phase ∈ {Pending,Running} ∧ restart) ∨ deleting
+      const uint32_t pend = (P * 0x10204080u) >> 28, ev = (E * 0x10204080u) >> 28;
+      if (OCC) {
+        const uint32_t b[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        pend |= ((b[k] & LWSE_POD_PHASE_MASK) == LWSE_POD_PHASE_PENDING ? 1u : 0u) << k;
-        ev |= (pod_has_event(b[k]) ? 1u : 0u) << k;
-        if (OCC) {
+        for (int k = 0; k < 4; k++) {
           if (b[k] & LWSE_POD_SCHEDULED) {
             const uint32_t node = b[k] >> LWSE_POD_NODE_SHIFT;
             if (node < a.n_nodes) atomicAdd(a.occupancy + node, 1u);

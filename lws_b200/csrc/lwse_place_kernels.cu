@@ -23,6 +23,8 @@
 
 namespace cg = cooperative_groups;
 
+extern const uint32_t* g_last_place_counters;
+
 namespace lwse {
 
 struct PlaceArgs {
@@ -125,6 +127,16 @@ __device__ __forceinline__ uint32_t load_occupancy(const PlaceArgs& a, uint32_t 
   return occ;
 }
 
+// phase timestamps (ns, %globaltimer) of CTA 0 for tuning: counters[16 + 2k, 16 + 2k + 1]
+__device__ __forceinline__ void stamp(const PlaceArgs& a, uint32_t k) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && k < 16u) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.counters[16 + 2 * k] = (uint32_t)t;
+    a.counters[17 + 2 * k] = (uint32_t)(t >> 32);
+  }
+}
+
 constexpr uint32_t kUnusable = 0xFFFFFFFFu;
 // node word: min(free,15) << 28 | domain (28 bits); the exact free count only feeds dom_free
 
@@ -134,10 +146,14 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   unsigned long long* s_best = reinterpret_cast<unsigned long long*>(smem + 16);  // 16 warps
   uint32_t* s_best_n = reinterpret_cast<uint32_t*>(smem + 16 + 16 * 8);
+  uint32_t* s_flag = reinterpret_cast<uint32_t*>(smem + 16 + 16 * 8 + 16 * 4);
   uint32_t* s_words = reinterpret_cast<uint32_t*>(smem + 256);
   const uint32_t n_pad = (a.n_nodes + 31u) & ~31u;
+  const uint32_t nd4 = (a.n_domains + 3u) & ~3u;
+  uint32_t* s_hi = s_words + n_pad + nd4;  // per-domain score of the current request, 0 = may not claim
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t gtid = blockIdx.x * blockDim.x + tid, gsize = gridDim.x * blockDim.x;
+  stamp(a, 0);
 
   // ---------------- phase 0: node words, domain capacities, pinned claims ----------------
   // (this scratch half was left clean — holders ~0, counters and capacities 0 — by the previous call)
@@ -179,8 +195,10 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  stamp(a, 1);
   __threadfence();
   grid.sync();
+  stamp(a, 2);
 
   const uint32_t n_unpinned = __ldcg(a.counters + 4);
   uint32_t* compact = a.g_compact;
@@ -200,6 +218,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
       compact = s_words;
       dom_free = s_words + n_pad;
     }
+    stamp(a, 3);
 
     // ---------------- phase 2: deferred-acceptance rounds, one CTA per request ----------------
     for (;; round++) {
@@ -210,36 +229,81 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
       for (uint32_t k = blockIdx.x; k < n_unpinned; k += gridDim.x) {
         const uint32_t r = __ldcg(a.unpinned + k);
         const lwse_place_req rq = load_req(a, r);
-        if (rq.ns >= a.n_namespaces || rq.size < 1) {
-          if (tid == 0) a.state[r] = 1;
-          continue;
-        }
-        if (__ldcg(a.state + r)) continue;
         const unsigned long long key = place_key(rq, r, false);
         unsigned long long* hold = a.holder + (uint64_t)rq.ns * a.n_domains;
-        const uint32_t cur = __ldcg(a.choice + r);
-        if (cur != LWSE_NONE) {
-          const uint32_t cd = compact[cur] & 0x0FFFFFFFu;
-          if (__ldcg(hold + cd) == key) continue;  // still holding its domain (block-uniform)
+        // Whether this request needs a proposal is decided by ONE thread and broadcast: holders
+        // change under our feet during a round (other CTAs' atomicMin), and a CTA whose threads
+        // disagreed would split around the barriers below.
+        __syncthreads();
+        if (tid == 0) {
+          uint32_t need = 1;
+          if (rq.ns >= a.n_namespaces || rq.size < 1) {
+            a.state[r] = 1;
+            need = 0;
+          } else if (__ldcg(a.state + r)) {
+            need = 0;
+          } else {
+            const uint32_t cur = __ldcg(a.choice + r);
+            if (cur != LWSE_NONE && __ldcg(hold + (compact[cur] & 0x0FFFFFFFu)) == key) need = 0;  // still holding
+          }
+          *s_flag = need;
         }
-        // score every (request, node) pair: the CTA's threads stride over the node words
+        __syncthreads();
+        if (!*s_flag) continue;
         const uint32_t key_lo = (uint32_t)rq.group_key, key_hi = (uint32_t)(rq.group_key >> 32);
         const uint32_t size = (uint32_t)rq.size;
         unsigned long long best = 0;
         uint32_t best_n = LWSE_NONE;
-        for (uint32_t n = tid; n < a.n_nodes; n += kPlaceThreads) {
-          const uint32_t w = compact[n];
-          if (w == kUnusable || (w >> 28) == 0u) continue;
-          const uint32_t d = w & 0x0FFFFFFFu;
-          const uint32_t df = dom_free[d];
-          if (df < size) continue;
-          if (__ldcg(hold + d) < key) continue;  // held by a higher-priority group (monotone: never frees)
-          const uint32_t hi = mix32(key_lo ^ (d * 0x9E3779B1u));  // per-group rendezvous hash of the domain
-          const uint32_t lo = ((w >> 28) << 28) | (mix32(key_hi ^ (n * 0x85EBCA77u)) >> 4);
-          const unsigned long long s = ((unsigned long long)hi << 32) | lo;
-          if (best_n == LWSE_NONE || s > best) {  // n ascends per thread: ties keep the lower index
-            best = s;
-            best_n = n;
+        if (a.smem_nodes) {
+          // Pass 1 — domains.  Capacity, "not held by a higher-priority group" and the domain part
+          // of the score are per-domain facts: compute them once per domain into shared memory
+          // and find the winning domain score H.  (Doing this per node made every node iteration
+          // wait on an L2 holder load — 8.8 us per request — and then spend ~60 instructions on
+          // two hashes — 5 us per request; both measured with %globaltimer stamps.)
+          uint32_t my_hi = 0;
+          for (uint32_t d = tid; d < a.n_domains; d += kPlaceThreads) {
+            uint32_t hi = 0;
+            if (dom_free[d] >= size && __ldcg(hold + d) >= key) hi = mix32(key_lo ^ (d * 0x9E3779B1u)) | 1u;
+            s_hi[d] = hi;  // 0 = this request may not claim d
+            my_hi = max(my_hi, hi);
+          }
+          my_hi = __reduce_max_sync(0xFFFFFFFFu, my_hi);
+          if (lane == 0) s_best_n[warp] = my_hi;
+          __syncthreads();
+          uint32_t H = 0;
+#pragma unroll
+          for (int w = 0; w < (int)(kPlaceThreads / 32); w++) H = max(H, s_best_n[w]);
+          __syncthreads();  // s_best_n is reused by the arg-max below
+          // Pass 2 — nodes of the winning domain(s): every (request, node) pair is looked at, but
+          // only nodes whose domain carries the winning score are hashed and ranked.
+          if (H != 0u) {
+            for (uint32_t n = tid; n < a.n_nodes; n += kPlaceThreads) {
+              const uint32_t w = compact[n];
+              if (w == kUnusable || (w >> 28) == 0u) continue;
+              if (s_hi[w & 0x0FFFFFFFu] != H) continue;
+              const uint32_t lo = ((w >> 28) << 28) | (mix32(key_hi ^ (n * 0x85EBCA77u)) >> 4);
+              const unsigned long long sc = ((unsigned long long)H << 32) | lo;
+              if (best_n == LWSE_NONE || sc > best) {  // n ascends per thread: ties keep the lower index
+                best = sc;
+                best_n = n;
+              }
+            }
+          }
+        } else {
+          // node words in global memory (table too large for shared memory): one fused pass
+          for (uint32_t n = tid; n < a.n_nodes; n += kPlaceThreads) {
+            const uint32_t w = compact[n];
+            if (w == kUnusable || (w >> 28) == 0u) continue;
+            const uint32_t d = w & 0x0FFFFFFFu;
+            if (dom_free[d] < size) continue;
+            if (__ldcg(hold + d) < key) continue;  // held by a higher-priority group (monotone: never frees)
+            const uint32_t hi = mix32(key_lo ^ (d * 0x9E3779B1u)) | 1u;
+            const uint32_t lo = ((w >> 28) << 28) | (mix32(key_hi ^ (n * 0x85EBCA77u)) >> 4);
+            const unsigned long long sc = ((unsigned long long)hi << 32) | lo;
+            if (best_n == LWSE_NONE || sc > best) {
+              best = sc;
+              best_n = n;
+            }
           }
         }
         auto better = [](unsigned long long os, uint32_t on, unsigned long long s, uint32_t n) {
@@ -286,8 +350,10 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
         }
         __syncthreads();  // s_best is reused by the CTA's next request
       }
+      stamp(a, 4 + 2 * round);
       __threadfence();
       grid.sync();
+      stamp(a, 5 + 2 * round);
       const uint32_t proposals = __ldcg(counter);
       if (proposals == 0u || round > a.n_reqs + 2u) break;
     }
@@ -329,6 +395,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
     }
     a.out[r] = o;
   }
+  stamp(a, 15);
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -403,7 +470,7 @@ int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_doma
   a.reqs_per_part = reqs_per_part ? reqs_per_part : n_reqs;
   a.part_stride_bytes = part_stride_bytes;
 
-  const size_t words_bytes = ((size_t)((n_nodes + 31u) & ~31u) + ((n_domains + 3u) & ~3u)) * 4;
+  const size_t words_bytes = ((size_t)((n_nodes + 31u) & ~31u) + 2 * (size_t)((n_domains + 3u) & ~3u)) * 4 + 16;
   size_t smem = 256 + words_bytes;
   a.smem_nodes = smem <= 227u * 1024u ? 1u : 0u;
   if (!a.smem_nodes) smem = 256;
@@ -416,6 +483,7 @@ int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_doma
     }
     smem_set = smem;
   }
+  ::g_last_place_counters = a.counters;
   void* params[] = {&a};
   // one CTA per SM at most; a grid barrier costs more the more CTAs take part, and a round
   // needs no more CTAs than there are requests

@@ -185,6 +185,7 @@ SWEEP_GANG = 1 << 0
 SWEEP_SKIP_GROUP_PASS = 1 << 1
 SWEEP_SKIP_LWS_PASS = 1 << 2
 SWEEP_SKIP_POD_SCAN = 1 << 3
+SWEEP_REUSE_POD_IDENT = 1 << 4
 
 # --------------------------------------------------------------------------- #
 # placement

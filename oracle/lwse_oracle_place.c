@@ -26,7 +26,7 @@
  *   unpinned r   in ascending key order takes, among the (domain d, node n ∈ d) pairs
  *                with   dom_free[d] ≥ size(r) ∧ free[n] ≥ 1 ∧ (ns(r), d) not held,
  *                the pair with the largest score
- *                   hi = mix(key_lo ^ d·φ)                      per-group rendezvous hash of the domain
+ *                   hi = mix(key_lo ^ d·φ) | 1                  per-group rendezvous hash of the domain
  *                   lo = min(free[n], 15) << 28 | mix(key_hi ^ n·ψ) >> 4    emptiest node of it first
  *                (a per-group preference order over domains: any capacity-derived term would
  *                give all groups the same order and serialise the claim rounds; capacity is a
@@ -129,7 +129,7 @@ LWSO_API int lwso_place(const lwse_node_rec* nodes, uint32_t n_nodes, const uint
       uint32_t d = nodes[n].domain_id;
       if (hold[d] != ~0ull) continue;
       if (dom_free[d] < (uint32_t)r->size) continue;
-      uint32_t hi = mix32(key_lo ^ (d * 0x9E3779B1u));
+      uint32_t hi = mix32(key_lo ^ (d * 0x9E3779B1u)) | 1u;
       uint32_t lo = ((free_[n] > 15 ? 15u : free_[n]) << 28) | (mix32(key_hi ^ (n * 0x85EBCA77u)) >> 4);
       uint64_t s = ((uint64_t)hi << 32) | lo;
       if (!found || s > best) { /* ties keep the lower node index */

@@ -166,3 +166,26 @@ def test_large_idempotent_and_order_independent(engine):
     c = engine.sweep_lws_host(lws2, grp2, t.pod_state, t.pod_ident, flags=t.flags)
     assert c[0].tobytes() == a[0][perm].tobytes()
     assert c[1].tobytes() == a[1].tobytes()
+
+
+def test_reuse_pod_ident_flag(engine):
+    """LWSE_SWEEP_REUSE_POD_IDENT keeps the identity column of the previous host sweep."""
+    import oracle
+
+    t = synth.make("fuzz", 0.3, seed=17)
+    engine.upload_nodes(t.nodes, t.n_domains)
+    run_both(engine, t, occupancy=False)  # uploads both pod columns
+    # pod status changes (restarts appear), identities stay
+    rng = np.random.default_rng(5)
+    flip = rng.random(len(t.pod_state)) < 0.1
+    t.pod_state[flip] |= R.POD_ANY_RESTART
+    garbage = R.aligned_empty(len(t.pod_ident), R.POD_IDENT)  # must NOT be read
+    want = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, flags=t.flags)
+    got = engine.sweep_lws_host(t.lws, t.groups, t.pod_state, garbage, flags=t.flags | R.SWEEP_REUSE_POD_IDENT)
+    assert_same(got[0], want[0], "lws_out")
+    assert_same(got[1], want[1], "group_out")
+    # a different pod count invalidates the resident column: the flag is ignored
+    t2 = synth.make("fuzz", 0.2, seed=18)
+    want2 = oracle.sweep_lws(t2.lws, t2.groups, t2.pod_state, t2.pod_ident, t2.nodes, flags=t2.flags)
+    got2 = engine.sweep_lws_host(t2.lws, t2.groups, t2.pod_state, t2.pod_ident, flags=t2.flags | R.SWEEP_REUSE_POD_IDENT)
+    assert_same(got2[1], want2[1], "group_out")
