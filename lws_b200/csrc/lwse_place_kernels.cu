@@ -229,27 +229,15 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
       for (uint32_t k = blockIdx.x; k < n_unpinned; k += gridDim.x) {
         const uint32_t r = __ldcg(a.unpinned + k);
         const lwse_place_req rq = load_req(a, r);
+        // state / choice are written by this CTA only → every thread reads the same value
+        const uint32_t st = __ldcg(a.state + r), cur = __ldcg(a.choice + r);
         const unsigned long long key = place_key(rq, r, false);
         unsigned long long* hold = a.holder + (uint64_t)rq.ns * a.n_domains;
-        // Whether this request needs a proposal is decided by ONE thread and broadcast: holders
-        // change under our feet during a round (other CTAs' atomicMin), and a CTA whose threads
-        // disagreed would split around the barriers below.
-        __syncthreads();
-        if (tid == 0) {
-          uint32_t need = 1;
-          if (rq.ns >= a.n_namespaces || rq.size < 1) {
-            a.state[r] = 1;
-            need = 0;
-          } else if (__ldcg(a.state + r)) {
-            need = 0;
-          } else {
-            const uint32_t cur = __ldcg(a.choice + r);
-            if (cur != LWSE_NONE && __ldcg(hold + (compact[cur] & 0x0FFFFFFFu)) == key) need = 0;  // still holding
-          }
-          *s_flag = need;
+        if (rq.ns >= a.n_namespaces || rq.size < 1) {
+          if (tid == 0) a.state[r] = 1;
+          continue;
         }
-        __syncthreads();
-        if (!*s_flag) continue;
+        if (st) continue;
         const uint32_t key_lo = (uint32_t)rq.group_key, key_hi = (uint32_t)(rq.group_key >> 32);
         const uint32_t size = (uint32_t)rq.size;
         unsigned long long best = 0;
@@ -257,23 +245,38 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
         if (a.smem_nodes) {
           // Pass 1 — domains.  Capacity, "not held by a higher-priority group" and the domain part
           // of the score are per-domain facts: compute them once per domain into shared memory
-          // and find the winning domain score H.  (Doing this per node made every node iteration
-          // wait on an L2 holder load — 8.8 us per request — and then spend ~60 instructions on
-          // two hashes — 5 us per request; both measured with %globaltimer stamps.)
-          uint32_t my_hi = 0;
+          // and find the winning domain score H.  The same pass notices whether this request
+          // still holds the domain it proposed to earlier (then nothing is left to do).  Holders
+          // change under our feet during a round (other CTAs' atomicMin), so every decision the
+          // CTA branches on is reduced through shared memory — threads never branch on their own
+          // reading of a holder.  (Per-node holder loads cost 8.8 us per request and per-node
+          // hashing 5 us; a serial chain of decision loads 2 us — all measured with %globaltimer.)
+          const uint32_t cur_dom = cur != LWSE_NONE ? (compact[cur] & 0x0FFFFFFFu) : LWSE_NONE;
+          uint32_t my_hi = 0, my_holding = 0;
           for (uint32_t d = tid; d < a.n_domains; d += kPlaceThreads) {
+            const unsigned long long h = __ldcg(hold + d);
             uint32_t hi = 0;
-            if (dom_free[d] >= size && __ldcg(hold + d) >= key) hi = mix32(key_lo ^ (d * 0x9E3779B1u)) | 1u;
+            if (dom_free[d] >= size && h >= key) hi = mix32(key_lo ^ (d * 0x9E3779B1u)) | 1u;
+            if (d == cur_dom && h == key) my_holding = 1u;
             s_hi[d] = hi;  // 0 = this request may not claim d
             my_hi = max(my_hi, hi);
           }
           my_hi = __reduce_max_sync(0xFFFFFFFFu, my_hi);
-          if (lane == 0) s_best_n[warp] = my_hi;
+          my_holding = __reduce_or_sync(0xFFFFFFFFu, my_holding);
+          __syncthreads();  // the previous request's arg-max is done with s_best / s_best_n
+          if (lane == 0) {
+            s_best_n[warp] = my_hi;
+            s_best[warp] = my_holding;
+          }
           __syncthreads();
-          uint32_t H = 0;
+          uint32_t H = 0, holding = 0;
 #pragma unroll
-          for (int w = 0; w < (int)(kPlaceThreads / 32); w++) H = max(H, s_best_n[w]);
-          __syncthreads();  // s_best_n is reused by the arg-max below
+          for (int w = 0; w < (int)(kPlaceThreads / 32); w++) {
+            H = max(H, s_best_n[w]);
+            holding |= (uint32_t)s_best[w];
+          }
+          __syncthreads();  // s_best / s_best_n are reused by the arg-max below
+          if (holding) continue;  // uniform: derived from shared memory
           // Pass 2 — nodes of the winning domain(s): every (request, node) pair is looked at, but
           // only nodes whose domain carries the winning score are hashed and ranked.
           if (H != 0u) {
@@ -290,7 +293,12 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
             }
           }
         } else {
-          // node words in global memory (table too large for shared memory): one fused pass
+          // node words in global memory (table too large for shared memory): one thread decides
+          // whether the request still holds its domain and broadcasts, then one fused pass
+          __syncthreads();
+          if (tid == 0) *s_flag = (cur != LWSE_NONE && __ldcg(hold + (compact[cur] & 0x0FFFFFFFu)) == key) ? 0u : 1u;
+          __syncthreads();
+          if (!*s_flag) continue;
           for (uint32_t n = tid; n < a.n_nodes; n += kPlaceThreads) {
             const uint32_t w = compact[n];
             if (w == kUnusable || (w >> 28) == 0u) continue;

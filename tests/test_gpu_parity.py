@@ -186,6 +186,7 @@ def test_reuse_pod_ident_flag(engine):
     assert_same(got[1], want[1], "group_out")
     # a different pod count invalidates the resident column: the flag is ignored
     t2 = synth.make("fuzz", 0.2, seed=18)
+    engine.upload_nodes(t2.nodes, t2.n_domains)
     want2 = oracle.sweep_lws(t2.lws, t2.groups, t2.pod_state, t2.pod_ident, t2.nodes, flags=t2.flags)
     got2 = engine.sweep_lws_host(t2.lws, t2.groups, t2.pod_state, t2.pod_ident, flags=t2.flags | R.SWEEP_REUSE_POD_IDENT)
     assert_same(got2[1], want2[1], "group_out")
