@@ -450,6 +450,13 @@ def run_ours(args):
                                    + 2 * words * 4 + ev * (4 + R.POD_IDENT.itemsize), ms_group),
             "lws_sweep_kernel": (n_lws * (R.LWS_REC.itemsize + R.LWS_OUT.itemsize) + n_grp * 4, ms_lws),
         }
+        traffic = None
+        try:  # per-launch DRAM bytes of the committed ncu capture (profiles/r1_final_summary.md)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if t.profile.name == "C3" and args.scale == 1.0:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
         dom = max(passes, key=lambda k: passes[k][1])
         dom_bytes, dom_ms = passes[dom]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
@@ -478,7 +485,7 @@ def run_ours(args):
                                            "(no pod created/deleted since the previous sweep), rank 0"}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": (traffic or {}).get(dom),
                          "bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms, "peak_source": peak_src,
                          "passes": {k: {"bytes": int(v[0]), "ms": v[1], "gbs": v[0] / (v[1] * 1e-3) / 1e9,
                                         "frac": v[0] / (v[1] * 1e-3) / 1e9 / peak} for k, v in passes.items()}},
