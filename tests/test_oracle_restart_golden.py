@@ -111,3 +111,33 @@ def test_container_restarted(oracle_sweep, phase, init, main, want):
 )
 def test_get_parent_name_and_ordinal(name, parent, ordinal):
     assert encoder.get_parent_name_and_ordinal(name) == (parent, ordinal)
+
+
+# pkg/schedulerprovider/volcano_provider_test.go:49-139: PodGroup MinMember = size (LeaderCreated) or 1 (LeaderReady)
+@pytest.mark.parametrize("startup,want", [(api.LeaderCreatedStartupPolicy, 3), (api.LeaderReadyStartupPolicy, 1)])
+def test_podgroup_min_member(oracle_sweep, startup, want):
+    lws = api.LeaderWorkerSet("test-lws", replicas=1, size=3, startupPolicy=startup)
+    leader = api.Pod("test-lws-0", labels=labels(lws, 0, 0), phase="Running")
+    item = encoder.LwsItem(lws=lws, revision_key="revision-1",
+                           leader_sts=api.StatefulSet(name=lws.name, replicas=1, annotations={api.ReplicasAnnotationKey: "1"}))
+    t = encoder.encode_lws([item], encoder.Cluster(pods=[leader]))
+    lo, go = oracle_sweep(t, R.SWEEP_GANG)
+    assert int(lo[0]["min_member"]) == want
+    assert go[0]["flags"] & R.GOUT_CREATE_PODGROUP  # pod_controller.go:130 reached for the leader pod
+    lo, go = oracle_sweep(t, 0)  # no SchedulerProvider configured
+    assert int(lo[0]["min_member"]) == 0 and not go[0]["flags"] & R.GOUT_CREATE_PODGROUP
+
+
+# pkg/utils/utils_test.go:25-64 SortByIndex: out-of-range and unparsable indices are dropped,
+# the last writer wins — observable through the encoder's row order
+def test_sort_by_index_semantics_in_encoder():
+    lws = api.LeaderWorkerSet("s", replicas=3, size=1)
+    mk = lambda name, idx: api.Pod(name, labels={api.SetNameLabelKey: "s", api.WorkerIndexLabelKey: "0",
+                                                  api.GroupIndexLabelKey: idx}, phase="Running", readyCondition=True)
+    pods = [mk("s-2", "2"), mk("s-0", "0"), mk("s-x", "abc")]
+    item = encoder.LwsItem(lws=lws, revision_key="r", leader_sts=api.StatefulSet(name="s", replicas=3, annotations={api.ReplicasAnnotationKey: "3"}))
+    t = encoder.encode_lws([item], encoder.Cluster(pods=pods))
+    assert len(t.groups) == 3  # slots 0..2; slot 1 is a zero-valued entry
+    present = [(int(g["flags"]) & R.GRP_POD_PRESENT) != 0 for g in t.groups]
+    assert present == [True, False, True]
+    assert t.lws[0]["flags"] & R.LWS_GROUP_LABEL_INVALID  # updateConditions would fail on "abc" (:434)
