@@ -177,3 +177,13 @@ def test_placement_gathered_parts_matches_oracle(engine):
     got = d_out.cpu().numpy().view(R.PLACE_OUT)
     same(got, want, "place_out(gathered)")
     assert rounds >= 1 and ((want["flags"] & R.PLACE_PLACED) != 0).sum() > 0
+
+
+@pytest.mark.parametrize("order", [("A", "B"), ("B", "A")])
+def test_ds_multi_cycle_flows_on_gpu(engine, order):
+    """executor_test.go:1244-1298 — 20 reconcile cycles each, decided by the CUDA planner."""
+    from test_oracle_ds_flows import run_flow
+
+    sweep = lambda t: engine.sweep_ds_host(t.ds, t.roles, t.revroles)
+    run_flow(sweep, (2, 4), (1, 2), (1, 2), (1, 1), order)
+    run_flow(sweep, (4, 3), (1, 2), (3, 1), (1, 2), order, check_orphans=True)

@@ -165,6 +165,38 @@ TRACES = {
         (seq(rdy(3), rdy(2), delete(4, 6)), (0, 4, 4, 2, None)),
         (rdy(1, 0), (0, 4, 4, 4, AV)),
     ]),
+    # :1404-1471 rolling update with replicas scaled up and maxSurge set
+    "T10": (_lws(2, ms=2), [
+        (all_rdy, (0, 2, 2, 2, AV)),
+        (seq(update_and_replicas(4), create_stale(2, 6)), (2, 6, None, None, UP)),
+        (all_rdy, (None, None, None, None, AV)),
+        (del_surge, (0, 4, 4, 4, AV)),
+    ]),
+    # :1473-1537 rolling update with replicas scaled down and maxSurge set
+    "T11": (_lws(6, ms=2), [
+        (all_rdy, (0, 6, 6, 6, AV)),
+        (update_and_replicas(3), (2, 5, None, None, UP)),
+        (seq(delete(5, 6), all_rdy), (None, None, None, None, AV)),
+        (del_surge, (0, 3, 3, 3, AV)),
+    ]),
+    # :1539-1607 rolling update with maxSurge greater than replicas
+    "T12": (_lws(2, ms=4), [
+        (all_rdy, (0, 2, 2, 2, AV)),
+        (seq(update, create_stale(2, 3)), (1, 3, None, None, UP)),
+        (all_rdy, (None, None, None, None, AV)),
+        (del_surge, (0, 2, 2, 2, AV)),
+    ]),
+    # :1609-1764 scale up and down during rolling update with maxSurge set
+    "T13": (_lws(4, ms=2), [
+        (all_rdy, (0, 4, 4, 4, AV)),
+        (seq(update, create_stale(4, 6)), (3, 6, 4, 0, UP)),
+        (replicas_then(6, create(6, 8)), (3, 8, 4, 2, UP)),
+        (rdy(7, 6), (3, 8, 6, 2, UP)),
+        (replicas_then(2, delete(4, 8), delete(3, 4)), (1, 3, 3, 0, UP)),
+        (rdy(2), (0, 3, 3, 1, UP)),
+        (seq(rdy(1), delete(2, 3)), (0, 2, 2, 1, UP)),
+        (rdy(0), (0, 2, 2, 2, AV)),
+    ]),
     # :1766-1876 multiple rolling update with maxSurge set
     "T14": (_lws(4, ms=2), [
         (all_rdy, (0, 4, 4, 4, AV)),
