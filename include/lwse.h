@@ -345,6 +345,45 @@ LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* host_tab
 LWSE_API int lwse_sweep_lws_device(lwse_engine* e, const lwse_lws_tables* dev_tables, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* Resident tables: incremental operation                                    */
+/* ------------------------------------------------------------------------- */
+/* A controller sees watch events, not tables: between two sweeps only a few rows change.
+ * The engine can keep the input tables resident in HBM; the host then sends row patches
+ * (lwse_resident_patch) and reads back only the result rows that changed
+ * (lwse_resident_sweep) — the actions the reconcilers have to take. */
+typedef enum lwse_table {
+  LWSE_TABLE_LWS = 0,       /* lwse_lws_rec    */
+  LWSE_TABLE_GROUPS = 1,    /* lwse_group_rec  */
+  LWSE_TABLE_POD_STATE = 2, /* lwse_pod_state  */
+  LWSE_TABLE_POD_IDENT = 3  /* lwse_pod_ident  */
+} lwse_table;
+
+/* Result rows that differ from the previous resident sweep (all rows after a load).
+ * n_* is the number of changed rows; if it exceeds the capacity the surplus rows are not
+ * returned and the caller falls back to lwse_resident_outputs.  Order is unspecified. */
+typedef struct lwse_changes {
+  uint32_t* lws_rows;        /* [lws_capacity]   row numbers          */
+  lwse_lws_out* lws_out;     /* [lws_capacity]   their new results    */
+  uint32_t lws_capacity;
+  uint32_t n_lws;            /* out */
+  uint32_t* group_rows;      /* [group_capacity] */
+  lwse_group_out* group_out; /* [group_capacity] */
+  uint32_t group_capacity;
+  uint32_t n_groups;         /* out */
+} lwse_changes;
+
+/* Copy the four input tables of `host` to the device; they stay resident (and the
+ * previous results are forgotten).  Output pointers in `host` are ignored. */
+LWSE_API int lwse_resident_load(lwse_engine* e, const lwse_lws_tables* host);
+/* Overwrite n rows of a resident table: row rows[i] ← the i-th packed row of `values`. */
+LWSE_API int lwse_resident_patch(lwse_engine* e, lwse_table which, const uint32_t* rows, const void* values,
+                                 uint32_t n);
+/* Sweep the resident tables (flags: LWSE_SWEEP_GANG).  `changes` may be NULL. */
+LWSE_API int lwse_resident_sweep(lwse_engine* e, uint32_t flags, lwse_changes* changes);
+/* Every result row of the last resident sweep. */
+LWSE_API int lwse_resident_outputs(lwse_engine* e, lwse_lws_out* lws_out, lwse_group_out* group_out);
+
+/* ------------------------------------------------------------------------- */
 /* Placement (build-defined spec — the reference has no node scoring)        */
 /* ------------------------------------------------------------------------- */
 

@@ -10,9 +10,20 @@
 
 namespace lwse {
 // lwse_lws_kernels.cu
+struct SweepChangeLists {
+  uint32_t* lws_rows = nullptr;
+  lwse_lws_out* lws_out = nullptr;
+  uint32_t lws_capacity = 0;
+  uint32_t* group_rows = nullptr;
+  lwse_group_out* group_out = nullptr;
+  uint32_t group_capacity = 0;
+  uint32_t* counts = nullptr;
+};
 int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
-                     void* scratch, int sm_count, cudaStream_t s, int* cuda_err);
+                     void* scratch, int sm_count, cudaStream_t s, int* cuda_err, const SweepChangeLists* cl);
 size_t lws_sweep_scratch_bytes(uint64_t n_pods);
+int launch_scatter(int row_words, void* table, uint64_t table_rows, const uint32_t* rows, const void* values,
+                   uint32_t n, cudaStream_t s, int* cuda_err);
 // lwse_place_kernels.cu
 int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_domains,
                  const lwse_place_req* d_reqs, uint32_t n_reqs, const uint32_t* d_occupancy,
@@ -68,6 +79,13 @@ struct lwse_engine {
   DevBuf lws, groups, pod_state, pod_ident, lws_out, group_out, occupancy, scan_scratch;
   DevBuf place_reqs, place_out, place_occ, place_scratch;
   uint64_t ident_rows = ~0ull;       // rows of the identity column resident from the last host sweep
+  // resident tables (lwse_resident_*)
+  DevBuf r_lws, r_groups, r_pst, r_pid, r_lws_out, r_group_out, r_scan;
+  DevBuf r_chg_lws_rows, r_chg_lws_out, r_chg_grp_rows, r_chg_grp_out, r_counts, r_patch_rows, r_patch_vals;
+  uint32_t rn_lws = 0, rn_groups = 0;
+  uint64_t rn_pods = 0;
+  bool r_loaded = false;
+  uint32_t* h_counts = nullptr;      // pinned, 2 words
   uint32_t place_calls = 0;          // selects the scratch half
   uint64_t place_geometry = 0;       // (n_reqs, n_namespaces, nodes, domains) the scratch was laid out for
   DevBuf ds, ds_roles, ds_revroles, ds_out, ds_role_out, ds_revrole_out;
@@ -179,7 +197,8 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
   }
   e->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMallocHost(reinterpret_cast<void**>(&e->h_rounds), 64) != cudaSuccess) {
+      cudaMallocHost(reinterpret_cast<void**>(&e->h_rounds), 64) != cudaSuccess ||
+      cudaMallocHost(reinterpret_cast<void**>(&e->h_counts), 64) != cudaSuccess) {
     (void)cudaGetLastError();
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -198,9 +217,13 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
                       &e->scan_scratch, &e->lws_out,
                       &e->group_out,  &e->occupancy,   &e->place_reqs, &e->place_out,   &e->place_occ,
                       &e->place_scratch, &e->ds,       &e->ds_roles,   &e->ds_revroles, &e->ds_out,
-                      &e->ds_role_out, &e->ds_revrole_out, &e->sha_bytes, &e->sha_offsets, &e->sha_digests};
+                      &e->ds_role_out, &e->ds_revrole_out, &e->sha_bytes, &e->sha_offsets, &e->sha_digests,
+                      &e->r_lws, &e->r_groups, &e->r_pst, &e->r_pid, &e->r_lws_out, &e->r_group_out, &e->r_scan,
+                      &e->r_chg_lws_rows, &e->r_chg_lws_out, &e->r_chg_grp_rows, &e->r_chg_grp_out, &e->r_counts,
+                      &e->r_patch_rows, &e->r_patch_vals};
     for (DevBuf* b : bufs) b->release();
     if (e->h_rounds) cudaFreeHost(e->h_rounds);
+    if (e->h_counts) cudaFreeHost(e->h_counts);
     cudaStreamDestroy(e->stream);
   }
   delete e;
@@ -241,7 +264,7 @@ LWSE_API int lwse_sweep_lws_device(lwse_engine* e, const lwse_lws_tables* t, voi
   LWSE_CUDA(e, e->scan_scratch.reserve(lwse::lws_sweep_scratch_bytes(t->n_pods)));
   int cuda_err = 0;
   int launched = lwse::launch_lws_sweep(t, (const lwse_node_rec*)e->nodes.p, e->n_nodes,
-                                        e->scan_scratch.p, e->sm_count, s, &cuda_err);
+                                        e->scan_scratch.p, e->sm_count, s, &cuda_err, nullptr);
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
   return LWSE_OK;
@@ -293,7 +316,7 @@ LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* h) {
   d.node_occupancy = want_occ ? (uint32_t*)e->occupancy.p : nullptr;
   int cuda_err = 0;
   int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes,
-                                        e->scan_scratch.p, e->sm_count, s, &cuda_err);
+                                        e->scan_scratch.p, e->sm_count, s, &cuda_err, nullptr);
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
 
@@ -301,6 +324,153 @@ LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* h) {
   if (b_go) LWSE_CUDA(e, cudaMemcpyAsync(h->group_out, e->group_out.p, b_go, cudaMemcpyDeviceToHost, s));
   if (want_occ)
     LWSE_CUDA(e, cudaMemcpyAsync(h->node_occupancy, e->occupancy.p, (size_t)e->n_nodes * 4,
+                                 cudaMemcpyDeviceToHost, s));
+  LWSE_CUDA(e, cudaStreamSynchronize(s));
+  return LWSE_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Resident tables
+// ---------------------------------------------------------------------------
+LWSE_API int lwse_resident_load(lwse_engine* e, const lwse_lws_tables* h) {
+  if (!e || !h) return LWSE_ERR_INVALID_ARG;
+  if ((h->n_lws && !h->lws) || (h->n_groups && !h->groups) || (h->n_pods && (!h->pod_state || !h->pod_ident)))
+    return LWSE_ERR_INVALID_ARG;
+  if (h->n_pods > 0xFFFFFFFFull) return LWSE_ERR_UNSUPPORTED;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  cudaStream_t s = e->stream;
+  const size_t b_lws = (size_t)h->n_lws * sizeof(lwse_lws_rec), b_grp = (size_t)h->n_groups * sizeof(lwse_group_rec);
+  const size_t b_pst = (size_t)h->n_pods * sizeof(lwse_pod_state), b_pid = (size_t)h->n_pods * sizeof(lwse_pod_ident);
+  const size_t b_lo = (size_t)h->n_lws * sizeof(lwse_lws_out), b_go = (size_t)h->n_groups * sizeof(lwse_group_out);
+  LWSE_CUDA(e, e->r_lws.reserve(b_lws + 16));
+  LWSE_CUDA(e, e->r_groups.reserve(b_grp + 16));
+  LWSE_CUDA(e, e->r_pst.reserve(b_pst + 16));
+  LWSE_CUDA(e, e->r_pid.reserve(b_pid + 16));
+  LWSE_CUDA(e, e->r_lws_out.reserve(b_lo + 16));
+  LWSE_CUDA(e, e->r_group_out.reserve(b_go + 16));
+  LWSE_CUDA(e, e->r_scan.reserve(lwse::lws_sweep_scratch_bytes(h->n_pods)));
+  LWSE_CUDA(e, e->r_counts.reserve(64));
+  if (b_lws) LWSE_CUDA(e, cudaMemcpyAsync(e->r_lws.p, h->lws, b_lws, cudaMemcpyHostToDevice, s));
+  if (b_grp) LWSE_CUDA(e, cudaMemcpyAsync(e->r_groups.p, h->groups, b_grp, cudaMemcpyHostToDevice, s));
+  if (b_pst) LWSE_CUDA(e, cudaMemcpyAsync(e->r_pst.p, h->pod_state, b_pst, cudaMemcpyHostToDevice, s));
+  if (b_pid) LWSE_CUDA(e, cudaMemcpyAsync(e->r_pid.p, h->pod_ident, b_pid, cudaMemcpyHostToDevice, s));
+  // forget previous results: an all-ones row never equals a real result, so the first sweep reports every row
+  if (b_lo) LWSE_CUDA(e, cudaMemsetAsync(e->r_lws_out.p, 0xFF, b_lo, s));
+  if (b_go) LWSE_CUDA(e, cudaMemsetAsync(e->r_group_out.p, 0xFF, b_go, s));
+  LWSE_CUDA(e, cudaStreamSynchronize(s));
+  e->rn_lws = h->n_lws;
+  e->rn_groups = h->n_groups;
+  e->rn_pods = h->n_pods;
+  e->r_loaded = true;
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_resident_patch(lwse_engine* e, lwse_table which, const uint32_t* rows, const void* values,
+                                 uint32_t n) {
+  if (!e || (n && (!rows || !values))) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->r_loaded) return LWSE_ERR_NOT_READY;
+  if (n == 0) return LWSE_OK;
+  DeviceGuard guard(e->device);
+  cudaStream_t s = e->stream;
+  void* table = nullptr;
+  uint64_t table_rows = 0;
+  int words = 0;
+  switch (which) {
+    case LWSE_TABLE_LWS: table = e->r_lws.p; table_rows = e->rn_lws; words = 16; break;
+    case LWSE_TABLE_GROUPS: table = e->r_groups.p; table_rows = e->rn_groups; words = 16; break;
+    case LWSE_TABLE_POD_STATE: table = e->r_pst.p; table_rows = e->rn_pods; words = 1; break;
+    case LWSE_TABLE_POD_IDENT: table = e->r_pid.p; table_rows = e->rn_pods; words = 3; break;
+    default: return LWSE_ERR_INVALID_ARG;
+  }
+  const size_t b_rows = (size_t)n * 4, b_vals = (size_t)n * words * 4;
+  LWSE_CUDA(e, e->r_patch_rows.reserve(b_rows + 16));
+  LWSE_CUDA(e, e->r_patch_vals.reserve(b_vals + 16));
+  LWSE_CUDA(e, cudaMemcpyAsync(e->r_patch_rows.p, rows, b_rows, cudaMemcpyHostToDevice, s));
+  LWSE_CUDA(e, cudaMemcpyAsync(e->r_patch_vals.p, values, b_vals, cudaMemcpyHostToDevice, s));
+  int cuda_err = 0;
+  int launched = lwse::launch_scatter(words, table, table_rows, (const uint32_t*)e->r_patch_rows.p,
+                                      e->r_patch_vals.p, n, s, &cuda_err);
+  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+  e->launches += (uint64_t)launched;
+  // the staging buffers are reused by the next patch: order it behind this one (same stream) — but the
+  // host buffers belong to the caller again only after the copies ran
+  LWSE_CUDA(e, cudaStreamSynchronize(s));
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_resident_sweep(lwse_engine* e, uint32_t flags, lwse_changes* ch) {
+  if (!e) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->r_loaded) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  cudaStream_t s = e->stream;
+  lwse_lws_tables d{};
+  d.lws = (const lwse_lws_rec*)e->r_lws.p;
+  d.n_lws = e->rn_lws;
+  d.groups = (const lwse_group_rec*)e->r_groups.p;
+  d.n_groups = e->rn_groups;
+  d.pod_state = (const lwse_pod_state*)e->r_pst.p;
+  d.pod_ident = (const lwse_pod_ident*)e->r_pid.p;
+  d.n_pods = e->rn_pods;
+  d.lws_out = (lwse_lws_out*)e->r_lws_out.p;
+  d.group_out = (lwse_group_out*)e->r_group_out.p;
+  d.flags = flags & LWSE_SWEEP_GANG;
+  lwse::SweepChangeLists cl;
+  if (ch) {
+    if ((ch->lws_capacity && (!ch->lws_rows || !ch->lws_out)) || (ch->group_capacity && (!ch->group_rows || !ch->group_out)))
+      return LWSE_ERR_INVALID_ARG;
+    LWSE_CUDA(e, e->r_chg_lws_rows.reserve((size_t)ch->lws_capacity * 4 + 16));
+    LWSE_CUDA(e, e->r_chg_lws_out.reserve((size_t)ch->lws_capacity * sizeof(lwse_lws_out) + 16));
+    LWSE_CUDA(e, e->r_chg_grp_rows.reserve((size_t)ch->group_capacity * 4 + 16));
+    LWSE_CUDA(e, e->r_chg_grp_out.reserve((size_t)ch->group_capacity * sizeof(lwse_group_out) + 16));
+    LWSE_CUDA(e, cudaMemsetAsync(e->r_counts.p, 0, 8, s));
+    cl.lws_rows = (uint32_t*)e->r_chg_lws_rows.p;
+    cl.lws_out = (lwse_lws_out*)e->r_chg_lws_out.p;
+    cl.lws_capacity = ch->lws_capacity;
+    cl.group_rows = (uint32_t*)e->r_chg_grp_rows.p;
+    cl.group_out = (lwse_group_out*)e->r_chg_grp_out.p;
+    cl.group_capacity = ch->group_capacity;
+    cl.counts = (uint32_t*)e->r_counts.p;
+  }
+  int cuda_err = 0;
+  int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes, e->r_scan.p, e->sm_count,
+                                        s, &cuda_err, ch ? &cl : nullptr);
+  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+  e->launches += (uint64_t)launched;
+  if (!ch) {
+    LWSE_CUDA(e, cudaStreamSynchronize(s));
+    return LWSE_OK;
+  }
+  LWSE_CUDA(e, cudaMemcpyAsync(e->h_counts, e->r_counts.p, 8, cudaMemcpyDeviceToHost, s));
+  LWSE_CUDA(e, cudaStreamSynchronize(s));
+  ch->n_lws = e->h_counts[0];
+  ch->n_groups = e->h_counts[1];
+  const uint32_t nl = ch->n_lws < ch->lws_capacity ? ch->n_lws : ch->lws_capacity;
+  const uint32_t ng = ch->n_groups < ch->group_capacity ? ch->n_groups : ch->group_capacity;
+  if (nl) {
+    LWSE_CUDA(e, cudaMemcpyAsync(ch->lws_rows, e->r_chg_lws_rows.p, (size_t)nl * 4, cudaMemcpyDeviceToHost, s));
+    LWSE_CUDA(e, cudaMemcpyAsync(ch->lws_out, e->r_chg_lws_out.p, (size_t)nl * sizeof(lwse_lws_out), cudaMemcpyDeviceToHost, s));
+  }
+  if (ng) {
+    LWSE_CUDA(e, cudaMemcpyAsync(ch->group_rows, e->r_chg_grp_rows.p, (size_t)ng * 4, cudaMemcpyDeviceToHost, s));
+    LWSE_CUDA(e, cudaMemcpyAsync(ch->group_out, e->r_chg_grp_out.p, (size_t)ng * sizeof(lwse_group_out), cudaMemcpyDeviceToHost, s));
+  }
+  if (nl || ng) LWSE_CUDA(e, cudaStreamSynchronize(s));
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_resident_outputs(lwse_engine* e, lwse_lws_out* lws_out, lwse_group_out* group_out) {
+  if (!e) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->r_loaded) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  cudaStream_t s = e->stream;
+  if (lws_out && e->rn_lws)
+    LWSE_CUDA(e, cudaMemcpyAsync(lws_out, e->r_lws_out.p, (size_t)e->rn_lws * sizeof(lwse_lws_out), cudaMemcpyDeviceToHost, s));
+  if (group_out && e->rn_groups)
+    LWSE_CUDA(e, cudaMemcpyAsync(group_out, e->r_group_out.p, (size_t)e->rn_groups * sizeof(lwse_group_out),
                                  cudaMemcpyDeviceToHost, s));
   LWSE_CUDA(e, cudaStreamSynchronize(s));
   return LWSE_OK;

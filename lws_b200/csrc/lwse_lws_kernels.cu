@@ -120,6 +120,36 @@ __global__ void __launch_bounds__(256) pod_scan_kernel(const PodScanArgs a) {
 // --------------------------------------------------------------------------
 // group pass
 // --------------------------------------------------------------------------
+// Optional change list: result rows that differ from what the output table held before.
+struct ChangeList {
+  uint32_t* rows;   // nullptr = off
+  void* outs;       // packed result rows
+  uint32_t* count;  // device counter
+  uint32_t capacity;
+};
+
+template <int N>  // N = uint4 per result row
+__device__ __forceinline__ void emit_if_changed(const ChangeList& c, uint4* slot, uint32_t row, const uint4 (&v)[N]) {
+  if (c.rows != nullptr) {
+    bool diff = false;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const uint4 old = slot[k];
+      diff |= old.x != v[k].x || old.y != v[k].y || old.z != v[k].z || old.w != v[k].w;
+    }
+    if (diff) {
+      const uint32_t i = atomicAdd(c.count, 1u);
+      if (i < c.capacity) {
+        c.rows[i] = row;
+#pragma unroll
+        for (int k = 0; k < N; k++) reinterpret_cast<uint4*>(c.outs)[(size_t)i * N + k] = v[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < N; k++) stg_stream(slot + k, v[k]);
+}
+
 struct GroupSweepArgs {
   const lwse_lws_rec* lws;
   const lwse_group_rec* groups;
@@ -134,6 +164,7 @@ struct GroupSweepArgs {
   uint32_t n_groups;
   uint32_t n_nodes;
   uint32_t sweep_flags;
+  ChangeList changes;
 };
 
 // bits [lo, hi) of a 32-bit word, 0 <= lo <= hi <= 32
@@ -332,7 +363,10 @@ __global__ void __launch_bounds__(256) group_sweep_kernel(const GroupSweepArgs a
         worker_replicas = size - 1;  // :437; ordinals start at 1 (:440)
       }
     }
-    if (lane == 0) stg_stream(a.out + g, make_uint4(oflags, first_out, (uint32_t)worker_replicas, domain));
+    if (lane == 0) {
+      const uint4 v[1] = {make_uint4(oflags, first_out, (uint32_t)worker_replicas, domain)};
+      emit_if_changed<1>(a.changes, reinterpret_cast<uint4*>(a.out + g), g, v);
+    }
   }
 }
 
@@ -346,6 +380,7 @@ struct LwsSweepArgs {
   uint32_t n_lws;
   uint32_t n_groups;
   uint32_t sweep_flags;
+  ChangeList changes;
 };
 
 __device__ __forceinline__ int32_t want_replicas(int32_t lws_replicas, int32_t surge, int32_t mu,
@@ -531,11 +566,9 @@ __global__ void __launch_bounds__(256) lws_sweep_kernel(const LwsSweepArgs a) {
       if (lflags & LWSE_LWS_IRREGULAR) oflags |= LWSE_LOUT_IRREGULAR;
     }
     if (lane == 0) {
-      uint4* o = reinterpret_cast<uint4*>(a.out + i);
-      stg_stream(o + 0, make_uint4((uint32_t)o_partition, (uint32_t)o_replicas, (uint32_t)o_mu,
-                                   (uint32_t)o_ready));
-      stg_stream(o + 1, make_uint4((uint32_t)o_updated, (uint32_t)o_min_member, oflags,
-                                   (uint32_t)o_unready));
+      const uint4 v[2] = {make_uint4((uint32_t)o_partition, (uint32_t)o_replicas, (uint32_t)o_mu, (uint32_t)o_ready),
+                          make_uint4((uint32_t)o_updated, (uint32_t)o_min_member, oflags, (uint32_t)o_unready)};
+      emit_if_changed<2>(a.changes, reinterpret_cast<uint4*>(a.out + i), i, v);
     }
   }
 }
@@ -596,8 +629,18 @@ size_t lws_sweep_scratch_bytes(uint64_t n_pods) {
 
 // Returns the number of kernels launched (>=0) or -1 with *cuda_err set.
 // scratch: lws_sweep_scratch_bytes(n_pods) bytes of device memory.
+struct SweepChangeLists {  // device pointers; all null = off
+  uint32_t* lws_rows = nullptr;
+  lwse_lws_out* lws_out = nullptr;
+  uint32_t lws_capacity = 0;
+  uint32_t* group_rows = nullptr;
+  lwse_group_out* group_out = nullptr;
+  uint32_t group_capacity = 0;
+  uint32_t* counts = nullptr;  // [0] lws, [1] groups; zeroed by the caller
+};
+
 int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
-                     void* scratch, int sm_count, cudaStream_t s, int* cuda_err) {
+                     void* scratch, int sm_count, cudaStream_t s, int* cuda_err, const SweepChangeLists* cl) {
   *cuda_err = 0;
   int launches = 0;
   cudaError_t e = cudaSuccess;
@@ -626,7 +669,8 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
   }
   if (group_pass) {
     GroupSweepArgs a{t->lws,   t->groups, t->pod_state, t->pod_ident, pending_bits, event_bits, d_nodes,
-                     t->group_out, t->n_pods, t->n_lws, t->n_groups, n_nodes, t->flags};
+                     t->group_out, t->n_pods, t->n_lws, t->n_groups, n_nodes, t->flags, ChangeList{}};
+    if (cl && cl->group_rows) a.changes = ChangeList{cl->group_rows, cl->group_out, cl->counts + 1, cl->group_capacity};
     // lanes per group: one per bitmap word of an average group, in {1, 2, 4, 8}
     const uint64_t avg_pods = (t->n_pods + t->n_groups - 1) / t->n_groups;
     const int w = avg_pods > 2048 ? 8 : avg_pods > 1024 ? 4 : avg_pods > 512 ? 2 : 1;
@@ -640,7 +684,8 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
     launches++;
   }
   if (t->n_lws && !(t->flags & LWSE_SWEEP_SKIP_LWS_PASS)) {
-    LwsSweepArgs a{t->lws, t->group_out, t->lws_out, t->n_lws, t->n_groups, t->flags};
+    LwsSweepArgs a{t->lws, t->group_out, t->lws_out, t->n_lws, t->n_groups, t->flags, ChangeList{}};
+    if (cl && cl->lws_rows) a.changes = ChangeList{cl->lws_rows, cl->lws_out, cl->counts + 0, cl->lws_capacity};
     switch (pick_tile(t->n_groups, t->n_lws)) {
       case 1: e = launch_lws<1>(a, sm_count, s); break;
       case 2: e = launch_lws<2>(a, sm_count, s); break;
@@ -653,6 +698,42 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
     launches++;
   }
   return launches;
+}
+
+// --------------------------------------------------------------------------
+// row patches for the resident tables
+// --------------------------------------------------------------------------
+template <int WORDS>  // 32-bit words per row
+__global__ void __launch_bounds__(256) scatter_rows_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ rows,
+                                                           const uint32_t* __restrict__ values, uint32_t n,
+                                                           uint64_t table_rows) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (uint64_t)n * WORDS) return;
+  const uint32_t k = (uint32_t)(i / WORDS), w = (uint32_t)(i % WORDS);
+  const uint32_t r = __ldg(rows + k);
+  if (r < table_rows) table[(uint64_t)r * WORDS + w] = __ldg(values + i);
+}
+
+int launch_scatter(int row_words, void* table, uint64_t table_rows, const uint32_t* rows, const void* values,
+                   uint32_t n, cudaStream_t s, int* cuda_err) {
+  *cuda_err = 0;
+  if (n == 0) return 0;
+  const uint64_t threads = (uint64_t)n * (uint64_t)row_words;
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  uint32_t* tb = static_cast<uint32_t*>(table);
+  const uint32_t* v = static_cast<const uint32_t*>(values);
+  switch (row_words) {
+    case 16: scatter_rows_kernel<16><<<grid, 256, 0, s>>>(tb, rows, v, n, table_rows); break;
+    case 3: scatter_rows_kernel<3><<<grid, 256, 0, s>>>(tb, rows, v, n, table_rows); break;
+    case 1: scatter_rows_kernel<1><<<grid, 256, 0, s>>>(tb, rows, v, n, table_rows); break;
+    default: *cuda_err = (int)cudaErrorInvalidValue; return -1;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    *cuda_err = (int)e;
+    return -1;
+  }
+  return 1;
 }
 
 }  // namespace lwse

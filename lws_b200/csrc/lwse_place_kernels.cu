@@ -140,6 +140,38 @@ __device__ __forceinline__ void stamp(const PlaceArgs& a, uint32_t k) {
 constexpr uint32_t kUnusable = 0xFFFFFFFFu;
 // node word: min(free,15) << 28 | domain (28 bits); the exact free count only feeds dom_free
 
+// A CTA's view of one of its unpinned requests, kept in shared memory across the rounds
+// (write-through: choice / state are mirrored in global memory for the CTAs' requests that
+// do not fit in the cache).
+struct ReqCache {
+  unsigned long long key;
+  uint32_t r, ns, size, key_lo, key_hi, cur, dead, pad;
+};
+constexpr uint32_t kCacheQ = 64;  // requests per CTA held in shared memory
+constexpr uint32_t kSmemHeader = 256 + kCacheQ * sizeof(ReqCache);
+
+__device__ __forceinline__ lwse_place_out pinned_result(const PlaceArgs& a, const lwse_place_req& rq, uint32_t r) {
+  lwse_place_out o;
+  o.domain_id = LWSE_NONE;
+  o.leader_node = rq.leader_node;
+  o.flags = LWSE_PLACE_PINNED;
+  o.score = 0;
+  if (rq.ns >= a.n_namespaces) {
+    o.flags |= LWSE_PLACE_UNSCHEDULABLE;
+  } else if (rq.leader_node < a.n_nodes) {
+    const uint4 nr = __ldg(reinterpret_cast<const uint4*>(a.nodes + rq.leader_node));
+    const uint32_t d = nr.z;
+    if (((nr.w >> 16) & LWSE_NODE_HAS_TOPOLOGY) && d < a.n_domains) {
+      o.domain_id = d;
+      // pinned keys (bit 63 clear) are below every unpinned key: once all pinned claims are in,
+      // the holder of a pinned domain never changes again
+      const unsigned long long h = __ldcg(a.holder + (uint64_t)rq.ns * a.n_domains + d);
+      o.flags |= h == place_key(rq, r, true) ? LWSE_PLACE_PLACED : LWSE_PLACE_CONFLICT;
+    }
+  }
+  return o;
+}
+
 __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(128) uint8_t smem[];
@@ -147,7 +179,8 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
   unsigned long long* s_best = reinterpret_cast<unsigned long long*>(smem + 16);  // 16 warps
   uint32_t* s_best_n = reinterpret_cast<uint32_t*>(smem + 16 + 16 * 8);
   uint32_t* s_flag = reinterpret_cast<uint32_t*>(smem + 16 + 16 * 8 + 16 * 4);
-  uint32_t* s_words = reinterpret_cast<uint32_t*>(smem + 256);
+  ReqCache* s_req = reinterpret_cast<ReqCache*>(smem + 256);
+  uint32_t* s_words = reinterpret_cast<uint32_t*>(smem + kSmemHeader);
   const uint32_t n_pad = (a.n_nodes + 31u) & ~31u;
   const uint32_t nd4 = (a.n_domains + 3u) & ~3u;
   uint32_t* s_hi = s_words + n_pad + nd4;  // per-domain score of the current request, 0 = may not claim
@@ -180,9 +213,9 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
   }
   for (uint32_t r = gtid; r < a.n_reqs; r += gsize) {
     const lwse_place_req rq = load_req(a, r);
-    a.choice[r] = LWSE_NONE;
-    a.state[r] = 0;
     if (rq.leader_node == LWSE_NONE) {
+      a.choice[r] = LWSE_NONE;
+      a.state[r] = 0;
       a.unpinned[atomicAdd(a.counters + 4, 1u)] = r;  // order is irrelevant: the fixed point is unique
     } else if (rq.ns < a.n_namespaces && rq.leader_node < a.n_nodes) {
       const uint4 nr = __ldg(reinterpret_cast<const uint4*>(a.nodes + rq.leader_node));
@@ -203,21 +236,47 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
   const uint32_t n_unpinned = __ldcg(a.counters + 4);
   uint32_t* compact = a.g_compact;
   uint32_t* dom_free = a.g_dom_free;
+  if (n_unpinned && a.smem_nodes && tid == 0) {
+    // TMA-stage the condensed node table and the domain capacities into shared memory (every
+    // (request, node) pair below is scored from on-chip memory); the copy flies while the pinned
+    // results are written and the request cache is filled
+    const uint32_t bytes_w = n_pad * 4u, bytes_d = nd4 * 4u;
+    mbar_expect_tx(bar, bytes_w + bytes_d);
+    tma_bulk_g2s(s_words, a.g_compact, bytes_w, bar);
+    tma_bulk_g2s(s_words + n_pad, a.g_dom_free, bytes_d, bar);
+  }
+  // results of the pinned requests: final as of now
+  for (uint32_t r = gtid; r < a.n_reqs; r += gsize) {
+    const lwse_place_req rq = load_req(a, r);
+    if (rq.leader_node != LWSE_NONE) a.out[r] = pinned_result(a, rq, r);
+  }
+
   uint32_t round = 0;
   if (n_unpinned) {
+    // this CTA's requests: k = blockIdx.x, blockIdx.x + gridDim.x, …; the first kCacheQ live in shared memory
+    const uint32_t my_count = blockIdx.x < n_unpinned ? (n_unpinned - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
+    if (tid < min(my_count, kCacheQ)) {
+      const uint32_t r = __ldcg(a.unpinned + blockIdx.x + tid * gridDim.x);
+      const lwse_place_req rq = load_req(a, r);
+      ReqCache q;
+      q.key = place_key(rq, r, false);
+      q.r = r;
+      q.ns = rq.ns;
+      q.size = (uint32_t)rq.size;
+      q.key_lo = (uint32_t)rq.group_key;
+      q.key_hi = (uint32_t)(rq.group_key >> 32);
+      q.cur = LWSE_NONE;
+      q.dead = (rq.ns >= a.n_namespaces || rq.size < 1) ? 1u : 0u;
+      q.pad = 0;
+      if (q.dead) a.state[r] = 1;
+      s_req[tid] = q;
+    }
     if (a.smem_nodes) {
-      // TMA-stage the condensed node table and the domain capacities into shared memory:
-      // every (request, node) pair below is scored from on-chip memory.
-      const uint32_t bytes_w = n_pad * 4u, bytes_d = ((a.n_domains + 3u) & ~3u) * 4u;
-      if (tid == 0) {
-        mbar_expect_tx(bar, bytes_w + bytes_d);
-        tma_bulk_g2s(s_words, a.g_compact, bytes_w, bar);
-        tma_bulk_g2s(s_words + n_pad, a.g_dom_free, bytes_d, bar);
-      }
       mbar_wait(bar, 0);
       compact = s_words;
       dom_free = s_words + n_pad;
     }
+    __syncthreads();
     stamp(a, 3);
 
     // ---------------- phase 2: deferred-acceptance rounds, one CTA per request ----------------
@@ -226,20 +285,27 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
       // when no CTA can still be reading it (it was last read after round k-2)
       uint32_t* counter = a.counters + (round % 3u);
       if (blockIdx.x == 0 && tid == 0) a.counters[(round + 1u) % 3u] = 0;
-      for (uint32_t k = blockIdx.x; k < n_unpinned; k += gridDim.x) {
-        const uint32_t r = __ldcg(a.unpinned + k);
-        const lwse_place_req rq = load_req(a, r);
-        // state / choice are written by this CTA only → every thread reads the same value
-        const uint32_t st = __ldcg(a.state + r), cur = __ldcg(a.choice + r);
-        const unsigned long long key = place_key(rq, r, false);
-        unsigned long long* hold = a.holder + (uint64_t)rq.ns * a.n_domains;
-        if (rq.ns >= a.n_namespaces || rq.size < 1) {
-          if (tid == 0) a.state[r] = 1;
-          continue;
+      for (uint32_t j = 0; j < my_count; j++) {
+        ReqCache q;
+        if (j < kCacheQ) {
+          q = s_req[j];
+        } else {  // overflow: the request lives in global memory (state / choice are written by this CTA only)
+          const uint32_t r = __ldcg(a.unpinned + blockIdx.x + j * gridDim.x);
+          const lwse_place_req rq = load_req(a, r);
+          q.key = place_key(rq, r, false);
+          q.r = r;
+          q.ns = rq.ns;
+          q.size = (uint32_t)rq.size;
+          q.key_lo = (uint32_t)rq.group_key;
+          q.key_hi = (uint32_t)(rq.group_key >> 32);
+          q.cur = __ldcg(a.choice + r);
+          q.dead = (rq.ns >= a.n_namespaces || rq.size < 1) ? 1u : __ldcg(a.state + r);
+          if (q.dead && tid == 0) a.state[r] = 1;
         }
-        if (st) continue;
-        const uint32_t key_lo = (uint32_t)rq.group_key, key_hi = (uint32_t)(rq.group_key >> 32);
-        const uint32_t size = (uint32_t)rq.size;
+        if (q.dead) continue;  // uniform
+        const unsigned long long key = q.key;
+        unsigned long long* hold = a.holder + (uint64_t)q.ns * a.n_domains;
+        const uint32_t size = q.size;
         unsigned long long best = 0;
         uint32_t best_n = LWSE_NONE;
         if (a.smem_nodes) {
@@ -249,14 +315,14 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
           // still holds the domain it proposed to earlier (then nothing is left to do).  Holders
           // change under our feet during a round (other CTAs' atomicMin), so every decision the
           // CTA branches on is reduced through shared memory — threads never branch on their own
-          // reading of a holder.  (Per-node holder loads cost 8.8 us per request and per-node
-          // hashing 5 us; a serial chain of decision loads 2 us — all measured with %globaltimer.)
-          const uint32_t cur_dom = cur != LWSE_NONE ? (compact[cur] & 0x0FFFFFFFu) : LWSE_NONE;
+          // reading of a holder.  (Per-node holder loads cost 8.8 us per request, per-node
+          // hashing 5 us, a serial chain of request/state loads 2 us — measured with %globaltimer.)
+          const uint32_t cur_dom = q.cur != LWSE_NONE ? (compact[q.cur] & 0x0FFFFFFFu) : LWSE_NONE;
           uint32_t my_hi = 0, my_holding = 0;
           for (uint32_t d = tid; d < a.n_domains; d += kPlaceThreads) {
             const unsigned long long h = __ldcg(hold + d);
             uint32_t hi = 0;
-            if (dom_free[d] >= size && h >= key) hi = mix32(key_lo ^ (d * 0x9E3779B1u)) | 1u;
+            if (dom_free[d] >= size && h >= key) hi = mix32(q.key_lo ^ (d * 0x9E3779B1u)) | 1u;
             if (d == cur_dom && h == key) my_holding = 1u;
             s_hi[d] = hi;  // 0 = this request may not claim d
             my_hi = max(my_hi, hi);
@@ -284,7 +350,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
               const uint32_t w = compact[n];
               if (w == kUnusable || (w >> 28) == 0u) continue;
               if (s_hi[w & 0x0FFFFFFFu] != H) continue;
-              const uint32_t lo = ((w >> 28) << 28) | (mix32(key_hi ^ (n * 0x85EBCA77u)) >> 4);
+              const uint32_t lo = ((w >> 28) << 28) | (mix32(q.key_hi ^ (n * 0x85EBCA77u)) >> 4);
               const unsigned long long sc = ((unsigned long long)H << 32) | lo;
               if (best_n == LWSE_NONE || sc > best) {  // n ascends per thread: ties keep the lower index
                 best = sc;
@@ -296,7 +362,8 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
           // node words in global memory (table too large for shared memory): one thread decides
           // whether the request still holds its domain and broadcasts, then one fused pass
           __syncthreads();
-          if (tid == 0) *s_flag = (cur != LWSE_NONE && __ldcg(hold + (compact[cur] & 0x0FFFFFFFu)) == key) ? 0u : 1u;
+          if (tid == 0)
+            *s_flag = (q.cur != LWSE_NONE && __ldcg(hold + (compact[q.cur] & 0x0FFFFFFFu)) == key) ? 0u : 1u;
           __syncthreads();
           if (!*s_flag) continue;
           for (uint32_t n = tid; n < a.n_nodes; n += kPlaceThreads) {
@@ -305,8 +372,8 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
             const uint32_t d = w & 0x0FFFFFFFu;
             if (dom_free[d] < size) continue;
             if (__ldcg(hold + d) < key) continue;  // held by a higher-priority group (monotone: never frees)
-            const uint32_t hi = mix32(key_lo ^ (d * 0x9E3779B1u)) | 1u;
-            const uint32_t lo = ((w >> 28) << 28) | (mix32(key_hi ^ (n * 0x85EBCA77u)) >> 4);
+            const uint32_t hi = mix32(q.key_lo ^ (d * 0x9E3779B1u)) | 1u;
+            const uint32_t lo = ((w >> 28) << 28) | (mix32(q.key_hi ^ (n * 0x85EBCA77u)) >> 4);
             const unsigned long long sc = ((unsigned long long)hi << 32) | lo;
             if (best_n == LWSE_NONE || sc > best) {
               best = sc;
@@ -345,18 +412,23 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
           }
           if (lane == 0) {
             if (best_n == LWSE_NONE) {
-              a.state[r] = 1;  // nothing feasible now, and the feasible set only shrinks
-              a.choice[r] = LWSE_NONE;
+              a.state[q.r] = 1;  // nothing feasible now, and the feasible set only shrinks
+              a.choice[q.r] = LWSE_NONE;
+              if (j < kCacheQ) {
+                s_req[j].dead = 1;
+                s_req[j].cur = LWSE_NONE;
+              }
             } else {
               const uint32_t d = compact[best_n] & 0x0FFFFFFFu;
               atomicMin(hold + d, key);
-              a.choice[r] = best_n;
-              a.out[r].score = (uint32_t)(best >> 32);
+              a.choice[q.r] = best_n;
+              if (j < kCacheQ) s_req[j].cur = best_n;
+              a.out[q.r].score = (uint32_t)(best >> 32);
               atomicAdd(counter, 1u);
             }
           }
         }
-        __syncthreads();  // s_best is reused by the CTA's next request
+        __syncthreads();  // s_best and the cache entry are settled before the next request
       }
       stamp(a, 4 + 2 * round);
       __threadfence();
@@ -365,44 +437,35 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
       const uint32_t proposals = __ldcg(counter);
       if (proposals == 0u || round > a.n_reqs + 2u) break;
     }
-  }
-  if (blockIdx.x == 0 && tid == 0) a.counters[3] = n_unpinned ? round + 1u : 0u;
 
-  // ---------------- results ----------------
-  for (uint32_t r = gtid; r < a.n_reqs; r += gsize) {
-    const lwse_place_req rq = load_req(a, r);
-    lwse_place_out o;
-    o.domain_id = LWSE_NONE;
-    o.leader_node = LWSE_NONE;
-    o.flags = 0;
-    o.score = 0;
-    if (rq.leader_node != LWSE_NONE) {
-      o.flags = LWSE_PLACE_PINNED;
-      o.leader_node = rq.leader_node;
-      if (rq.ns >= a.n_namespaces) {
-        o.flags |= LWSE_PLACE_UNSCHEDULABLE;
-      } else if (rq.leader_node < a.n_nodes) {
-        const uint4 nr = __ldg(reinterpret_cast<const uint4*>(a.nodes + rq.leader_node));
-        const uint32_t d = nr.z;
-        if (((nr.w >> 16) & LWSE_NODE_HAS_TOPOLOGY) && d < a.n_domains) {
-          o.domain_id = d;
-          const unsigned long long h = __ldcg(a.holder + (uint64_t)rq.ns * a.n_domains + d);
-          o.flags |= h == place_key(rq, r, true) ? LWSE_PLACE_PLACED : LWSE_PLACE_CONFLICT;
-        }
-      }
-    } else {
-      const uint32_t cur = __ldcg(a.choice + r);
-      if (__ldcg(a.state + r) || cur == LWSE_NONE) {
-        o.flags = LWSE_PLACE_UNSCHEDULABLE;
+    // results of this CTA's unpinned requests (fixed point: every live request holds its choice)
+    for (uint32_t j = tid; j < my_count; j += kPlaceThreads) {
+      uint32_t r, cur, dead;
+      if (j < kCacheQ) {
+        r = s_req[j].r;
+        cur = s_req[j].cur;
+        dead = s_req[j].dead;
       } else {
-        o.domain_id = __ldcg(a.g_compact + cur) & 0x0FFFFFFFu;
+        r = __ldcg(a.unpinned + blockIdx.x + j * gridDim.x);
+        cur = __ldcg(a.choice + r);
+        dead = __ldcg(a.state + r);
+      }
+      lwse_place_out o;
+      if (dead || cur == LWSE_NONE) {
+        o.domain_id = LWSE_NONE;
+        o.leader_node = LWSE_NONE;
+        o.flags = LWSE_PLACE_UNSCHEDULABLE;
+        o.score = 0;
+      } else {
+        o.domain_id = compact[cur] & 0x0FFFFFFFu;
         o.leader_node = cur;
         o.flags = LWSE_PLACE_PLACED;
         o.score = a.out[r].score;
       }
+      a.out[r] = o;
     }
-    a.out[r] = o;
   }
+  if (blockIdx.x == 0 && tid == 0) a.counters[3] = n_unpinned ? round + 1u : 0u;
   stamp(a, 15);
 }
 
@@ -479,9 +542,9 @@ int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_doma
   a.part_stride_bytes = part_stride_bytes;
 
   const size_t words_bytes = ((size_t)((n_nodes + 31u) & ~31u) + 2 * (size_t)((n_domains + 3u) & ~3u)) * 4 + 16;
-  size_t smem = 256 + words_bytes;
+  size_t smem = kSmemHeader + words_bytes;
   a.smem_nodes = smem <= 227u * 1024u ? 1u : 0u;
-  if (!a.smem_nodes) smem = 256;
+  if (!a.smem_nodes) smem = kSmemHeader;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     e = cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

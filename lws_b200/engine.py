@@ -30,6 +30,10 @@ SYMBOLS = {
     "lwse_upload_nodes": ([C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32], C.c_int),
     "lwse_sweep_lws_host": ([C.c_void_p, C.POINTER(R.LwsTables)], C.c_int),
     "lwse_sweep_lws_device": ([C.c_void_p, C.POINTER(R.LwsTables), C.c_void_p], C.c_int),
+    "lwse_resident_load": ([C.c_void_p, C.POINTER(R.LwsTables)], C.c_int),
+    "lwse_resident_patch": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32], C.c_int),
+    "lwse_resident_sweep": ([C.c_void_p, C.c_uint32, C.POINTER(R.Changes)], C.c_int),
+    "lwse_resident_outputs": ([C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
     "lwse_place_host": (
         [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)],
         C.c_int,
@@ -154,6 +158,47 @@ class Engine:
             R.ptr(d_lws_out), R.ptr(d_group_out), R.ptr(d_occupancy), flags,
         )
         self._check(lib().lwse_sweep_lws_device(self._h, C.byref(t), stream))
+
+    # ------------------------------------------------------- resident tables
+    def resident_load(self, lws, groups, pod_state, pod_ident):
+        """Make the four input tables resident on the device."""
+        self._resident_shape = (len(lws), len(groups))
+        t = R.LwsTables(R.ptr(lws), len(lws), R.ptr(groups), len(groups), R.ptr(pod_state), R.ptr(pod_ident),
+                        len(pod_state), None, None, None, 0)
+        self._check(lib().lwse_resident_load(self._h, C.byref(t)))
+        self._chg = None
+
+    _DT = {R.TABLE_LWS: R.LWS_REC, R.TABLE_GROUPS: R.GROUP_REC, R.TABLE_POD_STATE: R.POD_STATE,
+           R.TABLE_POD_IDENT: R.POD_IDENT}
+
+    def resident_patch(self, which: int, rows, values):
+        """Overwrite rows of a resident table (rows: uint32 indices, values: packed rows)."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        values = np.ascontiguousarray(values, dtype=self._DT[which])
+        assert len(rows) == len(values)
+        self._check(lib().lwse_resident_patch(self._h, which, R.ptr(rows) if len(rows) else None,
+                                              R.ptr(values) if len(rows) else None, len(rows)))
+
+    def resident_sweep(self, flags=0, lws_capacity=None, group_capacity=None):
+        """Sweep the resident tables → (lws_rows, lws_out, group_rows, group_out, n_lws_changed,
+        n_groups_changed): only result rows that changed since the previous resident sweep."""
+        n_lws, n_grp = self._resident_shape
+        lc = n_lws if lws_capacity is None else lws_capacity
+        gc = n_grp if group_capacity is None else group_capacity
+        if self._chg is None or self._chg[0] != (lc, gc):
+            self._chg = ((lc, gc), np.zeros(max(lc, 1), np.uint32), R.aligned_empty(max(lc, 1), R.LWS_OUT),
+                         np.zeros(max(gc, 1), np.uint32), R.aligned_empty(max(gc, 1), R.GROUP_OUT))
+        _, lr, lo, gr, go = self._chg
+        ch = R.Changes(R.ptr(lr), R.ptr(lo), lc, 0, R.ptr(gr), R.ptr(go), gc, 0)
+        self._check(lib().lwse_resident_sweep(self._h, flags, C.byref(ch)))
+        nl, ng = min(ch.n_lws, lc), min(ch.n_groups, gc)
+        return lr[:nl], lo[:nl], gr[:ng], go[:ng], ch.n_lws, ch.n_groups
+
+    def resident_outputs(self):
+        n_lws, n_grp = self._resident_shape
+        lo, go = R.aligned_empty(n_lws, R.LWS_OUT), R.aligned_empty(n_grp, R.GROUP_OUT)
+        self._check(lib().lwse_resident_outputs(self._h, R.ptr(lo), R.ptr(go)))
+        return lo, go
 
     # -------------------------------------------------------------- placement
     def place_host(self, reqs: np.ndarray, occupancy=None, n_namespaces=1):

@@ -288,6 +288,22 @@ class LwsTables(C.Structure):
     ]
 
 
+class Changes(C.Structure):
+    _fields_ = [
+        ("lws_rows", C.c_void_p),
+        ("lws_out", C.c_void_p),
+        ("lws_capacity", C.c_uint32),
+        ("n_lws", C.c_uint32),
+        ("group_rows", C.c_void_p),
+        ("group_out", C.c_void_p),
+        ("group_capacity", C.c_uint32),
+        ("n_groups", C.c_uint32),
+    ]
+
+
+TABLE_LWS, TABLE_GROUPS, TABLE_POD_STATE, TABLE_POD_IDENT = 0, 1, 2, 3
+
+
 class DsTables(C.Structure):
     _fields_ = [
         ("ds", C.c_void_p),

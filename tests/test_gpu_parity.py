@@ -190,3 +190,61 @@ def test_reuse_pod_ident_flag(engine):
     want2 = oracle.sweep_lws(t2.lws, t2.groups, t2.pod_state, t2.pod_ident, t2.nodes, flags=t2.flags)
     got2 = engine.sweep_lws_host(t2.lws, t2.groups, t2.pod_state, t2.pod_ident, flags=t2.flags | R.SWEEP_REUSE_POD_IDENT)
     assert_same(got2[1], want2[1], "group_out")
+
+
+def test_resident_tables_patches_and_change_lists(engine):
+    """lwse_resident_*: tables stay on the device, the host sends row patches and gets back
+    exactly the result rows that changed."""
+    import oracle
+
+    t = synth.make("fuzz", 0.5, seed=31)
+    engine.upload_nodes(t.nodes, t.n_domains)
+    engine.resident_load(t.lws, t.groups, t.pod_state, t.pod_ident)
+    before = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, flags=t.flags)
+
+    lr, lo, gr, go, nl, ng = engine.resident_sweep(t.flags)
+    assert nl == len(t.lws) and ng == len(t.groups), "the first sweep after a load reports every row"
+    o = np.argsort(lr)
+    assert np.array_equal(lr[o], np.arange(len(t.lws))) and lo[o].tobytes() == before[0].tobytes()
+    o = np.argsort(gr)
+    assert np.array_equal(gr[o], np.arange(len(t.groups))) and go[o].tobytes() == before[1].tobytes()
+
+    _, _, _, _, nl, ng = engine.resident_sweep(t.flags)
+    assert (nl, ng) == (0, 0), "nothing changed → nothing reported"
+
+    # watch events: some pods restart / go pending, some groups lose readiness, some objects move their partition
+    rng = np.random.default_rng(9)
+    prow = np.unique(rng.integers(0, len(t.pod_state), size=len(t.pod_state) // 50)).astype(np.uint32)
+    t.pod_state[prow] ^= np.where(rng.random(len(prow)) < 0.5, R.POD_ANY_RESTART, R.POD_PHASE_PENDING | R.POD_PHASE_RUNNING).astype(np.uint32)
+    grow = np.unique(rng.integers(0, len(t.groups), size=len(t.groups) // 100)).astype(np.uint32)
+    t.groups["flags"][grow] ^= R.GRP_POD_READY
+    lrow = np.unique(rng.integers(0, len(t.lws), size=len(t.lws) // 100)).astype(np.uint32)
+    t.lws["sts_partition"][lrow] += 1
+    irow = prow[:7]
+    t.pod_ident["owner_uid_hash"][irow] ^= 1
+    engine.resident_patch(R.TABLE_POD_STATE, prow, t.pod_state[prow])
+    engine.resident_patch(R.TABLE_GROUPS, grow, t.groups[grow])
+    engine.resident_patch(R.TABLE_LWS, lrow, t.lws[lrow])
+    engine.resident_patch(R.TABLE_POD_IDENT, irow, t.pod_ident[irow])
+    after = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, flags=t.flags)
+
+    lr, lo, gr, go, nl, ng = engine.resident_sweep(t.flags)
+    want_l = np.flatnonzero([a.tobytes() != b.tobytes() for a, b in zip(before[0], after[0])])
+    want_g = np.flatnonzero([a.tobytes() != b.tobytes() for a, b in zip(before[1], after[1])])
+    assert len(want_l) > 0 and len(want_g) > 0
+    o = np.argsort(lr)
+    assert np.array_equal(lr[o], want_l) and lo[o].tobytes() == after[0][want_l].tobytes()
+    o = np.argsort(gr)
+    assert np.array_equal(gr[o], want_g) and go[o].tobytes() == after[1][want_g].tobytes()
+    full = engine.resident_outputs()
+    assert full[0].tobytes() == after[0].tobytes() and full[1].tobytes() == after[1].tobytes()
+
+    # a change list that is too small: the count is still exact, the full outputs are the fallback
+    t.lws["replicas"][:] += 1
+    engine.resident_patch(R.TABLE_LWS, np.arange(len(t.lws), dtype=np.uint32), t.lws)
+    after2 = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, flags=t.flags)
+    lr, lo, gr, go, nl, ng = engine.resident_sweep(t.flags, lws_capacity=3, group_capacity=3)
+    want_l2 = sum(a.tobytes() != b.tobytes() for a, b in zip(after[0], after2[0]))
+    assert nl == want_l2 and len(lr) == 3
+    full = engine.resident_outputs()
+    assert full[0].tobytes() == after2[0].tobytes() and full[1].tobytes() == after2[1].tobytes()
