@@ -305,7 +305,22 @@ def run_ours(args):
         # inputs, deterministic kernel → identical results; each rank keeps the rows of its own part
         eng.place_gathered_device(gathered, world, part_stride, reqs_off, req_cap, 1, d_pout, stream=pptr)
 
+    # single GPU: one C-ABI call per tick (lwse_reconcile_device forks/joins the placement round
+    # on the engine's side stream); descriptors are built once
+    descs = {}
+
+    def desc(i, flags):
+        k = (i % copies, flags)
+        if k not in descs:
+            s = sets[i % copies]
+            descs[k] = eng.device_tables(s["lws"], n_lws, s["grp"], n_grp, s["pst"], s["pid"], n_pod, s["lo"],
+                                         s["go"], None, flags=flags)
+        return descs[k]
+
     def step(i, flags):
+        if place_on and world == 1:
+            eng.reconcile_device(desc(i, flags), d_reqs, n_req, d_occ, 1, d_pout, stream=sptr)
+            return
         if place_on:
             pstream.wait_stream(stream)  # fork: placement starts with the sweep …
             place()
@@ -361,8 +376,10 @@ def run_ours(args):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             l0 = eng.launch_count
             e0.record(stream)
+            h0 = time.perf_counter()
             for i in range(steps):
                 run(i)
+            timed.host_ms = (time.perf_counter() - h0) * 1e3 / steps  # host enqueue time per call
             e1.record(stream)
         barrier()
         launched = eng.launch_count - l0
@@ -386,6 +403,7 @@ def run_ours(args):
     count_launches(full_step)
     with ClockSampler(local_rank) as clk:
         ms_step, launches = timed(full_step, args.steps, W)
+        host_ms_step = getattr(timed, "host_ms", None)
         # each pass alone (same rotating inputs), for the per-kernel roofline
         ms_sweep, _ = timed(lambda i: sweep(i, t.flags), args.steps, 3)
         ms_scan, _ = timed(lambda i: sweep(i, t.flags | SCAN_ONLY), args.steps, 3)
@@ -494,7 +512,7 @@ def run_ours(args):
                                      "collective": "1 all_gather/step" if (world > 1 and place_on) else "none"},
                        "launch": ("CUDA graph replay (one graph per step: sweep kernels with programmatic edges, "
                                   "all-gather, placement)") if use_graph else "eager launches, programmatic dependent launch",
-                       "step": "pod scan + group pass + LWS pass, placement round concurrently on a second stream",
+                       "step": "one lwse_reconcile_device call per tick: pod scan + group pass + LWS pass, placement round concurrently on the engine's side stream" if world == 1 else "pod scan + group pass + LWS pass, placement round (one all-gather) concurrently on a second stream",
                        "l2": f"inputs rotate over {copies} resident copies ({copies * algo_bytes / 1e6:.0f} MB > L2)"},
             "e2e": {"value": total_groups / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
@@ -510,7 +528,7 @@ def run_ours(args):
                          "bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms, "peak_source": peak_src,
                          "passes": {k: {"bytes": int(v[0]), "ms": v[1], "gbs": v[0] / (v[1] * 1e-3) / 1e9,
                                         "frac": v[0] / (v[1] * 1e-3) / 1e9 / peak} for k, v in passes.items()}},
-            "ms_sweep_only": ms_sweep, "ms_placement_only": ms_place,
+            "ms_sweep_only": ms_sweep, "ms_placement_only": ms_place, "host_enqueue_ms_per_step": host_ms_step,
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"full {t.profile.name} step x{cpu_reps} ({cpu_s * 1e3:.1f} ms per step: sweep + placement spec round)"},
             "clocks": clocks,

@@ -432,6 +432,18 @@ LWSE_API int lwse_place_gathered_device(lwse_engine* e, const void* d_parts, uin
                                         uint32_t reqs_per_part, uint32_t n_namespaces,
                                         lwse_place_out* d_out, uint32_t* rounds_out, void* stream);
 
+/* One reconcile tick on device tables: lwse_sweep_lws_device(d) on `stream` and a
+ * placement round (as lwse_place_device, rounds_out = NULL) on an engine-owned side
+ * stream, forked from and joined back into `stream` with events — the placement
+ * round reads only its own inputs, never the sweep's outputs, so the two overlap.
+ * This is what one pass of the controller's work queue maps to: every
+ * Reconcile() (leaderworkerset_controller.go:106-193, pod_controller.go:71-201)
+ * plus the scheduler's share of the exclusive-topology contract.
+ * n_reqs == 0: sweep only. */
+LWSE_API int lwse_reconcile_device(lwse_engine* e, const lwse_lws_tables* d, const lwse_place_req* d_reqs,
+                                   uint32_t n_reqs, const uint32_t* d_occupancy, uint32_t n_namespaces,
+                                   lwse_place_out* d_place_out, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* DisaggregatedSet sweep                                                    */
 /* ------------------------------------------------------------------------- */

@@ -69,6 +69,8 @@ struct lwse_engine {
   int device = 0;
   int sm_count = lwse::kSmCount;
   cudaStream_t stream = nullptr;
+  cudaStream_t side_stream = nullptr;  // placement round of lwse_reconcile_device
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::mutex mu;
   int last_cuda_error = 0;
   uint64_t launches = 0;
@@ -197,9 +199,15 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
   }
   e->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&e->h_rounds), 64) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&e->h_counts), 64) != cudaSuccess) {
     (void)cudaGetLastError();
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->side_stream) cudaStreamDestroy(e->side_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return LWSE_ERR_CUDA;
@@ -224,6 +232,10 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
     for (DevBuf* b : bufs) b->release();
     if (e->h_rounds) cudaFreeHost(e->h_rounds);
     if (e->h_counts) cudaFreeHost(e->h_counts);
+    cudaStreamSynchronize(e->side_stream);
+    cudaEventDestroy(e->ev_fork);
+    cudaEventDestroy(e->ev_join);
+    cudaStreamDestroy(e->side_stream);
     cudaStreamDestroy(e->stream);
   }
   delete e;
@@ -252,13 +264,7 @@ LWSE_API int lwse_upload_nodes(lwse_engine* e, const lwse_node_rec* nodes, uint3
 // ---------------------------------------------------------------------------
 // LWS sweep
 // ---------------------------------------------------------------------------
-LWSE_API int lwse_sweep_lws_device(lwse_engine* e, const lwse_lws_tables* t, void* stream) {
-  if (!e) return LWSE_ERR_INVALID_ARG;
-  int rc = check_lws_tables(t);
-  if (rc != LWSE_OK) return rc;
-  std::lock_guard<std::mutex> lock(e->mu);
-  DeviceGuard guard(e->device);
-  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+static int sweep_device_locked(lwse_engine* e, const lwse_lws_tables* t, cudaStream_t s) {
   // the scan bitmaps live in engine-owned scratch; it only grows (a growth is a
   // cudaMalloc, so size it with one warm-up call before capturing a graph)
   LWSE_CUDA(e, e->scan_scratch.reserve(lwse::lws_sweep_scratch_bytes(t->n_pods)));
@@ -268,6 +274,15 @@ LWSE_API int lwse_sweep_lws_device(lwse_engine* e, const lwse_lws_tables* t, voi
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
   return LWSE_OK;
+}
+
+LWSE_API int lwse_sweep_lws_device(lwse_engine* e, const lwse_lws_tables* t, void* stream) {
+  if (!e) return LWSE_ERR_INVALID_ARG;
+  int rc = check_lws_tables(t);
+  if (rc != LWSE_OK) return rc;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  return sweep_device_locked(e, t, stream ? (cudaStream_t)stream : e->stream);
 }
 
 LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* h) {
@@ -479,15 +494,12 @@ LWSE_API int lwse_resident_outputs(lwse_engine* e, lwse_lws_out* lws_out, lwse_g
 // ---------------------------------------------------------------------------
 // Placement
 // ---------------------------------------------------------------------------
-static int place_common(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
+static int place_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
                         const uint32_t* d_occupancy, uint32_t n_namespaces, lwse_place_out* d_out,
-                        uint32_t* rounds_out, void* stream, uint32_t n_parts, uint32_t reqs_per_part,
+                        uint32_t* rounds_out, cudaStream_t s, uint32_t n_parts, uint32_t reqs_per_part,
                         uint64_t part_stride_bytes) {
-  if (!e || (n_reqs && (!d_reqs || !d_out)) || n_namespaces == 0) return LWSE_ERR_INVALID_ARG;
-  std::lock_guard<std::mutex> lock(e->mu);
+  if ((n_reqs && (!d_reqs || !d_out)) || n_namespaces == 0) return LWSE_ERR_INVALID_ARG;
   if (e->n_nodes == 0 || e->n_domains == 0) return LWSE_ERR_NOT_READY;
-  DeviceGuard guard(e->device);
-  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
   const size_t scratch = lwse::place_scratch_bytes(e->n_nodes, e->n_domains, n_reqs, n_namespaces);
   const void* before = e->place_scratch.p;
   LWSE_CUDA(e, e->place_scratch.reserve(scratch));
@@ -504,6 +516,42 @@ static int place_common(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
   if (rounds_out) *rounds_out = e->h_rounds[0];
+  return LWSE_OK;
+}
+
+static int place_common(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
+                        const uint32_t* d_occupancy, uint32_t n_namespaces, lwse_place_out* d_out,
+                        uint32_t* rounds_out, void* stream, uint32_t n_parts, uint32_t reqs_per_part,
+                        uint64_t part_stride_bytes) {
+  if (!e) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  return place_locked(e, d_reqs, n_reqs, d_occupancy, n_namespaces, d_out, rounds_out,
+                      stream ? (cudaStream_t)stream : e->stream, n_parts, reqs_per_part, part_stride_bytes);
+}
+
+// One reconcile tick on device tables: the placement round reads only inputs (requests, occupancy,
+// node table), never the sweep's outputs, so it is enqueued on the engine's side stream and runs
+// concurrently with the three sweep kernels; `stream` continues when both are done.
+LWSE_API int lwse_reconcile_device(lwse_engine* e, const lwse_lws_tables* t, const lwse_place_req* d_reqs,
+                                   uint32_t n_reqs, const uint32_t* d_occupancy, uint32_t n_namespaces,
+                                   lwse_place_out* d_place_out, void* stream) {
+  if (!e) return LWSE_ERR_INVALID_ARG;
+  int rc = check_lws_tables(t);
+  if (rc != LWSE_OK) return rc;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  if (n_reqs == 0) return sweep_device_locked(e, t, s);
+  LWSE_CUDA(e, cudaEventRecord(e->ev_fork, s));
+  LWSE_CUDA(e, cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+  rc = place_locked(e, d_reqs, n_reqs, d_occupancy, n_namespaces, d_place_out, nullptr, e->side_stream, 1, n_reqs, 0);
+  if (rc == LWSE_OK) rc = sweep_device_locked(e, t, s);
+  // join even after a failure, so that the side stream never runs ahead of `stream`
+  cudaError_t je = cudaEventRecord(e->ev_join, e->side_stream);
+  if (je == cudaSuccess) je = cudaStreamWaitEvent(s, e->ev_join, 0);
+  if (rc != LWSE_OK) return rc;
+  if (je != cudaSuccess) return fail_cuda(e, je);
   return LWSE_OK;
 }
 

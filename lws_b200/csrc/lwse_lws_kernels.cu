@@ -176,9 +176,13 @@ __device__ __forceinline__ uint32_t bit_range(uint32_t lo, uint32_t hi) {
 // One W-lane tile per group: the lanes share the group's bitmap words (lane j
 // takes words j, j+W, …) so that the rare per-pod visits of one group run in
 // parallel; W = 1 for small groups.
+// 128-thread CTAs capped at 64 registers: a tick's placement round holds a quarter of every
+// SM's register file while this kernel runs, and the groups of a 100k-group table should
+// still fit in one wave next to it.
+constexpr uint32_t kGroupThreads = 128;
 template <int W>
-__global__ void __launch_bounds__(256) group_sweep_kernel(const GroupSweepArgs a) {
-  constexpr uint32_t kTilesPerBlock = 256 / W;
+__global__ void __launch_bounds__(kGroupThreads, 8) group_sweep_kernel(const GroupSweepArgs a) {
+  constexpr uint32_t kTilesPerBlock = kGroupThreads / W;
   const uint32_t lane = threadIdx.x & (W - 1);
   const uint32_t stride = gridDim.x * kTilesPerBlock;
   pdl_launch_dependents();
@@ -603,12 +607,11 @@ static uint32_t resident_ctas(K kernel, int sm_count) {
 
 template <int W>
 static cudaError_t launch_group(const GroupSweepArgs& a, int sm_count, cudaStream_t s) {
-  constexpr uint32_t kTilesPerBlock = 256 / W;
-  static uint32_t resident = 0;
-  if (resident == 0) resident = resident_ctas(group_sweep_kernel<W>, sm_count);
-  (void)resident;
+  constexpr uint32_t kTilesPerBlock = kGroupThreads / W;
+  (void)sm_count;
   const uint32_t want = (a.n_groups + kTilesPerBlock - 1) / kTilesPerBlock;
-  return launch_pdl(group_sweep_kernel<W>, dim3(want < (1u << 20) ? want : (1u << 20)), dim3(256), 0, s, g_pdl, a);
+  return launch_pdl(group_sweep_kernel<W>, dim3(want < (1u << 20) ? want : (1u << 20)), dim3(kGroupThreads), 0, s,
+                    g_pdl, a);
 }
 
 template <int W>

@@ -35,7 +35,7 @@ struct PlaceArgs {
   unsigned long long* holder;  // n_namespaces x n_domains
   uint32_t* choice;            // per request: proposed node (or NONE)
   uint32_t* state;             // per request: 1 = unschedulable
-  uint32_t* counters;          // [0..2] proposals per round (rotating), [3] rounds, [4] unpinned requests
+  uint32_t* counters;          // [0..2] unsettled claims per round (rotating), [3] rounds, [4] unpinned requests
   uint32_t* g_compact;         // condensed node words (global copy, TMA source)
   uint32_t* g_dom_free;
   uint32_t* unpinned;          // indices of the unpinned requests (built in phase 0)
@@ -49,9 +49,9 @@ struct PlaceArgs {
   // occupancy of a node is the sum over the parts
   uint32_t n_parts, reqs_per_part;
   uint64_t part_stride_bytes;
+  uint32_t* soft_bar;  // non-null: [0] arrivals, [1] generation of the software grid barrier
 };
 
-constexpr uint32_t kPlaceThreads = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -137,6 +137,36 @@ __device__ __forceinline__ void stamp(const PlaceArgs& a, uint32_t k) {
   }
 }
 
+// Grid barrier.  Cooperative launches do not share the GPU with other grids, so the placement
+// round could never overlap the sweep kernels of the same step; launched as an ordinary grid of
+// at most one CTA per SM (every CTA becomes resident as soon as the other, finite, kernels
+// drain) the round uses this arrive-and-spin barrier instead.
+__device__ __forceinline__ void grid_barrier(const PlaceArgs& a, cg::grid_group& grid) {
+  if (a.soft_bar == nullptr) {
+    __threadfence();
+    grid.sync();
+    return;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t gen;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(a.soft_bar + 1) : "memory");
+    __threadfence();
+    const uint32_t arrived = atomicAdd(a.soft_bar, 1u);
+    if (arrived == gridDim.x - 1u) {
+      a.soft_bar[0] = 0u;
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.soft_bar + 1), "r"(gen + 1u) : "memory");
+    } else {
+      uint32_t now;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(a.soft_bar + 1) : "memory");
+      } while (now == gen);
+    }
+  }
+  __syncthreads();
+}
+
 constexpr uint32_t kUnusable = 0xFFFFFFFFu;
 // node word: min(free,15) << 28 | domain (28 bits); the exact free count only feeds dom_free
 
@@ -172,7 +202,11 @@ __device__ __forceinline__ lwse_place_out pinned_result(const PlaceArgs& a, cons
   return o;
 }
 
-__global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs a) {
+// kPlaceThreads threads per CTA, at least MINB CTAs' worth of registers per SM left to ptxas:
+// the round shares each SM with the sweep kernels of the same tick, so what it leaves free
+// (registers above all) decides how much of the sweep overlaps it.
+template <uint32_t kPlaceThreads, int MINB>
+__global__ void __launch_bounds__(kPlaceThreads, MINB) place_kernel(const PlaceArgs a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -229,8 +263,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   stamp(a, 1);
-  __threadfence();
-  grid.sync();
+  grid_barrier(a, grid);
   stamp(a, 2);
 
   const uint32_t n_unpinned = __ldcg(a.counters + 4);
@@ -317,6 +350,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
           // CTA branches on is reduced through shared memory — threads never branch on their own
           // reading of a holder.  (Per-node holder loads cost 8.8 us per request, per-node
           // hashing 5 us, a serial chain of request/state loads 2 us — measured with %globaltimer.)
+          if (round == 0 && j == 0) stamp(a, 10);
           const uint32_t cur_dom = q.cur != LWSE_NONE ? (compact[q.cur] & 0x0FFFFFFFu) : LWSE_NONE;
           uint32_t my_hi = 0, my_holding = 0;
           for (uint32_t d = tid; d < a.n_domains; d += kPlaceThreads) {
@@ -342,19 +376,33 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
             holding |= (uint32_t)s_best[w];
           }
           __syncthreads();  // s_best / s_best_n are reused by the arg-max below
+          if (round == 0 && j == 0) stamp(a, 11);
           if (holding) continue;  // uniform: derived from shared memory
           // Pass 2 — nodes of the winning domain(s): every (request, node) pair is looked at, but
           // only nodes whose domain carries the winning score are hashed and ranked.
           if (H != 0u) {
-            for (uint32_t n = tid; n < a.n_nodes; n += kPlaceThreads) {
-              const uint32_t w = compact[n];
-              if (w == kUnusable || (w >> 28) == 0u) continue;
-              if (s_hi[w & 0x0FFFFFFFu] != H) continue;
-              const uint32_t lo = ((w >> 28) << 28) | (mix32(q.key_hi ^ (n * 0x85EBCA77u)) >> 4);
-              const unsigned long long sc = ((unsigned long long)H << 32) | lo;
-              if (best_n == LWSE_NONE || sc > best) {  // n ascends per thread: ties keep the lower index
-                best = sc;
-                best_n = n;
+            // four node words per 128-bit shared-memory load; the four domain-score lookups are
+            // independent (padding words are kUnusable)
+            const uint4* words4 = reinterpret_cast<const uint4*>(compact);
+            for (uint32_t n4 = tid; n4 < (n_pad >> 2); n4 += kPlaceThreads) {
+              const uint4 w4 = words4[n4];
+              const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+              uint32_t hit[4];
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const bool ok = w[k] != kUnusable && (w[k] >> 28) != 0u;
+                hit[k] = ok ? s_hi[w[k] & 0x0FFFFFFFu] : 0u;
+              }
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                if (hit[k] != H) continue;
+                const uint32_t n = n4 * 4u + (uint32_t)k;
+                const uint32_t lo = ((w[k] >> 28) << 28) | (mix32(q.key_hi ^ (n * 0x85EBCA77u)) >> 4);
+                const unsigned long long sc = ((unsigned long long)H << 32) | lo;
+                if (best_n == LWSE_NONE || sc > best) {  // n ascends per thread: ties keep the lower index
+                  best = sc;
+                  best_n = n;
+                }
               }
             }
           }
@@ -381,6 +429,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
             }
           }
         }
+        if (round == 0 && j == 0) stamp(a, 12);
         auto better = [](unsigned long long os, uint32_t on, unsigned long long s, uint32_t n) {
           return on != LWSE_NONE && (n == LWSE_NONE || os > s || (os == s && on < n));
         };
@@ -420,22 +469,26 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) place_kernel(const PlaceArgs
               }
             } else {
               const uint32_t d = compact[best_n] & 0x0FFFFFFFu;
-              atomicMin(hold + d, key);
+              // A claim on an empty domain settles at once.  Any other outcome leaves somebody
+              // without a domain — the previous holder (old > key) or this request (old < key) —
+              // who proposes again next round: count it, so that the round after the last
+              // displacement is never run just to find nothing to do.
+              const unsigned long long old = atomicMin(hold + d, key);
               a.choice[q.r] = best_n;
               if (j < kCacheQ) s_req[j].cur = best_n;
               a.out[q.r].score = (uint32_t)(best >> 32);
-              atomicAdd(counter, 1u);
+              if (old != ~0ull) atomicAdd(counter, 1u);
             }
           }
         }
         __syncthreads();  // s_best and the cache entry are settled before the next request
+        if (round == 0 && j == 0) stamp(a, 13);
       }
       stamp(a, 4 + 2 * round);
-      __threadfence();
-      grid.sync();
+      grid_barrier(a, grid);
       stamp(a, 5 + 2 * round);
-      const uint32_t proposals = __ldcg(counter);
-      if (proposals == 0u || round > a.n_reqs + 2u) break;
+      const uint32_t unsettled = __ldcg(counter);
+      if (unsettled == 0u || round > a.n_reqs + 2u) break;
     }
 
     // results of this CTA's unpinned requests (fixed point: every live request holds its choice)
@@ -507,6 +560,7 @@ int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_doma
       e = cudaMemsetAsync(base + h * half, 0xFF, holder_bytes, s);
       if (e == cudaSuccess) e = cudaMemsetAsync(base + h * half + holder_bytes, 0, zero_bytes, s);
     }
+    if (e == cudaSuccess) e = cudaMemsetAsync(base + 2 * half, 0, 1024, s);  // software-barrier words
     if (e != cudaSuccess) {
       *cuda_err = (int)e;
       return -1;
@@ -545,9 +599,20 @@ int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_doma
   size_t smem = kSmemHeader + words_bytes;
   a.smem_nodes = smem <= 227u * 1024u ? 1u : 0u;
   if (!a.smem_nodes) smem = kSmemHeader;
+  static const int variant = [] {
+    const char* v = getenv("LWSE_PLACE_VARIANT");
+    return v ? atoi(v) : 0;
+  }();
+  // 256 threads x 64 registers: a quarter of the register file (the 512 x 92 first version held
+  // three quarters and the sweep's group pass of the same tick could not start next to it:
+  // 40.9 us per tick against 29.5 us)
+  void (*kernel)(PlaceArgs) = place_kernel<256, 2>;
+  unsigned threads = 256;
+  if (variant == 1) kernel = place_kernel<512, 1>, threads = 512;
+  if (variant == 2) kernel = place_kernel<512, 2>, threads = 512;
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    e = cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       *cuda_err = (int)e;
       return -1;
@@ -565,7 +630,17 @@ int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_doma
   unsigned ctas = (unsigned)sm_count;
   if (n_reqs < ctas) ctas = n_reqs < 16u ? 16u : n_reqs;
   if (env_ctas > 0 && (unsigned)env_ctas < ctas) ctas = (unsigned)env_ctas;
-  e = cudaLaunchCooperativeKernel((const void*)place_kernel, dim3(ctas), dim3(kPlaceThreads), params, smem, s);
+  static const bool soft = [] {
+    const char* v = getenv("LWSE_PLACE_SOFT_BARRIER");
+    return v && atoi(v) != 0;
+  }();
+  if (soft) {
+    a.soft_bar = reinterpret_cast<uint32_t*>(base + 2 * half);  // zero-filled when the scratch is allocated
+    kernel<<<dim3(ctas), dim3(threads), smem, s>>>(a);
+    e = cudaGetLastError();
+  } else {
+    e = cudaLaunchCooperativeKernel((const void*)kernel, dim3(ctas), dim3(threads), params, smem, s);
+  }
   if (e != cudaSuccess) {
     *cuda_err = (int)e;
     return -1;

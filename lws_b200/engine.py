@@ -47,6 +47,10 @@ SYMBOLS = {
          C.POINTER(C.c_uint32), C.c_void_p],
         C.c_int,
     ),
+    "lwse_reconcile_device": (
+        [C.c_void_p, C.POINTER(R.LwsTables), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p],
+        C.c_int,
+    ),
     "lwse_sweep_ds_host": ([C.c_void_p, C.POINTER(R.DsTables)], C.c_int),
     "lwse_sweep_ds_device": ([C.c_void_p, C.POINTER(R.DsTables), C.c_void_p], C.c_int),
     "lwse_group_keys_host": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p], C.c_int),
@@ -158,6 +162,21 @@ class Engine:
             R.ptr(d_lws_out), R.ptr(d_group_out), R.ptr(d_occupancy), flags,
         )
         self._check(lib().lwse_sweep_lws_device(self._h, C.byref(t), stream))
+
+    @staticmethod
+    def device_tables(d_lws, n_lws, d_groups, n_groups, d_pod_state, d_pod_ident, n_pods, d_lws_out, d_group_out,
+                      d_occupancy=None, flags=0):
+        """The ``lwse_lws_tables`` descriptor of device-resident tables (build once, reuse every tick)."""
+        return R.LwsTables(
+            R.ptr(d_lws), n_lws, R.ptr(d_groups), n_groups, R.ptr(d_pod_state), R.ptr(d_pod_ident), n_pods,
+            R.ptr(d_lws_out), R.ptr(d_group_out), R.ptr(d_occupancy), flags,
+        )
+
+    def reconcile_device(self, tables, d_reqs, n_reqs, d_occupancy, n_namespaces, d_place_out, stream=None):
+        """One reconcile tick: sweep on ``stream``, placement round concurrently on the engine's
+        side stream, joined back into ``stream``.  Enqueue only, no synchronize."""
+        self._check(lib().lwse_reconcile_device(self._h, C.byref(tables), R.ptr(d_reqs), n_reqs, R.ptr(d_occupancy),
+                                                n_namespaces, R.ptr(d_place_out), stream))
 
     # ------------------------------------------------------- resident tables
     def resident_load(self, lws, groups, pod_state, pod_ident):

@@ -187,3 +187,40 @@ def test_ds_multi_cycle_flows_on_gpu(engine, order):
     sweep = lambda t: engine.sweep_ds_host(t.ds, t.roles, t.revroles)
     run_flow(sweep, (2, 4), (1, 2), (1, 2), (1, 1), order)
     run_flow(sweep, (4, 3), (1, 2), (3, 1), (1, 2), order, check_orphans=True)
+
+
+def test_reconcile_tick_sweep_and_placement_concurrently(engine):
+    """lwse_reconcile_device: sweep on the caller's stream, placement round on the engine's side
+    stream, repeated ticks (the scratch halves alternate) — both results equal the oracle's."""
+    import torch
+    import oracle
+
+    t, reqs = place_case(n_lws=3000, n_nodes=4096, size=16, p_excl=0.5, p_unsched=0.6, seed=21, capacity=40)
+    engine.upload_nodes(t.nodes, t.n_domains)
+    dev = torch.device("cuda:0")
+
+    def up(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+
+    want_lo, want_go, occ = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, flags=t.flags,
+                                             want_occupancy=True)
+    want_place = oracle.place(t.nodes, occ, t.n_domains, 1, reqs)
+    d_lo = torch.zeros(len(t.lws) * R.LWS_OUT.itemsize, dtype=torch.uint8, device=dev)
+    d_go = torch.zeros(len(t.groups) * R.GROUP_OUT.itemsize, dtype=torch.uint8, device=dev)
+    d_po = torch.zeros(len(reqs) * R.PLACE_OUT.itemsize, dtype=torch.uint8, device=dev)
+    d_occ = torch.from_numpy(occ.view(np.int32)).to(dev)
+    d_in = [up(t.lws), up(t.groups), up(t.pod_state), up(t.pod_ident)]  # the descriptor holds raw pointers only
+    tables = engine.device_tables(d_in[0], len(t.lws), d_in[1], len(t.groups), d_in[2], d_in[3], len(t.pod_state),
+                                  d_lo, d_go, None, flags=t.flags)
+    d_reqs = up(reqs)
+    torch.cuda.synchronize()
+    for tick in range(5):
+        d_lo.zero_(), d_go.zero_(), d_po.zero_()
+        torch.cuda.synchronize()
+        before = engine.launch_count
+        engine.reconcile_device(tables, d_reqs, len(reqs), d_occ, 1, d_po)
+        torch.cuda.synchronize()
+        assert engine.launch_count - before == 4
+        same(d_lo.cpu().numpy().view(R.LWS_OUT), want_lo, f"tick{tick}.lws_out")
+        same(d_go.cpu().numpy().view(R.GROUP_OUT), want_go, f"tick{tick}.group_out")
+        same(d_po.cpu().numpy().view(R.PLACE_OUT), want_place, f"tick{tick}.place_out")
