@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <mutex>
+#include <vector>
 #include <new>
 
 #include "lwse_device.cuh"
@@ -25,7 +26,8 @@ size_t lws_sweep_scratch_bytes(uint64_t n_pods);
 int launch_scatter(int row_words, void* table, uint64_t table_rows, const uint32_t* rows, const void* values,
                    uint32_t n, cudaStream_t s, int* cuda_err);
 // lwse_place_kernels.cu
-int launch_place(const lwse_node_rec* d_nodes, uint32_t n_nodes, uint32_t n_domains,
+int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, const uint32_t* d_node_order,
+                 const uint32_t* d_node_pos, uint32_t n_nodes, uint32_t n_domains,
                  const lwse_place_req* d_reqs, uint32_t n_reqs, const uint32_t* d_occupancy,
                  uint32_t n_namespaces, lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes,
                  uint32_t* h_rounds, int sm_count, cudaStream_t s, int* cuda_err, uint32_t call_index,
@@ -76,6 +78,7 @@ struct lwse_engine {
   uint64_t launches = 0;
   // resident node table
   DevBuf nodes;
+  DevBuf dom_first, node_order, node_pos;  // static domain-sorted index of the node table (placement)
   uint32_t n_nodes = 0, n_domains = 0;
   // staging for the *_host entry points
   DevBuf lws, groups, pod_state, pod_ident, lws_out, group_out, occupancy, scan_scratch;
@@ -175,6 +178,15 @@ LWSE_API uint32_t lwse_shard_of(uint64_t uid_hash, uint32_t n_shards) {
   return (uint32_t)(x % n_shards);
 }
 
+// The placement round of a tick is short and latency-bound; at the highest priority its CTAs
+// take the first SM slots the sweep kernels free instead of queueing behind their blocks.
+static cudaError_t create_side_stream(cudaStream_t* s) {
+  int least = 0, greatest = 0;
+  cudaError_t e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
+  if (e != cudaSuccess) return e;
+  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, greatest);
+}
+
 LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
   if (!cfg || !out) return LWSE_ERR_INVALID_ARG;
   *out = nullptr;
@@ -199,7 +211,7 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
   }
   e->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      create_side_stream(&e->side_stream) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&e->h_rounds), 64) != cudaSuccess ||
@@ -221,7 +233,7 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
   {
     DeviceGuard guard(e->device);
     cudaStreamSynchronize(e->stream);
-    DevBuf* bufs[] = {&e->nodes,      &e->lws,         &e->groups,     &e->pod_state,   &e->pod_ident,
+    DevBuf* bufs[] = {&e->nodes,      &e->dom_first, &e->node_order, &e->node_pos, &e->lws,         &e->groups,     &e->pod_state,   &e->pod_ident,
                       &e->scan_scratch, &e->lws_out,
                       &e->group_out,  &e->occupancy,   &e->place_reqs, &e->place_out,   &e->place_occ,
                       &e->place_scratch, &e->ds,       &e->ds_roles,   &e->ds_revroles, &e->ds_out,
@@ -252,10 +264,38 @@ LWSE_API int lwse_upload_nodes(lwse_engine* e, const lwse_node_rec* nodes, uint3
   std::lock_guard<std::mutex> lock(e->mu);
   DeviceGuard guard(e->device);
   LWSE_CUDA(e, e->nodes.reserve((size_t)n_nodes * sizeof(lwse_node_rec) + 16));
+  // Static index for the placement round: the usable nodes (schedulable, labelled with a
+  // topology domain) in domain order — a counting sort, done once per node-table upload.
+  // dom_first[d] .. dom_first[d + 1] is the run of domain d in node_order; node_pos is the
+  // inverse (LWSE_NONE for nodes no request can use).
+  std::vector<uint32_t> first((size_t)n_domains + 2, 0u), order, pos(n_nodes ? n_nodes : 1, LWSE_NONE);
+  auto usable = [&](const lwse_node_rec& nd) {
+    return (nd.flags & LWSE_NODE_SCHEDULABLE) && (nd.flags & LWSE_NODE_HAS_TOPOLOGY) && nd.domain_id < n_domains;
+  };
+  for (uint32_t n = 0; n < n_nodes; n++)
+    if (usable(nodes[n])) first[(size_t)nodes[n].domain_id + 1]++;
+  for (uint32_t d = 0; d < n_domains; d++) first[(size_t)d + 1] += first[d];
+  order.resize(first[n_domains] ? first[n_domains] : 1, 0u);
+  {
+    std::vector<uint32_t> cursor(first.begin(), first.end() - 1);
+    for (uint32_t n = 0; n < n_nodes; n++)
+      if (usable(nodes[n])) {
+        const uint32_t p = cursor[nodes[n].domain_id]++;
+        order[p] = n;
+        pos[n] = p;
+      }
+  }
+  LWSE_CUDA(e, e->dom_first.reserve(((size_t)n_domains + 1) * 4 + 16));
+  LWSE_CUDA(e, e->node_order.reserve(order.size() * 4 + 16));
+  LWSE_CUDA(e, e->node_pos.reserve(pos.size() * 4 + 16));
   if (n_nodes)
     LWSE_CUDA(e, cudaMemcpyAsync(e->nodes.p, nodes, (size_t)n_nodes * sizeof(lwse_node_rec),
                                  cudaMemcpyHostToDevice, e->stream));
-  LWSE_CUDA(e, cudaStreamSynchronize(e->stream));
+  LWSE_CUDA(e, cudaMemcpyAsync(e->dom_first.p, first.data(), ((size_t)n_domains + 1) * 4, cudaMemcpyHostToDevice,
+                               e->stream));
+  LWSE_CUDA(e, cudaMemcpyAsync(e->node_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, e->stream));
+  LWSE_CUDA(e, cudaMemcpyAsync(e->node_pos.p, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, e->stream));
+  LWSE_CUDA(e, cudaStreamSynchronize(e->stream));  // the host vectors above go out of scope
   e->n_nodes = n_nodes;
   e->n_domains = n_domains;
   return LWSE_OK;
@@ -509,7 +549,9 @@ static int place_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n
   const bool fresh = before != e->place_scratch.p || geometry != e->place_geometry;
   e->place_geometry = geometry;
   int cuda_err = 0;
-  int launched = lwse::launch_place((const lwse_node_rec*)e->nodes.p, e->n_nodes, e->n_domains, d_reqs,
+  int launched = lwse::launch_place((const lwse_node_rec*)e->nodes.p, (const uint32_t*)e->dom_first.p,
+                                    (const uint32_t*)e->node_order.p, (const uint32_t*)e->node_pos.p, e->n_nodes,
+                                    e->n_domains, d_reqs,
                                     n_reqs, d_occupancy, n_namespaces, d_out, e->place_scratch.p,
                                     scratch, rounds_out ? e->h_rounds : nullptr, e->sm_count, s, &cuda_err,
                                     e->place_calls++, fresh, n_parts, reqs_per_part, part_stride_bytes);

@@ -23,15 +23,17 @@
  *                pinned claimants of a (namespace, domain) holds it (PLACED|PINNED),
  *                the others get PINNED|CONFLICT.  Pinned claims are facts: they are
  *                never displaced by unpinned requests (bit 63 of the key).
- *   unpinned r   in ascending key order takes, among the (domain d, node n ∈ d) pairs
- *                with   dom_free[d] ≥ size(r) ∧ free[n] ≥ 1 ∧ (ns(r), d) not held,
- *                the pair with the largest score
- *                   hi = mix(key_lo ^ d·φ) | 1                  per-group rendezvous hash of the domain
- *                   lo = min(free[n], 15) << 28 | mix(key_hi ^ n·ψ) >> 4    emptiest node of it first
- *                (a per-group preference order over domains: any capacity-derived term would
- *                give all groups the same order and serialise the claim rounds; capacity is a
- *                feasibility filter; ties → lower node index) and then holds (ns, d).
- *                No feasible pair → UNSCHEDULABLE.
+ *   unpinned r   in ascending key order picks, in two levels,
+ *                  1. the domain d with   dom_free[d] ≥ size(r) ∧ (ns(r), d) not held   that has
+ *                     the largest      hi = mix(key_lo ^ d·φ) | 1        (ties → lower d)
+ *                     — a per-group rendezvous hash: any capacity-derived term would give all
+ *                     groups the same preference order and serialise the claim rounds, so
+ *                     capacity is a feasibility filter only;
+ *                  2. in it the node n with free[n] ≥ 1 that has the largest
+ *                                      lo = min(free[n], 15) << 28 | mix(key_hi ^ n·ψ) >> 4
+ *                     — emptiest node first                              (ties → lower n)
+ *                and then holds (ns, d); score = hi.  No feasible domain → UNSCHEDULABLE.
+ *                (size ≥ 1, so a feasible domain always has a node with a free slot.)
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -121,33 +123,39 @@ LWSO_API int lwso_place(const lwse_node_rec* nodes, uint32_t n_nodes, const uint
       continue;
     }
     const uint32_t key_lo = (uint32_t)r->group_key, key_hi = (uint32_t)(r->group_key >> 32);
-    int found = 0;
-    uint64_t best = 0;
-    uint32_t best_n = 0;
-    for (uint32_t n = 0; n < n_nodes; n++) {
-      if (free_[n] < 1) continue;
-      uint32_t d = nodes[n].domain_id;
-      if (hold[d] != ~0ull) continue;
-      if (dom_free[d] < (uint32_t)r->size) continue;
-      uint32_t hi = mix32(key_lo ^ (d * 0x9E3779B1u)) | 1u;
-      uint32_t lo = ((free_[n] > 15 ? 15u : free_[n]) << 28) | (mix32(key_hi ^ (n * 0x85EBCA77u)) >> 4);
-      uint64_t s = ((uint64_t)hi << 32) | lo;
-      if (!found || s > best) { /* ties keep the lower node index */
-        found = 1;
-        best = s;
-        best_n = n;
+    /* level 1: the domain */
+    uint32_t best_hi = 0, d = LWSE_NONE;
+    for (uint32_t c = 0; c < n_domains; c++) {
+      if (hold[c] != ~0ull || dom_free[c] < (uint32_t)r->size) continue;
+      uint32_t hi = mix32(key_lo ^ (c * 0x9E3779B1u)) | 1u;
+      if (hi > best_hi) { /* ties keep the lower domain index */
+        best_hi = hi;
+        d = c;
       }
     }
-    if (!found) {
+    if (d == LWSE_NONE) {
       out[i].flags |= LWSE_PLACE_UNSCHEDULABLE;
       continue;
     }
-    uint32_t d = nodes[best_n].domain_id;
+    /* level 2: the node in it */
+    uint32_t best_lo = 0, best_n = LWSE_NONE;
+    for (uint32_t n = 0; n < n_nodes; n++) {
+      if (free_[n] < 1 || nodes[n].domain_id != d) continue; /* free_ > 0 implies usable */
+      uint32_t lo = ((free_[n] > 15 ? 15u : free_[n]) << 28) | (mix32(key_hi ^ (n * 0x85EBCA77u)) >> 4);
+      if (lo > best_lo) { /* ties keep the lower node index */
+        best_lo = lo;
+        best_n = n;
+      }
+    }
+    if (best_n == LWSE_NONE) { /* cannot happen: dom_free[d] >= size >= 1 */
+      out[i].flags |= LWSE_PLACE_UNSCHEDULABLE;
+      continue;
+    }
     hold[d] = order[k].key;
     out[i].domain_id = d;
     out[i].leader_node = best_n;
     out[i].flags |= LWSE_PLACE_PLACED;
-    out[i].score = (uint32_t)(best >> 32);
+    out[i].score = best_hi;
   }
   free(free_);
   free(dom_free);
