@@ -59,6 +59,18 @@ __device__ __forceinline__ uint32_t seg8_or(uint32_t nibble, uint32_t lane) {
   return v;
 }
 
+// SWAR over the 4 pods of a lane: byte k of X = low byte of pod k's state word (phase bits 0-1,
+// any-restart bit 2, deleting bit 3), both predicates evaluated on the four bytes at once, then
+// the four bit-0s are gathered into a nibble with one multiply.
+__device__ __forceinline__ void pod4_predicates(const uint4 v, uint32_t& pend, uint32_t& ev) {
+  const uint32_t X = __byte_perm(__byte_perm(v.x, v.y, 0x0040), __byte_perm(v.z, v.w, 0x0040), 0x5410);
+  const uint32_t y = X >> 1, z = X >> 2, w3 = X >> 3;
+  const uint32_t P = X & ~y & 0x01010101u;                // phase == Pending (bit0 ∧ ¬bit1)
+  const uint32_t E = (((X ^ y) & z) | w3) & 0x01010101u;  // (phase ∈ {Pending,Running} ∧ restart) ∨ deleting
+  pend = (P * 0x10204080u) >> 28;
+  ev = (E * 0x10204080u) >> 28;
+}
+
 template <int U, bool OCC>
 __global__ void __launch_bounds__(256) pod_scan_kernel(const PodScanArgs a) {
   const uint32_t lane = threadIdx.x & 31u;
@@ -89,14 +101,8 @@ __global__ void __launch_bounds__(256) pod_scan_kernel(const PodScanArgs a) {
     }
 #pragma unroll
     for (int j = 0; j < U; j++) {
-      // SWAR over the 4 pods of this lane: byte k of X = low byte of pod k's state word
-      // (phase bits 0-1, any-restart bit 2, deleting bit 3), both predicates evaluated on the
-      // four bytes at once, then the four bit-0s are gathered into a nibble with one multiply.
-      const uint32_t X = __byte_perm(__byte_perm(v[j].x, v[j].y, 0x0040), __byte_perm(v[j].z, v[j].w, 0x0040), 0x5410);
-      const uint32_t y = X >> 1, z = X >> 2, w3 = X >> 3;
-      const uint32_t P = X & ~y & 0x01010101u;                  // phase == Pending (bit0 ∧ ¬bit1)
-      const uint32_t E = (((X ^ y) & z) | w3) & 0x01010101u;    // (phase ∈ {Pending,Running} ∧ restart) ∨ deleting
-      const uint32_t pend = (P * 0x10204080u) >> 28, ev = (E * 0x10204080u) >> 28;
+      uint32_t pend, ev;
+      pod4_predicates(v[j], pend, ev);
       if (OCC) {
         const uint32_t b[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
@@ -173,27 +179,211 @@ __device__ __forceinline__ uint32_t bit_range(uint32_t lo, uint32_t hi) {
   return upto_hi & ~((1u << lo) - 1u) & (lo >= 32u ? 0u : 0xFFFFFFFFu);
 }
 
-// One W-lane tile per group: the lanes share the group's bitmap words (lane j
-// takes words j, j+W, …) so that the rare per-pod visits of one group run in
-// parallel; W = 1 for small groups.
-// 128-thread CTAs capped at 64 registers: a tick's placement round holds a quarter of every
-// SM's register file while this kernel runs, and the groups of a 100k-group table should
-// still fit in one wave next to it.
+// Where a group's bitmap words come from: the scan kernel's global bitmaps, or the
+// shared-memory window of the fused kernel.
+struct GlobalBits {
+  const uint32_t* pending_bits;
+  const uint32_t* event_bits;
+  __device__ __forceinline__ uint32_t pending(uint32_t w) const { return __ldg(pending_bits + w); }
+  __device__ __forceinline__ uint32_t event(uint32_t w) const { return __ldg(event_bits + w); }
+};
+
+// The group pass proper for group g (row ca..cd, first 16 bytes of its owner L): one W-lane
+// tile per group, the lanes share the group's bitmap words (lane j takes words j, j+W, …) so
+// that the rare per-pod visits of one group run in parallel; W = 1 for small groups.
+// Returns the 16-byte result row.
+template <int W, class Bits>
+__device__ __forceinline__ uint4 group_body(const GroupSweepArgs& a, const Bits& bits, uint32_t lane, const uint4 ca,
+                                            const uint4 cb, const uint4 cc, const uint4 cd, const uint4 L,
+                                            const bool bad) {
+  const uint32_t pod_base = cc.z, pod_count = cc.w, gflags = cd.y;
+  uint32_t oflags = 0, first_out = LWSE_NONE, domain = LWSE_NONE;
+  int32_t worker_replicas = 0;
+  if (bad) {
+    oflags = LWSE_GOUT_BAD_TABLE;
+  } else {
+    const int32_t size = (int32_t)L.z;
+    const uint32_t lflags = L.w;
+    const uint32_t policy = (lflags & LWSE_LWS_RESTART_MASK) >> LWSE_LWS_RESTART_SHIFT;
+    const bool policy_on = policy == LWSE_RESTART_ON_POD_RESTART || policy == LWSE_RESTART_AFTER_START;
+
+    // ---- pendingPodsInGroup :338-362 from the pending bitmap ----
+    const uint32_t pod_end = pod_base + pod_count;  // <= n_pods < 2^32 (checked by the entry points)
+    const uint32_t w_first = pod_base >> 5, w_last = pod_count ? ((pod_end - 1u) >> 5) : w_first;
+    uint32_t any_bits = 0;  // bit0 pending, bit1 event
+    if (pod_count) {
+      for (uint32_t w = w_first + lane; w <= w_last; w += W) {
+        const uint32_t lo = w == w_first ? (pod_base & 31u) : 0u;
+        const uint32_t hi = w == w_last ? (((pod_end - 1u) & 31u) + 1u) : 32u;
+        const uint32_t m = bit_range(lo, hi);
+        if (bits.pending(w) & m) any_bits |= 1u;
+        if (bits.event(w) & m) any_bits |= 2u;
+      }
+    }
+    any_bits = tile_or<W>(any_bits);
+    const bool pending = (uint32_t)size != pod_count || (any_bits & 1u);
+    if (pending) oflags |= LWSE_GOUT_PENDING;
+    // :222 skip when pending ∧ (AfterStart ∨ annotation)
+    const bool suppressed =
+        pending && (policy == LWSE_RESTART_AFTER_START || (lflags & LWSE_LWS_RECREATE_AFTER_START_ANNOT));
+
+    // ---- handleRestartPolicy :204-266 for the pods that have an event ----
+    bool leader_deleted = false;
+    if ((any_bits & 2u) && policy_on && !suppressed) {  // tile-uniform
+      const bool leader_found = (gflags & (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH)) ==
+                                (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH);  // :233
+      constexpr uint32_t kChain =
+          LWSE_GRP_WSTS_FOUND | LWSE_GRP_WSTS_OWNER_IS_POD | LWSE_GRP_WSTS_OWNER_NAME_MATCH;
+      const bool wsts_chain_ok = (gflags & kChain) == kChain && cc.x == cb.z;  // sts owner uid == leader uid
+      uint32_t acc = 0, first = LWSE_NONE;
+      // The pods to visit are collected four at a time so that their state and
+      // identity loads are all in flight together (one DRAM round trip per batch
+      // instead of one per pod).
+      auto visit = [&](const uint32_t* ev, int cnt) {
+        uint32_t bits[4], id_lo[4], id_hi[4], id_owner[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (k < cnt) {
+            const uint32_t p = ev[k];
+            bits[k] = __ldg(a.pod_state + p);
+            const uint32_t* idp = reinterpret_cast<const uint32_t*>(a.pod_ident + p);
+            id_lo[k] = __ldg(idp);
+            id_hi[k] = __ldg(idp + 1);
+            id_owner[k] = __ldg(idp + 2);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (k < cnt) {
+            const uint32_t b = bits[k];
+            bool cand, deleting;
+            if (b & LWSE_POD_IS_LEADER) {
+              cand = true;  // leader = pod (:251)
+              deleting = b & LWSE_POD_DELETING;
+            } else if (!(b & LWSE_POD_NAME_OK)) {
+              acc |= LWSE_GOUT_RESTART_ERROR;  // :230
+              cand = false;
+              deleting = false;
+            } else {
+              const uint32_t kind = (b & LWSE_POD_OWNER_MASK) >> LWSE_POD_OWNER_SHIFT;
+              // workerPodBelongsToLeader :268-295
+              const bool belongs = (b & LWSE_POD_OWNER_NAME_MATCH) &&
+                                   ((kind == 1u && id_owner[k] == cb.z) ||
+                                    (kind == 2u && id_owner[k] == cb.w && wsts_chain_ok));
+              cand = leader_found && id_lo[k] == ca.x && id_hi[k] == ca.y && belongs;  // :239
+              deleting = gflags & LWSE_GRP_POD_DELETING;
+            }
+            if (cand) {
+              acc |= deleting ? LWSE_GOUT_LEADER_DELETING : LWSE_GOUT_DELETE_LEADER;  // :255 / :259
+              if (b & LWSE_POD_IS_LEADER) acc |= 0x80000000u;
+              first = min(first, ev[k] - pod_base);
+            }
+          }
+        }
+      };
+      uint32_t ev[4];
+      int cnt = 0;
+      for (uint32_t w = w_first + lane; w <= w_last; w += W) {
+        const uint32_t lo = w == w_first ? (pod_base & 31u) : 0u;
+        const uint32_t hi = w == w_last ? (((pod_end - 1u) & 31u) + 1u) : 32u;
+        uint32_t m = bits.event(w) & bit_range(lo, hi);
+        while (m) {
+          const uint32_t p = (w << 5) + (__ffs(m) - 1u);
+          m &= m - 1u;
+          // fixed-slot insert keeps ev[] in registers
+          if (cnt == 0) ev[0] = p;
+          else if (cnt == 1) ev[1] = p;
+          else if (cnt == 2) ev[2] = p;
+          else ev[3] = p;
+          if (++cnt == 4) {
+            visit(ev, 4);
+            cnt = 0;
+          }
+        }
+      }
+      if (cnt) visit(ev, cnt);
+      acc = tile_or<W>(acc);
+      first_out = tile_min<W>(first);
+      leader_deleted = acc & 0x80000000u;
+      oflags |= acc & 0x7FFFFFFFu;
+    }
+
+    // ---- per-replica state bits (consumed by lws_sweep_kernel) ----
+    const bool no_wsts = size == 1;
+    const uint64_t rev = u64_of(L.x, L.y);
+    const bool leader_updated = u64_of(ca.x, ca.y) == rev;
+    const bool wsts_updated = u64_of(ca.z, ca.w) == rev;
+    const bool leader_ready = (gflags & (LWSE_GRP_POD_RUNNING | LWSE_GRP_POD_READY)) ==
+                              (LWSE_GRP_POD_RUNNING | LWSE_GRP_POD_READY);  // PodRunningAndReady
+    const bool wsts_ready = cb.x == cb.y && (gflags & LWSE_GRP_WSTS_REV_SETTLED);  // StatefulsetReady
+    const bool ready = leader_ready && (no_wsts || wsts_ready);
+    const bool updated = leader_updated && (no_wsts || wsts_updated);
+    // getReplicaStates :609-617 — names decide whether the slot is live
+    const bool named = (gflags & LWSE_GRP_POD_NAME_MATCH) &&
+                       (no_wsts || (gflags & LWSE_GRP_WSTS_LABEL_NAME_MATCH));
+    if (named && ready) oflags |= LWSE_GOUT_STATE_READY;
+    if (named && updated) oflags |= LWSE_GOUT_STATE_UPDATED;
+    // updateConditions :433-476 — existing leader pods whose worker sts is found
+    const bool counted = (gflags & LWSE_GRP_POD_PRESENT) && (no_wsts || (gflags & LWSE_GRP_WSTS_FOUND));
+    if (counted) {
+      oflags |= LWSE_GOUT_COUNTED;
+      if (ready) oflags |= LWSE_GOUT_COND_READY;
+      if (updated) oflags |= LWSE_GOUT_COND_UPDATED;
+    }
+
+    // ---- the leader pod's own Reconcile tail, pod_controller.go:95-198 ----
+    bool go_on = (gflags & LWSE_GRP_POD_PRESENT) && !leader_deleted &&
+                 !(gflags & (LWSE_GRP_MISTAKEN_ANNOTATION | LWSE_GRP_POD_DELETING));
+    if (go_on) {
+      if (a.sweep_flags & LWSE_SWEEP_GANG) oflags |= LWSE_GOUT_CREATE_PODGROUP;  // :130
+      go_on = !no_wsts &&                                                          // :138
+              !((lflags & LWSE_LWS_STARTUP_LEADER_READY) && !(gflags & LWSE_GRP_POD_READY));  // :143
+    }
+    if (go_on && !(gflags & LWSE_GRP_REVISION_EXISTS)) {  // :152
+      oflags |= LWSE_GOUT_REQUEUE_REVISION;
+      go_on = false;
+    }
+    if (go_on && (lflags & LWSE_LWS_EXCLUSIVE_TOPOLOGY)) {  // :162
+      const uint32_t node = cc.y;
+      if (node == LWSE_NONE) {  // :164
+        oflags |= LWSE_GOUT_WAIT_SCHEDULE;
+        go_on = false;
+      } else if (node != LWSE_NODE_NOT_FOUND && node < a.n_nodes) {
+        const uint4 nr = ldg_cached(reinterpret_cast<const uint4*>(a.nodes + node));
+        const uint32_t nflags = nr.w >> 16;
+        if (!(nflags & LWSE_NODE_HAS_TOPOLOGY)) {  // :330
+          oflags |= LWSE_GOUT_TOPOLOGY_ERROR;
+          go_on = false;
+        } else {
+          domain = nr.z;
+        }
+      }  // Node NotFound → empty value, nil error (:327)
+    }
+    if (go_on && !(gflags & LWSE_GRP_WSTS_FOUND)) {  // :188-192
+      oflags |= LWSE_GOUT_CREATE_WSTS;
+      worker_replicas = size - 1;  // :437; ordinals start at 1 (:440)
+    }
+  }
+  return make_uint4(oflags, first_out, (uint32_t)worker_replicas, domain);
+}
+
+// 128-thread CTAs capped at 64 registers: a tick's placement round holds part of the register
+// file of some SMs while this kernel runs, and the groups of a 100k-group table should still
+// fit in one wave next to it.
 constexpr uint32_t kGroupThreads = 128;
 template <int W>
 __global__ void __launch_bounds__(kGroupThreads, 8) group_sweep_kernel(const GroupSweepArgs a) {
   constexpr uint32_t kTilesPerBlock = kGroupThreads / W;
   const uint32_t lane = threadIdx.x & (W - 1);
   const uint32_t stride = gridDim.x * kTilesPerBlock;
+  const GlobalBits bits{a.pending_bits, a.event_bits};
   pdl_launch_dependents();
   bool waited = false;
   for (uint32_t g = blockIdx.x * kTilesPerBlock + threadIdx.x / W; g < a.n_groups; g += stride) {
     const uint4* row = reinterpret_cast<const uint4*>(a.groups + g);
     const uint4 ca = ldg_cached(row + 0), cb = ldg_cached(row + 1), cc = ldg_cached(row + 2),
                 cd = ldg_cached(row + 3);
-    const uint32_t pod_base = cc.z, pod_count = cc.w, lws_index = cd.x, gflags = cd.y;
-    uint32_t oflags = 0, first_out = LWSE_NONE, domain = LWSE_NONE;
-    int32_t worker_replicas = 0;
+    const uint32_t pod_base = cc.z, pod_count = cc.w, lws_index = cd.x;
     const bool bad = lws_index >= a.n_lws || (uint64_t)pod_base + pod_count > a.n_pods;
     // owner row: only its first 16 bytes (rev_hash, size, flags)
     uint4 L = make_uint4(0, 0, 0, 0);
@@ -202,176 +392,145 @@ __global__ void __launch_bounds__(kGroupThreads, 8) group_sweep_kernel(const Gro
       pdl_wait_prior();
       waited = true;
     }
-    if (bad) {
-      oflags = LWSE_GOUT_BAD_TABLE;
-    } else {
-      const int32_t size = (int32_t)L.z;
-      const uint32_t lflags = L.w;
-      const uint32_t policy = (lflags & LWSE_LWS_RESTART_MASK) >> LWSE_LWS_RESTART_SHIFT;
-      const bool policy_on = policy == LWSE_RESTART_ON_POD_RESTART || policy == LWSE_RESTART_AFTER_START;
+    const uint4 v[1] = {group_body<W>(a, bits, lane, ca, cb, cc, cd, L, bad)};
+    if (lane == 0) emit_if_changed<1>(a.changes, reinterpret_cast<uint4*>(a.out + g), g, v);
+  }
+}
 
-      // ---- pendingPodsInGroup :338-362 from the pending bitmap ----
-      const uint32_t pod_end = pod_base + pod_count;  // <= n_pods < 2^32 (checked by the entry points)
-      const uint32_t w_first = pod_base >> 5, w_last = pod_count ? ((pod_end - 1u) >> 5) : w_first;
-      uint32_t any_bits = 0;  // bit0 pending, bit1 event
-      if (pod_count) {
-        for (uint32_t w = w_first + lane; w <= w_last; w += W) {
-          const uint32_t lo = w == w_first ? (pod_base & 31u) : 0u;
-          const uint32_t hi = w == w_last ? (((pod_end - 1u) & 31u) + 1u) : 32u;
-          const uint32_t m = bit_range(lo, hi);
-          if (__ldg(a.pending_bits + w) & m) any_bits |= 1u;
-          if (__ldg(a.event_bits + w) & m) any_bits |= 2u;
-        }
-      }
-      any_bits = tile_or<W>(any_bits);
-      const bool pending = (uint32_t)size != pod_count || (any_bits & 1u);
-      if (pending) oflags |= LWSE_GOUT_PENDING;
-      // :222 skip when pending ∧ (AfterStart ∨ annotation)
-      const bool suppressed =
-          pending && (policy == LWSE_RESTART_AFTER_START || (lflags & LWSE_LWS_RECREATE_AFTER_START_ANNOT));
+// --------------------------------------------------------------------------
+// fused pod scan + group pass
+// --------------------------------------------------------------------------
+// One CTA per 256 consecutive groups, one thread per group.  The CTA first streams the pod
+// state words of its groups' pod window (the union of their ranges: contiguous for tables the
+// encoder lays out, pods of group g right after those of g-1) with the scan's coalesced 128-bit
+// loads and packs the two predicate bitmaps into SHARED memory; the group pass then reads its
+// bitmap words from there.  Against the two-kernel form this drops one kernel boundary and the
+// bitmaps' round trip through L2, and the state words of the event pods the group pass visits
+// were just loaded by the same SM.  Used when no per-node occupancy is wanted (that count needs
+// every pod exactly once, whatever the group table says) and groups are small (W = 1).
+// A window that does not fit (irregular tables: ranges far apart) falls back to deriving each
+// bitmap word from the state column directly — slow, still exact.
+constexpr uint32_t kFusedThreads = 256;
+constexpr uint32_t kWinWords = 2048;  // 65 536 pods per CTA: 2 x 8 KB of shared memory
 
-      // ---- handleRestartPolicy :204-266 for the pods that have an event ----
-      bool leader_deleted = false;
-      if ((any_bits & 2u) && policy_on && !suppressed) {  // tile-uniform
-        const bool leader_found = (gflags & (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH)) ==
-                                  (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH);  // :233
-        constexpr uint32_t kChain =
-            LWSE_GRP_WSTS_FOUND | LWSE_GRP_WSTS_OWNER_IS_POD | LWSE_GRP_WSTS_OWNER_NAME_MATCH;
-        const bool wsts_chain_ok = (gflags & kChain) == kChain && cc.x == cb.z;  // sts owner uid == leader uid
-        uint32_t acc = 0, first = LWSE_NONE;
-        // The pods to visit are collected four at a time so that their state and
-        // identity loads are all in flight together (one DRAM round trip per batch
-        // instead of one per pod).
-        auto visit = [&](const uint32_t* ev, int cnt) {
-          uint32_t bits[4], id_lo[4], id_hi[4], id_owner[4];
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            if (k < cnt) {
-              const uint32_t p = ev[k];
-              bits[k] = __ldg(a.pod_state + p);
-              const uint32_t* idp = reinterpret_cast<const uint32_t*>(a.pod_ident + p);
-              id_lo[k] = __ldg(idp);
-              id_hi[k] = __ldg(idp + 1);
-              id_owner[k] = __ldg(idp + 2);
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            if (k < cnt) {
-              const uint32_t b = bits[k];
-              bool cand, deleting;
-              if (b & LWSE_POD_IS_LEADER) {
-                cand = true;  // leader = pod (:251)
-                deleting = b & LWSE_POD_DELETING;
-              } else if (!(b & LWSE_POD_NAME_OK)) {
-                acc |= LWSE_GOUT_RESTART_ERROR;  // :230
-                cand = false;
-                deleting = false;
-              } else {
-                const uint32_t kind = (b & LWSE_POD_OWNER_MASK) >> LWSE_POD_OWNER_SHIFT;
-                // workerPodBelongsToLeader :268-295
-                const bool belongs = (b & LWSE_POD_OWNER_NAME_MATCH) &&
-                                     ((kind == 1u && id_owner[k] == cb.z) ||
-                                      (kind == 2u && id_owner[k] == cb.w && wsts_chain_ok));
-                cand = leader_found && id_lo[k] == ca.x && id_hi[k] == ca.y && belongs;  // :239
-                deleting = gflags & LWSE_GRP_POD_DELETING;
-              }
-              if (cand) {
-                acc |= deleting ? LWSE_GOUT_LEADER_DELETING : LWSE_GOUT_DELETE_LEADER;  // :255 / :259
-                if (b & LWSE_POD_IS_LEADER) acc |= 0x80000000u;
-                first = min(first, ev[k] - pod_base);
-              }
-            }
-          }
-        };
-        uint32_t ev[4];
-        int cnt = 0;
-        for (uint32_t w = w_first + lane; w <= w_last; w += W) {
-          const uint32_t lo = w == w_first ? (pod_base & 31u) : 0u;
-          const uint32_t hi = w == w_last ? (((pod_end - 1u) & 31u) + 1u) : 32u;
-          uint32_t m = __ldg(a.event_bits + w) & bit_range(lo, hi);
-          while (m) {
-            const uint32_t p = (w << 5) + (__ffs(m) - 1u);
-            m &= m - 1u;
-            // fixed-slot insert keeps ev[] in registers
-            if (cnt == 0) ev[0] = p;
-            else if (cnt == 1) ev[1] = p;
-            else if (cnt == 2) ev[2] = p;
-            else ev[3] = p;
-            if (++cnt == 4) {
-              visit(ev, 4);
-              cnt = 0;
-            }
-          }
-        }
-        if (cnt) visit(ev, cnt);
-        acc = tile_or<W>(acc);
-        first_out = tile_min<W>(first);
-        leader_deleted = acc & 0x80000000u;
-        oflags |= acc & 0x7FFFFFFFu;
-      }
+struct WindowBits {
+  const uint32_t* pend;  // word (w - w0)
+  const uint32_t* ev;
+  uint32_t w0;
+  __device__ __forceinline__ uint32_t pending(uint32_t w) const { return pend[w - w0]; }
+  __device__ __forceinline__ uint32_t event(uint32_t w) const { return ev[w - w0]; }
+};
 
-      // ---- per-replica state bits (consumed by lws_sweep_kernel) ----
-      const bool no_wsts = size == 1;
-      const uint64_t rev = u64_of(L.x, L.y);
-      const bool leader_updated = u64_of(ca.x, ca.y) == rev;
-      const bool wsts_updated = u64_of(ca.z, ca.w) == rev;
-      const bool leader_ready = (gflags & (LWSE_GRP_POD_RUNNING | LWSE_GRP_POD_READY)) ==
-                                (LWSE_GRP_POD_RUNNING | LWSE_GRP_POD_READY);  // PodRunningAndReady
-      const bool wsts_ready = cb.x == cb.y && (gflags & LWSE_GRP_WSTS_REV_SETTLED);  // StatefulsetReady
-      const bool ready = leader_ready && (no_wsts || wsts_ready);
-      const bool updated = leader_updated && (no_wsts || wsts_updated);
-      // getReplicaStates :609-617 — names decide whether the slot is live
-      const bool named = (gflags & LWSE_GRP_POD_NAME_MATCH) &&
-                         (no_wsts || (gflags & LWSE_GRP_WSTS_LABEL_NAME_MATCH));
-      if (named && ready) oflags |= LWSE_GOUT_STATE_READY;
-      if (named && updated) oflags |= LWSE_GOUT_STATE_UPDATED;
-      // updateConditions :433-476 — existing leader pods whose worker sts is found
-      const bool counted = (gflags & LWSE_GRP_POD_PRESENT) && (no_wsts || (gflags & LWSE_GRP_WSTS_FOUND));
-      if (counted) {
-        oflags |= LWSE_GOUT_COUNTED;
-        if (ready) oflags |= LWSE_GOUT_COND_READY;
-        if (updated) oflags |= LWSE_GOUT_COND_UPDATED;
-      }
-
-      // ---- the leader pod's own Reconcile tail, pod_controller.go:95-198 ----
-      bool go_on = (gflags & LWSE_GRP_POD_PRESENT) && !leader_deleted &&
-                   !(gflags & (LWSE_GRP_MISTAKEN_ANNOTATION | LWSE_GRP_POD_DELETING));
-      if (go_on) {
-        if (a.sweep_flags & LWSE_SWEEP_GANG) oflags |= LWSE_GOUT_CREATE_PODGROUP;  // :130
-        go_on = !no_wsts &&                                                          // :138
-                !((lflags & LWSE_LWS_STARTUP_LEADER_READY) && !(gflags & LWSE_GRP_POD_READY));  // :143
-      }
-      if (go_on && !(gflags & LWSE_GRP_REVISION_EXISTS)) {  // :152
-        oflags |= LWSE_GOUT_REQUEUE_REVISION;
-        go_on = false;
-      }
-      if (go_on && (lflags & LWSE_LWS_EXCLUSIVE_TOPOLOGY)) {  // :162
-        const uint32_t node = cc.y;
-        if (node == LWSE_NONE) {  // :164
-          oflags |= LWSE_GOUT_WAIT_SCHEDULE;
-          go_on = false;
-        } else if (node != LWSE_NODE_NOT_FOUND && node < a.n_nodes) {
-          const uint4 nr = ldg_cached(reinterpret_cast<const uint4*>(a.nodes + node));
-          const uint32_t nflags = nr.w >> 16;
-          if (!(nflags & LWSE_NODE_HAS_TOPOLOGY)) {  // :330
-            oflags |= LWSE_GOUT_TOPOLOGY_ERROR;
-            go_on = false;
-          } else {
-            domain = nr.z;
-          }
-        }  // Node NotFound → empty value, nil error (:327)
-      }
-      if (go_on && !(gflags & LWSE_GRP_WSTS_FOUND)) {  // :188-192
-        oflags |= LWSE_GOUT_CREATE_WSTS;
-        worker_replicas = size - 1;  // :437; ordinals start at 1 (:440)
-      }
-    }
-    if (lane == 0) {
-      const uint4 v[1] = {make_uint4(oflags, first_out, (uint32_t)worker_replicas, domain)};
-      emit_if_changed<1>(a.changes, reinterpret_cast<uint4*>(a.out + g), g, v);
+struct DirectBits {
+  const uint32_t* state;
+  uint64_t n_pods;
+  __device__ __forceinline__ void word(uint32_t w, uint32_t& pend, uint32_t& ev) const {
+    pend = ev = 0;
+    for (uint32_t k = 0; k < 32u; k++) {
+      const uint64_t p = ((uint64_t)w << 5) + k;
+      if (p >= n_pods) break;
+      const uint32_t b = __ldg(state + p);
+      if ((b & LWSE_POD_PHASE_MASK) == LWSE_POD_PHASE_PENDING) pend |= 1u << k;
+      if (pod_has_event(b)) ev |= 1u << k;
     }
   }
+  __device__ __forceinline__ uint32_t pending(uint32_t w) const {
+    uint32_t p, e;
+    word(w, p, e);
+    return p;
+  }
+  __device__ __forceinline__ uint32_t event(uint32_t w) const {
+    uint32_t p, e;
+    word(w, p, e);
+    return e;
+  }
+};
+
+__global__ void __launch_bounds__(kFusedThreads, 3) group_fused_kernel(const GroupSweepArgs a) {
+  __shared__ uint32_t s_pend[kWinWords], s_ev[kWinWords];
+  __shared__ uint32_t s_lo[kFusedThreads / 32], s_hi[kFusedThreads / 32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t g = blockIdx.x * kFusedThreads + tid;
+  const bool valid = g < a.n_groups;
+  pdl_launch_dependents();
+
+  uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, cc = ca, cd = ca, L = ca;
+  bool bad = true;
+  if (valid) {
+    const uint4* row = reinterpret_cast<const uint4*>(a.groups + g);
+    ca = ldg_cached(row + 0), cb = ldg_cached(row + 1), cc = ldg_cached(row + 2), cd = ldg_cached(row + 3);
+    bad = cd.x >= a.n_lws || (uint64_t)cc.z + cc.w > a.n_pods;
+    if (!bad) L = ldg_cached(reinterpret_cast<const uint4*>(a.lws + cd.x));  // first 16 bytes of the owner row
+  }
+  // the CTA's window of bitmap words
+  const bool has_pods = valid && !bad && cc.w != 0u;
+  uint32_t lo = has_pods ? (cc.z >> 5) : 0xFFFFFFFFu;
+  uint32_t hi = has_pods ? (((cc.z + cc.w - 1u) >> 5) + 1u) : 0u;
+  lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+  hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+  if (lane == 0) {
+    s_lo[warp] = lo;
+    s_hi[warp] = hi;
+  }
+  __syncthreads();
+  lo = s_lo[0], hi = s_hi[0];
+#pragma unroll
+  for (int k = 1; k < (int)(kFusedThreads / 32); k++) {
+    lo = min(lo, s_lo[k]);
+    hi = max(hi, s_hi[k]);
+  }
+  const uint32_t n_words = hi > lo ? hi - lo : 0u;
+  const bool windowed = n_words <= kWinWords;  // CTA-uniform
+
+  if (windowed && n_words) {
+    // the scan: 128 pods (4 bitmap words) per warp and chunk, U chunks in flight per warp
+    // (U = 8 is 0.7 us faster alone but takes 80 registers: three resident CTAs would then leave
+    // no SM with room for a placement CTA and the tick serialises — 27.0 us against 22.7 us)
+    constexpr int U = 4;
+    const uint32_t n_chunks = (n_words + 3u) >> 2;
+    const uint4* vec = reinterpret_cast<const uint4*>(a.pod_state);
+    for (uint32_t c0 = warp * U; c0 < n_chunks; c0 += (kFusedThreads / 32) * U) {
+      uint4 v[U];
+#pragma unroll
+      for (int j = 0; j < U; j++) {
+        const uint32_t c = c0 + (uint32_t)j;
+        const uint64_t idx = ((uint64_t)lo << 5) + (uint64_t)c * 128u + lane * 4u;
+        if (c >= n_chunks) {
+          v[j] = make_uint4(0, 0, 0, 0);
+        } else if (idx + 3u < a.n_pods) {
+          v[j] = ldg_stream(vec + (idx >> 2));
+        } else {  // ragged tail of the column
+          v[j].x = idx + 0u < a.n_pods ? __ldg(a.pod_state + idx + 0u) : 0u;
+          v[j].y = idx + 1u < a.n_pods ? __ldg(a.pod_state + idx + 1u) : 0u;
+          v[j].z = idx + 2u < a.n_pods ? __ldg(a.pod_state + idx + 2u) : 0u;
+          v[j].w = 0u;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < U; j++) {
+        uint32_t pend, ev;
+        pod4_predicates(v[j], pend, ev);
+        const uint32_t wp = seg8_or(pend, lane), we = seg8_or(ev, lane);
+        const uint32_t w = (c0 + (uint32_t)j) * 4u + (lane >> 3);
+        if ((lane & 7u) == 0u && w < n_words) {
+          s_pend[w] = wp;
+          s_ev[w] = we;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  uint4 v[1];
+  if (windowed) {
+    const WindowBits bits{s_pend, s_ev, lo};
+    v[0] = group_body<1>(a, bits, 0u, ca, cb, cc, cd, L, bad);
+  } else {
+    const DirectBits bits{a.pod_state, a.n_pods};
+    v[0] = group_body<1>(a, bits, 0u, ca, cb, cc, cd, L, bad);
+  }
+  pdl_wait_prior();  // group_out may still be read by the previous sweep's LWS pass
+  if (valid) emit_if_changed<1>(a.changes, reinterpret_cast<uint4*>(a.out + g), g, v);
 }
 
 // --------------------------------------------------------------------------
@@ -652,11 +811,30 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
   uint32_t* event_bits = pending_bits + ((words + 31u) & ~(uint64_t)31u);
   const bool group_pass = t->n_groups && !(t->flags & LWSE_SWEEP_SKIP_GROUP_PASS);
 
-  if (t->node_occupancy && n_nodes && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN)) {
+  // lanes per group: one per bitmap word of an average group, in {1, 2, 4, 8}
+  const uint64_t avg_pods = t->n_groups ? (t->n_pods + t->n_groups - 1) / t->n_groups : 0;
+  const int w = avg_pods > 2048 ? 8 : avg_pods > 1024 ? 4 : avg_pods > 512 ? 2 : 1;
+  static const bool no_fuse = [] {
+    const char* v = getenv("LWSE_NO_FUSE");
+    return v && atoi(v) != 0;
+  }();
+  // scan + group pass in one kernel: small groups, no occupancy count, both passes wanted
+  const bool fused = group_pass && w == 1 && !t->node_occupancy && !no_fuse &&
+                     !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN);
+  if (fused) {
+    GroupSweepArgs a{t->lws,   t->groups, t->pod_state, t->pod_ident, nullptr, nullptr, d_nodes,
+                     t->group_out, t->n_pods, t->n_lws, t->n_groups, n_nodes, t->flags, ChangeList{}};
+    if (cl && cl->group_rows) a.changes = ChangeList{cl->group_rows, cl->group_out, cl->counts + 1, cl->group_capacity};
+    const uint32_t grid = (t->n_groups + kFusedThreads - 1) / kFusedThreads;
+    e = launch_pdl(group_fused_kernel, dim3(grid), dim3(kFusedThreads), 0, s, g_pdl, a);
+    if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
+    launches++;
+  }
+  if (!fused && t->node_occupancy && n_nodes && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN)) {
     e = cudaMemsetAsync(t->node_occupancy, 0, (size_t)n_nodes * sizeof(uint32_t), s);
     if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
   }
-  if (t->n_pods && (t->n_groups || t->node_occupancy) && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN)) {
+  if (!fused && t->n_pods && (t->n_groups || t->node_occupancy) && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN)) {
     PodScanArgs a{t->pod_state, pending_bits, event_bits, t->node_occupancy, t->n_pods, n_nodes};
     // one chunk per warp: the kernel is a few microseconds long, so let the
     // hardware CTA scheduler balance it instead of a persistent grid-stride loop
@@ -670,13 +848,10 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
     if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
     launches++;
   }
-  if (group_pass) {
+  if (group_pass && !fused) {
     GroupSweepArgs a{t->lws,   t->groups, t->pod_state, t->pod_ident, pending_bits, event_bits, d_nodes,
                      t->group_out, t->n_pods, t->n_lws, t->n_groups, n_nodes, t->flags, ChangeList{}};
     if (cl && cl->group_rows) a.changes = ChangeList{cl->group_rows, cl->group_out, cl->counts + 1, cl->group_capacity};
-    // lanes per group: one per bitmap word of an average group, in {1, 2, 4, 8}
-    const uint64_t avg_pods = (t->n_pods + t->n_groups - 1) / t->n_groups;
-    const int w = avg_pods > 2048 ? 8 : avg_pods > 1024 ? 4 : avg_pods > 512 ? 2 : 1;
     switch (w) {
       case 8: e = launch_group<8>(a, sm_count, s); break;
       case 4: e = launch_group<4>(a, sm_count, s); break;

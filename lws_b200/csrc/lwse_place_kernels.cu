@@ -167,12 +167,14 @@ __device__ __forceinline__ void write_pinned(const PlaceArgs& a, const lwse_plac
   store_out(a.out + r, d, rq.leader_node, flags, 0u);
 }
 
-// The cluster form runs on 8 SMs and may use their whole register file; the grid form shares
-// every SM with the sweep kernels of the same tick and stays at 64 registers (a 512 x 92 version
-// held three quarters of each register file and the sweep's group pass could not start next to it).
+// 64 registers in either form: the round shares its SMs with the sweep kernels of the same tick,
+// and a cluster is only scheduled once EVERY one of its CTAs has an SM with room — 16 K registers
+// per 256-thread CTA fit next to three resident CTAs of the fused sweep kernel, 28 K did not
+// (the tick then serialised).  (A 512 x 92 first version held three quarters of each register
+// file and the sweep's group pass could not start next to it at all.)
 template <bool kCluster>
-__global__ void __launch_bounds__(kPlaceThreads, kCluster ? 1 : 2) place_kernel(const PlaceArgs a) {
-  constexpr int kDomChunk = kCluster ? 8 : 3;  // level 1: domain pairs per lane whose loads are in flight together
+__global__ void __launch_bounds__(kPlaceThreads, 2) place_kernel(const PlaceArgs a) {
+  constexpr int kDomChunk = kCluster ? 4 : 3;  // level 1: domain pairs per lane whose loads are in flight together
   __shared__ ReqCache s_req[kPlaceWarps][kCacheQ];
   __shared__ uint32_t s_scan[32];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;

@@ -220,7 +220,21 @@ def test_reconcile_tick_sweep_and_placement_concurrently(engine):
         before = engine.launch_count
         engine.reconcile_device(tables, d_reqs, len(reqs), d_occ, 1, d_po)
         torch.cuda.synchronize()
-        assert engine.launch_count - before == 4
+        assert engine.launch_count - before == 3  # placement + fused scan/group pass + LWS pass
         same(d_lo.cpu().numpy().view(R.LWS_OUT), want_lo, f"tick{tick}.lws_out")
         same(d_go.cpu().numpy().view(R.GROUP_OUT), want_go, f"tick{tick}.group_out")
         same(d_po.cpu().numpy().view(R.PLACE_OUT), want_place, f"tick{tick}.place_out")
+
+
+def test_placement_equal_domain_scores_keep_the_lower_domain(engine):
+    """Two domains with the same rendezvous score (hash collisions found by inverting the mixer):
+    the two-level spec takes the lower domain; interleaved node rows exercise the sorted index."""
+    import oracle
+    from test_place_spec import PLACE_TIES, tie_case
+
+    for key_lo, d1, d2, score in PLACE_TIES:
+        nodes, reqs = tie_case(key_lo, d1, d2)
+        engine.upload_nodes(nodes, 64)
+        got, _ = engine.place_host(reqs, None, 1)
+        same(got, oracle.place(nodes, None, 64, 1, reqs), "place_out")
+        assert got["domain_id"][0] == d1 and got["score"][0] == score

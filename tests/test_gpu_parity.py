@@ -41,6 +41,11 @@ def run_both(engine, t, occupancy=True):
     assert_same(got[1], want[1], "group_out")
     if occupancy:
         assert np.array_equal(got[2], want[2]), "node occupancy"
+        # without the occupancy count the scan and the group pass run as ONE fused kernel
+        # (small groups); same results
+        fused = engine.sweep_lws_host(t.lws, t.groups, t.pod_state, t.pod_ident, flags=t.flags, want_occupancy=False)
+        assert_same(fused[0], want[0], "fused.lws_out")
+        assert_same(fused[1], want[1], "fused.group_out")
     return got
 
 
@@ -248,3 +253,30 @@ def test_resident_tables_patches_and_change_lists(engine):
     assert nl == want_l2 and len(lr) == 3
     full = engine.resident_outputs()
     assert full[0].tobytes() == after2[0].tobytes() and full[1].tobytes() == after2[1].tobytes()
+
+
+def test_fused_pass_with_scattered_pod_ranges(engine):
+    """Pod ranges of neighbouring groups far apart (even groups' pods first, odd groups' after):
+    the fused kernel's shared-memory window does not fit and it derives the bitmap words from
+    the state column directly — same results."""
+    p = synth.profile("fuzz", 1.0)
+    p.n_lws, p.size_choices = 6000, (32, 64)
+    t = synth.make(p, seed=77)
+    assert len(t.pod_state) > 4 * 65536
+    order = np.concatenate([np.arange(0, len(t.groups), 2), np.arange(1, len(t.groups), 2)])
+    base, count = t.groups["pod_base"].astype(np.int64), t.groups["pod_count"].astype(np.int64)
+    new_base = np.zeros(len(t.groups), np.int64)
+    new_base[order] = np.concatenate([[0], np.cumsum(count[order])[:-1]])
+    src = np.concatenate([np.arange(base[g], base[g] + count[g]) for g in order]) if len(order) else np.zeros(0, np.int64)
+    pst, pid = R.aligned_empty(len(src), R.POD_STATE), R.aligned_empty(len(src), R.POD_IDENT)
+    pst[:], pid[:] = t.pod_state[src], t.pod_ident[src]
+    grp = R.aligned_empty(len(t.groups), R.GROUP_REC)
+    grp[:] = t.groups
+    grp["pod_base"] = new_base.astype(np.uint32)
+    import oracle
+
+    engine.upload_nodes(t.nodes, t.n_domains)
+    want = oracle.sweep_lws(t.lws, grp, pst, pid, t.nodes, flags=t.flags, want_occupancy=False)
+    got = engine.sweep_lws_host(t.lws, grp, pst, pid, flags=t.flags, want_occupancy=False)
+    assert_same(got[0], want[0], "lws_out")
+    assert_same(got[1], want[1], "group_out")

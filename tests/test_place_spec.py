@@ -57,3 +57,36 @@ def test_unschedulable_when_capacity_is_short():
     out = oracle.place(t.nodes, full_occ, t.n_domains, 1, reqs)
     unp = reqs["leader_node"] == R.NONE
     assert ((out["flags"][unp] & R.PLACE_UNSCHEDULABLE) != 0).all()
+
+
+# (group_key low word, d1, d2, shared score): mix(key ^ d1·φ)|1 == mix(key ^ d2·φ)|1, found by
+# inverting the mixer (tests/golden/find_place_ties.py)
+PLACE_TIES = [(0x5DD5FF0E, 24, 56, 0x3337DF), (0x0ECD4C3C, 11, 23, 0x43259F), (0xA7E9EB8E, 26, 35, 0x7036E3),
+              (0x5D7C00AC, 31, 36, 0x812E1B), (0xD88EC2CA, 6, 41, 0x932713)]
+
+
+def tie_case(key_lo, d1, d2, n_domains=64, nodes_per_domain=4):
+    """Only d1 and d2 have room; the request scores both the same."""
+    nodes = R.aligned_empty(n_domains * nodes_per_domain, R.NODE_REC)
+    nodes["topo_value_hash"] = 0
+    nodes["domain_id"] = np.arange(len(nodes)) % n_domains  # interleaved: runs are not contiguous
+    nodes["capacity"] = np.where(np.isin(nodes["domain_id"], [d1, d2]), 8, 0)
+    nodes["flags"] = R.NODE_HAS_TOPOLOGY | R.NODE_SCHEDULABLE
+    reqs = R.aligned_empty(3, R.PLACE_REQ)
+    reqs["priority"] = [5 << 25, 1 << 25, 9 << 25]
+    reqs["group_key"] = [key_lo | (0xABCDEF01 << 32), 0x1111, 0x2222]  # only row 0 carries the tie
+    reqs["group"] = [0, 1, 2]
+    reqs["ns"] = 0
+    reqs["size"] = [4, 100, 4]  # row 1 fits nowhere
+    reqs["leader_node"] = R.NONE
+    return nodes, reqs
+
+
+def test_equal_domain_scores_keep_the_lower_domain():
+    for key_lo, d1, d2, score in PLACE_TIES:
+        nodes, reqs = tie_case(key_lo, d1, d2)
+        out = oracle.place(nodes, None, 64, 1, reqs)
+        assert out["flags"][0] == R.PLACE_PLACED and out["domain_id"][0] == d1 and out["score"][0] == score
+        assert nodes["domain_id"][out["leader_node"][0]] == d1
+        assert out["flags"][1] == R.PLACE_UNSCHEDULABLE
+        assert out["flags"][2] == R.PLACE_PLACED and out["domain_id"][2] == d2  # what is left
