@@ -406,6 +406,7 @@ def run_ours(args):
         host_ms_step = getattr(timed, "host_ms", None)
         # each pass alone (same rotating inputs), for the per-kernel roofline
         ms_sweep, _ = timed(lambda i: sweep(i, t.flags), args.steps, 3)
+        ms_fused, _ = timed(lambda i: sweep(i, t.flags | R.SWEEP_SKIP_LWS_PASS), args.steps, 3)
         ms_scan, _ = timed(lambda i: sweep(i, t.flags | SCAN_ONLY), args.steps, 3)
         ms_group, _ = timed(lambda i: sweep(i, t.flags | GROUP_ONLY), args.steps, 3)
         ms_lws, _ = timed(lambda i: sweep(i, t.flags | LWS_ONLY), args.steps, 3)
@@ -438,27 +439,70 @@ def run_ours(args):
         keep.append(ten)
         h[name] = view
 
-    def e2e_step(extra_flags=0):
-        eng.sweep_lws_host(h["lws"], h["groups"], h["pst"], h["pid"], flags=t.flags | extra_flags,
-                           out=(h["lo"], h["go"]))
+    def e2e_step(extra_flags=0, engine=None):
+        en = engine or eng
+        en.sweep_lws_host(h["lws"], h["groups"], h["pst"], h["pid"], flags=t.flags | extra_flags,
+                          out=(h["lo"], h["go"]))
         if n_req and world == 1:
-            return eng.place_host(h["reqs"], h["occ"], 1)[0]
+            return en.place_host(h["reqs"], h["occ"], 1)[0]
         return None
 
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        pout_host = e2e_step()
-    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    # the same call when no pod was created or deleted since the last sweep: the 12-byte identity
-    # column stays resident, only the 4-byte state column (+ group and LWS rows) is re-sent
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step(R.SWEEP_REUSE_POD_IDENT)
-    e2e_state_s = (time.perf_counter() - t0) / args.e2e_steps
+    def wall(fn, reps):
+        for _ in range(3):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        return (time.perf_counter() - t0) / reps, r
+
+    # (1) the host entry points on pinned tables: every table is handed over every step; the engine
+    # uploads the state column and the group / LWS rows and reads the identity rows it needs (pods
+    # with an event) in place over PCIe
+    e2e_s, pout_host = wall(e2e_step, args.e2e_steps)
+    # (2) the same call when no pod was created or deleted since the last sweep: the identity
+    # column the engine holds from the previous call is reused
+    e2e_state_s, _ = wall(lambda: e2e_step(R.SWEEP_REUSE_POD_IDENT), args.e2e_steps)
+    # (3) every byte of every table uploaded (an engine created with LWSE_NO_ZERO_COPY=1)
+    e2e_full_s = None
+    if rank == 0:
+        os.environ["LWSE_NO_ZERO_COPY"] = "1"
+        eng_full = Engine(local_rank)
+        os.environ.pop("LWSE_NO_ZERO_COPY")
+        eng_full.upload_nodes(t.nodes, t.n_domains)
+        e2e_full_s, _ = wall(lambda: e2e_step(0, eng_full), args.e2e_steps)
+        eng_full.close()
+    # (4) resident tables (lwse_resident_*): the controller's informer cache feeds row patches —
+    # here 1 % of the pod state rows change per step — and reads back only the result rows that
+    # changed; the sweep still covers every row
+    resident = None
+    if rank == 0:
+        eng.resident_load(t.lws, t.groups, t.pod_state, t.pod_ident)
+        eng.resident_sweep(t.flags)
+        rng = np.random.Generator(np.random.PCG64(7))
+        n_patch = max(1, n_pod // 100)
+        patch_sets = []
+        for k in range(4):
+            rows = np.sort(rng.choice(n_pod, size=n_patch, replace=False)).astype(np.uint32)
+            vals = t.pod_state[rows].copy()
+            vals ^= np.where(rng.random(n_patch) < 0.5, R.POD_ANY_RESTART, 0).astype(np.uint32)  # restart counts move
+            patch_sets.append((rows, vals))
+        state = {"i": 0, "changed": 0}
+
+        def resident_step():
+            rows, vals = patch_sets[state["i"] % len(patch_sets)]
+            state["i"] += 1
+            eng.resident_patch(R.TABLE_POD_STATE, rows, vals)
+            out = eng.resident_sweep(t.flags)
+            state["changed"] = int(out[4]) + int(out[5])
+            return None
+
+        res_s, _ = wall(resident_step, max(args.e2e_steps, 20))
+        resident = {"value": n_grp / res_s, "unit": UNIT, "ms_per_step": res_s * 1e3,
+                    "h2d_bytes_per_step": int(n_patch * 8), "changed_result_rows_last_step": state["changed"],
+                    "api": "lwse_resident_patch + lwse_resident_sweep",
+                    "note": "tables resident on the device; per step 1 % of the pod state rows patched, full sweep, "
+                            "only changed result rows read back; rank 0, no placement round"}
     # the resident result must equal the host-path result
     same = (sets[0]["lo"].cpu().numpy().tobytes() == h["lo"].tobytes()
             and sets[0]["go"].cpu().numpy().tobytes() == h["go"].tobytes())
@@ -468,26 +512,32 @@ def run_ours(args):
         raise SystemExit("bench.py: resident and host-path results differ")
 
     # ---- max over ranks ----
-    stats = torch.tensor([ms_step, ms_group, e2e_s * 1e3, ms_scan, ms_lws, ms_place, ms_sweep], dtype=torch.float64,
-                         device=dev)
+    stats = torch.tensor([ms_step, ms_group, e2e_s * 1e3, ms_scan, ms_lws, ms_place, ms_sweep, ms_fused],
+                         dtype=torch.float64, device=dev)
     groups = torch.tensor([float(n_grp)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(groups, op=dist.ReduceOp.SUM)
-    ms_step, ms_group, e2e_ms, ms_scan, ms_lws, ms_place, ms_sweep = [float(x) for x in stats.tolist()]
+    ms_step, ms_group, e2e_ms, ms_scan, ms_lws, ms_place, ms_sweep, ms_fused = [float(x) for x in stats.tolist()]
     total_groups = float(groups.item())
 
     if rank == 0:
         peak, peak_src = measured_peak()
         ev = t.event_pods()
         words = (n_pod + 31) // 32
+        group_rows = n_grp * (R.GROUP_REC.itemsize + R.GROUP_OUT.itemsize) + n_lws * 16
+        fused_on = n_pod <= 512 * max(n_grp, 1)  # the engine's rule (lwse_lws_kernels.cu launch_lws_sweep)
         passes = {
-            # algorithmic bytes per launch: rows read once + rows written once
-            "pod_scan_kernel": (n_pod * 4 + 2 * words * 4, ms_scan),
-            "group_sweep_kernel": (n_grp * (R.GROUP_REC.itemsize + R.GROUP_OUT.itemsize) + n_lws * 16
-                                   + 2 * words * 4 + ev * (4 + R.POD_IDENT.itemsize), ms_group),
+            # algorithmic bytes per launch: rows read once + rows written once.  A sweep is the fused
+            # scan + group kernel followed by the LWS pass (small groups, no occupancy count); the
+            # two-kernel form (occupancy wanted, large groups) is timed beside it.
+            "group_fused_kernel": (n_pod * 4 + group_rows + ev * R.POD_IDENT.itemsize, ms_fused),
             "lws_sweep_kernel": (n_lws * (R.LWS_REC.itemsize + R.LWS_OUT.itemsize) + n_grp * 4, ms_lws),
+            "pod_scan_kernel": (n_pod * 4 + 2 * words * 4, ms_scan),
+            "group_sweep_kernel": (group_rows + 2 * words * 4 + ev * (4 + R.POD_IDENT.itemsize), ms_group),
         }
+        in_step = ("group_fused_kernel", "lws_sweep_kernel") if fused_on else (
+            "pod_scan_kernel", "group_sweep_kernel", "lws_sweep_kernel")
         traffic = None
         try:  # per-launch DRAM bytes of the committed ncu capture (profiles/r1_final_summary.md)
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
@@ -495,7 +545,7 @@ def run_ours(args):
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
-        dom = max(passes, key=lambda k: passes[k][1])
+        dom = max(in_step, key=lambda k: passes[k][1])
         dom_bytes, dom_ms = passes[dom]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         cpu_rate, cpu_s, cpu_reps = cpu_oracle_rate(t, 1)
@@ -514,20 +564,28 @@ def run_ours(args):
                                   "all-gather, placement)") if use_graph else "eager launches, programmatic dependent launch",
                        "step": "one lwse_reconcile_device call per tick: pod scan + group pass + LWS pass, placement round concurrently on the engine's side stream" if world == 1 else "pod scan + group pass + LWS pass, placement round (one all-gather) concurrently on a second stream",
                        "l2": f"inputs rotate over {copies} resident copies ({copies * algo_bytes / 1e6:.0f} MB > L2)"},
-            "e2e": {"value": total_groups / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "e2e": {"value": total_groups / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(h2d - t.pod_ident.nbytes + ev * R.POD_IDENT.itemsize),
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                     "api": "lwse_sweep_lws_host + lwse_place_host (pinned host tables)",
-                    "note": "every table re-uploaded every step (PCIe-bound)",
+                    "note": "every table handed over every step; state column, group and LWS rows uploaded, "
+                            f"identity rows of the {ev} event pods read in place over PCIe (12 B each counted)",
+                    "full_upload": {"value": n_grp * world / e2e_full_s if e2e_full_s else None,
+                                    "ms_per_step": e2e_full_s * 1e3 if e2e_full_s else None,
+                                    "h2d_bytes_per_step": h2d,
+                                    "note": "LWSE_NO_ZERO_COPY=1: identity column uploaded as well (PCIe-bound), rank 0"},
                     "state_only": {"value": n_grp * world / e2e_state_s, "ms_per_step": e2e_state_s * 1e3,
                                    "h2d_bytes_per_step": int(h2d - t.pod_ident.nbytes),
                                    "note": "LWSE_SWEEP_REUSE_POD_IDENT: pod identity column resident "
-                                           "(no pod created/deleted since the previous sweep), rank 0"}},
+                                           "(no pod created/deleted since the previous sweep), rank 0"},
+                    "resident": resident},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": (traffic or {}).get(dom),
                          "bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms, "peak_source": peak_src,
                          "passes": {k: {"bytes": int(v[0]), "ms": v[1], "gbs": v[0] / (v[1] * 1e-3) / 1e9,
-                                        "frac": v[0] / (v[1] * 1e-3) / 1e9 / peak} for k, v in passes.items()}},
+                                        "frac": v[0] / (v[1] * 1e-3) / 1e9 / peak, "in_step": k in in_step}
+                                    for k, v in passes.items()}},
             "ms_sweep_only": ms_sweep, "ms_placement_only": ms_place, "host_enqueue_ms_per_step": host_ms_step,
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"full {t.profile.name} step x{cpu_reps} ({cpu_s * 1e3:.1f} ms per step: sweep + placement spec round)"},

@@ -3,6 +3,7 @@
 // library: every sweep is a CUDA kernel launch or the call fails.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 #include <new>
@@ -21,7 +22,8 @@ struct SweepChangeLists {
   uint32_t* counts = nullptr;
 };
 int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
-                     void* scratch, int sm_count, cudaStream_t s, int* cuda_err, const SweepChangeLists* cl);
+                     void* scratch, int sm_count, cudaStream_t s, int* cuda_err, const SweepChangeLists* cl,
+                     uint32_t* d_event_count = nullptr);
 size_t lws_sweep_scratch_bytes(uint64_t n_pods);
 int launch_scatter(int row_words, void* table, uint64_t table_rows, const uint32_t* rows, const void* values,
                    uint32_t n, cudaStream_t s, int* cuda_err);
@@ -91,6 +93,8 @@ struct lwse_engine {
   uint64_t rn_pods = 0;
   bool r_loaded = false;
   uint32_t* h_counts = nullptr;      // pinned, 2 words
+  DevBuf h_counts_dev;               // event-pod count of the host entry point's scan
+  bool no_zero_copy = false;         // LWSE_NO_ZERO_COPY=1: always upload the identity column
   uint32_t place_calls = 0;          // selects the scratch half
   uint64_t place_geometry = 0;       // (n_reqs, n_namespaces, nodes, domains) the scratch was laid out for
   DevBuf ds, ds_roles, ds_revroles, ds_out, ds_role_out, ds_revrole_out;
@@ -224,6 +228,15 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
     delete e;
     return LWSE_ERR_CUDA;
   }
+  if (e->h_counts_dev.reserve(64) != cudaSuccess) {
+    (void)cudaGetLastError();
+    lwse_destroy(e);
+    return LWSE_ERR_OOM;
+  }
+  {
+    const char* v = getenv("LWSE_NO_ZERO_COPY");
+    e->no_zero_copy = v && atoi(v) != 0;
+  }
   *out = e;
   return LWSE_OK;
 }
@@ -240,7 +253,7 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
                       &e->ds_role_out, &e->ds_revrole_out, &e->sha_bytes, &e->sha_offsets, &e->sha_digests,
                       &e->r_lws, &e->r_groups, &e->r_pst, &e->r_pid, &e->r_lws_out, &e->r_group_out, &e->r_scan,
                       &e->r_chg_lws_rows, &e->r_chg_lws_out, &e->r_chg_grp_rows, &e->r_chg_grp_out, &e->r_counts,
-                      &e->r_patch_rows, &e->r_patch_vals};
+                      &e->r_patch_rows, &e->r_patch_vals, &e->h_counts_dev};
     for (DevBuf* b : bufs) b->release();
     if (e->h_rounds) cudaFreeHost(e->h_rounds);
     if (e->h_counts) cudaFreeHost(e->h_counts);
@@ -353,14 +366,6 @@ LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* h) {
   }
   if (b_lws) LWSE_CUDA(e, cudaMemcpyAsync(e->lws.p, h->lws, b_lws, cudaMemcpyHostToDevice, s));
   if (b_grp) LWSE_CUDA(e, cudaMemcpyAsync(e->groups.p, h->groups, b_grp, cudaMemcpyHostToDevice, s));
-  if (b_pst) {
-    LWSE_CUDA(e, cudaMemcpyAsync(e->pod_state.p, h->pod_state, b_pst, cudaMemcpyHostToDevice, s));
-    // the identity column only changes when pods are created or deleted
-    const bool reuse = (h->flags & LWSE_SWEEP_REUSE_POD_IDENT) && e->ident_rows == h->n_pods && !ident_moved;
-    if (!reuse) LWSE_CUDA(e, cudaMemcpyAsync(e->pod_ident.p, h->pod_ident, b_pid, cudaMemcpyHostToDevice, s));
-    e->ident_rows = h->n_pods;
-  }
-
   lwse_lws_tables d = *h;
   d.lws = (const lwse_lws_rec*)e->lws.p;
   d.groups = (const lwse_group_rec*)e->groups.p;
@@ -370,10 +375,61 @@ LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* h) {
   d.group_out = (lwse_group_out*)e->group_out.p;
   d.node_occupancy = want_occ ? (uint32_t*)e->occupancy.p : nullptr;
   int cuda_err = 0;
-  int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes,
-                                        e->scan_scratch.p, e->sm_count, s, &cuda_err, nullptr);
-  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
-  e->launches += (uint64_t)launched;
+  bool swept = false;
+  if (b_pst) {
+    LWSE_CUDA(e, cudaMemcpyAsync(e->pod_state.p, h->pod_state, b_pst, cudaMemcpyHostToDevice, s));
+    // The identity column (12 B / pod, three quarters of the input bytes) is only read for pods
+    // with a restart / deletion event.  It is left out of the upload
+    //  - when the caller says it did not change (LWSE_SWEEP_REUSE_POD_IDENT), or
+    //  - when the caller's buffer is pinned, mapped host memory and few pods have an event: the
+    //    group pass then reads those rows in place over PCIe.  The scan runs first, counts the
+    //    event pods, and the count decides (a 64-byte PCIe read per visited pod against 12 B / pod
+    //    in bulk).
+    const bool reuse = (h->flags & LWSE_SWEEP_REUSE_POD_IDENT) && e->ident_rows == h->n_pods && !ident_moved;
+    const void* mapped = nullptr;
+    if (!reuse && !e->no_zero_copy) {
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, h->pod_ident) == cudaSuccess && attr.type == cudaMemoryTypeHost)
+        mapped = attr.devicePointer;
+      else
+        (void)cudaGetLastError();
+    }
+    if (mapped && h->n_groups && !(h->flags & (LWSE_SWEEP_SKIP_POD_SCAN | LWSE_SWEEP_SKIP_GROUP_PASS))) {
+      LWSE_CUDA(e, cudaMemsetAsync(e->h_counts_dev.p, 0, 4, s));
+      lwse_lws_tables scan = d;
+      scan.flags |= LWSE_SWEEP_SKIP_GROUP_PASS | LWSE_SWEEP_SKIP_LWS_PASS;
+      int launched = lwse::launch_lws_sweep(&scan, (const lwse_node_rec*)e->nodes.p, e->n_nodes, e->scan_scratch.p,
+                                            e->sm_count, s, &cuda_err, nullptr, (uint32_t*)e->h_counts_dev.p);
+      if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+      e->launches += (uint64_t)launched;
+      LWSE_CUDA(e, cudaMemcpyAsync(e->h_counts, e->h_counts_dev.p, 4, cudaMemcpyDeviceToHost, s));
+      LWSE_CUDA(e, cudaStreamSynchronize(s));
+      const uint64_t events = e->h_counts[0];
+      if (events * 64u <= b_pid / 2u) {
+        d.pod_ident = (const lwse_pod_ident*)mapped;
+        e->ident_rows = ~0ull;  // the device copy is stale now
+      } else {
+        LWSE_CUDA(e, cudaMemcpyAsync(e->pod_ident.p, h->pod_ident, b_pid, cudaMemcpyHostToDevice, s));
+        e->ident_rows = h->n_pods;
+      }
+      lwse_lws_tables rest = d;
+      rest.flags |= LWSE_SWEEP_SKIP_POD_SCAN;
+      launched = lwse::launch_lws_sweep(&rest, (const lwse_node_rec*)e->nodes.p, e->n_nodes, e->scan_scratch.p,
+                                        e->sm_count, s, &cuda_err, nullptr);
+      if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+      e->launches += (uint64_t)launched;
+      swept = true;
+    } else {
+      if (!reuse) LWSE_CUDA(e, cudaMemcpyAsync(e->pod_ident.p, h->pod_ident, b_pid, cudaMemcpyHostToDevice, s));
+      e->ident_rows = h->n_pods;
+    }
+  }
+  if (!swept) {
+    int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes,
+                                          e->scan_scratch.p, e->sm_count, s, &cuda_err, nullptr);
+    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+    e->launches += (uint64_t)launched;
+  }
 
   if (b_lo) LWSE_CUDA(e, cudaMemcpyAsync(h->lws_out, e->lws_out.p, b_lo, cudaMemcpyDeviceToHost, s));
   if (b_go) LWSE_CUDA(e, cudaMemcpyAsync(h->group_out, e->group_out.p, b_go, cudaMemcpyDeviceToHost, s));

@@ -38,6 +38,8 @@ struct PodScanArgs {
   uint32_t* occupancy;  // nullable: scheduled pods per node
   uint64_t n_pods;
   uint32_t n_nodes;
+  uint32_t* event_count;  // nullable: += pods with an event bit (the host entry point sizes its
+                          // identity-column transfer with it)
 };
 
 __device__ __forceinline__ bool pod_has_event(uint32_t bits) {
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(256) pod_scan_kernel(const PodScanArgs a) {
   const uint4* vec = reinterpret_cast<const uint4*>(a.state);
   pdl_launch_dependents();
   bool waited = false;
+  uint32_t events = 0;
   for (uint64_t base = warp * kPodsPerChunk; base < a.n_pods; base += n_warps * kPodsPerChunk) {
     uint4 v[U];
 #pragma unroll
@@ -118,8 +121,13 @@ __global__ void __launch_bounds__(256) pod_scan_kernel(const PodScanArgs a) {
       if ((lane & 7u) == 0u && w < n_words) {
         a.pending_bits[w] = wp;
         a.event_bits[w] = we;
+        events += __popc(we);
       }
     }
+  }
+  if (a.event_count != nullptr) {
+    events = __reduce_add_sync(0xFFFFFFFFu, events);
+    if (lane == 0 && events) atomicAdd(a.event_count, events);
   }
 }
 
@@ -802,7 +810,8 @@ struct SweepChangeLists {  // device pointers; all null = off
 };
 
 int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
-                     void* scratch, int sm_count, cudaStream_t s, int* cuda_err, const SweepChangeLists* cl) {
+                     void* scratch, int sm_count, cudaStream_t s, int* cuda_err, const SweepChangeLists* cl,
+                     uint32_t* d_event_count) {
   *cuda_err = 0;
   int launches = 0;
   cudaError_t e = cudaSuccess;
@@ -819,7 +828,7 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
     return v && atoi(v) != 0;
   }();
   // scan + group pass in one kernel: small groups, no occupancy count, both passes wanted
-  const bool fused = group_pass && w == 1 && !t->node_occupancy && !no_fuse &&
+  const bool fused = group_pass && w == 1 && !t->node_occupancy && !no_fuse && !d_event_count &&
                      !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN);
   if (fused) {
     GroupSweepArgs a{t->lws,   t->groups, t->pod_state, t->pod_ident, nullptr, nullptr, d_nodes,
@@ -835,7 +844,7 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
     if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
   }
   if (!fused && t->n_pods && (t->n_groups || t->node_occupancy) && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN)) {
-    PodScanArgs a{t->pod_state, pending_bits, event_bits, t->node_occupancy, t->n_pods, n_nodes};
+    PodScanArgs a{t->pod_state, pending_bits, event_bits, t->node_occupancy, t->n_pods, n_nodes, d_event_count};
     // one chunk per warp: the kernel is a few microseconds long, so let the
     // hardware CTA scheduler balance it instead of a persistent grid-stride loop
     const uint64_t chunks = (t->n_pods + 128ull * kScanUnroll - 1) / (128ull * kScanUnroll);

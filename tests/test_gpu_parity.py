@@ -280,3 +280,34 @@ def test_fused_pass_with_scattered_pod_ranges(engine):
     got = engine.sweep_lws_host(t.lws, grp, pst, pid, flags=t.flags, want_occupancy=False)
     assert_same(got[0], want[0], "lws_out")
     assert_same(got[1], want[1], "group_out")
+
+
+@pytest.mark.parametrize("p_event", [0.002, 0.6])
+def test_host_entry_reads_pinned_identity_rows_in_place(engine, p_event):
+    """Pinned, mapped host tables: the identity column is not uploaded when few pods have an
+    event (the group pass reads those rows over PCIe); with many events it is uploaded after the
+    scan has counted them.  Same results either way."""
+    import torch
+    import oracle
+
+    p = synth.profile("C3", 0.05)
+    p.p_restarted = p_event
+    t = synth.make(p, seed=31)
+    keep = []
+
+    def pinned(a):
+        ten = torch.empty(max(a.nbytes, 16), dtype=torch.uint8).pin_memory()
+        view = ten.numpy()[: a.nbytes].view(a.dtype)
+        view[...] = a
+        keep.append(ten)
+        return view
+
+    lws, grp, pst, pid = pinned(t.lws), pinned(t.groups), pinned(t.pod_state), pinned(t.pod_ident)
+    engine.upload_nodes(t.nodes, t.n_domains)
+    want = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, flags=t.flags, want_occupancy=True)
+    for occupancy in (True, False):
+        got = engine.sweep_lws_host(lws, grp, pst, pid, flags=t.flags, want_occupancy=occupancy)
+        assert_same(got[0], want[0], "lws_out")
+        assert_same(got[1], want[1], "group_out")
+        if occupancy:
+            assert np.array_equal(got[2], want[2])
