@@ -1,4 +1,7 @@
-// LWS sweep kernels (sm_100a).  One sweep = three launches on one stream:
+// LWS sweep kernels (sm_100a).  One sweep = two launches on one stream when groups are small
+// and no per-node pod count is wanted — group_fused_kernel (the pod scan and the group pass of
+// 256 consecutive groups in one CTA, bitmaps in shared memory) and lws_sweep_kernel — and
+// three otherwise:
 //
 //   pod_scan_kernel<U>   pod-centric streaming pass over the 4-byte pod state
 //                        column: every lane takes U pods with coalesced loads
