@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU placement step: 'peer' = lwse_exchange_* (peer stores over NVLink, no "
+                         "collective library on the data path), 'nccl' = one NCCL all-gather per step")
     ap.add_argument("--graph", action="store_true",
                     help="replay CUDA graphs instead of eager launches (measured slower: programmatic "
                          "dependent launch does not span graph replays)")
@@ -277,6 +280,8 @@ def run_ours(args):
         send = torch.from_numpy(D.pack_part(occ_host, reqs, req_cap)).to(dev)  # [occupancy | requests]
         gathered = torch.empty(world * part_stride, dtype=torch.uint8, device=dev)
         d_pout = torch.empty(max(world * req_cap, 1) * R.PLACE_OUT.itemsize, dtype=torch.uint8, device=dev)
+        if args.collective == "peer":
+            D.connect_exchange(eng, req_cap, world, rank, device=dev)
     else:
         d_pout = torch.empty(max(n_req, 1) * R.PLACE_OUT.itemsize, dtype=torch.uint8, device=dev)
 
@@ -317,9 +322,14 @@ def run_ours(args):
                                          s["go"], None, flags=flags)
         return descs[k]
 
+    peer = world > 1 and place_on and args.collective == "peer"
+
     def step(i, flags):
         if place_on and world == 1:
             eng.reconcile_device(desc(i, flags), d_reqs, n_req, d_occ, 1, d_pout, stream=sptr)
+            return
+        if peer:  # one C call per tick: push part to the peers, wait for theirs, placement ∥ sweep
+            eng.reconcile_exchanged_device(desc(i, flags), send, 1, d_pout, stream=sptr)
             return
         if place_on:
             pstream.wait_stream(stream)  # fork: placement starts with the sweep …
@@ -329,6 +339,9 @@ def run_ours(args):
             stream.wait_stream(pstream)  # … join: the step ends when both are done
 
     def place_alone():
+        if peer:
+            eng.reconcile_exchanged_device(None, send, 1, d_pout, stream=sptr)
+            return
         pstream.wait_stream(stream)
         place()
         stream.wait_stream(pstream)
@@ -339,7 +352,9 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    use_graph = args.graph or world > 1  # multi-GPU: the eager step is bound by Python/NCCL launch overhead
+    # NCCL form: the eager step is bound by Python/NCCL launch overhead, so it is replayed as a graph;
+    # the peer-exchange form is one C call per tick and runs eagerly (its step number is a kernel argument)
+    use_graph = (args.graph or (world > 1 and not peer)) and not peer
 
     def timed(fn, steps, warmup):
         """ms per call of fn(i) over `steps` calls.  Single GPU: the calls for each rotating input
@@ -412,9 +427,13 @@ def run_ours(args):
         ms_lws, _ = timed(lambda i: sweep(i, t.flags | LWS_ONLY), args.steps, 3)
         ms_place = timed(lambda i: place_alone(), args.steps, 3)[0] if place_on else 0.0
         # keep the GPU under the same load long enough for nvidia-smi to sample clocks
-        t_end = time.perf_counter() + 1.0
+        # (a fixed number of steps, the same on every rank: the peer exchange needs matching calls)
+        n_load = torch.tensor([ms_step], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(n_load, op=dist.ReduceOp.MAX)
+        n_load = int(min(max(1000.0 / max(float(n_load.item()), 1e-3), 2000), 60000)) // 100
         i = 0
-        while time.perf_counter() < t_end:
+        for _ in range(n_load):
             for _ in range(100):
                 step(i, t.flags)
                 i += 1
@@ -447,10 +466,13 @@ def run_ours(args):
             return en.place_host(h["reqs"], h["occ"], 1)[0]
         return None
 
-    def wall(fn, reps):
+    def wall(fn, reps, all_ranks=True):
         for _ in range(3):
             fn()
-        barrier()
+        if all_ranks:
+            barrier()
+        else:  # a rank-0-only measurement must not enter a collective
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(reps):
             r = fn()
@@ -470,7 +492,7 @@ def run_ours(args):
         eng_full = Engine(local_rank)
         os.environ.pop("LWSE_NO_ZERO_COPY")
         eng_full.upload_nodes(t.nodes, t.n_domains)
-        e2e_full_s, _ = wall(lambda: e2e_step(0, eng_full), args.e2e_steps)
+        e2e_full_s, _ = wall(lambda: e2e_step(0, eng_full), args.e2e_steps, all_ranks=False)
         eng_full.close()
     # (4) resident tables (lwse_resident_*): the controller's informer cache feeds row patches —
     # here 1 % of the pod state rows change per step — and reads back only the result rows that
@@ -497,7 +519,7 @@ def run_ours(args):
             state["changed"] = int(out[4]) + int(out[5])
             return None
 
-        res_s, _ = wall(resident_step, max(args.e2e_steps, 20))
+        res_s, _ = wall(resident_step, max(args.e2e_steps, 20), all_ranks=False)
         resident = {"value": n_grp / res_s, "unit": UNIT, "ms_per_step": res_s * 1e3,
                     "h2d_bytes_per_step": int(n_patch * 8), "changed_result_rows_last_step": state["changed"],
                     "api": "lwse_resident_patch + lwse_resident_sweep",
@@ -511,6 +533,11 @@ def run_ours(args):
     if not same:
         raise SystemExit("bench.py: resident and host-path results differ")
 
+    if peer:  # a timed-out wait (a rank fell behind by more than 2 s or is gone) invalidates the run
+        xerr = torch.tensor([eng.exchange_status()], device=dev)
+        dist.all_reduce(xerr, op=dist.ReduceOp.MAX)
+        if int(xerr.item()) != 0:
+            raise SystemExit(f"bench.py[{rank}]: a peer-exchange wait timed out")
     # ---- max over ranks ----
     stats = torch.tensor([ms_step, ms_group, e2e_s * 1e3, ms_scan, ms_lws, ms_place, ms_sweep, ms_fused],
                          dtype=torch.float64, device=dev)
@@ -559,10 +586,13 @@ def run_ours(args):
             "dtype": "int32/u64 (integer compare)", "data": "synthetic",
             "config": {**t.describe(), "parallelism": f"shard-by-uid x{world}",
                        "placement": {"requests_per_rank": int(n_req), "rounds": rounds,
-                                     "collective": "1 all_gather/step" if (world > 1 and place_on) else "none"},
+                                     "collective": ("none: parts pushed to the peers with NVLink peer stores + flags (lwse_exchange_*)"
+                                                    if peer else "1 NCCL all_gather/step") if (world > 1 and place_on) else "none"},
                        "launch": ("CUDA graph replay (one graph per step: sweep kernels with programmatic edges, "
                                   "all-gather, placement)") if use_graph else "eager launches, programmatic dependent launch",
-                       "step": "one lwse_reconcile_device call per tick: pod scan + group pass + LWS pass, placement round concurrently on the engine's side stream" if world == 1 else "pod scan + group pass + LWS pass, placement round (one all-gather) concurrently on a second stream",
+                       "step": ("one lwse_reconcile_device call per tick: fused pod scan + group pass, LWS pass, placement round concurrently on the engine's side stream" if world == 1 else
+                                "one lwse_reconcile_exchanged_device call per tick and rank: sweep of the shard; on the side stream the part push to the peers, the wait for theirs and the placement round over all parts" if peer else
+                                "sweep of the shard, placement round (one all-gather) concurrently on a second stream"),
                        "l2": f"inputs rotate over {copies} resident copies ({copies * algo_bytes / 1e6:.0f} MB > L2)"},
             "e2e": {"value": total_groups / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(h2d - t.pod_ident.nbytes + ev * R.POD_IDENT.itemsize),
@@ -595,6 +625,8 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()  # no rank frees its exchange buffer while a peer may still push into it
+        eng.close()
         dist.destroy_process_group()
 
 

@@ -445,6 +445,37 @@ LWSE_API int lwse_reconcile_device(lwse_engine* e, const lwse_lws_tables* d, con
                                    lwse_place_out* d_place_out, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* Peer exchange: the multi-GPU placement step without a collective library  */
+/* ------------------------------------------------------------------------- */
+#define LWSE_MAX_RANKS 16u
+#define LWSE_IPC_HANDLE_BYTES 64u /* sizeof(cudaIpcMemHandle_t) */
+
+/* One process per GPU of one node.  Every rank creates its exchange buffer (room for
+ * `world` parts of [n_nodes occupancy counters | reqs_per_part request rows], twice) and
+ * gets an IPC handle for it; the caller all-gathers the handles (any transport — they are
+ * 64 opaque bytes) and hands all of them to lwse_exchange_connect, which maps the peers'
+ * buffers over NVLink.  lwse_upload_nodes must have been called (the layout depends on
+ * n_nodes); one exchange per engine. */
+LWSE_API int lwse_exchange_create(lwse_engine* e, uint32_t reqs_per_part, uint32_t world, uint32_t rank,
+                                  void* handle_out /* LWSE_IPC_HANDLE_BYTES */);
+LWSE_API int lwse_exchange_connect(lwse_engine* e, const void* handles /* world x LWSE_IPC_HANDLE_BYTES */);
+/* bytes of one part: align16(n_nodes * 4) + reqs_per_part * sizeof(lwse_place_req) */
+LWSE_API uint64_t lwse_exchange_part_bytes(const lwse_engine* e);
+
+/* A reconcile tick of one shard (see lwse_reconcile_device): `d_local_part` — this rank's
+ * [occupancy | request rows (unused rows: leader_node = LWSE_NONE, size = 0)] in device
+ * memory — is pushed into every peer's buffer with peer stores and a per-source flag is
+ * raised there; the same kernel waits for all sources' flags of this step; then the placement
+ * round runs over the gathered parts exactly as lwse_place_gathered_device does (d_place_out:
+ * world * reqs_per_part rows; every rank computes the same answer and keeps its own rows).
+ * All of it on the engine's side stream, concurrently with the sweep of `d` on `stream`
+ * (d == NULL: placement step only).  Every rank must call this the same number of times. */
+LWSE_API int lwse_reconcile_exchanged_device(lwse_engine* e, const lwse_lws_tables* d, const void* d_local_part,
+                                             uint32_t n_namespaces, lwse_place_out* d_place_out, void* stream);
+/* *error_out = 1 if a wait for the peers ever timed out (2 s; a rank is gone).  Synchronizes. */
+LWSE_API int lwse_exchange_status(lwse_engine* e, uint32_t* error_out);
+
+/* ------------------------------------------------------------------------- */
 /* DisaggregatedSet sweep                                                    */
 /* ------------------------------------------------------------------------- */
 #define LWSE_DS_MAX_ROLES 10u /* api/disaggregatedset/v1: 2..10 roles             */

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 #include <new>
@@ -40,6 +41,10 @@ int launch_ds_sweep(const lwse_ds_tables* t, int sm_count, cudaStream_t s, int* 
 // lwse_sha1_kernels.cu
 int launch_sha1(const uint8_t* d_bytes, const uint32_t* d_offsets, uint32_t n, uint8_t* d_digests,
                 int sm_count, cudaStream_t s, int* cuda_err);
+// lwse_exchange_kernels.cu
+int launch_exchange_push(const void* d_local_part, uint8_t* const* d_peer_base, void* d_local_base,
+                         uint64_t part_bytes, uint64_t part_stride, uint64_t half_bytes, uint64_t flags_offset,
+                         uint64_t step, uint32_t world, uint32_t rank, cudaStream_t s, int* cuda_err);
 }  // namespace lwse
 
 const uint32_t* g_last_place_counters = nullptr;
@@ -100,6 +105,12 @@ struct lwse_engine {
   DevBuf ds, ds_roles, ds_revroles, ds_out, ds_role_out, ds_revrole_out;
   DevBuf sha_bytes, sha_offsets, sha_digests;
   uint32_t* h_rounds = nullptr;  // pinned
+  // peer exchange of the multi-GPU placement step (lwse_exchange_*)
+  DevBuf xch, xch_peers_dev;
+  void* xch_peer[LWSE_MAX_RANKS] = {};
+  uint32_t xch_world = 0, xch_rank = 0, xch_reqs_per_part = 0;
+  uint64_t xch_stride = 0, xch_reqs_off = 0, xch_half = 0, xch_flags_off = 0, xch_step = 0;
+  bool xch_connected = false;
 };
 
 namespace {
@@ -246,6 +257,10 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
   {
     DeviceGuard guard(e->device);
     cudaStreamSynchronize(e->stream);
+    for (uint32_t p = 0; p < e->xch_world; p++)
+      if (e->xch_connected && p != e->xch_rank && e->xch_peer[p]) cudaIpcCloseMemHandle(e->xch_peer[p]);
+    e->xch.release();
+    e->xch_peers_dev.release();
     DevBuf* bufs[] = {&e->nodes,      &e->dom_first, &e->node_order, &e->node_pos, &e->lws,         &e->groups,     &e->pod_state,   &e->pod_ident,
                       &e->scan_scratch, &e->lws_out,
                       &e->group_out,  &e->occupancy,   &e->place_reqs, &e->place_out,   &e->place_occ,
@@ -670,6 +685,108 @@ LWSE_API int lwse_place_gathered_device(lwse_engine* e, const void* d_parts, uin
   return place_common(e, reinterpret_cast<const lwse_place_req*>(base + reqs_offset_bytes), n_parts * reqs_per_part,
                       reinterpret_cast<const uint32_t*>(base), n_namespaces, d_out, rounds_out, stream, n_parts,
                       reqs_per_part, part_stride_bytes);
+}
+
+// ---------------------------------------------------------------------------
+// Peer exchange (multi-GPU placement step)
+// ---------------------------------------------------------------------------
+LWSE_API int lwse_exchange_create(lwse_engine* e, uint32_t reqs_per_part, uint32_t world, uint32_t rank,
+                                  void* handle_out) {
+  if (!e || !handle_out || world == 0 || world > LWSE_MAX_RANKS || rank >= world) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (e->n_nodes == 0 || e->n_domains == 0) return LWSE_ERR_NOT_READY;
+  if (e->xch_world) return LWSE_ERR_UNSUPPORTED;  // one exchange per engine
+  DeviceGuard guard(e->device);
+  const uint64_t reqs_off = ((uint64_t)e->n_nodes * 4u + 15u) / 16u * 16u;
+  const uint64_t stride = reqs_off + (uint64_t)reqs_per_part * sizeof(lwse_place_req);
+  const uint64_t half = ((uint64_t)world * stride + 255u) / 256u * 256u;
+  const uint64_t flags_off = 2u * half;
+  const uint64_t total = flags_off + (uint64_t)world * 8u + 64u;
+  LWSE_CUDA(e, e->xch.reserve(total));
+  LWSE_CUDA(e, cudaMemset(e->xch.p, 0, total));
+  LWSE_CUDA(e, e->xch_peers_dev.reserve(sizeof(void*) * LWSE_MAX_RANKS));
+  cudaIpcMemHandle_t h;
+  LWSE_CUDA(e, cudaIpcGetMemHandle(&h, e->xch.p));
+  static_assert(sizeof(h) == LWSE_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, sizeof(h));
+  e->xch_world = world;
+  e->xch_rank = rank;
+  e->xch_reqs_per_part = reqs_per_part;
+  e->xch_stride = stride;
+  e->xch_reqs_off = reqs_off;
+  e->xch_half = half;
+  e->xch_flags_off = flags_off;
+  e->xch_step = 0;
+  e->xch_connected = false;
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_exchange_connect(lwse_engine* e, const void* handles) {
+  if (!e || !handles) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->xch_world || e->xch_connected) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  for (uint32_t p = 0; p < e->xch_world; p++) {
+    if (p == e->xch_rank) {
+      e->xch_peer[p] = e->xch.p;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const uint8_t*>(handles) + (size_t)p * LWSE_IPC_HANDLE_BYTES, sizeof(h));
+    LWSE_CUDA(e, cudaIpcOpenMemHandle(&e->xch_peer[p], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  LWSE_CUDA(e, cudaMemcpy(e->xch_peers_dev.p, e->xch_peer, sizeof(void*) * e->xch_world, cudaMemcpyHostToDevice));
+  e->xch_connected = true;
+  return LWSE_OK;
+}
+
+LWSE_API uint64_t lwse_exchange_part_bytes(const lwse_engine* e) { return e ? e->xch_stride : 0; }
+
+// One reconcile tick of a multi-GPU shard: as lwse_reconcile_device, with the placement round
+// solved over every rank's part — this rank's part is pushed to all peers first.
+LWSE_API int lwse_reconcile_exchanged_device(lwse_engine* e, const lwse_lws_tables* t, const void* d_local_part,
+                                             uint32_t n_namespaces, lwse_place_out* d_place_out, void* stream) {
+  if (!e || !d_local_part || !aligned16(d_local_part)) return LWSE_ERR_INVALID_ARG;
+  int rc = t ? check_lws_tables(t) : LWSE_OK;
+  if (rc != LWSE_OK) return rc;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->xch_connected) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  LWSE_CUDA(e, cudaEventRecord(e->ev_fork, s));
+  LWSE_CUDA(e, cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+  const uint64_t step = ++e->xch_step;
+  int cuda_err = 0;
+  int launched = lwse::launch_exchange_push(d_local_part, (uint8_t* const*)e->xch_peers_dev.p, e->xch.p, e->xch_stride,
+                                            e->xch_stride, e->xch_half, e->xch_flags_off, step, e->xch_world,
+                                            e->xch_rank, e->side_stream, &cuda_err);
+  if (launched < 0) {
+    rc = fail_cuda(e, (cudaError_t)cuda_err);
+  } else {
+    e->launches += (uint64_t)launched;
+    const uint8_t* half = static_cast<const uint8_t*>(e->xch.p) + (step & 1ull) * e->xch_half;
+    rc = place_locked(e, reinterpret_cast<const lwse_place_req*>(half + e->xch_reqs_off),
+                      e->xch_world * e->xch_reqs_per_part, reinterpret_cast<const uint32_t*>(half), n_namespaces,
+                      d_place_out, nullptr, e->side_stream, e->xch_world, e->xch_reqs_per_part, e->xch_stride);
+  }
+  if (rc == LWSE_OK && t) rc = sweep_device_locked(e, t, s);
+  cudaError_t je = cudaEventRecord(e->ev_join, e->side_stream);
+  if (je == cudaSuccess) je = cudaStreamWaitEvent(s, e->ev_join, 0);
+  if (rc != LWSE_OK) return rc;
+  if (je != cudaSuccess) return fail_cuda(e, je);
+  return LWSE_OK;
+}
+
+// 0 = every wait so far saw all peers; 1 = a wait timed out (a peer is gone).  Synchronizes.
+LWSE_API int lwse_exchange_status(lwse_engine* e, uint32_t* error_out) {
+  if (!e || !error_out) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->xch_world) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  LWSE_CUDA(e, cudaDeviceSynchronize());
+  LWSE_CUDA(e, cudaMemcpy(error_out, static_cast<const uint8_t*>(e->xch.p) + e->xch_flags_off + (uint64_t)e->xch_world * 8u + 4u,
+                          4, cudaMemcpyDeviceToHost));
+  return LWSE_OK;
 }
 
 // Tuning aid (not part of lwse.h): phase timestamps of the most recent placement kernel.

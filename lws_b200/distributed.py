@@ -51,6 +51,23 @@ def unpack_parts(gathered: np.ndarray, world: int, n_nodes: int, cap: int):
     return occ, reqs
 
 
+def connect_exchange(engine, reqs_per_part: int, world: int, rank: int, device=None) -> None:
+    """Set up the engine's peer exchange (``lwse_exchange_*``): create the local buffer, all-gather the
+    64-byte IPC handles with ``torch.distributed`` (setup only — the data path uses peer stores, not a
+    collective), map every peer's buffer.  Call on every rank after ``upload_nodes``."""
+    import torch
+    import torch.distributed as dist
+
+    handle = engine.exchange_create(reqs_per_part, world, rank)
+    mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8)
+    if device is not None:
+        mine = mine.to(device)
+    every = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    engine.exchange_connect(b"".join(bytes(t.cpu().numpy().tobytes()) for t in every))
+    dist.barrier()  # nobody pushes before every buffer is mapped everywhere
+
+
 def shard_index(uid_hash: np.ndarray, world: int) -> np.ndarray:
     """lwse_shard_of for a whole column."""
     if world <= 1:
@@ -98,4 +115,4 @@ def shard_lws_tables(lws, groups, pod_state, pod_ident, world: int):
     return out
 
 
-__all__ = ["part_layout", "pad_requests", "pack_part", "unpack_parts", "shard_index", "shard_lws_tables", "shard_of"]
+__all__ = ["connect_exchange", "part_layout", "pad_requests", "pack_part", "unpack_parts", "shard_index", "shard_lws_tables", "shard_of"]

@@ -51,6 +51,14 @@ SYMBOLS = {
         [C.c_void_p, C.POINTER(R.LwsTables), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p],
         C.c_int,
     ),
+    "lwse_exchange_create": ([C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p], C.c_int),
+    "lwse_exchange_connect": ([C.c_void_p, C.c_void_p], C.c_int),
+    "lwse_exchange_part_bytes": ([C.c_void_p], C.c_uint64),
+    "lwse_reconcile_exchanged_device": (
+        [C.c_void_p, C.POINTER(R.LwsTables), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p],
+        C.c_int,
+    ),
+    "lwse_exchange_status": ([C.c_void_p, C.POINTER(C.c_uint32)], C.c_int),
     "lwse_sweep_ds_host": ([C.c_void_p, C.POINTER(R.DsTables)], C.c_int),
     "lwse_sweep_ds_device": ([C.c_void_p, C.POINTER(R.DsTables), C.c_void_p], C.c_int),
     "lwse_group_keys_host": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p], C.c_int),
@@ -177,6 +185,35 @@ class Engine:
         side stream, joined back into ``stream``.  Enqueue only, no synchronize."""
         self._check(lib().lwse_reconcile_device(self._h, C.byref(tables), R.ptr(d_reqs), n_reqs, R.ptr(d_occupancy),
                                                 n_namespaces, R.ptr(d_place_out), stream))
+
+    # --------------------------------------------------------- peer exchange
+    def exchange_create(self, reqs_per_part: int, world: int, rank: int) -> bytes:
+        """Allocate this rank's exchange buffer → its 64-byte IPC handle (all-gather these)."""
+        h = (C.c_uint8 * 64)()
+        self._check(lib().lwse_exchange_create(self._h, reqs_per_part, world, rank, h))
+        return bytes(h)
+
+    def exchange_connect(self, handles: bytes):
+        """``handles``: every rank's handle, concatenated in rank order."""
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        self._check(lib().lwse_exchange_connect(self._h, buf))
+
+    @property
+    def exchange_part_bytes(self) -> int:
+        return int(lib().lwse_exchange_part_bytes(self._h))
+
+    def reconcile_exchanged_device(self, tables, d_local_part, n_namespaces, d_place_out, stream=None):
+        """One tick of a shard: push this rank's [occupancy | requests] part to every peer over
+        NVLink, wait for theirs, placement round over all parts — on the side stream, concurrently
+        with the sweep of ``tables`` (None: placement step only).  Enqueue only."""
+        self._check(lib().lwse_reconcile_exchanged_device(
+            self._h, C.byref(tables) if tables is not None else None, R.ptr(d_local_part), n_namespaces,
+            R.ptr(d_place_out), stream))
+
+    def exchange_status(self) -> int:
+        err = C.c_uint32(0)
+        self._check(lib().lwse_exchange_status(self._h, C.byref(err)))
+        return err.value
 
     # ------------------------------------------------------- resident tables
     def resident_load(self, lws, groups, pod_state, pod_ident):

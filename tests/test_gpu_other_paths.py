@@ -238,3 +238,22 @@ def test_placement_equal_domain_scores_keep_the_lower_domain(engine):
         got, _ = engine.place_host(reqs, None, 1)
         same(got, oracle.place(nodes, None, 64, 1, reqs), "place_out")
         assert got["domain_id"][0] == d1 and got["score"][0] == score
+
+
+def test_peer_exchange_placement_step_on_two_gpus():
+    """lwse_exchange_* / lwse_reconcile_exchanged_device: needs two GPUs of one node (skipped on a
+    one-GPU box); the check itself is tests/multi_gpu/exchange_check.py under torchrun."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+         "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multi_gpu", "exchange_check.py")],
+        capture_output=True, text=True, timeout=300)
+    assert "EXCHANGE_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
