@@ -34,7 +34,8 @@ int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, cons
                  const lwse_place_req* d_reqs, uint32_t n_reqs, const uint32_t* d_occupancy,
                  uint32_t n_namespaces, lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes,
                  uint32_t* h_rounds, int sm_count, cudaStream_t s, int* cuda_err, uint32_t call_index,
-                 bool fresh, uint32_t n_parts, uint32_t reqs_per_part, uint64_t part_stride_bytes);
+                 bool fresh, uint32_t n_parts, uint32_t reqs_per_part, uint64_t part_stride_bytes,
+                 uint32_t* h_unpinned);
 size_t place_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces);
 // lwse_ds_kernels.cu
 int launch_ds_sweep(const lwse_ds_tables* t, int sm_count, cudaStream_t s, int* cuda_err);
@@ -48,6 +49,7 @@ int launch_exchange_push(const void* d_local_part, uint8_t* const* d_peer_base, 
 }  // namespace lwse
 
 const uint32_t* g_last_place_counters = nullptr;
+const uint32_t* g_last_place_unpinned = nullptr;
 
 namespace {
 
@@ -79,6 +81,8 @@ struct lwse_engine {
   int sm_count = lwse::kSmCount;
   cudaStream_t stream = nullptr;
   cudaStream_t side_stream = nullptr;  // placement round of lwse_reconcile_device
+  cudaStream_t hist_stream = nullptr;  // copies the unpinned-request count of a round to the host, off the critical path
+  cudaEvent_t ev_hist = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::mutex mu;
   int last_cuda_error = 0;
@@ -229,11 +233,15 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
       create_side_stream(&e->side_stream) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->hist_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_hist, cudaEventDisableTiming) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&e->h_rounds), 64) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&e->h_counts), 64) != cudaSuccess) {
     (void)cudaGetLastError();
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->ev_hist) cudaEventDestroy(e->ev_hist);
+    if (e->hist_stream) cudaStreamDestroy(e->hist_stream);
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -273,6 +281,9 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
     if (e->h_rounds) cudaFreeHost(e->h_rounds);
     if (e->h_counts) cudaFreeHost(e->h_counts);
     cudaStreamSynchronize(e->side_stream);
+    cudaStreamSynchronize(e->hist_stream);
+    cudaEventDestroy(e->ev_hist);
+    cudaStreamDestroy(e->hist_stream);
     cudaEventDestroy(e->ev_fork);
     cudaEventDestroy(e->ev_join);
     cudaStreamDestroy(e->side_stream);
@@ -618,6 +629,7 @@ static int place_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n
   const uint64_t geometry = ((uint64_t)n_reqs << 40) ^ ((uint64_t)n_namespaces << 56) ^ ((uint64_t)e->n_nodes << 16) ^
                             (uint64_t)e->n_domains ^ 0x8000000000000000ull;
   const bool fresh = before != e->place_scratch.p || geometry != e->place_geometry;
+  if (fresh) e->h_rounds[2] = 0xFFFFFFFFu;  // no history for this geometry
   e->place_geometry = geometry;
   int cuda_err = 0;
   int launched = lwse::launch_place((const lwse_node_rec*)e->nodes.p, (const uint32_t*)e->dom_first.p,
@@ -625,10 +637,20 @@ static int place_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n
                                     e->n_domains, d_reqs,
                                     n_reqs, d_occupancy, n_namespaces, d_out, e->place_scratch.p,
                                     scratch, rounds_out ? e->h_rounds : nullptr, e->sm_count, s, &cuda_err,
-                                    e->place_calls++, fresh, n_parts, reqs_per_part, part_stride_bytes);
+                                    e->place_calls++, fresh, n_parts, reqs_per_part, part_stride_bytes,
+                                    e->h_rounds + 2);
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
   if (rounds_out) *rounds_out = e->h_rounds[0];
+  // history for the next call's cluster-or-grid decision (only consulted beyond 1024 requests):
+  // the round's unpinned-request count, copied on a third stream so that nothing waits for it
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  if (n_reqs > 1024u && g_last_place_unpinned && cudaStreamIsCapturing(s, &capturing) == cudaSuccess &&
+      capturing == cudaStreamCaptureStatusNone) {
+    LWSE_CUDA(e, cudaEventRecord(e->ev_hist, s));
+    LWSE_CUDA(e, cudaStreamWaitEvent(e->hist_stream, e->ev_hist, 0));
+    LWSE_CUDA(e, cudaMemcpyAsync(e->h_rounds + 2, g_last_place_unpinned, 4, cudaMemcpyDeviceToHost, e->hist_stream));
+  }
   return LWSE_OK;
 }
 

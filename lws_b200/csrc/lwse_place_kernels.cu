@@ -31,6 +31,7 @@
 namespace cg = cooperative_groups;
 
 extern const uint32_t* g_last_place_counters;
+extern const uint32_t* g_last_place_unpinned;
 
 namespace lwse {
 
@@ -53,6 +54,7 @@ struct PlaceArgs {
   uint32_t next_zero_words;
   uint32_t n_nodes, n_domains, n_reqs, n_namespaces;
   uint32_t hold_stride;  // n_domains rounded up to even: holder rows are 16-byte aligned
+  uint32_t* last_unpinned;  // scratch tail (never reset): the number of live unpinned requests of this call
   // gathered form (multi-GPU): `reqs` / `occupancy` point into part 0 of n_parts equally laid out
   // parts (one per rank, as all-gathered); request r lives in part r / reqs_per_part, and the
   // occupancy of a node is the sum over the parts
@@ -271,6 +273,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 2) place_kernel(const PlaceArgs
     }
   };
   const uint32_t n_unpinned = __ldcg(a.counters + 4);
+  if (gtid == 0) *a.last_unpinned = n_unpinned;
   if (!kCluster || n_unpinned == 0u) pinned_results();
 
   uint32_t round = 0;
@@ -432,7 +435,7 @@ int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, cons
                  uint32_t n_reqs, const uint32_t* d_occupancy, uint32_t n_namespaces, lwse_place_out* d_out,
                  void* d_scratch, size_t scratch_bytes, uint32_t* h_rounds, int sm_count, cudaStream_t s,
                  int* cuda_err, uint32_t call_index, bool fresh, uint32_t n_parts, uint32_t reqs_per_part,
-                 uint64_t part_stride_bytes) {
+                 uint64_t part_stride_bytes, uint32_t* h_unpinned) {
   *cuda_err = 0;
   if (n_reqs > 0xFFFFFFu || n_domains >= (1u << 28) ||
       scratch_bytes < place_scratch_bytes(n_nodes, n_domains, n_reqs, n_namespaces)) {
@@ -484,7 +487,9 @@ int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, cons
   a.n_parts = n_parts ? n_parts : 1u;
   a.reqs_per_part = reqs_per_part ? reqs_per_part : n_reqs;
   a.part_stride_bytes = part_stride_bytes;
+  a.last_unpinned = reinterpret_cast<uint32_t*>(base + 2 * half);
   ::g_last_place_counters = a.counters;
+  ::g_last_place_unpinned = a.last_unpinned;
 
   // One cluster while every request can have its own warp within a few passes; beyond that a
   // cooperative grid with one warp per request, at most one CTA per SM.
@@ -493,9 +498,17 @@ int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, cons
     return v ? atoi(v) : 0;
   }();
   // (phase 0 and the scratch reset are grid-stride loops: tables that 4096 threads cannot sweep in
-  // a few passes go to the grid as well)
-  const bool small = n_reqs <= kClusterCtas * kPlaceWarps * 8u && n_nodes <= (1u << 16) &&
-                     (uint64_t)n_namespaces * hold_stride_of(n_domains) <= (1u << 16);
+  // a few passes go to the grid as well.)  What decides is the number of UNPINNED requests — pinned
+  // ones cost one claim in phase 0 — and the host does not know it: the previous call's count,
+  // copied to pinned host memory off the critical path by the engine, predicts this call's (no
+  // history: all requests).  (Having the kernel post the count to mapped host memory itself cost
+  // 0.9 us per tick: the grid does not retire before the PCIe write is flushed.)
+  const bool few_reqs = n_reqs <= kClusterCtas * kPlaceWarps * 8u;  // ≤ 8 per warp even if all are unpinned
+  const uint32_t expect_unpinned = (!fresh && h_unpinned && *(volatile uint32_t*)h_unpinned != 0xFFFFFFFFu)
+                                       ? *(volatile uint32_t*)h_unpinned
+                                       : n_reqs;
+  const bool small = (few_reqs || (expect_unpinned <= kClusterCtas * kPlaceWarps * 2u && n_reqs <= (1u << 14))) &&
+                     n_nodes <= (1u << 16) && (uint64_t)n_namespaces * hold_stride_of(n_domains) <= (1u << 16);
   const bool cluster = env_path == 1 || (env_path != 2 && small);
   if (cluster) {
     // 16 CTAs x 256 threads where the device can co-schedule a 16-CTA cluster (non-portable size:
