@@ -311,3 +311,27 @@ def test_host_entry_reads_pinned_identity_rows_in_place(engine, p_event):
         assert_same(got[1], want[1], "group_out")
         if occupancy:
             assert np.array_equal(got[2], want[2])
+
+
+@pytest.mark.parametrize("seed", range(100, 124))
+def test_fuzz_campaign(engine, seed):
+    """More seeds at a small scale: both sweep forms and, from the same tables, a placement round
+    fed by the swept occupancy — every output row against the oracle."""
+    import oracle
+    from lws_b200 import encoder
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    p = synth.profile("fuzz", 0.15)
+    p.n_nodes = int(rng.choice([8, 64, 640]))
+    p.nodes_per_domain = int(rng.choice([1, 4, 16]))
+    p.node_capacity = int(rng.choice([1, 4, 40]))
+    p.p_exclusive = float(rng.choice([0.1, 0.5, 1.0]))
+    p.p_leader_unscheduled = float(rng.choice([0.1, 0.6, 1.0]))
+    t = synth.make(p, seed=seed)
+    got = run_both(engine, t)
+    reqs = encoder.encode_place_requests(t.lws, t.groups)
+    n_ns = 3
+    reqs["ns"] = (np.arange(len(reqs)) * 7 + seed) % (n_ns + 1)  # includes one out-of-range namespace
+    want = oracle.place(t.nodes, got[2], t.n_domains, n_ns, reqs)
+    out, _ = engine.place_host(reqs, got[2], n_ns)
+    assert_same(out, want, "place_out")
