@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 2) place_kernel(const PlaceArgs
           q.cur_dom = o.x;
           q.dead = (o.z & LWSE_PLACE_UNSCHEDULABLE) ? 1u : 0u;
         }
+        __syncwarp();  // every lane has its copy before lane 0 updates the cache entry below
         if (q.dead) continue;  // warp-uniform
         const unsigned long long key = q.key;
         unsigned long long* hold = a.holder + (uint64_t)q.ns * a.hold_stride;
