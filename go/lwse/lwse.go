@@ -96,7 +96,9 @@ func (e *Engine) UploadNodes(nodes *C.lwse_node_rec, n, nDomains uint32) error {
 	return e.check(C.lwse_upload_nodes(e.h, nodes, C.uint32_t(n), C.uint32_t(nDomains)))
 }
 
-// SweepLws: host tables in, host result tables out (H2D, three kernels, D2H, sync).
+// SweepLws: host tables in, host result tables out (H2D, two or three kernels, D2H, sync).  With
+// tables from the pinned arena the 12-byte pod identity column is not uploaded: the engine reads
+// the rows of pods with a restart / deletion event in place.
 func (e *Engine) SweepLws(t *LwsTables) error {
 	ct := t.c()
 	return e.check(C.lwse_sweep_lws_host(e.h, &ct))
@@ -115,4 +117,54 @@ func (e *Engine) SweepDs(t *C.lwse_ds_tables) error { return e.check(C.lwse_swee
 // GroupKeys computes SHA-1 digests (20 bytes each) of n strings laid out CSR-style.
 func (e *Engine) GroupKeys(bytes *C.uint8_t, offsets *C.uint32_t, n uint32, digests *C.uint8_t) error {
 	return e.check(C.lwse_group_keys_host(e.h, bytes, offsets, C.uint32_t(n), digests))
+}
+
+// --- incremental form: tables resident on the device, fed from watch events -----------------
+
+// ResidentLoad copies the four input tables to the device, where they stay.
+func (e *Engine) ResidentLoad(t *LwsTables) error {
+	ct := t.c()
+	return e.check(C.lwse_resident_load(e.h, &ct))
+}
+
+// ResidentPatch overwrites n rows of one resident table (rows[i] <- i-th packed row of values):
+// what an informer delta (pod phase change, sts status update, spec edit) turns into.
+func (e *Engine) ResidentPatch(which C.lwse_table, rows *C.uint32_t, values unsafe.Pointer, n uint32) error {
+	return e.check(C.lwse_resident_patch(e.h, which, rows, values, C.uint32_t(n)))
+}
+
+// ResidentSweep sweeps the resident tables and returns only the result rows that changed since
+// the previous sweep — the objects whose Reconcile() has something to do.
+func (e *Engine) ResidentSweep(flags uint32, ch *C.lwse_changes) error {
+	return e.check(C.lwse_resident_sweep(e.h, C.uint32_t(flags), ch))
+}
+
+// --- device-pointer form: one reconcile tick (sweep + placement round, concurrently) --------
+
+// ReconcileDevice enqueues one tick on stream (nil = the engine's stream); no synchronize.
+func (e *Engine) ReconcileDevice(t *LwsTables, reqs *C.lwse_place_req, n uint32, occupancy *C.uint32_t,
+	nNamespaces uint32, placeOut *C.lwse_place_out, stream unsafe.Pointer) error {
+	ct := t.c()
+	return e.check(C.lwse_reconcile_device(e.h, &ct, reqs, C.uint32_t(n), occupancy, C.uint32_t(nNamespaces), placeOut, stream))
+}
+
+// --- one operator replica per GPU of a node: placement parts exchanged over NVLink -----------
+
+// ExchangeCreate allocates this replica's exchange buffer and returns its 64-byte IPC handle;
+// the replicas swap handles (any transport) and each calls ExchangeConnect with all of them.
+func (e *Engine) ExchangeCreate(reqsPerPart, world, rank uint32) ([64]byte, error) {
+	var h [64]byte
+	err := e.check(C.lwse_exchange_create(e.h, C.uint32_t(reqsPerPart), C.uint32_t(world), C.uint32_t(rank), unsafe.Pointer(&h[0])))
+	return h, err
+}
+
+func (e *Engine) ExchangeConnect(handles []byte) error {
+	return e.check(C.lwse_exchange_connect(e.h, unsafe.Pointer(&handles[0])))
+}
+
+// ReconcileExchangedDevice: a tick of one shard; localPart = [occupancy | request rows] in device memory.
+func (e *Engine) ReconcileExchangedDevice(t *LwsTables, localPart unsafe.Pointer, nNamespaces uint32,
+	placeOut *C.lwse_place_out, stream unsafe.Pointer) error {
+	ct := t.c()
+	return e.check(C.lwse_reconcile_exchanged_device(e.h, &ct, localPart, C.uint32_t(nNamespaces), placeOut, stream))
 }

@@ -35,7 +35,7 @@ int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, cons
                  uint32_t n_namespaces, lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes,
                  uint32_t* h_rounds, int sm_count, cudaStream_t s, int* cuda_err, uint32_t call_index,
                  bool fresh, uint32_t n_parts, uint32_t reqs_per_part, uint64_t part_stride_bytes,
-                 uint32_t* h_unpinned);
+                 uint32_t* h_unpinned, const uint32_t** d_counters_out, const uint32_t** d_unpinned_out);
 size_t place_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces);
 // lwse_ds_kernels.cu
 int launch_ds_sweep(const lwse_ds_tables* t, int sm_count, cudaStream_t s, int* cuda_err);
@@ -48,8 +48,6 @@ int launch_exchange_push(const void* d_local_part, uint8_t* const* d_peer_base, 
                          uint64_t step, uint32_t world, uint32_t rank, cudaStream_t s, int* cuda_err);
 }  // namespace lwse
 
-const uint32_t* g_last_place_counters = nullptr;
-const uint32_t* g_last_place_unpinned = nullptr;
 
 namespace {
 
@@ -106,6 +104,8 @@ struct lwse_engine {
   bool no_zero_copy = false;         // LWSE_NO_ZERO_COPY=1: always upload the identity column
   uint32_t place_calls = 0;          // selects the scratch half
   uint64_t place_geometry = 0;       // (n_reqs, n_namespaces, nodes, domains) the scratch was laid out for
+  const uint32_t* place_counters = nullptr;  // device: counters / phase stamps of the last placement call
+  const uint32_t* place_unpinned = nullptr;  // device: its unpinned-request count
   DevBuf ds, ds_roles, ds_revroles, ds_out, ds_role_out, ds_revrole_out;
   DevBuf sha_bytes, sha_offsets, sha_digests;
   uint32_t* h_rounds = nullptr;  // pinned
@@ -638,18 +638,18 @@ static int place_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n
                                     n_reqs, d_occupancy, n_namespaces, d_out, e->place_scratch.p,
                                     scratch, rounds_out ? e->h_rounds : nullptr, e->sm_count, s, &cuda_err,
                                     e->place_calls++, fresh, n_parts, reqs_per_part, part_stride_bytes,
-                                    e->h_rounds + 2);
+                                    e->h_rounds + 2, &e->place_counters, &e->place_unpinned);
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
   if (rounds_out) *rounds_out = e->h_rounds[0];
   // history for the next call's cluster-or-grid decision (only consulted beyond 1024 requests):
   // the round's unpinned-request count, copied on a third stream so that nothing waits for it
   cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
-  if (n_reqs > 1024u && g_last_place_unpinned && cudaStreamIsCapturing(s, &capturing) == cudaSuccess &&
+  if (n_reqs > 1024u && e->place_unpinned && cudaStreamIsCapturing(s, &capturing) == cudaSuccess &&
       capturing == cudaStreamCaptureStatusNone) {
     LWSE_CUDA(e, cudaEventRecord(e->ev_hist, s));
     LWSE_CUDA(e, cudaStreamWaitEvent(e->hist_stream, e->ev_hist, 0));
-    LWSE_CUDA(e, cudaMemcpyAsync(e->h_rounds + 2, g_last_place_unpinned, 4, cudaMemcpyDeviceToHost, e->hist_stream));
+    LWSE_CUDA(e, cudaMemcpyAsync(e->h_rounds + 2, e->place_unpinned, 4, cudaMemcpyDeviceToHost, e->hist_stream));
   }
   return LWSE_OK;
 }
@@ -818,9 +818,9 @@ extern "C" __attribute__((visibility("default"))) int lwse_debug_place_trace(lws
   cudaDeviceSynchronize();
   // the half used by the last call: layout [holder | counters …]; holder size is unknown here, so the
   // launcher recorded the counters pointer
-  if (!g_last_place_counters) return LWSE_ERR_NOT_READY;
+  if (!e->place_counters) return LWSE_ERR_NOT_READY;
   uint32_t raw[32];
-  if (cudaMemcpy(raw, g_last_place_counters + 16, sizeof(raw), cudaMemcpyDeviceToHost) != cudaSuccess)
+  if (cudaMemcpy(raw, e->place_counters + 16, sizeof(raw), cudaMemcpyDeviceToHost) != cudaSuccess)
     return LWSE_ERR_CUDA;
   for (int k = 0; k < 16; k++) out16[k] = (uint64_t)raw[2 * k] | ((uint64_t)raw[2 * k + 1] << 32);
   return LWSE_OK;

@@ -30,8 +30,6 @@
 
 namespace cg = cooperative_groups;
 
-extern const uint32_t* g_last_place_counters;
-extern const uint32_t* g_last_place_unpinned;
 
 namespace lwse {
 
@@ -436,7 +434,8 @@ int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, cons
                  uint32_t n_reqs, const uint32_t* d_occupancy, uint32_t n_namespaces, lwse_place_out* d_out,
                  void* d_scratch, size_t scratch_bytes, uint32_t* h_rounds, int sm_count, cudaStream_t s,
                  int* cuda_err, uint32_t call_index, bool fresh, uint32_t n_parts, uint32_t reqs_per_part,
-                 uint64_t part_stride_bytes, uint32_t* h_unpinned) {
+                 uint64_t part_stride_bytes, uint32_t* h_unpinned, const uint32_t** d_counters_out,
+                 const uint32_t** d_unpinned_out) {
   *cuda_err = 0;
   if (n_reqs > 0xFFFFFFu || n_domains >= (1u << 28) ||
       scratch_bytes < place_scratch_bytes(n_nodes, n_domains, n_reqs, n_namespaces)) {
@@ -489,8 +488,8 @@ int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, cons
   a.reqs_per_part = reqs_per_part ? reqs_per_part : n_reqs;
   a.part_stride_bytes = part_stride_bytes;
   a.last_unpinned = reinterpret_cast<uint32_t*>(base + 2 * half);
-  ::g_last_place_counters = a.counters;
-  ::g_last_place_unpinned = a.last_unpinned;
+  if (d_counters_out) *d_counters_out = a.counters;       // phase stamps of this call (tuning aid)
+  if (d_unpinned_out) *d_unpinned_out = a.last_unpinned;  // where this call leaves its unpinned-request count
 
   // One cluster while every request can have its own warp within a few passes; beyond that a
   // cooperative grid with one warp per request, at most one CTA per SM.
@@ -515,30 +514,32 @@ int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, cons
     // 16 CTAs x 256 threads where the device can co-schedule a 16-CTA cluster (non-portable size:
     // B200 can), else 8 x 512: the same 128 warps on twice the SMs — the rounds are bound by the
     // instruction issue of the warps sharing a scheduler (23.6 -> 22.9 us per tick on C3).
-    static const int wide = [] {
+    // (function attributes are per device: probe once per device this process launches on)
+    static int wide_by_device[64];  // 0 = not probed, 1 = 8 x 512, 2 = 16 x 256
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& probed = wide_by_device[dev & 63];
+    if (probed == 0) {
+      probed = 1;
       const char* v = getenv("LWSE_PLACE_CLUSTER16");
-      if (v && atoi(v) == 0) return 0;
-      if (cudaFuncSetAttribute(place_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-        (void)cudaGetLastError();
-        return 0;
+      if (!(v && atoi(v) == 0) &&
+          cudaFuncSetAttribute(place_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+        cudaLaunchConfig_t probe{};
+        probe.gridDim = dim3(16);
+        probe.blockDim = dim3(256);
+        cudaLaunchAttribute pa[1];
+        pa[0].id = cudaLaunchAttributeClusterDimension;
+        pa[0].val.clusterDim.x = 16;
+        pa[0].val.clusterDim.y = 1;
+        pa[0].val.clusterDim.z = 1;
+        probe.attrs = pa;
+        probe.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, place_kernel<true>, &probe) == cudaSuccess && n >= 1) probed = 2;
       }
-      cudaLaunchConfig_t probe{};
-      probe.gridDim = dim3(16);
-      probe.blockDim = dim3(256);
-      cudaLaunchAttribute pa[1];
-      pa[0].id = cudaLaunchAttributeClusterDimension;
-      pa[0].val.clusterDim.x = 16;
-      pa[0].val.clusterDim.y = 1;
-      pa[0].val.clusterDim.z = 1;
-      probe.attrs = pa;
-      probe.numAttrs = 1;
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, place_kernel<true>, &probe) != cudaSuccess || n < 1) {
-        (void)cudaGetLastError();
-        return 0;
-      }
-      return 1;
-    }();
+      (void)cudaGetLastError();
+    }
+    const int wide = probed == 2;
     const unsigned cl = wide ? 16u : kClusterCtas;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(cl);
