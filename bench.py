@@ -453,17 +453,18 @@ def run_ours(args):
     keep, h = [], {}
     for name, arr in (("lws", t.lws), ("groups", t.groups), ("pst", t.pod_state), ("pid", t.pod_ident),
                       ("lo", R.aligned_empty(n_lws, R.LWS_OUT)), ("go", R.aligned_empty(n_grp, R.GROUP_OUT)),
-                      ("reqs", reqs), ("occ", occ_host)):
+                      ("reqs", reqs), ("occ", occ_host), ("po", R.aligned_empty(max(n_req, 1), R.PLACE_OUT))):
         ten, view = pinned(arr)
         keep.append(ten)
         h[name] = view
 
     def e2e_step(extra_flags=0, engine=None):
         en = engine or eng
+        if n_req and world == 1:  # one call per tick: lwse_reconcile_host
+            return en.reconcile_host(h["lws"], h["groups"], h["pst"], h["pid"], h["reqs"], h["occ"], 1,
+                                     flags=t.flags | extra_flags, out=(h["lo"], h["go"]), place_out=h["po"])[2]
         en.sweep_lws_host(h["lws"], h["groups"], h["pst"], h["pid"], flags=t.flags | extra_flags,
                           out=(h["lo"], h["go"]))
-        if n_req and world == 1:
-            return en.place_host(h["reqs"], h["occ"], 1)[0]
         return None
 
     def wall(fn, reps, all_ranks=True):
@@ -597,7 +598,7 @@ def run_ours(args):
             "e2e": {"value": total_groups / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(h2d - t.pod_ident.nbytes + ev * R.POD_IDENT.itemsize),
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                    "api": "lwse_sweep_lws_host + lwse_place_host (pinned host tables)",
+                    "api": "lwse_reconcile_host (= lwse_sweep_lws_host + lwse_place_host in one call; pinned host tables)",
                     "note": "every table handed over every step; state column, group and LWS rows uploaded, "
                             f"identity rows of the {ev} event pods read in place over PCIe (12 B each counted)",
                     "full_upload": {"value": n_grp * world / e2e_full_s if e2e_full_s else None,

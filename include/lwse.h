@@ -416,7 +416,9 @@ LWSE_API int lwse_place_host(lwse_engine* e, const lwse_place_req* reqs, uint32_
                              const uint32_t* occupancy, uint32_t n_namespaces,
                              lwse_place_out* out, uint32_t* rounds_out);
 /* Device pointers; enqueued on `stream`.  rounds_out == NULL: no synchronize;
- * otherwise the call waits for the round count. */
+ * otherwise the call waits for the round count.  The placement rounds of one engine share
+ * its scratch: they must not overlap in time — keep them on one stream (lwse_reconcile_*
+ * use the engine's side stream for theirs) or order the streams with events. */
 LWSE_API int lwse_place_device(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
                                const uint32_t* d_occupancy, uint32_t n_namespaces,
                                lwse_place_out* d_out, uint32_t* rounds_out, void* stream);
@@ -443,6 +445,13 @@ LWSE_API int lwse_place_gathered_device(lwse_engine* e, const void* d_parts, uin
 LWSE_API int lwse_reconcile_device(lwse_engine* e, const lwse_lws_tables* d, const lwse_place_req* d_reqs,
                                    uint32_t n_reqs, const uint32_t* d_occupancy, uint32_t n_namespaces,
                                    lwse_place_out* d_place_out, void* stream);
+
+/* The same tick from host tables: lwse_sweep_lws_host(host) and lwse_place_host(reqs, …) in one
+ * call, the placement round solved on the side stream while the sweep's tables are uploaded;
+ * returns when all results are in the caller's buffers.  n_reqs == 0: sweep only. */
+LWSE_API int lwse_reconcile_host(lwse_engine* e, const lwse_lws_tables* host, const lwse_place_req* reqs,
+                                 uint32_t n_reqs, const uint32_t* occupancy, uint32_t n_namespaces,
+                                 lwse_place_out* place_out);
 
 /* ------------------------------------------------------------------------- */
 /* Peer exchange: the multi-GPU placement step without a collective library  */

@@ -364,12 +364,9 @@ LWSE_API int lwse_sweep_lws_device(lwse_engine* e, const lwse_lws_tables* t, voi
   return sweep_device_locked(e, t, stream ? (cudaStream_t)stream : e->stream);
 }
 
-LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* h) {
-  if (!e) return LWSE_ERR_INVALID_ARG;
-  int rc = check_lws_tables(h);
-  if (rc != LWSE_OK) return rc;
-  std::lock_guard<std::mutex> lock(e->mu);
-  DeviceGuard guard(e->device);
+// lwse_sweep_lws_host with the engine locked and its device current; returns after the results
+// are in the caller's tables (stream synchronized).
+static int sweep_host_locked(lwse_engine* e, const lwse_lws_tables* h) {
   cudaStream_t s = e->stream;
   const size_t b_lws = (size_t)h->n_lws * sizeof(lwse_lws_rec);
   const size_t b_grp = (size_t)h->n_groups * sizeof(lwse_group_rec);
@@ -464,6 +461,15 @@ LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* h) {
                                  cudaMemcpyDeviceToHost, s));
   LWSE_CUDA(e, cudaStreamSynchronize(s));
   return LWSE_OK;
+}
+
+LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* h) {
+  if (!e) return LWSE_ERR_INVALID_ARG;
+  int rc = check_lws_tables(h);
+  if (rc != LWSE_OK) return rc;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  return sweep_host_locked(e, h);
 }
 
 // ---------------------------------------------------------------------------
@@ -859,6 +865,43 @@ LWSE_API int lwse_place_host(lwse_engine* e, const lwse_place_req* reqs, uint32_
                                  cudaMemcpyDeviceToHost, e->stream));
   LWSE_CUDA(e, cudaStreamSynchronize(e->stream));
   return LWSE_OK;
+}
+
+// One reconcile tick from host tables: lwse_sweep_lws_host and lwse_place_host in one call.  The
+// placement round (its inputs are 70 KB) is uploaded, solved and read back on the side stream
+// while the tables of the sweep are still crossing PCIe; one synchronize at the end.
+LWSE_API int lwse_reconcile_host(lwse_engine* e, const lwse_lws_tables* h, const lwse_place_req* reqs,
+                                 uint32_t n_reqs, const uint32_t* occupancy, uint32_t n_namespaces,
+                                 lwse_place_out* place_out) {
+  if (!e || (n_reqs && (!reqs || !place_out || n_namespaces == 0))) return LWSE_ERR_INVALID_ARG;
+  int rc = check_lws_tables(h);
+  if (rc != LWSE_OK) return rc;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  if (n_reqs) {
+    if (e->n_nodes == 0 || e->n_domains == 0) return LWSE_ERR_NOT_READY;
+    cudaStream_t ps = e->side_stream;
+    LWSE_CUDA(e, e->place_reqs.reserve((size_t)n_reqs * sizeof(lwse_place_req) + 16));
+    LWSE_CUDA(e, e->place_out.reserve((size_t)n_reqs * sizeof(lwse_place_out) + 16));
+    LWSE_CUDA(e, e->place_occ.reserve((size_t)e->n_nodes * 4 + 16));
+    // (the side stream only ever runs work enqueued under this lock and joined before it is released)
+    LWSE_CUDA(e, cudaMemcpyAsync(e->place_reqs.p, reqs, (size_t)n_reqs * sizeof(lwse_place_req), cudaMemcpyHostToDevice, ps));
+    if (occupancy)
+      LWSE_CUDA(e, cudaMemcpyAsync(e->place_occ.p, occupancy, (size_t)e->n_nodes * 4, cudaMemcpyHostToDevice, ps));
+    else
+      LWSE_CUDA(e, cudaMemsetAsync(e->place_occ.p, 0, (size_t)e->n_nodes * 4, ps));
+    rc = place_locked(e, (const lwse_place_req*)e->place_reqs.p, n_reqs, (const uint32_t*)e->place_occ.p, n_namespaces,
+                      (lwse_place_out*)e->place_out.p, nullptr, ps, 1, n_reqs, 0);
+    if (rc == LWSE_OK)
+      LWSE_CUDA(e, cudaMemcpyAsync(place_out, e->place_out.p, (size_t)n_reqs * sizeof(lwse_place_out),
+                                   cudaMemcpyDeviceToHost, ps));
+  }
+  const int rc_sweep = rc == LWSE_OK ? sweep_host_locked(e, h) : rc;
+  if (n_reqs) {
+    const cudaError_t pe = cudaStreamSynchronize(e->side_stream);
+    if (rc_sweep == LWSE_OK && pe != cudaSuccess) return fail_cuda(e, pe);
+  }
+  return rc_sweep;
 }
 
 // ---------------------------------------------------------------------------

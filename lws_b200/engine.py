@@ -51,6 +51,10 @@ SYMBOLS = {
         [C.c_void_p, C.POINTER(R.LwsTables), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p],
         C.c_int,
     ),
+    "lwse_reconcile_host": (
+        [C.c_void_p, C.POINTER(R.LwsTables), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p],
+        C.c_int,
+    ),
     "lwse_exchange_create": ([C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p], C.c_int),
     "lwse_exchange_connect": ([C.c_void_p, C.c_void_p], C.c_int),
     "lwse_exchange_part_bytes": ([C.c_void_p], C.c_uint64),
@@ -161,6 +165,25 @@ class Engine:
         )
         self._check(lib().lwse_sweep_lws_host(self._h, C.byref(t)))
         return lws_out, group_out, (occ[: self.n_nodes] if occ is not None else None)
+
+    def reconcile_host(self, lws, groups, pod_state, pod_ident, reqs, occupancy=None, n_namespaces=1, flags=0,
+                       out=None, place_out=None):
+        """Host tables + placement requests in → (lws_out, group_out, place_out): one tick, one call."""
+        assert lws.dtype == R.LWS_REC and groups.dtype == R.GROUP_REC and reqs.dtype == R.PLACE_REQ
+        assert pod_state.dtype == R.POD_STATE and pod_ident.dtype == R.POD_IDENT and len(pod_state) == len(pod_ident)
+        lws_out, group_out = out if out is not None else (R.aligned_empty(len(lws), R.LWS_OUT),
+                                                          R.aligned_empty(len(groups), R.GROUP_OUT))
+        if place_out is None:
+            place_out = R.aligned_empty(len(reqs), R.PLACE_OUT)
+        if occupancy is not None:
+            occupancy = np.ascontiguousarray(occupancy, dtype=np.uint32)
+        t = R.LwsTables(
+            R.ptr(lws), len(lws), R.ptr(groups), len(groups), R.ptr(pod_state), R.ptr(pod_ident), len(pod_state),
+            R.ptr(lws_out), R.ptr(group_out), None, flags,
+        )
+        self._check(lib().lwse_reconcile_host(self._h, C.byref(t), R.ptr(reqs) if len(reqs) else None, len(reqs),
+                                              R.ptr(occupancy), n_namespaces, R.ptr(place_out) if len(reqs) else None))
+        return lws_out, group_out, place_out
 
     def sweep_lws_device(self, d_lws, n_lws, d_groups, n_groups, d_pod_state, d_pod_ident, n_pods, d_lws_out,
                          d_group_out, d_occupancy=None, flags=0, stream=None):

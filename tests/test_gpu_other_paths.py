@@ -257,3 +257,35 @@ def test_peer_exchange_placement_step_on_two_gpus():
          "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multi_gpu", "exchange_check.py")],
         capture_output=True, text=True, timeout=300)
     assert "EXCHANGE_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_reconcile_host_one_call(engine):
+    """lwse_reconcile_host = lwse_sweep_lws_host + lwse_place_host in one call (placement on the
+    side stream while the tables upload); pageable and pinned tables."""
+    import torch
+    import oracle
+
+    t, reqs = place_case(n_lws=2500, n_nodes=4096, size=16, p_excl=0.5, p_unsched=0.6, seed=23, capacity=40)
+    engine.upload_nodes(t.nodes, t.n_domains)
+    want_lo, want_go, occ = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, flags=t.flags,
+                                             want_occupancy=True)
+    want_place = oracle.place(t.nodes, occ, t.n_domains, 1, reqs)
+    keep = []
+
+    def pinned(a):
+        ten = torch.empty(max(a.nbytes, 16), dtype=torch.uint8).pin_memory()
+        view = ten.numpy()[: a.nbytes].view(a.dtype)
+        view[...] = a
+        keep.append(ten)
+        return view
+
+    for conv in (lambda a: a, pinned):
+        lo, go, po = engine.reconcile_host(conv(t.lws), conv(t.groups), conv(t.pod_state), conv(t.pod_ident),
+                                           conv(reqs), occ, 1, flags=t.flags)
+        same(lo, want_lo, "lws_out")
+        same(go, want_go, "group_out")
+        same(po, want_place, "place_out")
+    # no requests: sweep only
+    lo, go, po = engine.reconcile_host(t.lws, t.groups, t.pod_state, t.pod_ident, reqs[:0], None, 1, flags=t.flags)
+    same(lo, want_lo, "lws_out")
+    assert len(po) == 0
