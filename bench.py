@@ -554,7 +554,7 @@ def run_ours(args):
         ev = t.event_pods()
         words = (n_pod + 31) // 32
         group_rows = n_grp * (R.GROUP_REC.itemsize + R.GROUP_OUT.itemsize) + n_lws * 16
-        fused_on = n_pod <= 512 * max(n_grp, 1)  # the engine's rule (lwse_lws_kernels.cu launch_lws_sweep)
+        fused_on = n_pod <= 256 * max(n_grp, 1)  # the engine's rule (lwse_lws_kernels.cu launch_lws_sweep)
         passes = {
             # algorithmic bytes per launch: rows read once + rows written once.  A sweep is the fused
             # scan + group kernel followed by the LWS pass (small groups, no occupancy count); the

@@ -830,8 +830,12 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
     const char* v = getenv("LWSE_NO_FUSE");
     return v && atoi(v) != 0;
   }();
-  // scan + group pass in one kernel: small groups, no occupancy count, both passes wanted
-  const bool fused = group_pass && w == 1 && !t->node_occupancy && !no_fuse && !d_event_count &&
+  // scan + group pass in one kernel: small groups (the pod window of 256 consecutive groups has to
+  // fit the CTA's bitmap window of 65 536 pods), no occupancy count, both passes wanted.
+  // (A variant that staged the window's state words in shared memory with one TMA bulk copy per CTA
+  // — 128 groups, 32 KB — and evaluated the predicates from there was slower: 11.7 us against 9.6 us;
+  // the register scan already keeps ~48 KB in flight per SM, and a single bulk copy per CTA does not.)
+  const bool fused = group_pass && avg_pods <= 256 && !t->node_occupancy && !no_fuse && !d_event_count &&
                      !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN);
   if (fused) {
     GroupSweepArgs a{t->lws,   t->groups, t->pod_state, t->pod_ident, nullptr, nullptr, d_nodes,
