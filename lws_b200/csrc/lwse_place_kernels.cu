@@ -88,7 +88,7 @@ __device__ __forceinline__ lwse_place_req load_req(const PlaceArgs& a, uint32_t 
   } else {
     p += r;
   }
-  const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p)), hi = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  const uint4 lo = ldg_keep(reinterpret_cast<const uint4*>(p)), hi = ldg_keep(reinterpret_cast<const uint4*>(p) + 1);
   lwse_place_req q;
   q.priority = u64_of(lo.x, lo.y);
   q.group_key = u64_of(lo.z, lo.w);
@@ -103,8 +103,8 @@ __device__ __forceinline__ uint32_t load_occupancy(const PlaceArgs& a, uint32_t 
   if (!a.occupancy) return 0u;
   uint32_t occ = 0;
   for (uint32_t p = 0; p < a.n_parts; p++)
-    occ += __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(a.occupancy) +
-                                                    (uint64_t)p * a.part_stride_bytes) + n);
+    occ += ldg_keep_u32(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(a.occupancy) +
+                                                           (uint64_t)p * a.part_stride_bytes) + n);
   return occ;
 }
 
@@ -150,7 +150,7 @@ __device__ __forceinline__ void store_out(lwse_place_out* p, uint32_t d, uint32_
 // the domain a pinned request claims (its leader's node decides), or LWSE_NONE
 __device__ __forceinline__ uint32_t pinned_domain(const PlaceArgs& a, const lwse_place_req& rq) {
   if (rq.ns >= a.n_namespaces || rq.leader_node >= a.n_nodes) return LWSE_NONE;
-  const uint4 nr = __ldg(reinterpret_cast<const uint4*>(a.nodes + rq.leader_node));
+  const uint4 nr = ldg_keep(reinterpret_cast<const uint4*>(a.nodes + rq.leader_node));
   return (((nr.w >> 16) & LWSE_NODE_HAS_TOPOLOGY) && nr.z < a.n_domains) ? nr.z : LWSE_NONE;
 }
 
@@ -195,8 +195,8 @@ __global__ void __launch_bounds__(kPlaceThreads, 2) place_kernel(const PlaceArgs
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       const uint32_t n = base + (uint32_t)k * gsize;
-      pos[k] = n < a.n_nodes ? __ldg(a.node_pos + n) : LWSE_NONE;
-      nr[k] = n < a.n_nodes ? ldg_stream(reinterpret_cast<const uint4*>(a.nodes + n)) : make_uint4(0, 0, 0, 0);
+      pos[k] = n < a.n_nodes ? ldg_keep_u32(a.node_pos + n) : LWSE_NONE;
+      nr[k] = n < a.n_nodes ? ldg_keep(reinterpret_cast<const uint4*>(a.nodes + n)) : make_uint4(0, 0, 0, 0);
       occ[k] = n < a.n_nodes ? load_occupancy(a, n) : 0u;
     }
 #pragma unroll
@@ -370,11 +370,11 @@ __global__ void __launch_bounds__(kPlaceThreads, 2) place_kernel(const PlaceArgs
         }
         const uint32_t best_d = __reduce_min_sync(0xFFFFFFFFu, my_hi == H ? my_d : LWSE_NONE);
         // Level 2 — the node: the domain's run of the sorted node words.
-        const uint32_t first = __ldg(a.dom_first + best_d), last = __ldg(a.dom_first + best_d + 1u);
+        const uint32_t first = ldg_keep_u32(a.dom_first + best_d), last = ldg_keep_u32(a.dom_first + best_d + 1u);
         uint32_t my_lo = 0, my_n = LWSE_NONE;
         for (uint32_t i = first + lane; i < last; i += 32u) {
           const uint32_t w = __ldcg(a.g_sorted + i);
-          const uint32_t n = __ldg(a.node_order + i);
+          const uint32_t n = ldg_keep_u32(a.node_order + i);
           if ((w >> 28) == 0u) continue;
           const uint32_t lo = ((w >> 28) << 28) | (mix32(q.key_hi ^ (n * 0x85EBCA77u)) >> 4);
           if (lo > my_lo || (lo == my_lo && n < my_n)) {
