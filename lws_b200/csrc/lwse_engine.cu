@@ -265,6 +265,8 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
   {
     DeviceGuard guard(e->device);
     cudaStreamSynchronize(e->stream);
+    cudaStreamSynchronize(e->side_stream);
+    cudaStreamSynchronize(e->hist_stream);  // its copies target h_rounds, freed below
     for (uint32_t p = 0; p < e->xch_world; p++)
       if (e->xch_connected && p != e->xch_rank && e->xch_peer[p]) cudaIpcCloseMemHandle(e->xch_peer[p]);
     e->xch.release();
@@ -280,8 +282,6 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
     for (DevBuf* b : bufs) b->release();
     if (e->h_rounds) cudaFreeHost(e->h_rounds);
     if (e->h_counts) cudaFreeHost(e->h_counts);
-    cudaStreamSynchronize(e->side_stream);
-    cudaStreamSynchronize(e->hist_stream);
     cudaEventDestroy(e->ev_hist);
     cudaStreamDestroy(e->hist_stream);
     cudaEventDestroy(e->ev_fork);
