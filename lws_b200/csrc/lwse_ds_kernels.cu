@@ -14,7 +14,6 @@
 namespace lwse {
 
 constexpr int MAXR = (int)LWSE_DS_MAX_ROLES;
-constexpr int MAXV = (int)LWSE_DS_MAX_OLD_REVS;
 
 struct RuConfig {
   int ms, mu;

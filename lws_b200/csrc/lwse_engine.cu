@@ -35,7 +35,8 @@ int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, cons
                  uint32_t n_namespaces, lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes,
                  uint32_t* h_rounds, int sm_count, cudaStream_t s, int* cuda_err, uint32_t call_index,
                  bool fresh, uint32_t n_parts, uint32_t reqs_per_part, uint64_t part_stride_bytes,
-                 uint32_t* h_unpinned, const uint32_t** d_counters_out, const uint32_t** d_unpinned_out);
+                 uint32_t* h_unpinned, const uint32_t** d_counters_out, const uint32_t** d_unpinned_out,
+                 bool after_push);
 size_t place_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces);
 // lwse_ds_kernels.cu
 int launch_ds_sweep(const lwse_ds_tables* t, int sm_count, cudaStream_t s, int* cuda_err);
@@ -625,7 +626,7 @@ LWSE_API int lwse_resident_outputs(lwse_engine* e, lwse_lws_out* lws_out, lwse_g
 static int place_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
                         const uint32_t* d_occupancy, uint32_t n_namespaces, lwse_place_out* d_out,
                         uint32_t* rounds_out, cudaStream_t s, uint32_t n_parts, uint32_t reqs_per_part,
-                        uint64_t part_stride_bytes) {
+                        uint64_t part_stride_bytes, bool after_push = false) {
   if ((n_reqs && (!d_reqs || !d_out)) || n_namespaces == 0) return LWSE_ERR_INVALID_ARG;
   if (e->n_nodes == 0 || e->n_domains == 0) return LWSE_ERR_NOT_READY;
   const size_t scratch = lwse::place_scratch_bytes(e->n_nodes, e->n_domains, n_reqs, n_namespaces);
@@ -644,7 +645,7 @@ static int place_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n
                                     n_reqs, d_occupancy, n_namespaces, d_out, e->place_scratch.p,
                                     scratch, rounds_out ? e->h_rounds : nullptr, e->sm_count, s, &cuda_err,
                                     e->place_calls++, fresh, n_parts, reqs_per_part, part_stride_bytes,
-                                    e->h_rounds + 2, &e->place_counters, &e->place_unpinned);
+                                    e->h_rounds + 2, &e->place_counters, &e->place_unpinned, after_push);
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
   if (rounds_out) *rounds_out = e->h_rounds[0];
@@ -795,7 +796,8 @@ LWSE_API int lwse_reconcile_exchanged_device(lwse_engine* e, const lwse_lws_tabl
     const uint8_t* half = static_cast<const uint8_t*>(e->xch.p) + (step & 1ull) * e->xch_half;
     rc = place_locked(e, reinterpret_cast<const lwse_place_req*>(half + e->xch_reqs_off),
                       e->xch_world * e->xch_reqs_per_part, reinterpret_cast<const uint32_t*>(half), n_namespaces,
-                      d_place_out, nullptr, e->side_stream, e->xch_world, e->xch_reqs_per_part, e->xch_stride);
+                      d_place_out, nullptr, e->side_stream, e->xch_world, e->xch_reqs_per_part, e->xch_stride,
+                      /*after_push=*/true);
   }
   if (rc == LWSE_OK && t) rc = sweep_device_locked(e, t, s);
   cudaError_t je = cudaEventRecord(e->ev_join, e->side_stream);

@@ -39,6 +39,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 
 __global__ void __launch_bounds__(256) exchange_push_kernel(const ExchangeArgs a) {
   __shared__ uint32_t s_last;
+  pdl_launch_dependents();  // the placement round may take its SMs now; it waits for this grid to complete
   const uint64_t n_vec = a.part_bytes >> 4;
   const uint64_t dst_off = (a.step & 1ull) * a.half_bytes + (uint64_t)a.rank * a.part_stride;
   // every peer's copy of this rank's part: the loads of the local part are shared by all targets

@@ -757,9 +757,17 @@ static const bool g_pdl = [] {
 }();
 
 static int pick_tile(uint64_t items, uint64_t owners) {
-  // lanes per owner: next power of two >= average items per owner, in [1, 32]
+  // Lanes per object: every lane of a tile runs the object-level logic (the five cases, the walk)
+  // itself, so lanes only pay off when there are several group words per lane to read — next power
+  // of two >= (average groups per object) / kGroupsPerLane, in [1, 32].  One lane per group
+  // (divisor 1) made the C5 shape (16 groups per object) instruction-bound: 42 us for 100 k objects.
+  static const uint64_t div = [] {
+    const char* v = getenv("LWSE_LWS_TILE_DIV");
+    const int d = v ? atoi(v) : 8;
+    return (uint64_t)(d < 1 ? 1 : d);
+  }();
   if (owners == 0) return 1;
-  const uint64_t avg = (items + owners - 1) / owners;
+  const uint64_t avg = ((items + owners - 1) / owners + div - 1) / div;
   int w = 1;
   while (w < 32 && (uint64_t)w < avg) w <<= 1;
   return w;

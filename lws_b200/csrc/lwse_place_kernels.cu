@@ -180,6 +180,9 @@ __global__ void __launch_bounds__(kPlaceThreads, 2) place_kernel(const PlaceArgs
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t gtid = blockIdx.x * blockDim.x + tid, gsize = gridDim.x * blockDim.x;
   stamp(a, 0);
+  // After a peer exchange the round is launched programmatically dependent on the push kernel: the
+  // cluster is already resident when the parts arrive (no-op for an ordinary launch).
+  pdl_wait_prior();
 
   // ---------------- phase 0: node words, domain capacities, pinned claims ----------------
   // (this scratch half was left clean — holders ~0, counters and capacities 0 — by the previous call)
@@ -435,7 +438,7 @@ int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, cons
                  void* d_scratch, size_t scratch_bytes, uint32_t* h_rounds, int sm_count, cudaStream_t s,
                  int* cuda_err, uint32_t call_index, bool fresh, uint32_t n_parts, uint32_t reqs_per_part,
                  uint64_t part_stride_bytes, uint32_t* h_unpinned, const uint32_t** d_counters_out,
-                 const uint32_t** d_unpinned_out) {
+                 const uint32_t** d_unpinned_out, bool after_push) {
   *cuda_err = 0;
   if (n_reqs > 0xFFFFFFu || n_domains >= (1u << 28) ||
       scratch_bytes < place_scratch_bytes(n_nodes, n_domains, n_reqs, n_namespaces)) {
@@ -545,13 +548,15 @@ int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, cons
     cfg.gridDim = dim3(cl);
     cfg.blockDim = dim3(wide ? 256u : kPlaceThreads);
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cl;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = after_push ? 2 : 1;
     e = cudaLaunchKernelEx(&cfg, place_kernel<true>, a);
   } else {
     unsigned ctas = (n_reqs + kPlaceWarps - 1u) / kPlaceWarps;

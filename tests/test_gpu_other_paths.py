@@ -289,3 +289,41 @@ def test_reconcile_host_one_call(engine):
     lo, go, po = engine.reconcile_host(t.lws, t.groups, t.pod_state, t.pod_ident, reqs[:0], None, 1, flags=t.flags)
     same(lo, want_lo, "lws_out")
     assert len(po) == 0
+
+
+def test_peer_exchange_degenerate_world_of_one():
+    """The exchange path on one GPU (world = 1: the part is pushed to the local buffer, the flag wait
+    sees its own flag): push kernel → programmatically dependent placement round → results equal the
+    oracle's, over several ticks with changing parts (both buffer halves)."""
+    import torch
+    import oracle
+    from lws_b200 import distributed as D
+    from lws_b200.engine import Engine
+
+    eng = Engine(0)  # its own engine: one exchange per engine
+    try:
+        t, reqs = place_case(n_lws=1500, n_nodes=2048, size=16, p_excl=0.5, p_unsched=0.6, seed=41, capacity=40)
+        eng.upload_nodes(t.nodes, t.n_domains)
+        cap = len(reqs) + 5
+        handle = eng.exchange_create(cap, 1, 0)
+        eng.exchange_connect(handle)
+        stride, _ = D.part_layout(len(t.nodes), cap)
+        assert eng.exchange_part_bytes == stride
+        dev = torch.device("cuda:0")
+        d_po = torch.zeros(cap * R.PLACE_OUT.itemsize, dtype=torch.uint8, device=dev)
+        for tick in range(4):
+            rng = np.random.Generator(np.random.PCG64(tick))
+            occ = rng.integers(0, 3, size=len(t.nodes)).astype(np.uint32)
+            rq = reqs.copy()
+            rq["leader_node"][rng.random(len(rq)) < 0.2] = R.NONE
+            part = D.pack_part(occ, rq, cap)
+            d_part = torch.from_numpy(part).to(dev)
+            torch.cuda.synchronize()
+            eng.reconcile_exchanged_device(None, d_part, 1, d_po)
+            torch.cuda.synchronize()
+            occ_sum, reqs_cat = D.unpack_parts(part, 1, len(t.nodes), cap)
+            same(d_po.cpu().numpy().view(R.PLACE_OUT), oracle.place(t.nodes, occ_sum, t.n_domains, 1, reqs_cat),
+                 f"tick{tick}.place_out")
+        assert eng.exchange_status() == 0
+    finally:
+        eng.close()

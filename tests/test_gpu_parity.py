@@ -62,7 +62,7 @@ def test_every_tile_width(engine, size):
     run_both(engine, synth.make(p, seed=size))
 
 
-@pytest.mark.parametrize("replicas", [(0,), (1,), (3,), (31, 32, 33), (200,), (1, 1000)])
+@pytest.mark.parametrize("replicas", [(0,), (1,), (3,), (12,), (31, 32, 33), (60,), (100,), (200,), (1, 1000)])
 def test_every_lws_tile_width(engine, replicas):
     p = synth.profile("fuzz", 0.1)
     p.size_choices = (2,)
