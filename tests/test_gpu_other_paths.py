@@ -327,3 +327,21 @@ def test_peer_exchange_degenerate_world_of_one():
         assert eng.exchange_status() == 0
     finally:
         eng.close()
+
+
+def test_ds_order_stability_readiness_vectors_on_gpu(engine):
+    """executor_test.go:486-588 and the service readiness rule, through the CUDA DS sweep
+    (tests/test_oracle_ds_order_stability.py holds the vectors and checks the oracle)."""
+    import test_oracle_ds_order_stability as V
+
+    def gpu_sweep_ds(t):
+        return engine.sweep_ds_host(t.ds, t.roles, t.revroles)
+
+    for revisions, want in V.SORT_CASES:
+        assert V.drain_order(gpu_sweep_ds, revisions) == want
+    for case, want in V.STABLE_CASES:
+        ds_out, _, rr = gpu_sweep_ds(V.stability_tables(case))
+        assert bool(ds_out[0]["flags"] & R.DOUT_STABLE) == want
+    for ready, want in V.READY_CASES:
+        ds_out, _, _ = gpu_sweep_ds(V.readiness_tables(ready))
+        assert bool(ds_out[0]["flags"] & R.DOUT_NEW_READY) == want
