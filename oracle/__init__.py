@@ -65,6 +65,10 @@ _OPTIONAL = [
         [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
         C.c_int,
     ),
+    ("lwso_ds_batch_size", [C.c_int, C.c_int], C.c_int),
+    ("lwso_ds_total_steps", [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    ("lwso_ds_next_new", [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p], None),
+    ("lwso_ds_next_old", [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p], None),
     (
         "lwso_ds_scale_down_old",
         [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
@@ -111,6 +115,34 @@ def ds_compute_next_step(initial_old, current_old, current_new, target_new, max_
     if rc < 0:
         raise RuntimeError("lwso_ds_compute_next_step failed")
     return (past.tolist(), new.tolist()) if rc else None
+
+
+def ds_batch_size(max_surge, max_unavailable):
+    """planner.go:61 batchSize."""
+    return int(lib().lwso_ds_batch_size(int(max_surge), int(max_unavailable)))
+
+
+def ds_total_steps(initial_old, target, max_surge, max_unavailable):
+    """planner.go:68 computeTotalSteps."""
+    arr = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+    a = [arr(x) for x in (initial_old, target, max_surge, max_unavailable)]
+    return int(lib().lwso_ds_total_steps(len(initial_old), *[R.ptr(x) for x in a]))
+
+
+def ds_next_new(target, current_new, total_steps):
+    """planner.go:80 computeNextNewReplicas."""
+    arr = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+    t, c, out = arr(target), arr(current_new), np.zeros(len(target), np.int32)
+    lib().lwso_ds_next_new(len(t), R.ptr(t), R.ptr(c), int(total_steps), R.ptr(out))
+    return out.tolist()
+
+
+def ds_next_old(initial_old, current_old, total_steps):
+    """planner.go:115 computeNextOldReplicas."""
+    arr = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+    i, c, out = arr(initial_old), arr(current_old), np.zeros(len(initial_old), np.int32)
+    lib().lwso_ds_next_old(len(i), R.ptr(i), R.ptr(c), int(total_steps), R.ptr(out))
+    return out.tolist()
 
 
 def ds_compute_all_steps(initial_old, target, max_surge, max_unavailable):

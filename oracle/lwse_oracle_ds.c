@@ -93,6 +93,26 @@ static void compute_next_old_replicas(int n, const int* initial_old, const int* 
   }
 }
 
+/* Exported for the tests that pin the helpers on the reference's own helper-level vectors
+ * (planner_test.go:674-720, :800-902). */
+LWSO_API int lwso_ds_batch_size(int max_surge, int max_unavailable) { return batch_size(max_surge, max_unavailable); }
+LWSO_API int lwso_ds_total_steps(int n, const int* initial_old, const int* target, const int* max_surge,
+                                 const int* max_unavailable) {
+  ru_config cfg[16];
+  if (n < 0 || n > 16) return -1;
+  for (int i = 0; i < n; i++) {
+    cfg[i].max_surge = max_surge[i];
+    cfg[i].max_unavailable = max_unavailable[i];
+  }
+  return compute_total_steps(n, initial_old, target, cfg);
+}
+LWSO_API void lwso_ds_next_new(int n, const int* target, const int* current_new, int total_steps, int* result) {
+  compute_next_new_replicas(n, target, current_new, total_steps, result);
+}
+LWSO_API void lwso_ds_next_old(int n, const int* initial_old, const int* current_old, int total_steps, int* result) {
+  compute_next_old_replicas(n, initial_old, current_old, total_steps, result);
+}
+
 /* planner.go:252-262 */
 static int can_drain_all_to_zero(int n, const int* next_new, const int* initial_old, const int* target,
                                  const ru_config* cfg) {

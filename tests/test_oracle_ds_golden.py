@@ -239,3 +239,44 @@ def test_initial_replicas_annotation_rules():  # pkg/utils/disaggregatedset/util
     assert encoder.get_initial_replicas(mk("abc")) == -1
     assert encoder.get_initial_replicas(mk("5")) == 5
     assert encoder.get_initial_replicas(mk("99999999999")) == -1
+
+
+# ---- helper-level vectors of the reference (the oracle exports its helpers for exactly this) ----
+@pytest.mark.parametrize("surge,unavail,want", [(1, 0, 1), (2, 0, 2), (0, 1, 1), (0, 2, 2), (0, 0, 1), (3, 2, 3)])
+def test_batch_size(surge, unavail, want):  # planner_test.go:674-690
+    assert oracle.ds_batch_size(surge, unavail) == want
+
+
+@pytest.mark.parametrize(
+    "initial_old,target,surge,want",  # planner_test.go:692-720 (DefaultRollingUpdateConfig = surge 1, unavailable 0)
+    [((4, 4), (4, 4), (1, 1), 4), ((6, 2), (6, 2), (1, 1), 6), ((4, 4), (4, 4), (2, 2), 2), ((0, 0), (3, 3), (1, 1), 3)],
+)
+def test_compute_total_steps(initial_old, target, surge, want):
+    assert oracle.ds_total_steps(list(initial_old), list(target), list(surge), [0, 0]) == want
+
+
+def test_compute_next_new_replicas_edge_cases():  # planner_test.go:800-846
+    r = oracle.ds_next_new([0, 4], [0, 2], 4)
+    assert r[0] == 0 and r[1] > 2
+    r = oracle.ds_next_new([4, 0], [2, 0], 4)
+    assert r[0] > 2 and r[1] == 0
+    assert oracle.ds_next_new([4, 4], [2, 2], 0) == [4, 4]
+
+
+def test_compute_next_old_replicas_edge_cases():  # planner_test.go:852-898
+    r = oracle.ds_next_old([0, 4], [0, 3], 4)
+    assert r[0] == 0 and r[1] <= 3
+    r = oracle.ds_next_old([4, 0], [3, 0], 4)
+    assert r[0] <= 3 and r[1] == 0
+    assert oracle.ds_next_old([4, 4], [2, 2], 0) == [0, 0]
+
+
+def test_n_role_default_config():  # planner_test.go:1057-1069: surge 1, unavailable 0 when no config is given
+    for n in (3, 4, 5):
+        roles = [api.DisaggregatedRoleSpec(f"r{i}", 2) for i in range(n)]
+        kids = [api.ChildLWS(f"r{i}", "old", 2, 2, 1.0) for i in range(n)] + \
+               [api.ChildLWS(f"r{i}", "new", 0, 0, 2.0) for i in range(n)]
+        t = encoder.encode_ds([encoder.DsItem(api.DisaggregatedSet("t", roles=roles), "new", kids)])
+        _, role_out, _ = oracle.sweep_ds(t.ds, t.roles, t.revroles)
+        direct = oracle.ds_compute_next_step([2] * n, [2] * n, [0] * n, [2] * n, [1] * n, [0] * n)
+        assert [int(role_out[i]["next_new"]) for i in range(n)] == direct[1] == [1] * n

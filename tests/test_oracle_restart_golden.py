@@ -141,3 +141,21 @@ def test_sort_by_index_semantics_in_encoder():
     present = [(int(g["flags"]) & R.GRP_POD_PRESENT) != 0 for g in t.groups]
     assert present == [True, False, True]
     assert t.lws[0]["flags"] & R.LWS_GROUP_LABEL_INVALID  # updateConditions would fail on "abc" (:434)
+
+
+# pkg/utils/statefulset/statefulset_utils_test.go:81-153 StatefulsetReady: availableReplicas == *spec.replicas
+# and currentRevision == updateRevision — observable as the group's ready state (a ready leader pod
+# with a ready worker sts, leaderworkerset_controller.go:620-627)
+@pytest.mark.parametrize("available,current,update,want",
+                         [(3, "rev-1", "rev-1", True), (2, "rev-1", "rev-1", False),
+                          (3, "rev-1", "rev-2", False), (2, "rev-1", "rev-2", False)])
+def test_statefulset_ready(oracle_sweep, available, current, update, want):
+    lws = api.LeaderWorkerSet("test-lws", replicas=1, size=4)
+    leader = api.Pod("test-lws-0", labels=labels(lws, 0, 0), phase="Running", readyCondition=True)
+    wsts = api.StatefulSet("test-lws-0", replicas=3, availableReplicas=available, currentRevision=current,
+                           updateRevision=update,
+                           labels={api.SetNameLabelKey: lws.name, api.GroupIndexLabelKey: "0", api.RevisionKey: "revision-1"})
+    flags, _, _ = group_flags(oracle_sweep, lws, [leader], [wsts])
+    assert bool(flags & R.GOUT_STATE_READY) == want
+    assert bool(flags & R.GOUT_COND_READY) == want
+    assert flags & R.GOUT_STATE_UPDATED  # revisions of the leader pod and of the sts template both match
