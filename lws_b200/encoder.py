@@ -442,6 +442,20 @@ def encode_ds(items: Iterable[DsItem]) -> DsTablesHost:
 
 
 # --------------------------------------------------------------------------- #
+# PodGroup MinResources (host arithmetic: stays off the device)
+# --------------------------------------------------------------------------- #
+def pod_group_min_resources(leader_requests: Optional[dict], worker_requests: dict, size: int) -> dict:
+    """pkg/utils/utils.go:84-103 CalculatePGMinResources over pre-summed per-template request
+    vectors (resource name → integer milli-units; `PodRequests` of a single-container template):
+    leader (the worker template's when no leader template is given) + (size − 1) × worker."""
+    total = dict(worker_requests if leader_requests is None else leader_requests)
+    for _ in range(max(int(size) - 1, 0)):  # quotav1.Add: union of the keys, summed
+        for name, v in worker_requests.items():
+            total[name] = total.get(name, 0) + v
+    return total
+
+
+# --------------------------------------------------------------------------- #
 # Placement requests
 # --------------------------------------------------------------------------- #
 def encode_place_requests(lws: np.ndarray, groups: np.ndarray, ns_of_lws: Optional[np.ndarray] = None) -> np.ndarray:

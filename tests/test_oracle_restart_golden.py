@@ -159,3 +159,15 @@ def test_statefulset_ready(oracle_sweep, available, current, update, want):
     assert bool(flags & R.GOUT_STATE_READY) == want
     assert bool(flags & R.GOUT_COND_READY) == want
     assert flags & R.GOUT_STATE_UPDATED  # revisions of the leader pod and of the sts template both match
+
+
+def test_podgroup_min_resources():
+    """volcano_provider_test.go:65-139: three pods requesting 100m CPU each → MinResources cpu 300m, for
+    both startup policies (test/testutils/util.go:846-865: the same for LeaderCreated and LeaderReady)."""
+    worker = {"cpu": 100}
+    assert encoder.pod_group_min_resources(None, worker, 3) == {"cpu": 300}
+    assert encoder.pod_group_min_resources({"cpu": 100}, worker, 3) == {"cpu": 300}
+    # a leader template of its own, a resource only the workers ask for, size 1 (no workers)
+    assert encoder.pod_group_min_resources({"cpu": 500, "memory": 64}, {"cpu": 100, "nvidia.com/gpu": 8000}, 4) == {
+        "cpu": 800, "memory": 64, "nvidia.com/gpu": 24000}
+    assert encoder.pod_group_min_resources({"cpu": 500}, worker, 1) == {"cpu": 500}
