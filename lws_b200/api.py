@@ -102,6 +102,7 @@ class Pod:
     containerRestartCounts: list = field(default_factory=list)
     ownerReferences: list = field(default_factory=list)
     nodeName: str = ""
+    subdomain: str = ""  # spec.subdomain (set by the pod webhook for SubdomainUniquePerReplica)
 
     def __post_init__(self):
         if not self.uid:

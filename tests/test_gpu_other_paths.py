@@ -345,3 +345,19 @@ def test_ds_order_stability_readiness_vectors_on_gpu(engine):
     for ready, want in V.READY_CASES:
         ds_out, _, _ = gpu_sweep_ds(V.readiness_tables(ready))
         assert bool(ds_out[0]["flags"] & R.DOUT_NEW_READY) == want
+
+
+def test_webhook_label_batch_over_the_cuda_sha1_kernel(engine):
+    """lws_b200/webhook.py with Engine.group_keys_host as its hasher: the reference's webhook label
+    vectors and the three genGroupUniqueKey KATs (tests/test_webhook_batch.py holds them)."""
+    import test_webhook_batch as V
+    from lws_b200 import api, webhook
+
+    V.run_cases(engine.group_keys_host)
+    pods = [api.Pod(name, ns, labels={api.SetNameLabelKey: "x", api.WorkerIndexLabelKey: "0", api.GroupIndexLabelKey: "0"},
+                    annotations={api.SizeAnnotationKey: "1"})
+            for name, ns in (("test-sample", "default"), ("podName", "default"), ("test-sample", "leaderworkerset"))]
+    assert webhook.default_labels_batch(pods, engine.group_keys_host) == [None] * 3
+    assert [p.labels[api.GroupUniqueHashLabelKey] for p in pods] == [
+        "95e88034e460983f51a9952fe128729fbc0663b5", "390b34ab671d29e9997d7d4252b8bbf8da02f5b7",
+        "39f5d7e9122b9d94d3932e3720b43fd3b56347e8"]
