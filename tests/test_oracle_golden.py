@@ -91,3 +91,35 @@ def test_sha1_against_hashlib_all_padding_lengths():
 @pytest.mark.parametrize("pod_count,sg,widx,want", [(4, 2, 2, 1), (5, 2, 2, 0), (9, 4, 8, 1), (8, 4, 7, 1), (8, 4, 3, 0)])
 def test_sub_group_index(pod_count, sg, widx, want):
     assert oracle.lib().lwso_sub_group_index(pod_count, sg, widx) == want
+
+
+# pkg/controllers/leaderworkerset_controller_test.go:50-758 TestLeaderStatefulSetApplyConfig: the numeric fields
+# of the leader StatefulSet apply configuration — spec.replicas, the replicas annotation and
+# rollingUpdate.maxUnavailable = max(1, maxUnavailable + min(maxSurge, lws replicas)) (:811-830).  No
+# StatefulSet exists in these cases except the last one (3 replicas), so replicas = lws replicas (:290-298).
+@pytest.mark.parametrize(
+    "replicas,size,mu,ms,sts_replicas,want_mu,want_replicas",
+    [(1, 1, 1, 0, None, 1, 1),       # :63   defaults
+     (1, 2, 1, 0, None, 1, 1),       # :140  exclusive placement
+     (2, 2, 1, 0, None, 1, 2),       # :209  leader template
+     (1, 1, 2, 1, None, 3, 1),       # :279  2 maxUnavailable + 1 maxSurge
+     (1, 1, 0, 2, None, 1, 1),       # :346  maxSurge capped at the replica count: 0 + min(2, 1)
+     (1, 2, 1, 0, None, 1, 1),       # :413  subgroup size
+     (1, 1, 1, 0, None, 1, 1),       # :483  volumeClaimTemplates
+     (0, 1, 0, 0, None, 1, 0),       # :601  0 replicas, 0 / 0: at least 1
+     (2, 1, 1, "50%", 3, 2, None)],  # :670  50 % of the LWS replicas (2), not of the sts replicas (3): 1 + 1
+)
+def test_leader_statefulset_apply_config_numbers(oracle_sweep, replicas, size, mu, ms, sts_replicas, want_mu, want_replicas):
+    lws = api.LeaderWorkerSet(name="test-sample", replicas=replicas, size=size,
+                              rollingUpdate=api.RollingUpdateConfiguration(partition=0, maxUnavailable=mu, maxSurge=ms))
+    sts = None
+    if sts_replicas is not None:
+        sts = api.StatefulSet(name=lws.name, replicas=sts_replicas, partition=0,
+                              annotations={api.ReplicasAnnotationKey: str(replicas)})
+    item = encoder.LwsItem(lws=lws, revision_key="rev", lws_updated=False, leader_sts=sts)
+    t = encoder.encode_lws([item], encoder.Cluster())
+    lws_out, _ = oracle_sweep(t)
+    assert not lws_out[0]["flags"] & R.LOUT_RUP_ERROR
+    assert int(lws_out[0]["sts_max_unavailable"]) == want_mu
+    if want_replicas is not None:
+        assert int(lws_out[0]["sts_replicas"]) == want_replicas and int(lws_out[0]["sts_partition"]) == 0
