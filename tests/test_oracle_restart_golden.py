@@ -171,3 +171,19 @@ def test_podgroup_min_resources():
     assert encoder.pod_group_min_resources({"cpu": 500, "memory": 64}, {"cpu": 100, "nvidia.com/gpu": 8000}, 4) == {
         "cpu": 800, "memory": 64, "nvidia.com/gpu": 24000}
     assert encoder.pod_group_min_resources({"cpu": 500}, worker, 1) == {"cpu": 500}
+
+
+# pkg/controllers/pod_controller_test.go:42-425 TestConstructWorkerStatefulSetApplyConfiguration: the worker
+# StatefulSet has size − 1 replicas and ordinals starting at 1 (:434-443); Reconcile only builds it for
+# size > 1 (:138).  (Labels, templates and volume claims of that test are object construction.)
+@pytest.mark.parametrize("size,want_create,want_replicas", [(1, False, 0), (2, True, 1), (5, True, 4)])
+def test_worker_statefulset_replicas_and_gate(oracle_sweep, size, want_create, want_replicas):
+    lws = api.LeaderWorkerSet("test-sample", replicas=2, size=size)
+    leader = api.Pod("test-sample-1", labels=labels(lws, 1, 0), phase="Running", readyCondition=True)
+    item = encoder.LwsItem(lws=lws, revision_key="revision-1",
+                           leader_sts=api.StatefulSet(name=lws.name, replicas=2, annotations={api.ReplicasAnnotationKey: "2"}))
+    t = encoder.encode_lws([item], encoder.Cluster(pods=[leader]))
+    _, go = oracle_sweep(t)
+    assert bool(go[1]["flags"] & R.GOUT_CREATE_WSTS) == want_create
+    assert int(go[1]["worker_replicas"]) == want_replicas  # pods <lws>-1-1 … <lws>-1-(size-1)
+    assert not go[0]["flags"] & R.GOUT_CREATE_WSTS  # group 0 has no leader pod yet
