@@ -123,3 +123,12 @@ def test_leader_statefulset_apply_config_numbers(oracle_sweep, replicas, size, m
     assert int(lws_out[0]["sts_max_unavailable"]) == want_mu
     if want_replicas is not None:
         assert int(lws_out[0]["sts_replicas"]) == want_replicas and int(lws_out[0]["sts_partition"]) == 0
+
+
+# pkg/webhooks/leaderworkerset_webhook_test.go:27-83 getPercentValue: the input domain of the percent fields —
+# an int is not a percentage, a string without '%' is invalid, "1%" and "101%" parse (the > 100 check is a
+# separate validation, :126-170).  The encoder's parser is what feeds the kernels' percent flags.
+@pytest.mark.parametrize("value,want_val,want_pct,want_valid",
+                         [(1, 1, False, True), ("1", 0, False, False), ("1%", 1, True, True), ("101%", 101, True, True)])
+def test_percent_value_parsing(value, want_val, want_pct, want_valid):
+    assert encoder.parse_int_or_percent(value) == (want_val, want_pct, want_valid)
