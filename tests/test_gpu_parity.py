@@ -150,6 +150,10 @@ def test_reference_integration_traces_on_gpu(engine):
             for g, w in zip(got, want):
                 if w is not None:
                     assert g == w, f"{name} step {i}: got {got} want {want}"
+    # the scale / create / startup-policy / condition entries (tests/test_oracle_lifecycle_traces.py)
+    from test_oracle_lifecycle_traces import run_lifecycle_entries
+
+    run_lifecycle_entries(sweep)
 
 
 def test_large_idempotent_and_order_independent(engine):

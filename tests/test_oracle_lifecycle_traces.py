@@ -1,0 +1,118 @@
+"""More entries of test/integration/controllers/leaderworkerset_test.go replayed through tests/sim.py —
+the scale / create / startup-policy / condition entries (the rolling-update family is tests/traces.py):
+
+  :90   scale up number of groups            :109  scale down number of groups
+  :128  scale down to 0                      :147  scale up from 0
+  :166  group size is 1                      :187  zero replicas
+  :200  2 groups, size 2                     :215  deleted worker StatefulSet is recreated
+  :346  available state                      :359  progressing → available → progressing
+  :2091 startupPolicy LeaderReady            :2120 startupPolicy LeaderCreated
+
+What the reference asserts there and what is checked here: the leader StatefulSet's replica count
+(ExpectValidLeaderStatefulSet, test/testutils/validators.go), one worker StatefulSet of size − 1 replicas
+per existing leader pod and none for size 1 (ExpectValidWorkerStatefulSets / …NotCreated), and the
+LWS condition (ExpectLeaderWorkerSetAvailable / Progressing).
+"""
+import pytest
+
+from lws_b200 import api
+from lws_b200 import records as R
+from sim import LwsSim
+
+AV, PR = R.COND_AVAILABLE, R.COND_PROGRESSING
+
+
+def build(replicas=2, size=2, startup=api.LeaderCreatedStartupPolicy):  # wrappers.BuildLeaderWorkerSet defaults
+    return api.LeaderWorkerSet(name="test-sample", replicas=replicas, size=size, startupPolicy=startup,
+                               restartPolicy=api.RecreateGroupOnPodRestart,
+                               rollingUpdate=api.RollingUpdateConfiguration(partition=0, maxUnavailable=1, maxSurge=0))
+
+
+def start(sweep, **kw):
+    """The table's preamble: create the LWS, wait for the leader sts, create the leader pods."""
+    sim = LwsSim(build(**kw), sweep)
+    sim.settle()
+    sim.create_leader_pods(0, sim.lws.replicas)
+    return sim
+
+
+def expect_valid(sim, replicas):
+    assert sim.leader_sts.replicas == replicas
+    want = {name for name in sim.pods} if sim.lws.size > 1 else set()
+    assert set(sim.stss) == want, (sorted(sim.stss), sorted(want))
+    for sts in sim.stss.values():
+        assert sts.replicas == sim.lws.size - 1
+
+
+def set_leader_pods_ready(sim, a, b):
+    """SetLeaderPodsToReady (test/testutils/util.go:693-719): leader pods only, no worker sts status."""
+    for i in range(a, b):
+        pod = sim.pods[f"{sim.lws.name}-{i}"]
+        pod.phase, pod.readyCondition = "Running", True
+    sim.settle()
+
+
+def run_lifecycle_entries(sweep):
+    # :90 scale up number of groups
+    sim = start(sweep, replicas=2)
+    sim.set_replicas(3)
+    sim.create_leader_pods(2, 3)
+    expect_valid(sim, 3)
+    # :109 scale down number of groups
+    sim = start(sweep, replicas=4)
+    sim.set_replicas(3)
+    sim.delete_leader_pods_above_replicas()
+    expect_valid(sim, 3)
+    # :128 scale down to 0
+    sim = start(sweep, replicas=2)
+    sim.set_replicas(0)
+    sim.delete_leader_pods_above_replicas()
+    expect_valid(sim, 0)
+    assert not sim.pods and not sim.stss
+    # :147 scale up from 0
+    sim = start(sweep, replicas=0)
+    expect_valid(sim, 0)
+    sim.set_replicas(3)
+    sim.create_leader_pods(0, 3)
+    expect_valid(sim, 3)
+    # :166 group size is 1: no worker StatefulSets; ready leaders alone make it available
+    sim = start(sweep, size=1)
+    expect_valid(sim, 2)
+    set_leader_pods_ready(sim, 0, 2)
+    assert sim.status["condition"] == AV and sim.status["readyReplicas"] == 2
+    # :187 zero replicas
+    sim = start(sweep, replicas=0)
+    expect_valid(sim, 0)
+    # :200 two groups of size 2: a worker sts per leader pod
+    sim = start(sweep)
+    expect_valid(sim, 2)
+    assert sorted(sim.stss) == ["test-sample-0", "test-sample-1"]
+    # :215 a deleted worker StatefulSet is recreated
+    del sim.stss["test-sample-0"]
+    sim.settle()
+    expect_valid(sim, 2)
+    # :346 available state
+    sim = start(sweep)
+    sim.set_all_ready()
+    assert sim.status["condition"] == AV
+    # :359 progressing → available → progressing (0 of 2 ready, 2 of 2, then 2 of 3 after a scale-up)
+    sim = start(sweep)
+    assert sim.status["condition"] == PR and sim.status["readyReplicas"] == 0
+    sim.set_all_ready()
+    assert sim.status["condition"] == AV and sim.status["readyReplicas"] == 2
+    sim.set_replicas(3)
+    assert sim.status["condition"] == PR and sim.status["readyReplicas"] == 2
+    # :2091 startupPolicy LeaderReady: worker StatefulSets only for leaders that are ready
+    sim = start(sweep, replicas=4, startup=api.LeaderReadyStartupPolicy)
+    assert not sim.stss
+    set_leader_pods_ready(sim, 0, 2)
+    assert sorted(sim.stss) == ["test-sample-0", "test-sample-1"]
+    set_leader_pods_ready(sim, 2, 4)
+    assert sorted(sim.stss) == [f"test-sample-{i}" for i in range(4)]
+    # :2120 startupPolicy LeaderCreated: all of them at once
+    sim = start(sweep, replicas=4, startup=api.LeaderCreatedStartupPolicy)
+    assert sorted(sim.stss) == [f"test-sample-{i}" for i in range(4)]
+
+
+def test_lifecycle_entries_on_the_oracle(oracle_sweep):
+    run_lifecycle_entries(oracle_sweep)
