@@ -7,6 +7,7 @@ the scale / create / startup-policy / condition entries (the rolling-update fami
   :200  2 groups, size 2                     :215  deleted worker StatefulSet is recreated
   :346  available state                      :359  progressing → available → progressing
   :2091 startupPolicy LeaderReady            :2120 startupPolicy LeaderCreated
+  :1878 a not-yet-updated group that restarts during an update gets its worker sts back with the OLD spec
 
 What the reference asserts there and what is checked here: the leader StatefulSet's replica count
 (ExpectValidLeaderStatefulSet, test/testutils/validators.go), one worker StatefulSet of size − 1 replicas
@@ -112,6 +113,28 @@ def run_lifecycle_entries(sweep):
     # :2120 startupPolicy LeaderCreated: all of them at once
     sim = start(sweep, replicas=4, startup=api.LeaderCreatedStartupPolicy)
     assert sorted(sim.stss) == [f"test-sample-{i}" for i in range(4)]
+
+
+    # :1878-1962 restart of a not-yet-updated group during a rolling update
+    UP = R.COND_UPDATE_IN_PROGRESS
+    rev = lambda sim, i: sim.stss[f"test-sample-{i}"].labels[api.RevisionKey]
+    sim = start(sweep, replicas=4)
+    sim.set_all_ready()
+    assert sim.status["condition"] == AV and (sim.status["readyReplicas"], sim.status["updatedReplicas"]) == (4, 4)
+    expect_valid(sim, 4)
+    sim.update_template()  # UpdateWorkerTemplate
+    assert sim.status["condition"] == UP and (sim.status["readyReplicas"], sim.status["updatedReplicas"]) == (4, 0)
+    sim.set_pod_group_ready(3)
+    assert (sim.status["readyReplicas"], sim.status["updatedReplicas"]) == (4, 1) and sim.status["condition"] == UP
+    assert rev(sim, 3) == "rev-2" and [rev(sim, i) for i in (2, 1, 0)] == ["rev-1"] * 3
+    sim.delete_leader_pod(0, 1)
+    sim.create_leader_pods(0, 1, rev_key="rev-1")  # CreateLeaderPodsFromRevisionNumber(…, 1): the old template
+    expect_valid(sim, 4)
+    assert rev(sim, 3) == "rev-2" and [rev(sim, i) for i in (2, 1, 0)] == ["rev-1"] * 3  # old spec again
+    assert sim.status["condition"] == UP
+    sim.set_all_ready()
+    expect_valid(sim, 4)
+    assert sim.status["condition"] == AV and all(rev(sim, i) == "rev-2" for i in range(4))
 
 
 def test_lifecycle_entries_on_the_oracle(oracle_sweep):
