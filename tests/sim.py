@@ -25,7 +25,8 @@ class LwsSim:
         self.gang = gang
         self.template_rev = 1  # bumped by update_template(): a new ControllerRevision
         self.leader_sts = None
-        self.pods: dict[str, api.Pod] = {}
+        self.pods: dict[str, api.Pod] = {}  # leader pods
+        self.workers: dict[str, api.Pod] = {}  # worker pods (only the entries that need them create any)
         self.stss: dict[str, api.StatefulSet] = {}
         self.nodes = nodes or []
         self.topology_key = topology_key
@@ -42,7 +43,8 @@ class LwsSim:
 
     def _cluster(self):
         return encoder.Cluster(
-            pods=list(self.pods.values()), statefulsets=list(self.stss.values()), nodes=self.nodes
+            pods=list(self.pods.values()) + list(self.workers.values()), statefulsets=list(self.stss.values()),
+            nodes=self.nodes
         )
 
     def _sweep(self):
@@ -183,6 +185,38 @@ class LwsSim:
             if int(name.rsplit("-", 1)[1]) >= self.lws.replicas:
                 del self.pods[name]
                 self.stss.pop(name, None)
+        self.settle()
+
+    def create_worker_pods(self, group):
+        """CreateWorkerPodsForLeaderPod (test/testutils/util.go:58-88): workers 1..size-1 of the group,
+        owned by the leader Pod, carrying the leader pod's current revision key."""
+        leader = self.pods[f"{self.lws.name}-{group}"]
+        for w in range(1, self.lws.size):
+            name = f"{leader.name}-{w}"
+            self.workers[name] = api.Pod(
+                name=name,
+                namespace=self.lws.namespace,
+                labels={
+                    api.SetNameLabelKey: self.lws.name,
+                    api.WorkerIndexLabelKey: str(w),
+                    api.GroupIndexLabelKey: leader.labels[api.GroupIndexLabelKey],
+                    api.RevisionKey: leader.labels[api.RevisionKey],
+                },
+                annotations={api.SizeAnnotationKey: str(self.lws.size)},
+                phase="Running",
+                ownerReferences=[api.OwnerReference("Pod", leader.name, leader.uid)],
+            )
+        self.settle()
+
+    def delete_worker_pods(self, names=None):
+        """k8sClient.Delete on worker pods: the pod controller sees them with a deletionTimestamp
+        (PodDeleted, pod_utils.go:48); afterwards they are gone."""
+        names = list(self.workers) if names is None else list(names)
+        for n in names:
+            self.workers[n].deletionTimestamp = True
+        self.settle()
+        for n in names:
+            del self.workers[n]
         self.settle()
 
     # ------------------------------------------------------------ lws edits

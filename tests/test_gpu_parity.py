@@ -150,10 +150,6 @@ def test_reference_integration_traces_on_gpu(engine):
             for g, w in zip(got, want):
                 if w is not None:
                     assert g == w, f"{name} step {i}: got {got} want {want}"
-    # the scale / create / startup-policy / condition entries (tests/test_oracle_lifecycle_traces.py)
-    from test_oracle_lifecycle_traces import run_lifecycle_entries
-
-    run_lifecycle_entries(sweep)
 
 
 def test_large_idempotent_and_order_independent(engine):
@@ -339,3 +335,16 @@ def test_fuzz_campaign(engine, seed):
     want = oracle.place(t.nodes, got[2], t.n_domains, n_ns, reqs)
     out, _ = engine.place_host(reqs, got[2], n_ns)
     assert_same(out, want, "place_out")
+
+
+def test_reference_lifecycle_entries_on_gpu(engine):
+    """The scale / create / startup-policy / condition / restart-during-update entries of the reference's
+    integration table (tests/test_oracle_lifecycle_traces.py), reconciled by the CUDA engine."""
+    from test_oracle_lifecycle_traces import run_lifecycle_entries
+
+    def sweep(tables, flags=0):
+        engine.upload_nodes(tables.nodes, tables.n_domains)
+        lo, go, _ = engine.sweep_lws_host(tables.lws, tables.groups, tables.pod_state, tables.pod_ident, flags=flags)
+        return lo, go
+
+    run_lifecycle_entries(sweep)

@@ -8,6 +8,9 @@ the scale / create / startup-policy / condition entries (the rolling-update fami
   :346  available state                      :359  progressing → available → progressing
   :2091 startupPolicy LeaderReady            :2120 startupPolicy LeaderCreated
   :1878 a not-yet-updated group that restarts during an update gets its worker sts back with the OLD spec
+  :1964 RecreateGroupOnPodRestart during a rolling update: deleting the workers of the OLD revision does not
+        delete the already updated leader (handleRestartPolicy compares revisions, pod_controller.go:239);
+        after the update a worker deletion recreates the group
 
 What the reference asserts there and what is checked here: the leader StatefulSet's replica count
 (ExpectValidLeaderStatefulSet, test/testutils/validators.go), one worker StatefulSet of size − 1 replicas
@@ -135,6 +138,25 @@ def run_lifecycle_entries(sweep):
     sim.set_all_ready()
     expect_valid(sim, 4)
     assert sim.status["condition"] == AV and all(rev(sim, i) == "rev-2" for i in range(4))
+
+
+    # :1964-2054 the leader is only restarted once during a rolling update
+    sim = start(sweep, replicas=4)
+    sim.set_all_ready()
+    sim.create_worker_pods(3)
+    assert sim.status["condition"] == AV and (sim.status["readyReplicas"], sim.status["updatedReplicas"]) == (4, 4)
+    sim.update_template()
+    assert sim.status["condition"] == UP and (sim.status["readyReplicas"], sim.status["updatedReplicas"]) == (4, 0)
+    sim.set_pod_group_ready(3)  # the leader pod of group 3 now carries the new revision
+    assert (sim.status["readyReplicas"], sim.status["updatedReplicas"]) == (4, 1)
+    sim.delete_worker_pods()  # old-revision workers go away: this must not delete the leader
+    assert not sim.pods["test-sample-3"].deletionTimestamp and not sim.deleted_leaders
+    sim.set_all_ready()
+    sim.create_worker_pods(3)
+    expect_valid(sim, 4)
+    assert sim.status["condition"] == AV
+    sim.delete_worker_pods(["test-sample-3-1"])  # same revision now: the group is recreated
+    assert sim.pods["test-sample-3"].deletionTimestamp and sim.deleted_leaders == ["test-sample-3"]
 
 
 def test_lifecycle_entries_on_the_oracle(oracle_sweep):
