@@ -8,6 +8,8 @@ the scale / create / startup-policy / condition entries (the rolling-update fami
   :346  available state                      :359  progressing → available → progressing
   :2091 startupPolicy LeaderReady            :2120 startupPolicy LeaderCreated
   :1878 a not-yet-updated group that restarts during an update gets its worker sts back with the OLD spec
+  :2575 PodGroup per leader pod, MinMember = size; gang rolling update 2 → 1 → 0
+  :2277 resize (size 3 → 4) rolls every group and resizes the worker StatefulSets
   :1964 RecreateGroupOnPodRestart during a rolling update: deleting the workers of the OLD revision does not
         delete the already updated leader (handleRestartPolicy compares revisions, pod_controller.go:239);
         after the update a worker deletion recreates the group
@@ -159,5 +161,54 @@ def run_lifecycle_entries(sweep):
     assert sim.pods["test-sample-3"].deletionTimestamp and sim.deleted_leaders == ["test-sample-3"]
 
 
+def run_more_entries(sweep):
+    """Entries added after the GPU budget of the round was spent: oracle only for now."""
+    # :2277-2310 resize should update the size of the replicas (a size change is a template change)
+    sim = start(sweep, replicas=2, size=3)
+    sim.set_all_ready()
+    assert sim.status["condition"] == AV and sim.leader_sts.partition == 0
+    expect_valid(sim, 2)
+    assert (sim.status["readyReplicas"], sim.status["updatedReplicas"]) == (2, 2)
+    sim.lws.size = 4  # UpdateSize
+    sim.update_template()
+    sim.set_all_ready()
+    assert sim.status["condition"] == AV and sim.leader_sts.partition == 0
+    expect_valid(sim, 2)  # worker StatefulSets now have size - 1 = 3 replicas
+    assert all(sts.replicas == 3 for sts in sim.stss.values())
+    assert (sim.status["readyReplicas"], sim.status["updatedReplicas"]) == (2, 2)
+
+
+    # :2575-2660 gang scheduling (a SchedulerProvider is configured): a PodGroup per leader pod with
+    # MinMember = size, and the rolling update walks the partition 2 → 1 → 0 with 3 replicas
+    UP = R.COND_UPDATE_IN_PROGRESS
+
+    def pod_groups_ok(sim, n):
+        sim.reconcile_pods()
+        go = sim.last_group_out
+        assert int(sim.last_lws_out[0]["min_member"]) == sim.lws.size
+        assert [bool(go[i]["flags"] & R.GOUT_CREATE_PODGROUP) for i in range(n)] == [True] * n
+
+    sim = LwsSim(build(replicas=2), sweep, gang=True)
+    sim.settle()
+    sim.create_leader_pods(0, 2)
+    pod_groups_ok(sim, 2)
+    sim = LwsSim(build(replicas=3), sweep, gang=True)
+    sim.settle()
+    sim.create_leader_pods(0, 3)
+    sim.set_all_ready()
+    assert sim.status["condition"] == AV and sim.leader_sts.partition == 0
+    pod_groups_ok(sim, 3)
+    sim.update_template()
+    assert sim.status["condition"] == UP and sim.leader_sts.partition == 2
+    sim.set_pod_group_ready(2)
+    assert sim.leader_sts.partition == 1
+    sim.set_pod_group_ready(1)
+    assert sim.leader_sts.partition == 0
+    sim.set_pod_group_ready(0)
+    assert sim.status["condition"] == AV
+    pod_groups_ok(sim, 3)
+
+
 def test_lifecycle_entries_on_the_oracle(oracle_sweep):
     run_lifecycle_entries(oracle_sweep)
+    run_more_entries(oracle_sweep)
