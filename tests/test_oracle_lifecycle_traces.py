@@ -9,6 +9,7 @@ the scale / create / startup-policy / condition entries (the rolling-update fami
   :2091 startupPolicy LeaderReady            :2120 startupPolicy LeaderCreated
   :1878 a not-yet-updated group that restarts during an update gets its worker sts back with the OLD spec
   :2575 PodGroup per leader pod, MinMember = size; gang rolling update 2 → 1 → 0
+  :395  exclusive placement: worker StatefulSets wait for the leader pod to be scheduled; topology value
   :2277 resize (size 3 → 4) rolls every group and resizes the worker StatefulSets
   :1964 RecreateGroupOnPodRestart during a rolling update: deleting the workers of the OLD revision does not
         delete the already updated leader (handleRestartPolicy compares revisions, pod_controller.go:239);
@@ -207,6 +208,40 @@ def run_more_entries(sweep):
     sim.set_pod_group_ready(0)
     assert sim.status["condition"] == AV
     pod_groups_ok(sim, 3)
+
+
+    # :395-406 exclusive placement: no worker StatefulSet until the leader pod is scheduled
+    # (validators.go:224-226: "only expect sts count to be 1"), then one per leader, carrying the
+    # topology value of the leader's node as nodeSelector (pod_controller.go:162-172, :297-336)
+    key = "cloud.google.com/gke-nodepool"
+    nodes = [api.Node("node-a", labels={key: "pool-1"}), api.Node("node-b", labels={key: "pool-2"}),
+             api.Node("node-nolabel")]
+    lws = build()
+    lws.annotations[api.ExclusiveKeyAnnotationKey] = key
+    sim = LwsSim(lws, sweep, nodes=nodes, topology_key=key)
+    sim.settle()
+    sim.create_leader_pods(0, 2)
+    assert sim.leader_sts.replicas == 2 and not sim.stss  # leaders are not scheduled yet
+    assert all(sim.last_group_out[i]["flags"] & R.GOUT_WAIT_SCHEDULE for i in range(2))
+    sim.pods["test-sample-0"].nodeName = "node-a"
+    sim.pods["test-sample-1"].nodeName = "node-b"
+    sim.settle()
+    assert sorted(sim.stss) == ["test-sample-0", "test-sample-1"]
+    node_dom = {n: int(sim.last_tables.nodes["domain_id"][k]) for k, n in enumerate(["node-a", "node-b", "node-nolabel"])}
+    # (the domain is reported together with CREATE_WSTS, i.e. while the worker sts does not exist yet)
+    # pod_controller.go:330: a node without the topology label is an error — no worker sts for that group
+    sim.stss.clear()
+    sim.pods["test-sample-1"].nodeName = "node-nolabel"
+    sim._sweep()
+    go = sim.last_group_out
+    assert go[0]["flags"] & R.GOUT_CREATE_WSTS and int(go[0]["domain_id"]) == node_dom["node-a"]
+    assert go[1]["flags"] & R.GOUT_TOPOLOGY_ERROR and not go[1]["flags"] & R.GOUT_CREATE_WSTS
+    # :327 a node that does not exist yields an empty value and no error: the worker sts is created
+    sim.pods["test-sample-1"].nodeName = "node-gone"
+    sim._sweep()
+    go = sim.last_group_out
+    assert go[1]["flags"] & R.GOUT_CREATE_WSTS and not go[1]["flags"] & R.GOUT_TOPOLOGY_ERROR
+    assert int(go[1]["domain_id"]) == R.NONE
 
 
 def test_lifecycle_entries_on_the_oracle(oracle_sweep):
