@@ -1,27 +1,32 @@
 #!/usr/bin/env python
-"""Benchmark of the reconcile sweep — BASELINE.json's metric on its config.
+"""Benchmark of the reconcile tick — BASELINE.json's metric on its config.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3|C3-steady|C2|C5|C4]
 
-metric   pod-group reconciles/sec: pod groups swept / time of one full sweep
-         (group+pod pass, LWS pass; the placement round when the workload has
+metric   pod-group reconciles/sec: pod groups brought up to date / time of one tick (fused pod
+         scan + group pass, LWS pass; the placement round when the workload has
          exclusive-topology groups).
-workload BASELINE.json configs[2] ("C3"): 100k LWS x size 64 (100k groups,
-         6.4M pod rows), 10k nodes, topology-aware gang placement on.  It fits
-         one GPU, so N=1 runs exactly it; N>1 is weak scaling — every rank holds
-         its own C3-sized shard of an N-times larger cluster (objects shard by
-         LWS UID hash, no data-path collective for the sweep).
-value    whole-job groups/s with the tables resident in HBM (CUDA events on the
-         launching stream, max over ranks).  Inputs rotate through copies whose
-         total size exceeds L2, so no step reads a warm cache.
-e2e      the same metric through lwse_sweep_lws_host(): pinned host tables in,
-         host result tables out, H2D + kernels + D2H inside the timed region.
-roofline the dominant kernel (group/pod pass) alone: algorithmic bytes / its
-         CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth.
-cpu_baseline  the CPU oracle (a port of the reference's Go arithmetic — the
-         reference itself needs a Go toolchain, absent here) on one host core.
+workload BASELINE.json configs[2] ("C3"): 100k LWS x size 64 (100k groups, 6.3M pod rows), 10k
+         nodes, topology-aware gang placement on for every group (200 namespaces, 5 % of the
+         leaders unscheduled).  It fits one GPU, so N=1 runs exactly it; N>1 is weak scaling by
+         default — every rank holds its own C3-sized shard of an N-times larger cluster (objects
+         shard by LWS UID hash, no data-path collective for the sweep) — and `--scaling strong`
+         shards the ONE C3 cluster over the ranks.
+value    whole-job groups/s with the tables resident in HBM (CUDA events on the launching
+         stream, max over ranks).  Inputs rotate through copies whose total size exceeds L2.
+e2e      the same metric through the product path a controller uses, lwse_resident_tick():
+         watch-event churn in (1 % of the pod state rows + scheduling events per tick, written
+         into the engine's pinned arena), changed result rows out (pinned change lists), the
+         full sweep and the placement round inside, HOST wall clock around the call.
+         e2e.full_handover is the stateless path (lwse_reconcile_host: every table handed over
+         every step).
+roofline the dominant kernel alone: algorithmic bytes / its CUDA-event duration, against
+         MEASURED_PEAKS.json's HBM copy bandwidth.
+cpu_baseline  the CPU oracle (a port of the reference's Go arithmetic — the reference itself
+         needs a Go toolchain, absent here) on one host core, full sweep.
 
---impl reference times that same oracle on all host threads (rank 0 only).
+--impl reference times that same oracle on the host threads as an event-driven controller: per
+step it applies the same churn to its host tables and reconciles the dirty objects (rank 0 only).
 """
 from __future__ import annotations
 
@@ -41,6 +46,8 @@ import numpy as np  # noqa: E402
 METRIC = "pod-group reconciles/sec on 100k-group x 10k-node synthetic cluster"
 UNIT = "groups/s"
 L2_BYTES = 126 * 1024 * 1024
+CHURN = 0.01        # share of the pod state rows that change per tick (the e2e workload)
+CHURN_REQS = 0.01   # share of the placement requests that change sides per tick
 
 
 def parse():
@@ -51,13 +58,15 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU placement step: 'peer' = lwse_exchange_* (peer stores over NVLink, no "
                          "collective library on the data path), 'nccl' = one NCCL all-gather per step")
     ap.add_argument("--graph", action="store_true",
                     help="replay CUDA graphs instead of eager launches (measured slower: programmatic "
                          "dependent launch does not span graph replays)")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle comparison of the outputs")
     return ap.parse_args()
 
 
@@ -128,48 +137,72 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
-def make_tables(args, rank):
+def make_tables(args, rank, world=1):
+    """The rank's tables.  weak scaling: every rank its own cluster shard (own seed, own
+    namespaces); strong scaling: the one cluster of seed 0 split by LWS UID hash."""
     from lws_b200 import synth
 
+    if args.scaling == "strong" and world > 1:
+        from lws_b200 import distributed as D
+        from lws_b200 import records as R
+
+        t = synth.make(args.workload, args.scale, seed=synth.SEED)
+        s_lws, s_grp, s_pst, s_pid, lrows, _ = D.shard_lws_tables(t.lws, t.groups, t.pod_state, t.pod_ident, world)[rank]
+        return synth.Tables(profile=t.profile, lws=s_lws, groups=s_grp, pod_state=s_pst, pod_ident=s_pid, nodes=t.nodes,
+                            n_domains=t.n_domains, flags=t.flags, ns_of_lws=t.ns_of_lws[lrows], n_namespaces=t.n_namespaces)
     return synth.make(args.workload, args.scale, seed=synth.SEED + rank)
 
 
-def _cpu_step_fn(t, threads):
-    """One CPU step = the oracle's sweep over the whole workload (+ the placement spec
-    round when the workload has exclusive-topology groups)."""
-    import ctypes as C
+# --------------------------------------------------------------------------- #
+# the CPU arm
+# --------------------------------------------------------------------------- #
+class CpuArm:
+    """The reference's arithmetic (oracle port) as a controller would run it: host tables, the
+    placement spec round, and — for the churn workload — event-driven reconciles of the dirty objects."""
 
-    import oracle
-    from lws_b200 import encoder
-    from lws_b200 import records as R
+    def __init__(self, t, threads):
+        import oracle
+        from lws_b200 import records as R
 
-    lws_out = R.aligned_empty(len(t.lws), R.LWS_OUT)
-    group_out = R.aligned_empty(len(t.groups), R.GROUP_OUT)
-    tab = R.LwsTables(R.ptr(t.lws), len(t.lws), R.ptr(t.groups), len(t.groups), R.ptr(t.pod_state),
-                      R.ptr(t.pod_ident), len(t.pod_state), R.ptr(lws_out), R.ptr(group_out), None, t.flags)
-    reqs = encoder.encode_place_requests(t.lws, t.groups)
-    sched = (t.pod_state & R.POD_SCHEDULED) != 0
-    occ = np.bincount((t.pod_state[sched] >> R.POD_NODE_SHIFT).astype(np.int64), minlength=len(t.nodes)).astype(np.uint32)
-    pout = R.aligned_empty(len(reqs), R.PLACE_OUT)
-    lib = oracle.lib()
-    keep = (lws_out, group_out, reqs, occ, pout, tab)
+        self.o, self.R, self.t, self.threads = oracle, R, t, threads
+        self.lws, self.groups = t.lws.copy(), t.groups.copy()
+        self.pst, self.pid = t.pod_state.copy(), t.pod_ident
+        self.reqs = t.place_requests()
+        self.occ = R.occupancy_of(t.pod_ident, len(t.nodes))
+        self.lws_out = R.aligned_empty(len(t.lws), R.LWS_OUT)
+        self.group_out = R.aligned_empty(len(t.groups), R.GROUP_OUT)
+        self.place_out = None
 
-    def step():
-        lib.lwso_sweep_lws(C.byref(tab), R.ptr(t.nodes), len(t.nodes), threads)
-        if len(reqs):
-            lib.lwso_place(R.ptr(t.nodes), len(t.nodes), R.ptr(occ), t.n_domains, 1, R.ptr(reqs), len(reqs), R.ptr(pout))
+    def place(self):
+        if len(self.reqs):
+            self.place_out = self.o.place(self.t.nodes, self.occ, self.t.n_domains, self.t.n_namespaces, self.reqs,
+                                          threads=self.threads)
 
-    step.keep = keep
-    return step
+    def full_step(self):
+        lo, go, _ = self.o.sweep_lws(self.lws, self.groups, self.pst, self.pid, self.t.nodes, flags=self.t.flags,
+                                     threads=self.threads)
+        self.lws_out, self.group_out = lo, go
+        self.place()
+
+    def churn_step(self, ps):
+        o, R = self.o, self.R
+        o.apply_patch(self.pst, ps.pod_rows, ps.pod_vals)
+        if len(ps.grp_rows):
+            o.apply_patch(self.groups, ps.grp_rows, ps.grp_vals)
+        if len(ps.req_rows):
+            o.apply_patch(self.reqs, ps.req_rows, ps.req_vals)
+        o.sweep_dirty(self.lws, self.groups, self.pst, self.pid, self.t.nodes, self.lws_out, self.group_out,
+                      ps.dirty_groups, ps.dirty_lws, flags=self.t.flags, threads=self.threads)
+        self.place()  # the placement spec has no incremental form: the round is solved again
 
 
 def cpu_oracle_rate(t, threads, min_seconds=1.0, max_reps=50):
-    """groups/s of the CPU oracle over the whole workload, `threads` host threads."""
-    step = _cpu_step_fn(t, threads)
-    step()  # warm
+    """groups/s of the CPU oracle over the whole workload (full sweep + placement spec round)."""
+    arm = CpuArm(t, threads)
+    arm.full_step()  # warm
     reps, t0 = 0, time.perf_counter()
     while True:
-        step()
+        arm.full_step()
         reps += 1
         dt = time.perf_counter() - t0
         if dt >= min_seconds or reps >= max_reps:
@@ -177,54 +210,232 @@ def cpu_oracle_rate(t, threads, min_seconds=1.0, max_reps=50):
     return len(t.groups) * reps / dt, dt / reps, reps
 
 
+def churn_plan(t, reqs, place_out, frac_pods=CHURN, frac_reqs=CHURN_REQS, n_sets=4):
+    """The tick-by-tick event stream both arms digest (same seed: same events)."""
+    from lws_b200 import churn
+    from lws_b200 import records as R
+
+    if frac_pods <= 0:
+        return [churn.PatchSet(np.zeros(0, np.uint32), R.aligned_empty(0, R.POD_STATE))]
+    return churn.make_plan(t, reqs if len(reqs) else None, place_out if len(reqs) else None, frac_pods,
+                           frac_reqs if len(reqs) else 0.0, n_sets=n_sets, seed=11)
+
+
 def run_reference(args):
-    """The reference arm: the reference's CPU arithmetic (oracle port) on all host threads."""
+    """The reference arm: the reference's CPU arithmetic (oracle port) on the host threads, driven
+    by the same churn plan as the engine's e2e leg."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    t = make_tables(args, 0)
-    # the port spawns its worker threads per sweep; pick the thread count that is fastest on this
+    if args.workload == "C4":
+        return run_reference_ds(args)
+    t = make_tables(args, 0, world)
+    # the port spawns its worker threads per step; pick the thread count that is fastest on this
     # box (more threads than the memory system can feed only add spawn cost) — the baseline gets
     # the best configuration available to it
+    probe = CpuArm(t, 1)
+    probe.full_step()
+    plan = churn_plan(t, probe.reqs, probe.place_out)
     best = None
-    for cand in sorted({c for c in (4, 8, 16, 32, 64, 128, host_threads()) if c <= host_threads()}):
-        fn = _cpu_step_fn(t, cand)
-        fn()
+    for cand in sorted({c for c in (1, 4, 8, 16, 32, 64, 128, host_threads()) if c <= host_threads()}):
+        arm = CpuArm(t, cand)
+        arm.full_step()
+        arm.churn_step(plan[0])
         t0 = time.perf_counter()
-        for _ in range(3):
-            fn()
-        dt = (time.perf_counter() - t0) / 3
+        for k in range(4):
+            arm.churn_step(plan[(k + 1) % len(plan)])
+        dt = (time.perf_counter() - t0) / 4
         if best is None or dt < best[0]:
-            best = (dt, cand, fn)
-    _, threads, step = best
+            best = (dt, cand)
+    threads = best[1]
+    arm = CpuArm(t, threads)
+    arm.full_step()
+    i = 0
     for _ in range(max(args.warmup, 1)):
-        step()
+        arm.churn_step(plan[i % len(plan)])
+        i += 1
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        arm.churn_step(plan[i % len(plan)])
+        i += 1
     dt = time.perf_counter() - t0
     value = len(t.groups) * args.steps / dt
+    # the same arm sweeping everything every step (no event source): reported beside it
+    full = CpuArm(t, threads)
+    full.full_step()
+    t1 = time.perf_counter()
+    n_full = max(3, min(args.steps, 10))
+    for _ in range(n_full):
+        full.full_step()
+    full_dt = (time.perf_counter() - t1) / n_full
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/u64 (integer compare)",
-        "data": "synthetic", "config": t.describe(),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8/int32/u64 (integer compare)",
+        "data": "synthetic", "config": {**t.describe(), "churn": {"pod_state_rows": CHURN, "placement_requests": CHURN_REQS}},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"full {t.profile.name} workload per step (sweep on {threads} of {host_threads()} "
-                                   f"host threads — the fastest count on this box — + placement spec round), "
-                                   f"{args.steps} steps"},
+                         "sample": f"full {t.profile.name} cluster per step as an event-driven controller: apply the step's "
+                                   f"{len(plan[0].pod_rows)} pod-status / {len(plan[0].req_rows)} scheduling events to the host "
+                                   f"tables, reconcile the {len(plan[0].dirty_groups)} dirty groups / {len(plan[0].dirty_lws)} "
+                                   f"dirty objects on {threads} of {host_threads()} host threads (the fastest count on this "
+                                   f"box), solve the placement spec round; {args.steps} steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "full_sweep": {"value": len(t.groups) / full_dt, "unit": UNIT, "ms_per_step": full_dt * 1e3, "cores": threads,
+                       "note": "the same port sweeping every object every step (no event source)"},
         "note": "CPU port of the reference's Go arithmetic (no Go toolchain here); excludes the "
                 "informer-cache List/DeepCopy and API round-trips that dominate the real reconciler",
     }
     print(json.dumps(line), flush=True)
 
 
+def run_reference_ds(args):
+    import oracle
+    from lws_b200 import synth
+
+    n_ds = max(1, int(round(50_000 * args.scale)))
+    d = synth.make_ds(n_ds, (2,))
+    oracle.sweep_ds(d.ds, d.roles, d.revroles)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.sweep_ds(d.ds, d.roles, d.revroles)
+    dt = time.perf_counter() - t0
+    value = n_ds * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "DisaggregatedSet reconciles/sec (2-role rollout partition calc)", "value": value,
+        "unit": "sets/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "int32 (float64 planner in the port)", "data": "synthetic",
+        "config": {"workload": "C4", "sets": n_ds, "roles": 2},
+        "cpu_baseline": {"value": value, "unit": "sets/s", "cores": 1, "kind": "port", "sample": f"{n_ds} sets per step"},
+        "e2e": {"value": value, "unit": "sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+# --------------------------------------------------------------------------- #
+# C4: DisaggregatedSet sweep
+# --------------------------------------------------------------------------- #
+def run_ours_ds(args):
+    import torch
+    import torch.distributed as dist
+
+    import oracle
+    from lws_b200 import records as R
+    from lws_b200 import synth
+    from lws_b200.engine import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_total = max(world, int(round(50_000 * args.scale)))
+    # a DS and its child LWS rows shard together by hash(DS.UID): rank r sweeps its share
+    n_ds = n_total // world if args.scaling == "strong" else n_total
+    d = synth.make_ds(n_ds, (2,), seed=synth.SEED + rank)
+    eng = Engine(local_rank)
+
+    def up(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+
+    copies = 8
+    sets = [dict(ds=up(d.ds), ro=up(d.roles), rr=up(d.revroles),
+                 o1=torch.empty(len(d.ds) * R.DS_OUT.itemsize, dtype=torch.uint8, device=dev),
+                 o2=torch.empty(len(d.roles) * R.DS_ROLE_OUT.itemsize, dtype=torch.uint8, device=dev),
+                 o3=torch.empty(len(d.revroles) * 4, dtype=torch.uint8, device=dev)) for _ in range(copies)]
+    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+
+    def step(i):
+        s = sets[i % copies]
+        eng.sweep_ds_device(s["ds"], len(d.ds), s["ro"], len(d.roles), s["rr"], len(d.revroles), s["o1"], s["o2"], s["o3"],
+                            stream=eng.stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    W = max(args.warmup, 3)
+    for i in range(W):
+        step(i)
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for i in range(args.steps):
+                step(i)
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / args.steps
+        launches = eng.launch_count - l0
+        for i in range(20000):
+            step(i)
+        torch.cuda.synchronize()
+    # e2e: host tables in, host results out
+    def e2e():
+        return eng.sweep_ds_host(d.ds, d.roles, d.revroles)
+
+    got = e2e()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = 20
+    for _ in range(n_e2e):
+        e2e()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    want = oracle.sweep_ds(d.ds, d.roles, d.revroles)
+    ok = all(a.tobytes() == b.tobytes() for a, b in zip(got, want))
+    if not ok:
+        raise SystemExit("bench.py: DS sweep differs from the oracle")
+    stats = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(n_ds)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms, e2e_ms = [float(x) for x in stats.tolist()]
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        algo = d.algorithmic_bytes()
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 1.0:
+            oracle.sweep_ds(d.ds, d.roles, d.revroles)
+            reps += 1
+        cpu = n_ds * reps / (time.perf_counter() - t0)
+        print(json.dumps({
+            "metric": "DisaggregatedSet reconciles/sec (2-role rollout partition calc)", "value": float(tot.item()) / (ms * 1e-3),
+            "unit": "sets/s", "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int32/int64", "data": "synthetic",
+            "config": {"workload": "C4", "sets_per_rank": n_ds, "roles": 2, "revision_role_rows": int(len(d.revroles)),
+                       "parallelism": f"shard-by-ds-uid x{world}", "l2": f"{copies} rotating copies (tables are {algo / 1e6:.1f} MB: L2-resident by size — launch-bound)"},
+            "e2e": {"value": float(tot.item()) / (e2e_ms * 1e-3), "unit": "sets/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(d.ds.nbytes + d.roles.nbytes + d.revroles.nbytes),
+                    "d2h_bytes_per_step": int(len(d.ds) * 16 + len(d.roles) * 8 + len(d.revroles) * 4),
+                    "api": "lwse_sweep_ds_host"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "ds_sweep_kernel", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "bytes_per_launch": int(algo), "peak_source": peak_src,
+                         "note": "7 MB per launch: the kernel is launch / latency bound, not HBM bound"},
+            "cpu_baseline": {"value": cpu, "unit": "sets/s", "cores": 1, "kind": "port", "sample": f"{n_ds} sets x{reps}"},
+            "oracle_check": {"outputs_equal_oracle": True},
+            "clocks": clk.summary()}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- #
+# the engine
+# --------------------------------------------------------------------------- #
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from lws_b200 import encoder
+    from lws_b200 import churn
     from lws_b200 import records as R
     from lws_b200.engine import Engine
 
@@ -233,24 +444,25 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU path to benchmark")
+    if args.workload == "C4":
+        return run_ours_ds(args)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    t = make_tables(args, rank)
+    t = make_tables(args, rank, world)
     eng = Engine(local_rank)
     eng.upload_nodes(t.nodes, t.n_domains)
     n_lws, n_grp, n_pod, n_nodes = len(t.lws), len(t.groups), len(t.pod_state), len(t.nodes)
+    n_ns = t.n_namespaces
     algo_bytes = t.algorithmic_bytes()
-    # placement: one request per group of an exclusive-topology object; the per-node
-    # occupancy of this shard's pods is a resident input column (the host maintains it
-    # incrementally from pod events; lwse can recount it)
-    reqs = encoder.encode_place_requests(t.lws, t.groups)
+    # placement: one request per group of an exclusive-topology object; the per-node occupancy of
+    # this shard's pods is a resident input column (the resident engine maintains it itself)
+    reqs = t.place_requests()
     n_req = len(reqs)
     place_on = n_req > 0
-    sched = (t.pod_state & R.POD_SCHEDULED) != 0
-    occ_host = np.bincount((t.pod_state[sched] >> R.POD_NODE_SHIFT).astype(np.int64), minlength=n_nodes).astype(np.uint32)
+    occ_host = R.occupancy_of(t.pod_ident, n_nodes)
 
     # ---- resident copies, rotated so that the working set exceeds L2 ----
     copies = max(2, int(np.ceil(2.5 * L2_BYTES / algo_bytes)) + 1)  # bytes a sweep touches x copies > 2.5 x L2
@@ -266,9 +478,9 @@ def run_ours(args):
             go=torch.empty(n_grp * R.GROUP_OUT.itemsize, dtype=torch.uint8, device=dev)))
     d_occ = torch.from_numpy(occ_host.view(np.int32)).to(dev)
     d_reqs = up(reqs) if place_on else None
-    # multi-GPU placement: ONE all-gather of [occupancy | request count | requests] per step
+    # multi-GPU placement: every rank needs every shard's [occupancy | requests] part
     req_cap = 0
-    if world > 1 and place_on is not None:
+    if world > 1:
         cap = torch.tensor([n_req], dtype=torch.int64, device=dev)
         dist.all_reduce(cap, op=dist.ReduceOp.MAX)
         req_cap = int(cap.item())
@@ -288,8 +500,6 @@ def run_ours(args):
     # time on the stream the kernels are launched on: the engine's own stream
     stream = torch.cuda.ExternalStream(eng.stream, device=dev)
     sptr = eng.stream
-    # the placement round reads only inputs (requests, occupancy, node table), never the sweep's
-    # outputs: it runs on its own stream, concurrently with the sweep kernels
     pstream = torch.cuda.Stream(device=dev)
     pptr = pstream.cuda_stream
 
@@ -302,16 +512,12 @@ def run_ours(args):
         if not place_on:
             return
         if world == 1:
-            eng.place_device(d_reqs, n_req, d_occ, 1, d_pout, stream=pptr)
+            eng.place_device(d_reqs, n_req, d_occ, n_ns, d_pout, stream=pptr)
             return
         with torch.cuda.stream(pstream):
             dist.all_gather_into_tensor(gathered, send)  # the single collective of a step
-        # every rank solves the whole (small) placement problem on the gathered parts: identical
-        # inputs, deterministic kernel → identical results; each rank keeps the rows of its own part
-        eng.place_gathered_device(gathered, world, part_stride, reqs_off, req_cap, 1, d_pout, stream=pptr)
+        eng.place_gathered_device(gathered, world, part_stride, reqs_off, req_cap, n_ns, d_pout, stream=pptr)
 
-    # single GPU: one C-ABI call per tick (lwse_reconcile_device forks/joins the placement round
-    # on the engine's side stream); descriptors are built once
     descs = {}
 
     def desc(i, flags):
@@ -325,22 +531,22 @@ def run_ours(args):
     peer = world > 1 and place_on and args.collective == "peer"
 
     def step(i, flags):
-        if place_on and world == 1:
-            eng.reconcile_device(desc(i, flags), d_reqs, n_req, d_occ, 1, d_pout, stream=sptr)
+        if world == 1:  # one C call per tick: sweep on the engine's stream, placement round on its side stream
+            eng.reconcile_device(desc(i, flags), d_reqs, n_req if place_on else 0, d_occ, n_ns, d_pout, stream=sptr)
             return
         if peer:  # one C call per tick: push part to the peers, wait for theirs, placement ∥ sweep
-            eng.reconcile_exchanged_device(desc(i, flags), send, 1, d_pout, stream=sptr)
+            eng.reconcile_exchanged_device(desc(i, flags), send, n_ns, d_pout, stream=sptr)
             return
         if place_on:
-            pstream.wait_stream(stream)  # fork: placement starts with the sweep …
+            pstream.wait_stream(stream)
             place()
         sweep(i, flags)
         if place_on:
-            stream.wait_stream(pstream)  # … join: the step ends when both are done
+            stream.wait_stream(pstream)
 
     def place_alone():
         if peer:
-            eng.reconcile_exchanged_device(None, send, 1, d_pout, stream=sptr)
+            eng.reconcile_exchanged_device(None, send, n_ns, d_pout, stream=sptr)
             return
         pstream.wait_stream(stream)
         place()
@@ -352,14 +558,10 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # NCCL form: the eager step is bound by Python/NCCL launch overhead, so it is replayed as a graph;
-    # the peer-exchange form is one C call per tick and runs eagerly (its step number is a kernel argument)
     use_graph = (args.graph or (world > 1 and not peer)) and not peer
 
     def timed(fn, steps, warmup):
-        """ms per call of fn(i) over `steps` calls.  Single GPU: the calls for each rotating input
-        set are captured once into a CUDA graph and replayed (launch overhead off the device
-        timeline); multi GPU: eager (the step contains a NCCL collective)."""
+        """ms per call of fn(i) over `steps` calls, CUDA events on the launching stream."""
         for i in range(warmup):
             fn(i)
         barrier()
@@ -376,7 +578,7 @@ def run_ours(args):
             except Exception as exc:  # pragma: no cover
                 print(f"bench.py[{rank}]: graph capture failed ({exc}); timing eager launches", file=sys.stderr)
                 ok = 0
-            if world > 1:  # all ranks replay graphs, or none does
+            if world > 1:
                 flag = torch.tensor([ok], device=dev)
                 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
                 ok = int(flag.item())
@@ -394,11 +596,11 @@ def run_ours(args):
             h0 = time.perf_counter()
             for i in range(steps):
                 run(i)
-            timed.host_ms = (time.perf_counter() - h0) * 1e3 / steps  # host enqueue time per call
+            timed.host_ms = (time.perf_counter() - h0) * 1e3 / steps
             e1.record(stream)
         barrier()
         launched = eng.launch_count - l0
-        if graphs:  # replays do not pass through the engine's counter: kernels per captured call x calls
+        if graphs:
             launched = timed.per_call.get(fn, 0) * steps
         return e0.elapsed_time(e1) / steps, launched
 
@@ -422,12 +624,11 @@ def run_ours(args):
         # each pass alone (same rotating inputs), for the per-kernel roofline
         ms_sweep, _ = timed(lambda i: sweep(i, t.flags), args.steps, 3)
         ms_fused, _ = timed(lambda i: sweep(i, t.flags | R.SWEEP_SKIP_LWS_PASS), args.steps, 3)
+        ms_lws, _ = timed(lambda i: sweep(i, t.flags | LWS_ONLY), args.steps, 3)
         ms_scan, _ = timed(lambda i: sweep(i, t.flags | SCAN_ONLY), args.steps, 3)
         ms_group, _ = timed(lambda i: sweep(i, t.flags | GROUP_ONLY), args.steps, 3)
-        ms_lws, _ = timed(lambda i: sweep(i, t.flags | LWS_ONLY), args.steps, 3)
         ms_place = timed(lambda i: place_alone(), args.steps, 3)[0] if place_on else 0.0
         # keep the GPU under the same load long enough for nvidia-smi to sample clocks
-        # (a fixed number of steps, the same on every rank: the peer exchange needs matching calls)
         n_load = torch.tensor([ms_step], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(n_load, op=dist.ReduceOp.MAX)
@@ -440,99 +641,135 @@ def run_ours(args):
             torch.cuda.synchronize()
     clocks = clk.summary()
     torch.cuda.synchronize()
-    rounds = eng.place_device(d_reqs, n_req, d_occ, 1, d_pout, stream=pptr, want_rounds=True) if (place_on and world == 1) else None
+    rounds = eng.place_device(d_reqs, n_req, d_occ, n_ns, d_pout, stream=pptr, want_rounds=True) if (place_on and world == 1) else None
     torch.cuda.synchronize()
 
-    # ---- end to end through the host entry points, pinned buffers ----
+    # ---- outputs of the device-resident tick against the oracle (outside the timed region) ----
+    check = {"done": False}
+    if not args.no_check:
+        import oracle
+
+        want_lo, want_go, _ = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, flags=t.flags,
+                                               threads=min(host_threads(), 32))
+        step(0, t.flags)
+        torch.cuda.synchronize()
+        ok = (sets[0]["lo"].cpu().numpy().tobytes() == want_lo.tobytes()
+              and sets[0]["go"].cpu().numpy().tobytes() == want_go.tobytes())
+        place_ok = None
+        if place_on:
+            if world == 1:
+                want_po = oracle.place(t.nodes, occ_host, t.n_domains, n_ns, reqs, threads=min(host_threads(), 32))
+                place_ok = d_pout.cpu().numpy()[: n_req * R.PLACE_OUT.itemsize].tobytes() == want_po.tobytes()
+            else:  # the gathered problem: every rank's part, unpacked the way the kernel sees it
+                from lws_b200 import distributed as D
+
+                dist.all_gather_into_tensor(gathered, send)
+                torch.cuda.synchronize()
+                occ_all, reqs_all = D.unpack_parts(gathered.cpu().numpy(), world, n_nodes, req_cap)
+                want_po = oracle.place(t.nodes, occ_all, t.n_domains, n_ns, reqs_all, threads=min(host_threads(), 32))
+                place_ok = d_pout.cpu().numpy()[: world * req_cap * R.PLACE_OUT.itemsize].tobytes() == want_po.tobytes()
+        check = {"done": True, "sweep_equals_oracle": bool(ok), "placement_equals_spec_oracle": place_ok}
+        if not ok or place_ok is False:
+            raise SystemExit(f"bench.py[{rank}]: device-resident tick differs from the oracle: {check}")
+
+    # ---- end to end (1): the resident tick, the product path ----
     def pinned(a):
         ten = torch.empty(max(a.nbytes, 16), dtype=torch.uint8).pin_memory()
         view = ten.numpy()[: a.nbytes].view(a.dtype)
         view[...] = a
         return ten, view
 
-    keep, h = [], {}
-    for name, arr in (("lws", t.lws), ("groups", t.groups), ("pst", t.pod_state), ("pid", t.pod_ident),
-                      ("lo", R.aligned_empty(n_lws, R.LWS_OUT)), ("go", R.aligned_empty(n_grp, R.GROUP_OUT)),
-                      ("reqs", reqs), ("occ", occ_host), ("po", R.aligned_empty(max(n_req, 1), R.PLACE_OUT))):
-        ten, view = pinned(arr)
-        keep.append(ten)
-        h[name] = view
-
-    def e2e_step(extra_flags=0, engine=None):
-        en = engine or eng
-        if n_req and world == 1:  # one call per tick: lwse_reconcile_host
-            return en.reconcile_host(h["lws"], h["groups"], h["pst"], h["pid"], h["reqs"], h["occ"], 1,
-                                     flags=t.flags | extra_flags, out=(h["lo"], h["go"]), place_out=h["po"])[2]
-        en.sweep_lws_host(h["lws"], h["groups"], h["pst"], h["pid"], flags=t.flags | extra_flags,
-                          out=(h["lo"], h["go"]))
-        return None
-
-    def wall(fn, reps, all_ranks=True):
-        for _ in range(3):
+    def wall(fn, reps, warm=3):
+        for _ in range(warm):
             fn()
-        if all_ranks:
-            barrier()
-        else:  # a rank-0-only measurement must not enter a collective
-            torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(reps):
             r = fn()
         return (time.perf_counter() - t0) / reps, r
 
-    # (1) the host entry points on pinned tables: every table is handed over every step; the engine
-    # uploads the state column and the group / LWS rows and reads the identity rows it needs (pods
-    # with an event) in place over PCIe
-    e2e_s, pout_host = wall(e2e_step, args.e2e_steps)
-    # (2) the same call when no pod was created or deleted since the last sweep: the identity
-    # column the engine holds from the previous call is reused
-    e2e_state_s, _ = wall(lambda: e2e_step(R.SWEEP_REUSE_POD_IDENT), args.e2e_steps)
-    # (3) every byte of every table uploaded (an engine created with LWSE_NO_ZERO_COPY=1)
-    e2e_full_s = None
-    if rank == 0:
-        os.environ["LWSE_NO_ZERO_COPY"] = "1"
-        eng_full = Engine(local_rank)
-        os.environ.pop("LWSE_NO_ZERO_COPY")
-        eng_full.upload_nodes(t.nodes, t.n_domains)
-        e2e_full_s, _ = wall(lambda: e2e_step(0, eng_full), args.e2e_steps, all_ranks=False)
-        eng_full.close()
-    # (4) resident tables (lwse_resident_*): the controller's informer cache feeds row patches —
-    # here 1 % of the pod state rows change per step — and reads back only the result rows that
-    # changed; the sweep still covers every row
-    resident = None
-    if rank == 0:
+    eng.resident_load(t.lws, t.groups, t.pod_state, t.pod_ident)
+    tick_flags = t.flags
+    if n_req:
+        eng.resident_place_load(reqs, n_ns)
+        tick_flags |= R.TICK_PLACE
+    first = eng.resident_tick(eng.make_tick((), tick_flags))  # every row is reported once
+    base_place = eng.resident_place_outputs() if n_req else None
+    e2e_variants = {}
+    mirror = None
+    for name, frac_p, frac_r in (("churn_1pct", CHURN, CHURN_REQS), ("churn_10pct", 0.10, CHURN_REQS),
+                                 ("churn_100pct", 1.0, CHURN_REQS), ("no_churn", 0.0, 0.0)):
+        if name != "churn_1pct" and world > 1:
+            continue
+        plan = churn_plan(t, reqs, base_place, frac_p, frac_r)
+        # every variant starts from the loaded tables
         eng.resident_load(t.lws, t.groups, t.pod_state, t.pod_ident)
-        eng.resident_sweep(t.flags)
-        rng = np.random.Generator(np.random.PCG64(7))
-        n_patch = max(1, n_pod // 100)
-        patch_sets = []
-        for k in range(4):
-            rows = np.sort(rng.choice(n_pod, size=n_patch, replace=False)).astype(np.uint32)
-            vals = t.pod_state[rows].copy()
-            vals ^= np.where(rng.random(n_patch) < 0.5, R.POD_ANY_RESTART, 0).astype(np.uint32)  # restart counts move
-            patch_sets.append((rows, vals))
-        state = {"i": 0, "changed": 0}
+        if n_req:
+            eng.resident_place_load(reqs, n_ns)
+        ap = churn.ArenaPlan(eng, plan, tick_flags)
+        eng.resident_tick(eng.make_tick((), tick_flags))
+        state = {"i": 0, "d2h": 0, "rows": (0, 0, 0)}
 
-        def resident_step():
-            rows, vals = patch_sets[state["i"] % len(patch_sets)]
+        def tick_step(ap=ap, state=state):
+            r = eng.resident_tick(ap.ticks[state["i"] % len(ap.ticks)])
             state["i"] += 1
-            eng.resident_patch(R.TABLE_POD_STATE, rows, vals)
-            out = eng.resident_sweep(t.flags)
-            state["changed"] = int(out[4]) + int(out[5])
-            return None
+            state["rows"] = (r["n_lws"], r["n_groups"], r["n_place"])
+            return r
 
-        res_s, _ = wall(resident_step, max(args.e2e_steps, 20), all_ranks=False)
-        resident = {"value": n_grp / res_s, "unit": UNIT, "ms_per_step": res_s * 1e3,
-                    "h2d_bytes_per_step": int(n_patch * 8), "changed_result_rows_last_step": state["changed"],
-                    "api": "lwse_resident_patch + lwse_resident_sweep",
-                    "note": "tables resident on the device; per step 1 % of the pod state rows patched, full sweep, "
-                            "only changed result rows read back; rank 0, no placement round"}
-    # the resident result must equal the host-path result
-    same = (sets[0]["lo"].cpu().numpy().tobytes() == h["lo"].tobytes()
-            and sets[0]["go"].cpu().numpy().tobytes() == h["go"].tobytes())
-    if pout_host is not None:
-        same = same and d_pout.cpu().numpy()[: n_req * R.PLACE_OUT.itemsize].tobytes() == pout_host.tobytes()
-    if not same:
-        raise SystemExit("bench.py: resident and host-path results differ")
+        reps = args.e2e_steps if frac_p < 0.5 else max(20, args.e2e_steps // 5)
+        reps = (reps + len(plan) - 1) // len(plan) * len(plan)  # whole cycles: every rank ends on the same set
+        sec, last = wall(tick_step, reps, warm=len(plan))
+        changed = state["rows"]
+        d2h = changed[0] * (4 + R.LWS_OUT.itemsize) + changed[1] * (4 + R.GROUP_OUT.itemsize) + changed[2] * (4 + R.PLACE_OUT.itemsize) + 28
+        e2e_variants[name] = {"ms_per_step": sec * 1e3, "h2d_bytes_per_step": int(np.mean(ap.h2d_bytes)),
+                              "d2h_bytes_per_step": int(d2h), "changed_rows_last_step": {"lws": changed[0], "groups": changed[1], "placement": changed[2]},
+                              "pod_rows_per_step": int(len(plan[0].pod_rows)), "request_rows_per_step": int(len(plan[0].req_rows)),
+                              "placement_rounds": int(last["rounds"])}
+        if name == "churn_1pct" and not args.no_check:
+            # replay the same ticks on host mirrors, run the oracle on them, compare every row
+            import oracle
+
+            m_pst, m_grp, m_req = t.pod_state.copy(), t.groups.copy(), (reqs.copy() if n_req else None)
+            for k in range(state["i"]):
+                churn.apply_to_mirror(plan[k % len(plan)], m_pst, m_grp, m_req)
+            w_lo, w_go, _ = oracle.sweep_lws(t.lws, m_grp, m_pst, t.pod_ident, t.nodes, flags=t.flags,
+                                             threads=min(host_threads(), 32))
+            g_lo, g_go = eng.resident_outputs()
+            ok = g_lo.tobytes() == w_lo.tobytes() and g_go.tobytes() == w_go.tobytes()
+            pl_ok = None
+            if n_req:
+                w_po = oracle.place(t.nodes, occ_host, t.n_domains, n_ns, m_req, threads=min(host_threads(), 32))
+                pl_ok = eng.resident_place_outputs().tobytes() == w_po.tobytes()
+            mirror = {"ticks_replayed": state["i"], "sweep_equals_oracle": bool(ok), "placement_equals_spec_oracle": pl_ok}
+            if not ok or pl_ok is False:
+                raise SystemExit(f"bench.py[{rank}]: resident tick differs from the oracle after {state['i']} ticks: {mirror}")
+    e2e_tick_s = e2e_variants["churn_1pct"]["ms_per_step"] * 1e-3
+
+    # ---- end to end (2): full handover through the stateless host entry point ----
+    full = None
+    if world == 1:
+        keep, h = [], {}
+        for name, arr in (("lws", t.lws), ("groups", t.groups), ("pst", t.pod_state), ("pid", t.pod_ident),
+                          ("lo", R.aligned_empty(n_lws, R.LWS_OUT)), ("go", R.aligned_empty(n_grp, R.GROUP_OUT)),
+                          ("reqs", reqs), ("occ", occ_host), ("po", R.aligned_empty(max(n_req, 1), R.PLACE_OUT))):
+            ten, view = pinned(arr)
+            keep.append(ten)
+            h[name] = view
+
+        def handover():
+            if n_req:
+                return eng.reconcile_host(h["lws"], h["groups"], h["pst"], h["pid"], h["reqs"], h["occ"], n_ns,
+                                          flags=t.flags, out=(h["lo"], h["go"]), place_out=h["po"])[2]
+            eng.sweep_lws_host(h["lws"], h["groups"], h["pst"], h["pid"], flags=t.flags, out=(h["lo"], h["go"]))
+
+        sec, _ = wall(handover, max(10, args.e2e_steps // 10))
+        ev = t.event_pods()
+        full = {"value": n_grp / sec, "unit": UNIT, "ms_per_step": sec * 1e3,
+                "h2d_bytes_per_step": int(t.lws.nbytes + t.groups.nbytes + t.pod_state.nbytes + ev * R.POD_IDENT.itemsize
+                                          + reqs.nbytes + occ_host.nbytes),
+                "d2h_bytes_per_step": int(n_lws * R.LWS_OUT.itemsize + n_grp * R.GROUP_OUT.itemsize + n_req * R.PLACE_OUT.itemsize),
+                "api": "lwse_reconcile_host: every table handed over every step (pinned host tables); state bytes, group and "
+                       f"LWS rows uploaded, identity rows of the {ev} event pods read in place over PCIe"}
 
     if peer:  # a timed-out wait (a rank fell behind by more than 2 s or is gone) invalidates the run
         xerr = torch.tensor([eng.exchange_status()], device=dev)
@@ -540,7 +777,7 @@ def run_ours(args):
         if int(xerr.item()) != 0:
             raise SystemExit(f"bench.py[{rank}]: a peer-exchange wait timed out")
     # ---- max over ranks ----
-    stats = torch.tensor([ms_step, ms_group, e2e_s * 1e3, ms_scan, ms_lws, ms_place, ms_sweep, ms_fused],
+    stats = torch.tensor([ms_step, ms_group, e2e_tick_s * 1e3, ms_scan, ms_lws, ms_place, ms_sweep, ms_fused],
                          dtype=torch.float64, device=dev)
     groups = torch.tensor([float(n_grp)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -553,23 +790,23 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         ev = t.event_pods()
         words = (n_pod + 31) // 32
-        group_rows = n_grp * (R.GROUP_REC.itemsize + R.GROUP_OUT.itemsize) + n_lws * 16
+        group_rows = n_grp * (R.GROUP_REC.itemsize + R.GROUP_OUT.itemsize + 1) + n_lws * 16
         fused_on = n_pod <= 256 * max(n_grp, 1)  # the engine's rule (lwse_lws_kernels.cu launch_lws_sweep)
         passes = {
             # algorithmic bytes per launch: rows read once + rows written once.  A sweep is the fused
-            # scan + group kernel followed by the LWS pass (small groups, no occupancy count); the
-            # two-kernel form (occupancy wanted, large groups) is timed beside it.
-            "group_fused_kernel": (n_pod * 4 + group_rows + ev * R.POD_IDENT.itemsize, ms_fused),
-            "lws_sweep_kernel": (n_lws * (R.LWS_REC.itemsize + R.LWS_OUT.itemsize) + n_grp * 4, ms_lws),
-            "pod_scan_kernel": (n_pod * 4 + 2 * words * 4, ms_scan),
-            "group_sweep_kernel": (group_rows + 2 * words * 4 + ev * (4 + R.POD_IDENT.itemsize), ms_group),
+            # scan + group kernel followed by the LWS pass (small groups); the three-kernel form
+            # (large groups) is timed beside it.
+            "group_fused_kernel": (n_pod * 1 + group_rows + ev * (1 + R.POD_IDENT.itemsize), ms_fused),
+            "lws_sweep_kernel": (n_lws * (R.LWS_REC.itemsize + R.LWS_OUT.itemsize) + n_grp * 1, ms_lws),
+            "pod_scan_kernel": (n_pod * 1 + 2 * words * 4, ms_scan),
+            "group_sweep_kernel": (group_rows + 2 * words * 4 + ev * (1 + R.POD_IDENT.itemsize), ms_group),
         }
         in_step = ("group_fused_kernel", "lws_sweep_kernel") if fused_on else (
             "pod_scan_kernel", "group_sweep_kernel", "lws_sweep_kernel")
         traffic = None
-        try:  # per-launch DRAM bytes of the committed ncu capture (profiles/r1_final_summary.md)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            if t.profile.name == "C3" and args.scale == 1.0:
+        try:  # per-launch DRAM bytes of the committed ncu capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            if t.profile.name == tj.get("workload", "C3") and args.scale == 1.0:
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
@@ -577,49 +814,50 @@ def run_ours(args):
         dom_bytes, dom_ms = passes[dom]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         cpu_rate, cpu_s, cpu_reps = cpu_oracle_rate(t, 1)
-        h2d = int(t.table_bytes() + (reqs.nbytes + occ_host.nbytes if world == 1 else 0))
-        d2h = int(n_lws * R.LWS_OUT.itemsize + n_grp * R.GROUP_OUT.itemsize
-                  + (n_req * R.PLACE_OUT.itemsize if world == 1 else 0))
+        tick = e2e_variants["churn_1pct"]
+        pair_evals = None
+        if place_on and world == 1 and rounds:
+            unp = int((reqs["leader_node"] == R.NONE).sum())
+            pair_evals = {"unpinned_requests": unp, "domains": int(t.n_domains), "nodes": n_nodes, "rounds": int(rounds),
+                          "request_x_domain_evals_per_s": unp * t.n_domains / (ms_place * 1e-3) if ms_place else None,
+                          "note": "level 1 scores (request x domain) once per request (a displaced request scans again); "
+                                  "see the scan form for (request x node) pair-evals/s"}
         line = {
             "metric": METRIC, "value": total_groups / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32/u64 (integer compare)", "data": "synthetic",
-            "config": {**t.describe(), "parallelism": f"shard-by-uid x{world}",
-                       "placement": {"requests_per_rank": int(n_req), "rounds": rounds,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "u8/int32/u64 (integer compare)", "data": "synthetic",
+            "config": {**t.describe(), "parallelism": f"shard-by-uid x{world} ({args.scaling})",
+                       "placement": {"requests_per_rank": int(n_req), "unpinned": int((reqs['leader_node'] == R.NONE).sum()) if n_req else 0,
+                                     "namespaces": int(n_ns), "rounds": rounds, "pair_evals": pair_evals,
                                      "collective": ("none: parts pushed to the peers with NVLink peer stores + flags (lwse_exchange_*)"
                                                     if peer else "1 NCCL all_gather/step") if (world > 1 and place_on) else "none"},
-                       "launch": ("CUDA graph replay (one graph per step: sweep kernels with programmatic edges, "
-                                  "all-gather, placement)") if use_graph else "eager launches, programmatic dependent launch",
+                       "launch": ("CUDA graph replay") if use_graph else "eager launches, programmatic dependent launch",
                        "step": ("one lwse_reconcile_device call per tick: fused pod scan + group pass, LWS pass, placement round concurrently on the engine's side stream" if world == 1 else
-                                "one lwse_reconcile_exchanged_device call per tick and rank: sweep of the shard; on the side stream the part push to the peers, the wait for theirs and the placement round over all parts" if peer else
+                                "one lwse_reconcile_exchanged_device call per tick and rank" if peer else
                                 "sweep of the shard, placement round (one all-gather) concurrently on a second stream"),
                        "l2": f"inputs rotate over {copies} resident copies ({copies * algo_bytes / 1e6:.0f} MB > L2)"},
-            "e2e": {"value": total_groups / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(h2d - t.pod_ident.nbytes + ev * R.POD_IDENT.itemsize),
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                    "api": "lwse_reconcile_host (= lwse_sweep_lws_host + lwse_place_host in one call; pinned host tables)",
-                    "note": "every table handed over every step; state column, group and LWS rows uploaded, "
-                            f"identity rows of the {ev} event pods read in place over PCIe (12 B each counted)",
-                    "full_upload": {"value": n_grp * world / e2e_full_s if e2e_full_s else None,
-                                    "ms_per_step": e2e_full_s * 1e3 if e2e_full_s else None,
-                                    "h2d_bytes_per_step": h2d,
-                                    "note": "LWSE_NO_ZERO_COPY=1: identity column uploaded as well (PCIe-bound), rank 0"},
-                    "state_only": {"value": n_grp * world / e2e_state_s, "ms_per_step": e2e_state_s * 1e3,
-                                   "h2d_bytes_per_step": int(h2d - t.pod_ident.nbytes),
-                                   "note": "LWSE_SWEEP_REUSE_POD_IDENT: pod identity column resident "
-                                           "(no pod created/deleted since the previous sweep), rank 0"},
-                    "resident": resident},
+            "e2e": {"value": total_groups / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": tick["h2d_bytes_per_step"], "d2h_bytes_per_step": tick["d2h_bytes_per_step"],
+                    "api": "lwse_resident_tick: per step the watch-event churn (row patches written into the engine's pinned "
+                           "arena, read by the scatter kernel over PCIe) in, full sweep + placement round, changed result rows "
+                           "(written by the kernels into pinned change lists) out; host wall clock around the call",
+                    "churn": {"pod_state_rows": CHURN, "placement_requests": CHURN_REQS},
+                    "timing": "host wall clock (time.perf_counter) around the calls, max over ranks",
+                    "variants": e2e_variants, "full_handover": full, "oracle_check": mirror},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": (traffic or {}).get(dom),
                          "bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms, "peak_source": peak_src,
+                         "timing": "back-to-back launches of the kernel alone (programmatic dependent launch lets "
+                                   "consecutive launches overlap their prologues), CUDA events",
                          "passes": {k: {"bytes": int(v[0]), "ms": v[1], "gbs": v[0] / (v[1] * 1e-3) / 1e9,
                                         "frac": v[0] / (v[1] * 1e-3) / 1e9 / peak, "in_step": k in in_step}
                                     for k, v in passes.items()}},
             "ms_sweep_only": ms_sweep, "ms_placement_only": ms_place, "host_enqueue_ms_per_step": host_ms_step,
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": f"full {t.profile.name} step x{cpu_reps} ({cpu_s * 1e3:.1f} ms per step: sweep + placement spec round)"},
+                             "sample": f"full {t.profile.name} step x{cpu_reps} ({cpu_s * 1e3:.1f} ms per step: full sweep + placement spec round)"},
+            "oracle_check": check,
             "clocks": clocks,
             "algorithmic_bytes_per_step": int(algo_bytes),
             "sweep_gbs": algo_bytes / (ms_sweep * 1e-3) / 1e9,

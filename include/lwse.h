@@ -57,7 +57,7 @@
 extern "C" {
 #endif
 
-#define LWSE_ABI_VERSION 1u
+#define LWSE_ABI_VERSION 2u
 
 #if defined(__GNUC__)
 #define LWSE_API __attribute__((visibility("default")))
@@ -161,15 +161,19 @@ typedef struct lwse_group_rec {
 #define LWSE_GRP_MISTAKEN_ANNOTATION (1u << 10)  /* leader carries leader-name annotation     */
 #define LWSE_GRP_REVISION_EXISTS (1u << 11)      /* ControllerRevision for leader's key found */
 
-/* Pods are stored column-split: the per-sweep-hot state word (4 B, changes
- * with every status update) and the cold identity (12 B, fixed at pod
- * creation, read only for pods that have a restart / deletion event). */
-typedef uint32_t lwse_pod_state; /* LWSE_POD_* | node << LWSE_POD_NODE_SHIFT */
+/* Pods are stored column-split: the per-sweep-hot state BYTE (changes with every status
+ * update; the only pod column a sweep streams) and the cold identity row (16 B, 16-byte
+ * aligned; fixed at pod creation apart from the node binding; read only for pods that have a
+ * restart / deletion event, and by the optional occupancy count). */
+typedef uint8_t lwse_pod_state; /* LWSE_POD_* */
 
-typedef struct lwse_pod_ident { /* 12 B */
-  uint32_t rev_hash_lo; /* template-revision-hash label (hash64, two halves) */
-  uint32_t rev_hash_hi;
-  uint32_t owner_uid_hash; /* controller ownerRef.uid */
+typedef struct lwse_pod_ident { /* 16 B */
+  uint64_t rev_hash;       /* template-revision-hash label (hash64)                  */
+  uint32_t owner_uid_hash; /* controller ownerRef.uid — a 32-bit hash: two different UIDs
+                              compare equal with probability 2^-32 per comparison (only
+                              pods that already have a restart event are ever compared;
+                              DESIGN.md "hash widths")                                */
+  uint32_t place;          /* LWSE_PODID_* | node << LWSE_PODID_NODE_SHIFT            */
 } lwse_pod_ident;
 
 #define LWSE_POD_PHASE_MASK 3u       /* 0 other, 1 Pending, 2 Running              */
@@ -181,9 +185,10 @@ typedef struct lwse_pod_ident { /* 12 B */
 #define LWSE_POD_OWNER_MASK (3u << 4)
 #define LWSE_POD_OWNER_NAME_MATCH (1u << 6) /* ownerRef.name == "<lws>-<group>"    */
 #define LWSE_POD_IS_LEADER (1u << 7) /* worker-index label == "0"                  */
-#define LWSE_POD_NAME_OK (1u << 8)   /* GetParentNameAndOrdinal ordinal != -1      */
-#define LWSE_POD_SCHEDULED (1u << 9) /* node field below is valid                  */
-#define LWSE_POD_NODE_SHIFT 10       /* 22-bit node-table row                      */
+
+#define LWSE_PODID_NAME_OK (1u << 0)   /* GetParentNameAndOrdinal ordinal != -1    */
+#define LWSE_PODID_SCHEDULED (1u << 1) /* node field below is valid                */
+#define LWSE_PODID_NODE_SHIFT 10       /* 22-bit node-table row                    */
 #define LWSE_POD_NODE_MAX ((1u << 22) - 1u)
 
 /* One node (16 B). */
@@ -281,7 +286,8 @@ typedef struct lwse_lws_tables {
   lwse_group_out* group_out; /* n_groups rows */
   uint32_t* node_occupancy;  /* optional: n_nodes counters, scheduled pods per node
                                 over the whole pod table (the call overwrites
-                                them); NULL to skip                               */
+                                them; it reads the identity column for it); NULL
+                                to skip                                           */
   uint32_t flags;            /* LWSE_SWEEP_* */
 } lwse_lws_tables;
 
@@ -355,7 +361,8 @@ typedef enum lwse_table {
   LWSE_TABLE_LWS = 0,       /* lwse_lws_rec    */
   LWSE_TABLE_GROUPS = 1,    /* lwse_group_rec  */
   LWSE_TABLE_POD_STATE = 2, /* lwse_pod_state  */
-  LWSE_TABLE_POD_IDENT = 3  /* lwse_pod_ident  */
+  LWSE_TABLE_POD_IDENT = 3, /* lwse_pod_ident  */
+  LWSE_TABLE_PLACE_REQS = 4 /* lwse_place_req (lwse_resident_place_load)  */
 } lwse_table;
 
 /* Result rows that differ from the previous resident sweep (all rows after a load).
@@ -375,13 +382,80 @@ typedef struct lwse_changes {
 /* Copy the four input tables of `host` to the device; they stay resident (and the
  * previous results are forgotten).  Output pointers in `host` are ignored. */
 LWSE_API int lwse_resident_load(lwse_engine* e, const lwse_lws_tables* host);
-/* Overwrite n rows of a resident table: row rows[i] ← the i-th packed row of `values`. */
+/* Overwrite n rows of a resident table: row rows[i] ← the i-th packed row of `values` (rows
+ * distinct).  Synchronous convenience form of one patch segment of lwse_resident_tick. */
 LWSE_API int lwse_resident_patch(lwse_engine* e, lwse_table which, const uint32_t* rows, const void* values,
                                  uint32_t n);
 /* Sweep the resident tables (flags: LWSE_SWEEP_GANG).  `changes` may be NULL. */
 LWSE_API int lwse_resident_sweep(lwse_engine* e, uint32_t flags, lwse_changes* changes);
 /* Every result row of the last resident sweep. */
 LWSE_API int lwse_resident_outputs(lwse_engine* e, lwse_lws_out* lws_out, lwse_group_out* group_out);
+
+/* ---- the resident tick: what one pass of the controllers' work queues maps to ---------------
+ * Watch events in (as row patches), actions out (the result rows that changed), ONE call:
+ *   patches -> scatter kernel -> fused pod scan + group pass -> LWS pass     (engine stream)
+ *           \-> placement round over the resident request table            (side stream)
+ * The patch rows / values are read by the GPU where the host wrote them when they lie in the
+ * engine's arena (pinned, mapped memory: lwse_resident_arena) — no staging copy; the kernels
+ * write the changed result rows straight into pinned, mapped result buffers and the last CTA of
+ * each branch raises a sequence word the call spins on: no stream synchronize, no device->host
+ * copy on the critical path.  Replaces, per reconcile pass, the informer-cache reads of
+ * leaderworkerset_controller.go:421,584,598 and pod_controller.go:348 (List) for every object. */
+
+typedef struct lwse_place_req lwse_place_req; /* defined below (Placement) */
+typedef struct lwse_place_out lwse_place_out;
+
+/* One patch segment. */
+typedef struct lwse_patch_seg {
+  uint32_t table;       /* lwse_table                                                      */
+  uint32_t flags;       /* LWSE_PATCH_*                                                    */
+  uint32_t n;           /* rows patched                                                    */
+  uint32_t first_row;   /* LWSE_PATCH_RANGE: rows first_row .. first_row + n - 1           */
+  const uint32_t* rows; /* n distinct row numbers (ignored for a range)                    */
+  const void* values;   /* n packed rows of the table's record type                        */
+} lwse_patch_seg;
+
+#define LWSE_PATCH_RANGE (1u << 0) /* contiguous rows: one DMA copy instead of a scatter (use it
+                                      when a large share of a column changed)              */
+#define LWSE_TICK_MAX_SEGS 8u
+
+typedef struct lwse_tick {
+  /* in */
+  const lwse_patch_seg* segs;
+  uint32_t n_segs;
+  uint32_t flags; /* LWSE_SWEEP_GANG | LWSE_TICK_* */
+  /* out: views of engine-owned pinned memory, valid until the next lwse_resident_* call on this
+   * engine.  n_* counts every changed row; rows beyond the capacity (= table size, so this
+   * cannot happen for the sweep) are not listed.  Order is unspecified. */
+  const uint32_t* lws_rows;
+  const lwse_lws_out* lws_out;
+  uint32_t n_lws;
+  uint32_t n_groups;
+  const uint32_t* group_rows;
+  const lwse_group_out* group_out;
+  const uint32_t* place_rows; /* request rows whose placement changed (LWSE_TICK_PLACE) */
+  const lwse_place_out* place_out;
+  uint32_t n_place;
+  uint32_t place_rounds;
+} lwse_tick;
+
+#define LWSE_TICK_PLACE (1u << 8)     /* run the placement round over the resident request table */
+#define LWSE_TICK_NO_SWEEP (1u << 9)  /* patches (+ placement) only */
+
+/* The engine's patch arena: at least min_bytes of pinned, mapped host memory (grown on demand;
+ * growing invalidates the previous base).  Patch segments whose rows / values pointers lie inside
+ * it are consumed in place; others are first copied into it by the call. */
+LWSE_API int lwse_resident_arena(lwse_engine* e, uint64_t min_bytes, void** base_out, uint64_t* bytes_out);
+/* Make the placement request table resident (rows are then patched with LWSE_TABLE_PLACE_REQS);
+ * the per-node occupancy the rounds use is counted by the engine from the resident identity
+ * column and follows its patches.  Needs lwse_upload_nodes and lwse_resident_load first. */
+LWSE_API int lwse_resident_place_load(lwse_engine* e, const lwse_place_req* reqs, uint32_t n_reqs,
+                                      uint32_t n_namespaces);
+LWSE_API int lwse_resident_tick(lwse_engine* e, lwse_tick* t);
+/* Every placement row of the last tick with LWSE_TICK_PLACE / the occupancy counters the engine
+ * maintains (n_nodes words). */
+LWSE_API int lwse_resident_place_outputs(lwse_engine* e, lwse_place_out* out);
+LWSE_API int lwse_resident_occupancy(lwse_engine* e, uint32_t* occupancy_out);
 
 /* ------------------------------------------------------------------------- */
 /* Placement (build-defined spec — the reference has no node scoring)        */

@@ -330,7 +330,7 @@ inline Tables EncodeLws(const std::vector<LwsItem>& items, const Cluster& c, con
           auto any_pos = [](const std::vector<int32_t>& v) { return std::any_of(v.begin(), v.end(), [](int32_t x) { return x > 0; }); };
           if (any_pos(p->initContainerRestartCounts) || any_pos(p->containerRestartCounts)) bits |= LWSE_POD_ANY_RESTART;
           if (p->deletionTimestamp) bits |= LWSE_POD_DELETING;
-          uint32_t owner_uid = 0;
+          uint32_t owner_uid = 0, place = 0;  // place: the identity row's cold word (name check, node binding)
           if (const OwnerReference* o = controllerOf(p->ownerReferences)) {
             const uint32_t kind = o->kind == "Pod" ? 1u : o->kind == "StatefulSet" ? 2u : 3u;
             bits |= kind << LWSE_POD_OWNER_SHIFT;
@@ -341,22 +341,23 @@ inline Tables EncodeLws(const std::vector<LwsItem>& items, const Cluster& c, con
               irregular = true;
           }
           if (get(p->labels, WorkerIndexLabelKey) == "0") {
-            bits |= LWSE_POD_IS_LEADER | LWSE_POD_NAME_OK;
+            bits |= LWSE_POD_IS_LEADER;
+            place |= LWSE_PODID_NAME_OK;
           } else {
             auto po = GetParentNameAndOrdinal(p->name);
             if (po.second != -1) {
-              bits |= LWSE_POD_NAME_OK;
+              place |= LWSE_PODID_NAME_OK;
               if (po.first != nominated) irregular = true;
             }
           }
           if (!p->nodeName.empty()) {
             auto ni = node_index.find(p->nodeName);
             if (ni != node_index.end() && ni->second <= LWSE_POD_NODE_MAX)
-              bits |= LWSE_POD_SCHEDULED | (ni->second << LWSE_POD_NODE_SHIFT);
+              place |= LWSE_PODID_SCHEDULED | (ni->second << LWSE_PODID_NODE_SHIFT);
           }
           const uint64_t rev = hash64(get(p->labels, RevisionKey));
-          t.pod_state.push_back(bits);
-          t.pod_ident.push_back({(uint32_t)rev, (uint32_t)(rev >> 32), owner_uid});
+          t.pod_state.push_back((lwse_pod_state)bits);
+          t.pod_ident.push_back({rev, owner_uid, place});
           names.push_back(p->name);
         }
       }

@@ -3,6 +3,8 @@
 // library: every sweep is a CUDA kernel launch or the call fails.
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -21,13 +23,26 @@ struct SweepChangeLists {
   lwse_group_out* group_out = nullptr;
   uint32_t group_capacity = 0;
   uint32_t* counts = nullptr;
+  uint32_t* host_words = nullptr;
+  uint32_t seq = 0;
 };
 int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
                      void* scratch, int sm_count, cudaStream_t s, int* cuda_err, const SweepChangeLists* cl,
-                     uint32_t* d_event_count = nullptr);
-size_t lws_sweep_scratch_bytes(uint64_t n_pods);
-int launch_scatter(int row_words, void* table, uint64_t table_rows, const uint32_t* rows, const void* values,
-                   uint32_t n, cudaStream_t s, int* cuda_err);
+                     uint32_t* d_event_count = nullptr, bool first_pdl = true);
+size_t lws_sweep_scratch_bytes(uint64_t n_pods, uint32_t n_groups);
+struct ScatterSegHost {
+  void* table;
+  uint64_t table_rows;
+  const uint32_t* rows;
+  const void* values;
+  uint32_t n;
+  uint32_t row_bytes;
+  bool is_ident;
+};
+int launch_scatter(const ScatterSegHost* segs, int n_segs, uint32_t* d_occupancy, uint32_t n_nodes, cudaStream_t s,
+                   bool pdl, int* cuda_err);
+int launch_occupancy(const lwse_pod_ident* d_ident, uint64_t n_pods, uint32_t* d_occupancy, uint32_t n_nodes, int sm_count,
+                     cudaStream_t s, int* cuda_err);
 // lwse_place_kernels.cu
 int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, const uint32_t* d_node_order,
                  const uint32_t* d_node_pos, uint32_t n_nodes, uint32_t n_domains,
@@ -38,6 +53,9 @@ int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, cons
                  uint32_t* h_unpinned, const uint32_t** d_counters_out, const uint32_t** d_unpinned_out,
                  bool after_push);
 size_t place_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces);
+int launch_place_publish(const lwse_place_out* d_cur, lwse_place_out* d_prev, uint32_t n, uint32_t* h_rows,
+                         lwse_place_out* h_outs, uint32_t capacity, uint32_t* d_count, uint32_t* d_ticket,
+                         const uint32_t* d_rounds, uint32_t* h_words, uint32_t seq, cudaStream_t s, int* cuda_err);
 // lwse_ds_kernels.cu
 int launch_ds_sweep(const lwse_ds_tables* t, int sm_count, cudaStream_t s, int* cuda_err);
 // lwse_sha1_kernels.cu
@@ -73,6 +91,44 @@ struct DevBuf {
   }
 };
 
+// Pinned, mapped host memory that only grows: the host writes / reads it in place and the GPU
+// reaches it through `d` (patch arena, change lists, tick words).
+struct PinBuf {
+  void* h = nullptr;
+  void* d = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (h) cudaFreeHost(h);
+    h = d = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaHostAlloc(&h, want, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&d, h, 0);
+    if (e == cudaSuccess) {
+      cap = want;
+      memset(h, 0, want);  // sequence words and counters start at zero
+    } else if (h) {
+      cudaFreeHost(h);
+      h = d = nullptr;
+    }
+    return e;
+  }
+  void release() {
+    if (h) cudaFreeHost(h);
+    h = d = nullptr;
+    cap = 0;
+  }
+  bool holds(const void* ptr, size_t bytes) const {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(ptr), b = reinterpret_cast<uintptr_t>(h);
+    return h && a >= b && a + bytes <= b + cap;
+  }
+  template <typename T>
+  T* dev_of(const T* host_ptr) const {
+    return reinterpret_cast<T*>(static_cast<uint8_t*>(d) + (reinterpret_cast<const uint8_t*>(host_ptr) - static_cast<uint8_t*>(h)));
+  }
+};
+
 }  // namespace
 
 struct lwse_engine {
@@ -94,17 +150,29 @@ struct lwse_engine {
   DevBuf lws, groups, pod_state, pod_ident, lws_out, group_out, occupancy, scan_scratch;
   DevBuf place_reqs, place_out, place_occ, place_scratch;
   uint64_t ident_rows = ~0ull;       // rows of the identity column resident from the last host sweep
+  uint64_t ident_hint_pods = ~0ull;  // n_pods the hint below was measured on
+  uint32_t ident_hint_events = 0;    // event pods the previous host sweep of that table visited
   // resident tables (lwse_resident_*)
   DevBuf r_lws, r_groups, r_pst, r_pid, r_lws_out, r_group_out, r_scan;
-  DevBuf r_chg_lws_rows, r_chg_lws_out, r_chg_grp_rows, r_chg_grp_out, r_counts, r_patch_rows, r_patch_vals;
-  uint32_t rn_lws = 0, rn_groups = 0;
+  DevBuf r_counts;                   // [0] lws changes, [1] group changes, [2] sweep ticket, [4] place changes, [5] place ticket
+  DevBuf r_occ;                      // scheduled pods per node of the resident identity column
+  DevBuf r_preq, r_pout, r_pout_prev;  // resident placement requests / results of this and the previous tick
+  PinBuf arena;                      // patch arena handed to the caller
+  PinBuf stage;                      // staging for patch segments that lie outside the arena
+  PinBuf chg;                        // change lists: [lws rows | lws out | group rows | group out | place rows | place out]
+  PinBuf tickw;                      // [0] lws changes [1] group changes [2] sweep seq | [4] place changes [5] rounds [6] place seq
+  size_t chg_off[6] = {};
+  uint32_t rn_lws = 0, rn_groups = 0, rn_reqs = 0, rn_namespaces = 0;
   uint64_t rn_pods = 0;
-  bool r_loaded = false;
+  bool r_loaded = false, r_place_loaded = false;
+  uint32_t tick_seq = 0;
   uint32_t* h_counts = nullptr;      // pinned, 2 words
-  DevBuf h_counts_dev;               // event-pod count of the host entry point's scan
+  DevBuf h_counts_dev;               // event-pod count of the host entry point's sweep
   bool no_zero_copy = false;         // LWSE_NO_ZERO_COPY=1: always upload the identity column
   uint32_t place_calls = 0;          // selects the scratch half
-  uint64_t place_geometry = 0;       // (n_reqs, n_namespaces, nodes, domains) the scratch was laid out for
+  uint32_t place_geometry[4] = {0, 0, 0, 0};  // (n_reqs, n_namespaces, nodes, domains) the scratch was laid out for
+  cudaEvent_t ev_place = nullptr;    // end of the last placement call: the next one (any stream) orders behind it
+  bool place_pending = false;
   const uint32_t* place_counters = nullptr;  // device: counters / phase stamps of the last placement call
   const uint32_t* place_unpinned = nullptr;  // device: its unpinned-request count
   DevBuf ds, ds_roles, ds_revroles, ds_out, ds_role_out, ds_revrole_out;
@@ -154,7 +222,7 @@ int check_lws_tables(const lwse_lws_tables* t) {
   if (t->n_pods && (!t->pod_state || !t->pod_ident)) return LWSE_ERR_INVALID_ARG;
   if (t->n_pods > 0xFFFFFFFFull) return LWSE_ERR_UNSUPPORTED;  // pod_base / pod_count are 32-bit
   if (!aligned16(t->lws) || !aligned16(t->groups) || !aligned16(t->lws_out) || !aligned16(t->group_out) ||
-      !aligned16(t->pod_state) || (reinterpret_cast<uintptr_t>(t->pod_ident) & 3u))
+      !aligned16(t->pod_state) || !aligned16(t->pod_ident))
     return LWSE_ERR_INVALID_ARG;
   return LWSE_OK;
 }
@@ -236,12 +304,14 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->hist_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_hist, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_place, cudaEventDisableTiming) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&e->h_rounds), 64) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&e->h_counts), 64) != cudaSuccess) {
     (void)cudaGetLastError();
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->ev_hist) cudaEventDestroy(e->ev_hist);
+    if (e->ev_place) cudaEventDestroy(e->ev_place);
     if (e->hist_stream) cudaStreamDestroy(e->hist_stream);
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -278,9 +348,11 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
                       &e->place_scratch, &e->ds,       &e->ds_roles,   &e->ds_revroles, &e->ds_out,
                       &e->ds_role_out, &e->ds_revrole_out, &e->sha_bytes, &e->sha_offsets, &e->sha_digests,
                       &e->r_lws, &e->r_groups, &e->r_pst, &e->r_pid, &e->r_lws_out, &e->r_group_out, &e->r_scan,
-                      &e->r_chg_lws_rows, &e->r_chg_lws_out, &e->r_chg_grp_rows, &e->r_chg_grp_out, &e->r_counts,
-                      &e->r_patch_rows, &e->r_patch_vals, &e->h_counts_dev};
+                      &e->r_counts, &e->r_occ, &e->r_preq, &e->r_pout, &e->r_pout_prev, &e->h_counts_dev};
     for (DevBuf* b : bufs) b->release();
+    PinBuf* pins[] = {&e->arena, &e->stage, &e->chg, &e->tickw};
+    for (PinBuf* b : pins) b->release();
+    if (e->ev_place) cudaEventDestroy(e->ev_place);
     if (e->h_rounds) cudaFreeHost(e->h_rounds);
     if (e->h_counts) cudaFreeHost(e->h_counts);
     cudaEventDestroy(e->ev_hist);
@@ -338,6 +410,7 @@ LWSE_API int lwse_upload_nodes(lwse_engine* e, const lwse_node_rec* nodes, uint3
   LWSE_CUDA(e, cudaStreamSynchronize(e->stream));  // the host vectors above go out of scope
   e->n_nodes = n_nodes;
   e->n_domains = n_domains;
+  e->place_geometry[0] = e->place_geometry[1] = e->place_geometry[2] = e->place_geometry[3] = 0;  // re-initialise the scratch
   return LWSE_OK;
 }
 
@@ -347,7 +420,7 @@ LWSE_API int lwse_upload_nodes(lwse_engine* e, const lwse_node_rec* nodes, uint3
 static int sweep_device_locked(lwse_engine* e, const lwse_lws_tables* t, cudaStream_t s) {
   // the scan bitmaps live in engine-owned scratch; it only grows (a growth is a
   // cudaMalloc, so size it with one warm-up call before capturing a graph)
-  LWSE_CUDA(e, e->scan_scratch.reserve(lwse::lws_sweep_scratch_bytes(t->n_pods)));
+  LWSE_CUDA(e, e->scan_scratch.reserve(lwse::lws_sweep_scratch_bytes(t->n_pods, t->n_groups)));
   int cuda_err = 0;
   int launched = lwse::launch_lws_sweep(t, (const lwse_node_rec*)e->nodes.p, e->n_nodes,
                                         e->scan_scratch.p, e->sm_count, s, &cuda_err, nullptr);
@@ -366,7 +439,7 @@ LWSE_API int lwse_sweep_lws_device(lwse_engine* e, const lwse_lws_tables* t, voi
 }
 
 // lwse_sweep_lws_host with the engine locked and its device current; returns after the results
-// are in the caller's tables (stream synchronized).
+// are in the caller's tables (stream synchronized — the only synchronize of the call).
 static int sweep_host_locked(lwse_engine* e, const lwse_lws_tables* h) {
   cudaStream_t s = e->stream;
   const size_t b_lws = (size_t)h->n_lws * sizeof(lwse_lws_rec);
@@ -377,19 +450,21 @@ static int sweep_host_locked(lwse_engine* e, const lwse_lws_tables* h) {
   const size_t b_go = (size_t)h->n_groups * sizeof(lwse_group_out);
   LWSE_CUDA(e, e->lws.reserve(b_lws + 16));
   LWSE_CUDA(e, e->groups.reserve(b_grp + 16));
-  LWSE_CUDA(e, e->pod_state.reserve(b_pst + 16));
+  LWSE_CUDA(e, e->pod_state.reserve(b_pst + 32));
   const void* ident_before = e->pod_ident.p;
   LWSE_CUDA(e, e->pod_ident.reserve(b_pid + 16));
   const bool ident_moved = ident_before != e->pod_ident.p;
-  LWSE_CUDA(e, e->scan_scratch.reserve(lwse::lws_sweep_scratch_bytes(h->n_pods)));
+  LWSE_CUDA(e, e->scan_scratch.reserve(lwse::lws_sweep_scratch_bytes(h->n_pods, h->n_groups)));
   LWSE_CUDA(e, e->lws_out.reserve(b_lo + 16));
   LWSE_CUDA(e, e->group_out.reserve(b_go + 16));
   const bool want_occ = h->node_occupancy != nullptr && e->n_nodes > 0;
   if (want_occ) {
     LWSE_CUDA(e, e->occupancy.reserve((size_t)e->n_nodes * 4 + 16));
   }
-  if (b_lws) LWSE_CUDA(e, cudaMemcpyAsync(e->lws.p, h->lws, b_lws, cudaMemcpyHostToDevice, s));
+  // the hot byte column first: it is what the sweep's first kernel streams
+  if (b_pst) LWSE_CUDA(e, cudaMemcpyAsync(e->pod_state.p, h->pod_state, b_pst, cudaMemcpyHostToDevice, s));
   if (b_grp) LWSE_CUDA(e, cudaMemcpyAsync(e->groups.p, h->groups, b_grp, cudaMemcpyHostToDevice, s));
+  if (b_lws) LWSE_CUDA(e, cudaMemcpyAsync(e->lws.p, h->lws, b_lws, cudaMemcpyHostToDevice, s));
   lwse_lws_tables d = *h;
   d.lws = (const lwse_lws_rec*)e->lws.p;
   d.groups = (const lwse_group_rec*)e->groups.p;
@@ -399,68 +474,53 @@ static int sweep_host_locked(lwse_engine* e, const lwse_lws_tables* h) {
   d.group_out = (lwse_group_out*)e->group_out.p;
   d.node_occupancy = want_occ ? (uint32_t*)e->occupancy.p : nullptr;
   int cuda_err = 0;
-  bool swept = false;
+  bool counted = false;
   if (b_pst) {
-    LWSE_CUDA(e, cudaMemcpyAsync(e->pod_state.p, h->pod_state, b_pst, cudaMemcpyHostToDevice, s));
-    // The identity column (12 B / pod, three quarters of the input bytes) is only read for pods
+    // The identity column (16 B / pod, 16 of the 17 input bytes per pod) is only read for pods
     // with a restart / deletion event.  It is left out of the upload
     //  - when the caller says it did not change (LWSE_SWEEP_REUSE_POD_IDENT), or
     //  - when the caller's buffer is pinned, mapped host memory and few pods have an event: the
-    //    group pass then reads those rows in place over PCIe.  The scan runs first, counts the
-    //    event pods, and the count decides (a 64-byte PCIe read per visited pod against 12 B / pod
-    //    in bulk).
+    //    group pass then reads those rows in place over PCIe (a 64-byte read per visited pod
+    //    against 16 B / pod in bulk).  "Few" is what the PREVIOUS sweep of a table of this size
+    //    visited (no mid-step synchronize; the first sweep of a table is optimistic).
     const bool reuse = (h->flags & LWSE_SWEEP_REUSE_POD_IDENT) && e->ident_rows == h->n_pods && !ident_moved;
     const void* mapped = nullptr;
-    if (!reuse && !e->no_zero_copy) {
+    if (!reuse && !e->no_zero_copy && !want_occ) {
       cudaPointerAttributes attr;
       if (cudaPointerGetAttributes(&attr, h->pod_ident) == cudaSuccess && attr.type == cudaMemoryTypeHost)
         mapped = attr.devicePointer;
       else
         (void)cudaGetLastError();
     }
-    if (mapped && h->n_groups && !(h->flags & (LWSE_SWEEP_SKIP_POD_SCAN | LWSE_SWEEP_SKIP_GROUP_PASS))) {
-      LWSE_CUDA(e, cudaMemsetAsync(e->h_counts_dev.p, 0, 4, s));
-      lwse_lws_tables scan = d;
-      scan.flags |= LWSE_SWEEP_SKIP_GROUP_PASS | LWSE_SWEEP_SKIP_LWS_PASS;
-      int launched = lwse::launch_lws_sweep(&scan, (const lwse_node_rec*)e->nodes.p, e->n_nodes, e->scan_scratch.p,
-                                            e->sm_count, s, &cuda_err, nullptr, (uint32_t*)e->h_counts_dev.p);
-      if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
-      e->launches += (uint64_t)launched;
-      LWSE_CUDA(e, cudaMemcpyAsync(e->h_counts, e->h_counts_dev.p, 4, cudaMemcpyDeviceToHost, s));
-      LWSE_CUDA(e, cudaStreamSynchronize(s));
-      const uint64_t events = e->h_counts[0];
-      if (events * 64u <= b_pid / 2u) {
-        d.pod_ident = (const lwse_pod_ident*)mapped;
-        e->ident_rows = ~0ull;  // the device copy is stale now
-      } else {
-        LWSE_CUDA(e, cudaMemcpyAsync(e->pod_ident.p, h->pod_ident, b_pid, cudaMemcpyHostToDevice, s));
-        e->ident_rows = h->n_pods;
-      }
-      lwse_lws_tables rest = d;
-      rest.flags |= LWSE_SWEEP_SKIP_POD_SCAN;
-      launched = lwse::launch_lws_sweep(&rest, (const lwse_node_rec*)e->nodes.p, e->n_nodes, e->scan_scratch.p,
-                                        e->sm_count, s, &cuda_err, nullptr);
-      if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
-      e->launches += (uint64_t)launched;
-      swept = true;
+    const bool few = e->ident_hint_pods != h->n_pods || (uint64_t)e->ident_hint_events * 64u <= b_pid / 2u;
+    if (mapped && few && h->n_groups && !(h->flags & (LWSE_SWEEP_SKIP_POD_SCAN | LWSE_SWEEP_SKIP_GROUP_PASS))) {
+      d.pod_ident = (const lwse_pod_ident*)mapped;
+      e->ident_rows = ~0ull;  // the device copy is stale now
     } else {
       if (!reuse) LWSE_CUDA(e, cudaMemcpyAsync(e->pod_ident.p, h->pod_ident, b_pid, cudaMemcpyHostToDevice, s));
       e->ident_rows = h->n_pods;
     }
+    counted = h->n_groups && !(h->flags & (LWSE_SWEEP_SKIP_POD_SCAN | LWSE_SWEEP_SKIP_GROUP_PASS));
+    if (counted) LWSE_CUDA(e, cudaMemsetAsync(e->h_counts_dev.p, 0, 4, s));
   }
-  if (!swept) {
-    int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes,
-                                          e->scan_scratch.p, e->sm_count, s, &cuda_err, nullptr);
-    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
-    e->launches += (uint64_t)launched;
-  }
+  int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes, e->scan_scratch.p, e->sm_count,
+                                        s, &cuda_err, nullptr, counted ? (uint32_t*)e->h_counts_dev.p : nullptr,
+                                        /*first_pdl=*/false);
+  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+  e->launches += (uint64_t)launched;
 
-  if (b_lo) LWSE_CUDA(e, cudaMemcpyAsync(h->lws_out, e->lws_out.p, b_lo, cudaMemcpyDeviceToHost, s));
+  // group results first: they are complete while the LWS pass still runs
   if (b_go) LWSE_CUDA(e, cudaMemcpyAsync(h->group_out, e->group_out.p, b_go, cudaMemcpyDeviceToHost, s));
+  if (b_lo) LWSE_CUDA(e, cudaMemcpyAsync(h->lws_out, e->lws_out.p, b_lo, cudaMemcpyDeviceToHost, s));
   if (want_occ)
     LWSE_CUDA(e, cudaMemcpyAsync(h->node_occupancy, e->occupancy.p, (size_t)e->n_nodes * 4,
                                  cudaMemcpyDeviceToHost, s));
+  if (counted) LWSE_CUDA(e, cudaMemcpyAsync(e->h_counts, e->h_counts_dev.p, 4, cudaMemcpyDeviceToHost, s));
   LWSE_CUDA(e, cudaStreamSynchronize(s));
+  if (counted) {
+    e->ident_hint_pods = h->n_pods;
+    e->ident_hint_events = e->h_counts[0];
+  }
   return LWSE_OK;
 }
 
@@ -476,6 +536,23 @@ LWSE_API int lwse_sweep_lws_host(lwse_engine* e, const lwse_lws_tables* h) {
 // ---------------------------------------------------------------------------
 // Resident tables
 // ---------------------------------------------------------------------------
+static size_t align256(size_t v) { return (v + 255u) & ~(size_t)255u; }
+
+// (re)allocate the pinned change lists for the resident tables' sizes
+static int reserve_change_lists(lwse_engine* e) {
+  size_t off = 0;
+  const size_t sizes[6] = {(size_t)e->rn_lws * 4,       (size_t)e->rn_lws * sizeof(lwse_lws_out),
+                           (size_t)e->rn_groups * 4,    (size_t)e->rn_groups * sizeof(lwse_group_out),
+                           (size_t)e->rn_reqs * 4,      (size_t)e->rn_reqs * sizeof(lwse_place_out)};
+  for (int k = 0; k < 6; k++) {
+    e->chg_off[k] = off;
+    off += align256(sizes[k] + 16);
+  }
+  LWSE_CUDA(e, e->chg.reserve(off));
+  LWSE_CUDA(e, e->tickw.reserve(256));
+  return LWSE_OK;
+}
+
 LWSE_API int lwse_resident_load(lwse_engine* e, const lwse_lws_tables* h) {
   if (!e || !h) return LWSE_ERR_INVALID_ARG;
   if ((h->n_lws && !h->lws) || (h->n_groups && !h->groups) || (h->n_pods && (!h->pod_state || !h->pod_ident)))
@@ -489,12 +566,14 @@ LWSE_API int lwse_resident_load(lwse_engine* e, const lwse_lws_tables* h) {
   const size_t b_lo = (size_t)h->n_lws * sizeof(lwse_lws_out), b_go = (size_t)h->n_groups * sizeof(lwse_group_out);
   LWSE_CUDA(e, e->r_lws.reserve(b_lws + 16));
   LWSE_CUDA(e, e->r_groups.reserve(b_grp + 16));
-  LWSE_CUDA(e, e->r_pst.reserve(b_pst + 16));
+  LWSE_CUDA(e, e->r_pst.reserve(b_pst + 32));
   LWSE_CUDA(e, e->r_pid.reserve(b_pid + 16));
   LWSE_CUDA(e, e->r_lws_out.reserve(b_lo + 16));
   LWSE_CUDA(e, e->r_group_out.reserve(b_go + 16));
-  LWSE_CUDA(e, e->r_scan.reserve(lwse::lws_sweep_scratch_bytes(h->n_pods)));
+  LWSE_CUDA(e, e->r_scan.reserve(lwse::lws_sweep_scratch_bytes(h->n_pods, h->n_groups)));
   LWSE_CUDA(e, e->r_counts.reserve(64));
+  LWSE_CUDA(e, e->r_occ.reserve((size_t)e->n_nodes * 4 + 16));
+  LWSE_CUDA(e, cudaMemsetAsync(e->r_counts.p, 0, 64, s));
   if (b_lws) LWSE_CUDA(e, cudaMemcpyAsync(e->r_lws.p, h->lws, b_lws, cudaMemcpyHostToDevice, s));
   if (b_grp) LWSE_CUDA(e, cudaMemcpyAsync(e->r_groups.p, h->groups, b_grp, cudaMemcpyHostToDevice, s));
   if (b_pst) LWSE_CUDA(e, cudaMemcpyAsync(e->r_pst.p, h->pod_state, b_pst, cudaMemcpyHostToDevice, s));
@@ -502,11 +581,126 @@ LWSE_API int lwse_resident_load(lwse_engine* e, const lwse_lws_tables* h) {
   // forget previous results: an all-ones row never equals a real result, so the first sweep reports every row
   if (b_lo) LWSE_CUDA(e, cudaMemsetAsync(e->r_lws_out.p, 0xFF, b_lo, s));
   if (b_go) LWSE_CUDA(e, cudaMemsetAsync(e->r_group_out.p, 0xFF, b_go, s));
+  if (e->n_nodes) {  // scheduled pods per node; identity-row patches keep it current from here on
+    int cuda_err = 0;
+    int launched = lwse::launch_occupancy((const lwse_pod_ident*)e->r_pid.p, h->n_pods, (uint32_t*)e->r_occ.p, e->n_nodes,
+                                          e->sm_count, s, &cuda_err);
+    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+    e->launches += (uint64_t)launched;
+  }
   LWSE_CUDA(e, cudaStreamSynchronize(s));
   e->rn_lws = h->n_lws;
   e->rn_groups = h->n_groups;
   e->rn_pods = h->n_pods;
   e->r_loaded = true;
+  e->r_place_loaded = false;
+  e->rn_reqs = 0;
+  return reserve_change_lists(e);
+}
+
+LWSE_API int lwse_resident_arena(lwse_engine* e, uint64_t min_bytes, void** base_out, uint64_t* bytes_out) {
+  if (!e || !base_out) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  LWSE_CUDA(e, cudaStreamSynchronize(e->stream));  // nothing may still be reading a buffer that is replaced
+  LWSE_CUDA(e, e->arena.reserve(min_bytes ? (size_t)min_bytes : ((size_t)8 << 20)));
+  *base_out = e->arena.h;
+  if (bytes_out) *bytes_out = e->arena.cap;
+  return LWSE_OK;
+}
+
+// table → (device base, rows, bytes per row)
+static bool resident_table(lwse_engine* e, uint32_t which, void** base, uint64_t* rows, uint32_t* row_bytes) {
+  switch (which) {
+    case LWSE_TABLE_LWS: *base = e->r_lws.p; *rows = e->rn_lws; *row_bytes = sizeof(lwse_lws_rec); return true;
+    case LWSE_TABLE_GROUPS: *base = e->r_groups.p; *rows = e->rn_groups; *row_bytes = sizeof(lwse_group_rec); return true;
+    case LWSE_TABLE_POD_STATE: *base = e->r_pst.p; *rows = e->rn_pods; *row_bytes = sizeof(lwse_pod_state); return true;
+    case LWSE_TABLE_POD_IDENT: *base = e->r_pid.p; *rows = e->rn_pods; *row_bytes = sizeof(lwse_pod_ident); return true;
+    case LWSE_TABLE_PLACE_REQS:
+      if (!e->r_place_loaded) return false;
+      *base = e->r_preq.p; *rows = e->rn_reqs; *row_bytes = sizeof(lwse_place_req); return true;
+    default: return false;
+  }
+}
+
+// Enqueue the patch segments of a tick on the engine's stream.  *wrote = some table changed
+// (the sweep's first kernel then has to wait for the scatter kernel to finish).
+static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_segs, bool* wrote) {
+  *wrote = false;
+  if (n_segs == 0) return LWSE_OK;
+  if (!segs || n_segs > LWSE_TICK_MAX_SEGS) return LWSE_ERR_INVALID_ARG;
+  cudaStream_t s = e->stream;
+  // room for every segment that is not in the arena
+  size_t need = 0;
+  for (uint32_t i = 0; i < n_segs; i++) {
+    void* base;
+    uint64_t rows;
+    uint32_t rb;
+    if (!resident_table(e, segs[i].table, &base, &rows, &rb)) return LWSE_ERR_INVALID_ARG;
+    if (segs[i].n == 0) continue;
+    if (!segs[i].values || (!(segs[i].flags & LWSE_PATCH_RANGE) && !segs[i].rows)) return LWSE_ERR_INVALID_ARG;
+    if (segs[i].flags & LWSE_PATCH_RANGE) {
+      if ((uint64_t)segs[i].first_row + segs[i].n > rows) return LWSE_ERR_BAD_TABLE;
+      continue;
+    }
+    if (!e->arena.holds(segs[i].rows, (size_t)segs[i].n * 4)) need += align256((size_t)segs[i].n * 4);
+    if (!e->arena.holds(segs[i].values, (size_t)segs[i].n * rb) || (rb > 1 && !aligned16(segs[i].values)))
+      need += align256((size_t)segs[i].n * rb);
+  }
+  if (need > e->stage.cap) {
+    LWSE_CUDA(e, cudaStreamSynchronize(s));
+    LWSE_CUDA(e, e->stage.reserve(need));
+  }
+  lwse::ScatterSegHost sc[LWSE_TICK_MAX_SEGS];
+  int n_sc = 0;
+  size_t cursor = 0;
+  bool recount = false;
+  for (uint32_t i = 0; i < n_segs; i++) {
+    const lwse_patch_seg& g = segs[i];
+    if (g.n == 0) continue;
+    void* base;
+    uint64_t rows;
+    uint32_t rb;
+    resident_table(e, g.table, &base, &rows, &rb);
+    *wrote = true;
+    if (g.flags & LWSE_PATCH_RANGE) {  // one DMA copy straight into the table
+      LWSE_CUDA(e, cudaMemcpyAsync(static_cast<uint8_t*>(base) + (size_t)g.first_row * rb, g.values, (size_t)g.n * rb,
+                                   cudaMemcpyHostToDevice, s));
+      if (g.table == LWSE_TABLE_POD_IDENT) recount = true;
+      continue;
+    }
+    const uint32_t* d_rows;
+    const void* d_vals;
+    if (e->arena.holds(g.rows, (size_t)g.n * 4)) {
+      d_rows = e->arena.dev_of(g.rows);
+    } else {
+      uint8_t* dst = static_cast<uint8_t*>(e->stage.h) + cursor;
+      memcpy(dst, g.rows, (size_t)g.n * 4);
+      d_rows = reinterpret_cast<const uint32_t*>(static_cast<uint8_t*>(e->stage.d) + cursor);
+      cursor += align256((size_t)g.n * 4);
+    }
+    if (e->arena.holds(g.values, (size_t)g.n * rb) && (rb == 1 || aligned16(g.values))) {
+      d_vals = e->arena.dev_of(static_cast<const uint8_t*>(g.values));
+    } else {
+      uint8_t* dst = static_cast<uint8_t*>(e->stage.h) + cursor;
+      memcpy(dst, g.values, (size_t)g.n * rb);
+      d_vals = static_cast<uint8_t*>(e->stage.d) + cursor;
+      cursor += align256((size_t)g.n * rb);
+    }
+    sc[n_sc++] = lwse::ScatterSegHost{base, rows, d_rows, d_vals, g.n, rb, g.table == LWSE_TABLE_POD_IDENT};
+  }
+  int cuda_err = 0;
+  if (n_sc) {
+    int launched = lwse::launch_scatter(sc, n_sc, e->n_nodes ? (uint32_t*)e->r_occ.p : nullptr, e->n_nodes, s, true, &cuda_err);
+    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+    e->launches += (uint64_t)launched;
+  }
+  if (recount && e->n_nodes) {
+    int launched = lwse::launch_occupancy((const lwse_pod_ident*)e->r_pid.p, e->rn_pods, (uint32_t*)e->r_occ.p, e->n_nodes,
+                                          e->sm_count, s, &cuda_err);
+    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+    e->launches += (uint64_t)launched;
+  }
   return LWSE_OK;
 }
 
@@ -517,91 +711,16 @@ LWSE_API int lwse_resident_patch(lwse_engine* e, lwse_table which, const uint32_
   if (!e->r_loaded) return LWSE_ERR_NOT_READY;
   if (n == 0) return LWSE_OK;
   DeviceGuard guard(e->device);
-  cudaStream_t s = e->stream;
-  void* table = nullptr;
-  uint64_t table_rows = 0;
-  int words = 0;
-  switch (which) {
-    case LWSE_TABLE_LWS: table = e->r_lws.p; table_rows = e->rn_lws; words = 16; break;
-    case LWSE_TABLE_GROUPS: table = e->r_groups.p; table_rows = e->rn_groups; words = 16; break;
-    case LWSE_TABLE_POD_STATE: table = e->r_pst.p; table_rows = e->rn_pods; words = 1; break;
-    case LWSE_TABLE_POD_IDENT: table = e->r_pid.p; table_rows = e->rn_pods; words = 3; break;
-    default: return LWSE_ERR_INVALID_ARG;
-  }
-  const size_t b_rows = (size_t)n * 4, b_vals = (size_t)n * words * 4;
-  LWSE_CUDA(e, e->r_patch_rows.reserve(b_rows + 16));
-  LWSE_CUDA(e, e->r_patch_vals.reserve(b_vals + 16));
-  LWSE_CUDA(e, cudaMemcpyAsync(e->r_patch_rows.p, rows, b_rows, cudaMemcpyHostToDevice, s));
-  LWSE_CUDA(e, cudaMemcpyAsync(e->r_patch_vals.p, values, b_vals, cudaMemcpyHostToDevice, s));
-  int cuda_err = 0;
-  int launched = lwse::launch_scatter(words, table, table_rows, (const uint32_t*)e->r_patch_rows.p,
-                                      e->r_patch_vals.p, n, s, &cuda_err);
-  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
-  e->launches += (uint64_t)launched;
-  // the staging buffers are reused by the next patch: order it behind this one (same stream) — but the
-  // host buffers belong to the caller again only after the copies ran
-  LWSE_CUDA(e, cudaStreamSynchronize(s));
-  return LWSE_OK;
-}
-
-LWSE_API int lwse_resident_sweep(lwse_engine* e, uint32_t flags, lwse_changes* ch) {
-  if (!e) return LWSE_ERR_INVALID_ARG;
-  std::lock_guard<std::mutex> lock(e->mu);
-  if (!e->r_loaded) return LWSE_ERR_NOT_READY;
-  DeviceGuard guard(e->device);
-  cudaStream_t s = e->stream;
-  lwse_lws_tables d{};
-  d.lws = (const lwse_lws_rec*)e->r_lws.p;
-  d.n_lws = e->rn_lws;
-  d.groups = (const lwse_group_rec*)e->r_groups.p;
-  d.n_groups = e->rn_groups;
-  d.pod_state = (const lwse_pod_state*)e->r_pst.p;
-  d.pod_ident = (const lwse_pod_ident*)e->r_pid.p;
-  d.n_pods = e->rn_pods;
-  d.lws_out = (lwse_lws_out*)e->r_lws_out.p;
-  d.group_out = (lwse_group_out*)e->r_group_out.p;
-  d.flags = flags & LWSE_SWEEP_GANG;
-  lwse::SweepChangeLists cl;
-  if (ch) {
-    if ((ch->lws_capacity && (!ch->lws_rows || !ch->lws_out)) || (ch->group_capacity && (!ch->group_rows || !ch->group_out)))
-      return LWSE_ERR_INVALID_ARG;
-    LWSE_CUDA(e, e->r_chg_lws_rows.reserve((size_t)ch->lws_capacity * 4 + 16));
-    LWSE_CUDA(e, e->r_chg_lws_out.reserve((size_t)ch->lws_capacity * sizeof(lwse_lws_out) + 16));
-    LWSE_CUDA(e, e->r_chg_grp_rows.reserve((size_t)ch->group_capacity * 4 + 16));
-    LWSE_CUDA(e, e->r_chg_grp_out.reserve((size_t)ch->group_capacity * sizeof(lwse_group_out) + 16));
-    LWSE_CUDA(e, cudaMemsetAsync(e->r_counts.p, 0, 8, s));
-    cl.lws_rows = (uint32_t*)e->r_chg_lws_rows.p;
-    cl.lws_out = (lwse_lws_out*)e->r_chg_lws_out.p;
-    cl.lws_capacity = ch->lws_capacity;
-    cl.group_rows = (uint32_t*)e->r_chg_grp_rows.p;
-    cl.group_out = (lwse_group_out*)e->r_chg_grp_out.p;
-    cl.group_capacity = ch->group_capacity;
-    cl.counts = (uint32_t*)e->r_counts.p;
-  }
-  int cuda_err = 0;
-  int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes, e->r_scan.p, e->sm_count,
-                                        s, &cuda_err, ch ? &cl : nullptr);
-  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
-  e->launches += (uint64_t)launched;
-  if (!ch) {
-    LWSE_CUDA(e, cudaStreamSynchronize(s));
-    return LWSE_OK;
-  }
-  LWSE_CUDA(e, cudaMemcpyAsync(e->h_counts, e->r_counts.p, 8, cudaMemcpyDeviceToHost, s));
-  LWSE_CUDA(e, cudaStreamSynchronize(s));
-  ch->n_lws = e->h_counts[0];
-  ch->n_groups = e->h_counts[1];
-  const uint32_t nl = ch->n_lws < ch->lws_capacity ? ch->n_lws : ch->lws_capacity;
-  const uint32_t ng = ch->n_groups < ch->group_capacity ? ch->n_groups : ch->group_capacity;
-  if (nl) {
-    LWSE_CUDA(e, cudaMemcpyAsync(ch->lws_rows, e->r_chg_lws_rows.p, (size_t)nl * 4, cudaMemcpyDeviceToHost, s));
-    LWSE_CUDA(e, cudaMemcpyAsync(ch->lws_out, e->r_chg_lws_out.p, (size_t)nl * sizeof(lwse_lws_out), cudaMemcpyDeviceToHost, s));
-  }
-  if (ng) {
-    LWSE_CUDA(e, cudaMemcpyAsync(ch->group_rows, e->r_chg_grp_rows.p, (size_t)ng * 4, cudaMemcpyDeviceToHost, s));
-    LWSE_CUDA(e, cudaMemcpyAsync(ch->group_out, e->r_chg_grp_out.p, (size_t)ng * sizeof(lwse_group_out), cudaMemcpyDeviceToHost, s));
-  }
-  if (nl || ng) LWSE_CUDA(e, cudaStreamSynchronize(s));
+  lwse_patch_seg seg{};
+  seg.table = (uint32_t)which;
+  seg.n = n;
+  seg.rows = rows;
+  seg.values = values;
+  bool wrote = false;
+  const int rc = apply_patches_locked(e, &seg, 1, &wrote);
+  if (rc != LWSE_OK) return rc;
+  // the caller's buffers (and the staging copy) are free again once the scatter ran
+  LWSE_CUDA(e, cudaStreamSynchronize(e->stream));
   return LWSE_OK;
 }
 
@@ -633,11 +752,15 @@ static int place_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n
   const void* before = e->place_scratch.p;
   LWSE_CUDA(e, e->place_scratch.reserve(scratch));
   // the two scratch halves are laid out for one geometry; any change re-initialises them
-  const uint64_t geometry = ((uint64_t)n_reqs << 40) ^ ((uint64_t)n_namespaces << 56) ^ ((uint64_t)e->n_nodes << 16) ^
-                            (uint64_t)e->n_domains ^ 0x8000000000000000ull;
-  const bool fresh = before != e->place_scratch.p || geometry != e->place_geometry;
+  const uint32_t geometry[4] = {n_reqs, n_namespaces, e->n_nodes, e->n_domains};
+  const bool fresh = before != e->place_scratch.p || memcmp(geometry, e->place_geometry, sizeof(geometry)) != 0;
   if (fresh) e->h_rounds[2] = 0xFFFFFFFFu;  // no history for this geometry
-  e->place_geometry = geometry;
+  memcpy(e->place_geometry, geometry, sizeof(geometry));
+  // placement calls of one engine share the scratch (a call resets the half the next one uses):
+  // whatever streams they run on, each orders behind the previous one
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  const bool eager = cudaStreamIsCapturing(s, &capturing) == cudaSuccess && capturing == cudaStreamCaptureStatusNone;
+  if (eager && e->place_pending) LWSE_CUDA(e, cudaStreamWaitEvent(s, e->ev_place, 0));
   int cuda_err = 0;
   int launched = lwse::launch_place((const lwse_node_rec*)e->nodes.p, (const uint32_t*)e->dom_first.p,
                                     (const uint32_t*)e->node_order.p, (const uint32_t*)e->node_pos.p, e->n_nodes,
@@ -649,13 +772,14 @@ static int place_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
   if (rounds_out) *rounds_out = e->h_rounds[0];
+  if (eager) {
+    LWSE_CUDA(e, cudaEventRecord(e->ev_place, s));
+    e->place_pending = true;
+  }
   // history for the next call's cluster-or-grid decision (only consulted beyond 1024 requests):
   // the round's unpinned-request count, copied on a third stream so that nothing waits for it
-  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
-  if (n_reqs > 1024u && e->place_unpinned && cudaStreamIsCapturing(s, &capturing) == cudaSuccess &&
-      capturing == cudaStreamCaptureStatusNone) {
-    LWSE_CUDA(e, cudaEventRecord(e->ev_hist, s));
-    LWSE_CUDA(e, cudaStreamWaitEvent(e->hist_stream, e->ev_hist, 0));
+  if (n_reqs > 1024u && e->place_unpinned && eager) {
+    LWSE_CUDA(e, cudaStreamWaitEvent(e->hist_stream, e->ev_place, 0));
     LWSE_CUDA(e, cudaMemcpyAsync(e->h_rounds + 2, e->place_unpinned, 4, cudaMemcpyDeviceToHost, e->hist_stream));
   }
   return LWSE_OK;
@@ -838,34 +962,27 @@ LWSE_API int lwse_place_host(lwse_engine* e, const lwse_place_req* reqs, uint32_
                              const uint32_t* occupancy, uint32_t n_namespaces, lwse_place_out* out,
                              uint32_t* rounds_out) {
   if (!e || (n_reqs && (!reqs || !out)) || n_namespaces == 0) return LWSE_ERR_INVALID_ARG;
-  uint32_t n_nodes;
-  {
-    std::lock_guard<std::mutex> lock(e->mu);
-    if (e->n_nodes == 0 || e->n_domains == 0) return LWSE_ERR_NOT_READY;
-    n_nodes = e->n_nodes;
-    DeviceGuard guard(e->device);
-    LWSE_CUDA(e, e->place_reqs.reserve((size_t)n_reqs * sizeof(lwse_place_req) + 16));
-    LWSE_CUDA(e, e->place_out.reserve((size_t)n_reqs * sizeof(lwse_place_out) + 16));
-    LWSE_CUDA(e, e->place_occ.reserve((size_t)n_nodes * 4 + 16));
-    if (n_reqs)
-      LWSE_CUDA(e, cudaMemcpyAsync(e->place_reqs.p, reqs, (size_t)n_reqs * sizeof(lwse_place_req),
-                                   cudaMemcpyHostToDevice, e->stream));
-    if (occupancy)
-      LWSE_CUDA(e, cudaMemcpyAsync(e->place_occ.p, occupancy, (size_t)n_nodes * 4,
-                                   cudaMemcpyHostToDevice, e->stream));
-    else
-      LWSE_CUDA(e, cudaMemsetAsync(e->place_occ.p, 0, (size_t)n_nodes * 4, e->stream));
-  }
-  int rc = lwse_place_device(e, (const lwse_place_req*)e->place_reqs.p, n_reqs,
-                             (const uint32_t*)e->place_occ.p, n_namespaces,
-                             (lwse_place_out*)e->place_out.p, rounds_out, nullptr);
-  if (rc != LWSE_OK) return rc;
+  // one lock for staging, launch and download: concurrent callers (Go reconcile workers) share
+  // the staging buffers
   std::lock_guard<std::mutex> lock(e->mu);
+  if (e->n_nodes == 0 || e->n_domains == 0) return LWSE_ERR_NOT_READY;
   DeviceGuard guard(e->device);
+  cudaStream_t s = e->stream;
+  LWSE_CUDA(e, e->place_reqs.reserve((size_t)n_reqs * sizeof(lwse_place_req) + 16));
+  LWSE_CUDA(e, e->place_out.reserve((size_t)n_reqs * sizeof(lwse_place_out) + 16));
+  LWSE_CUDA(e, e->place_occ.reserve((size_t)e->n_nodes * 4 + 16));
   if (n_reqs)
-    LWSE_CUDA(e, cudaMemcpyAsync(out, e->place_out.p, (size_t)n_reqs * sizeof(lwse_place_out),
-                                 cudaMemcpyDeviceToHost, e->stream));
-  LWSE_CUDA(e, cudaStreamSynchronize(e->stream));
+    LWSE_CUDA(e, cudaMemcpyAsync(e->place_reqs.p, reqs, (size_t)n_reqs * sizeof(lwse_place_req), cudaMemcpyHostToDevice, s));
+  if (occupancy)
+    LWSE_CUDA(e, cudaMemcpyAsync(e->place_occ.p, occupancy, (size_t)e->n_nodes * 4, cudaMemcpyHostToDevice, s));
+  else
+    LWSE_CUDA(e, cudaMemsetAsync(e->place_occ.p, 0, (size_t)e->n_nodes * 4, s));
+  const int rc = place_locked(e, (const lwse_place_req*)e->place_reqs.p, n_reqs, (const uint32_t*)e->place_occ.p, n_namespaces,
+                              (lwse_place_out*)e->place_out.p, rounds_out, s, 1, n_reqs, 0);
+  if (rc != LWSE_OK) return rc;
+  if (n_reqs)
+    LWSE_CUDA(e, cudaMemcpyAsync(out, e->place_out.p, (size_t)n_reqs * sizeof(lwse_place_out), cudaMemcpyDeviceToHost, s));
+  LWSE_CUDA(e, cudaStreamSynchronize(s));
   return LWSE_OK;
 }
 
@@ -904,6 +1021,218 @@ LWSE_API int lwse_reconcile_host(lwse_engine* e, const lwse_lws_tables* h, const
     if (rc_sweep == LWSE_OK && pe != cudaSuccess) return fail_cuda(e, pe);
   }
   return rc_sweep;
+}
+
+// ---------------------------------------------------------------------------
+// The resident tick
+// ---------------------------------------------------------------------------
+LWSE_API int lwse_resident_place_load(lwse_engine* e, const lwse_place_req* reqs, uint32_t n_reqs,
+                                      uint32_t n_namespaces) {
+  if (!e || (n_reqs && !reqs) || n_namespaces == 0 || !aligned16(reqs)) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->r_loaded || e->n_nodes == 0 || e->n_domains == 0) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  cudaStream_t s = e->stream;
+  const size_t b_req = (size_t)n_reqs * sizeof(lwse_place_req), b_out = (size_t)n_reqs * sizeof(lwse_place_out);
+  LWSE_CUDA(e, e->r_preq.reserve(b_req + 16));
+  LWSE_CUDA(e, e->r_pout.reserve(b_out + 16));
+  LWSE_CUDA(e, e->r_pout_prev.reserve(b_out + 16));
+  if (b_req) LWSE_CUDA(e, cudaMemcpyAsync(e->r_preq.p, reqs, b_req, cudaMemcpyHostToDevice, s));
+  if (b_out) LWSE_CUDA(e, cudaMemsetAsync(e->r_pout_prev.p, 0xFF, b_out, s));  // the first tick reports every row
+  LWSE_CUDA(e, cudaStreamSynchronize(s));
+  e->rn_reqs = n_reqs;
+  e->rn_namespaces = n_namespaces;
+  e->r_place_loaded = true;
+  return reserve_change_lists(e);
+}
+
+static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#endif
+}
+
+// Spin until the device has raised *w to `seq` (mapped host memory).  While waiting, look at the
+// stream now and then: a faulted kernel never raises the word.  false = error or 10 s without news.
+static bool wait_word(volatile uint32_t* w, uint32_t seq, cudaStream_t s, cudaError_t* err) {
+  *err = cudaSuccess;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint64_t it = 1;; it++) {
+    if (*w == seq) {
+      std::atomic_thread_fence(std::memory_order_acquire);
+      return true;
+    }
+    cpu_relax();
+    if ((it & 0x3FFFu) == 0) {
+      const cudaError_t q = cudaStreamQuery(s);
+      if (q != cudaSuccess && q != cudaErrorNotReady) {
+        *err = q;
+        return false;
+      }
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 10.0) return *w == seq;
+    }
+  }
+}
+
+struct TickCounts {
+  uint32_t n_lws = 0, n_groups = 0, n_place = 0, rounds = 0;
+};
+
+static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_segs, uint32_t flags, TickCounts* out) {
+  cudaStream_t s = e->stream;
+  uint32_t seq = ++e->tick_seq;
+  if (seq == 0) seq = ++e->tick_seq;
+  volatile uint32_t* hw = static_cast<volatile uint32_t*>(e->tickw.h);
+  uint32_t* hw_dev = static_cast<uint32_t*>(e->tickw.d);
+  uint8_t* chg_d = static_cast<uint8_t*>(e->chg.d);
+  bool wrote = false;
+  int rc = apply_patches_locked(e, segs, n_segs, &wrote);
+  if (rc != LWSE_OK) return rc;
+  const bool do_place = (flags & LWSE_TICK_PLACE) && e->r_place_loaded && e->rn_reqs > 0;
+  const bool do_sweep = !(flags & LWSE_TICK_NO_SWEEP) && (e->rn_lws || e->rn_groups);
+  int cuda_err = 0;
+  if (do_place) {
+    // the round reads the request table and the occupancy counters, which the patches may have
+    // touched: it forks from the engine's stream behind the scatter kernel
+    LWSE_CUDA(e, cudaEventRecord(e->ev_fork, s));
+    LWSE_CUDA(e, cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+    rc = place_locked(e, (const lwse_place_req*)e->r_preq.p, e->rn_reqs, (const uint32_t*)e->r_occ.p, e->rn_namespaces,
+                      (lwse_place_out*)e->r_pout.p, nullptr, e->side_stream, 1, e->rn_reqs, 0);
+    if (rc != LWSE_OK) return rc;
+    int launched = lwse::launch_place_publish(
+        (const lwse_place_out*)e->r_pout.p, (lwse_place_out*)e->r_pout_prev.p, e->rn_reqs,
+        reinterpret_cast<uint32_t*>(chg_d + e->chg_off[4]), reinterpret_cast<lwse_place_out*>(chg_d + e->chg_off[5]),
+        e->rn_reqs, (uint32_t*)e->r_counts.p + 4, (uint32_t*)e->r_counts.p + 5, e->place_counters + 3, hw_dev + 4, seq,
+        e->side_stream, &cuda_err);
+    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+    e->launches += (uint64_t)launched;
+  }
+  bool published = false;
+  if (do_sweep) {
+    lwse_lws_tables d{};
+    d.lws = (const lwse_lws_rec*)e->r_lws.p;
+    d.n_lws = e->rn_lws;
+    d.groups = (const lwse_group_rec*)e->r_groups.p;
+    d.n_groups = e->rn_groups;
+    d.pod_state = (const lwse_pod_state*)e->r_pst.p;
+    d.pod_ident = (const lwse_pod_ident*)e->r_pid.p;
+    d.n_pods = e->rn_pods;
+    d.lws_out = (lwse_lws_out*)e->r_lws_out.p;
+    d.group_out = (lwse_group_out*)e->r_group_out.p;
+    d.flags = flags & LWSE_SWEEP_GANG;
+    lwse::SweepChangeLists cl;
+    cl.lws_rows = reinterpret_cast<uint32_t*>(chg_d + e->chg_off[0]);
+    cl.lws_out = reinterpret_cast<lwse_lws_out*>(chg_d + e->chg_off[1]);
+    cl.lws_capacity = e->rn_lws;
+    cl.group_rows = reinterpret_cast<uint32_t*>(chg_d + e->chg_off[2]);
+    cl.group_out = reinterpret_cast<lwse_group_out*>(chg_d + e->chg_off[3]);
+    cl.group_capacity = e->rn_groups;
+    cl.counts = (uint32_t*)e->r_counts.p;
+    cl.host_words = hw_dev;
+    cl.seq = seq;
+    int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes, e->r_scan.p, e->sm_count, s,
+                                          &cuda_err, &cl, nullptr, /*first_pdl=*/!wrote);
+    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+    e->launches += (uint64_t)launched;
+    published = e->rn_lws > 0;  // the LWS pass's last CTA raises the sequence word
+  }
+  // ---- the tick's only wait ----
+  cudaError_t werr = cudaSuccess;
+  bool ok = true;
+  if (published) {
+    ok = wait_word(hw + 2, seq, s, &werr);
+  } else if (do_sweep || wrote) {
+    werr = cudaStreamSynchronize(s);
+    ok = werr == cudaSuccess;
+    if (ok && do_sweep) {  // (no LWS rows: fetch the group pass's counter the slow way)
+      uint32_t c[2] = {0, 0};
+      werr = cudaMemcpy(c, e->r_counts.p, 8, cudaMemcpyDeviceToHost);
+      if (werr == cudaSuccess) werr = cudaMemset(e->r_counts.p, 0, 8);
+      ok = werr == cudaSuccess;
+      hw[0] = c[0];
+      hw[1] = c[1];
+    }
+  }
+  if (ok && do_place) ok = wait_word(hw + 6, seq, e->side_stream, &werr);
+  if (!ok) {
+    const cudaError_t a = cudaStreamSynchronize(s), b = cudaStreamSynchronize(e->side_stream);
+    return fail_cuda(e, werr != cudaSuccess ? werr : a != cudaSuccess ? a : b != cudaSuccess ? b : cudaErrorUnknown);
+  }
+  out->n_lws = do_sweep ? hw[0] : 0u;
+  out->n_groups = do_sweep ? hw[1] : 0u;
+  out->n_place = do_place ? hw[4] : 0u;
+  out->rounds = do_place ? hw[5] : 0u;
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_resident_tick(lwse_engine* e, lwse_tick* t) {
+  if (!e || !t || (t->n_segs && !t->segs)) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->r_loaded) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  TickCounts c;
+  const int rc = tick_locked(e, t->segs, t->n_segs, t->flags, &c);
+  if (rc != LWSE_OK) return rc;
+  const uint8_t* base = static_cast<const uint8_t*>(e->chg.h);
+  t->lws_rows = reinterpret_cast<const uint32_t*>(base + e->chg_off[0]);
+  t->lws_out = reinterpret_cast<const lwse_lws_out*>(base + e->chg_off[1]);
+  t->group_rows = reinterpret_cast<const uint32_t*>(base + e->chg_off[2]);
+  t->group_out = reinterpret_cast<const lwse_group_out*>(base + e->chg_off[3]);
+  t->place_rows = reinterpret_cast<const uint32_t*>(base + e->chg_off[4]);
+  t->place_out = reinterpret_cast<const lwse_place_out*>(base + e->chg_off[5]);
+  t->n_lws = c.n_lws;
+  t->n_groups = c.n_groups;
+  t->n_place = c.n_place;
+  t->place_rounds = c.rounds;
+  return LWSE_OK;
+}
+
+// The earlier form of the tick: no patches, no placement, results copied to the caller's arrays.
+LWSE_API int lwse_resident_sweep(lwse_engine* e, uint32_t flags, lwse_changes* ch) {
+  if (!e) return LWSE_ERR_INVALID_ARG;
+  if (ch && ((ch->lws_capacity && (!ch->lws_rows || !ch->lws_out)) || (ch->group_capacity && (!ch->group_rows || !ch->group_out))))
+    return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->r_loaded) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  TickCounts c;
+  const int rc = tick_locked(e, nullptr, 0, flags & LWSE_SWEEP_GANG, &c);
+  if (rc != LWSE_OK || !ch) return rc;
+  ch->n_lws = c.n_lws;
+  ch->n_groups = c.n_groups;
+  const uint32_t nl = c.n_lws < ch->lws_capacity ? c.n_lws : ch->lws_capacity;
+  const uint32_t ng = c.n_groups < ch->group_capacity ? c.n_groups : ch->group_capacity;
+  const uint8_t* base = static_cast<const uint8_t*>(e->chg.h);
+  if (nl) {
+    memcpy(ch->lws_rows, base + e->chg_off[0], (size_t)nl * 4);
+    memcpy(ch->lws_out, base + e->chg_off[1], (size_t)nl * sizeof(lwse_lws_out));
+  }
+  if (ng) {
+    memcpy(ch->group_rows, base + e->chg_off[2], (size_t)ng * 4);
+    memcpy(ch->group_out, base + e->chg_off[3], (size_t)ng * sizeof(lwse_group_out));
+  }
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_resident_place_outputs(lwse_engine* e, lwse_place_out* out) {
+  if (!e || !out) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->r_place_loaded) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  LWSE_CUDA(e, cudaStreamSynchronize(e->side_stream));
+  if (e->rn_reqs)
+    LWSE_CUDA(e, cudaMemcpy(out, e->r_pout.p, (size_t)e->rn_reqs * sizeof(lwse_place_out), cudaMemcpyDeviceToHost));
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_resident_occupancy(lwse_engine* e, uint32_t* occupancy_out) {
+  if (!e || !occupancy_out) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->r_loaded || e->n_nodes == 0) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  LWSE_CUDA(e, cudaStreamSynchronize(e->stream));
+  LWSE_CUDA(e, cudaMemcpy(occupancy_out, e->r_occ.p, (size_t)e->n_nodes * 4, cudaMemcpyDeviceToHost));
+  return LWSE_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -973,17 +1302,21 @@ LWSE_API int lwse_sweep_ds_host(lwse_engine* e, const lwse_ds_tables* h) {
 // ---------------------------------------------------------------------------
 // SHA-1 group keys
 // ---------------------------------------------------------------------------
-LWSE_API int lwse_group_keys_device(lwse_engine* e, const uint8_t* d_bytes, const uint32_t* d_offsets,
-                                    uint32_t n, uint8_t* d_digests, void* stream) {
-  if (!e || (n && (!d_offsets || !d_digests))) return LWSE_ERR_INVALID_ARG;
-  std::lock_guard<std::mutex> lock(e->mu);
-  DeviceGuard guard(e->device);
-  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+static int group_keys_locked(lwse_engine* e, const uint8_t* d_bytes, const uint32_t* d_offsets, uint32_t n,
+                             uint8_t* d_digests, cudaStream_t s) {
   int cuda_err = 0;
   int launched = lwse::launch_sha1(d_bytes, d_offsets, n, d_digests, e->sm_count, s, &cuda_err);
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
   return LWSE_OK;
+}
+
+LWSE_API int lwse_group_keys_device(lwse_engine* e, const uint8_t* d_bytes, const uint32_t* d_offsets,
+                                    uint32_t n, uint8_t* d_digests, void* stream) {
+  if (!e || (n && (!d_offsets || !d_digests))) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  return group_keys_locked(e, d_bytes, d_offsets, n, d_digests, stream ? (cudaStream_t)stream : e->stream);
 }
 
 LWSE_API int lwse_group_keys_host(lwse_engine* e, const uint8_t* bytes, const uint32_t* offsets,
@@ -992,23 +1325,20 @@ LWSE_API int lwse_group_keys_host(lwse_engine* e, const uint8_t* bytes, const ui
   if (n == 0) return LWSE_OK;
   const size_t total = offsets[n];
   if (total && !bytes) return LWSE_ERR_INVALID_ARG;
-  {
-    std::lock_guard<std::mutex> lock(e->mu);
-    DeviceGuard guard(e->device);
-    LWSE_CUDA(e, e->sha_bytes.reserve(total + 64));
-    LWSE_CUDA(e, e->sha_offsets.reserve((size_t)(n + 1) * 4 + 16));
-    LWSE_CUDA(e, e->sha_digests.reserve((size_t)n * 20 + 16));
-    if (total) LWSE_CUDA(e, cudaMemcpyAsync(e->sha_bytes.p, bytes, total, cudaMemcpyHostToDevice, e->stream));
-    LWSE_CUDA(e, cudaMemcpyAsync(e->sha_offsets.p, offsets, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice,
-                                 e->stream));
-  }
-  int rc = lwse_group_keys_device(e, (const uint8_t*)e->sha_bytes.p, (const uint32_t*)e->sha_offsets.p, n,
-                                  (uint8_t*)e->sha_digests.p, nullptr);
-  if (rc != LWSE_OK) return rc;
+  // one lock for staging, launch and download (concurrent webhook admissions share the buffers)
   std::lock_guard<std::mutex> lock(e->mu);
   DeviceGuard guard(e->device);
-  LWSE_CUDA(e, cudaMemcpyAsync(digests, e->sha_digests.p, (size_t)n * 20, cudaMemcpyDeviceToHost, e->stream));
-  LWSE_CUDA(e, cudaStreamSynchronize(e->stream));
+  cudaStream_t s = e->stream;
+  LWSE_CUDA(e, e->sha_bytes.reserve(total + 64));
+  LWSE_CUDA(e, e->sha_offsets.reserve((size_t)(n + 1) * 4 + 16));
+  LWSE_CUDA(e, e->sha_digests.reserve((size_t)n * 20 + 16));
+  if (total) LWSE_CUDA(e, cudaMemcpyAsync(e->sha_bytes.p, bytes, total, cudaMemcpyHostToDevice, s));
+  LWSE_CUDA(e, cudaMemcpyAsync(e->sha_offsets.p, offsets, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s));
+  const int rc = group_keys_locked(e, (const uint8_t*)e->sha_bytes.p, (const uint32_t*)e->sha_offsets.p, n,
+                                   (uint8_t*)e->sha_digests.p, s);
+  if (rc != LWSE_OK) return rc;
+  LWSE_CUDA(e, cudaMemcpyAsync(digests, e->sha_digests.p, (size_t)n * 20, cudaMemcpyDeviceToHost, s));
+  LWSE_CUDA(e, cudaStreamSynchronize(s));
   return LWSE_OK;
 }
 

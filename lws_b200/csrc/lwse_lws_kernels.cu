@@ -1,30 +1,27 @@
-// LWS sweep kernels (sm_100a).  One sweep = two launches on one stream when groups are small
-// and no per-node pod count is wanted — group_fused_kernel (the pod scan and the group pass of
-// 256 consecutive groups in one CTA, bitmaps in shared memory) and lws_sweep_kernel — and
-// three otherwise:
+// LWS sweep kernels (sm_100a).  One sweep = two launches on one stream when groups are small —
+// group_fused_kernel (the pod scan and the group pass of 256 consecutive groups in one CTA,
+// bitmaps in shared memory) and lws_sweep_kernel — and three otherwise:
 //
-//   pod_scan_kernel<U>   pod-centric streaming pass over the 4-byte pod state
-//                        column: every lane takes U pods with coalesced loads
-//                        (all U loads in flight before the first use), derives
-//                        "Pending" (pod_controller.go:356) and "has a restart or
-//                        deletion event" (pod_utils.go:29-50) per pod and packs
-//                        them with __ballot_sync into two bitmaps (1 bit / pod).
-//                        No dependence on group rows → pure HBM streaming.
-//   group_sweep_kernel   one lane per pod group.  Reads its 64-byte group row,
-//                        the first 16 bytes of its owner row and the bitmap words
-//                        of its pod range; only pods whose event bit is set are
-//                        visited individually (state word + 12-byte identity row:
-//                        workerPodBelongsToLeader, pod_controller.go:268-295).
-//                        Emits the per-replica state bits
-//                        (leaderworkerset_controller.go:608-638, :433-476), the
-//                        restart verdict (pod_controller.go:204-266) and the
-//                        leader pod's worker-sts gating (:100-198).  16 B out.
-//   lws_sweep_kernel<W>  one W-lane tile per LeaderWorkerSet over its groups'
-//                        flag words: counters via redux.sync, the five cases of
-//                        rollingUpdateParameters, the partition walk (:643-673)
-//                        as three reductions.  32 B out per object.
+//   pod_scan_kernel<U>   pod-centric streaming pass over the 1-BYTE pod state column: every
+//                        lane takes U x 16 pods with coalesced 128-bit loads (all U loads in
+//                        flight before the first use), derives "Pending" (pod_controller.go:356)
+//                        and "has a restart or deletion event" (pod_utils.go:29-50) for 4 pods
+//                        per 32-bit SWAR step and packs them into two bitmaps (1 bit / pod).
+//   group_sweep_kernel   one lane (or W-lane tile) per pod group.  Reads its 64-byte group row,
+//                        the first 16 bytes of its owner row and the bitmap words of its pod
+//                        range; only pods whose event bit is set are visited individually
+//                        (state byte + 16-byte identity row: workerPodBelongsToLeader,
+//                        pod_controller.go:268-295).  Emits the restart verdict
+//                        (pod_controller.go:204-266), the leader pod's worker-sts gating
+//                        (:100-198), and the per-replica state bits
+//                        (leaderworkerset_controller.go:608-638, :433-476) — the latter also as
+//                        one BYTE per group in a dense column for the LWS pass.
+//   lws_sweep_kernel<W>  one lane (W lanes for objects with hundreds of groups) per
+//                        LeaderWorkerSet over its groups' flag bytes, 8 groups per 64-bit SWAR
+//                        step: counters are popcounts of masked byte lanes, the partition walk
+//                        (:643-673) is three such reductions.  32 B out per object.
 //
-// All three are integer/compare kernels bound by HBM traffic.
+// All of them are integer/compare kernels bound by HBM traffic.
 #include <cstdlib>
 
 #include "lwse_device.cuh"
@@ -35,12 +32,10 @@ namespace lwse {
 // pod scan
 // --------------------------------------------------------------------------
 struct PodScanArgs {
-  const uint32_t* state;
+  const uint8_t* state;
   uint32_t* pending_bits;  // ceil(n_pods / 32) words
   uint32_t* event_bits;
-  uint32_t* occupancy;  // nullable: scheduled pods per node
   uint64_t n_pods;
-  uint32_t n_nodes;
   uint32_t* event_count;  // nullable: += pods with an event bit (the host entry point sizes its
                           // identity-column transfer with it)
 };
@@ -51,39 +46,48 @@ __device__ __forceinline__ bool pod_has_event(uint32_t bits) {
   return ((phase - 1u) < 2u && (bits & LWSE_POD_ANY_RESTART)) || (bits & LWSE_POD_DELETING);
 }
 
-// 4 predicate bits of the 4 pods a lane holds, moved to the lane's nibble of its
-// 8-lane segment; a 3-step xor butterfly ORs the segment into one bitmap word
-// (32 consecutive pods) that every lane of the segment ends up holding.
-// (__reduce_or_sync with a sub-warp mask compiles to a serialised per-segment
-// loop on sm_100a — measured slower — so the butterfly uses plain shuffles.)
-__device__ __forceinline__ uint32_t seg8_or(uint32_t nibble, uint32_t lane) {
-  uint32_t v = nibble << ((lane & 7u) * 4u);
-  v |= __shfl_xor_sync(0xFFFFFFFFu, v, 1);
-  v |= __shfl_xor_sync(0xFFFFFFFFu, v, 2);
-  v |= __shfl_xor_sync(0xFFFFFFFFu, v, 4);
-  return v;
+// SWAR over the 16 pods of one 128-bit load: every byte is one pod's state (phase bits 0-1,
+// any-restart bit 2, deleting bit 3).  Both predicates are evaluated on four bytes at once and
+// the four bit-0s are gathered into a nibble with one multiply; 16 bits per predicate per lane.
+__device__ __forceinline__ void pod16_predicates(const uint4 v, uint32_t& pend16, uint32_t& ev16) {
+  const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+  pend16 = 0;
+  ev16 = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t X = x[k], y = X >> 1, z = X >> 2, w3 = X >> 3;
+    const uint32_t P = X & ~y & 0x01010101u;                // phase == Pending (bit0 ∧ ¬bit1)
+    const uint32_t E = (((X ^ y) & z) | w3) & 0x01010101u;  // (phase ∈ {Pending,Running} ∧ restart) ∨ deleting
+    pend16 |= ((P * 0x10204080u) >> 28) << (4 * k);
+    ev16 |= ((E * 0x10204080u) >> 28) << (4 * k);
+  }
 }
 
-// SWAR over the 4 pods of a lane: byte k of X = low byte of pod k's state word (phase bits 0-1,
-// any-restart bit 2, deleting bit 3), both predicates evaluated on the four bytes at once, then
-// the four bit-0s are gathered into a nibble with one multiply.
-__device__ __forceinline__ void pod4_predicates(const uint4 v, uint32_t& pend, uint32_t& ev) {
-  const uint32_t X = __byte_perm(__byte_perm(v.x, v.y, 0x0040), __byte_perm(v.z, v.w, 0x0040), 0x5410);
-  const uint32_t y = X >> 1, z = X >> 2, w3 = X >> 3;
-  const uint32_t P = X & ~y & 0x01010101u;                // phase == Pending (bit0 ∧ ¬bit1)
-  const uint32_t E = (((X ^ y) & z) | w3) & 0x01010101u;  // (phase ∈ {Pending,Running} ∧ restart) ∨ deleting
-  pend = (P * 0x10204080u) >> 28;
-  ev = (E * 0x10204080u) >> 28;
+// Two neighbouring lanes hold the 32 pods of one bitmap word: one shuffle moves both predicate
+// halves; the even lane ends up with the two words.
+__device__ __forceinline__ void pair_words(uint32_t pend16, uint32_t ev16, uint32_t& wp, uint32_t& we) {
+  const uint32_t mine = pend16 | (ev16 << 16);
+  const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, mine, 1);
+  wp = (mine & 0xFFFFu) | (other << 16);
+  we = (mine >> 16) | (other & 0xFFFF0000u);
 }
 
-template <int U, bool OCC>
+// 16 state bytes at pod index idx (idx % 16 == 0); bytes past the end of the column read as 0
+__device__ __forceinline__ uint4 load_pods16(const uint8_t* state, uint64_t idx, uint64_t n_pods) {
+  if (idx + 15u < n_pods) return ldg_stream(state + idx);
+  uint32_t w[4] = {0, 0, 0, 0};
+  for (uint32_t k = 0; k < 16u; k++)
+    if (idx + k < n_pods) w[k >> 2] |= (uint32_t)__ldg(state + idx + k) << (8u * (k & 3u));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int U>
 __global__ void __launch_bounds__(256) pod_scan_kernel(const PodScanArgs a) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t warp = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5);
   const uint64_t n_warps = (uint64_t)gridDim.x * 8u;
   const uint64_t n_words = (a.n_pods + 31u) >> 5;
-  constexpr uint64_t kPodsPerChunk = 128ull * U;  // 32 lanes x 4 pods x U
-  const uint4* vec = reinterpret_cast<const uint4*>(a.state);
+  constexpr uint64_t kPodsPerChunk = 512ull * U;  // 32 lanes x 16 pods x U
   pdl_launch_dependents();
   bool waited = false;
   uint32_t events = 0;
@@ -91,15 +95,8 @@ __global__ void __launch_bounds__(256) pod_scan_kernel(const PodScanArgs a) {
     uint4 v[U];
 #pragma unroll
     for (int j = 0; j < U; j++) {  // all U 128-bit loads in flight before the first use
-      const uint64_t idx = base + (uint64_t)j * 128u + lane * 4u;
-      if (idx + 3u < a.n_pods) {
-        v[j] = ldg_stream(vec + (idx >> 2));
-      } else {  // ragged tail of the column
-        v[j].x = idx + 0u < a.n_pods ? __ldg(a.state + idx + 0u) : 0u;
-        v[j].y = idx + 1u < a.n_pods ? __ldg(a.state + idx + 1u) : 0u;
-        v[j].z = idx + 2u < a.n_pods ? __ldg(a.state + idx + 2u) : 0u;
-        v[j].w = 0u;
-      }
+      const uint64_t idx = base + (uint64_t)j * 512u + lane * 16u;
+      v[j] = idx < a.n_pods ? load_pods16(a.state, idx, a.n_pods) : make_uint4(0, 0, 0, 0);
     }
     if (!waited) {  // the bitmaps (and counters) may still be read by the previous sweep's group pass
       pdl_wait_prior();
@@ -107,21 +104,11 @@ __global__ void __launch_bounds__(256) pod_scan_kernel(const PodScanArgs a) {
     }
 #pragma unroll
     for (int j = 0; j < U; j++) {
-      uint32_t pend, ev;
-      pod4_predicates(v[j], pend, ev);
-      if (OCC) {
-        const uint32_t b[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          if (b[k] & LWSE_POD_SCHEDULED) {
-            const uint32_t node = b[k] >> LWSE_POD_NODE_SHIFT;
-            if (node < a.n_nodes) atomicAdd(a.occupancy + node, 1u);
-          }
-        }
-      }
-      const uint32_t wp = seg8_or(pend, lane), we = seg8_or(ev, lane);
-      const uint64_t w = ((base + (uint64_t)j * 128u) >> 5) + (lane >> 3);
-      if ((lane & 7u) == 0u && w < n_words) {
+      uint32_t pend, ev, wp, we;
+      pod16_predicates(v[j], pend, ev);
+      pair_words(pend, ev, wp, we);
+      const uint64_t w = ((base + (uint64_t)j * 512u) >> 5) + (lane >> 1);
+      if ((lane & 1u) == 0u && w < n_words) {
         a.pending_bits[w] = wp;
         a.event_bits[w] = we;
         events += __popc(we);
@@ -134,10 +121,25 @@ __global__ void __launch_bounds__(256) pod_scan_kernel(const PodScanArgs a) {
   }
 }
 
+// Scheduled pods per node (the placement occupancy): the node binding lives in the cold identity
+// rows, so this optional count reads that column (16 B / pod).  The resident engine counts once
+// at load and then follows the identity-row patches (scatter kernel below).
+__global__ void __launch_bounds__(256) pod_occupancy_kernel(const lwse_pod_ident* __restrict__ ident, uint64_t n_pods,
+                                                            uint32_t* __restrict__ occupancy, uint32_t n_nodes) {
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pods; p += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 r = ldg_stream(ident + p);
+    if (r.w & LWSE_PODID_SCHEDULED) {
+      const uint32_t node = r.w >> LWSE_PODID_NODE_SHIFT;
+      if (node < n_nodes) atomicAdd(occupancy + node, 1u);
+    }
+  }
+}
+
 // --------------------------------------------------------------------------
 // group pass
 // --------------------------------------------------------------------------
-// Optional change list: result rows that differ from what the output table held before.
+// Optional change list: result rows that differ from what the output table held before.  The
+// list may live in mapped host memory (lwse_resident_tick): writers fence at system scope.
 struct ChangeList {
   uint32_t* rows;   // nullptr = off
   void* outs;       // packed result rows
@@ -151,7 +153,7 @@ __device__ __forceinline__ void emit_if_changed(const ChangeList& c, uint4* slot
     bool diff = false;
 #pragma unroll
     for (int k = 0; k < N; k++) {
-      const uint4 old = slot[k];
+      const uint4 old = __ldcg(slot + k);
       diff |= old.x != v[k].x || old.y != v[k].y || old.z != v[k].z || old.w != v[k].w;
     }
     if (diff) {
@@ -160,6 +162,7 @@ __device__ __forceinline__ void emit_if_changed(const ChangeList& c, uint4* slot
         c.rows[i] = row;
 #pragma unroll
         for (int k = 0; k < N; k++) reinterpret_cast<uint4*>(c.outs)[(size_t)i * N + k] = v[k];
+        __threadfence_system();  // the list may be host memory read right after the tick's flag
       }
     }
   }
@@ -170,18 +173,21 @@ __device__ __forceinline__ void emit_if_changed(const ChangeList& c, uint4* slot
 struct GroupSweepArgs {
   const lwse_lws_rec* lws;
   const lwse_group_rec* groups;
-  const uint32_t* pod_state;
+  const uint8_t* pod_state;
   const lwse_pod_ident* pod_ident;
   const uint32_t* pending_bits;
   const uint32_t* event_bits;
   const lwse_node_rec* nodes;
   lwse_group_out* out;
+  uint8_t* gflag8;  // dense column: the low 5 bits of out.flags, one byte per group (for the LWS pass)
   uint64_t n_pods;
   uint32_t n_lws;
   uint32_t n_groups;
   uint32_t n_nodes;
   uint32_t sweep_flags;
   ChangeList changes;
+  uint32_t* event_count;  // nullable (fused kernel): += (group, event pod) pairs visited — sizes the host
+                          // entry point's identity-column transfer of the NEXT call
 };
 
 // bits [lo, hi) of a 32-bit word, 0 <= lo <= hi <= 32
@@ -190,193 +196,228 @@ __device__ __forceinline__ uint32_t bit_range(uint32_t lo, uint32_t hi) {
   return upto_hi & ~((1u << lo) - 1u) & (lo >= 32u ? 0u : 0xFFFFFFFFu);
 }
 
-// Where a group's bitmap words come from: the scan kernel's global bitmaps, or the
+// Where a group's bitmap words come from: the scan kernel's global bitmaps (written by the
+// previous kernel of the same sweep: read through L2, never the non-coherent path), or the
 // shared-memory window of the fused kernel.
 struct GlobalBits {
   const uint32_t* pending_bits;
   const uint32_t* event_bits;
-  __device__ __forceinline__ uint32_t pending(uint32_t w) const { return __ldg(pending_bits + w); }
-  __device__ __forceinline__ uint32_t event(uint32_t w) const { return __ldg(event_bits + w); }
+  __device__ __forceinline__ uint32_t pending(uint32_t w) const { return __ldcg(pending_bits + w); }
+  __device__ __forceinline__ uint32_t event(uint32_t w) const { return __ldcg(event_bits + w); }
 };
 
-// The group pass proper for group g (row ca..cd, first 16 bytes of its owner L): one W-lane
-// tile per group, the lanes share the group's bitmap words (lane j takes words j, j+W, …) so
-// that the rare per-pod visits of one group run in parallel; W = 1 for small groups.
-// Returns the 16-byte result row.
-template <int W, class Bits>
-__device__ __forceinline__ uint4 group_body(const GroupSweepArgs& a, const Bits& bits, uint32_t lane, const uint4 ca,
-                                            const uint4 cb, const uint4 cc, const uint4 cd, const uint4 L,
-                                            const bool bad) {
-  const uint32_t pod_base = cc.z, pod_count = cc.w, gflags = cd.y;
-  uint32_t oflags = 0, first_out = LWSE_NONE, domain = LWSE_NONE;
-  int32_t worker_replicas = 0;
-  if (bad) {
-    oflags = LWSE_GOUT_BAD_TABLE;
+// What deciding one event pod needs from its group (pod_controller.go:233-257).
+struct VisitCtx {
+  uint32_t rev_lo, rev_hi;  // leader pod's revision hash
+  uint32_t leader_uid, wsts_uid;
+  uint32_t pod_base;
+  uint32_t bits;  // kLeaderFound | kChainOk | kLeaderDeleting
+};
+constexpr uint32_t kLeaderFound = 1u, kChainOk = 2u, kLeaderDeleting = 4u;
+constexpr uint32_t kAccLeaderCand = 0x80000000u;
+
+// handleRestartPolicy (:204-266) for ONE pod that has a restart / deletion event, policy checks
+// already done: returns the verdict bits it contributes; *cand = it would recreate the group.
+__device__ __forceinline__ uint32_t visit_pod(const VisitCtx& c, uint32_t state, const uint4 id, bool& cand) {
+  uint32_t acc = 0;
+  bool deleting;
+  if (state & LWSE_POD_IS_LEADER) {
+    cand = true;  // leader = pod (:251)
+    deleting = state & LWSE_POD_DELETING;
+    acc |= kAccLeaderCand;
+  } else if (!(id.w & LWSE_PODID_NAME_OK)) {
+    cand = false;
+    return LWSE_GOUT_RESTART_ERROR;  // :230
   } else {
-    const int32_t size = (int32_t)L.z;
-    const uint32_t lflags = L.w;
-    const uint32_t policy = (lflags & LWSE_LWS_RESTART_MASK) >> LWSE_LWS_RESTART_SHIFT;
-    const bool policy_on = policy == LWSE_RESTART_ON_POD_RESTART || policy == LWSE_RESTART_AFTER_START;
+    const uint32_t kind = (state & LWSE_POD_OWNER_MASK) >> LWSE_POD_OWNER_SHIFT;
+    // workerPodBelongsToLeader :268-295
+    const bool belongs = (state & LWSE_POD_OWNER_NAME_MATCH) &&
+                         ((kind == 1u && id.z == c.leader_uid) || (kind == 2u && id.z == c.wsts_uid && (c.bits & kChainOk)));
+    cand = (c.bits & kLeaderFound) && id.x == c.rev_lo && id.y == c.rev_hi && belongs;  // :233, :239
+    deleting = c.bits & kLeaderDeleting;
+  }
+  if (!cand) return 0;
+  return acc | (deleting ? LWSE_GOUT_LEADER_DELETING : LWSE_GOUT_DELETE_LEADER);  // :255 / :259
+}
 
-    // ---- pendingPodsInGroup :338-362 from the pending bitmap ----
-    const uint32_t pod_end = pod_base + pod_count;  // <= n_pods < 2^32 (checked by the entry points)
-    const uint32_t w_first = pod_base >> 5, w_last = pod_count ? ((pod_end - 1u) >> 5) : w_first;
-    uint32_t any_bits = 0;  // bit0 pending, bit1 event
-    if (pod_count) {
-      for (uint32_t w = w_first + lane; w <= w_last; w += W) {
-        const uint32_t lo = w == w_first ? (pod_base & 31u) : 0u;
-        const uint32_t hi = w == w_last ? (((pod_end - 1u) & 31u) + 1u) : 32u;
-        const uint32_t m = bit_range(lo, hi);
-        if (bits.pending(w) & m) any_bits |= 1u;
-        if (bits.event(w) & m) any_bits |= 2u;
+// First part of the group pass for group g (row ca..cd, first 16 bytes of its owner L):
+// pendingPodsInGroup (:338-362) from the pending bitmap and the decision whether the group's
+// event pods have to be visited at all.
+struct GroupPre {
+  uint32_t oflags;
+  uint32_t w_first, w_last, pod_end;
+  bool visit;  // tile-uniform
+  VisitCtx ctx;
+};
+
+template <int W, class Bits>
+__device__ __forceinline__ GroupPre group_pre(const Bits& bits, uint32_t lane, const uint4 ca, const uint4 cb,
+                                              const uint4 cc, const uint4 cd, const uint4 L) {
+  GroupPre r;
+  const uint32_t pod_base = cc.z, pod_count = cc.w, gflags = cd.y;
+  const int32_t size = (int32_t)L.z;
+  const uint32_t lflags = L.w;
+  const uint32_t policy = (lflags & LWSE_LWS_RESTART_MASK) >> LWSE_LWS_RESTART_SHIFT;
+  const bool policy_on = policy == LWSE_RESTART_ON_POD_RESTART || policy == LWSE_RESTART_AFTER_START;
+  r.oflags = 0;
+  r.pod_end = pod_base + pod_count;  // <= n_pods < 2^32 (checked by the entry points)
+  r.w_first = pod_base >> 5;
+  r.w_last = pod_count ? ((r.pod_end - 1u) >> 5) : r.w_first;
+  uint32_t any_bits = 0;  // bit0 pending, bit1 event
+  if (pod_count) {
+    for (uint32_t w = r.w_first + lane; w <= r.w_last; w += W) {
+      const uint32_t lo = w == r.w_first ? (pod_base & 31u) : 0u;
+      const uint32_t hi = w == r.w_last ? (((r.pod_end - 1u) & 31u) + 1u) : 32u;
+      const uint32_t m = bit_range(lo, hi);
+      if (bits.pending(w) & m) any_bits |= 1u;
+      if (bits.event(w) & m) any_bits |= 2u;
+    }
+  }
+  any_bits = tile_or<W>(any_bits);
+  const bool pending = (uint32_t)size != pod_count || (any_bits & 1u);
+  if (pending) r.oflags |= LWSE_GOUT_PENDING;
+  // :222 skip when pending ∧ (AfterStart ∨ annotation)
+  const bool suppressed =
+      pending && (policy == LWSE_RESTART_AFTER_START || (lflags & LWSE_LWS_RECREATE_AFTER_START_ANNOT));
+  r.visit = (any_bits & 2u) && policy_on && !suppressed;
+  constexpr uint32_t kChain = LWSE_GRP_WSTS_FOUND | LWSE_GRP_WSTS_OWNER_IS_POD | LWSE_GRP_WSTS_OWNER_NAME_MATCH;
+  r.ctx.rev_lo = ca.x;
+  r.ctx.rev_hi = ca.y;
+  r.ctx.leader_uid = cb.z;
+  r.ctx.wsts_uid = cb.w;
+  r.ctx.pod_base = pod_base;
+  r.ctx.bits = 0;
+  if ((gflags & (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH)) == (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH))
+    r.ctx.bits |= kLeaderFound;  // :233
+  if ((gflags & kChain) == kChain && cc.x == cb.z) r.ctx.bits |= kChainOk;  // sts owner uid == leader uid
+  if (gflags & LWSE_GRP_POD_DELETING) r.ctx.bits |= kLeaderDeleting;
+  return r;
+}
+
+// The event pods of one group visited by the group's own lanes: collected four at a time so
+// that their state and identity loads are all in flight together.
+template <int W, class Bits>
+__device__ __forceinline__ void group_visit_inline(const GroupSweepArgs& a, const Bits& bits, uint32_t lane,
+                                                   const GroupPre& pre, uint32_t& acc_out, uint32_t& first_out) {
+  uint32_t acc = 0, first = LWSE_NONE;
+  auto visit = [&](const uint32_t* ev, int cnt) {
+    uint32_t st[4];
+    uint4 id[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (k < cnt) {
+        st[k] = __ldg(a.pod_state + ev[k]);
+        id[k] = ldg_cached(a.pod_ident + ev[k]);
       }
     }
-    any_bits = tile_or<W>(any_bits);
-    const bool pending = (uint32_t)size != pod_count || (any_bits & 1u);
-    if (pending) oflags |= LWSE_GOUT_PENDING;
-    // :222 skip when pending ∧ (AfterStart ∨ annotation)
-    const bool suppressed =
-        pending && (policy == LWSE_RESTART_AFTER_START || (lflags & LWSE_LWS_RECREATE_AFTER_START_ANNOT));
-
-    // ---- handleRestartPolicy :204-266 for the pods that have an event ----
-    bool leader_deleted = false;
-    if ((any_bits & 2u) && policy_on && !suppressed) {  // tile-uniform
-      const bool leader_found = (gflags & (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH)) ==
-                                (LWSE_GRP_POD_PRESENT | LWSE_GRP_POD_NAME_MATCH);  // :233
-      constexpr uint32_t kChain =
-          LWSE_GRP_WSTS_FOUND | LWSE_GRP_WSTS_OWNER_IS_POD | LWSE_GRP_WSTS_OWNER_NAME_MATCH;
-      const bool wsts_chain_ok = (gflags & kChain) == kChain && cc.x == cb.z;  // sts owner uid == leader uid
-      uint32_t acc = 0, first = LWSE_NONE;
-      // The pods to visit are collected four at a time so that their state and
-      // identity loads are all in flight together (one DRAM round trip per batch
-      // instead of one per pod).
-      auto visit = [&](const uint32_t* ev, int cnt) {
-        uint32_t bits[4], id_lo[4], id_hi[4], id_owner[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          if (k < cnt) {
-            const uint32_t p = ev[k];
-            bits[k] = __ldg(a.pod_state + p);
-            const uint32_t* idp = reinterpret_cast<const uint32_t*>(a.pod_ident + p);
-            id_lo[k] = __ldg(idp);
-            id_hi[k] = __ldg(idp + 1);
-            id_owner[k] = __ldg(idp + 2);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          if (k < cnt) {
-            const uint32_t b = bits[k];
-            bool cand, deleting;
-            if (b & LWSE_POD_IS_LEADER) {
-              cand = true;  // leader = pod (:251)
-              deleting = b & LWSE_POD_DELETING;
-            } else if (!(b & LWSE_POD_NAME_OK)) {
-              acc |= LWSE_GOUT_RESTART_ERROR;  // :230
-              cand = false;
-              deleting = false;
-            } else {
-              const uint32_t kind = (b & LWSE_POD_OWNER_MASK) >> LWSE_POD_OWNER_SHIFT;
-              // workerPodBelongsToLeader :268-295
-              const bool belongs = (b & LWSE_POD_OWNER_NAME_MATCH) &&
-                                   ((kind == 1u && id_owner[k] == cb.z) ||
-                                    (kind == 2u && id_owner[k] == cb.w && wsts_chain_ok));
-              cand = leader_found && id_lo[k] == ca.x && id_hi[k] == ca.y && belongs;  // :239
-              deleting = gflags & LWSE_GRP_POD_DELETING;
-            }
-            if (cand) {
-              acc |= deleting ? LWSE_GOUT_LEADER_DELETING : LWSE_GOUT_DELETE_LEADER;  // :255 / :259
-              if (b & LWSE_POD_IS_LEADER) acc |= 0x80000000u;
-              first = min(first, ev[k] - pod_base);
-            }
-          }
-        }
-      };
-      uint32_t ev[4];
-      int cnt = 0;
-      for (uint32_t w = w_first + lane; w <= w_last; w += W) {
-        const uint32_t lo = w == w_first ? (pod_base & 31u) : 0u;
-        const uint32_t hi = w == w_last ? (((pod_end - 1u) & 31u) + 1u) : 32u;
-        uint32_t m = bits.event(w) & bit_range(lo, hi);
-        while (m) {
-          const uint32_t p = (w << 5) + (__ffs(m) - 1u);
-          m &= m - 1u;
-          // fixed-slot insert keeps ev[] in registers
-          if (cnt == 0) ev[0] = p;
-          else if (cnt == 1) ev[1] = p;
-          else if (cnt == 2) ev[2] = p;
-          else ev[3] = p;
-          if (++cnt == 4) {
-            visit(ev, 4);
-            cnt = 0;
-          }
-        }
+    for (int k = 0; k < 4; k++) {
+      if (k < cnt) {
+        bool cand;
+        acc |= visit_pod(pre.ctx, st[k], id[k], cand);
+        if (cand) first = min(first, ev[k] - pre.ctx.pod_base);
       }
-      if (cnt) visit(ev, cnt);
-      acc = tile_or<W>(acc);
-      first_out = tile_min<W>(first);
-      leader_deleted = acc & 0x80000000u;
-      oflags |= acc & 0x7FFFFFFFu;
     }
+  };
+  uint32_t ev[4];
+  int cnt = 0;
+  for (uint32_t w = pre.w_first + lane; w <= pre.w_last; w += W) {
+    const uint32_t lo = w == pre.w_first ? (pre.ctx.pod_base & 31u) : 0u;
+    const uint32_t hi = w == pre.w_last ? (((pre.pod_end - 1u) & 31u) + 1u) : 32u;
+    uint32_t m = bits.event(w) & bit_range(lo, hi);
+    while (m) {
+      const uint32_t p = (w << 5) + (__ffs(m) - 1u);
+      m &= m - 1u;
+      // fixed-slot insert keeps ev[] in registers
+      if (cnt == 0) ev[0] = p;
+      else if (cnt == 1) ev[1] = p;
+      else if (cnt == 2) ev[2] = p;
+      else ev[3] = p;
+      if (++cnt == 4) {
+        visit(ev, 4);
+        cnt = 0;
+      }
+    }
+  }
+  if (cnt) visit(ev, cnt);
+  acc_out = tile_or<W>(acc);
+  first_out = tile_min<W>(first);
+}
 
-    // ---- per-replica state bits (consumed by lws_sweep_kernel) ----
-    const bool no_wsts = size == 1;
-    const uint64_t rev = u64_of(L.x, L.y);
-    const bool leader_updated = u64_of(ca.x, ca.y) == rev;
-    const bool wsts_updated = u64_of(ca.z, ca.w) == rev;
-    const bool leader_ready = (gflags & (LWSE_GRP_POD_RUNNING | LWSE_GRP_POD_READY)) ==
-                              (LWSE_GRP_POD_RUNNING | LWSE_GRP_POD_READY);  // PodRunningAndReady
-    const bool wsts_ready = cb.x == cb.y && (gflags & LWSE_GRP_WSTS_REV_SETTLED);  // StatefulsetReady
-    const bool ready = leader_ready && (no_wsts || wsts_ready);
-    const bool updated = leader_updated && (no_wsts || wsts_updated);
-    // getReplicaStates :609-617 — names decide whether the slot is live
-    const bool named = (gflags & LWSE_GRP_POD_NAME_MATCH) &&
-                       (no_wsts || (gflags & LWSE_GRP_WSTS_LABEL_NAME_MATCH));
-    if (named && ready) oflags |= LWSE_GOUT_STATE_READY;
-    if (named && updated) oflags |= LWSE_GOUT_STATE_UPDATED;
-    // updateConditions :433-476 — existing leader pods whose worker sts is found
-    const bool counted = (gflags & LWSE_GRP_POD_PRESENT) && (no_wsts || (gflags & LWSE_GRP_WSTS_FOUND));
-    if (counted) {
-      oflags |= LWSE_GOUT_COUNTED;
-      if (ready) oflags |= LWSE_GOUT_COND_READY;
-      if (updated) oflags |= LWSE_GOUT_COND_UPDATED;
-    }
+// Last part: the per-replica state bits, the leader pod's own Reconcile tail
+// (pod_controller.go:95-198) and the 16-byte result row.
+__device__ __forceinline__ uint4 group_finish(const GroupSweepArgs& a, const uint4 ca, const uint4 cb, const uint4 cc,
+                                              const uint4 cd, const uint4 L, uint32_t oflags, uint32_t acc,
+                                              uint32_t first_out) {
+  const uint32_t gflags = cd.y;
+  const int32_t size = (int32_t)L.z;
+  const uint32_t lflags = L.w;
+  uint32_t domain = LWSE_NONE;
+  int32_t worker_replicas = 0;
+  const bool leader_deleted = acc & kAccLeaderCand;
+  oflags |= acc & ~kAccLeaderCand;
 
-    // ---- the leader pod's own Reconcile tail, pod_controller.go:95-198 ----
-    bool go_on = (gflags & LWSE_GRP_POD_PRESENT) && !leader_deleted &&
-                 !(gflags & (LWSE_GRP_MISTAKEN_ANNOTATION | LWSE_GRP_POD_DELETING));
-    if (go_on) {
-      if (a.sweep_flags & LWSE_SWEEP_GANG) oflags |= LWSE_GOUT_CREATE_PODGROUP;  // :130
-      go_on = !no_wsts &&                                                          // :138
-              !((lflags & LWSE_LWS_STARTUP_LEADER_READY) && !(gflags & LWSE_GRP_POD_READY));  // :143
-    }
-    if (go_on && !(gflags & LWSE_GRP_REVISION_EXISTS)) {  // :152
-      oflags |= LWSE_GOUT_REQUEUE_REVISION;
+  // ---- per-replica state bits (consumed by lws_sweep_kernel) ----
+  const bool no_wsts = size == 1;
+  const uint64_t rev = u64_of(L.x, L.y);
+  const bool leader_updated = u64_of(ca.x, ca.y) == rev;
+  const bool wsts_updated = u64_of(ca.z, ca.w) == rev;
+  const bool leader_ready = (gflags & (LWSE_GRP_POD_RUNNING | LWSE_GRP_POD_READY)) ==
+                            (LWSE_GRP_POD_RUNNING | LWSE_GRP_POD_READY);  // PodRunningAndReady
+  const bool wsts_ready = cb.x == cb.y && (gflags & LWSE_GRP_WSTS_REV_SETTLED);  // StatefulsetReady
+  const bool ready = leader_ready && (no_wsts || wsts_ready);
+  const bool updated = leader_updated && (no_wsts || wsts_updated);
+  // getReplicaStates :609-617 — names decide whether the slot is live
+  const bool named = (gflags & LWSE_GRP_POD_NAME_MATCH) && (no_wsts || (gflags & LWSE_GRP_WSTS_LABEL_NAME_MATCH));
+  if (named && ready) oflags |= LWSE_GOUT_STATE_READY;
+  if (named && updated) oflags |= LWSE_GOUT_STATE_UPDATED;
+  // updateConditions :433-476 — existing leader pods whose worker sts is found
+  const bool counted = (gflags & LWSE_GRP_POD_PRESENT) && (no_wsts || (gflags & LWSE_GRP_WSTS_FOUND));
+  if (counted) {
+    oflags |= LWSE_GOUT_COUNTED;
+    if (ready) oflags |= LWSE_GOUT_COND_READY;
+    if (updated) oflags |= LWSE_GOUT_COND_UPDATED;
+  }
+
+  // ---- the leader pod's own Reconcile tail, pod_controller.go:95-198 ----
+  bool go_on = (gflags & LWSE_GRP_POD_PRESENT) && !leader_deleted &&
+               !(gflags & (LWSE_GRP_MISTAKEN_ANNOTATION | LWSE_GRP_POD_DELETING));
+  if (go_on) {
+    if (a.sweep_flags & LWSE_SWEEP_GANG) oflags |= LWSE_GOUT_CREATE_PODGROUP;  // :130
+    go_on = !no_wsts &&                                                          // :138
+            !((lflags & LWSE_LWS_STARTUP_LEADER_READY) && !(gflags & LWSE_GRP_POD_READY));  // :143
+  }
+  if (go_on && !(gflags & LWSE_GRP_REVISION_EXISTS)) {  // :152
+    oflags |= LWSE_GOUT_REQUEUE_REVISION;
+    go_on = false;
+  }
+  if (go_on && (lflags & LWSE_LWS_EXCLUSIVE_TOPOLOGY)) {  // :162
+    const uint32_t node = cc.y;
+    if (node == LWSE_NONE) {  // :164
+      oflags |= LWSE_GOUT_WAIT_SCHEDULE;
       go_on = false;
-    }
-    if (go_on && (lflags & LWSE_LWS_EXCLUSIVE_TOPOLOGY)) {  // :162
-      const uint32_t node = cc.y;
-      if (node == LWSE_NONE) {  // :164
-        oflags |= LWSE_GOUT_WAIT_SCHEDULE;
+    } else if (node != LWSE_NODE_NOT_FOUND && node < a.n_nodes) {
+      const uint4 nr = ldg_cached(reinterpret_cast<const uint4*>(a.nodes + node));
+      const uint32_t nflags = nr.w >> 16;
+      if (!(nflags & LWSE_NODE_HAS_TOPOLOGY)) {  // :330
+        oflags |= LWSE_GOUT_TOPOLOGY_ERROR;
         go_on = false;
-      } else if (node != LWSE_NODE_NOT_FOUND && node < a.n_nodes) {
-        const uint4 nr = ldg_cached(reinterpret_cast<const uint4*>(a.nodes + node));
-        const uint32_t nflags = nr.w >> 16;
-        if (!(nflags & LWSE_NODE_HAS_TOPOLOGY)) {  // :330
-          oflags |= LWSE_GOUT_TOPOLOGY_ERROR;
-          go_on = false;
-        } else {
-          domain = nr.z;
-        }
-      }  // Node NotFound → empty value, nil error (:327)
-    }
-    if (go_on && !(gflags & LWSE_GRP_WSTS_FOUND)) {  // :188-192
-      oflags |= LWSE_GOUT_CREATE_WSTS;
-      worker_replicas = size - 1;  // :437; ordinals start at 1 (:440)
-    }
+      } else {
+        domain = nr.z;
+      }
+    }  // Node NotFound → empty value, nil error (:327)
+  }
+  if (go_on && !(gflags & LWSE_GRP_WSTS_FOUND)) {  // :188-192
+    oflags |= LWSE_GOUT_CREATE_WSTS;
+    worker_replicas = size - 1;  // :437; ordinals start at 1 (:440)
   }
   return make_uint4(oflags, first_out, (uint32_t)worker_replicas, domain);
 }
+
+__device__ __forceinline__ uint4 bad_group_row() { return make_uint4(LWSE_GOUT_BAD_TABLE, LWSE_NONE, 0u, LWSE_NONE); }
+constexpr uint32_t kFlagByteMask = LWSE_GOUT_STATE_READY | LWSE_GOUT_STATE_UPDATED | LWSE_GOUT_COUNTED |
+                                   LWSE_GOUT_COND_READY | LWSE_GOUT_COND_UPDATED;
+static_assert(kFlagByteMask == 0x1Fu, "the LWS pass reads the low five bits of group_out.flags as one byte");
 
 // 128-thread CTAs capped at 64 registers: a tick's placement round holds part of the register
 // file of some SMs while this kernel runs, and the groups of a 100k-group table should still
@@ -403,26 +444,43 @@ __global__ void __launch_bounds__(kGroupThreads, 8) group_sweep_kernel(const Gro
       pdl_wait_prior();
       waited = true;
     }
-    const uint4 v[1] = {group_body<W>(a, bits, lane, ca, cb, cc, cd, L, bad)};
-    if (lane == 0) emit_if_changed<1>(a.changes, reinterpret_cast<uint4*>(a.out + g), g, v);
+    uint4 v[1] = {bad_group_row()};
+    if (!bad) {
+      const GroupPre pre = group_pre<W>(bits, lane, ca, cb, cc, cd, L);
+      uint32_t acc = 0, first = LWSE_NONE;
+      if (pre.visit) group_visit_inline<W>(a, bits, lane, pre, acc, first);
+      v[0] = group_finish(a, ca, cb, cc, cd, L, pre.oflags, acc, first);
+    }
+    if (lane == 0) {
+      emit_if_changed<1>(a.changes, reinterpret_cast<uint4*>(a.out + g), g, v);
+      a.gflag8[g] = (uint8_t)(v[0].x & kFlagByteMask);
+    }
   }
 }
 
 // --------------------------------------------------------------------------
 // fused pod scan + group pass
 // --------------------------------------------------------------------------
-// One CTA per 256 consecutive groups, one thread per group.  The CTA first streams the pod
-// state words of its groups' pod window (the union of their ranges: contiguous for tables the
-// encoder lays out, pods of group g right after those of g-1) with the scan's coalesced 128-bit
-// loads and packs the two predicate bitmaps into SHARED memory; the group pass then reads its
-// bitmap words from there.  Against the two-kernel form this drops one kernel boundary and the
-// bitmaps' round trip through L2, and the state words of the event pods the group pass visits
-// were just loaded by the same SM.  Used when no per-node occupancy is wanted (that count needs
-// every pod exactly once, whatever the group table says) and groups are small (W = 1).
-// A window that does not fit (irregular tables: ranges far apart) falls back to deriving each
-// bitmap word from the state column directly — slow, still exact.
+// One CTA per 256 consecutive groups, one thread per group.
+//   1. rows: the CTA loads its 256 group rows and the first 16 B of their owners, and reduces the
+//      union of their pod ranges to a window of bitmap words (contiguous for tables the encoder
+//      lays out: pods of group g right after those of g-1);
+//   2. scan: the window's state BYTES are streamed with coalesced 128-bit loads (16 pods each,
+//      4 in flight per lane) and the two predicate bitmaps are packed into SHARED memory;
+//   3. pre: every thread derives pendingPodsInGroup of its group and counts the event pods it
+//      has to visit (policy on, not suppressed);
+//   4. visit, event-centric: the (group, pod) pairs of the whole CTA are compacted into shared
+//      memory and taken by all 256 threads, one pair each — every identity-row load of the CTA
+//      is in flight at once instead of per-group batches of four behind divergent loops; verdicts
+//      meet in shared memory (atomicOr / atomicMin per group);
+//   5. finish: state bits, worker-sts gating, one 16-byte store and one flag byte per group.
+// Used when groups are small (the window of 256 groups fits 65 536 pods).  A window that does
+// not fit (irregular tables: ranges far apart) falls back to deriving each bitmap word from the
+// state column directly, and more pairs than the shared list holds to the per-group visit —
+// slow, still exact.
 constexpr uint32_t kFusedThreads = 256;
 constexpr uint32_t kWinWords = 2048;  // 65 536 pods per CTA: 2 x 8 KB of shared memory
+constexpr uint32_t kPairCap = 1280;   // (group, event pod) pairs visited cooperatively per CTA
 
 struct WindowBits {
   const uint32_t* pend;  // word (w - w0)
@@ -433,7 +491,7 @@ struct WindowBits {
 };
 
 struct DirectBits {
-  const uint32_t* state;
+  const uint8_t* state;
   uint64_t n_pods;
   __device__ __forceinline__ void word(uint32_t w, uint32_t& pend, uint32_t& ev) const {
     pend = ev = 0;
@@ -459,12 +517,17 @@ struct DirectBits {
 
 __global__ void __launch_bounds__(kFusedThreads, 3) group_fused_kernel(const GroupSweepArgs a) {
   __shared__ uint32_t s_pend[kWinWords], s_ev[kWinWords];
-  __shared__ uint32_t s_lo[kFusedThreads / 32], s_hi[kFusedThreads / 32];
+  __shared__ uint32_t s_pair[kPairCap];  // tid << 16 | pod index relative to the window start
+  __shared__ uint4 s_ctx4[kFusedThreads];
+  __shared__ uint2 s_ctx2[kFusedThreads];
+  __shared__ uint32_t s_acc[kFusedThreads], s_first[kFusedThreads];
+  __shared__ uint32_t s_lo[kFusedThreads / 32], s_hi[kFusedThreads / 32], s_cnt[kFusedThreads / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t g = blockIdx.x * kFusedThreads + tid;
   const bool valid = g < a.n_groups;
   pdl_launch_dependents();
 
+  // ---- 1. rows ----
   uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, cc = ca, cd = ca, L = ca;
   bool bad = true;
   if (valid) {
@@ -490,40 +553,30 @@ __global__ void __launch_bounds__(kFusedThreads, 3) group_fused_kernel(const Gro
     lo = min(lo, s_lo[k]);
     hi = max(hi, s_hi[k]);
   }
+  lo &= ~3u;  // 128-byte aligned window start: the scan's 128-bit loads stay aligned
   const uint32_t n_words = hi > lo ? hi - lo : 0u;
   const bool windowed = n_words <= kWinWords;  // CTA-uniform
 
+  // ---- 2. scan ----
   if (windowed && n_words) {
-    // the scan: 128 pods (4 bitmap words) per warp and chunk, U chunks in flight per warp
-    // (U = 8 is 0.7 us faster alone but takes 80 registers: three resident CTAs would then leave
-    // no SM with room for a placement CTA and the tick serialises — 27.0 us against 22.7 us)
+    // 512 pods (16 bitmap words) per warp and chunk, U chunks in flight per warp
     constexpr int U = 4;
-    const uint32_t n_chunks = (n_words + 3u) >> 2;
-    const uint4* vec = reinterpret_cast<const uint4*>(a.pod_state);
+    const uint32_t n_chunks = (n_words + 15u) >> 4;
     for (uint32_t c0 = warp * U; c0 < n_chunks; c0 += (kFusedThreads / 32) * U) {
       uint4 v[U];
 #pragma unroll
       for (int j = 0; j < U; j++) {
         const uint32_t c = c0 + (uint32_t)j;
-        const uint64_t idx = ((uint64_t)lo << 5) + (uint64_t)c * 128u + lane * 4u;
-        if (c >= n_chunks) {
-          v[j] = make_uint4(0, 0, 0, 0);
-        } else if (idx + 3u < a.n_pods) {
-          v[j] = ldg_stream(vec + (idx >> 2));
-        } else {  // ragged tail of the column
-          v[j].x = idx + 0u < a.n_pods ? __ldg(a.pod_state + idx + 0u) : 0u;
-          v[j].y = idx + 1u < a.n_pods ? __ldg(a.pod_state + idx + 1u) : 0u;
-          v[j].z = idx + 2u < a.n_pods ? __ldg(a.pod_state + idx + 2u) : 0u;
-          v[j].w = 0u;
-        }
+        const uint64_t idx = ((uint64_t)lo << 5) + (uint64_t)c * 512u + lane * 16u;
+        v[j] = (c < n_chunks && idx < a.n_pods) ? load_pods16(a.pod_state, idx, a.n_pods) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int j = 0; j < U; j++) {
-        uint32_t pend, ev;
-        pod4_predicates(v[j], pend, ev);
-        const uint32_t wp = seg8_or(pend, lane), we = seg8_or(ev, lane);
-        const uint32_t w = (c0 + (uint32_t)j) * 4u + (lane >> 3);
-        if ((lane & 7u) == 0u && w < n_words) {
+        uint32_t pend, ev, wp, we;
+        pod16_predicates(v[j], pend, ev);
+        pair_words(pend, ev, wp, we);
+        const uint32_t w = (c0 + (uint32_t)j) * 16u + (lane >> 1);
+        if ((lane & 1u) == 0u && w < n_words) {
           s_pend[w] = wp;
           s_ev[w] = we;
         }
@@ -532,29 +585,119 @@ __global__ void __launch_bounds__(kFusedThreads, 3) group_fused_kernel(const Gro
   }
   __syncthreads();
 
-  uint4 v[1];
+  uint4 v[1] = {bad_group_row()};
   if (windowed) {
+    // ---- 3. pre ----
     const WindowBits bits{s_pend, s_ev, lo};
-    v[0] = group_body<1>(a, bits, 0u, ca, cb, cc, cd, L, bad);
-  } else {
+    GroupPre pre{};
+    uint32_t my_pairs = 0;
+    if (!bad) {
+      pre = group_pre<1>(bits, 0u, ca, cb, cc, cd, L);
+      if (pre.visit) {
+        for (uint32_t w = pre.w_first; w <= pre.w_last; w++) {
+          const uint32_t blo = w == pre.w_first ? (cc.z & 31u) : 0u;
+          const uint32_t bhi = w == pre.w_last ? (((pre.pod_end - 1u) & 31u) + 1u) : 32u;
+          my_pairs += __popc(bits.event(w) & bit_range(blo, bhi));
+        }
+      }
+    }
+    // exclusive scan of the pair counts over the CTA
+    uint32_t incl = my_pairs;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+      if ((int)lane >= off) incl += up;
+    }
+    if (lane == 31u) s_cnt[warp] = incl;
+    s_acc[tid] = 0u;
+    s_first[tid] = LWSE_NONE;
+    __syncthreads();
+    uint32_t warp_base = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < (int)(kFusedThreads / 32); k++) {
+      const uint32_t c = s_cnt[k];
+      if (k < (int)warp) warp_base += c;
+      total += c;
+    }
+    if (a.event_count != nullptr && tid == 0 && total) atomicAdd(a.event_count, total);
+    uint32_t acc = 0, first = LWSE_NONE;
+    if (total <= kPairCap) {  // CTA-uniform
+      // ---- 4. visit, event-centric ----
+      if (total) {
+        if (my_pairs) {
+          uint32_t at = warp_base + incl - my_pairs;
+          for (uint32_t w = pre.w_first; w <= pre.w_last; w++) {
+            const uint32_t blo = w == pre.w_first ? (cc.z & 31u) : 0u;
+            const uint32_t bhi = w == pre.w_last ? (((pre.pod_end - 1u) & 31u) + 1u) : 32u;
+            uint32_t m = bits.event(w) & bit_range(blo, bhi);
+            while (m) {
+              const uint32_t rel = ((w - lo) << 5) + (__ffs(m) - 1u);  // < 65 536
+              m &= m - 1u;
+              s_pair[at++] = (tid << 16) | rel;
+            }
+          }
+          s_ctx4[tid] = make_uint4(pre.ctx.rev_lo, pre.ctx.rev_hi, pre.ctx.leader_uid, pre.ctx.wsts_uid);
+          s_ctx2[tid] = make_uint2(pre.ctx.pod_base, pre.ctx.bits);
+        }
+        __syncthreads();
+        for (uint32_t e = tid; e < total; e += kFusedThreads) {
+          const uint32_t pr = s_pair[e], t = pr >> 16;
+          const uint32_t p = (lo << 5) + (pr & 0xFFFFu);
+          const uint32_t st = __ldg(a.pod_state + p);       // the SM loaded this line a moment ago
+          const uint4 id = ldg_stream(a.pod_ident + p);     // the CTA's only gathers
+          const uint4 c4 = s_ctx4[t];
+          const uint2 c2 = s_ctx2[t];
+          const VisitCtx ctx{c4.x, c4.y, c4.z, c4.w, c2.x, c2.y};
+          bool cand;
+          const uint32_t bitsv = visit_pod(ctx, st, id, cand);
+          if (bitsv) atomicOr(&s_acc[t], bitsv);
+          if (cand) atomicMin(&s_first[t], p - c2.x);
+        }
+        __syncthreads();
+        acc = s_acc[tid];
+        first = s_first[tid];
+      }
+    } else if (pre.visit) {
+      group_visit_inline<1>(a, bits, 0u, pre, acc, first);
+    }
+    // ---- 5. finish ----
+    if (!bad) v[0] = group_finish(a, ca, cb, cc, cd, L, pre.oflags, acc, first);
+  } else if (!bad) {
     const DirectBits bits{a.pod_state, a.n_pods};
-    v[0] = group_body<1>(a, bits, 0u, ca, cb, cc, cd, L, bad);
+    const GroupPre pre = group_pre<1>(bits, 0u, ca, cb, cc, cd, L);
+    uint32_t acc = 0, first = LWSE_NONE;
+    if (pre.visit) group_visit_inline<1>(a, bits, 0u, pre, acc, first);
+    v[0] = group_finish(a, ca, cb, cc, cd, L, pre.oflags, acc, first);
   }
-  pdl_wait_prior();  // group_out may still be read by the previous sweep's LWS pass
-  if (valid) emit_if_changed<1>(a.changes, reinterpret_cast<uint4*>(a.out + g), g, v);
+  pdl_wait_prior();  // group_out / the flag column may still be read by the previous sweep's LWS pass
+  if (valid) {
+    emit_if_changed<1>(a.changes, reinterpret_cast<uint4*>(a.out + g), g, v);
+    a.gflag8[g] = (uint8_t)(v[0].x & kFlagByteMask);
+  }
 }
 
 // --------------------------------------------------------------------------
 // LWS-level pass
 // --------------------------------------------------------------------------
+// A tick's last kernel tells the host that the results are in (lwse_resident_tick): the last
+// CTA copies the change-list counters to mapped host memory and then raises the sequence
+// number the host spins on — no stream synchronize on the critical path.
+struct TickPublish {
+  uint32_t* host_words;      // mapped host memory: [0] lws changes, [1] group changes, [2] sequence; nullptr = off
+  uint32_t* device_counts;   // [0] lws, [1] groups (reset here for the next tick)
+  uint32_t* ticket;          // device: CTA completion counter
+  uint32_t seq;
+};
+
 struct LwsSweepArgs {
   const lwse_lws_rec* lws;
-  const lwse_group_out* gout;
+  const uint8_t* gflag8;  // one flag byte per group (written by the group pass)
   lwse_lws_out* out;
   uint32_t n_lws;
   uint32_t n_groups;
   uint32_t sweep_flags;
   ChangeList changes;
+  TickPublish publish;
 };
 
 __device__ __forceinline__ int32_t want_replicas(int32_t lws_replicas, int32_t surge, int32_t mu,
@@ -574,18 +717,33 @@ __device__ __forceinline__ int32_t want_replicas(int32_t lws_replicas, int32_t s
   return fin;
 }
 
+// Byte-lane masks of one 64-bit word of the flag column.  Byte b of word j is group slot
+// idx = off + b of the object (off = 8 j - group_base, negative in the object's first word).
+constexpr uint64_t kLaneOnes = 0x0101010101010101ull;
+__device__ __forceinline__ uint64_t lanes_upto(int64_t n) {  // bit 0 of bytes [0, n)
+  if (n <= 0) return 0ull;
+  if (n >= 8) return kLaneOnes;
+  return kLaneOnes & ((1ull << (8 * (int)n)) - 1ull);
+}
+__device__ __forceinline__ uint64_t lanes_idx_range(int32_t off, int32_t lo, int32_t hi) {  // lo <= idx < hi
+  return lanes_upto((int64_t)hi - off) & ~lanes_upto((int64_t)lo - off);
+}
+__device__ __forceinline__ int32_t highest_lane(uint64_t m) { return (63 - __clzll((long long)m)) >> 3; }  // m != 0
+
 template <int W>
 __global__ void __launch_bounds__(256) lws_sweep_kernel(const LwsSweepArgs a) {
   constexpr uint32_t kTilesPerBlock = 256 / W;
+  __shared__ uint32_t s_last;
   const uint32_t lane = threadIdx.x & (W - 1);
   const uint32_t n_tiles = gridDim.x * kTilesPerBlock;
+  const uint64_t* words = reinterpret_cast<const uint64_t*>(a.gflag8);
   pdl_launch_dependents();
   bool waited = false;
   for (uint32_t i = blockIdx.x * kTilesPerBlock + threadIdx.x / W; i < a.n_lws; i += n_tiles) {
     const uint4* row = reinterpret_cast<const uint4*>(a.lws + i);
     const uint4 r0 = ldg_stream(row + 0), r1 = ldg_stream(row + 1), r2 = ldg_stream(row + 2),
                 r3 = ldg_stream(row + 3);
-    if (!waited) {  // the object rows are input; the group pass's flag words come next
+    if (!waited) {  // the object rows are input; the group pass's flag bytes come next
       pdl_wait_prior();
       waited = true;
     }
@@ -603,13 +761,14 @@ __global__ void __launch_bounds__(256) lws_sweep_kernel(const LwsSweepArgs a) {
     if ((uint64_t)gbase + gc > a.n_groups) {
       oflags = LWSE_LOUT_BAD_TABLE;
     } else {
-      const lwse_group_out* go = a.gout + gbase;
       const bool sts_exists = lflags & LWSE_LWS_STS_EXISTS;
       const bool intstr_bad = lflags & LWSE_LWS_INTSTR_INVALID;
       int32_t mu = scaled_value((int32_t)r1.w, lflags & LWSE_LWS_UNAVAIL_IS_PERCENT, R, false);
       int32_t surge = scaled_value((int32_t)r1.z, lflags & LWSE_LWS_SURGE_IS_PERCENT, R, true);
       if (surge > R) surge = R;  // :307
       const int32_t burst = R + surge;
+      const int32_t gcs = (int32_t)min(gc, 0x7FFFFFFFu);
+      const uint32_t j0 = gbase >> 3, j1 = gc ? ((gbase + gc - 1u) >> 3) : j0;  // words of the object's flag bytes
 
       // ---- pass A: counters over every group slot of the object ----
       // updateConditions counters (:450-475) and, for slots below the leader
@@ -617,28 +776,27 @@ __global__ void __launch_bounds__(256) lws_sweep_kernel(const LwsSweepArgs a) {
       int32_t c_ready = 0, c_updated = 0, c_cur_nb = 0, c_upd_nb = 0, c_ready_nb = 0, c_upd_rdy = 0;
       int32_t c_ok_below_R = 0;  // slots < min(R, n) that are ready ∧ updated
       int32_t max_bad = -1;      // highest slot < n that is not (ready ∧ updated)
-      const int32_t n_live = min(n, (int32_t)min(gc, 0x7FFFFFFFu));
-      for (uint32_t idx = lane; idx < gc; idx += W) {
-        const uint32_t f = __ldg(&go[idx].flags);
-        const int32_t ix = (int32_t)idx;
-        const bool in_nb = ix < R && ix >= P;
-        if (f & LWSE_GOUT_COUNTED) {
-          const bool rd = f & LWSE_GOUT_COND_READY, up = f & LWSE_GOUT_COND_UPDATED;
-          c_ready += rd;
-          c_updated += up;
-          c_cur_nb += in_nb;
-          c_upd_nb += in_nb && up;
-          c_ready_nb += (ix < R) && rd;
-          c_upd_rdy += in_nb && rd && up;
-        }
-        if (ix < n_live) {
-          const bool ok = (f & (LWSE_GOUT_STATE_READY | LWSE_GOUT_STATE_UPDATED)) ==
-                          (LWSE_GOUT_STATE_READY | LWSE_GOUT_STATE_UPDATED);
-          if (ok && ix < R) c_ok_below_R++;
-          if (!ok) max_bad = ix;  // idx ascends per lane
+      const int32_t n_live = min(n, gcs);
+      if (gc) {
+        for (uint32_t j = j0 + lane; j <= j1; j += W) {
+          const uint64_t w = __ldcg(words + j);
+          const int32_t off = (int32_t)(j << 3) - (int32_t)gbase;  // |off| < 2^31: n_groups < 2^31 in practice
+          const uint64_t valid = lanes_idx_range(off, 0, gcs);
+          const uint64_t st_rd = w & kLaneOnes, st_up = (w >> 1) & kLaneOnes;
+          const uint64_t cnt = (w >> 2) & valid, rd = (w >> 3) & kLaneOnes, up = (w >> 4) & kLaneOnes;
+          const uint64_t in_R = lanes_idx_range(off, 0, R), in_nb = lanes_idx_range(off, P, R);
+          c_ready += __popcll(cnt & rd);
+          c_updated += __popcll(cnt & up);
+          c_cur_nb += __popcll(cnt & in_nb);
+          c_upd_nb += __popcll(cnt & in_nb & up);
+          c_ready_nb += __popcll(cnt & in_R & rd);
+          c_upd_rdy += __popcll(cnt & in_nb & rd & up);
+          const uint64_t live = valid & lanes_idx_range(off, 0, n_live), ok = st_rd & st_up;
+          c_ok_below_R += __popcll(ok & live & in_R);
+          const uint64_t badm = live & ~ok;
+          if (badm) max_bad = off + highest_lane(badm);  // j ascends per lane
         }
       }
-      // pack the six small counters pairwise to halve the reductions
       c_ready = tile_add<W>(c_ready);
       c_updated = tile_add<W>(c_updated);
       c_cur_nb = tile_add<W>(c_cur_nb);
@@ -699,8 +857,13 @@ __global__ void __launch_bounds__(256) lws_sweep_kernel(const LwsSweepArgs a) {
           // pass B: unavailable = #{idx < rsp : !ready}
           int32_t unavail = 0;
           const int32_t rsp_live = min(rsp, n_live);
-          for (int32_t idx = (int32_t)lane; idx < rsp_live; idx += W)
-            unavail += !(__ldg(&go[idx].flags) & LWSE_GOUT_STATE_READY);
+          if (rsp_live > 0) {
+            const uint32_t jb = (gbase + (uint32_t)rsp_live - 1u) >> 3;
+            for (uint32_t j = j0 + lane; j <= jb; j += W) {
+              const int32_t off = (int32_t)(j << 3) - (int32_t)gbase;
+              unavail += __popcll(~__ldcg(words + j) & lanes_idx_range(off, 0, rsp_live));
+            }
+          }
           unavail = tile_add<W>(unavail) + (rsp - rsp_live);
           int32_t part = rsp + unavail;
           const int32_t hi = min(part, n - 1);
@@ -708,9 +871,14 @@ __global__ void __launch_bounds__(256) lws_sweep_kernel(const LwsSweepArgs a) {
             // pass C: the walk stops at the highest idx in [rsp, hi] that is ready ∧ ¬updated
             int32_t blocker = -1;
             const int32_t hi_live = min(hi, n_live - 1);
-            for (int32_t idx = rsp + (int32_t)lane; idx <= hi_live; idx += W) {
-              const uint32_t f = __ldg(&go[idx].flags);
-              if ((f & LWSE_GOUT_STATE_READY) && !(f & LWSE_GOUT_STATE_UPDATED)) blocker = idx;
+            if (hi_live >= rsp) {
+              const uint32_t ja = (gbase + (uint32_t)rsp) >> 3, jb = (gbase + (uint32_t)hi_live) >> 3;
+              for (uint32_t j = ja + lane; j <= jb; j += W) {
+                const uint64_t w = __ldcg(words + j);
+                const int32_t off = (int32_t)(j << 3) - (int32_t)gbase;
+                const uint64_t m = w & ~(w >> 1) & lanes_idx_range(off, rsp, hi_live + 1);
+                if (m) blocker = off + highest_lane(m);
+              }
             }
             blocker = tile_max<W>(blocker);
             if (blocker < 0)
@@ -745,6 +913,25 @@ __global__ void __launch_bounds__(256) lws_sweep_kernel(const LwsSweepArgs a) {
       emit_if_changed<2>(a.changes, reinterpret_cast<uint4*>(a.out + i), i, v);
     }
   }
+  if (a.publish.host_words != nullptr) {
+    if (!waited) pdl_wait_prior();  // a CTA without rows still has to see the group pass's counter
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(a.publish.ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+      __threadfence();
+      const uint32_t nl = __ldcg(a.publish.device_counts + 0), ng = __ldcg(a.publish.device_counts + 1);
+      a.publish.device_counts[0] = 0u;  // ready for the next tick (stream-ordered)
+      a.publish.device_counts[1] = 0u;
+      *a.publish.ticket = 0u;
+      volatile uint32_t* hw = a.publish.host_words;
+      hw[0] = nl;
+      hw[1] = ng;
+      __threadfence_system();
+      hw[2] = a.publish.seq;
+    }
+  }
 }
 
 // --------------------------------------------------------------------------
@@ -757,13 +944,12 @@ static const bool g_pdl = [] {
 }();
 
 static int pick_tile(uint64_t items, uint64_t owners) {
-  // Lanes per object: every lane of a tile runs the object-level logic (the five cases, the walk)
-  // itself, so lanes only pay off when there are several group words per lane to read — next power
-  // of two >= (average groups per object) / kGroupsPerLane, in [1, 32].  One lane per group
-  // (divisor 1) made the C5 shape (16 groups per object) instruction-bound: 42 us for 100 k objects.
+  // Lanes per object: a lane handles 8 groups per 64-bit word, and every lane of a tile runs the
+  // object-level logic (the five cases, the walk) itself — one lane per object until objects
+  // average more than 64 groups, then next power of two >= avg / 64, in [1, 32].
   static const uint64_t div = [] {
     const char* v = getenv("LWSE_LWS_TILE_DIV");
-    const int d = v ? atoi(v) : 8;
+    const int d = v ? atoi(v) : 64;
     return (uint64_t)(d < 1 ? 1 : d);
   }();
   if (owners == 0) return 1;
@@ -803,32 +989,39 @@ static cudaError_t launch_lws(const LwsSweepArgs& a, int sm_count, cudaStream_t 
 
 constexpr int kScanUnroll = 4;  // 128-bit loads per lane per chunk: 4 x 512 B = 2 KB in flight per warp
 
-size_t lws_sweep_scratch_bytes(uint64_t n_pods) {
-  const uint64_t words = (n_pods + 31u) / 32u;
-  return (size_t)(2 * words * sizeof(uint32_t) + 256);
+// scratch: [pending bitmap | event bitmap | flag bytes (one per group, padded to 8)]
+static uint64_t bitmap_words(uint64_t n_pods) { return ((n_pods + 31u) / 32u + 31u) & ~(uint64_t)31u; }
+size_t lws_sweep_scratch_bytes(uint64_t n_pods, uint32_t n_groups) {
+  return (size_t)(2 * bitmap_words(n_pods) * sizeof(uint32_t) + (((uint64_t)n_groups + 7u) & ~7ull) + 256);
 }
 
 // Returns the number of kernels launched (>=0) or -1 with *cuda_err set.
-// scratch: lws_sweep_scratch_bytes(n_pods) bytes of device memory.
-struct SweepChangeLists {  // device pointers; all null = off
+// scratch: lws_sweep_scratch_bytes(n_pods, n_groups) bytes of device memory.
+struct SweepChangeLists {  // device (or mapped host) pointers; all null = off
   uint32_t* lws_rows = nullptr;
   lwse_lws_out* lws_out = nullptr;
   uint32_t lws_capacity = 0;
   uint32_t* group_rows = nullptr;
   lwse_group_out* group_out = nullptr;
   uint32_t group_capacity = 0;
-  uint32_t* counts = nullptr;  // [0] lws, [1] groups; zeroed by the caller
+  uint32_t* counts = nullptr;  // device: [0] lws, [1] groups, [2] ticket; zeroed by the caller
+  uint32_t* host_words = nullptr;  // mapped host: the LWS pass publishes the counts and `seq` there
+  uint32_t seq = 0;
 };
 
+// first_pdl: the sweep's first kernel may start before the previous kernel on the stream has
+// finished (it reads only input tables before its griddepcontrol.wait) — false when that previous
+// kernel WRITES the input tables (the patch scatter of a tick).
 int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
                      void* scratch, int sm_count, cudaStream_t s, int* cuda_err, const SweepChangeLists* cl,
-                     uint32_t* d_event_count) {
+                     uint32_t* d_event_count, bool first_pdl) {
   *cuda_err = 0;
   int launches = 0;
   cudaError_t e = cudaSuccess;
-  const uint64_t words = (t->n_pods + 31u) / 32u;
+  const uint64_t words = bitmap_words(t->n_pods);
   uint32_t* pending_bits = static_cast<uint32_t*>(scratch);
-  uint32_t* event_bits = pending_bits + ((words + 31u) & ~(uint64_t)31u);
+  uint32_t* event_bits = pending_bits + words;
+  uint8_t* gflag8 = reinterpret_cast<uint8_t*>(event_bits + words);
   const bool group_pass = t->n_groups && !(t->flags & LWSE_SWEEP_SKIP_GROUP_PASS);
 
   // lanes per group: one per bitmap word of an average group, in {1, 2, 4, 8}
@@ -839,42 +1032,44 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
     return v && atoi(v) != 0;
   }();
   // scan + group pass in one kernel: small groups (the pod window of 256 consecutive groups has to
-  // fit the CTA's bitmap window of 65 536 pods), no occupancy count, both passes wanted.
-  // (A variant that staged the window's state words in shared memory with one TMA bulk copy per CTA
-  // — 128 groups, 32 KB — and evaluated the predicates from there was slower: 11.7 us against 9.6 us;
-  // the register scan already keeps ~48 KB in flight per SM, and a single bulk copy per CTA does not.)
-  const bool fused = group_pass && avg_pods <= 256 && !t->node_occupancy && !no_fuse && !d_event_count &&
-                     !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN);
+  // fit the CTA's bitmap window of 65 536 pods), both passes wanted.
+  const bool fused = group_pass && avg_pods <= 256 && !no_fuse && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN);
+  if (t->node_occupancy && n_nodes && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN)) {
+    e = cudaMemsetAsync(t->node_occupancy, 0, (size_t)n_nodes * sizeof(uint32_t), s);
+    if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
+    if (t->n_pods) {
+      const uint64_t want = (t->n_pods + 255) / 256;
+      const uint32_t cap = (uint32_t)sm_count * 16u;
+      pod_occupancy_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(t->pod_ident, t->n_pods, t->node_occupancy, n_nodes);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
+      launches++;
+    }
+  }
   if (fused) {
     GroupSweepArgs a{t->lws,   t->groups, t->pod_state, t->pod_ident, nullptr, nullptr, d_nodes,
-                     t->group_out, t->n_pods, t->n_lws, t->n_groups, n_nodes, t->flags, ChangeList{}};
+                     t->group_out, gflag8, t->n_pods, t->n_lws, t->n_groups, n_nodes, t->flags, ChangeList{}, d_event_count};
     if (cl && cl->group_rows) a.changes = ChangeList{cl->group_rows, cl->group_out, cl->counts + 1, cl->group_capacity};
     const uint32_t grid = (t->n_groups + kFusedThreads - 1) / kFusedThreads;
-    e = launch_pdl(group_fused_kernel, dim3(grid), dim3(kFusedThreads), 0, s, g_pdl, a);
+    // (a memset / occupancy kernel right before: an ordinary launch orders behind it)
+    e = launch_pdl(group_fused_kernel, dim3(grid), dim3(kFusedThreads), 0, s, g_pdl && first_pdl && !t->node_occupancy, a);
     if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
     launches++;
   }
-  if (!fused && t->node_occupancy && n_nodes && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN)) {
-    e = cudaMemsetAsync(t->node_occupancy, 0, (size_t)n_nodes * sizeof(uint32_t), s);
-    if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
-  }
-  if (!fused && t->n_pods && (t->n_groups || t->node_occupancy) && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN)) {
-    PodScanArgs a{t->pod_state, pending_bits, event_bits, t->node_occupancy, t->n_pods, n_nodes, d_event_count};
+  if (!fused && t->n_pods && t->n_groups && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN)) {
+    PodScanArgs a{t->pod_state, pending_bits, event_bits, t->n_pods, d_event_count};
     // one chunk per warp: the kernel is a few microseconds long, so let the
     // hardware CTA scheduler balance it instead of a persistent grid-stride loop
-    const uint64_t chunks = (t->n_pods + 128ull * kScanUnroll - 1) / (128ull * kScanUnroll);
+    const uint64_t chunks = (t->n_pods + 512ull * kScanUnroll - 1) / (512ull * kScanUnroll);
     const uint64_t want = (chunks + 7) / 8;
     const uint32_t grid = (uint32_t)(want < (1u << 20) ? want : (1u << 20));
-    if (t->node_occupancy)
-      e = launch_pdl(pod_scan_kernel<kScanUnroll, true>, dim3(grid), dim3(256), 0, s, false, a);  // follows a memset
-    else
-      e = launch_pdl(pod_scan_kernel<kScanUnroll, false>, dim3(grid), dim3(256), 0, s, g_pdl, a);
+    e = launch_pdl(pod_scan_kernel<kScanUnroll>, dim3(grid), dim3(256), 0, s, g_pdl && first_pdl && !t->node_occupancy && !d_event_count, a);
     if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
     launches++;
   }
   if (group_pass && !fused) {
     GroupSweepArgs a{t->lws,   t->groups, t->pod_state, t->pod_ident, pending_bits, event_bits, d_nodes,
-                     t->group_out, t->n_pods, t->n_lws, t->n_groups, n_nodes, t->flags, ChangeList{}};
+                     t->group_out, gflag8, t->n_pods, t->n_lws, t->n_groups, n_nodes, t->flags, ChangeList{}, nullptr};
     if (cl && cl->group_rows) a.changes = ChangeList{cl->group_rows, cl->group_out, cl->counts + 1, cl->group_capacity};
     switch (w) {
       case 8: e = launch_group<8>(a, sm_count, s); break;
@@ -886,8 +1081,9 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
     launches++;
   }
   if (t->n_lws && !(t->flags & LWSE_SWEEP_SKIP_LWS_PASS)) {
-    LwsSweepArgs a{t->lws, t->group_out, t->lws_out, t->n_lws, t->n_groups, t->flags, ChangeList{}};
+    LwsSweepArgs a{t->lws, gflag8, t->lws_out, t->n_lws, t->n_groups, t->flags, ChangeList{}, TickPublish{}};
     if (cl && cl->lws_rows) a.changes = ChangeList{cl->lws_rows, cl->lws_out, cl->counts + 0, cl->lws_capacity};
+    if (cl && cl->host_words) a.publish = TickPublish{cl->host_words, cl->counts, cl->counts + 2, cl->seq};
     switch (pick_tile(t->n_groups, t->n_lws)) {
       case 1: e = launch_lws<1>(a, sm_count, s); break;
       case 2: e = launch_lws<2>(a, sm_count, s); break;
@@ -905,36 +1101,120 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
 // --------------------------------------------------------------------------
 // row patches for the resident tables
 // --------------------------------------------------------------------------
-template <int WORDS>  // 32-bit words per row
-__global__ void __launch_bounds__(256) scatter_rows_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ rows,
-                                                           const uint32_t* __restrict__ values, uint32_t n,
-                                                           uint64_t table_rows) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (uint64_t)n * WORDS) return;
-  const uint32_t k = (uint32_t)(i / WORDS), w = (uint32_t)(i % WORDS);
-  const uint32_t r = __ldg(rows + k);
-  if (r < table_rows) table[(uint64_t)r * WORDS + w] = __ldg(values + i);
+// One launch applies every scattered patch segment of a tick (lwse_resident_tick): row numbers
+// and packed values are read where the host wrote them (mapped pinned memory, or a staged device
+// copy).  Identity-row patches also move the pod's occupancy count from its old node to the new.
+struct ScatterSeg {
+  void* table;
+  const uint32_t* rows;
+  const void* values;
+  uint64_t table_rows;
+  uint32_t n;
+  uint32_t row_bytes;   // 1, 16 (identity), 32 (placement request), 64
+  uint32_t work_begin;  // first work item of this segment (16-byte pieces, or rows for 1-byte rows)
+  uint32_t is_ident;
+};
+constexpr int kMaxScatterSegs = 8;
+struct ScatterArgs {
+  ScatterSeg seg[kMaxScatterSegs];
+  uint32_t n_segs;
+  uint32_t total_work;
+  uint32_t* occupancy;  // nullable
+  uint32_t n_nodes;
+};
+
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const __grid_constant__ ScatterArgs a) {
+  pdl_launch_dependents();
+  pdl_wait_prior();  // the tables may still be read by the previous tick's kernels
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.total_work; i += gridDim.x * blockDim.x) {
+    int k = 0;
+#pragma unroll
+    for (int q = 1; q < kMaxScatterSegs; q++)
+      if (q < (int)a.n_segs && i >= a.seg[q].work_begin) k = q;
+    const ScatterSeg& sg = a.seg[k];
+    const uint32_t j = i - sg.work_begin;
+    if (sg.row_bytes == 1u) {
+      const uint32_t r = sg.rows[j];
+      if (r < sg.table_rows) static_cast<uint8_t*>(sg.table)[r] = static_cast<const uint8_t*>(sg.values)[j];
+    } else {
+      const uint32_t pieces = sg.row_bytes >> 4;
+      const uint32_t row_i = j / pieces, piece = j - row_i * pieces;
+      const uint32_t r = sg.rows[row_i];
+      if (r >= sg.table_rows) continue;
+      const uint4 v = static_cast<const uint4*>(sg.values)[j];
+      uint4* dst = static_cast<uint4*>(sg.table) + (uint64_t)r * pieces + piece;
+      if (sg.is_ident && a.occupancy != nullptr) {
+        const uint32_t old = dst->w;
+        if (old != v.w) {
+          if ((old & LWSE_PODID_SCHEDULED) && (old >> LWSE_PODID_NODE_SHIFT) < a.n_nodes)
+            atomicSub(a.occupancy + (old >> LWSE_PODID_NODE_SHIFT), 1u);
+          if ((v.w & LWSE_PODID_SCHEDULED) && (v.w >> LWSE_PODID_NODE_SHIFT) < a.n_nodes)
+            atomicAdd(a.occupancy + (v.w >> LWSE_PODID_NODE_SHIFT), 1u);
+        }
+      }
+      *dst = v;
+    }
+  }
 }
 
-int launch_scatter(int row_words, void* table, uint64_t table_rows, const uint32_t* rows, const void* values,
-                   uint32_t n, cudaStream_t s, int* cuda_err) {
+struct ScatterSegHost {
+  void* table;
+  uint64_t table_rows;
+  const uint32_t* rows;
+  const void* values;
+  uint32_t n;
+  uint32_t row_bytes;
+  bool is_ident;
+};
+
+int launch_scatter(const ScatterSegHost* segs, int n_segs, uint32_t* d_occupancy, uint32_t n_nodes, cudaStream_t s,
+                   bool pdl, int* cuda_err) {
   *cuda_err = 0;
-  if (n == 0) return 0;
-  const uint64_t threads = (uint64_t)n * (uint64_t)row_words;
-  const unsigned grid = (unsigned)((threads + 255) / 256);
-  uint32_t* tb = static_cast<uint32_t*>(table);
-  const uint32_t* v = static_cast<const uint32_t*>(values);
-  switch (row_words) {
-    case 16: scatter_rows_kernel<16><<<grid, 256, 0, s>>>(tb, rows, v, n, table_rows); break;
-    case 3: scatter_rows_kernel<3><<<grid, 256, 0, s>>>(tb, rows, v, n, table_rows); break;
-    case 1: scatter_rows_kernel<1><<<grid, 256, 0, s>>>(tb, rows, v, n, table_rows); break;
-    default: *cuda_err = (int)cudaErrorInvalidValue; return -1;
+  ScatterArgs a{};
+  uint64_t work = 0;
+  int k = 0;
+  for (int i = 0; i < n_segs; i++) {
+    if (segs[i].n == 0) continue;
+    if (k >= kMaxScatterSegs || (segs[i].row_bytes != 1u && (segs[i].row_bytes & 15u))) {
+      *cuda_err = (int)cudaErrorInvalidValue;
+      return -1;
+    }
+    a.seg[k] = ScatterSeg{segs[i].table, segs[i].rows, segs[i].values, segs[i].table_rows, segs[i].n,
+                          segs[i].row_bytes, (uint32_t)work, segs[i].is_ident ? 1u : 0u};
+    work += (uint64_t)segs[i].n * (segs[i].row_bytes == 1u ? 1u : segs[i].row_bytes >> 4);
+    k++;
   }
-  cudaError_t e = cudaGetLastError();
+  if (k == 0) return 0;
+  if (work > 0xFFFFFFFFull) {
+    *cuda_err = (int)cudaErrorInvalidValue;
+    return -1;
+  }
+  a.n_segs = (uint32_t)k;
+  a.total_work = (uint32_t)work;
+  a.occupancy = d_occupancy;
+  a.n_nodes = n_nodes;
+  uint64_t grid = (work + 255) / 256;
+  if (grid > 148ull * 16ull) grid = 148ull * 16ull;
+  const cudaError_t e = launch_pdl(scatter_rows_kernel, dim3((unsigned)grid), dim3(256), 0, s, pdl && g_pdl, a);
   if (e != cudaSuccess) {
     *cuda_err = (int)e;
     return -1;
   }
+  return 1;
+}
+
+// Scheduled pods per node of a resident identity column (at load).
+int launch_occupancy(const lwse_pod_ident* d_ident, uint64_t n_pods, uint32_t* d_occupancy, uint32_t n_nodes, int sm_count,
+                     cudaStream_t s, int* cuda_err) {
+  *cuda_err = 0;
+  cudaError_t e = cudaMemsetAsync(d_occupancy, 0, (size_t)n_nodes * 4, s);
+  if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
+  if (n_pods == 0) return 0;
+  const uint64_t want = (n_pods + 255) / 256;
+  const uint32_t cap = (uint32_t)sm_count * 16u;
+  pod_occupancy_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(d_ident, n_pods, d_occupancy, n_nodes);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
   return 1;
 }
 

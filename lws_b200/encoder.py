@@ -105,7 +105,7 @@ class LwsTables:
 
 def _state_column(pod_rows) -> np.ndarray:
     col = R.aligned_empty(len(pod_rows), R.POD_STATE)
-    col[:] = np.array([r[2] for r in pod_rows], dtype=np.uint32)
+    col[:] = np.array([r[2] for r in pod_rows], dtype=np.uint8)
     return col
 
 
@@ -293,20 +293,21 @@ def encode_lws(items: Iterable[LwsItem], cluster: Cluster, topology_key: Optiona
                         bits |= R.POD_OWNER_NAME_MATCH
                     elif kind == R.POD_OWNER_STS:
                         irregular = True  # would Get() a foreign StatefulSet
+                place = 0  # the cold word: name check + node binding
                 if p.labels.get(api.WorkerIndexLabelKey) == "0":
                     bits |= R.POD_IS_LEADER
-                    bits |= R.POD_NAME_OK
+                    place |= R.PODID_NAME_OK
                 else:
                     parent, ordinal = get_parent_name_and_ordinal(p.name)
                     if ordinal != -1:
-                        bits |= R.POD_NAME_OK
+                        place |= R.PODID_NAME_OK
                         if parent != nominated:
                             irregular = True  # leader lookup would hit another group
                 if p.nodeName != "" and p.nodeName in node_index:
                     ni = node_index[p.nodeName]
                     if ni <= R.POD_NODE_MAX:
-                        bits |= R.POD_SCHEDULED | (ni << R.POD_NODE_SHIFT)
-                pod_rows.append((R.hash64(p.labels.get(api.RevisionKey, "")), owner_uid, bits))
+                        place |= R.PODID_SCHEDULED | (ni << R.PODID_NODE_SHIFT)
+                pod_rows.append((R.hash64(p.labels.get(api.RevisionKey, "")), owner_uid, bits, place))
                 names.append(p.name)
             group_pod_names.append(names)
             group_rows.append(
@@ -341,7 +342,8 @@ def encode_lws(items: Iterable[LwsItem], cluster: Cluster, topology_key: Optiona
         groups=table(group_rows, R.GROUP_REC),
         pod_state=_state_column(pod_rows),
         pod_ident=R.pod_ident_table(
-            np.array([r[0] for r in pod_rows], dtype=np.uint64), np.array([r[1] for r in pod_rows], dtype=np.uint32)
+            np.array([r[0] for r in pod_rows], dtype=np.uint64), np.array([r[1] for r in pod_rows], dtype=np.uint32),
+            np.array([r[3] for r in pod_rows], dtype=np.uint32),
         ),
         nodes=node_rec,
         n_domains=len(domain_values),

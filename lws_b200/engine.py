@@ -34,6 +34,11 @@ SYMBOLS = {
     "lwse_resident_patch": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32], C.c_int),
     "lwse_resident_sweep": ([C.c_void_p, C.c_uint32, C.POINTER(R.Changes)], C.c_int),
     "lwse_resident_outputs": ([C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    "lwse_resident_arena": ([C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)], C.c_int),
+    "lwse_resident_place_load": ([C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32], C.c_int),
+    "lwse_resident_tick": ([C.c_void_p, C.POINTER(R.Tick)], C.c_int),
+    "lwse_resident_place_outputs": ([C.c_void_p, C.c_void_p], C.c_int),
+    "lwse_resident_occupancy": ([C.c_void_p, C.c_void_p], C.c_int),
     "lwse_place_host": (
         [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)],
         C.c_int,
@@ -242,13 +247,83 @@ class Engine:
     def resident_load(self, lws, groups, pod_state, pod_ident):
         """Make the four input tables resident on the device."""
         self._resident_shape = (len(lws), len(groups))
+        self._resident_pods = len(pod_state)
+        self._n_place = 0
         t = R.LwsTables(R.ptr(lws), len(lws), R.ptr(groups), len(groups), R.ptr(pod_state), R.ptr(pod_ident),
                         len(pod_state), None, None, None, 0)
         self._check(lib().lwse_resident_load(self._h, C.byref(t)))
         self._chg = None
 
     _DT = {R.TABLE_LWS: R.LWS_REC, R.TABLE_GROUPS: R.GROUP_REC, R.TABLE_POD_STATE: R.POD_STATE,
-           R.TABLE_POD_IDENT: R.POD_IDENT}
+           R.TABLE_POD_IDENT: R.POD_IDENT, R.TABLE_PLACE_REQS: R.PLACE_REQ}
+
+    # ----------------------------------------------------------- resident tick
+    def resident_arena(self, min_bytes: int = 0) -> np.ndarray:
+        """The engine's pinned, mapped patch arena as a uint8 array: patch rows / values written
+        into it are read by the GPU in place (no staging copy)."""
+        base, size = C.c_void_p(), C.c_uint64()
+        self._check(lib().lwse_resident_arena(self._h, min_bytes, C.byref(base), C.byref(size)))
+        buf = (C.c_uint8 * size.value).from_address(base.value)
+        return np.frombuffer(buf, dtype=np.uint8)
+
+    def resident_place_load(self, reqs: np.ndarray, n_namespaces: int = 1):
+        assert reqs.dtype == R.PLACE_REQ
+        self._n_place = len(reqs)
+        self._check(lib().lwse_resident_place_load(self._h, R.ptr(reqs) if len(reqs) else None, len(reqs), n_namespaces))
+
+    def make_tick(self, segments=(), flags=0) -> "R.Tick":
+        """Build a reusable ``lwse_tick`` descriptor.  ``segments``: (table, rows, values) with
+        numpy arrays (ideally views of the arena), or (table, first_row, values, True) for a range."""
+        segs = (R.PatchSeg * max(len(segments), 1))()
+        keep = []
+        for i, sg in enumerate(segments):
+            if len(sg) == 4 and sg[3]:
+                table, first, values = sg[0], sg[1], sg[2]
+                segs[i] = R.PatchSeg(table, R.PATCH_RANGE, len(values), int(first), None, R.ptr(values))
+                keep.append(values)
+            else:
+                table, rows, values = sg[0], sg[1], sg[2]
+                assert rows.dtype == np.uint32 and len(rows) == len(values) and values.dtype == self._DT[table]
+                segs[i] = R.PatchSeg(table, 0, len(rows), 0, R.ptr(rows) if len(rows) else None,
+                                     R.ptr(values) if len(rows) else None)
+                keep.append((rows, values))
+        t = R.Tick()
+        t.segs = segs
+        t.n_segs = len(segments)
+        t.flags = flags
+        t._keep = (segs, keep)
+        return t
+
+    def resident_tick(self, tick: "R.Tick"):
+        """One tick: patches in, changed result rows out (views of engine-owned pinned memory,
+        valid until the next resident call).  → dict of numpy views."""
+        self._check(lib().lwse_resident_tick(self._h, C.byref(tick)))
+
+        def view(ptr, n, dtype):
+            if not ptr or n == 0:
+                return np.zeros(0, dtype=dtype)
+            nbytes = n * np.dtype(dtype).itemsize
+            return np.frombuffer((C.c_uint8 * nbytes).from_address(ptr), dtype=dtype)
+
+        n_lws = min(tick.n_lws, self._resident_shape[0])
+        n_grp = min(tick.n_groups, self._resident_shape[1])
+        n_pl = min(tick.n_place, getattr(self, "_n_place", 0))
+        return {
+            "lws_rows": view(tick.lws_rows, n_lws, np.uint32), "lws_out": view(tick.lws_out, n_lws, R.LWS_OUT),
+            "group_rows": view(tick.group_rows, n_grp, np.uint32), "group_out": view(tick.group_out, n_grp, R.GROUP_OUT),
+            "place_rows": view(tick.place_rows, n_pl, np.uint32), "place_out": view(tick.place_out, n_pl, R.PLACE_OUT),
+            "n_lws": tick.n_lws, "n_groups": tick.n_groups, "n_place": tick.n_place, "rounds": tick.place_rounds,
+        }
+
+    def resident_place_outputs(self) -> np.ndarray:
+        out = R.aligned_empty(self._n_place, R.PLACE_OUT)
+        self._check(lib().lwse_resident_place_outputs(self._h, R.ptr(out)))
+        return out
+
+    def resident_occupancy(self) -> np.ndarray:
+        occ = np.zeros(max(self.n_nodes, 1), dtype=np.uint32)
+        self._check(lib().lwse_resident_occupancy(self._h, R.ptr(occ)))
+        return occ[: self.n_nodes]
 
     def resident_patch(self, which: int, rows, values):
         """Overwrite rows of a resident table (rows: uint32 indices, values: packed rows)."""

@@ -11,7 +11,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NONE = 0xFFFFFFFF
 NODE_NOT_FOUND = 0xFFFFFFFE
 
@@ -91,18 +91,18 @@ GRP_WSTS_OWNER_NAME_MATCH = 1 << 9
 GRP_MISTAKEN_ANNOTATION = 1 << 10
 GRP_REVISION_EXISTS = 1 << 11
 
-POD_STATE = np.dtype("<u4")  # lwse_pod_state
-POD_IDENT = np.dtype([("rev_hash_lo", "<u4"), ("rev_hash_hi", "<u4"), ("owner_uid_hash", "<u4")], align=False)
-assert POD_IDENT.itemsize == 12
+POD_STATE = np.dtype("u1")  # lwse_pod_state: the hot byte column
+POD_IDENT = np.dtype([("rev_hash", "<u8"), ("owner_uid_hash", "<u4"), ("place", "<u4")], align=False)
+assert POD_IDENT.itemsize == 16
 
 
-def pod_ident_table(rev_hash: np.ndarray, owner_uid_hash: np.ndarray) -> np.ndarray:
-    """Build the identity column from 64-bit revision hashes and 32-bit owner uid hashes."""
+def pod_ident_table(rev_hash: np.ndarray, owner_uid_hash: np.ndarray, place: np.ndarray | int = 0) -> np.ndarray:
+    """Build the identity column from 64-bit revision hashes, 32-bit owner uid hashes and the
+    ``place`` words (PODID_NAME_OK | PODID_SCHEDULED | node << PODID_NODE_SHIFT)."""
     t = aligned_empty(len(rev_hash), POD_IDENT)
-    rev = np.asarray(rev_hash, dtype=np.uint64)
-    t["rev_hash_lo"] = (rev & np.uint64(0xFFFFFFFF)).astype(np.uint32)
-    t["rev_hash_hi"] = (rev >> np.uint64(32)).astype(np.uint32)
+    t["rev_hash"] = np.asarray(rev_hash, dtype=np.uint64)
     t["owner_uid_hash"] = owner_uid_hash
+    t["place"] = place
     return t
 
 
@@ -116,10 +116,19 @@ POD_OWNER_MASK = 3 << 4
 POD_OWNER_NONE, POD_OWNER_POD, POD_OWNER_STS, POD_OWNER_OTHER = 0, 1, 2, 3
 POD_OWNER_NAME_MATCH = 1 << 6
 POD_IS_LEADER = 1 << 7
-POD_NAME_OK = 1 << 8
-POD_SCHEDULED = 1 << 9
-POD_NODE_SHIFT = 10
+PODID_NAME_OK = 1 << 0
+PODID_SCHEDULED = 1 << 1
+PODID_NODE_SHIFT = 10
 POD_NODE_MAX = (1 << 22) - 1
+
+
+def occupancy_of(pod_ident: np.ndarray, n_nodes: int) -> np.ndarray:
+    """Scheduled pods per node of an identity column (what the engine counts at load)."""
+    place = pod_ident["place"]
+    sched = (place & PODID_SCHEDULED) != 0
+    node = (place[sched] >> PODID_NODE_SHIFT).astype(np.int64)
+    return np.bincount(node[node < n_nodes], minlength=n_nodes).astype(np.uint32)
+
 
 NODE_REC = np.dtype(
     [("topo_value_hash", "<u8"), ("domain_id", "<u4"), ("capacity", "<u2"), ("flags", "<u2")],
@@ -301,7 +310,40 @@ class Changes(C.Structure):
     ]
 
 
-TABLE_LWS, TABLE_GROUPS, TABLE_POD_STATE, TABLE_POD_IDENT = 0, 1, 2, 3
+TABLE_LWS, TABLE_GROUPS, TABLE_POD_STATE, TABLE_POD_IDENT, TABLE_PLACE_REQS = 0, 1, 2, 3, 4
+PATCH_RANGE = 1 << 0
+TICK_MAX_SEGS = 8
+TICK_PLACE = 1 << 8
+TICK_NO_SWEEP = 1 << 9
+
+
+class PatchSeg(C.Structure):
+    _fields_ = [
+        ("table", C.c_uint32),
+        ("flags", C.c_uint32),
+        ("n", C.c_uint32),
+        ("first_row", C.c_uint32),
+        ("rows", C.c_void_p),
+        ("values", C.c_void_p),
+    ]
+
+
+class Tick(C.Structure):
+    _fields_ = [
+        ("segs", C.POINTER(PatchSeg)),
+        ("n_segs", C.c_uint32),
+        ("flags", C.c_uint32),
+        ("lws_rows", C.c_void_p),
+        ("lws_out", C.c_void_p),
+        ("n_lws", C.c_uint32),
+        ("n_groups", C.c_uint32),
+        ("group_rows", C.c_void_p),
+        ("group_out", C.c_void_p),
+        ("place_rows", C.c_void_p),
+        ("place_out", C.c_void_p),
+        ("n_place", C.c_uint32),
+        ("place_rounds", C.c_uint32),
+    ]
 
 
 class DsTables(C.Structure):

@@ -49,6 +49,8 @@ class Profile:
     restart_policy_p: tuple = (0.1, 0.7, 0.2)  # None / OnPodRestart / AfterStart
     p_leader_ready_policy: float = 0.1
     fuzz: float = 0.0  # probability of flipping "can't happen" bits (parity fuzzing)
+    n_namespaces: int = 1  # objects are dealt to namespaces round-robin (exclusivity is per namespace)
+    conflict_free: bool = False  # scheduled leaders of one namespace sit in distinct domains
     gang: bool = True
     extra: dict = field(default_factory=dict)
 
@@ -62,8 +64,19 @@ def profile(name: str, scale: float = 1.0) -> Profile:
     if name == "C2":  # 10k LWS x size 8, 1k nodes, placement off
         return Profile("C2", s(10_000), size_choices=(8,), replicas_choices=(1, 2, 4, 8), n_nodes=1000,
                        f_mid_update=0.10)
-    if name == "C3":  # 100k LWS x size 64, 10k nodes, topology-aware gang placement on
+    if name == "C3":
+        # 100k LWS x size 64, 10k nodes, topology-aware gang placement ON for every group: every object
+        # carries the exclusive-topology annotation.  One domain holds one group per namespace, so the
+        # objects live in enough namespaces to fit (200 x 625 domains >= 100k groups); scheduled leaders
+        # of a namespace sit in distinct domains (what a scheduler honouring the constraint leaves
+        # behind), 5 % of the leaders are not scheduled yet and compete for the free domains.
+        # BASELINE's counts put ~600 pods on a node: capacity 650.
         return Profile("C3", s(100_000), size_choices=(64,), replicas_choices=(1,), n_nodes=10_000,
+                       nodes_per_domain=16, node_capacity=650, p_exclusive=1.0, f_mid_update=0.10,
+                       n_namespaces=max(1, int(round(200 * min(scale, 1.0)))) if scale < 1.0 else 200,
+                       conflict_free=True)
+    if name == "C3-steady":  # round 1's placement load: 1 % of the objects exclusive, one namespace
+        return Profile("C3-steady", s(100_000), size_choices=(64,), replicas_choices=(1,), n_nodes=10_000,
                        nodes_per_domain=16, node_capacity=650, p_exclusive=0.01, f_mid_update=0.10)
     if name == "C5":  # 100k LWS rolling update maxSurge=10% + restart sweep
         return Profile("C5", s(100_000), size_choices=(8,), replicas_choices=(16,), n_nodes=10_000,
@@ -93,6 +106,13 @@ class Tables:
     nodes: np.ndarray
     n_domains: int
     flags: int
+    ns_of_lws: np.ndarray = None  # dense namespace id per object
+    n_namespaces: int = 1
+
+    def place_requests(self) -> np.ndarray:
+        from . import encoder
+
+        return encoder.encode_place_requests(self.lws, self.groups, self.ns_of_lws)
 
     def algorithmic_bytes(self) -> int:
         """Compulsory HBM traffic of one sweep: every input row read once, every
@@ -126,6 +146,7 @@ class Tables:
             "pods": int(len(self.pod_state)),
             "nodes": int(len(self.nodes)),
             "domains": int(self.n_domains),
+            "namespaces": int(self.n_namespaces),
             "size": list(p.size_choices),
             "replicas": list(p.replicas_choices),
             "seed": hex(SEED),
@@ -266,6 +287,20 @@ def make(name_or_profile, scale: float = 1.0, seed: int = SEED) -> Tables:
     g["wsts_owner_uid_hash"] = np.where(stale_owner, _u32(rng, G), g["leader_uid_hash"])
     sched = rng.random(G) >= p.p_leader_unscheduled
     node = rng.integers(0, max(p.n_nodes, 1), size=G).astype(np.uint32)
+    ns_of_lws = (np.arange(n, dtype=np.int64) % max(p.n_namespaces, 1)).astype(np.uint32)
+    if p.conflict_free and n_domains:
+        # the k-th group of a namespace takes the k-th domain of that namespace's own permutation
+        # (groups beyond the number of domains stay unscheduled), a random node inside it
+        g_ns = ns_of_lws[owner].astype(np.int64)
+        order = np.argsort(g_ns, kind="stable")
+        first = np.searchsorted(g_ns[order], np.arange(max(p.n_namespaces, 1)))
+        rank = np.empty(G, dtype=np.int64)
+        rank[order] = np.arange(G) - first[g_ns[order]]
+        perm = np.argsort(rng.random((max(p.n_namespaces, 1), n_domains)), axis=1)
+        dom = perm[g_ns, np.minimum(rank, n_domains - 1)]
+        sched &= rank < n_domains
+        node = np.minimum(dom * p.nodes_per_domain + rng.integers(0, max(p.nodes_per_domain, 1), size=G),
+                          max(p.n_nodes - 1, 0)).astype(np.uint32)
     leader_node = np.where(sched, node, np.uint32(R.NONE)).astype(np.uint32)
     if p.fuzz:
         leader_node = np.where(rng.random(G) < p.fuzz / 2, np.uint32(R.NODE_NOT_FOUND), leader_node)
@@ -325,7 +360,6 @@ def make(name_or_profile, scale: float = 1.0, seed: int = SEED) -> Tables:
         kind[k_other] = R.POD_OWNER_OTHER
     stale = rng.random(Pn) < (0.01 + p.fuzz)
     owner_uid = np.where(stale, _u32(rng, Pn), owner_uid)
-    pod_ident = R.pod_ident_table(pod_rev, owner_uid)
     phase = np.full(Pn, R.POD_PHASE_RUNNING, dtype=np.uint32)
     phase[rng.random(Pn) < p.p_pending] = R.POD_PHASE_PENDING
     if p.fuzz:
@@ -339,7 +373,7 @@ def make(name_or_profile, scale: float = 1.0, seed: int = SEED) -> Tables:
     name_match = rng.random(Pn) > p.fuzz
     bits |= np.where(name_match, R.POD_OWNER_NAME_MATCH, 0).astype(np.uint32)
     bits |= np.where(is_leader, R.POD_IS_LEADER, 0).astype(np.uint32)
-    bits |= np.where(rng.random(Pn) > p.fuzz / 2, R.POD_NAME_OK, 0).astype(np.uint32)
+    place = np.where(rng.random(Pn) > p.fuzz / 2, R.PODID_NAME_OK, 0).astype(np.uint32)
     # placement: pods of a group sit in the leader's domain, spread over its nodes
     gl = g["leader_node"][pg]
     g_sched = (gl != R.NONE) & (gl != R.NODE_NOT_FOUND)
@@ -347,12 +381,13 @@ def make(name_or_profile, scale: float = 1.0, seed: int = SEED) -> Tables:
     pnode = np.minimum(dom_first + (within % max(p.nodes_per_domain, 1)).astype(np.uint32),
                        np.uint32(max(p.n_nodes - 1, 0)))
     p_sched = g_sched & (rng.random(Pn) > p.p_pending)
-    bits |= np.where(p_sched, np.uint32(R.POD_SCHEDULED) | (pnode << np.uint32(R.POD_NODE_SHIFT)), 0).astype(np.uint32)
+    place |= np.where(p_sched, np.uint32(R.PODID_SCHEDULED) | (pnode << np.uint32(R.PODID_NODE_SHIFT)), 0).astype(np.uint32)
+    pod_ident = R.pod_ident_table(pod_rev, owner_uid, place)
     pod_state = R.aligned_empty(Pn, R.POD_STATE)
-    pod_state[:] = bits
+    pod_state[:] = bits.astype(np.uint8)
 
     return Tables(profile=p, lws=lws, groups=g, pod_state=pod_state, pod_ident=pod_ident, nodes=nodes, n_domains=n_domains,
-                  flags=R.SWEEP_GANG if p.gang else 0)
+                  flags=R.SWEEP_GANG if p.gang else 0, ns_of_lws=ns_of_lws, n_namespaces=max(p.n_namespaces, 1))
 
 
 def _norm(ps):

@@ -19,11 +19,26 @@ SubdomainUniquePerReplica = "UniquePerReplica"  # :263
 SubGroupPolicyTypeLeaderExcluded = "LeaderExcluded"  # :241
 
 
+def _go_div(a: int, b: int) -> int:
+    """Go's integer division: truncates toward zero (Python's // floors)."""
+    q = abs(a) // abs(b)
+    return q if (a < 0) == (b < 0) else -q
+
+
+def _go_mod(a: int, b: int) -> int:
+    return a - b * _go_div(a, b)
+
+
 def get_sub_group_index(pod_count: int, sub_group_size: int, worker_index: int) -> str:
-    """pod_webhook.go:249-255 (Go integer division truncates toward zero; all operands are >= 0 here)."""
-    if (pod_count - 1) % sub_group_size == 0:
-        return str((worker_index - 1) // sub_group_size if worker_index >= 1 else 0)
-    return str(worker_index // sub_group_size)
+    """pod_webhook.go:249-255 with Go's truncating division: worker 0 under the "leader is extra"
+    rule gives (0 - 1) / sg = 0 for sg > 1 but -1 for sg == 1, exactly as the Go expression does.
+    sub_group_size == 0 is a division by zero in Go (a panic the caller turns into a per-pod
+    error): ZeroDivisionError here."""
+    if sub_group_size == 0:
+        raise ZeroDivisionError("subGroupSize is 0")
+    if _go_mod(pod_count - 1, sub_group_size) == 0:
+        return str(_go_div(worker_index - 1, sub_group_size))
+    return str(_go_div(worker_index, sub_group_size))
 
 
 def default_labels_batch(pods: Sequence[api.Pod], sha1_batch: Callable[[list], "np.ndarray"]) -> list[Optional[str]]:
@@ -70,6 +85,9 @@ def default_labels_batch(pods: Sequence[api.Pod], sha1_batch: Callable[[list], "
                     errors[i] = f'strconv.Atoi: parsing "{sub_size}": invalid syntax'
                     continue
                 leader_name = pod.annotations.get(api.LeaderPodNameAnnotationKey, "")
+                if sub_size_int == 0:  # Go panics (integer divide by zero): one pod's admission fails, not the batch
+                    errors[i] = "runtime error: integer divide by zero"
+                    continue
                 idx = get_sub_group_index(pod_count, sub_size_int, worker_index)
                 pod.labels[api.SubGroupIndexLabelKey] = idx
                 want.append((i, api.SubGroupUniqueHashLabelKey, f"{leader_name}/{idx}"))

@@ -58,6 +58,17 @@ _OPTIONAL = [
         [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p],
         C.c_int,
     ),
+    (
+        "lwso_place_mt",
+        [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int],
+        C.c_int,
+    ),
+    ("lwso_apply_patch", [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32], None),
+    (
+        "lwso_sweep_dirty",
+        [C.POINTER(R.LwsTables), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int],
+        C.c_int,
+    ),
     ("lwso_sweep_ds", [C.POINTER(R.DsTables)], C.c_int),
     ("lwso_sha1", [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p], C.c_int),
     (
@@ -91,6 +102,25 @@ def sweep_lws(lws, groups, pod_state, pod_ident, nodes=None, flags=0, want_occup
     if rc != 0:
         raise RuntimeError(f"lwso_sweep_lws failed: {rc}")
     return lws_out, group_out, (occ[:n_nodes] if occ is not None else None)
+
+
+def apply_patch(table: np.ndarray, rows: np.ndarray, values: np.ndarray) -> None:
+    """table[rows] = values, in C (the CPU arm of a churn step applies its events the same way)."""
+    assert table.dtype == values.dtype and rows.dtype == np.uint32 and len(rows) == len(values)
+    lib().lwso_apply_patch(R.ptr(table), table.dtype.itemsize, len(table), R.ptr(rows), R.ptr(values), len(rows))
+
+
+def sweep_dirty(lws, groups, pod_state, pod_ident, nodes, lws_out, group_out, dirty_groups, dirty_lws, flags=0, threads=1):
+    """Reconcile only the listed group / object rows (results written in place)."""
+    n_nodes = 0 if nodes is None else len(nodes)
+    dg = np.ascontiguousarray(dirty_groups, dtype=np.uint32)
+    dl = np.ascontiguousarray(dirty_lws, dtype=np.uint32)
+    t = R.LwsTables(R.ptr(lws), len(lws), R.ptr(groups), len(groups), R.ptr(pod_state), R.ptr(pod_ident), len(pod_state),
+                    R.ptr(lws_out), R.ptr(group_out), None, flags)
+    rc = lib().lwso_sweep_dirty(C.byref(t), R.ptr(nodes) if n_nodes else None, n_nodes, R.ptr(dg), len(dg), R.ptr(dl), len(dl),
+                                threads)
+    if rc != 0:
+        raise RuntimeError(f"lwso_sweep_dirty failed: {rc}")
 
 
 def sweep_ds(ds, roles, revroles):
@@ -172,12 +202,13 @@ def ds_scale_down_old(replicas, order, current, target):
     return reps.reshape(len(order), n).tolist()
 
 
-def place(nodes, occupancy, n_domains, n_namespaces, reqs):
-    """Sequential statement of the placement spec (parity unpinned, build-defined)."""
+def place(nodes, occupancy, n_domains, n_namespaces, reqs, threads=1):
+    """Sequential statement of the placement spec (parity unpinned, build-defined); ``threads`` > 1
+    solves the (independent) namespaces side by side — same rows."""
     out = R.aligned_empty(len(reqs), R.PLACE_OUT)
     occ = None if occupancy is None else np.ascontiguousarray(occupancy, dtype=np.uint32)
-    rc = lib().lwso_place(R.ptr(nodes), len(nodes), R.ptr(occ), n_domains, n_namespaces, R.ptr(reqs), len(reqs),
-                          R.ptr(out))
+    rc = lib().lwso_place_mt(R.ptr(nodes), len(nodes), R.ptr(occ), n_domains, n_namespaces, R.ptr(reqs), len(reqs),
+                             R.ptr(out), threads)
     if rc != 0:
         raise RuntimeError(f"lwso_place failed: {rc}")
     return out

@@ -321,7 +321,8 @@ static int update_conditions(const lwse_lws_rec* l, const lwse_group_rec* groups
 typedef struct {
   uint64_t rev_hash;
   uint32_t owner_uid_hash;
-  uint32_t bits;
+  uint32_t bits;  /* the state byte */
+  uint32_t place; /* the identity row's cold word: name check, node binding */
 } pod_view;
 
 typedef struct {
@@ -331,9 +332,10 @@ typedef struct {
 
 static pod_view get_pod(const pod_cols* c, uint64_t i) {
   pod_view p;
-  p.rev_hash = (uint64_t)c->ident[i].rev_hash_lo | ((uint64_t)c->ident[i].rev_hash_hi << 32);
+  p.rev_hash = c->ident[i].rev_hash;
   p.owner_uid_hash = c->ident[i].owner_uid_hash;
   p.bits = c->state[i];
+  p.place = c->ident[i].place;
   return p;
 }
 
@@ -383,7 +385,7 @@ static int handle_restart_policy(const lwse_lws_rec* l, const lwse_group_rec* g,
   if (pending && (policy == LWSE_RESTART_AFTER_START || has_annot)) return 0;
   int leader_deleting;
   if (!(p->bits & LWSE_POD_IS_LEADER)) {
-    if (!(p->bits & LWSE_POD_NAME_OK)) return -1; /* :230-232 */
+    if (!(p->place & LWSE_PODID_NAME_OK)) return -1; /* :230-232 */
     /* :233-237 Get(leader by parsed name) */
     if (!((g->flags & LWSE_GRP_POD_PRESENT) && (g->flags & LWSE_GRP_POD_NAME_MATCH))) return 0;
     if (g->leader_rev_hash != p->rev_hash) return 0; /* :239 */
@@ -565,13 +567,70 @@ LWSO_API int lwso_sweep_lws(const lwse_lws_tables* t, const lwse_node_rec* nodes
     /* scheduled pods per node, over the whole pod table */
     memset(t->node_occupancy, 0, sizeof(uint32_t) * (size_t)n_nodes);
     for (uint64_t p = 0; p < t->n_pods; p++) {
-      uint32_t b = t->pod_state[p];
-      if (b & LWSE_POD_SCHEDULED) {
-        uint32_t node = b >> LWSE_POD_NODE_SHIFT;
+      uint32_t b = t->pod_ident[p].place;
+      if (b & LWSE_PODID_SCHEDULED) {
+        uint32_t node = b >> LWSE_PODID_NODE_SHIFT;
         if (node < n_nodes) t->node_occupancy[node]++;
       }
     }
   }
+  return LWSE_OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* event-driven form (bench.py's churn workloads)                            */
+/* ------------------------------------------------------------------------- */
+/* A controller does not sweep: watch events enqueue the objects they touch and Reconcile()
+ * runs for those (leaderworkerset_controller.go:106, pod_controller.go:69).  The CPU arm of a
+ * churn step therefore (1) applies the step's row patches to its host tables and (2) reconciles
+ * exactly the dirty groups / objects, whose row numbers the event source hands it. */
+LWSO_API void lwso_apply_patch(void* table, uint32_t row_bytes, uint64_t table_rows, const uint32_t* rows,
+                               const void* values, uint32_t n) {
+  uint8_t* t = (uint8_t*)table;
+  const uint8_t* v = (const uint8_t*)values;
+  for (uint32_t i = 0; i < n; i++)
+    if (rows[i] < table_rows) memcpy(t + (size_t)rows[i] * row_bytes, v + (size_t)i * row_bytes, row_bytes);
+}
+
+typedef struct {
+  const lwse_lws_tables* t;
+  const lwse_node_rec* nodes;
+  uint32_t n_nodes;
+  const uint32_t *dg, *dl;
+  uint32_t dg_begin, dg_end, dl_begin, dl_end;
+} dirty_job;
+
+static void* dirty_range(void* arg) {
+  dirty_job* j = (dirty_job*)arg;
+  for (uint32_t k = j->dl_begin; k < j->dl_end; k++)
+    if (j->dl[k] < j->t->n_lws) sweep_one_lws(j->t, j->dl[k]);
+  for (uint32_t k = j->dg_begin; k < j->dg_end; k++)
+    if (j->dg[k] < j->t->n_groups) sweep_one_group(j->t, j->nodes, j->n_nodes, j->dg[k]);
+  return NULL;
+}
+
+LWSO_API int lwso_sweep_dirty(const lwse_lws_tables* t, const lwse_node_rec* nodes, uint32_t n_nodes,
+                              const uint32_t* dirty_groups, uint32_t n_dg, const uint32_t* dirty_lws,
+                              uint32_t n_dl, int threads) {
+  if (!t) return LWSE_ERR_INVALID_ARG;
+  if (threads < 1) threads = 1;
+  if (threads > 256) threads = 256;
+  if (threads == 1 || (uint64_t)n_dg + n_dl < (uint64_t)threads * 4u) {
+    dirty_job j = {t, nodes, n_nodes, dirty_groups, dirty_lws, 0, n_dg, 0, n_dl};
+    dirty_range(&j);
+    return LWSE_OK;
+  }
+  pthread_t tid[256];
+  dirty_job jobs[256];
+  for (int k = 0; k < threads; k++) {
+    jobs[k] = (dirty_job){t, nodes, n_nodes, dirty_groups, dirty_lws,
+                          (uint32_t)((uint64_t)n_dg * (uint64_t)k / (uint64_t)threads),
+                          (uint32_t)((uint64_t)n_dg * (uint64_t)(k + 1) / (uint64_t)threads),
+                          (uint32_t)((uint64_t)n_dl * (uint64_t)k / (uint64_t)threads),
+                          (uint32_t)((uint64_t)n_dl * (uint64_t)(k + 1) / (uint64_t)threads)};
+    pthread_create(&tid[k], NULL, dirty_range, &jobs[k]);
+  }
+  for (int k = 0; k < threads; k++) pthread_join(tid[k], NULL);
   return LWSE_OK;
 }
 

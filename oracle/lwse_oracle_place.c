@@ -35,6 +35,7 @@
  *                and then holds (ns, d); score = hi.  No feasible domain → UNSCHEDULABLE.
  *                (size ≥ 1, so a feasible domain always has a node with a free slot.)
  */
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -67,43 +68,32 @@ static int cmp_order(const void* a, const void* b) {
   return x < y ? -1 : x > y ? 1 : 0;
 }
 
-LWSO_API int lwso_place(const lwse_node_rec* nodes, uint32_t n_nodes, const uint32_t* occupancy,
-                        uint32_t n_domains, uint32_t n_namespaces, const lwse_place_req* reqs,
-                        uint32_t n_reqs, lwse_place_out* out) {
-  if (n_reqs > 0xFFFFFFu) return LWSE_ERR_UNSUPPORTED;
-  uint32_t* free_ = (uint32_t*)calloc(n_nodes ? n_nodes : 1, sizeof(uint32_t));
-  uint32_t* dom_free = (uint32_t*)calloc(n_domains ? n_domains : 1, sizeof(uint32_t));
-  uint64_t* holder = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(n_namespaces * (uint64_t)n_domains + 1));
-  order_ent* order = (order_ent*)malloc(sizeof(order_ent) * (n_reqs ? n_reqs : 1));
-  memset(holder, 0xFF, sizeof(uint64_t) * (size_t)(n_namespaces * (uint64_t)n_domains + 1));
-  for (uint32_t n = 0; n < n_nodes; n++) {
-    const lwse_node_rec* nd = &nodes[n];
-    uint32_t occ = occupancy ? occupancy[n] : 0;
-    int usable = (nd->flags & LWSE_NODE_SCHEDULABLE) && (nd->flags & LWSE_NODE_HAS_TOPOLOGY) &&
-                 nd->domain_id < n_domains;
-    free_[n] = usable && nd->capacity > occ ? nd->capacity - occ : 0;
-    if (usable) dom_free[nd->domain_id] += free_[n];
-  }
-  /* classify, default outputs */
-  for (uint32_t i = 0; i < n_reqs; i++) {
-    const lwse_place_req* r = &reqs[i];
-    int pinned = r->leader_node != LWSE_NONE;
-    order[i].key = lwso_place_key(r, i, pinned);
-    order[i].idx = i;
-    out[i].domain_id = LWSE_NONE;
-    out[i].leader_node = pinned ? r->leader_node : LWSE_NONE;
-    out[i].flags = pinned ? LWSE_PLACE_PINNED : 0;
-    out[i].score = 0;
-  }
-  qsort(order, n_reqs, sizeof(order_ent), cmp_order);
-  for (uint32_t k = 0; k < n_reqs; k++) {
-    uint32_t i = order[k].idx;
-    const lwse_place_req* r = &reqs[i];
-    if (r->ns >= n_namespaces) {
-      out[i].flags |= LWSE_PLACE_UNSCHEDULABLE;
-      continue;
-    }
-    uint64_t* hold = holder + (size_t)r->ns * n_domains;
+/* Exclusivity is per namespace and capacity is a snapshot (no claim consumes it), so the
+ * namespaces are independent sub-problems: solving them one after the other in ascending key
+ * order (threads = 1) or side by side on several host threads gives the same rows. */
+typedef struct {
+  const lwse_node_rec* nodes;
+  const uint32_t* free_;
+  const uint32_t* dom_free;
+  uint32_t n_nodes, n_domains;
+  const lwse_place_req* reqs;
+  lwse_place_out* out;
+  const uint32_t* dom_first; /* usable nodes grouped by domain: dom_nodes[dom_first[d] .. dom_first[d+1]) */
+  const uint32_t* dom_nodes; /* ascending node index inside a domain */
+  const order_ent* items;    /* requests bucketed by namespace, ascending key inside a bucket */
+  const uint32_t* ns_first;  /* n_namespaces + 1 */
+  uint32_t n_namespaces;
+  int thread, threads;
+} place_job;
+
+static void solve_namespace(const place_job* j, uint32_t ns, uint64_t* hold) {
+  const uint32_t n_domains = j->n_domains, n_nodes = j->n_nodes;
+  const lwse_node_rec* nodes = j->nodes;
+  lwse_place_out* out = j->out;
+  memset(hold, 0xFF, sizeof(uint64_t) * ((size_t)n_domains + 1));
+  for (uint32_t k = j->ns_first[ns]; k < j->ns_first[ns + 1]; k++) {
+    const uint32_t i = j->items[k].idx;
+    const lwse_place_req* r = &j->reqs[i];
     if (r->leader_node != LWSE_NONE) {
       /* pinned: the leader's node decides */
       if (r->leader_node >= n_nodes) continue; /* node object missing: no claim */
@@ -111,7 +101,7 @@ LWSO_API int lwso_place(const lwse_node_rec* nodes, uint32_t n_nodes, const uint
       if (!(nd->flags & LWSE_NODE_HAS_TOPOLOGY) || nd->domain_id >= n_domains) continue;
       out[i].domain_id = nd->domain_id;
       if (hold[nd->domain_id] == ~0ull) {
-        hold[nd->domain_id] = order[k].key;
+        hold[nd->domain_id] = j->items[k].key;
         out[i].flags |= LWSE_PLACE_PLACED;
       } else {
         out[i].flags |= LWSE_PLACE_CONFLICT;
@@ -126,7 +116,7 @@ LWSO_API int lwso_place(const lwse_node_rec* nodes, uint32_t n_nodes, const uint
     /* level 1: the domain */
     uint32_t best_hi = 0, d = LWSE_NONE;
     for (uint32_t c = 0; c < n_domains; c++) {
-      if (hold[c] != ~0ull || dom_free[c] < (uint32_t)r->size) continue;
+      if (hold[c] != ~0ull || j->dom_free[c] < (uint32_t)r->size) continue;
       uint32_t hi = mix32(key_lo ^ (c * 0x9E3779B1u)) | 1u;
       if (hi > best_hi) { /* ties keep the lower domain index */
         best_hi = hi;
@@ -139,9 +129,10 @@ LWSO_API int lwso_place(const lwse_node_rec* nodes, uint32_t n_nodes, const uint
     }
     /* level 2: the node in it */
     uint32_t best_lo = 0, best_n = LWSE_NONE;
-    for (uint32_t n = 0; n < n_nodes; n++) {
-      if (free_[n] < 1 || nodes[n].domain_id != d) continue; /* free_ > 0 implies usable */
-      uint32_t lo = ((free_[n] > 15 ? 15u : free_[n]) << 28) | (mix32(key_hi ^ (n * 0x85EBCA77u)) >> 4);
+    for (uint32_t q = j->dom_first[d]; q < j->dom_first[d + 1]; q++) { /* the nodes of domain d, ascending */
+      const uint32_t n = j->dom_nodes[q];
+      if (j->free_[n] < 1) continue;
+      uint32_t lo = ((j->free_[n] > 15 ? 15u : j->free_[n]) << 28) | (mix32(key_hi ^ (n * 0x85EBCA77u)) >> 4);
       if (lo > best_lo) { /* ties keep the lower node index */
         best_lo = lo;
         best_n = n;
@@ -151,15 +142,107 @@ LWSO_API int lwso_place(const lwse_node_rec* nodes, uint32_t n_nodes, const uint
       out[i].flags |= LWSE_PLACE_UNSCHEDULABLE;
       continue;
     }
-    hold[d] = order[k].key;
+    hold[d] = j->items[k].key;
     out[i].domain_id = d;
     out[i].leader_node = best_n;
     out[i].flags |= LWSE_PLACE_PLACED;
     out[i].score = best_hi;
   }
+}
+
+static void* place_worker(void* arg) {
+  const place_job* j = (const place_job*)arg;
+  uint64_t* hold = (uint64_t*)malloc(sizeof(uint64_t) * ((size_t)j->n_domains + 1));
+  for (uint32_t ns = (uint32_t)j->thread; ns < j->n_namespaces; ns += (uint32_t)j->threads)
+    if (j->ns_first[ns + 1] > j->ns_first[ns]) solve_namespace(j, ns, hold);
+  free(hold);
+  return NULL;
+}
+
+LWSO_API int lwso_place_mt(const lwse_node_rec* nodes, uint32_t n_nodes, const uint32_t* occupancy,
+                           uint32_t n_domains, uint32_t n_namespaces, const lwse_place_req* reqs,
+                           uint32_t n_reqs, lwse_place_out* out, int threads) {
+  if (n_reqs > 0xFFFFFFu) return LWSE_ERR_UNSUPPORTED;
+  if (threads < 1) threads = 1;
+  if (threads > 256) threads = 256;
+  uint32_t* free_ = (uint32_t*)calloc(n_nodes ? n_nodes : 1, sizeof(uint32_t));
+  uint32_t* dom_free = (uint32_t*)calloc(n_domains ? n_domains : 1, sizeof(uint32_t));
+  order_ent* order = (order_ent*)malloc(sizeof(order_ent) * (n_reqs ? n_reqs : 1));
+  order_ent* items = (order_ent*)malloc(sizeof(order_ent) * (n_reqs ? n_reqs : 1));
+  uint32_t* ns_first = (uint32_t*)calloc((size_t)n_namespaces + 2, sizeof(uint32_t));
+  uint32_t* dom_first = (uint32_t*)calloc((size_t)n_domains + 2, sizeof(uint32_t));
+  uint32_t* dom_nodes = (uint32_t*)malloc(sizeof(uint32_t) * (n_nodes ? n_nodes : 1));
+  for (uint32_t n = 0; n < n_nodes; n++) {
+    const lwse_node_rec* nd = &nodes[n];
+    uint32_t occ = occupancy ? occupancy[n] : 0;
+    int usable = (nd->flags & LWSE_NODE_SCHEDULABLE) && (nd->flags & LWSE_NODE_HAS_TOPOLOGY) &&
+                 nd->domain_id < n_domains;
+    free_[n] = usable && nd->capacity > occ ? nd->capacity - occ : 0;
+    if (usable) {
+      dom_free[nd->domain_id] += free_[n];
+      dom_first[nd->domain_id + 1]++;
+    }
+  }
+  for (uint32_t d = 0; d < n_domains; d++) dom_first[d + 1] += dom_first[d];
+  {
+    uint32_t* cur = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)n_domains + 1));
+    memcpy(cur, dom_first, sizeof(uint32_t) * ((size_t)n_domains + 1));
+    for (uint32_t n = 0; n < n_nodes; n++) {
+      const lwse_node_rec* nd = &nodes[n];
+      if ((nd->flags & LWSE_NODE_SCHEDULABLE) && (nd->flags & LWSE_NODE_HAS_TOPOLOGY) && nd->domain_id < n_domains)
+        dom_nodes[cur[nd->domain_id]++] = n;
+    }
+    free(cur);
+  }
+  /* classify, default outputs */
+  for (uint32_t i = 0; i < n_reqs; i++) {
+    const lwse_place_req* r = &reqs[i];
+    int pinned = r->leader_node != LWSE_NONE;
+    order[i].key = lwso_place_key(r, i, pinned);
+    order[i].idx = i;
+    out[i].domain_id = LWSE_NONE;
+    out[i].leader_node = pinned ? r->leader_node : LWSE_NONE;
+    out[i].flags = pinned ? LWSE_PLACE_PINNED : 0;
+    out[i].score = 0;
+    if (r->ns >= n_namespaces)
+      out[i].flags |= LWSE_PLACE_UNSCHEDULABLE;
+    else
+      ns_first[r->ns + 1]++;
+  }
+  qsort(order, n_reqs, sizeof(order_ent), cmp_order);
+  for (uint32_t ns = 0; ns < n_namespaces; ns++) ns_first[ns + 1] += ns_first[ns];
+  {
+    uint32_t* cursor = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)n_namespaces + 1));
+    memcpy(cursor, ns_first, sizeof(uint32_t) * ((size_t)n_namespaces + 1));
+    for (uint32_t k = 0; k < n_reqs; k++) { /* ascending key order is kept inside every bucket */
+      const uint32_t ns = reqs[order[k].idx].ns;
+      if (ns < n_namespaces) items[cursor[ns]++] = order[k];
+    }
+    free(cursor);
+  }
+  place_job jobs[256];
+  pthread_t tid[256];
+  for (int k = 0; k < threads; k++)
+    jobs[k] = (place_job){nodes, free_, dom_free, n_nodes, n_domains, reqs, out, dom_first, dom_nodes, items, ns_first,
+                          n_namespaces, k, threads};
+  if (threads == 1) {
+    place_worker(&jobs[0]);
+  } else {
+    for (int k = 0; k < threads; k++) pthread_create(&tid[k], NULL, place_worker, &jobs[k]);
+    for (int k = 0; k < threads; k++) pthread_join(tid[k], NULL);
+  }
   free(free_);
   free(dom_free);
-  free(holder);
+  free(dom_first);
+  free(dom_nodes);
   free(order);
+  free(items);
+  free(ns_first);
   return LWSE_OK;
+}
+
+LWSO_API int lwso_place(const lwse_node_rec* nodes, uint32_t n_nodes, const uint32_t* occupancy,
+                        uint32_t n_domains, uint32_t n_namespaces, const lwse_place_req* reqs,
+                        uint32_t n_reqs, lwse_place_out* out) {
+  return lwso_place_mt(nodes, n_nodes, occupancy, n_domains, n_namespaces, reqs, n_reqs, out, 1);
 }

@@ -8,8 +8,7 @@ from lws_b200.engine import Engine
 
 t = synth.make("C3", float(os.environ.get("SCALE", "1.0")))
 reqs = encoder.encode_place_requests(t.lws, t.groups)
-sched = (t.pod_state & R.POD_SCHEDULED) != 0
-occ = np.bincount((t.pod_state[sched] >> R.POD_NODE_SHIFT).astype(np.int64), minlength=len(t.nodes)).astype(np.uint32)
+occ = R.occupancy_of(t.pod_ident, len(t.nodes))
 e = Engine(0)
 e.upload_nodes(t.nodes, t.n_domains)
 dev = torch.device("cuda:0")

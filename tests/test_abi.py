@@ -62,7 +62,11 @@ def test_record_sizes_match_header():
         for f in dt.names:
             lines.append(f'printf("{s}.{f} %zu\\n", offsetof({s}, {f}));')
     lines += ['printf("lwse_lws_tables %zu\\n", sizeof(lwse_lws_tables));',
-              'printf("lwse_ds_tables %zu\\n", sizeof(lwse_ds_tables));', "return 0;}"]
+              'printf("lwse_ds_tables %zu\\n", sizeof(lwse_ds_tables));',
+              'printf("lwse_patch_seg %zu\\n", sizeof(lwse_patch_seg));',
+              'printf("lwse_tick %zu\\n", sizeof(lwse_tick));',
+              'printf("lwse_tick.place_rounds %zu\\n", offsetof(lwse_tick, place_rounds));',
+              'printf("lwse_pod_state %zu\\n", sizeof(lwse_pod_state));', "return 0;}"]
     with tempfile.TemporaryDirectory() as d:
         src, exe = os.path.join(d, "p.c"), os.path.join(d, "p")
         open(src, "w").write("\n".join(lines))
@@ -75,6 +79,10 @@ def test_record_sizes_match_header():
             assert int(got[f"{s}.{f}"]) == dt.fields[f][1], f"{s}.{f}"
     assert int(got["lwse_lws_tables"]) == C.sizeof(R.LwsTables)
     assert int(got["lwse_ds_tables"]) == C.sizeof(R.DsTables)
+    assert int(got["lwse_patch_seg"]) == C.sizeof(R.PatchSeg)
+    assert int(got["lwse_tick"]) == C.sizeof(R.Tick)
+    assert int(got["lwse_tick.place_rounds"]) == R.Tick.place_rounds.offset
+    assert int(got["lwse_pod_state"]) == R.POD_STATE.itemsize == 1
 
 
 def test_create_without_gpu_fails_loudly(lib):

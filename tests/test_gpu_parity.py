@@ -70,9 +70,34 @@ def test_every_lws_tile_width(engine, replicas):
     run_both(engine, synth.make(p, seed=7))
 
 
-@pytest.mark.parametrize("name,scale", [("C1", 1.0), ("C2", 1.0), ("C3", 0.1), ("C5", 0.05)])
+@pytest.mark.parametrize("name,scale", [("C1", 1.0), ("C2", 1.0), ("C3", 0.1), ("C5", 0.05), ("C3-steady", 0.1)])
 def test_baseline_configs(engine, name, scale):
     run_both(engine, synth.make(name, scale))
+
+
+@pytest.mark.parametrize("name", ["C3", "C5"])
+def test_baseline_configs_full_size(engine, name):
+    """BASELINE.json's configs at scale 1.0 (100k objects; 6.3M / 12.8M pod rows): every output
+    row of the fused sweep — and, for C3, of the placement round over its 98k requests in 200
+    namespaces — against the oracle (which sweeps them on the host threads in well under a second)."""
+    import os
+
+    import oracle
+
+    t = synth.make(name, 1.0)
+    threads = min(len(os.sched_getaffinity(0)), 32)
+    engine.upload_nodes(t.nodes, t.n_domains)
+    want = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, flags=t.flags, threads=threads)
+    got = engine.sweep_lws_host(t.lws, t.groups, t.pod_state, t.pod_ident, flags=t.flags)
+    assert_same(got[0], want[0], "lws_out")
+    assert_same(got[1], want[1], "group_out")
+    reqs = t.place_requests()
+    if len(reqs):
+        occ = R.occupancy_of(t.pod_ident, len(t.nodes))
+        want_p = oracle.place(t.nodes, occ, t.n_domains, t.n_namespaces, reqs, threads=threads)
+        got_p, rounds = engine.place_host(reqs, occ, t.n_namespaces)
+        assert_same(got_p, want_p, "place_out")
+        assert rounds >= 1
 
 
 def test_empty_tables(engine):
@@ -183,7 +208,7 @@ def test_reuse_pod_ident_flag(engine):
     # pod status changes (restarts appear), identities stay
     rng = np.random.default_rng(5)
     flip = rng.random(len(t.pod_state)) < 0.1
-    t.pod_state[flip] |= R.POD_ANY_RESTART
+    t.pod_state[flip] |= np.uint8(R.POD_ANY_RESTART)
     garbage = R.aligned_empty(len(t.pod_ident), R.POD_IDENT)  # must NOT be read
     want = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, flags=t.flags)
     got = engine.sweep_lws_host(t.lws, t.groups, t.pod_state, garbage, flags=t.flags | R.SWEEP_REUSE_POD_IDENT)
@@ -220,7 +245,7 @@ def test_resident_tables_patches_and_change_lists(engine):
     # watch events: some pods restart / go pending, some groups lose readiness, some objects move their partition
     rng = np.random.default_rng(9)
     prow = np.unique(rng.integers(0, len(t.pod_state), size=len(t.pod_state) // 50)).astype(np.uint32)
-    t.pod_state[prow] ^= np.where(rng.random(len(prow)) < 0.5, R.POD_ANY_RESTART, R.POD_PHASE_PENDING | R.POD_PHASE_RUNNING).astype(np.uint32)
+    t.pod_state[prow] ^= np.where(rng.random(len(prow)) < 0.5, R.POD_ANY_RESTART, R.POD_PHASE_PENDING | R.POD_PHASE_RUNNING).astype(np.uint8)
     grow = np.unique(rng.integers(0, len(t.groups), size=len(t.groups) // 100)).astype(np.uint32)
     t.groups["flags"][grow] ^= R.GRP_POD_READY
     lrow = np.unique(rng.integers(0, len(t.lws), size=len(t.lws) // 100)).astype(np.uint32)
@@ -305,7 +330,9 @@ def test_host_entry_reads_pinned_identity_rows_in_place(engine, p_event):
     lws, grp, pst, pid = pinned(t.lws), pinned(t.groups), pinned(t.pod_state), pinned(t.pod_ident)
     engine.upload_nodes(t.nodes, t.n_domains)
     want = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, flags=t.flags, want_occupancy=True)
-    for occupancy in (True, False):
+    # (True: the occupancy count reads the whole identity column → uploaded; False: first call
+    # optimistic zero-copy, second call decided by the event count the first one measured)
+    for occupancy in (True, False, False):
         got = engine.sweep_lws_host(lws, grp, pst, pid, flags=t.flags, want_occupancy=occupancy)
         assert_same(got[0], want[0], "lws_out")
         assert_same(got[1], want[1], "group_out")

@@ -1,0 +1,136 @@
+"""The resident tick (lwse_resident_tick) on the GPU: watch-event patches in, changed result
+rows out — every tick's full outputs and change lists against the oracle run on host mirrors."""
+import numpy as np
+import pytest
+
+from lws_b200 import churn
+from lws_b200 import records as R
+from lws_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from lws_b200.engine import Engine
+
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _rows_differ(a, b):
+    return np.flatnonzero(np.any(a.view(np.uint8).reshape(len(a), -1) != b.view(np.uint8).reshape(len(b), -1), axis=1))
+
+
+def _check_changes(res, prefix, before, after):
+    want = _rows_differ(before, after)
+    rows, outs = res[f"{prefix}_rows"], res[f"{prefix}_out"]
+    assert res[f"n_{'groups' if prefix == 'group' else prefix}"] == len(want), prefix
+    o = np.argsort(rows)
+    assert np.array_equal(rows[o], want), prefix
+    assert outs[o].tobytes() == after[want].tobytes(), prefix
+
+
+@pytest.mark.parametrize("in_arena", [True, False])
+def test_ticks_match_the_oracle(engine, in_arena):
+    import oracle
+
+    p = synth.profile("fuzz", 0.5)
+    p.n_namespaces = 3
+    t = synth.make(p, seed=41)
+    reqs = t.place_requests()
+    assert len(reqs) > 100
+    engine.upload_nodes(t.nodes, t.n_domains)
+    engine.resident_load(t.lws, t.groups, t.pod_state, t.pod_ident)
+    engine.resident_place_load(reqs, t.n_namespaces)
+    occ = R.occupancy_of(t.pod_ident, len(t.nodes))
+    assert np.array_equal(engine.resident_occupancy(), occ)
+    flags = t.flags | R.TICK_PLACE
+    m_pst, m_grp, m_req = t.pod_state.copy(), t.groups.copy(), reqs.copy()
+
+    def oracle_now():
+        lo, go, _ = oracle.sweep_lws(t.lws, m_grp, m_pst, t.pod_ident, t.nodes, flags=t.flags)
+        return lo, go, oracle.place(t.nodes, occ, t.n_domains, t.n_namespaces, m_req)
+
+    prev = oracle_now()
+    first = engine.resident_tick(engine.make_tick((), flags))
+    assert first["n_lws"] == len(t.lws) and first["n_groups"] == len(t.groups) and first["n_place"] == len(reqs)
+    assert engine.resident_place_outputs().tobytes() == prev[2].tobytes()
+    again = engine.resident_tick(engine.make_tick((), flags))
+    assert (again["n_lws"], again["n_groups"], again["n_place"]) == (0, 0, 0)
+
+    plan = churn.make_plan(t, reqs, prev[2], 0.03, 0.05, n_sets=6, seed=5)
+    if in_arena:
+        ticks = churn.ArenaPlan(engine, plan, flags).ticks
+    else:  # caller-owned pageable buffers: the call stages them
+        ticks = []
+        for ps in plan:
+            segs = [(R.TABLE_POD_STATE, ps.pod_rows, ps.pod_vals)]
+            if len(ps.grp_rows):
+                segs.append((R.TABLE_GROUPS, ps.grp_rows, ps.grp_vals))
+            if len(ps.req_rows):
+                segs.append((R.TABLE_PLACE_REQS, ps.req_rows, ps.req_vals))
+            ticks.append(engine.make_tick(segs, flags))
+    for k in range(9):
+        ps = plan[k % len(plan)]
+        churn.apply_to_mirror(ps, m_pst, m_grp, m_req)
+        now = oracle_now()
+        res = engine.resident_tick(ticks[k % len(plan)])
+        g_lo, g_go = engine.resident_outputs()
+        assert g_lo.tobytes() == now[0].tobytes() and g_go.tobytes() == now[1].tobytes(), f"tick {k}"
+        assert engine.resident_place_outputs().tobytes() == now[2].tobytes(), f"tick {k} placement"
+        _check_changes(res, "lws", prev[0], now[0])
+        _check_changes(res, "group", prev[1], now[1])
+        _check_changes(res, "place", prev[2], now[2])
+        assert res["rounds"] >= 1
+        prev = now
+
+
+def test_range_patch_and_identity_patches_keep_the_occupancy(engine):
+    import oracle
+
+    t = synth.make("fuzz", 0.3, seed=43)
+    engine.upload_nodes(t.nodes, t.n_domains)
+    engine.resident_load(t.lws, t.groups, t.pod_state, t.pod_ident)
+    engine.resident_tick(engine.make_tick((), t.flags))
+    rng = np.random.default_rng(3)
+    m_pst, m_pid = t.pod_state.copy(), t.pod_ident.copy()
+    # (1) a whole-column range patch of the state bytes
+    new = R.aligned_empty(len(m_pst), R.POD_STATE)
+    new[:] = m_pst ^ np.where(rng.random(len(m_pst)) < 0.3, R.POD_ANY_RESTART, 0).astype(np.uint8)
+    m_pst[:] = new
+    engine.resident_tick(engine.make_tick([(R.TABLE_POD_STATE, 0, new, True)], t.flags))
+    # (2) pods move: scattered identity-row patches move their occupancy count with them
+    rows = np.unique(rng.integers(0, len(m_pid), size=len(m_pid) // 20)).astype(np.uint32)
+    vals = R.aligned_empty(len(rows), R.POD_IDENT)
+    vals[:] = m_pid[rows]
+    node = rng.integers(0, len(t.nodes), size=len(rows)).astype(np.uint32)
+    vals["place"] = np.where(rng.random(len(rows)) < 0.8, R.PODID_SCHEDULED | R.PODID_NAME_OK | (node << R.PODID_NODE_SHIFT),
+                             R.PODID_NAME_OK).astype(np.uint32)
+    vals["owner_uid_hash"] ^= (rng.random(len(rows)) < 0.1).astype(np.uint32)
+    m_pid[rows] = vals
+    engine.resident_tick(engine.make_tick([(R.TABLE_POD_IDENT, rows, vals)], t.flags))
+    lo, go, occ = oracle.sweep_lws(t.lws, t.groups, m_pst, m_pid, t.nodes, flags=t.flags, want_occupancy=True)
+    g_lo, g_go = engine.resident_outputs()
+    assert g_lo.tobytes() == lo.tobytes() and g_go.tobytes() == go.tobytes()
+    assert np.array_equal(engine.resident_occupancy(), occ)
+    # (3) a range patch of the identity column: the engine recounts
+    first = len(m_pid) // 3
+    seg = R.aligned_empty(len(m_pid) - first, R.POD_IDENT)
+    seg[:] = m_pid[first:]
+    seg["place"] &= ~np.uint32(R.PODID_SCHEDULED)
+    m_pid[first:] = seg
+    engine.resident_tick(engine.make_tick([(R.TABLE_POD_IDENT, first, seg, True)], t.flags))
+    assert np.array_equal(engine.resident_occupancy(), R.occupancy_of(m_pid, len(t.nodes)))
+
+
+def test_ds_sweep_c4_full_size(engine):
+    """BASELINE.json configs[3]: 50k two-role DisaggregatedSets, every output against the oracle."""
+    import oracle
+
+    d = synth.make_ds(50_000, (2,))
+    got = engine.sweep_ds_host(d.ds, d.roles, d.revroles)
+    want = oracle.sweep_ds(d.ds, d.roles, d.revroles)
+    for a, b, name in zip(got, want, ("ds_out", "role_out", "revrole_out")):
+        assert a.tobytes() == b.tobytes(), name
