@@ -463,6 +463,9 @@ def run_ours(args):
     n_req = len(reqs)
     place_on = n_req > 0
     occ_host = R.occupancy_of(t.pod_ident, n_nodes)
+    # the encoder lays the requests out grouped by namespace: the engine then gives every namespace its own CTA
+    grouped = n_req > 0 and bool(np.all(np.diff(reqs["ns"].astype(np.int64)) >= 0))
+    place_flags = R.SWEEP_PLACE_GROUPED if (grouped and world == 1) else 0
 
     # ---- resident copies, rotated so that the working set exceeds L2 ----
     copies = max(2, int(np.ceil(2.5 * L2_BYTES / algo_bytes)) + 1)  # bytes a sweep touches x copies > 2.5 x L2
@@ -616,7 +619,7 @@ def run_ours(args):
     GROUP_ONLY = R.SWEEP_SKIP_POD_SCAN | R.SWEEP_SKIP_LWS_PASS
     LWS_ONLY = R.SWEEP_SKIP_POD_SCAN | R.SWEEP_SKIP_GROUP_PASS
     W = max(args.warmup, 3)
-    full_step = lambda i: step(i, t.flags)  # noqa: E731
+    full_step = lambda i: step(i, t.flags | place_flags)  # noqa: E731
     count_launches(full_step)
     with ClockSampler(local_rank) as clk:
         ms_step, launches = timed(full_step, args.steps, W)
@@ -636,12 +639,34 @@ def run_ours(args):
         i = 0
         for _ in range(n_load):
             for _ in range(100):
-                step(i, t.flags)
+                step(i, t.flags | place_flags)
                 i += 1
             torch.cuda.synchronize()
+        # the placement round alone, in each of its forms (same rows; checked against the oracle below)
+        forms = {}
+        if place_on and world == 1:
+            d_pout2 = torch.empty_like(d_pout)
+
+            def form_fn(kind):
+                if kind == "general":
+                    return lambda i: eng.place_device(d_reqs, n_req, d_occ, n_ns, d_pout2, stream=sptr)
+                fl = R.SWEEP_PLACE_SCAN if kind == "scan" else 0
+                return lambda i: eng.place_grouped_device(d_reqs, n_req, d_occ, n_ns, d_pout2, flags=fl, stream=sptr)
+
+            for kind in (("general", "grouped", "scan") if grouped else ("general",)):
+                ms_k, _ = timed(form_fn(kind), max(10, args.steps // 2), 3)
+                forms[kind] = {"ms": ms_k}
+                if kind != "general":
+                    r_k, scans = eng.place_grouped_device(d_reqs, n_req, d_occ, n_ns, d_pout2, stream=sptr, want_rounds=True,
+                                                          flags=R.SWEEP_PLACE_SCAN if kind == "scan" else 0)
+                    forms[kind].update({"rounds": int(r_k), "request_scans": int(scans)})
     clocks = clk.summary()
     torch.cuda.synchronize()
-    rounds = eng.place_device(d_reqs, n_req, d_occ, n_ns, d_pout, stream=pptr, want_rounds=True) if (place_on and world == 1) else None
+    if place_on and world == 1:
+        rounds = (eng.place_grouped_device(d_reqs, n_req, d_occ, n_ns, d_pout, stream=pptr, want_rounds=True)[0] if grouped
+                  else eng.place_device(d_reqs, n_req, d_occ, n_ns, d_pout, stream=pptr, want_rounds=True))
+    else:
+        rounds = None
     torch.cuda.synchronize()
 
     # ---- outputs of the device-resident tick against the oracle (outside the timed region) ----
@@ -651,7 +676,7 @@ def run_ours(args):
 
         want_lo, want_go, _ = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, flags=t.flags,
                                                threads=min(host_threads(), 32))
-        step(0, t.flags)
+        step(0, t.flags | place_flags)
         torch.cuda.synchronize()
         ok = (sets[0]["lo"].cpu().numpy().tobytes() == want_lo.tobytes()
               and sets[0]["go"].cpu().numpy().tobytes() == want_go.tobytes())
@@ -660,6 +685,12 @@ def run_ours(args):
             if world == 1:
                 want_po = oracle.place(t.nodes, occ_host, t.n_domains, n_ns, reqs, threads=min(host_threads(), 32))
                 place_ok = d_pout.cpu().numpy()[: n_req * R.PLACE_OUT.itemsize].tobytes() == want_po.tobytes()
+                for kind in forms:  # every form of the round gives the same rows
+                    form_fn(kind)(0)
+                    torch.cuda.synchronize()
+                    forms[kind]["equals_spec_oracle"] = bool(
+                        d_pout2.cpu().numpy()[: n_req * R.PLACE_OUT.itemsize].tobytes() == want_po.tobytes())
+                    place_ok = place_ok and forms[kind]["equals_spec_oracle"]
             else:  # the gathered problem: every rank's part, unpacked the way the kernel sees it
                 from lws_b200 import distributed as D
 
@@ -816,12 +847,15 @@ def run_ours(args):
         cpu_rate, cpu_s, cpu_reps = cpu_oracle_rate(t, 1)
         tick = e2e_variants["churn_1pct"]
         pair_evals = None
-        if place_on and world == 1 and rounds:
+        if place_on and world == 1 and "scan" in forms:
             unp = int((reqs["leader_node"] == R.NONE).sum())
-            pair_evals = {"unpinned_requests": unp, "domains": int(t.n_domains), "nodes": n_nodes, "rounds": int(rounds),
-                          "request_x_domain_evals_per_s": unp * t.n_domains / (ms_place * 1e-3) if ms_place else None,
-                          "note": "level 1 scores (request x domain) once per request (a displaced request scans again); "
-                                  "see the scan form for (request x node) pair-evals/s"}
+            sc = forms["scan"]
+            pairs = sc["request_scans"] * n_nodes
+            pair_evals = {"form": "scan (lwse_place_grouped_device, LWSE_SWEEP_PLACE_SCAN): every (request, node) pair scored "
+                                  "from the TMA-staged node table", "unpinned_requests": unp, "nodes": n_nodes,
+                          "request_scans": sc["request_scans"], "pairs_per_call": int(pairs), "ms_per_call": sc["ms"],
+                          "pair_evals_per_s": pairs / (sc["ms"] * 1e-3),
+                          "note": "ms includes the condense kernel and the 93k pinned claims of the same call"}
         line = {
             "metric": METRIC, "value": total_groups / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms_step,
@@ -829,7 +863,8 @@ def run_ours(args):
             "dtype": "u8/int32/u64 (integer compare)", "data": "synthetic",
             "config": {**t.describe(), "parallelism": f"shard-by-uid x{world} ({args.scaling})",
                        "placement": {"requests_per_rank": int(n_req), "unpinned": int((reqs['leader_node'] == R.NONE).sum()) if n_req else 0,
-                                     "namespaces": int(n_ns), "rounds": rounds, "pair_evals": pair_evals,
+                                     "namespaces": int(n_ns), "rounds": rounds, "grouped_by_namespace": bool(grouped),
+                                     "forms": forms, "pair_evals": pair_evals,
                                      "collective": ("none: parts pushed to the peers with NVLink peer stores + flags (lwse_exchange_*)"
                                                     if peer else "1 NCCL all_gather/step") if (world > 1 and place_on) else "none"},
                        "launch": ("CUDA graph replay") if use_graph else "eager launches, programmatic dependent launch",

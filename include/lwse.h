@@ -300,6 +300,12 @@ typedef struct lwse_lws_tables {
                                                 (revision hash, owner uid — fixed at pod creation)
                                                 is unchanged since this engine's previous host
                                                 sweep with the same n_pods; skip its upload     */
+#define LWSE_SWEEP_PLACE_GROUPED (1u << 5)   /* lwse_reconcile_*_device: the placement requests are grouped by
+                                                namespace (ns non-decreasing) — enables the namespace-parallel
+                                                placement kernels (one CTA per namespace, state in shared memory).
+                                                A promise: a violated order is counted, rows are then unspecified  */
+#define LWSE_SWEEP_PLACE_SCAN (1u << 6)      /* with GROUPED: brute-force (request x node) scoring from the
+                                                TMA-staged node table instead of the two-level search (same rows) */
 #define LWSE_SWEEP_SKIP_POD_SCAN (1u << 3)   /* profiling: skip the pod-state scan (its
                                                 bitmaps must hold a previous result)     */
 
@@ -441,6 +447,8 @@ typedef struct lwse_tick {
 
 #define LWSE_TICK_PLACE (1u << 8)     /* run the placement round over the resident request table */
 #define LWSE_TICK_NO_SWEEP (1u << 9)  /* patches (+ placement) only */
+/* (LWSE_SWEEP_PLACE_SCAN selects the brute-force form of the round; the resident request table
+ * is checked for namespace grouping when it is loaded) */
 
 /* The engine's patch arena: at least min_bytes of pinned, mapped host memory (grown on demand;
  * growing invalidates the previous base).  Patch segments whose rows / values pointers lie inside
@@ -496,6 +504,15 @@ LWSE_API int lwse_place_host(lwse_engine* e, const lwse_place_req* reqs, uint32_
 LWSE_API int lwse_place_device(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
                                const uint32_t* d_occupancy, uint32_t n_namespaces,
                                lwse_place_out* d_out, uint32_t* rounds_out, void* stream);
+
+/* As lwse_place_device for a request table the caller keeps GROUPED BY NAMESPACE (ns
+ * non-decreasing): one CTA per namespace, holder table / capacities / node table in shared memory
+ * (the latter staged by TMA).  flags: LWSE_SWEEP_PLACE_SCAN.  pair_scans_out (optional, with
+ * rounds_out): number of (request, round) searches the call made — x usable nodes = (request x
+ * node) pairs the scan form scored. */
+LWSE_API int lwse_place_grouped_device(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
+                                       const uint32_t* d_occupancy, uint32_t n_namespaces, lwse_place_out* d_out,
+                                       uint32_t flags, uint32_t* rounds_out, uint32_t* pair_scans_out, void* stream);
 
 /* Multi-GPU form: `d_parts` is the result of ONE all-gather over the ranks; part p
  * (rank p, at d_parts + p * part_stride_bytes) holds that shard's per-node occupancy

@@ -53,6 +53,13 @@ int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, cons
                  uint32_t* h_unpinned, const uint32_t** d_counters_out, const uint32_t** d_unpinned_out,
                  bool after_push);
 size_t place_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces);
+size_t place_ns_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces);
+bool place_ns_supported(uint32_t n_nodes, uint32_t n_domains);
+int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, const uint32_t* d_node_order, uint32_t n_nodes,
+                    uint32_t n_usable, uint32_t n_domains, const lwse_place_req* d_reqs, uint32_t n_reqs,
+                    const uint32_t* d_occupancy, uint32_t n_parts, uint64_t part_stride_bytes, uint32_t n_namespaces,
+                    lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes, bool fresh, uint32_t call_index, bool scan,
+                    int sm_count, cudaStream_t s, int* cuda_err, const uint32_t** d_counters_out, bool first_pdl);
 int launch_place_publish(const lwse_place_out* d_cur, lwse_place_out* d_prev, uint32_t n, uint32_t* h_rows,
                          lwse_place_out* h_outs, uint32_t capacity, uint32_t* d_count, uint32_t* d_ticket,
                          const uint32_t* d_rounds, uint32_t* h_words, uint32_t seq, cudaStream_t s, int* cuda_err);
@@ -173,6 +180,14 @@ struct lwse_engine {
   uint32_t place_geometry[4] = {0, 0, 0, 0};  // (n_reqs, n_namespaces, nodes, domains) the scratch was laid out for
   cudaEvent_t ev_place = nullptr;    // end of the last placement call: the next one (any stream) orders behind it
   bool place_pending = false;
+  DevBuf place_ns_scratch;           // namespace-parallel form (grouped request tables)
+  uint32_t place_ns_calls = 0;
+  uint32_t place_ns_geometry[4] = {0, 0, 0, 0};
+  uint32_t n_usable = 0;             // nodes a request can use (schedulable, labelled): length of the sorted index
+  const uint32_t* place_rounds_ptr = nullptr;  // device: the round counter of the last placement call
+  const uint32_t* place_scans_ptr = nullptr;   // device: its (request, round) search counter (grouped form), or null
+  bool r_place_grouped = false;      // the resident request table is grouped by namespace
+  std::vector<uint32_t> r_req_ns;    // its namespace column (host copy: patches must not regroup it)
   const uint32_t* place_counters = nullptr;  // device: counters / phase stamps of the last placement call
   const uint32_t* place_unpinned = nullptr;  // device: its unpinned-request count
   DevBuf ds, ds_roles, ds_revroles, ds_out, ds_role_out, ds_revrole_out;
@@ -348,7 +363,7 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
                       &e->place_scratch, &e->ds,       &e->ds_roles,   &e->ds_revroles, &e->ds_out,
                       &e->ds_role_out, &e->ds_revrole_out, &e->sha_bytes, &e->sha_offsets, &e->sha_digests,
                       &e->r_lws, &e->r_groups, &e->r_pst, &e->r_pid, &e->r_lws_out, &e->r_group_out, &e->r_scan,
-                      &e->r_counts, &e->r_occ, &e->r_preq, &e->r_pout, &e->r_pout_prev, &e->h_counts_dev};
+                      &e->r_counts, &e->r_occ, &e->r_preq, &e->r_pout, &e->r_pout_prev, &e->h_counts_dev, &e->place_ns_scratch};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&e->arena, &e->stage, &e->chg, &e->tickw};
     for (PinBuf* b : pins) b->release();
@@ -410,6 +425,8 @@ LWSE_API int lwse_upload_nodes(lwse_engine* e, const lwse_node_rec* nodes, uint3
   LWSE_CUDA(e, cudaStreamSynchronize(e->stream));  // the host vectors above go out of scope
   e->n_nodes = n_nodes;
   e->n_domains = n_domains;
+  e->n_usable = (uint32_t)first[n_domains];
+  e->place_ns_geometry[0] = e->place_ns_geometry[1] = e->place_ns_geometry[2] = e->place_ns_geometry[3] = 0;
   e->place_geometry[0] = e->place_geometry[1] = e->place_geometry[2] = e->place_geometry[3] = 0;  // re-initialise the scratch
   return LWSE_OK;
 }
@@ -625,11 +642,17 @@ static bool resident_table(lwse_engine* e, uint32_t which, void** base, uint64_t
 
 // Enqueue the patch segments of a tick on the engine's stream.  *wrote = some table changed
 // (the sweep's first kernel then has to wait for the scatter kernel to finish).
-static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_segs, bool* wrote) {
+// `tables`: bit t set = apply the segments of lwse_table t (a tick applies the placement request
+// patches on the side stream, where the round that reads them runs, and the rest on the engine's
+// stream); `stage_base`: where in the staging buffer this call may put copies.
+static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_segs, bool* wrote,
+                                uint32_t tables = 0xFFFFFFFFu, cudaStream_t s = nullptr, size_t stage_base = 0,
+                                size_t* stage_used = nullptr) {
   *wrote = false;
+  if (stage_used) *stage_used = stage_base;
   if (n_segs == 0) return LWSE_OK;
   if (!segs || n_segs > LWSE_TICK_MAX_SEGS) return LWSE_ERR_INVALID_ARG;
-  cudaStream_t s = e->stream;
+  if (!s) s = e->stream;
   // room for every segment that is not in the arena
   size_t need = 0;
   for (uint32_t i = 0; i < n_segs; i++) {
@@ -637,7 +660,7 @@ static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint
     uint64_t rows;
     uint32_t rb;
     if (!resident_table(e, segs[i].table, &base, &rows, &rb)) return LWSE_ERR_INVALID_ARG;
-    if (segs[i].n == 0) continue;
+    if (segs[i].n == 0 || !((tables >> segs[i].table) & 1u)) continue;
     if (!segs[i].values || (!(segs[i].flags & LWSE_PATCH_RANGE) && !segs[i].rows)) return LWSE_ERR_INVALID_ARG;
     if (segs[i].flags & LWSE_PATCH_RANGE) {
       if ((uint64_t)segs[i].first_row + segs[i].n > rows) return LWSE_ERR_BAD_TABLE;
@@ -647,22 +670,41 @@ static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint
     if (!e->arena.holds(segs[i].values, (size_t)segs[i].n * rb) || (rb > 1 && !aligned16(segs[i].values)))
       need += align256((size_t)segs[i].n * rb);
   }
-  if (need > e->stage.cap) {
-    LWSE_CUDA(e, cudaStreamSynchronize(s));
+  if (stage_base + need > e->stage.cap) {
+    if (stage_base) return LWSE_ERR_OOM;  // (the tick sizes the buffer for both of its calls up front)
+    LWSE_CUDA(e, cudaStreamSynchronize(e->stream));
+    LWSE_CUDA(e, cudaStreamSynchronize(e->side_stream));
     LWSE_CUDA(e, e->stage.reserve(need));
   }
   lwse::ScatterSegHost sc[LWSE_TICK_MAX_SEGS];
   int n_sc = 0;
-  size_t cursor = 0;
+  size_t cursor = stage_base;
   bool recount = false;
   for (uint32_t i = 0; i < n_segs; i++) {
     const lwse_patch_seg& g = segs[i];
-    if (g.n == 0) continue;
+    if (g.n == 0 || !((tables >> g.table) & 1u)) continue;
     void* base;
     uint64_t rows;
     uint32_t rb;
     resident_table(e, g.table, &base, &rows, &rb);
     *wrote = true;
+    if (g.table == LWSE_TABLE_PLACE_REQS && e->r_place_grouped) {
+      // a request that moves to another namespace breaks the grouping the fast placement kernels rely on
+      const lwse_place_req* v = static_cast<const lwse_place_req*>(g.values);
+      for (uint32_t k = 0; k < g.n; k++) {
+        const uint32_t row = (g.flags & LWSE_PATCH_RANGE) ? g.first_row + k : g.rows[k];
+        if (row < e->rn_reqs && v[k].ns != e->r_req_ns[row]) {
+          e->r_req_ns[row] = v[k].ns;
+          e->r_place_grouped = false;
+        }
+      }
+    } else if (g.table == LWSE_TABLE_PLACE_REQS) {
+      const lwse_place_req* v = static_cast<const lwse_place_req*>(g.values);
+      for (uint32_t k = 0; k < g.n; k++) {
+        const uint32_t row = (g.flags & LWSE_PATCH_RANGE) ? g.first_row + k : g.rows[k];
+        if (row < e->rn_reqs) e->r_req_ns[row] = v[k].ns;
+      }
+    }
     if (g.flags & LWSE_PATCH_RANGE) {  // one DMA copy straight into the table
       LWSE_CUDA(e, cudaMemcpyAsync(static_cast<uint8_t*>(base) + (size_t)g.first_row * rb, g.values, (size_t)g.n * rb,
                                    cudaMemcpyHostToDevice, s));
@@ -701,7 +743,16 @@ static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint
     if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
     e->launches += (uint64_t)launched;
   }
+  if (stage_used) *stage_used = cursor;
   return LWSE_OK;
+}
+
+// bytes of staging the segments of a tick need in the worst case (nothing in the arena)
+static size_t stage_bytes_upper_bound(const lwse_patch_seg* segs, uint32_t n_segs) {
+  size_t need = 0;
+  for (uint32_t i = 0; i < n_segs; i++)
+    if (segs && !(segs[i].flags & LWSE_PATCH_RANGE)) need += align256((size_t)segs[i].n * 4) + align256((size_t)segs[i].n * 64);
+  return need;
 }
 
 LWSE_API int lwse_resident_patch(lwse_engine* e, lwse_table which, const uint32_t* rows, const void* values,
@@ -742,12 +793,63 @@ LWSE_API int lwse_resident_outputs(lwse_engine* e, lwse_lws_out* lws_out, lwse_g
 // ---------------------------------------------------------------------------
 // Placement
 // ---------------------------------------------------------------------------
+constexpr uint32_t kFormGeneral = 0, kFormGrouped = 1, kFormScan = 2;
+static const int g_place_form_env = [] {  // LWSE_PLACE_FORM=general|grouped|scan: A/B measurements
+  const char* v = getenv("LWSE_PLACE_FORM");
+  if (!v) return -1;
+  return v[0] == 'g' && v[1] == 'e' ? 0 : v[0] == 's' ? 2 : 1;
+}();
+
+// The namespace-parallel form (request table grouped by namespace): condense kernel + one CTA per
+// namespace.  `first_pdl`: nothing on the stream right before writes the request table.
+static int place_grouped_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs, const uint32_t* d_occupancy,
+                                uint32_t n_parts, uint64_t part_stride_bytes, uint32_t n_namespaces, lwse_place_out* d_out,
+                                bool scan, uint32_t* rounds_out, uint32_t* scans_out, cudaStream_t s, bool first_pdl) {
+  const size_t scratch = lwse::place_ns_scratch_bytes(e->n_nodes, e->n_domains, n_reqs, n_namespaces);
+  const void* before = e->place_ns_scratch.p;
+  LWSE_CUDA(e, e->place_ns_scratch.reserve(scratch));
+  const uint32_t geometry[4] = {n_reqs, n_namespaces, e->n_nodes, e->n_domains};
+  const bool fresh = before != e->place_ns_scratch.p || memcmp(geometry, e->place_ns_geometry, sizeof(geometry)) != 0;
+  memcpy(e->place_ns_geometry, geometry, sizeof(geometry));
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  const bool eager = cudaStreamIsCapturing(s, &capturing) == cudaSuccess && capturing == cudaStreamCaptureStatusNone;
+  if (eager && e->place_pending) LWSE_CUDA(e, cudaStreamWaitEvent(s, e->ev_place, 0));
+  int cuda_err = 0;
+  const uint32_t* counters = nullptr;
+  int launched = lwse::launch_place_ns((const lwse_node_rec*)e->nodes.p, (const uint32_t*)e->dom_first.p,
+                                       (const uint32_t*)e->node_order.p, e->n_nodes, e->n_usable, e->n_domains, d_reqs, n_reqs,
+                                       d_occupancy, n_parts, part_stride_bytes, n_namespaces, d_out, e->place_ns_scratch.p,
+                                       scratch, fresh, e->place_ns_calls++, scan, e->sm_count, s, &cuda_err, &counters,
+                                       first_pdl && !fresh);
+  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+  e->launches += (uint64_t)launched;
+  e->place_rounds_ptr = counters;
+  e->place_scans_ptr = counters + 3;
+  if (eager) {
+    LWSE_CUDA(e, cudaEventRecord(e->ev_place, s));
+    e->place_pending = true;
+  }
+  if (rounds_out) {
+    LWSE_CUDA(e, cudaMemcpyAsync(e->h_rounds + 4, counters, 16, cudaMemcpyDeviceToHost, s));
+    LWSE_CUDA(e, cudaStreamSynchronize(s));
+    *rounds_out = e->h_rounds[4];
+    if (scans_out) *scans_out = e->h_rounds[7];
+  }
+  return LWSE_OK;
+}
+
 static int place_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
                         const uint32_t* d_occupancy, uint32_t n_namespaces, lwse_place_out* d_out,
                         uint32_t* rounds_out, cudaStream_t s, uint32_t n_parts, uint32_t reqs_per_part,
-                        uint64_t part_stride_bytes, bool after_push = false) {
+                        uint64_t part_stride_bytes, bool after_push = false, uint32_t form = kFormGeneral,
+                        bool first_pdl = false) {
   if ((n_reqs && (!d_reqs || !d_out)) || n_namespaces == 0) return LWSE_ERR_INVALID_ARG;
   if (e->n_nodes == 0 || e->n_domains == 0) return LWSE_ERR_NOT_READY;
+  if (g_place_form_env == 0) form = kFormGeneral;
+  if (g_place_form_env == 2 && form != kFormGeneral) form = kFormScan;
+  if (form != kFormGeneral && n_parts <= 1 && lwse::place_ns_supported(e->n_nodes, e->n_domains))
+    return place_grouped_locked(e, d_reqs, n_reqs, d_occupancy, 1, 0, n_namespaces, d_out, form == kFormScan, rounds_out, nullptr,
+                                s, first_pdl);
   const size_t scratch = lwse::place_scratch_bytes(e->n_nodes, e->n_domains, n_reqs, n_namespaces);
   const void* before = e->place_scratch.p;
   LWSE_CUDA(e, e->place_scratch.reserve(scratch));
@@ -771,6 +873,8 @@ static int place_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n
                                     e->h_rounds + 2, &e->place_counters, &e->place_unpinned, after_push);
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
+  e->place_rounds_ptr = e->place_counters + 3;
+  e->place_scans_ptr = nullptr;
   if (rounds_out) *rounds_out = e->h_rounds[0];
   if (eager) {
     LWSE_CUDA(e, cudaEventRecord(e->ev_place, s));
@@ -783,6 +887,18 @@ static int place_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n
     LWSE_CUDA(e, cudaMemcpyAsync(e->h_rounds + 2, e->place_unpinned, 4, cudaMemcpyDeviceToHost, e->hist_stream));
   }
   return LWSE_OK;
+}
+
+// ns non-decreasing over the table?  (host tables: a 4-byte read per 32-byte row)
+static bool grouped_by_namespace(const lwse_place_req* reqs, uint32_t n) {
+  for (uint32_t i = 1; i < n; i++)
+    if (reqs[i].ns < reqs[i - 1].ns) return false;
+  return true;
+}
+
+static uint32_t form_of_flags(uint32_t sweep_flags) {
+  if (!(sweep_flags & LWSE_SWEEP_PLACE_GROUPED)) return kFormGeneral;
+  return (sweep_flags & LWSE_SWEEP_PLACE_SCAN) ? kFormScan : kFormGrouped;
 }
 
 static int place_common(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
@@ -811,7 +927,8 @@ LWSE_API int lwse_reconcile_device(lwse_engine* e, const lwse_lws_tables* t, con
   if (n_reqs == 0) return sweep_device_locked(e, t, s);
   LWSE_CUDA(e, cudaEventRecord(e->ev_fork, s));
   LWSE_CUDA(e, cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
-  rc = place_locked(e, d_reqs, n_reqs, d_occupancy, n_namespaces, d_place_out, nullptr, e->side_stream, 1, n_reqs, 0);
+  rc = place_locked(e, d_reqs, n_reqs, d_occupancy, n_namespaces, d_place_out, nullptr, e->side_stream, 1, n_reqs, 0, false,
+                    form_of_flags(t->flags), /*first_pdl=*/false);
   if (rc == LWSE_OK) rc = sweep_device_locked(e, t, s);
   // join even after a failure, so that the side stream never runs ahead of `stream`
   cudaError_t je = cudaEventRecord(e->ev_join, e->side_stream);
@@ -825,6 +942,20 @@ LWSE_API int lwse_place_device(lwse_engine* e, const lwse_place_req* d_reqs, uin
                                const uint32_t* d_occupancy, uint32_t n_namespaces,
                                lwse_place_out* d_out, uint32_t* rounds_out, void* stream) {
   return place_common(e, d_reqs, n_reqs, d_occupancy, n_namespaces, d_out, rounds_out, stream, 1, n_reqs, 0);
+}
+
+LWSE_API int lwse_place_grouped_device(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
+                                       const uint32_t* d_occupancy, uint32_t n_namespaces, lwse_place_out* d_out,
+                                       uint32_t flags, uint32_t* rounds_out, uint32_t* pair_scans_out, void* stream) {
+  if (!e || (n_reqs && (!d_reqs || !d_out)) || n_namespaces == 0) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (e->n_nodes == 0 || e->n_domains == 0) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  if (!lwse::place_ns_supported(e->n_nodes, e->n_domains))  // too many domains for one CTA's shared memory
+    return place_locked(e, d_reqs, n_reqs, d_occupancy, n_namespaces, d_out, rounds_out, s, 1, n_reqs, 0);
+  return place_grouped_locked(e, d_reqs, n_reqs, d_occupancy, 1, 0, n_namespaces, d_out, (flags & LWSE_SWEEP_PLACE_SCAN) != 0,
+                              rounds_out, pair_scans_out, s, /*first_pdl=*/false);
 }
 
 LWSE_API int lwse_place_gathered_device(lwse_engine* e, const void* d_parts, uint32_t n_parts,
@@ -977,8 +1108,10 @@ LWSE_API int lwse_place_host(lwse_engine* e, const lwse_place_req* reqs, uint32_
     LWSE_CUDA(e, cudaMemcpyAsync(e->place_occ.p, occupancy, (size_t)e->n_nodes * 4, cudaMemcpyHostToDevice, s));
   else
     LWSE_CUDA(e, cudaMemsetAsync(e->place_occ.p, 0, (size_t)e->n_nodes * 4, s));
+  // a table grouped by namespace (the encoder emits it that way) takes the namespace-parallel kernels
+  const uint32_t form = n_reqs && grouped_by_namespace(reqs, n_reqs) ? kFormGrouped : kFormGeneral;
   const int rc = place_locked(e, (const lwse_place_req*)e->place_reqs.p, n_reqs, (const uint32_t*)e->place_occ.p, n_namespaces,
-                              (lwse_place_out*)e->place_out.p, rounds_out, s, 1, n_reqs, 0);
+                              (lwse_place_out*)e->place_out.p, rounds_out, s, 1, n_reqs, 0, false, form);
   if (rc != LWSE_OK) return rc;
   if (n_reqs)
     LWSE_CUDA(e, cudaMemcpyAsync(out, e->place_out.p, (size_t)n_reqs * sizeof(lwse_place_out), cudaMemcpyDeviceToHost, s));
@@ -1009,8 +1142,10 @@ LWSE_API int lwse_reconcile_host(lwse_engine* e, const lwse_lws_tables* h, const
       LWSE_CUDA(e, cudaMemcpyAsync(e->place_occ.p, occupancy, (size_t)e->n_nodes * 4, cudaMemcpyHostToDevice, ps));
     else
       LWSE_CUDA(e, cudaMemsetAsync(e->place_occ.p, 0, (size_t)e->n_nodes * 4, ps));
+    const uint32_t form = grouped_by_namespace(reqs, n_reqs)
+                              ? ((h->flags & LWSE_SWEEP_PLACE_SCAN) ? kFormScan : kFormGrouped) : kFormGeneral;
     rc = place_locked(e, (const lwse_place_req*)e->place_reqs.p, n_reqs, (const uint32_t*)e->place_occ.p, n_namespaces,
-                      (lwse_place_out*)e->place_out.p, nullptr, ps, 1, n_reqs, 0);
+                      (lwse_place_out*)e->place_out.p, nullptr, ps, 1, n_reqs, 0, false, form);
     if (rc == LWSE_OK)
       LWSE_CUDA(e, cudaMemcpyAsync(place_out, e->place_out.p, (size_t)n_reqs * sizeof(lwse_place_out),
                                    cudaMemcpyDeviceToHost, ps));
@@ -1043,6 +1178,9 @@ LWSE_API int lwse_resident_place_load(lwse_engine* e, const lwse_place_req* reqs
   e->rn_reqs = n_reqs;
   e->rn_namespaces = n_namespaces;
   e->r_place_loaded = true;
+  e->r_place_grouped = grouped_by_namespace(reqs, n_reqs);
+  e->r_req_ns.resize(n_reqs);
+  for (uint32_t i = 0; i < n_reqs; i++) e->r_req_ns[i] = reqs[i].ns;
   return reserve_change_lists(e);
 }
 
@@ -1085,24 +1223,56 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
   volatile uint32_t* hw = static_cast<volatile uint32_t*>(e->tickw.h);
   uint32_t* hw_dev = static_cast<uint32_t*>(e->tickw.d);
   uint8_t* chg_d = static_cast<uint8_t*>(e->chg.d);
-  bool wrote = false;
-  int rc = apply_patches_locked(e, segs, n_segs, &wrote);
-  if (rc != LWSE_OK) return rc;
   const bool do_place = (flags & LWSE_TICK_PLACE) && e->r_place_loaded && e->rn_reqs > 0;
   const bool do_sweep = !(flags & LWSE_TICK_NO_SWEEP) && (e->rn_lws || e->rn_groups);
+  // Patches go where their readers run: the placement request table is read only by the round on
+  // the side stream, everything else by the sweep on the engine's stream — the (long) round then
+  // starts behind its own few rows instead of behind the whole scatter.  Identity-row patches move
+  // occupancy counts, which the round reads: with those in the tick it forks behind the main scatter.
+  constexpr uint32_t kSideTables = 1u << LWSE_TABLE_PLACE_REQS;
+  bool has_ident = false, has_side = false;
+  for (uint32_t i = 0; i < n_segs; i++) {
+    if (!segs) return LWSE_ERR_INVALID_ARG;
+    if (segs[i].n && segs[i].table == LWSE_TABLE_POD_IDENT) has_ident = true;
+    if (segs[i].n && segs[i].table == LWSE_TABLE_PLACE_REQS) has_side = true;
+  }
+  {
+    const size_t ub = stage_bytes_upper_bound(segs, n_segs);
+    if (ub > e->stage.cap) {  // rare: only segments outside the arena are staged
+      bool all_in_arena = true;
+      for (uint32_t i = 0; i < n_segs; i++)
+        if (segs[i].n && !(segs[i].flags & LWSE_PATCH_RANGE) &&
+            (!e->arena.holds(segs[i].rows, (size_t)segs[i].n * 4) || !e->arena.holds(segs[i].values, 1)))
+          all_in_arena = false;
+      if (!all_in_arena) {
+        LWSE_CUDA(e, cudaStreamSynchronize(s));
+        LWSE_CUDA(e, cudaStreamSynchronize(e->side_stream));
+        LWSE_CUDA(e, e->stage.reserve(ub));
+      }
+    }
+  }
+  bool wrote = false, wrote_side = false;
+  size_t stage_used = 0;
+  int rc = apply_patches_locked(e, segs, n_segs, &wrote, ~kSideTables, s, 0, &stage_used);
+  if (rc != LWSE_OK) return rc;
   int cuda_err = 0;
+  if (do_place || has_side) {
+    if (has_ident) {  // the round reads the occupancy counters the main scatter just moved
+      LWSE_CUDA(e, cudaEventRecord(e->ev_fork, s));
+      LWSE_CUDA(e, cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+    }
+    rc = apply_patches_locked(e, segs, n_segs, &wrote_side, kSideTables, e->side_stream, stage_used, nullptr);
+    if (rc != LWSE_OK) return rc;
+  }
   if (do_place) {
-    // the round reads the request table and the occupancy counters, which the patches may have
-    // touched: it forks from the engine's stream behind the scatter kernel
-    LWSE_CUDA(e, cudaEventRecord(e->ev_fork, s));
-    LWSE_CUDA(e, cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+    const uint32_t form = !e->r_place_grouped ? kFormGeneral : (flags & LWSE_SWEEP_PLACE_SCAN) ? kFormScan : kFormGrouped;
     rc = place_locked(e, (const lwse_place_req*)e->r_preq.p, e->rn_reqs, (const uint32_t*)e->r_occ.p, e->rn_namespaces,
-                      (lwse_place_out*)e->r_pout.p, nullptr, e->side_stream, 1, e->rn_reqs, 0);
+                      (lwse_place_out*)e->r_pout.p, nullptr, e->side_stream, 1, e->rn_reqs, 0, false, form, /*first_pdl=*/false);
     if (rc != LWSE_OK) return rc;
     int launched = lwse::launch_place_publish(
         (const lwse_place_out*)e->r_pout.p, (lwse_place_out*)e->r_pout_prev.p, e->rn_reqs,
         reinterpret_cast<uint32_t*>(chg_d + e->chg_off[4]), reinterpret_cast<lwse_place_out*>(chg_d + e->chg_off[5]),
-        e->rn_reqs, (uint32_t*)e->r_counts.p + 4, (uint32_t*)e->r_counts.p + 5, e->place_counters + 3, hw_dev + 4, seq,
+        e->rn_reqs, (uint32_t*)e->r_counts.p + 4, (uint32_t*)e->r_counts.p + 5, e->place_rounds_ptr, hw_dev + 4, seq,
         e->side_stream, &cuda_err);
     if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
     e->launches += (uint64_t)launched;
@@ -1154,6 +1324,10 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
     }
   }
   if (ok && do_place) ok = wait_word(hw + 6, seq, e->side_stream, &werr);
+  if (ok && !do_place && wrote_side) {
+    werr = cudaStreamSynchronize(e->side_stream);
+    ok = werr == cudaSuccess;
+  }
   if (!ok) {
     const cudaError_t a = cudaStreamSynchronize(s), b = cudaStreamSynchronize(e->side_stream);
     return fail_cuda(e, werr != cudaSuccess ? werr : a != cudaSuccess ? a : b != cudaSuccess ? b : cudaErrorUnknown);

@@ -1,0 +1,496 @@
+// Placement round, namespace-parallel form (sm_100a) — same build-defined spec as
+// lwse_place_kernels.cu (oracle/lwse_oracle_place.c), for request tables GROUPED BY NAMESPACE.
+//
+// Exclusivity is per namespace and capacity is a snapshot that no claim consumes, so the
+// namespaces are independent sub-problems.  That turns the round's hot state — the holder table
+// of one namespace (8 B x domains), the per-domain free capacity and the condensed node-topology
+// table (one word per usable node: free slots | domain, in domain order) — into a few tens of KB
+// that fit the shared memory of ONE CTA:
+//
+//   place_condense_kernel   node rows + occupancy -> sorted node words + per-domain capacity
+//                           (a warp per domain over its run of the static domain-sorted index:
+//                           no atomics), and the namespace index of the request table
+//                           (ns_first[v] = first request of namespace v; order violations counted).
+//   place_ns_kernel         one CTA per namespace.  The node-word table and the capacities are
+//                           staged with TMA (cp.async.bulk.tensor.2d / cp.async.bulk + mbarrier,
+//                           issued by one thread while the others clear the holder table), the
+//                           holder table lives in shared memory, claims are 64-bit shared-memory
+//                           atomicMin, rounds are separated by __syncthreads() — no grid or
+//                           cluster barrier, no L2 round trip per domain.  Deferred acceptance
+//                           runs to ITS OWN fixed point per namespace.
+//   scan form               the same kernel brute-forcing every (request x node) pair from the
+//                           staged table instead of the two-level (domain, then node) search:
+//                           feasibility + both rendezvous hashes per pair, lexicographic arg-max
+//                           (domain score, lower domain, node score, lower node) — identical rows.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "lwse_device.cuh"
+
+namespace lwse {
+
+struct PlaceNsArgs {
+  const lwse_node_rec* nodes;
+  const lwse_place_req* reqs;  // grouped by namespace (ns non-decreasing)
+  const uint32_t* occupancy;   // nullable; n_parts blocks of n_nodes counters, part_stride_bytes apart
+  lwse_place_out* out;
+  const uint32_t* dom_first;   // static index (lwse_upload_nodes)
+  const uint32_t* node_order;
+  uint32_t* g_words;     // condensed node words in domain-sorted position, padded with zeros to whole rows of 256
+  uint32_t* g_dom_free;  // n_domains (+ padding)
+  uint32_t* ns_first;    // n_namespaces + 1
+  uint32_t* unpinned;    // n_reqs: namespace v's live unpinned requests at [ns_first[v], …)
+  uint32_t* counters;    // this call's block: [0] max rounds [1] live unpinned [2] order violations [3] (request, round) scans
+  uint32_t* next_counters;  // the other block, cleared for the next call
+  uint32_t n_nodes, n_usable, n_domains, n_reqs, n_namespaces;
+  uint32_t n_parts;
+  uint64_t part_stride_bytes;
+  uint32_t word_rows;   // rows of 256 words of g_words
+  uint32_t scan;        // 1 = brute-force (request x node) form
+  uint32_t stage_words; // the word table fits shared memory and is staged
+  uint32_t use_tensor_map;
+};
+
+__device__ __forceinline__ uint32_t mix32n(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+
+__device__ __forceinline__ unsigned long long ns_place_key(unsigned long long priority, uint32_t index, bool pinned) {
+  return ((unsigned long long)(pinned ? 0 : 1) << 63) | (((priority >> 25) & 0x7FFFFFFFFFull) << 24) |
+         (unsigned long long)(index & 0xFFFFFFu);
+}
+
+__device__ __forceinline__ uint32_t occupancy_sum(const PlaceNsArgs& a, uint32_t n) {
+  if (!a.occupancy) return 0u;
+  uint32_t occ = 0;
+  for (uint32_t p = 0; p < a.n_parts; p++)
+    occ += ldg_keep_u32(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(a.occupancy) +
+                                                           (uint64_t)p * a.part_stride_bytes) + n);
+  return occ;
+}
+
+__device__ __forceinline__ void store_row(lwse_place_out* p, uint32_t d, uint32_t n, uint32_t flags, uint32_t score) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(d, n, flags, score);
+}
+
+// --------------------------------------------------------------------------
+// condense: node words, domain capacities, namespace index
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) place_condense_kernel(const PlaceNsArgs a) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  pdl_launch_dependents();  // the namespace kernel may load its requests meanwhile; it waits before the tables below
+  pdl_wait_prior();         // the previous call's namespace kernel may still read the tables written here
+  // A. a warp per domain: its nodes are a run of the sorted index
+  for (uint32_t d = gwarp; d < a.n_domains; d += n_warps) {
+    const uint32_t first = ldg_keep_u32(a.dom_first + d), last = ldg_keep_u32(a.dom_first + d + 1u);
+    uint32_t sum = 0;
+    for (uint32_t i = first + lane; i < last; i += 32u) {
+      const uint32_t n = ldg_keep_u32(a.node_order + i);
+      const uint4 nr = ldg_keep(reinterpret_cast<const uint4*>(a.nodes + n));
+      const uint32_t cap = nr.w & 0xFFFFu, occ = occupancy_sum(a, n);
+      const uint32_t fr = cap > occ ? cap - occ : 0u;
+      a.g_words[i] = (min(fr, 15u) << 28) | d;
+      sum += fr;
+    }
+    sum = __reduce_add_sync(0xFFFFFFFFu, sum);
+    if (lane == 0) a.g_dom_free[d] = sum;
+  }
+  // B. the namespace index of the (promised) grouped request table
+  if (a.n_reqs == 0u) {
+    for (uint32_t v = gtid; v <= a.n_namespaces; v += gsize) a.ns_first[v] = 0u;
+  }
+  for (uint32_t i = gtid; i < a.n_reqs; i += gsize) {
+    const uint4 hi = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + i) + 1);
+    const uint32_t b = hi.y;
+    uint32_t lo_v;  // namespaces (lo_v, b] start at request i; for i == 0 also namespace lo_v itself
+    if (i == 0u) {
+      for (uint32_t v = 0; v <= min(b, a.n_namespaces); v++) a.ns_first[v] = 0u;
+    } else {
+      const uint32_t prev = ldg_keep_u32(reinterpret_cast<const uint32_t*>(a.reqs + i - 1) + 5);  // .ns
+      if (prev > b) atomicAdd(a.counters + 2, 1u);  // not grouped: the caller broke its promise
+      lo_v = min(prev, a.n_namespaces);
+      for (uint32_t v = lo_v + 1u; v <= min(b, a.n_namespaces); v++) a.ns_first[v] = i;
+    }
+    if (i == a.n_reqs - 1u)
+      for (uint32_t v = min(b, a.n_namespaces) + 1u; v <= a.n_namespaces; v++) a.ns_first[v] = a.n_reqs;
+    if (b >= a.n_namespaces) {  // no such namespace: never takes part in a round
+      const bool pinned = hi.w != LWSE_NONE;
+      store_row(a.out + i, LWSE_NONE, pinned ? hi.w : LWSE_NONE,
+                (pinned ? LWSE_PLACE_PINNED : 0u) | LWSE_PLACE_UNSCHEDULABLE, 0u);
+    }
+  }
+  if (gtid < 8u) a.next_counters[gtid] = 0u;
+}
+
+// --------------------------------------------------------------------------
+// one CTA per namespace
+// --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+constexpr uint32_t kNsThreads = 512;
+
+template <bool kScan>
+__global__ void __launch_bounds__(kNsThreads, 1)
+    place_ns_kernel(const PlaceNsArgs a, const __grid_constant__ CUtensorMap words_map) {
+  extern __shared__ uint8_t s_dyn[];
+  // layout (from a 128-byte aligned base: the TMA destination): [words: word_rows x 256 u32]
+  //         [dom_free: n_domains u32, 16-byte padded] [holder: n_domains u64] [mbarrier]
+  uint8_t* s_raw = s_dyn + ((128u - (smem_u32(s_dyn) & 127u)) & 127u);
+  const uint32_t words_bytes = a.stage_words ? a.word_rows * 1024u : 0u;
+  const uint32_t free_bytes = ((a.n_domains * 4u) + 15u) & ~15u;
+  uint32_t* s_words = reinterpret_cast<uint32_t*>(s_raw);
+  uint32_t* s_free = reinterpret_cast<uint32_t*>(s_raw + words_bytes);
+  unsigned long long* s_hold = reinterpret_cast<unsigned long long*>(s_raw + words_bytes + free_bytes);
+  unsigned long long* s_mbar = s_hold + a.n_domains;
+  __shared__ uint32_t s_n_unp, s_unsettled[3];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, n_warps = blockDim.x >> 5;
+  const uint32_t* words = a.stage_words ? s_words : a.g_words;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // (no early griddepcontrol.launch_dependents: the tick's publish kernel would only park its CTAs
+  // on SMs the concurrent sweep wants; it still launches ahead and starts the moment this grid ends)
+  pdl_wait_prior();  // the condense kernel's tables (and the request table a tick's scatter patched)
+  if (tid == 0) {
+    // TMA: the node-word table (a 2D tensor of 256-word rows) and the capacity vector land in shared
+    // memory while the other threads clear the holder table; one mbarrier collects the bytes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(s_mbar)), "r"(words_bytes + free_bytes)
+                 : "memory");
+    if (a.stage_words) {
+      if (a.use_tensor_map) {
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                         smem_u32(s_words)),
+                     "l"(&words_map), "r"(smem_u32(s_mbar)), "r"(0), "r"(0)
+                     : "memory");
+      } else {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_words)),
+                     "l"(a.g_words), "r"(words_bytes), "r"(smem_u32(s_mbar))
+                     : "memory");
+      }
+    }
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_free)),
+                 "l"(a.g_dom_free), "r"(free_bytes), "r"(smem_u32(s_mbar))
+                 : "memory");
+  }
+  bool staged = false;
+
+  for (uint32_t ns = blockIdx.x; ns < a.n_namespaces; ns += gridDim.x) {
+    const uint32_t first = __ldcg(a.ns_first + ns), last = __ldcg(a.ns_first + ns + 1u);
+    if (tid == 0) {
+      s_n_unp = 0u;
+      s_unsettled[0] = s_unsettled[1] = s_unsettled[2] = 0u;
+    }
+    for (uint32_t d = tid; d < a.n_domains; d += blockDim.x) s_hold[d] = ~0ull;
+    __syncthreads();
+    if (first >= last) continue;  // CTA-uniform
+
+    // ---- phase 1: pinned claims, the list of live unpinned requests ----
+    for (uint32_t r = first + tid; r < last; r += blockDim.x) {
+      const uint4 lo = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r)), hi = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r) + 1);
+      const uint32_t leader = hi.w;
+      if (leader == LWSE_NONE) {
+        const bool dead = (int32_t)hi.z < 1;
+        store_row(a.out + r, LWSE_NONE, LWSE_NONE, dead ? LWSE_PLACE_UNSCHEDULABLE : 0u, 0u);
+        if (!dead) a.unpinned[first + atomicAdd(&s_n_unp, 1u)] = r;
+      } else {
+        uint32_t d = LWSE_NONE;
+        if (leader < a.n_nodes) {
+          const uint4 nr = ldg_keep(reinterpret_cast<const uint4*>(a.nodes + leader));
+          if (((nr.w >> 16) & LWSE_NODE_HAS_TOPOLOGY) && nr.z < a.n_domains) d = nr.z;
+        }
+        if (d != LWSE_NONE) atomicMin(s_hold + d, ns_place_key(u64_of(lo.x, lo.y), r, true));
+      }
+    }
+    __syncthreads();
+    // results of the pinned requests: final from here on (pinned keys are below every unpinned key)
+    for (uint32_t r = first + tid; r < last; r += blockDim.x) {
+      const uint4 lo = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r)), hi = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r) + 1);
+      const uint32_t leader = hi.w;
+      if (leader == LWSE_NONE) continue;
+      uint32_t d = LWSE_NONE, flags = LWSE_PLACE_PINNED;
+      if (leader < a.n_nodes) {
+        const uint4 nr = ldg_keep(reinterpret_cast<const uint4*>(a.nodes + leader));
+        if (((nr.w >> 16) & LWSE_NODE_HAS_TOPOLOGY) && nr.z < a.n_domains) d = nr.z;
+      }
+      if (d != LWSE_NONE) flags |= s_hold[d] == ns_place_key(u64_of(lo.x, lo.y), r, true) ? LWSE_PLACE_PLACED : LWSE_PLACE_CONFLICT;
+      store_row(a.out + r, d, leader, flags, 0u);
+    }
+    const uint32_t n_unp = s_n_unp;
+    if (n_unp == 0u) {
+      __syncthreads();
+      continue;
+    }
+    if (tid == 0) atomicAdd(a.counters + 1, n_unp);
+    if (!staged) {  // the first namespace with work waits for the staged tables
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(s_mbar)) : "memory");
+      staged = true;
+    }
+
+    // ---- deferred-acceptance rounds of this namespace, one warp per request ----
+    uint32_t round = 0;
+    for (;; round++) {
+      // three rotating counters: the one for round k+1 is cleared during round k, when nobody can
+      // still be reading it (it was last read after round k-2)
+      uint32_t* unsettled_ctr = &s_unsettled[round % 3u];
+      if (tid == 0) s_unsettled[(round + 1u) % 3u] = 0u;
+      uint32_t scans = 0;
+      for (uint32_t k = warp; k < n_unp; k += n_warps) {
+        const uint32_t r = __ldcg(a.unpinned + first + k);
+        const uint4 o = __ldcg(reinterpret_cast<const uint4*>(a.out + r));  // state: written by this warp only
+        if (o.z & LWSE_PLACE_UNSCHEDULABLE) continue;  // warp-uniform
+        const uint4 lo = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r)), hi = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r) + 1);
+        const unsigned long long key = ns_place_key(u64_of(lo.x, lo.y), r, false);
+        const uint32_t key_lo = lo.z, key_hi = lo.w, size = hi.z;
+        if (o.x != LWSE_NONE && s_hold[o.x] == key) continue;  // still holds what it proposed to
+        scans++;
+        uint32_t H = 0, best_d = LWSE_NONE, best_n = LWSE_NONE;
+        if constexpr (!kScan) {
+          // Level 1 — the domain, from shared memory (holders change under our feet during a round;
+          // a stale reading can only make a proposal fail: holder keys only decrease).
+          uint32_t my_hi = 0, my_d = LWSE_NONE;
+          for (uint32_t d = lane; d < a.n_domains; d += 32u) {
+            const uint32_t h = (s_free[d] >= size && s_hold[d] >= key) ? (mix32n(key_lo ^ (d * 0x9E3779B1u)) | 1u) : 0u;
+            if (h > my_hi) {  // ascending d per lane: ties keep the lower domain
+              my_hi = h;
+              my_d = d;
+            }
+          }
+          H = __reduce_max_sync(0xFFFFFFFFu, my_hi);
+          if (H != 0u) {
+            best_d = __reduce_min_sync(0xFFFFFFFFu, my_hi == H ? my_d : LWSE_NONE);
+            // Level 2 — the node: the domain's run of the sorted words.
+            const uint32_t f2 = ldg_keep_u32(a.dom_first + best_d), l2 = ldg_keep_u32(a.dom_first + best_d + 1u);
+            uint32_t my_lo = 0, my_n = LWSE_NONE;
+            for (uint32_t i = f2 + lane; i < l2; i += 32u) {
+              const uint32_t w = words[i];
+              if ((w >> 28) == 0u) continue;
+              const uint32_t n = ldg_keep_u32(a.node_order + i);
+              const uint32_t l = ((w >> 28) << 28) | (mix32n(key_hi ^ (n * 0x85EBCA77u)) >> 4);
+              if (l > my_lo || (l == my_lo && n < my_n)) {
+                my_lo = l;
+                my_n = n;
+              }
+            }
+            const uint32_t L = __reduce_max_sync(0xFFFFFFFFu, my_lo);
+            best_n = __reduce_min_sync(0xFFFFFFFFu, (my_lo == L && L != 0u) ? my_n : LWSE_NONE);
+          }
+        } else {
+          // Brute force: every (request, node) pair of the staged table.  Lexicographic arg-max of
+          // (domain score, lower domain, node score, lower node) — the two-level result.
+          uint32_t my_hi = 0, my_d = LWSE_NONE, my_lo = 0, my_n = LWSE_NONE;
+          for (uint32_t i = lane; i < a.n_usable; i += 32u) {
+            const uint32_t w = words[i], d = w & 0x0FFFFFFFu;
+            if ((w >> 28) == 0u || s_free[d] < size || s_hold[d] < key) continue;
+            const uint32_t h = mix32n(key_lo ^ (d * 0x9E3779B1u)) | 1u;
+            if (h < my_hi || (h == my_hi && d > my_d)) continue;
+            const uint32_t n = ldg_keep_u32(a.node_order + i);
+            const uint32_t l = ((w >> 28) << 28) | (mix32n(key_hi ^ (n * 0x85EBCA77u)) >> 4);
+            const bool better = h > my_hi || d < my_d || l > my_lo || (l == my_lo && n < my_n);
+            if (better) {
+              my_hi = h;
+              my_d = d;
+              my_lo = l;
+              my_n = n;
+            }
+          }
+          H = __reduce_max_sync(0xFFFFFFFFu, my_hi);
+          if (H != 0u) {
+            best_d = __reduce_min_sync(0xFFFFFFFFu, my_hi == H ? my_d : LWSE_NONE);
+            const bool in = my_hi == H && my_d == best_d;
+            const uint32_t L = __reduce_max_sync(0xFFFFFFFFu, in ? my_lo : 0u);
+            best_n = __reduce_min_sync(0xFFFFFFFFu, (in && my_lo == L && L != 0u) ? my_n : LWSE_NONE);
+          }
+        }
+        if (lane == 0) {
+          if (H == 0u || best_n == LWSE_NONE) {  // nothing feasible now, and the feasible set only shrinks
+            store_row(a.out + r, LWSE_NONE, LWSE_NONE, LWSE_PLACE_UNSCHEDULABLE, 0u);
+          } else {
+            store_row(a.out + r, best_d, best_n, LWSE_PLACE_PLACED, H);
+            // A claim on an empty domain settles at once; any other outcome leaves somebody without
+            // a domain who proposes again next round: count it.
+            const unsigned long long old = atomicMin(s_hold + best_d, key);
+            if (old != ~0ull) atomicAdd(unsettled_ctr, 1u);
+          }
+        }
+        __syncwarp();
+      }
+      if (lane == 0 && scans) atomicAdd(a.counters + 3, scans);
+      __syncthreads();
+      const uint32_t unsettled = *unsettled_ctr;
+      if (unsettled == 0u || round > n_unp + 2u) break;
+    }
+    if (tid == 0) atomicMax(a.counters + 0, round + 1u);
+    __syncthreads();
+  }
+  if (!staged) {  // never leave a bulk copy in flight behind a CTA that exits
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smem_u32(s_mbar)) : "memory");
+  }
+}
+
+// --------------------------------------------------------------------------
+// launcher
+// --------------------------------------------------------------------------
+static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+
+// scratch: [words (rows x 1 KB)] [dom_free] [ns_first] [unpinned] [counters: 2 blocks of 8 words]
+struct NsLayout {
+  size_t words, dom_free, ns_first, unpinned, counters, total;
+  uint32_t word_rows;
+};
+static NsLayout ns_layout(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces) {
+  NsLayout l{};
+  l.word_rows = (n_nodes + 255u) / 256u;
+  if (l.word_rows == 0) l.word_rows = 1;
+  size_t off = 0;
+  l.words = off;
+  off += up256((size_t)l.word_rows * 1024);
+  l.dom_free = off;
+  off += up256((size_t)n_domains * 4 + 16);
+  l.ns_first = off;
+  off += up256(((size_t)n_namespaces + 2) * 4);
+  l.unpinned = off;
+  off += up256((size_t)n_reqs * 4 + 16);
+  l.counters = off;
+  off += 256;
+  l.total = off;
+  return l;
+}
+size_t place_ns_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces) {
+  return ns_layout(n_nodes, n_domains, n_reqs, n_namespaces).total;
+}
+
+// shared memory the namespace kernel needs when it stages the word table / when it does not
+static size_t ns_smem_bytes(uint32_t word_rows, uint32_t n_domains, bool stage) {
+  return (stage ? (size_t)word_rows * 1024 : 0) + (((size_t)n_domains * 4 + 15) & ~(size_t)15) + (size_t)n_domains * 8 + 16 + 128;
+}
+bool place_ns_supported(uint32_t n_nodes, uint32_t n_domains) {
+  return ns_smem_bytes((n_nodes + 255u) / 256u, n_domains, false) <= 200u * 1024u && n_domains < (1u << 28);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool encode_words_map(CUtensorMap* map, void* g_words, uint32_t word_rows) {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  if (!fn || word_rows == 0 || word_rows > 256) return false;
+  const cuuint64_t dims[2] = {256, word_rows};
+  const cuuint64_t strides[1] = {1024};
+  const cuuint32_t box[2] = {256, word_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, g_words, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Returns kernels launched or -1.  `fresh`: the scratch was (re)allocated: zero it first.
+int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, const uint32_t* d_node_order, uint32_t n_nodes,
+                    uint32_t n_usable, uint32_t n_domains, const lwse_place_req* d_reqs, uint32_t n_reqs,
+                    const uint32_t* d_occupancy, uint32_t n_parts, uint64_t part_stride_bytes, uint32_t n_namespaces,
+                    lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes, bool fresh, uint32_t call_index, bool scan,
+                    int sm_count, cudaStream_t s, int* cuda_err, const uint32_t** d_counters_out, bool first_pdl) {
+  *cuda_err = 0;
+  const NsLayout l = ns_layout(n_nodes, n_domains, n_reqs, n_namespaces);
+  if (scratch_bytes < l.total || n_reqs > 0xFFFFFFu) {
+    *cuda_err = (int)cudaErrorInvalidValue;
+    return -1;
+  }
+  uint8_t* base = static_cast<uint8_t*>(d_scratch);
+  cudaError_t e = cudaSuccess;
+  if (fresh) {
+    e = cudaMemsetAsync(base, 0, l.total, s);
+    if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
+  }
+  PlaceNsArgs a{};
+  a.nodes = d_nodes;
+  a.reqs = d_reqs;
+  a.occupancy = d_occupancy;
+  a.out = d_out;
+  a.dom_first = d_dom_first;
+  a.node_order = d_node_order;
+  a.g_words = reinterpret_cast<uint32_t*>(base + l.words);
+  a.g_dom_free = reinterpret_cast<uint32_t*>(base + l.dom_free);
+  a.ns_first = reinterpret_cast<uint32_t*>(base + l.ns_first);
+  a.unpinned = reinterpret_cast<uint32_t*>(base + l.unpinned);
+  a.counters = reinterpret_cast<uint32_t*>(base + l.counters) + (call_index & 1u) * 8u;
+  a.next_counters = reinterpret_cast<uint32_t*>(base + l.counters) + ((call_index + 1u) & 1u) * 8u;
+  a.n_nodes = n_nodes;
+  a.n_usable = n_usable;
+  a.n_domains = n_domains;
+  a.n_reqs = n_reqs;
+  a.n_namespaces = n_namespaces;
+  a.n_parts = d_occupancy ? (n_parts ? n_parts : 1u) : 0u;
+  a.part_stride_bytes = part_stride_bytes;
+  a.word_rows = l.word_rows;
+  a.scan = scan ? 1u : 0u;
+  if (d_counters_out) *d_counters_out = a.counters;
+
+  // does the word table fit next to the holder table?  (227 KB of shared memory per CTA)
+  const size_t with_words = ns_smem_bytes(l.word_rows, n_domains, true);
+  a.stage_words = with_words <= 200u * 1024u ? 1u : 0u;
+  const size_t smem = a.stage_words ? with_words : ns_smem_bytes(l.word_rows, n_domains, false);
+  // the tensor map of the word table: re-encoded when the scratch moved
+  static thread_local CUtensorMap map;
+  static thread_local void* map_for = nullptr;
+  static thread_local uint32_t map_rows = 0;
+  static thread_local bool map_ok = false;
+  if (a.stage_words && (map_for != a.g_words || map_rows != l.word_rows)) {
+    map_ok = encode_words_map(&map, a.g_words, l.word_rows);
+    map_for = a.g_words;
+    map_rows = l.word_rows;
+  }
+  static const bool no_tensor_map = [] {
+    const char* v = getenv("LWSE_PLACE_NO_TENSOR_MAP");
+    return v && atoi(v) != 0;
+  }();
+  a.use_tensor_map = (a.stage_words && map_ok && !no_tensor_map) ? 1u : 0u;
+
+  {  // condense: a warp per domain, a thread per request
+    uint64_t threads = (uint64_t)n_domains * 32u;
+    if (threads < n_reqs) threads = n_reqs;
+    uint64_t grid = (threads + 255) / 256;
+    if (grid < 1) grid = 1;
+    if (grid > (uint64_t)sm_count * 8u) grid = (uint64_t)sm_count * 8u;
+    e = launch_pdl(place_condense_kernel, dim3((unsigned)grid), dim3(256), 0, s, first_pdl, a);
+    if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
+  }
+  {
+    unsigned grid = n_namespaces < (unsigned)sm_count * 2u ? n_namespaces : (unsigned)sm_count * 2u;
+    if (grid < 1u) grid = 1u;
+    auto kern = scan ? place_ns_kernel<true> : place_ns_kernel<false>;
+    static thread_local size_t attr_set[2] = {0, 0};
+    if (smem > attr_set[scan ? 1 : 0]) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
+      attr_set[scan ? 1 : 0] = smem;
+    }
+    e = launch_pdl(kern, dim3(grid), dim3(kNsThreads), smem, s, true, a, map);
+    if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
+  }
+  return 2;
+}
+
+}  // namespace lwse

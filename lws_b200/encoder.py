@@ -490,4 +490,11 @@ def encode_place_requests(lws: np.ndarray, groups: np.ndarray, ns_of_lws: Option
     reqs["ns"] = 0 if ns_of_lws is None else ns_of_lws[o]
     reqs["size"] = lws["size"][o]
     reqs["leader_node"] = groups["leader_node"][sel]
+    if ns_of_lws is not None and len(reqs):
+        # grouped by namespace (stable: group order inside a namespace): the namespaces are independent
+        # sub-problems and the engine gives each its own CTA when the table is laid out this way
+        order = np.argsort(reqs["ns"], kind="stable")
+        grouped = R.aligned_empty(len(reqs), R.PLACE_REQ)
+        grouped[:] = reqs[order]
+        reqs = grouped
     return reqs

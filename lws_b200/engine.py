@@ -47,6 +47,11 @@ SYMBOLS = {
         [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p],
         C.c_int,
     ),
+    "lwse_place_grouped_device": (
+        [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
+         C.POINTER(C.c_uint32), C.c_void_p],
+        C.c_int,
+    ),
     "lwse_place_gathered_device": (
         [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p,
          C.POINTER(C.c_uint32), C.c_void_p],
@@ -375,6 +380,15 @@ class Engine:
                                     R.ptr(d_out), C.byref(rounds) if want_rounds else None, stream)
         )
         return rounds.value if want_rounds else None
+
+    def place_grouped_device(self, d_reqs, n_reqs, d_occupancy, n_namespaces, d_out, flags=0, stream=None, want_rounds=False):
+        """Placement round over a request table grouped by namespace (one CTA per namespace; flags:
+        SWEEP_PLACE_SCAN = brute-force (request x node) form).  → (rounds, scans) when ``want_rounds``."""
+        rounds, scans = C.c_uint32(0), C.c_uint32(0)
+        self._check(lib().lwse_place_grouped_device(self._h, R.ptr(d_reqs), n_reqs, R.ptr(d_occupancy), n_namespaces,
+                                                    R.ptr(d_out), flags, C.byref(rounds) if want_rounds else None,
+                                                    C.byref(scans) if want_rounds else None, stream))
+        return (rounds.value, scans.value) if want_rounds else None
 
     def place_gathered_device(self, d_parts, n_parts, part_stride_bytes, reqs_offset_bytes, reqs_per_part,
                               n_namespaces, d_out, stream=None, want_rounds=False):

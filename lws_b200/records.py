@@ -195,6 +195,8 @@ SWEEP_SKIP_GROUP_PASS = 1 << 1
 SWEEP_SKIP_LWS_PASS = 1 << 2
 SWEEP_SKIP_POD_SCAN = 1 << 3
 SWEEP_REUSE_POD_IDENT = 1 << 4
+SWEEP_PLACE_GROUPED = 1 << 5
+SWEEP_PLACE_SCAN = 1 << 6
 
 # --------------------------------------------------------------------------- #
 # placement

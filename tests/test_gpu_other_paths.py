@@ -59,6 +59,57 @@ def test_placement_matches_spec_oracle(engine, kw):
         assert rounds >= 1
 
 
+@pytest.mark.parametrize(
+    "kw,n_ns",
+    [(dict(n_lws=300, n_nodes=3200, size=16, p_excl=0.6, p_unsched=0.5, seed=21), 1),
+     (dict(n_lws=3000, n_nodes=10000, size=64, p_excl=1.0, p_unsched=0.3, seed=22), 7),
+     (dict(n_lws=900, n_nodes=640, size=8, p_excl=0.9, p_unsched=0.7, seed=23), 3),  # heavy contention, many rounds
+     (dict(n_lws=400, n_nodes=4096, size=4, p_excl=0.7, p_unsched=0.5, seed=24, fuzz=True), 5),
+     (dict(n_lws=50, n_nodes=60000, size=8, p_excl=1.0, p_unsched=0.5, seed=25, nodes_per_domain=100), 2),  # table not staged
+     (dict(n_lws=700, n_nodes=3000, size=2, p_excl=1.0, p_unsched=0.6, seed=26, nodes_per_domain=1, capacity=2), 4),  # hostname topology
+     (dict(n_lws=64, n_nodes=48, size=2, p_excl=1.0, p_unsched=1.0, seed=27, nodes_per_domain=2, capacity=1), 300)],  # mostly empty namespaces
+)
+def test_placement_forms_agree(engine, kw, n_ns):
+    """The three forms of the round — general (one warp per request over the whole grid, holders in
+    L2), namespace-parallel (one CTA per namespace, holders + TMA-staged node table in shared memory)
+    and its brute-force (request x node) scan — give the spec oracle's rows on tables grouped by
+    namespace, including an out-of-range namespace at the end."""
+    import torch
+
+    import oracle
+
+    t, reqs = place_case(**kw)
+    rng = np.random.default_rng(kw["seed"])
+    ns = np.sort(rng.integers(0, n_ns, size=len(reqs))).astype(np.uint32)
+    ns[-3:] = n_ns + 2  # no such namespace
+    reqs["ns"] = ns
+    engine.upload_nodes(t.nodes, t.n_domains)
+    occ = R.occupancy_of(t.pod_ident, len(t.nodes)) // 4
+    want = oracle.place(t.nodes, occ, t.n_domains, n_ns, reqs)
+    dev = torch.device("cuda:0")
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+    d_reqs, d_occ = up(reqs), up(occ)
+    d_out = torch.zeros(len(reqs) * R.PLACE_OUT.itemsize, dtype=torch.uint8, device=dev)
+
+    def rows():
+        torch.cuda.synchronize()
+        return d_out.cpu().numpy().view(R.PLACE_OUT).copy()
+
+    rounds = engine.place_device(d_reqs, len(reqs), d_occ, n_ns, d_out, want_rounds=True)
+    same(rows(), want, "general")
+    for flags, name in ((0, "grouped"), (R.SWEEP_PLACE_SCAN, "scan")):
+        d_out.zero_()
+        r2, scans = engine.place_grouped_device(d_reqs, len(reqs), d_occ, n_ns, d_out, flags=flags, want_rounds=True)
+        same(rows(), want, name)
+        live = int(((reqs["leader_node"] == R.NONE) & (reqs["size"] >= 1) & (reqs["ns"] < n_ns)).sum())
+        assert (r2 >= 1 and scans >= live) if live else (r2 == 0 and scans == 0)
+        assert rounds >= 1 or not live
+    # twice in a row (the scratch is reused, counters alternate)
+    d_out.zero_()
+    engine.place_grouped_device(d_reqs, len(reqs), d_occ, n_ns, d_out)
+    same(rows(), want, "grouped, second call")
+
+
 def test_placement_namespaces_and_empty(engine):
     import oracle
 
