@@ -43,6 +43,8 @@ CONSTS = {
     "leaderworkerset.SizeAnnotationKey": "leaderworkerset.sigs.k8s.io/size",
     "leaderworkerset.LeaderPodNameAnnotationKey": "leaderworkerset.sigs.k8s.io/leader-name",
     "leaderworkerset.ReplicasAnnotationKey": "leaderworkerset.sigs.k8s.io/replicas",
+    "leaderworkerset.SubGroupPolicyTypeAnnotationKey": "leaderworkerset.sigs.k8s.io/subgroup-policy-type",
+    "corev1.PersistentVolumeFilesystem": "Filesystem",
     "leaderworkerset.RollingUpdateStrategyType": "RollingUpdate",
     "leaderworkerset.RecreateGroupOnPodRestart": "RecreateGroupOnPodRestart",
     "leaderworkerset.SubGroupPolicyTypeLeaderWorker": "LeaderWorker",
