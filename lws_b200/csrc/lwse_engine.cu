@@ -41,6 +41,8 @@ struct ScatterSegHost {
 };
 int launch_scatter(const ScatterSegHost* segs, int n_segs, uint32_t* d_occupancy, uint32_t n_nodes, cudaStream_t s,
                    bool pdl, int* cuda_err);
+int launch_ident_prefetch(const uint8_t* d_state, uint64_t n_pods, const lwse_pod_ident* mapped_host_ident,
+                          lwse_pod_ident* d_ident, int sm_count, cudaStream_t s, int* cuda_err);
 int launch_occupancy(const lwse_pod_ident* d_ident, uint64_t n_pods, uint32_t* d_occupancy, uint32_t n_nodes, int sm_count,
                      cudaStream_t s, int* cuda_err);
 // lwse_place_kernels.cu
@@ -413,7 +415,11 @@ LWSE_API int lwse_upload_nodes(lwse_engine* e, const lwse_node_rec* nodes, uint3
       }
   }
   LWSE_CUDA(e, e->dom_first.reserve(((size_t)n_domains + 1) * 4 + 16));
-  LWSE_CUDA(e, e->node_order.reserve(order.size() * 4 + 16));
+  // (padded to whole rows of 256 entries: the namespace-parallel placement kernel stages the index
+  // into shared memory with one bulk copy of that size)
+  const size_t order_padded = ((size_t)(n_nodes + 255u) / 256u + 1u) * 1024u;
+  LWSE_CUDA(e, e->node_order.reserve(order_padded + 16));
+  LWSE_CUDA(e, cudaMemsetAsync(e->node_order.p, 0, order_padded, e->stream));
   LWSE_CUDA(e, e->node_pos.reserve(pos.size() * 4 + 16));
   if (n_nodes)
     LWSE_CUDA(e, cudaMemcpyAsync(e->nodes.p, nodes, (size_t)n_nodes * sizeof(lwse_node_rec),
@@ -478,10 +484,8 @@ static int sweep_host_locked(lwse_engine* e, const lwse_lws_tables* h) {
   if (want_occ) {
     LWSE_CUDA(e, e->occupancy.reserve((size_t)e->n_nodes * 4 + 16));
   }
-  // the hot byte column first: it is what the sweep's first kernel streams
+  // the hot byte column first: the identity prefetch below needs only it
   if (b_pst) LWSE_CUDA(e, cudaMemcpyAsync(e->pod_state.p, h->pod_state, b_pst, cudaMemcpyHostToDevice, s));
-  if (b_grp) LWSE_CUDA(e, cudaMemcpyAsync(e->groups.p, h->groups, b_grp, cudaMemcpyHostToDevice, s));
-  if (b_lws) LWSE_CUDA(e, cudaMemcpyAsync(e->lws.p, h->lws, b_lws, cudaMemcpyHostToDevice, s));
   lwse_lws_tables d = *h;
   d.lws = (const lwse_lws_rec*)e->lws.p;
   d.groups = (const lwse_group_rec*)e->groups.p;
@@ -491,15 +495,16 @@ static int sweep_host_locked(lwse_engine* e, const lwse_lws_tables* h) {
   d.group_out = (lwse_group_out*)e->group_out.p;
   d.node_occupancy = want_occ ? (uint32_t*)e->occupancy.p : nullptr;
   int cuda_err = 0;
-  bool counted = false;
+  bool counted = false, prefetching = false;
   if (b_pst) {
     // The identity column (16 B / pod, 16 of the 17 input bytes per pod) is only read for pods
     // with a restart / deletion event.  It is left out of the upload
     //  - when the caller says it did not change (LWSE_SWEEP_REUSE_POD_IDENT), or
-    //  - when the caller's buffer is pinned, mapped host memory and few pods have an event: the
-    //    group pass then reads those rows in place over PCIe (a 64-byte read per visited pod
-    //    against 16 B / pod in bulk).  "Few" is what the PREVIOUS sweep of a table of this size
-    //    visited (no mid-step synchronize; the first sweep of a table is optimistic).
+    //  - when the caller's buffer is pinned, mapped host memory and few pods have an event: a
+    //    prefetch kernel on the side stream copies just those rows over PCIe while the other
+    //    tables are still being uploaded (a 64-byte read per event pod against 16 B / pod in
+    //    bulk).  "Few" is what the PREVIOUS sweep of a table of this size visited (no mid-step
+    //    synchronize; the first sweep of a table is optimistic).
     const bool reuse = (h->flags & LWSE_SWEEP_REUSE_POD_IDENT) && e->ident_rows == h->n_pods && !ident_moved;
     const void* mapped = nullptr;
     if (!reuse && !e->no_zero_copy && !want_occ) {
@@ -511,8 +516,15 @@ static int sweep_host_locked(lwse_engine* e, const lwse_lws_tables* h) {
     }
     const bool few = e->ident_hint_pods != h->n_pods || (uint64_t)e->ident_hint_events * 64u <= b_pid / 2u;
     if (mapped && few && h->n_groups && !(h->flags & (LWSE_SWEEP_SKIP_POD_SCAN | LWSE_SWEEP_SKIP_GROUP_PASS))) {
-      d.pod_ident = (const lwse_pod_ident*)mapped;
-      e->ident_rows = ~0ull;  // the device copy is stale now
+      LWSE_CUDA(e, cudaEventRecord(e->ev_fork, s));
+      LWSE_CUDA(e, cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+      int launched = lwse::launch_ident_prefetch((const uint8_t*)e->pod_state.p, h->n_pods, (const lwse_pod_ident*)mapped,
+                                                 (lwse_pod_ident*)e->pod_ident.p, e->sm_count, e->side_stream, &cuda_err);
+      if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+      e->launches += (uint64_t)launched;
+      LWSE_CUDA(e, cudaEventRecord(e->ev_join, e->side_stream));
+      prefetching = true;
+      e->ident_rows = ~0ull;  // the device copy holds the event pods' rows only
     } else {
       if (!reuse) LWSE_CUDA(e, cudaMemcpyAsync(e->pod_ident.p, h->pod_ident, b_pid, cudaMemcpyHostToDevice, s));
       e->ident_rows = h->n_pods;
@@ -520,6 +532,9 @@ static int sweep_host_locked(lwse_engine* e, const lwse_lws_tables* h) {
     counted = h->n_groups && !(h->flags & (LWSE_SWEEP_SKIP_POD_SCAN | LWSE_SWEEP_SKIP_GROUP_PASS));
     if (counted) LWSE_CUDA(e, cudaMemsetAsync(e->h_counts_dev.p, 0, 4, s));
   }
+  if (b_grp) LWSE_CUDA(e, cudaMemcpyAsync(e->groups.p, h->groups, b_grp, cudaMemcpyHostToDevice, s));
+  if (b_lws) LWSE_CUDA(e, cudaMemcpyAsync(e->lws.p, h->lws, b_lws, cudaMemcpyHostToDevice, s));
+  if (prefetching) LWSE_CUDA(e, cudaStreamWaitEvent(s, e->ev_join, 0));
   int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes, e->scan_scratch.p, e->sm_count,
                                         s, &cuda_err, nullptr, counted ? (uint32_t*)e->h_counts_dev.p : nullptr,
                                         /*first_pdl=*/false);
@@ -640,6 +655,17 @@ static bool resident_table(lwse_engine* e, uint32_t which, void** base, uint64_t
   }
 }
 
+// A segment's rows / values are read by the scatter kernel where the caller wrote them when they
+// lie in the arena and are aligned for its vector loads (16-byte row-number reads; 16-byte value
+// reads, 4-byte for the byte column); otherwise the call stages a copy.
+static bool rows_in_place(const lwse_engine* e, const lwse_patch_seg& g) {
+  return e->arena.holds(g.rows, (size_t)g.n * 4) && aligned16(g.rows);
+}
+static bool values_in_place(const lwse_engine* e, const lwse_patch_seg& g, uint32_t rb) {
+  return e->arena.holds(g.values, (size_t)g.n * rb) &&
+         (rb == 1 ? (reinterpret_cast<uintptr_t>(g.values) & 3u) == 0 : aligned16(g.values));
+}
+
 // Enqueue the patch segments of a tick on the engine's stream.  *wrote = some table changed
 // (the sweep's first kernel then has to wait for the scatter kernel to finish).
 // `tables`: bit t set = apply the segments of lwse_table t (a tick applies the placement request
@@ -666,9 +692,8 @@ static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint
       if ((uint64_t)segs[i].first_row + segs[i].n > rows) return LWSE_ERR_BAD_TABLE;
       continue;
     }
-    if (!e->arena.holds(segs[i].rows, (size_t)segs[i].n * 4)) need += align256((size_t)segs[i].n * 4);
-    if (!e->arena.holds(segs[i].values, (size_t)segs[i].n * rb) || (rb > 1 && !aligned16(segs[i].values)))
-      need += align256((size_t)segs[i].n * rb);
+    if (!rows_in_place(e, segs[i])) need += align256((size_t)segs[i].n * 4);
+    if (!values_in_place(e, segs[i], rb)) need += align256((size_t)segs[i].n * rb);
   }
   if (stage_base + need > e->stage.cap) {
     if (stage_base) return LWSE_ERR_OOM;  // (the tick sizes the buffer for both of its calls up front)
@@ -713,7 +738,7 @@ static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint
     }
     const uint32_t* d_rows;
     const void* d_vals;
-    if (e->arena.holds(g.rows, (size_t)g.n * 4)) {
+    if (rows_in_place(e, g)) {
       d_rows = e->arena.dev_of(g.rows);
     } else {
       uint8_t* dst = static_cast<uint8_t*>(e->stage.h) + cursor;
@@ -721,7 +746,7 @@ static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint
       d_rows = reinterpret_cast<const uint32_t*>(static_cast<uint8_t*>(e->stage.d) + cursor);
       cursor += align256((size_t)g.n * 4);
     }
-    if (e->arena.holds(g.values, (size_t)g.n * rb) && (rb == 1 || aligned16(g.values))) {
+    if (values_in_place(e, g, rb)) {
       d_vals = e->arena.dev_of(static_cast<const uint8_t*>(g.values));
     } else {
       uint8_t* dst = static_cast<uint8_t*>(e->stage.h) + cursor;
@@ -1242,7 +1267,7 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
       bool all_in_arena = true;
       for (uint32_t i = 0; i < n_segs; i++)
         if (segs[i].n && !(segs[i].flags & LWSE_PATCH_RANGE) &&
-            (!e->arena.holds(segs[i].rows, (size_t)segs[i].n * 4) || !e->arena.holds(segs[i].values, 1)))
+            (!rows_in_place(e, segs[i]) || !e->arena.holds(segs[i].values, 1)))
           all_in_arena = false;
       if (!all_in_arena) {
         LWSE_CUDA(e, cudaStreamSynchronize(s));

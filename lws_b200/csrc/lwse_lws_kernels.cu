@@ -135,6 +135,43 @@ __global__ void __launch_bounds__(256) pod_occupancy_kernel(const lwse_pod_ident
   }
 }
 
+// The host entry point with a pinned, mapped identity column: only pods with an event bit ever
+// need their identity row.  This kernel streams the (already uploaded) state bytes and copies
+// exactly those rows host -> device, on a side stream, WHILE the group and LWS tables are still
+// crossing PCIe — the latency-bound gather hides behind the bandwidth-bound copies.
+__global__ void __launch_bounds__(256) ident_prefetch_kernel(const uint8_t* __restrict__ state, uint64_t n_pods,
+                                                             const lwse_pod_ident* __restrict__ host_ident,
+                                                             lwse_pod_ident* __restrict__ dev_ident) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warp = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5), n_warps = (uint64_t)gridDim.x * 8u;
+  for (uint64_t base = warp * 512u; base < n_pods; base += n_warps * 512u) {
+    const uint64_t idx = base + lane * 16u;
+    if (idx >= n_pods) continue;
+    uint32_t pend, ev;
+    pod16_predicates(load_pods16(state, idx, n_pods), pend, ev);
+    while (ev) {
+      const uint64_t p = idx + (__ffs(ev) - 1u);
+      ev &= ev - 1u;
+      if (p < n_pods) stg_stream(dev_ident + p, ldg_stream(host_ident + p));
+    }
+  }
+}
+
+int launch_ident_prefetch(const uint8_t* d_state, uint64_t n_pods, const lwse_pod_ident* mapped_host_ident,
+                          lwse_pod_ident* d_ident, int sm_count, cudaStream_t s, int* cuda_err) {
+  *cuda_err = 0;
+  if (n_pods == 0) return 0;
+  const uint64_t want = (n_pods + 4095u) / 4096u;
+  const uint32_t cap = (uint32_t)sm_count * 8u;
+  ident_prefetch_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(d_state, n_pods, mapped_host_ident, d_ident);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    *cuda_err = (int)e;
+    return -1;
+  }
+  return 1;
+}
+
 // --------------------------------------------------------------------------
 // group pass
 // --------------------------------------------------------------------------
@@ -1111,7 +1148,7 @@ struct ScatterSeg {
   uint64_t table_rows;
   uint32_t n;
   uint32_t row_bytes;   // 1, 16 (identity), 32 (placement request), 64
-  uint32_t work_begin;  // first work item of this segment (16-byte pieces, or rows for 1-byte rows)
+  uint32_t work_begin;  // first work item of this segment (16-byte pieces, or groups of four 1-byte rows)
   uint32_t is_ident;
 };
 constexpr int kMaxScatterSegs = 8;
@@ -1134,8 +1171,23 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const __grid_constant
     const ScatterSeg& sg = a.seg[k];
     const uint32_t j = i - sg.work_begin;
     if (sg.row_bytes == 1u) {
-      const uint32_t r = sg.rows[j];
-      if (r < sg.table_rows) static_cast<uint8_t*>(sg.table)[r] = static_cast<const uint8_t*>(sg.values)[j];
+      // four patches per thread: one 16-byte read of row numbers and one 4-byte read of values —
+      // over PCIe (the arena is host memory) the number of read requests is what costs, not the bytes
+      const uint32_t k0 = j * 4u;
+      uint8_t* tb = static_cast<uint8_t*>(sg.table);
+      if (k0 + 3u < sg.n) {
+        const uint4 r4 = *reinterpret_cast<const uint4*>(sg.rows + k0);
+        const uint32_t v4 = *reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(sg.values) + k0);
+        if (r4.x < sg.table_rows) tb[r4.x] = (uint8_t)v4;
+        if (r4.y < sg.table_rows) tb[r4.y] = (uint8_t)(v4 >> 8);
+        if (r4.z < sg.table_rows) tb[r4.z] = (uint8_t)(v4 >> 16);
+        if (r4.w < sg.table_rows) tb[r4.w] = (uint8_t)(v4 >> 24);
+      } else {
+        for (uint32_t k = k0; k < sg.n; k++) {
+          const uint32_t r = sg.rows[k];
+          if (r < sg.table_rows) tb[r] = static_cast<const uint8_t*>(sg.values)[k];
+        }
+      }
     } else {
       const uint32_t pieces = sg.row_bytes >> 4;
       const uint32_t row_i = j / pieces, piece = j - row_i * pieces;
@@ -1181,7 +1233,7 @@ int launch_scatter(const ScatterSegHost* segs, int n_segs, uint32_t* d_occupancy
     }
     a.seg[k] = ScatterSeg{segs[i].table, segs[i].rows, segs[i].values, segs[i].table_rows, segs[i].n,
                           segs[i].row_bytes, (uint32_t)work, segs[i].is_ident ? 1u : 0u};
-    work += (uint64_t)segs[i].n * (segs[i].row_bytes == 1u ? 1u : segs[i].row_bytes >> 4);
+    work += segs[i].row_bytes == 1u ? ((uint64_t)segs[i].n + 3u) / 4u : (uint64_t)segs[i].n * (segs[i].row_bytes >> 4);
     k++;
   }
   if (k == 0) return 0;

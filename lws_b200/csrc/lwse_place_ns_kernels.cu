@@ -135,24 +135,52 @@ __global__ void __launch_bounds__(256) place_condense_kernel(const PlaceNsArgs a
 // --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-constexpr uint32_t kNsThreads = 512;
+constexpr uint32_t kNsThreads = 256;  // two CTAs share an SM (one wave for a few hundred namespaces)
+constexpr uint32_t kNsKeep = 4;       // requests per thread kept in registers between the claim and the result pass
+constexpr uint32_t kNsCache = 256;    // unpinned requests of a namespace whose state lives in shared memory
+
+// An unpinned request across the rounds (shared memory; written by the one warp that owns it).
+struct NsReq {
+  unsigned long long key;
+  uint32_t r, key_lo, key_hi, size, cur_dom, dead;
+};
+
+__device__ __forceinline__ void mbar_wait(unsigned long long* mbar) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(mbar)) : "memory");
+}
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(mbar))
+               : "memory");
+}
 
 template <bool kScan>
-__global__ void __launch_bounds__(kNsThreads, 1)
+__global__ void __launch_bounds__(kNsThreads, 2)
     place_ns_kernel(const PlaceNsArgs a, const __grid_constant__ CUtensorMap words_map) {
   extern __shared__ uint8_t s_dyn[];
-  // layout (from a 128-byte aligned base: the TMA destination): [words: word_rows x 256 u32]
-  //         [dom_free: n_domains u32, 16-byte padded] [holder: n_domains u64] [mbarrier]
+  // layout (from a 128-byte aligned base: the TMA destination):
+  //   [words: word_rows x 256 u32] [node order: word_rows x 256 u32]      (staged when they fit)
+  //   [dom_free: n_domains u32] [dom_first: n_domains + 1 u32] [holder: n_domains u64]
+  //   [request cache: kNsCache x 32 B] [mbarrier]
   uint8_t* s_raw = s_dyn + ((128u - (smem_u32(s_dyn) & 127u)) & 127u);
-  const uint32_t words_bytes = a.stage_words ? a.word_rows * 1024u : 0u;
+  const uint32_t table_bytes = a.stage_words ? a.word_rows * 1024u : 0u;
   const uint32_t free_bytes = ((a.n_domains * 4u) + 15u) & ~15u;
+  const uint32_t first_bytes = (((a.n_domains + 1u) * 4u) + 15u) & ~15u;
   uint32_t* s_words = reinterpret_cast<uint32_t*>(s_raw);
-  uint32_t* s_free = reinterpret_cast<uint32_t*>(s_raw + words_bytes);
-  unsigned long long* s_hold = reinterpret_cast<unsigned long long*>(s_raw + words_bytes + free_bytes);
-  unsigned long long* s_mbar = s_hold + a.n_domains;
+  uint32_t* s_order = reinterpret_cast<uint32_t*>(s_raw + table_bytes);
+  uint32_t* s_free = reinterpret_cast<uint32_t*>(s_raw + 2u * table_bytes);
+  uint32_t* s_first = reinterpret_cast<uint32_t*>(s_raw + 2u * table_bytes + free_bytes);
+  unsigned long long* s_hold = reinterpret_cast<unsigned long long*>(s_raw + 2u * table_bytes + free_bytes + first_bytes);
+  NsReq* s_req = reinterpret_cast<NsReq*>(s_hold + a.n_domains);
+  unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_req + kNsCache);
   __shared__ uint32_t s_n_unp, s_unsettled[3];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, n_warps = blockDim.x >> 5;
   const uint32_t* words = a.stage_words ? s_words : a.g_words;
+  const uint32_t* order = a.stage_words ? s_order : a.node_order;
 
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_mbar)));
@@ -163,9 +191,11 @@ __global__ void __launch_bounds__(kNsThreads, 1)
   // on SMs the concurrent sweep wants; it still launches ahead and starts the moment this grid ends)
   pdl_wait_prior();  // the condense kernel's tables (and the request table a tick's scatter patched)
   if (tid == 0) {
-    // TMA: the node-word table (a 2D tensor of 256-word rows) and the capacity vector land in shared
-    // memory while the other threads clear the holder table; one mbarrier collects the bytes
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(s_mbar)), "r"(words_bytes + free_bytes)
+    // TMA: the node-word table (a 2D tensor of 256-word rows), the node order, the capacity vector
+    // and the domain index land in shared memory while the other threads clear the holder table
+    // and take the pinned claims; one mbarrier collects the bytes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(s_mbar)),
+                 "r"(2u * table_bytes + free_bytes + first_bytes)
                  : "memory");
     if (a.stage_words) {
       if (a.use_tensor_map) {
@@ -174,14 +204,12 @@ __global__ void __launch_bounds__(kNsThreads, 1)
                      "l"(&words_map), "r"(smem_u32(s_mbar)), "r"(0), "r"(0)
                      : "memory");
       } else {
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_words)),
-                     "l"(a.g_words), "r"(words_bytes), "r"(smem_u32(s_mbar))
-                     : "memory");
+        bulk_load(s_words, a.g_words, table_bytes, s_mbar);
       }
+      bulk_load(s_order, a.node_order, table_bytes, s_mbar);
     }
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_free)),
-                 "l"(a.g_dom_free), "r"(free_bytes), "r"(smem_u32(s_mbar))
-                 : "memory");
+    bulk_load(s_free, a.g_dom_free, free_bytes, s_mbar);
+    bulk_load(s_first, a.dom_first, first_bytes, s_mbar);
   }
   bool staged = false;
 
@@ -196,35 +224,75 @@ __global__ void __launch_bounds__(kNsThreads, 1)
     if (first >= last) continue;  // CTA-uniform
 
     // ---- phase 1: pinned claims, the list of live unpinned requests ----
-    for (uint32_t r = first + tid; r < last; r += blockDim.x) {
-      const uint4 lo = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r)), hi = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r) + 1);
+    // the first kNsKeep requests of a thread stay in registers until their result is written
+    uint4 k_lo[kNsKeep], k_hi[kNsKeep];
+    uint32_t k_dom[kNsKeep];
+#pragma unroll
+    for (uint32_t j = 0; j < kNsKeep; j++) {  // all request loads of the thread in flight together
+      const uint32_t r = first + tid + j * kNsThreads;
+      if (r < last) {
+        k_lo[j] = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r));
+        k_hi[j] = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r) + 1);
+      }
+    }
+    auto claim = [&](uint32_t r, const uint4 lo, const uint4 hi) -> uint32_t {
       const uint32_t leader = hi.w;
+      uint32_t d = LWSE_NONE;
       if (leader == LWSE_NONE) {
         const bool dead = (int32_t)hi.z < 1;
         store_row(a.out + r, LWSE_NONE, LWSE_NONE, dead ? LWSE_PLACE_UNSCHEDULABLE : 0u, 0u);
-        if (!dead) a.unpinned[first + atomicAdd(&s_n_unp, 1u)] = r;
+        if (!dead) {
+          const uint32_t k = atomicAdd(&s_n_unp, 1u);
+          a.unpinned[first + k] = r;
+          if (k < kNsCache) {
+            NsReq q;
+            q.key = ns_place_key(u64_of(lo.x, lo.y), r, false);
+            q.r = r;
+            q.key_lo = lo.z;
+            q.key_hi = lo.w;
+            q.size = hi.z;
+            q.cur_dom = LWSE_NONE;
+            q.dead = 0u;
+            s_req[k] = q;
+          }
+        }
       } else {
-        uint32_t d = LWSE_NONE;
         if (leader < a.n_nodes) {
           const uint4 nr = ldg_keep(reinterpret_cast<const uint4*>(a.nodes + leader));
           if (((nr.w >> 16) & LWSE_NODE_HAS_TOPOLOGY) && nr.z < a.n_domains) d = nr.z;
         }
         if (d != LWSE_NONE) atomicMin(s_hold + d, ns_place_key(u64_of(lo.x, lo.y), r, true));
       }
+      return d;
+    };
+    auto result = [&](uint32_t r, const uint4 lo, const uint4 hi, uint32_t d) {
+      if (hi.w == LWSE_NONE) return;
+      uint32_t flags = LWSE_PLACE_PINNED;
+      if (d != LWSE_NONE) flags |= s_hold[d] == ns_place_key(u64_of(lo.x, lo.y), r, true) ? LWSE_PLACE_PLACED : LWSE_PLACE_CONFLICT;
+      store_row(a.out + r, d, hi.w, flags, 0u);
+    };
+#pragma unroll
+    for (uint32_t j = 0; j < kNsKeep; j++) {
+      const uint32_t r = first + tid + j * kNsThreads;
+      if (r < last) k_dom[j] = claim(r, k_lo[j], k_hi[j]);
     }
+    for (uint32_t r = first + tid + kNsKeep * kNsThreads; r < last; r += kNsThreads)  // big namespaces: the rest, unkept
+      claim(r, ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r)), ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r) + 1));
     __syncthreads();
     // results of the pinned requests: final from here on (pinned keys are below every unpinned key)
-    for (uint32_t r = first + tid; r < last; r += blockDim.x) {
+#pragma unroll
+    for (uint32_t j = 0; j < kNsKeep; j++) {
+      const uint32_t r = first + tid + j * kNsThreads;
+      if (r < last) result(r, k_lo[j], k_hi[j], k_dom[j]);
+    }
+    for (uint32_t r = first + tid + kNsKeep * kNsThreads; r < last; r += kNsThreads) {
       const uint4 lo = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r)), hi = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r) + 1);
-      const uint32_t leader = hi.w;
-      if (leader == LWSE_NONE) continue;
-      uint32_t d = LWSE_NONE, flags = LWSE_PLACE_PINNED;
-      if (leader < a.n_nodes) {
-        const uint4 nr = ldg_keep(reinterpret_cast<const uint4*>(a.nodes + leader));
+      uint32_t d = LWSE_NONE;
+      if (hi.w != LWSE_NONE && hi.w < a.n_nodes) {
+        const uint4 nr = ldg_keep(reinterpret_cast<const uint4*>(a.nodes + hi.w));
         if (((nr.w >> 16) & LWSE_NODE_HAS_TOPOLOGY) && nr.z < a.n_domains) d = nr.z;
       }
-      if (d != LWSE_NONE) flags |= s_hold[d] == ns_place_key(u64_of(lo.x, lo.y), r, true) ? LWSE_PLACE_PLACED : LWSE_PLACE_CONFLICT;
-      store_row(a.out + r, d, leader, flags, 0u);
+      result(r, lo, hi, d);
     }
     const uint32_t n_unp = s_n_unp;
     if (n_unp == 0u) {
@@ -233,10 +301,7 @@ __global__ void __launch_bounds__(kNsThreads, 1)
     }
     if (tid == 0) atomicAdd(a.counters + 1, n_unp);
     if (!staged) {  // the first namespace with work waits for the staged tables
-      uint32_t done = 0;
-      while (!done)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(smem_u32(s_mbar)) : "memory");
+      mbar_wait(s_mbar);
       staged = true;
     }
 
@@ -249,13 +314,26 @@ __global__ void __launch_bounds__(kNsThreads, 1)
       if (tid == 0) s_unsettled[(round + 1u) % 3u] = 0u;
       uint32_t scans = 0;
       for (uint32_t k = warp; k < n_unp; k += n_warps) {
-        const uint32_t r = __ldcg(a.unpinned + first + k);
-        const uint4 o = __ldcg(reinterpret_cast<const uint4*>(a.out + r));  // state: written by this warp only
-        if (o.z & LWSE_PLACE_UNSCHEDULABLE) continue;  // warp-uniform
-        const uint4 lo = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r)), hi = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r) + 1);
-        const unsigned long long key = ns_place_key(u64_of(lo.x, lo.y), r, false);
-        const uint32_t key_lo = lo.z, key_hi = lo.w, size = hi.z;
-        if (o.x != LWSE_NONE && s_hold[o.x] == key) continue;  // still holds what it proposed to
+        NsReq q;
+        const bool cached = k < kNsCache;
+        if (cached) {
+          q = s_req[k];
+        } else {  // overflow: the state lives in the result row (written by this warp only)
+          q.r = __ldcg(a.unpinned + first + k);
+          const uint4 o = __ldcg(reinterpret_cast<const uint4*>(a.out + q.r));
+          const uint4 lo = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + q.r)), hi = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + q.r) + 1);
+          q.key = ns_place_key(u64_of(lo.x, lo.y), q.r, false);
+          q.key_lo = lo.z;
+          q.key_hi = lo.w;
+          q.size = hi.z;
+          q.cur_dom = o.x;
+          q.dead = (o.z & LWSE_PLACE_UNSCHEDULABLE) ? 1u : 0u;
+        }
+        __syncwarp();  // every lane has its copy before lane 0 updates the cache entry below
+        if (q.dead) continue;  // warp-uniform
+        const unsigned long long key = q.key;
+        const uint32_t key_lo = q.key_lo, key_hi = q.key_hi, size = q.size, r = q.r;
+        if (q.cur_dom != LWSE_NONE && s_hold[q.cur_dom] == key) continue;  // still holds what it proposed to
         scans++;
         uint32_t H = 0, best_d = LWSE_NONE, best_n = LWSE_NONE;
         if constexpr (!kScan) {
@@ -273,12 +351,12 @@ __global__ void __launch_bounds__(kNsThreads, 1)
           if (H != 0u) {
             best_d = __reduce_min_sync(0xFFFFFFFFu, my_hi == H ? my_d : LWSE_NONE);
             // Level 2 — the node: the domain's run of the sorted words.
-            const uint32_t f2 = ldg_keep_u32(a.dom_first + best_d), l2 = ldg_keep_u32(a.dom_first + best_d + 1u);
+            const uint32_t f2 = s_first[best_d], l2 = s_first[best_d + 1u];
             uint32_t my_lo = 0, my_n = LWSE_NONE;
             for (uint32_t i = f2 + lane; i < l2; i += 32u) {
               const uint32_t w = words[i];
               if ((w >> 28) == 0u) continue;
-              const uint32_t n = ldg_keep_u32(a.node_order + i);
+              const uint32_t n = order[i];
               const uint32_t l = ((w >> 28) << 28) | (mix32n(key_hi ^ (n * 0x85EBCA77u)) >> 4);
               if (l > my_lo || (l == my_lo && n < my_n)) {
                 my_lo = l;
@@ -297,7 +375,7 @@ __global__ void __launch_bounds__(kNsThreads, 1)
             if ((w >> 28) == 0u || s_free[d] < size || s_hold[d] < key) continue;
             const uint32_t h = mix32n(key_lo ^ (d * 0x9E3779B1u)) | 1u;
             if (h < my_hi || (h == my_hi && d > my_d)) continue;
-            const uint32_t n = ldg_keep_u32(a.node_order + i);
+            const uint32_t n = order[i];
             const uint32_t l = ((w >> 28) << 28) | (mix32n(key_hi ^ (n * 0x85EBCA77u)) >> 4);
             const bool better = h > my_hi || d < my_d || l > my_lo || (l == my_lo && n < my_n);
             if (better) {
@@ -318,8 +396,10 @@ __global__ void __launch_bounds__(kNsThreads, 1)
         if (lane == 0) {
           if (H == 0u || best_n == LWSE_NONE) {  // nothing feasible now, and the feasible set only shrinks
             store_row(a.out + r, LWSE_NONE, LWSE_NONE, LWSE_PLACE_UNSCHEDULABLE, 0u);
+            if (cached) s_req[k].dead = 1u;
           } else {
             store_row(a.out + r, best_d, best_n, LWSE_PLACE_PLACED, H);
+            if (cached) s_req[k].cur_dom = best_d;
             // A claim on an empty domain settles at once; any other outcome leaves somebody without
             // a domain who proposes again next round: count it.
             const unsigned long long old = atomicMin(s_hold + best_d, key);
@@ -336,12 +416,7 @@ __global__ void __launch_bounds__(kNsThreads, 1)
     if (tid == 0) atomicMax(a.counters + 0, round + 1u);
     __syncthreads();
   }
-  if (!staged) {  // never leave a bulk copy in flight behind a CTA that exits
-    uint32_t done = 0;
-    while (!done)
-      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                   : "=r"(done) : "r"(smem_u32(s_mbar)) : "memory");
-  }
+  if (!staged) mbar_wait(s_mbar);  // never leave a bulk copy in flight behind a CTA that exits
 }
 
 // --------------------------------------------------------------------------
@@ -378,7 +453,8 @@ size_t place_ns_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_r
 
 // shared memory the namespace kernel needs when it stages the word table / when it does not
 static size_t ns_smem_bytes(uint32_t word_rows, uint32_t n_domains, bool stage) {
-  return (stage ? (size_t)word_rows * 1024 : 0) + (((size_t)n_domains * 4 + 15) & ~(size_t)15) + (size_t)n_domains * 8 + 16 + 128;
+  return (stage ? (size_t)word_rows * 2048 : 0) + (((size_t)n_domains * 4 + 15) & ~(size_t)15) +
+         ((((size_t)n_domains + 1) * 4 + 15) & ~(size_t)15) + (size_t)n_domains * 8 + 256 * 32 + 16 + 128;
 }
 bool place_ns_supported(uint32_t n_nodes, uint32_t n_domains) {
   return ns_smem_bytes((n_nodes + 255u) / 256u, n_domains, false) <= 200u * 1024u && n_domains < (1u << 28);
@@ -450,7 +526,7 @@ int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, c
 
   // does the word table fit next to the holder table?  (227 KB of shared memory per CTA)
   const size_t with_words = ns_smem_bytes(l.word_rows, n_domains, true);
-  a.stage_words = with_words <= 200u * 1024u ? 1u : 0u;
+  a.stage_words = with_words <= 100u * 1024u ? 1u : 0u;  // two CTAs per SM keep their tables side by side
   const size_t smem = a.stage_words ? with_words : ns_smem_bytes(l.word_rows, n_domains, false);
   // the tensor map of the word table: re-encoded when the scratch moved
   static thread_local CUtensorMap map;
