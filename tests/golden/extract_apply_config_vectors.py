@@ -190,7 +190,8 @@ class Parser:
         args = self.args()
         if name.startswith("ptr.To") or name in ("intstr.FromInt32", "intstr.FromInt", "intstr.FromString", "resource.MustParse",
                                                  "corev1.Protocol", "appsv1.StatefulSetUpdateStrategyType", "string",
-                                                 "int32", "metav1.NewTime", "appsv1.PodManagementPolicyType"):
+                                                 "int32", "metav1.NewTime", "appsv1.PodManagementPolicyType", "corev1.ResourceName",
+                                                 "types.UID", "corev1.PodPhase"):
             return args[0]
         if name.startswith("wrappers.") or name.startswith("testutils."):
             return {"$chain": [[name.split(".", 1)[1]] + args]}
@@ -234,7 +235,9 @@ class Parser:
                 k = self.eat("id")[1]
             self.eat("p", ":")
             v = self.value()
-            if not keyed:
+            if not keyed and k in CONSTS:  # a constant used as the key of a named map type
+                k = CONSTS[k]
+            elif not keyed:
                 if k == "TypeMetaApplyConfiguration" or k == "TypeMeta":
                     out.update(v)
                     k = None
