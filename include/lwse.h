@@ -31,7 +31,9 @@
  *                      :330-398 (scaleDownOld), disaggregatedset_controller.go:
  *                      203-236 (cleanup predicate), service_manager.go:57-89
  *   lwse_group_keys_*  pkg/webhooks/pod_webhook.go:180-182 + pkg/utils/utils.go:39-43
- *                      (SHA-1 group / subgroup keys), :249-255 (getSubGroupIndex)
+ *                      (SHA-1 group / subgroup keys)
+ *   lwse_subgroup_keys_*  pkg/webhooks/pod_webhook.go:249-255 (getSubGroupIndex) + :130,:151
+ *                      (the subgroup key of that index)
  *
  * Conventions
  *   - All records are little-endian plain-old-data with explicit padding; every
@@ -679,6 +681,22 @@ LWSE_API int lwse_group_keys_host(lwse_engine* e, const uint8_t* bytes, const ui
 LWSE_API int lwse_group_keys_device(lwse_engine* e, const uint8_t* d_bytes,
                                     const uint32_t* d_offsets, uint32_t n, uint8_t* d_digests,
                                     void* stream);
+
+/* Subgroup indices and subgroup keys of n pods in one pass (pod_webhook.go:249-255
+ * getSubGroupIndex, :130/:151 the subgroup key): pod i has leader-pod name
+ * bytes[offsets[i] .. offsets[i+1]), group size pod_count[i], subgroup size subgroup_size[i] and
+ * worker index worker_index[i].  index_out[i] = getSubGroupIndex(...) with Go's truncating
+ * division (worker 0 of a "leader is extra" group with subgroup size 1 gives -1, as the Go
+ * expression does); digests[i] = SHA-1("<leaderName>/<index>") — the "/<index>" suffix is formed on
+ * the device.  subgroup_size[i] == 0 (a division by zero in Go): index_out[i] = INT32_MIN and a
+ * zero digest. */
+LWSE_API int lwse_subgroup_keys_host(lwse_engine* e, const uint8_t* bytes, const uint32_t* offsets, uint32_t n,
+                                     const int32_t* pod_count, const int32_t* subgroup_size,
+                                     const int32_t* worker_index, int32_t* index_out, uint8_t* digests);
+LWSE_API int lwse_subgroup_keys_device(lwse_engine* e, const uint8_t* d_bytes, const uint32_t* d_offsets, uint32_t n,
+                                       const int32_t* d_pod_count, const int32_t* d_subgroup_size,
+                                       const int32_t* d_worker_index, int32_t* d_index_out, uint8_t* d_digests,
+                                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -70,6 +70,9 @@ int launch_ds_sweep(const lwse_ds_tables* t, int sm_count, cudaStream_t s, int* 
 // lwse_sha1_kernels.cu
 int launch_sha1(const uint8_t* d_bytes, const uint32_t* d_offsets, uint32_t n, uint8_t* d_digests,
                 int sm_count, cudaStream_t s, int* cuda_err);
+int launch_subgroup_keys(const uint8_t* d_bytes, const uint32_t* d_offsets, uint32_t n, const int32_t* d_pod_count,
+                         const int32_t* d_subgroup_size, const int32_t* d_worker_index, int32_t* d_index_out,
+                         uint8_t* d_digests, int sm_count, cudaStream_t s, int* cuda_err);
 // lwse_exchange_kernels.cu
 int launch_exchange_push(const void* d_local_part, uint8_t* const* d_peer_base, void* d_local_base,
                          uint64_t part_bytes, uint64_t part_stride, uint64_t half_bytes, uint64_t flags_offset,
@@ -193,7 +196,7 @@ struct lwse_engine {
   const uint32_t* place_counters = nullptr;  // device: counters / phase stamps of the last placement call
   const uint32_t* place_unpinned = nullptr;  // device: its unpinned-request count
   DevBuf ds, ds_roles, ds_revroles, ds_out, ds_role_out, ds_revrole_out;
-  DevBuf sha_bytes, sha_offsets, sha_digests;
+  DevBuf sha_bytes, sha_offsets, sha_digests, sha_ints;
   uint32_t* h_rounds = nullptr;  // pinned
   // peer exchange of the multi-GPU placement step (lwse_exchange_*)
   DevBuf xch, xch_peers_dev;
@@ -363,7 +366,7 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
                       &e->scan_scratch, &e->lws_out,
                       &e->group_out,  &e->occupancy,   &e->place_reqs, &e->place_out,   &e->place_occ,
                       &e->place_scratch, &e->ds,       &e->ds_roles,   &e->ds_revroles, &e->ds_out,
-                      &e->ds_role_out, &e->ds_revrole_out, &e->sha_bytes, &e->sha_offsets, &e->sha_digests,
+                      &e->ds_role_out, &e->ds_revrole_out, &e->sha_bytes, &e->sha_offsets, &e->sha_digests, &e->sha_ints,
                       &e->r_lws, &e->r_groups, &e->r_pst, &e->r_pid, &e->r_lws_out, &e->r_group_out, &e->r_scan,
                       &e->r_counts, &e->r_occ, &e->r_preq, &e->r_pout, &e->r_pout_prev, &e->h_counts_dev, &e->place_ns_scratch};
     for (DevBuf* b : bufs) b->release();
@@ -1536,6 +1539,56 @@ LWSE_API int lwse_group_keys_host(lwse_engine* e, const uint8_t* bytes, const ui
   const int rc = group_keys_locked(e, (const uint8_t*)e->sha_bytes.p, (const uint32_t*)e->sha_offsets.p, n,
                                    (uint8_t*)e->sha_digests.p, s);
   if (rc != LWSE_OK) return rc;
+  LWSE_CUDA(e, cudaMemcpyAsync(digests, e->sha_digests.p, (size_t)n * 20, cudaMemcpyDeviceToHost, s));
+  LWSE_CUDA(e, cudaStreamSynchronize(s));
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_subgroup_keys_device(lwse_engine* e, const uint8_t* d_bytes, const uint32_t* d_offsets, uint32_t n,
+                                       const int32_t* d_pod_count, const int32_t* d_subgroup_size,
+                                       const int32_t* d_worker_index, int32_t* d_index_out, uint8_t* d_digests,
+                                       void* stream) {
+  if (!e || (n && (!d_offsets || !d_digests || !d_pod_count || !d_subgroup_size || !d_worker_index || !d_index_out)))
+    return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  int cuda_err = 0;
+  int launched = lwse::launch_subgroup_keys(d_bytes, d_offsets, n, d_pod_count, d_subgroup_size, d_worker_index, d_index_out,
+                                            d_digests, e->sm_count, stream ? (cudaStream_t)stream : e->stream, &cuda_err);
+  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+  e->launches += (uint64_t)launched;
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_subgroup_keys_host(lwse_engine* e, const uint8_t* bytes, const uint32_t* offsets, uint32_t n,
+                                     const int32_t* pod_count, const int32_t* subgroup_size,
+                                     const int32_t* worker_index, int32_t* index_out, uint8_t* digests) {
+  if (!e || (n && (!offsets || !digests || !pod_count || !subgroup_size || !worker_index || !index_out)))
+    return LWSE_ERR_INVALID_ARG;
+  if (n == 0) return LWSE_OK;
+  const size_t total = offsets[n];
+  if (total && !bytes) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  cudaStream_t s = e->stream;
+  const size_t b_int = (size_t)n * 4;
+  LWSE_CUDA(e, e->sha_bytes.reserve(total + 64));
+  LWSE_CUDA(e, e->sha_offsets.reserve((size_t)(n + 1) * 4 + 16));
+  LWSE_CUDA(e, e->sha_digests.reserve((size_t)n * 20 + 16));
+  LWSE_CUDA(e, e->sha_ints.reserve(4 * b_int + 64));
+  int32_t* d_int = static_cast<int32_t*>(e->sha_ints.p);
+  if (total) LWSE_CUDA(e, cudaMemcpyAsync(e->sha_bytes.p, bytes, total, cudaMemcpyHostToDevice, s));
+  LWSE_CUDA(e, cudaMemcpyAsync(e->sha_offsets.p, offsets, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s));
+  LWSE_CUDA(e, cudaMemcpyAsync(d_int, pod_count, b_int, cudaMemcpyHostToDevice, s));
+  LWSE_CUDA(e, cudaMemcpyAsync(d_int + n, subgroup_size, b_int, cudaMemcpyHostToDevice, s));
+  LWSE_CUDA(e, cudaMemcpyAsync(d_int + 2 * (size_t)n, worker_index, b_int, cudaMemcpyHostToDevice, s));
+  int cuda_err = 0;
+  int launched = lwse::launch_subgroup_keys((const uint8_t*)e->sha_bytes.p, (const uint32_t*)e->sha_offsets.p, n, d_int, d_int + n,
+                                            d_int + 2 * (size_t)n, d_int + 3 * (size_t)n, (uint8_t*)e->sha_digests.p,
+                                            e->sm_count, s, &cuda_err);
+  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+  e->launches += (uint64_t)launched;
+  LWSE_CUDA(e, cudaMemcpyAsync(index_out, d_int + 3 * (size_t)n, b_int, cudaMemcpyDeviceToHost, s));
   LWSE_CUDA(e, cudaMemcpyAsync(digests, e->sha_digests.p, (size_t)n * 20, cudaMemcpyDeviceToHost, s));
   LWSE_CUDA(e, cudaStreamSynchronize(s));
   return LWSE_OK;

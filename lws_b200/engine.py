@@ -76,6 +76,11 @@ SYMBOLS = {
     "lwse_sweep_ds_host": ([C.c_void_p, C.POINTER(R.DsTables)], C.c_int),
     "lwse_sweep_ds_device": ([C.c_void_p, C.POINTER(R.DsTables), C.c_void_p], C.c_int),
     "lwse_group_keys_host": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p], C.c_int),
+    "lwse_subgroup_keys_host": (
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    "lwse_subgroup_keys_device": (
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p], C.c_int),
     "lwse_group_keys_device": (
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p],
         C.c_int,
@@ -434,3 +439,20 @@ class Engine:
             lib().lwse_group_keys_host(self._h, R.ptr(blob), R.ptr(offsets), len(enc), R.ptr(digests))
         )
         return digests
+
+    def subgroup_keys_host(self, leader_names, pod_count, subgroup_size, worker_index):
+        """getSubGroupIndex + SHA-1("<leaderName>/<index>") for a batch of pods → (index int32[n], digests (n, 20))."""
+        enc = [s.encode() if isinstance(s, str) else bytes(s) for s in leader_names]
+        n = len(enc)
+        offsets = np.zeros(n + 1, dtype=np.uint32)
+        offsets[1:] = np.cumsum([len(b) for b in enc], dtype=np.uint64).astype(np.uint32)
+        blob = np.frombuffer(b"".join(enc) + b"\0\0\0\0", dtype=np.uint8)
+        pc, sg, wi = (np.ascontiguousarray(x, dtype=np.int32) for x in (pod_count, subgroup_size, worker_index))
+        index = np.zeros(n, dtype=np.int32)
+        digests = np.zeros((n, 20), dtype=np.uint8)
+        self._check(lib().lwse_subgroup_keys_host(self._h, R.ptr(blob), R.ptr(offsets), n, R.ptr(pc), R.ptr(sg), R.ptr(wi),
+                                                  R.ptr(index), R.ptr(digests)))
+        return index, digests
+
+    def group_keys_device(self, d_bytes, d_offsets, n, d_digests, stream=None):
+        self._check(lib().lwse_group_keys_device(self._h, R.ptr(d_bytes), R.ptr(d_offsets), n, R.ptr(d_digests), stream))

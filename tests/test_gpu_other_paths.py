@@ -412,3 +412,42 @@ def test_webhook_label_batch_over_the_cuda_sha1_kernel(engine):
     assert [p.labels[api.GroupUniqueHashLabelKey] for p in pods] == [
         "95e88034e460983f51a9952fe128729fbc0663b5", "390b34ab671d29e9997d7d4252b8bbf8da02f5b7",
         "39f5d7e9122b9d94d3932e3720b43fd3b56347e8"]
+
+
+def test_subgroup_index_and_keys_on_gpu(engine):
+    """lwse_subgroup_keys_host: getSubGroupIndex (pod_webhook.go:249-255, Go's truncating division) and
+    SHA-1("<leaderName>/<index>") formed on the device — against the host restatement + hashlib, including
+    the reference's five getSubGroupIndex vectors (pod_webhook_test.go:272-305), worker 0 with subgroup size 1
+    (index -1) and a zero subgroup size."""
+    from lws_b200 import webhook as W
+
+    rng = np.random.default_rng(12)
+    kat = [(4, 2, 2, 1), (5, 2, 2, 0), (9, 4, 8, 1), (8, 4, 7, 1), (8, 4, 3, 0)]
+    n = 5000
+    pc = rng.integers(1, 70, size=n).astype(np.int32)
+    sg = rng.integers(1, 9, size=n).astype(np.int32)
+    wi = rng.integers(0, 70, size=n).astype(np.int32)
+    for k, (a, b, c, _) in enumerate(kat):
+        pc[k], sg[k], wi[k] = a, b, c
+    pc[10], sg[10], wi[10] = 3, 1, 0  # (0 - 1) / 1 = -1 in Go
+    sg[11] = 0
+    names = [f"lws-{'x' * int(rng.integers(0, 90))}-{i}" for i in range(n)]
+    index, digests = engine.subgroup_keys_host(names, pc, sg, wi)
+    for k, (_, _, _, want) in enumerate(kat):
+        assert index[k] == want
+    assert index[10] == -1 and index[11] == np.iinfo(np.int32).min and not digests[11].any()
+    for i in range(n):
+        if sg[i] == 0:
+            continue
+        want = int(W.get_sub_group_index(int(pc[i]), int(sg[i]), int(wi[i])))
+        assert index[i] == want, i
+        assert bytes(digests[i]) == hashlib.sha1(f"{names[i]}/{want}".encode()).digest(), i
+
+
+def test_sha1_large_batch_and_odd_layouts(engine):
+    """Keys longer than one block, empty keys, a warp whose strings do not fit the staging buffer, n % 32 != 0."""
+    rng = np.random.default_rng(13)
+    strings = [("k%d/" % i) + "y" * int(rng.integers(0, 200)) for i in range(1000)] + ["", "a" * 55, "b" * 56, "c" * 64, "d" * 119, "e" * 3000]
+    got = engine.group_keys_host(strings)
+    for s, d in zip(strings, got):
+        assert bytes(d) == hashlib.sha1(s.encode()).digest()
