@@ -2,8 +2,11 @@
 // reconcile-and-placement engine behind the LeaderWorkerSet / DisaggregatedSet
 // reconcilers.
 //
-// NOT COMPILED IN THIS REPOSITORY'S BUILD IMAGE (it has no Go toolchain); it is the
-// binding a maintainer adds to sigs.k8s.io/lws, kept next to the header it binds.
+// A SKETCH, NOT A BUILD ARTEFACT: this repository's image has no Go toolchain, so these two
+// files (lwse.go, arena.go) have never been compiled.  They show the binding a maintainer adds
+// to sigs.k8s.io/lws, kept next to the header it binds; what IS built and run here is the same
+// calling pattern in C — C-malloc'd tables, several threads on one handle, the resident tick fed
+// from the pinned arena — tests/host_c/cgo_pattern_check.c, driven by tests/test_cgo_pattern.py.
 // Every exported function maps 1:1 to a C symbol; tables are passed as C-allocated
 // (or pinned) memory because cgo forbids the C side to retain Go pointers.
 package lwse
@@ -97,8 +100,8 @@ func (e *Engine) UploadNodes(nodes *C.lwse_node_rec, n, nDomains uint32) error {
 }
 
 // SweepLws: host tables in, host result tables out (H2D, two or three kernels, D2H, sync).  With
-// tables from the pinned arena the 12-byte pod identity column is not uploaded: the engine reads
-// the rows of pods with a restart / deletion event in place.
+// pinned, mapped tables the 16-byte pod identity column is not uploaded: a prefetch kernel copies
+// just the rows of pods with a restart / deletion event while the other tables cross PCIe.
 func (e *Engine) SweepLws(t *LwsTables) error {
 	ct := t.c()
 	return e.check(C.lwse_sweep_lws_host(e.h, &ct))
