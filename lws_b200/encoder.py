@@ -129,9 +129,12 @@ def encode_nodes(nodes: Iterable[api.Node], topology_key: Optional[str]):
     return rec, values, {n.name: i for i, n in enumerate(nodes)}
 
 
-def encode_lws(items: Iterable[LwsItem], cluster: Cluster, topology_key: Optional[str] = None) -> LwsTables:
+def encode_lws(items: Iterable[LwsItem], cluster: Cluster, topology_key: Optional[str] = None,
+               encoded_nodes=None) -> LwsTables:
+    """``encoded_nodes``: the result of ``encode_nodes`` when the caller encodes many object batches
+    against one node table (the incremental encoder re-encodes one object per watch event)."""
     items = list(items)
-    node_rec, domain_values, node_index = encode_nodes(cluster.nodes, topology_key)
+    node_rec, domain_values, node_index = encoded_nodes if encoded_nodes is not None else encode_nodes(cluster.nodes, topology_key)
 
     pods_by_ns_set: dict[tuple, list] = {}
     for p in cluster.pods:

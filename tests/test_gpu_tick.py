@@ -134,3 +134,43 @@ def test_ds_sweep_c4_full_size(engine):
     want = oracle.sweep_ds(d.ds, d.roles, d.revroles)
     for a, b, name in zip(got, want, ("ds_out", "role_out", "revrole_out")):
         assert a.tobytes() == b.tobytes(), name
+
+
+def test_watch_events_through_the_incremental_encoder(engine):
+    """Watch events → lws_b200.informer.IncrementalEncoder → patch segments → lwse_resident_tick (sweep +
+    placement): after every tick the engine's resident results equal the oracle's on a FRESH full encode of
+    the same objects, object by object (the two layouts differ; results are matched by name)."""
+    import oracle
+    from informer_world import World, make_world, outputs_by_name
+    from lws_b200 import encoder, informer
+
+    items, cluster = make_world(3, n_lws=20, n_nodes=40)
+    world = World(items, cluster, 4)
+    enc = informer.IncrementalEncoder(list(world.items.values()), world.cluster(), "zone")
+    lws, groups, pst, pid, reqs = enc.full_tables()
+    engine.upload_nodes(enc.node_rec, len(enc.domain_values))
+    engine.resident_load(lws, groups, pst, pid)
+    engine.resident_place_load(reqs, enc.n_namespaces)
+    flags = R.SWEEP_GANG | R.TICK_PLACE
+    engine.resident_tick(engine.make_tick((), flags))
+    names = {sl.lws_row: key for key, sl in enc.slots.items()}
+    for tick in range(25):
+        for _ in range(int(world.rng.integers(1, 8))):
+            world.step(enc)
+        patches = enc.flush()
+        assert not enc.needs_reload
+        engine.resident_tick(engine.make_tick(patches.segments, flags))
+        g_lo, g_go = engine.resident_outputs()
+        got_l, got_g = outputs_by_name(enc.lws[: enc.n_lws], enc.groups, g_lo, g_go, names)
+        fresh_items = list(world.items.values())
+        ft = encoder.encode_lws(fresh_items, world.cluster(), "zone")
+        w_lo, w_go, w_occ = oracle.sweep_lws(ft.lws, ft.groups, ft.pod_state, ft.pod_ident, ft.nodes, flags=R.SWEEP_GANG,
+                                             want_occupancy=True)
+        want_l, want_g = outputs_by_name(ft.lws, ft.groups, w_lo, w_go,
+                                         {i: (it.lws.namespace, it.lws.name) for i, it in enumerate(fresh_items)})
+        assert got_l == want_l and got_g == want_g, f"tick {tick}"
+        # the engine's occupancy counters followed the identity-row patches
+        assert np.array_equal(engine.resident_occupancy(), w_occ), f"tick {tick}"
+        # placement over the resident request table = the spec oracle on the same rows
+        want_p = oracle.place(enc.node_rec, w_occ, len(enc.domain_values), enc.n_namespaces, enc.reqs)
+        assert engine.resident_place_outputs().tobytes() == want_p.tobytes(), f"tick {tick} placement"
