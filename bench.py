@@ -60,9 +60,9 @@ def parse():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--e2e-steps", type=int, default=200)
-    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
-                    help="multi-GPU placement step: 'peer' = lwse_exchange_* (peer stores over NVLink, no "
-                         "collective library on the data path), 'nccl' = one NCCL all-gather per step")
+    ap.add_argument("--exchange", default="lagged", choices=["lagged", "instep"],
+                    help="multi-GPU occupancy exchange: 'lagged' = the round of tick s reads the snapshot every rank pushed "
+                         "at tick s-1 (no rank waits for the slowest launch), 'instep' = it waits for this tick's pushes")
     ap.add_argument("--graph", action="store_true",
                     help="replay CUDA graphs instead of eager launches (measured slower: programmatic "
                          "dependent launch does not span graph replays)")
@@ -139,18 +139,24 @@ def host_threads() -> int:
 
 def make_tables(args, rank, world=1):
     """The rank's tables.  weak scaling: every rank its own cluster shard (own seed, own
-    namespaces); strong scaling: the one cluster of seed 0 split by LWS UID hash."""
+    namespaces), all on the same nodes; strong scaling: the ONE cluster of seed 0 — its sweep
+    sharded by LWS UID hash, its placement requests by namespace owner (exclusivity is per
+    namespace, so whole namespaces are the unit of placement work)."""
     from lws_b200 import synth
 
     if args.scaling == "strong" and world > 1:
         from lws_b200 import distributed as D
-        from lws_b200 import records as R
 
         t = synth.make(args.workload, args.scale, seed=synth.SEED)
         s_lws, s_grp, s_pst, s_pid, lrows, _ = D.shard_lws_tables(t.lws, t.groups, t.pod_state, t.pod_ident, world)[rank]
-        return synth.Tables(profile=t.profile, lws=s_lws, groups=s_grp, pod_state=s_pst, pod_ident=s_pid, nodes=t.nodes,
-                            n_domains=t.n_domains, flags=t.flags, ns_of_lws=t.ns_of_lws[lrows], n_namespaces=t.n_namespaces)
-    return synth.make(args.workload, args.scale, seed=synth.SEED + rank)
+        reqs, n_ns, _ = D.requests_of_rank(t.place_requests(), world, rank)
+        shard = synth.Tables(profile=t.profile, lws=s_lws, groups=s_grp, pod_state=s_pst, pod_ident=s_pid, nodes=t.nodes,
+                             n_domains=t.n_domains, flags=t.flags, ns_of_lws=t.ns_of_lws[lrows], n_namespaces=n_ns)
+        shard.requests = reqs
+        return shard
+    t = synth.make(args.workload, args.scale, seed=synth.SEED + rank)
+    t.requests = t.place_requests()
+    return t
 
 
 # --------------------------------------------------------------------------- #
@@ -167,7 +173,10 @@ class CpuArm:
         self.o, self.R, self.t, self.threads = oracle, R, t, threads
         self.lws, self.groups = t.lws.copy(), t.groups.copy()
         self.pst, self.pid = t.pod_state.copy(), t.pod_ident
-        self.reqs = t.place_requests()
+        self.reqs = getattr(t, "requests", None)
+        if self.reqs is None:
+            self.reqs = t.place_requests()
+        self.reqs = self.reqs.copy()
         self.occ = R.occupancy_of(t.pod_ident, len(t.nodes))
         self.lws_out = R.aligned_empty(len(t.lws), R.LWS_OUT)
         self.group_out = R.aligned_empty(len(t.groups), R.GROUP_OUT)
@@ -459,13 +468,21 @@ def run_ours(args):
     algo_bytes = t.algorithmic_bytes()
     # placement: one request per group of an exclusive-topology object; the per-node occupancy of
     # this shard's pods is a resident input column (the resident engine maintains it itself)
-    reqs = t.place_requests()
+    reqs = t.requests
     n_req = len(reqs)
     place_on = n_req > 0
-    occ_host = R.occupancy_of(t.pod_ident, n_nodes)
+    occ_host = R.occupancy_of(t.pod_ident, n_nodes)  # this rank's pods
     # the encoder lays the requests out grouped by namespace: the engine then gives every namespace its own CTA
     grouped = n_req > 0 and bool(np.all(np.diff(reqs["ns"].astype(np.int64)) >= 0))
     place_flags = R.SWEEP_PLACE_GROUPED if (grouped and world == 1) else 0
+    occ_sum = occ_host
+    if world > 1:  # every rank's pods load the same nodes: the rounds see the sum (exchanged on the device per tick)
+        tot = torch.from_numpy(occ_host.astype(np.int64)).to(dev)
+        dist.all_reduce(tot)
+        occ_sum = tot.cpu().numpy().astype(np.uint32)
+        anyreq = torch.tensor([n_req], dtype=torch.int64, device=dev)
+        dist.all_reduce(anyreq, op=dist.ReduceOp.MAX)
+        place_on = int(anyreq.item()) > 0
 
     # ---- resident copies, rotated so that the working set exceeds L2 ----
     copies = max(2, int(np.ceil(2.5 * L2_BYTES / algo_bytes)) + 1)  # bytes a sweep touches x copies > 2.5 x L2
@@ -479,47 +496,27 @@ def run_ours(args):
             lws=up(t.lws), grp=up(t.groups), pst=up(t.pod_state), pid=up(t.pod_ident),
             lo=torch.empty(n_lws * R.LWS_OUT.itemsize, dtype=torch.uint8, device=dev),
             go=torch.empty(n_grp * R.GROUP_OUT.itemsize, dtype=torch.uint8, device=dev)))
-    d_occ = torch.from_numpy(occ_host.view(np.int32)).to(dev)
-    d_reqs = up(reqs) if place_on else None
-    # multi-GPU placement: every rank needs every shard's [occupancy | requests] part
-    req_cap = 0
-    if world > 1:
-        cap = torch.tensor([n_req], dtype=torch.int64, device=dev)
-        dist.all_reduce(cap, op=dist.ReduceOp.MAX)
-        req_cap = int(cap.item())
-        place_on = req_cap > 0
-    if world > 1 and place_on:
-        from lws_b200 import distributed as D
+    from lws_b200 import distributed as D
 
-        part_stride, reqs_off = D.part_layout(n_nodes, req_cap)
-        send = torch.from_numpy(D.pack_part(occ_host, reqs, req_cap)).to(dev)  # [occupancy | requests]
-        gathered = torch.empty(world * part_stride, dtype=torch.uint8, device=dev)
-        d_pout = torch.empty(max(world * req_cap, 1) * R.PLACE_OUT.itemsize, dtype=torch.uint8, device=dev)
-        if args.collective == "peer":
-            D.connect_exchange(eng, req_cap, world, rank, device=dev)
-    else:
-        d_pout = torch.empty(max(n_req, 1) * R.PLACE_OUT.itemsize, dtype=torch.uint8, device=dev)
+    d_occ = torch.from_numpy(D.padded_occupancy(occ_host).view(np.int32)).to(dev)
+    d_reqs = up(reqs) if n_req else torch.zeros(32, dtype=torch.uint8, device=dev)
+    d_pout = torch.empty(max(n_req, 1) * R.PLACE_OUT.itemsize, dtype=torch.uint8, device=dev)
+    xflags = 0
+    if world > 1 and place_on:
+        # multi-GPU: requests are local to the rank (own namespaces), the per-node occupancy is shared —
+        # each tick the rank's counters go to every peer with NVLink peer stores + flags (no collective
+        # library on the data path), lagged by one tick so that no rank waits for the slowest launch
+        D.connect_exchange(eng, 0, world, rank, device=dev)
+        xflags = R.EXCHANGE_LAGGED if args.exchange == "lagged" else 0
 
     # time on the stream the kernels are launched on: the engine's own stream
     stream = torch.cuda.ExternalStream(eng.stream, device=dev)
     sptr = eng.stream
-    pstream = torch.cuda.Stream(device=dev)
-    pptr = pstream.cuda_stream
 
     def sweep(i, flags):
         s = sets[i % copies]
         eng.sweep_lws_device(s["lws"], n_lws, s["grp"], n_grp, s["pst"], s["pid"], n_pod, s["lo"], s["go"], None,
                              flags=flags, stream=sptr)
-
-    def place():
-        if not place_on:
-            return
-        if world == 1:
-            eng.place_device(d_reqs, n_req, d_occ, n_ns, d_pout, stream=pptr)
-            return
-        with torch.cuda.stream(pstream):
-            dist.all_gather_into_tensor(gathered, send)  # the single collective of a step
-        eng.place_gathered_device(gathered, world, part_stride, reqs_off, req_cap, n_ns, d_pout, stream=pptr)
 
     descs = {}
 
@@ -531,29 +528,23 @@ def run_ours(args):
                                          s["go"], None, flags=flags)
         return descs[k]
 
-    peer = world > 1 and place_on and args.collective == "peer"
-
     def step(i, flags):
-        if world == 1:  # one C call per tick: sweep on the engine's stream, placement round on its side stream
+        """One C call per tick: sweep on the engine's stream, the placement branch on its side stream."""
+        if world == 1:
             eng.reconcile_device(desc(i, flags), d_reqs, n_req if place_on else 0, d_occ, n_ns, d_pout, stream=sptr)
-            return
-        if peer:  # one C call per tick: push part to the peers, wait for theirs, placement ∥ sweep
-            eng.reconcile_exchanged_device(desc(i, flags), send, n_ns, d_pout, stream=sptr)
-            return
-        if place_on:
-            pstream.wait_stream(stream)
-            place()
-        sweep(i, flags)
-        if place_on:
-            stream.wait_stream(pstream)
+        elif place_on:
+            eng.reconcile_shared_device(desc(i, flags), d_reqs, n_req, d_occ, n_ns, d_pout, flags=xflags, stream=sptr)
+        else:
+            sweep(i, flags)
 
     def place_alone():
-        if peer:
-            eng.reconcile_exchanged_device(None, send, n_ns, d_pout, stream=sptr)
-            return
-        pstream.wait_stream(stream)
-        place()
-        stream.wait_stream(pstream)
+        if world == 1:
+            if grouped:
+                eng.place_grouped_device(d_reqs, n_req, d_occ, n_ns, d_pout, stream=sptr)
+            else:
+                eng.place_device(d_reqs, n_req, d_occ, n_ns, d_pout, stream=sptr)
+        else:
+            eng.reconcile_shared_device(None, d_reqs, n_req, d_occ, n_ns, d_pout, flags=xflags, stream=sptr)
 
     def barrier():
         torch.cuda.synchronize()
@@ -561,7 +552,7 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    use_graph = (args.graph or (world > 1 and not peer)) and not peer
+    use_graph = args.graph and world == 1
 
     def timed(fn, steps, warmup):
         """ms per call of fn(i) over `steps` calls, CUDA events on the launching stream."""
@@ -663,8 +654,8 @@ def run_ours(args):
     clocks = clk.summary()
     torch.cuda.synchronize()
     if place_on and world == 1:
-        rounds = (eng.place_grouped_device(d_reqs, n_req, d_occ, n_ns, d_pout, stream=pptr, want_rounds=True)[0] if grouped
-                  else eng.place_device(d_reqs, n_req, d_occ, n_ns, d_pout, stream=pptr, want_rounds=True))
+        rounds = (eng.place_grouped_device(d_reqs, n_req, d_occ, n_ns, d_pout, stream=sptr, want_rounds=True)[0] if grouped
+                  else eng.place_device(d_reqs, n_req, d_occ, n_ns, d_pout, stream=sptr, want_rounds=True))
     else:
         rounds = None
     torch.cuda.synchronize()
@@ -691,14 +682,9 @@ def run_ours(args):
                     forms[kind]["equals_spec_oracle"] = bool(
                         d_pout2.cpu().numpy()[: n_req * R.PLACE_OUT.itemsize].tobytes() == want_po.tobytes())
                     place_ok = place_ok and forms[kind]["equals_spec_oracle"]
-            else:  # the gathered problem: every rank's part, unpacked the way the kernel sees it
-                from lws_b200 import distributed as D
-
-                dist.all_gather_into_tensor(gathered, send)
-                torch.cuda.synchronize()
-                occ_all, reqs_all = D.unpack_parts(gathered.cpu().numpy(), world, n_nodes, req_cap)
-                want_po = oracle.place(t.nodes, occ_all, t.n_domains, n_ns, reqs_all, threads=min(host_threads(), 32))
-                place_ok = d_pout.cpu().numpy()[: world * req_cap * R.PLACE_OUT.itemsize].tobytes() == want_po.tobytes()
+            else:  # this rank's requests against the occupancy of every rank's pods (static here: lag or not, the same sum)
+                want_po = oracle.place(t.nodes, occ_sum, t.n_domains, n_ns, reqs, threads=min(host_threads(), 32))
+                place_ok = d_pout.cpu().numpy()[: n_req * R.PLACE_OUT.itemsize].tobytes() == want_po.tobytes()
         check = {"done": True, "sweep_equals_oracle": bool(ok), "placement_equals_spec_oracle": place_ok}
         if not ok or place_ok is False:
             raise SystemExit(f"bench.py[{rank}]: device-resident tick differs from the oracle: {check}")
@@ -724,6 +710,8 @@ def run_ours(args):
     if n_req:
         eng.resident_place_load(reqs, n_ns)
         tick_flags |= R.TICK_PLACE
+        if world > 1:
+            tick_flags |= R.TICK_SHARED_OCCUPANCY | xflags
     first = eng.resident_tick(eng.make_tick((), tick_flags))  # every row is reported once
     base_place = eng.resident_place_outputs() if n_req else None
     e2e_variants = {}
@@ -769,7 +757,7 @@ def run_ours(args):
             ok = g_lo.tobytes() == w_lo.tobytes() and g_go.tobytes() == w_go.tobytes()
             pl_ok = None
             if n_req:
-                w_po = oracle.place(t.nodes, occ_host, t.n_domains, n_ns, m_req, threads=min(host_threads(), 32))
+                w_po = oracle.place(t.nodes, occ_sum, t.n_domains, n_ns, m_req, threads=min(host_threads(), 32))
                 pl_ok = eng.resident_place_outputs().tobytes() == w_po.tobytes()
             mirror = {"ticks_replayed": state["i"], "sweep_equals_oracle": bool(ok), "placement_equals_spec_oracle": pl_ok}
             if not ok or pl_ok is False:
@@ -802,7 +790,7 @@ def run_ours(args):
                 "api": "lwse_reconcile_host: every table handed over every step (pinned host tables); state bytes, group and "
                        f"LWS rows uploaded, identity rows of the {ev} event pods read in place over PCIe"}
 
-    if peer:  # a timed-out wait (a rank fell behind by more than 2 s or is gone) invalidates the run
+    if world > 1 and place_on:  # a timed-out wait (a rank fell behind by more than 2 s or is gone) invalidates the run
         xerr = torch.tensor([eng.exchange_status()], device=dev)
         dist.all_reduce(xerr, op=dist.ReduceOp.MAX)
         if int(xerr.item()) != 0:
@@ -865,12 +853,12 @@ def run_ours(args):
                        "placement": {"requests_per_rank": int(n_req), "unpinned": int((reqs['leader_node'] == R.NONE).sum()) if n_req else 0,
                                      "namespaces": int(n_ns), "rounds": rounds, "grouped_by_namespace": bool(grouped),
                                      "forms": forms, "pair_evals": pair_evals,
-                                     "collective": ("none: parts pushed to the peers with NVLink peer stores + flags (lwse_exchange_*)"
-                                                    if peer else "1 NCCL all_gather/step") if (world > 1 and place_on) else "none"},
+                                     "exchange": (f"per tick the rank's occupancy counters ({n_nodes * 4} B) to every peer with NVLink peer stores + "
+                                                  f"flags (lwse_reconcile_shared_device, {args.exchange}); requests are rank-local (ranks own "
+                                                  "namespaces); no collective library on the data path") if (world > 1 and place_on) else "none"},
                        "launch": ("CUDA graph replay") if use_graph else "eager launches, programmatic dependent launch",
                        "step": ("one lwse_reconcile_device call per tick: fused pod scan + group pass, LWS pass, placement round concurrently on the engine's side stream" if world == 1 else
-                                "one lwse_reconcile_exchanged_device call per tick and rank" if peer else
-                                "sweep of the shard, placement round (one all-gather) concurrently on a second stream"),
+                                "one lwse_reconcile_shared_device call per tick and rank: sweep of the shard ∥ (occupancy push, placement round over the rank's namespaces)"),
                        "l2": f"inputs rotate over {copies} resident copies ({copies * algo_bytes / 1e6:.0f} MB > L2)"},
             "e2e": {"value": total_groups / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": tick["h2d_bytes_per_step"], "d2h_bytes_per_step": tick["d2h_bytes_per_step"],

@@ -449,6 +449,10 @@ typedef struct lwse_tick {
 
 #define LWSE_TICK_PLACE (1u << 8)     /* run the placement round over the resident request table */
 #define LWSE_TICK_NO_SWEEP (1u << 9)  /* patches (+ placement) only */
+#define LWSE_TICK_SHARED_OCCUPANCY (1u << 10) /* multi-rank: the round runs as lwse_reconcile_shared_device does
+                                                 — the engine's occupancy counters are pushed to the peers
+                                                 (lwse_exchange_*), the resident requests are solved against
+                                                 the sum; combine with LWSE_EXCHANGE_LAGGED                    */
 /* (LWSE_SWEEP_PLACE_SCAN selects the brute-force form of the round; the resident request table
  * is checked for namespace grouping when it is loaded) */
 
@@ -557,7 +561,8 @@ LWSE_API int lwse_reconcile_host(lwse_engine* e, const lwse_lws_tables* host, co
  * gets an IPC handle for it; the caller all-gathers the handles (any transport — they are
  * 64 opaque bytes) and hands all of them to lwse_exchange_connect, which maps the peers'
  * buffers over NVLink.  lwse_upload_nodes must have been called (the layout depends on
- * n_nodes); one exchange per engine. */
+ * n_nodes); one exchange per engine.  reqs_per_part = 0: the parts carry occupancy only
+ * (lwse_reconcile_shared_device). */
 LWSE_API int lwse_exchange_create(lwse_engine* e, uint32_t reqs_per_part, uint32_t world, uint32_t rank,
                                   void* handle_out /* LWSE_IPC_HANDLE_BYTES */);
 LWSE_API int lwse_exchange_connect(lwse_engine* e, const void* handles /* world x LWSE_IPC_HANDLE_BYTES */);
@@ -574,6 +579,21 @@ LWSE_API uint64_t lwse_exchange_part_bytes(const lwse_engine* e);
  * (d == NULL: placement step only).  Every rank must call this the same number of times. */
 LWSE_API int lwse_reconcile_exchanged_device(lwse_engine* e, const lwse_lws_tables* d, const void* d_local_part,
                                              uint32_t n_namespaces, lwse_place_out* d_place_out, void* stream);
+/* The tick of a shard whose placement requests are LOCAL to the rank and whose node occupancy is
+ * shared — the north star's "single all-gather of the per-node occupancy vector": ranks own disjoint
+ * namespaces (exclusivity is per namespace, so their rounds are independent), every rank's pods load
+ * the same nodes.  `d_local_occupancy` (n_nodes counters, this rank's pods) is pushed into every
+ * peer's buffer with peer stores + flags (lwse_exchange_create with reqs_per_part = 0 is enough);
+ * the round then solves the n_reqs local requests (grouped by namespace) against the SUM of all
+ * ranks' counters, concurrently with the sweep of `d` (NULL: placement branch only).
+ * flags: LWSE_SWEEP_PLACE_SCAN, LWSE_EXCHANGE_LAGGED.  Every rank must call it the same number of times. */
+#define LWSE_EXCHANGE_LAGGED (1u << 16) /* solve against the snapshot every rank pushed in the PREVIOUS
+                                           call (own part included): no rank waits for the slowest
+                                           rank's launch of this tick; results lag remote occupancy
+                                           changes by one tick (the first call is in step)           */
+LWSE_API int lwse_reconcile_shared_device(lwse_engine* e, const lwse_lws_tables* d, const lwse_place_req* d_reqs,
+                                          uint32_t n_reqs, const uint32_t* d_local_occupancy, uint32_t n_namespaces,
+                                          lwse_place_out* d_place_out, uint32_t flags, void* stream);
 /* *error_out = 1 if a wait for the peers ever timed out (2 s; a rank is gone).  Synchronizes. */
 LWSE_API int lwse_exchange_status(lwse_engine* e, uint32_t* error_out);
 

@@ -76,7 +76,7 @@ int launch_subgroup_keys(const uint8_t* d_bytes, const uint32_t* d_offsets, uint
 // lwse_exchange_kernels.cu
 int launch_exchange_push(const void* d_local_part, uint8_t* const* d_peer_base, void* d_local_base,
                          uint64_t part_bytes, uint64_t part_stride, uint64_t half_bytes, uint64_t flags_offset,
-                         uint64_t step, uint32_t world, uint32_t rank, cudaStream_t s, int* cuda_err);
+                         uint64_t step, uint64_t wait_step, uint32_t world, uint32_t rank, cudaStream_t s, int* cuda_err);
 }  // namespace lwse
 
 
@@ -1012,7 +1012,7 @@ LWSE_API int lwse_exchange_create(lwse_engine* e, uint32_t reqs_per_part, uint32
   const uint64_t reqs_off = ((uint64_t)e->n_nodes * 4u + 15u) / 16u * 16u;
   const uint64_t stride = reqs_off + (uint64_t)reqs_per_part * sizeof(lwse_place_req);
   const uint64_t half = ((uint64_t)world * stride + 255u) / 256u * 256u;
-  const uint64_t flags_off = 2u * half;
+  const uint64_t flags_off = 3u * half;  // three buffers: step s uses buffer s % 3 (lwse_exchange_kernels.cu)
   const uint64_t total = flags_off + (uint64_t)world * 8u + 64u;
   LWSE_CUDA(e, e->xch.reserve(total));
   LWSE_CUDA(e, cudaMemset(e->xch.p, 0, total));
@@ -1070,18 +1070,65 @@ LWSE_API int lwse_reconcile_exchanged_device(lwse_engine* e, const lwse_lws_tabl
   const uint64_t step = ++e->xch_step;
   int cuda_err = 0;
   int launched = lwse::launch_exchange_push(d_local_part, (uint8_t* const*)e->xch_peers_dev.p, e->xch.p, e->xch_stride,
-                                            e->xch_stride, e->xch_half, e->xch_flags_off, step, e->xch_world,
+                                            e->xch_stride, e->xch_half, e->xch_flags_off, step, step, e->xch_world,
                                             e->xch_rank, e->side_stream, &cuda_err);
   if (launched < 0) {
     rc = fail_cuda(e, (cudaError_t)cuda_err);
   } else {
     e->launches += (uint64_t)launched;
-    const uint8_t* half = static_cast<const uint8_t*>(e->xch.p) + (step & 1ull) * e->xch_half;
+    const uint8_t* half = static_cast<const uint8_t*>(e->xch.p) + (step % 3ull) * e->xch_half;
     rc = place_locked(e, reinterpret_cast<const lwse_place_req*>(half + e->xch_reqs_off),
                       e->xch_world * e->xch_reqs_per_part, reinterpret_cast<const uint32_t*>(half), n_namespaces,
                       d_place_out, nullptr, e->side_stream, e->xch_world, e->xch_reqs_per_part, e->xch_stride,
                       /*after_push=*/true);
   }
+  if (rc == LWSE_OK && t) rc = sweep_device_locked(e, t, s);
+  cudaError_t je = cudaEventRecord(e->ev_join, e->side_stream);
+  if (je == cudaSuccess) je = cudaStreamWaitEvent(s, e->ev_join, 0);
+  if (rc != LWSE_OK) return rc;
+  if (je != cudaSuccess) return fail_cuda(e, je);
+  return LWSE_OK;
+}
+
+// The placement branch of a tick whose requests are LOCAL and whose occupancy is shared: push this
+// rank's occupancy counters to every peer, then solve the local requests against the sum of all
+// ranks' counters.  Enqueued on `ps`.  lagged: read the previous step's snapshot (see the kernel file).
+static int shared_occupancy_place_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
+                                         const uint32_t* d_local_occ, uint32_t n_namespaces, lwse_place_out* d_out,
+                                         uint32_t form, bool lagged, cudaStream_t ps) {
+  const uint64_t step = ++e->xch_step;
+  const uint64_t read_step = (lagged && step > 1) ? step - 1 : step;
+  int cuda_err = 0;
+  int launched = lwse::launch_exchange_push(d_local_occ, (uint8_t* const*)e->xch_peers_dev.p, e->xch.p,
+                                            e->xch_reqs_off,  // the occupancy block of a part: n_nodes counters, 16-byte padded
+                                            e->xch_stride, e->xch_half, e->xch_flags_off, step, read_step, e->xch_world,
+                                            e->xch_rank, ps, &cuda_err);
+  if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+  e->launches += (uint64_t)launched;
+  if (n_reqs == 0) return LWSE_OK;
+  const uint32_t* occ_parts = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(e->xch.p) + (read_step % 3ull) * e->xch_half);
+  if (form != kFormGeneral && lwse::place_ns_supported(e->n_nodes, e->n_domains))
+    return place_grouped_locked(e, d_reqs, n_reqs, occ_parts, e->xch_world, e->xch_stride, n_namespaces, d_out,
+                                form == kFormScan, nullptr, nullptr, ps, /*first_pdl=*/false);
+  return LWSE_ERR_UNSUPPORTED;  // the shared-occupancy form needs a request table grouped by namespace
+}
+
+LWSE_API int lwse_reconcile_shared_device(lwse_engine* e, const lwse_lws_tables* t, const lwse_place_req* d_reqs,
+                                          uint32_t n_reqs, const uint32_t* d_local_occupancy, uint32_t n_namespaces,
+                                          lwse_place_out* d_place_out, uint32_t flags, void* stream) {
+  if (!e || !d_local_occupancy || !aligned16(d_local_occupancy) || (n_reqs && (!d_reqs || !d_place_out)) || n_namespaces == 0)
+    return LWSE_ERR_INVALID_ARG;
+  int rc = t ? check_lws_tables(t) : LWSE_OK;
+  if (rc != LWSE_OK) return rc;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->xch_connected) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  LWSE_CUDA(e, cudaEventRecord(e->ev_fork, s));
+  LWSE_CUDA(e, cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+  rc = shared_occupancy_place_locked(e, d_reqs, n_reqs, d_local_occupancy, n_namespaces, d_place_out,
+                                     (flags & LWSE_SWEEP_PLACE_SCAN) ? kFormScan : kFormGrouped,
+                                     (flags & LWSE_EXCHANGE_LAGGED) != 0, e->side_stream);
   if (rc == LWSE_OK && t) rc = sweep_device_locked(e, t, s);
   cudaError_t je = cudaEventRecord(e->ev_join, e->side_stream);
   if (je == cudaSuccess) je = cudaStreamWaitEvent(s, e->ev_join, 0);
@@ -1294,8 +1341,15 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
   }
   if (do_place) {
     const uint32_t form = !e->r_place_grouped ? kFormGeneral : (flags & LWSE_SWEEP_PLACE_SCAN) ? kFormScan : kFormGrouped;
-    rc = place_locked(e, (const lwse_place_req*)e->r_preq.p, e->rn_reqs, (const uint32_t*)e->r_occ.p, e->rn_namespaces,
-                      (lwse_place_out*)e->r_pout.p, nullptr, e->side_stream, 1, e->rn_reqs, 0, false, form, /*first_pdl=*/false);
+    if (flags & LWSE_TICK_SHARED_OCCUPANCY) {  // multi-rank: this rank's counters go to the peers, the round sees the sum
+      if (!e->xch_connected) return LWSE_ERR_NOT_READY;
+      rc = shared_occupancy_place_locked(e, (const lwse_place_req*)e->r_preq.p, e->rn_reqs, (const uint32_t*)e->r_occ.p,
+                                         e->rn_namespaces, (lwse_place_out*)e->r_pout.p, form,
+                                         (flags & LWSE_EXCHANGE_LAGGED) != 0, e->side_stream);
+    } else {
+      rc = place_locked(e, (const lwse_place_req*)e->r_preq.p, e->rn_reqs, (const uint32_t*)e->r_occ.p, e->rn_namespaces,
+                        (lwse_place_out*)e->r_pout.p, nullptr, e->side_stream, 1, e->rn_reqs, 0, false, form, /*first_pdl=*/false);
+    }
     if (rc != LWSE_OK) return rc;
     int launched = lwse::launch_place_publish(
         (const lwse_place_out*)e->r_pout.p, (lwse_place_out*)e->r_pout_prev.p, e->rn_reqs,

@@ -8,10 +8,17 @@
 // no collective library on the data path.
 //
 // Buffers (one cudaMalloc per rank, exported with cudaIpcGetMemHandle, opened by every peer):
-//   [half 0: world x part_stride][half 1: world x part_stride][flags: world x 8 B][ticket][error]
-// Step s uses half s & 1.  A rank can be at most one step ahead of the slowest one (it cannot
-// finish step s + 1 before every rank has pushed s + 1, which each does only after its own
-// placement round of step s has read half s & 1 — stream order), so two halves suffice.
+//   [buffer 0: world x part_stride][buffer 1][buffer 2][flags: world x 8 B][ticket][error]
+// Step s uses buffer s % 3.  Two ways to wait:
+//   - in step   (wait_step = s): the round of step s reads the parts every rank pushed for step s;
+//   - lagged    (wait_step = s - 1): the round of step s reads buffer (s - 1) % 3, the parts of the
+//     PREVIOUS step (own part included: every rank sees the same snapshot).  Nobody waits for the
+//     slowest rank's launch of this step — the flags of s - 1 were raised a whole tick ago — so the
+//     ranks stay only loosely coupled (one tick of slack absorbs launch skew).
+// Three buffers make both safe: rank A writes buffer s % 3 only after every rank raised its flag
+// for s - 1 (A's own wait of tick s - 1 or s), i.e. after every rank B has enqueued push(s - 1),
+// which on B's stream comes after B's round of tick s - 2 — the last reader of buffer (s - 3) % 3
+// = s % 3.
 #include "lwse_device.cuh"
 
 namespace lwse {
@@ -23,7 +30,7 @@ struct ExchangeArgs {
   uint32_t* ticket;                // local: CTA completion counter
   uint32_t* error;                 // local: set to 1 when the wait timed out
   uint64_t part_bytes, part_stride, half_bytes, flags_offset;
-  uint64_t step;
+  uint64_t step, wait_step;
   uint32_t world, rank;
   uint64_t timeout_ns;
 };
@@ -41,7 +48,7 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const ExchangeArgs a
   __shared__ uint32_t s_last;
   pdl_launch_dependents();  // the placement round may take its SMs now; it waits for this grid to complete
   const uint64_t n_vec = a.part_bytes >> 4;
-  const uint64_t dst_off = (a.step & 1ull) * a.half_bytes + (uint64_t)a.rank * a.part_stride;
+  const uint64_t dst_off = (a.step % 3ull) * a.half_bytes + (uint64_t)a.rank * a.part_stride;
   // every peer's copy of this rank's part: the loads of the local part are shared by all targets
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint4 v = __ldg(a.local_part + i);
@@ -61,7 +68,7 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const ExchangeArgs a
     // … and wait for source threadIdx.x to have pushed this step here
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (ld_acquire_sys(a.flags + threadIdx.x) < a.step) {
+    while (ld_acquire_sys(a.flags + threadIdx.x) < a.wait_step) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (t - t0 > a.timeout_ns) {  // a peer is gone: do not hang the GPU, report
@@ -74,7 +81,7 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const ExchangeArgs a
 
 int launch_exchange_push(const void* d_local_part, uint8_t* const* d_peer_base, void* d_local_base,
                          uint64_t part_bytes, uint64_t part_stride, uint64_t half_bytes, uint64_t flags_offset,
-                         uint64_t step, uint32_t world, uint32_t rank, cudaStream_t s, int* cuda_err) {
+                         uint64_t step, uint64_t wait_step, uint32_t world, uint32_t rank, cudaStream_t s, int* cuda_err) {
   *cuda_err = 0;
   ExchangeArgs a{};
   uint8_t* base = static_cast<uint8_t*>(d_local_base);
@@ -88,6 +95,7 @@ int launch_exchange_push(const void* d_local_part, uint8_t* const* d_peer_base, 
   a.half_bytes = half_bytes;
   a.flags_offset = flags_offset;
   a.step = step;
+  a.wait_step = wait_step;
   a.world = world;
   a.rank = rank;
   a.timeout_ns = 2000000000ull;

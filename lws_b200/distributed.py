@@ -116,3 +116,35 @@ def shard_lws_tables(lws, groups, pod_state, pod_ident, world: int):
 
 
 __all__ = ["connect_exchange", "part_layout", "pad_requests", "pack_part", "unpack_parts", "shard_index", "shard_lws_tables", "shard_of"]
+
+
+# --------------------------------------------------------------------------- #
+# shared occupancy: ranks own namespaces, nodes are common
+# --------------------------------------------------------------------------- #
+def namespace_owner(ns: np.ndarray, world: int) -> np.ndarray:
+    """Which rank solves the placement rounds of a namespace (exclusivity is per namespace, so whole
+    namespaces — never single requests — are the unit of placement work)."""
+    return (np.asarray(ns, dtype=np.uint64) % np.uint64(max(world, 1))).astype(np.uint32)
+
+
+def requests_of_rank(reqs: np.ndarray, world: int, rank: int):
+    """The rows of a (namespace-grouped) global request table that `rank` solves, with dense local
+    namespace ids → (requests, n_namespaces, global row numbers).  Strong scaling: the sweep shards by
+    LWS UID hash, the placement by namespace; the only per-tick exchange is the occupancy vector."""
+    if world <= 1:
+        n_ns = int(reqs["ns"].max()) + 1 if len(reqs) else 1
+        return reqs, n_ns, np.arange(len(reqs))
+    rows = np.flatnonzero(namespace_owner(reqs["ns"], world) == rank)
+    mine = R.aligned_empty(len(rows), R.PLACE_REQ)
+    mine[:] = reqs[rows]
+    mine["ns"] = mine["ns"] // np.uint32(world)  # dense and still non-decreasing
+    n_ns = int(mine["ns"].max()) + 1 if len(mine) else 1
+    return mine, n_ns, rows
+
+
+def padded_occupancy(occupancy: np.ndarray) -> np.ndarray:
+    """The rank's occupancy counters padded to a multiple of 16 bytes (what lwse_reconcile_shared_device pushes)."""
+    n = (len(occupancy) * 4 + 15) // 16 * 4
+    out = np.zeros(n, dtype=np.uint32)
+    out[: len(occupancy)] = occupancy
+    return out

@@ -72,6 +72,10 @@ SYMBOLS = {
         [C.c_void_p, C.POINTER(R.LwsTables), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p],
         C.c_int,
     ),
+    "lwse_reconcile_shared_device": (
+        [C.c_void_p, C.POINTER(R.LwsTables), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p],
+        C.c_int,
+    ),
     "lwse_exchange_status": ([C.c_void_p, C.POINTER(C.c_uint32)], C.c_int),
     "lwse_sweep_ds_host": ([C.c_void_p, C.POINTER(R.DsTables)], C.c_int),
     "lwse_sweep_ds_device": ([C.c_void_p, C.POINTER(R.DsTables), C.c_void_p], C.c_int),
@@ -247,6 +251,14 @@ class Engine:
         self._check(lib().lwse_reconcile_exchanged_device(
             self._h, C.byref(tables) if tables is not None else None, R.ptr(d_local_part), n_namespaces,
             R.ptr(d_place_out), stream))
+
+    def reconcile_shared_device(self, tables, d_reqs, n_reqs, d_local_occupancy, n_namespaces, d_place_out, flags=0, stream=None):
+        """One tick of a shard with LOCAL requests and SHARED occupancy: the rank's occupancy counters go to
+        every peer over NVLink, the local (namespace-grouped) requests are solved against the sum — on the
+        side stream, concurrently with the sweep of ``tables`` (None: placement branch only)."""
+        self._check(lib().lwse_reconcile_shared_device(
+            self._h, C.byref(tables) if tables is not None else None, R.ptr(d_reqs), n_reqs, R.ptr(d_local_occupancy),
+            n_namespaces, R.ptr(d_place_out), flags, stream))
 
     def exchange_status(self) -> int:
         err = C.c_uint32(0)

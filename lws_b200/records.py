@@ -197,6 +197,7 @@ SWEEP_SKIP_POD_SCAN = 1 << 3
 SWEEP_REUSE_POD_IDENT = 1 << 4
 SWEEP_PLACE_GROUPED = 1 << 5
 SWEEP_PLACE_SCAN = 1 << 6
+EXCHANGE_LAGGED = 1 << 16
 
 # --------------------------------------------------------------------------- #
 # placement
@@ -317,6 +318,7 @@ PATCH_RANGE = 1 << 0
 TICK_MAX_SEGS = 8
 TICK_PLACE = 1 << 8
 TICK_NO_SWEEP = 1 << 9
+TICK_SHARED_OCCUPANCY = 1 << 10
 
 
 class PatchSeg(C.Structure):

@@ -141,3 +141,68 @@ def test_pack_unpack_roundtrip():
     # padding rows are inert: unpinned and size 0
     pad = reqs_all[cap - 1]
     assert pad["leader_node"] == R.NONE and pad["size"] == 0
+
+
+def _shared_worker(rank, world, port, q):
+    """The shared-occupancy layout on CPU (gloo): sweep sharded by UID hash, placement by namespace owner,
+    ONE all-gather of the occupancy vector — what lwse_reconcile_shared_device does with peer stores."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    import oracle
+    from lws_b200 import distributed as D
+    from lws_b200 import synth
+    from lws_b200 import records as R
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p = synth.profile("C3", 0.03)
+        p.n_namespaces, p.n_nodes, p.p_leader_unscheduled = 10, 1024, 0.4
+        t = synth.make(p, seed=78)
+        shards = D.shard_lws_tables(t.lws, t.groups, t.pod_state, t.pod_ident, world)
+        lws, grp, pst, pid, _, _ = shards[rank]
+        _, _, occ = oracle.sweep_lws(lws, grp, pst, pid, t.nodes, flags=t.flags, want_occupancy=True)
+        mine = torch.from_numpy(D.padded_occupancy(occ).view(np.int32).copy())
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)  # the single collective of the step
+        occ_sum = sum(x.numpy().view(np.uint32)[: len(t.nodes)].astype(np.uint64) for x in parts).astype(np.uint32)
+        reqs_global = t.place_requests()
+        reqs, n_ns, rows = D.requests_of_rank(reqs_global, world, rank)
+        assert np.all(np.diff(reqs["ns"].astype(np.int64)) >= 0)  # still grouped by namespace
+        out = oracle.place(t.nodes, occ_sum, t.n_domains, n_ns, reqs)
+        q.put((rank, rows, out.tobytes(), occ_sum.tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_occupancy_layout_gloo_world2():
+    import torch.multiprocessing as mp
+
+    import oracle
+    from lws_b200 import records as R
+    from lws_b200 import synth
+
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shared_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    got = sorted([q.get(timeout=300) for _ in range(world)], key=lambda x: x[0])
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    p = synth.profile("C3", 0.03)
+    p.n_namespaces, p.n_nodes, p.p_leader_unscheduled = 10, 1024, 0.4
+    t = synth.make(p, seed=78)
+    occ = R.occupancy_of(t.pod_ident, len(t.nodes))
+    assert got[0][3] == occ.tobytes() == got[1][3]  # summed shard occupancies = the cluster's
+    reqs = t.place_requests()
+    whole = oracle.place(t.nodes, occ, t.n_domains, t.n_namespaces, reqs)
+    seen = np.zeros(len(reqs), bool)
+    for rank, rows, out, _ in got:
+        assert np.frombuffer(out, R.PLACE_OUT).tobytes() == whole[rows].tobytes()  # every rank's rows = the unsharded answer
+        seen[rows] = True
+    assert seen.all()

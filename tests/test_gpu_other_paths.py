@@ -310,6 +310,26 @@ def test_peer_exchange_placement_step_on_two_gpus():
     assert "EXCHANGE_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_shared_occupancy_tick_on_every_gpu_of_the_box():
+    """lwse_reconcile_shared_device / LWSE_TICK_SHARED_OCCUPANCY on all GPUs of the box (2, 4 or 8;
+    skipped on a one-GPU box): tests/multi_gpu/shared_occupancy_check.py under torchrun."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
+         "127.0.0.1", "--master-port", "29534", os.path.join(root, "tests", "multi_gpu", "shared_occupancy_check.py")],
+        capture_output=True, text=True, timeout=600)
+    assert "SHARED_OCCUPANCY_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_reconcile_host_one_call(engine):
     """lwse_reconcile_host = lwse_sweep_lws_host + lwse_place_host in one call (placement on the
     side stream while the tables upload); pageable and pinned tables."""
