@@ -501,3 +501,61 @@ def encode_place_requests(lws: np.ndarray, groups: np.ndarray, ns_of_lws: Option
         grouped[:] = reqs[order]
         reqs = grouped
     return reqs
+
+
+def sub_group_layout(size: int, sub_group_size: int, leader_excluded: bool) -> list:
+    """Worker-index ranges of the subgroups of one group → [(first worker index, pods)], following
+    getSubGroupIndex (pkg/webhooks/pod_webhook.go:249-255) and the leader rule (:125-135): the leader
+    (worker 0) sits in subgroup 0 unless the policy type is LeaderExcluded; when size - 1 is a multiple of
+    the subgroup size the leader is an extra pod of subgroup 0."""
+    if sub_group_size <= 0 or size <= 0:
+        return []
+    index_of = (lambda w: (w - 1) // sub_group_size) if (size - 1) % sub_group_size == 0 else (lambda w: w // sub_group_size)
+    members: dict[int, list] = {}
+    for w in range(size):
+        if w == 0:
+            if leader_excluded:
+                continue
+            members.setdefault(0, []).append(0)
+        else:
+            members.setdefault(index_of(w), []).append(w)
+    return [(min(ws), len(ws)) for _, ws in sorted(members.items())]
+
+
+def encode_subgroup_place_requests(lws: np.ndarray, groups: np.ndarray, pod_ident: np.ndarray, sub_exclusive: np.ndarray,
+                                   ns_of_lws: Optional[np.ndarray] = None, n_namespaces: int = 1) -> np.ndarray:
+    """Requests for SUBGROUP-exclusive placement (pod_webhook.go:132-134, :153-155: affinity / anti-affinity on
+    the subgroup-key label, same shape as the group-level terms): one request per (group, subgroup) of the
+    objects flagged in `sub_exclusive` (bool per object: the subgroup-exclusive-topology annotation is set).
+
+    The anti-affinity term selects on the SUBGROUP key label, so subgroup claims only exclude other
+    subgroups — never group-level claims, which select on the group key label.  The two label keys are two
+    independent exclusivity classes; a class is addressed as its own namespace id:
+    ns' = n_namespaces + ns (group-level requests keep ns).  Pass n_namespaces * 2 to the placement call
+    when both kinds are in one table.  `group` carries group row | subgroup index << 24.  The first pod of
+    the subgroup decides pinning (its node binding, read from the identity column); groups whose pod rows
+    are not the regular size-many (pods in worker-index order) are left to the stock path."""
+    out = []
+    for li in np.flatnonzero(sub_exclusive):
+        size, sg = int(lws["size"][li]), int(lws["subgroup_size"][li])
+        excluded = bool(int(lws["flags"][li]) & R.LWS_SUBGROUP_LEADER_EXCLUDED)
+        layout = sub_group_layout(size, sg, excluded)
+        ns = 0 if ns_of_lws is None else int(ns_of_lws[li])
+        uid = int(lws["uid_hash"][li])
+        base, count = int(lws["group_base"][li]), int(lws["group_count"][li])
+        for gi in range(count):
+            g = groups[base + gi]
+            if not (int(g["flags"]) & R.GRP_POD_PRESENT) or int(g["pod_count"]) != size or (base + gi) >= (1 << 24):
+                continue
+            for si, (first_w, pods) in enumerate(layout):
+                place = int(pod_ident["place"][int(g["pod_base"]) + first_w])
+                node = (place >> R.PODID_NODE_SHIFT) if (place & R.PODID_SCHEDULED) else R.NONE
+                mix = (uid ^ ((gi * 0x9E3779B97F4A7C15 + si * 0xC2B2AE3D27D4EB4F) & 0xFFFFFFFFFFFFFFFF)) * 0xBF58476D1CE4E5B9 & 0xFFFFFFFFFFFFFFFF
+                mix ^= mix >> 31
+                key = ((uid + gi * 131 + si) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+                key ^= key >> 29
+                out.append((mix, key, (base + gi) | (si << 24), n_namespaces + ns, pods, node))
+    reqs = R.aligned_empty(len(out), R.PLACE_REQ)
+    for i, row in enumerate(sorted(out, key=lambda r: r[3])):  # grouped by (class, namespace)
+        reqs[i] = row
+    return reqs

@@ -471,3 +471,30 @@ def test_sha1_large_batch_and_odd_layouts(engine):
     got = engine.group_keys_host(strings)
     for s, d in zip(strings, got):
         assert bytes(d) == hashlib.sha1(s.encode()).digest()
+
+
+def test_constraint_cases_on_gpu(engine):
+    """tests/test_place_constraints.py's table (namespace scoping, Exists ∧ NotIn, pinned leaders, capacity
+    filter) and the subgroup-exclusive class through the CUDA kernels: every row equals the spec oracle's."""
+    import oracle
+    from test_place_constraints import CASES, check, nodes, reqs
+
+    for name, n_dom, n_ns, rows, want in CASES:
+        n, rq = nodes(n_dom), reqs(rows)
+        engine.upload_nodes(n, n_dom)
+        got, _ = engine.place_host(rq, None, n_ns)
+        same(got, oracle.place(n, None, n_dom, n_ns, rq), name)
+        check(got, want)
+    p = synth.profile("fuzz", 0.05)
+    p.size_choices, p.replicas_choices, p.p_exclusive, p.fuzz, p.p_short_group, p.n_nodes, p.nodes_per_domain = (5,), (2,), 1.0, 0.0, 0.0, 400, 4
+    p.node_capacity, p.p_leader_unscheduled = 40, 0.5
+    t = synth.make(p, seed=3)
+    t.lws["subgroup_size"] = 2
+    sub = encoder.encode_subgroup_place_requests(t.lws, t.groups, t.pod_ident, np.ones(len(t.lws), bool), t.ns_of_lws, t.n_namespaces)
+    g = t.place_requests()
+    both = R.aligned_empty(len(g) + len(sub), R.PLACE_REQ)
+    both[: len(g)], both[len(g):] = g, sub
+    occ = R.occupancy_of(t.pod_ident, len(t.nodes))
+    engine.upload_nodes(t.nodes, t.n_domains)
+    got, _ = engine.place_host(both, occ, 2 * t.n_namespaces)
+    same(got, oracle.place(t.nodes, occ, t.n_domains, 2 * t.n_namespaces, both), "group + subgroup classes")
