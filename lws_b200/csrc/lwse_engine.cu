@@ -171,6 +171,8 @@ struct lwse_engine {
   DevBuf r_preq, r_pout, r_pout_prev;  // resident placement requests / results of this and the previous tick
   PinBuf arena;                      // patch arena handed to the caller
   PinBuf stage;                      // staging for patch segments that lie outside the arena
+  DevBuf arena_mirror, stage_mirror; // device copies of the two: a tick with many patches moves them with one DMA
+                                     // copy per buffer (SM reads of host memory are latency-bound: ~6 GB/s measured)
   PinBuf chg;                        // change lists: [lws rows | lws out | group rows | group out | place rows | place out]
   PinBuf tickw;                      // [0] lws changes [1] group changes [2] sweep seq | [4] place changes [5] rounds [6] place seq
   size_t chg_off[6] = {};
@@ -368,7 +370,8 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
                       &e->place_scratch, &e->ds,       &e->ds_roles,   &e->ds_revroles, &e->ds_out,
                       &e->ds_role_out, &e->ds_revrole_out, &e->sha_bytes, &e->sha_offsets, &e->sha_digests, &e->sha_ints,
                       &e->r_lws, &e->r_groups, &e->r_pst, &e->r_pid, &e->r_lws_out, &e->r_group_out, &e->r_scan,
-                      &e->r_counts, &e->r_occ, &e->r_preq, &e->r_pout, &e->r_pout_prev, &e->h_counts_dev, &e->place_ns_scratch};
+                      &e->r_counts, &e->r_occ, &e->r_preq, &e->r_pout, &e->r_pout_prev, &e->h_counts_dev, &e->place_ns_scratch,
+                      &e->arena_mirror, &e->stage_mirror};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&e->arena, &e->stage, &e->chg, &e->tickw};
     for (PinBuf* b : pins) b->release();
@@ -761,6 +764,49 @@ static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint
   }
   int cuda_err = 0;
   if (n_sc) {
+    // Few patch bytes: the scatter kernel reads them in place over PCIe (one round trip, no copy
+    // launch).  Many: one DMA copy per pinned buffer of the span this call uses, then the kernel
+    // reads device memory — the copy engine moves 400 KB in ~10 us, SM reads of host memory need 60.
+    static const long dma_threshold = [] {
+      const char* v = getenv("LWSE_PATCH_DMA_BYTES");
+      return v ? atol(v) : 16384L;
+    }();
+    size_t total = 0;
+    for (int k = 0; k < n_sc; k++) total += (size_t)sc[k].n * (4u + sc[k].row_bytes);
+    if (dma_threshold >= 0 && total >= (size_t)dma_threshold) {
+      struct Span { const PinBuf* pin; DevBuf* mirror; uintptr_t lo, hi; } spans[2] = {
+          {&e->arena, &e->arena_mirror, UINTPTR_MAX, 0}, {&e->stage, &e->stage_mirror, UINTPTR_MAX, 0}};
+      auto touch = [&](const void* dptr, size_t bytes) {
+        for (Span& sp : spans) {
+          const uintptr_t d0 = reinterpret_cast<uintptr_t>(sp.pin->d), a = reinterpret_cast<uintptr_t>(dptr);
+          if (sp.pin->d && a >= d0 && a + bytes <= d0 + sp.pin->cap) {
+            sp.lo = a - d0 < sp.lo ? a - d0 : sp.lo;
+            sp.hi = a - d0 + bytes > sp.hi ? a - d0 + bytes : sp.hi;
+          }
+        }
+      };
+      for (int k = 0; k < n_sc; k++) {
+        touch(sc[k].rows, (size_t)sc[k].n * 4);
+        touch(sc[k].values, (size_t)sc[k].n * sc[k].row_bytes);
+      }
+      for (Span& sp : spans) {
+        if (sp.hi <= sp.lo) continue;
+        if (sp.mirror->cap < sp.pin->cap) {  // (first use, or the pinned buffer grew)
+          LWSE_CUDA(e, cudaStreamSynchronize(e->stream));
+          LWSE_CUDA(e, cudaStreamSynchronize(e->side_stream));
+          LWSE_CUDA(e, sp.mirror->reserve(sp.pin->cap));
+        }
+        LWSE_CUDA(e, cudaMemcpyAsync(static_cast<uint8_t*>(sp.mirror->p) + sp.lo, static_cast<const uint8_t*>(sp.pin->h) + sp.lo,
+                                     sp.hi - sp.lo, cudaMemcpyHostToDevice, s));
+        const uintptr_t d0 = reinterpret_cast<uintptr_t>(sp.pin->d), m0 = reinterpret_cast<uintptr_t>(sp.mirror->p);
+        for (int k = 0; k < n_sc; k++) {
+          uintptr_t a = reinterpret_cast<uintptr_t>(sc[k].rows);
+          if (a >= d0 && a < d0 + sp.pin->cap) sc[k].rows = reinterpret_cast<const uint32_t*>(m0 + (a - d0));
+          a = reinterpret_cast<uintptr_t>(sc[k].values);
+          if (a >= d0 && a < d0 + sp.pin->cap) sc[k].values = reinterpret_cast<const void*>(m0 + (a - d0));
+        }
+      }
+    }
     int launched = lwse::launch_scatter(sc, n_sc, e->n_nodes ? (uint32_t*)e->r_occ.p : nullptr, e->n_nodes, s, true, &cuda_err);
     if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
     e->launches += (uint64_t)launched;
