@@ -23,9 +23,18 @@ struct SweepChangeLists {
   lwse_group_out* group_out = nullptr;
   uint32_t group_capacity = 0;
   uint32_t* counts = nullptr;
-  uint32_t* host_words = nullptr;
-  uint32_t seq = 0;
 };
+struct PublishListHost {
+  const uint32_t* src_rows;
+  const void* src_outs;
+  uint32_t* dst_rows;
+  void* dst_outs;
+  uint32_t* count;
+  uint32_t capacity;
+  uint32_t out_bytes;
+};
+int launch_publish(const PublishListHost* lists, int n_lists, const uint32_t* d_extra, uint32_t* h_words, uint32_t seq_slot,
+                   uint32_t seq, uint32_t* d_ticket, uint32_t expected_rows, cudaStream_t s, int* cuda_err);
 int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
                      void* scratch, int sm_count, cudaStream_t s, int* cuda_err, const SweepChangeLists* cl,
                      uint32_t* d_event_count = nullptr, bool first_pdl = true);
@@ -62,9 +71,8 @@ int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, c
                     const uint32_t* d_occupancy, uint32_t n_parts, uint64_t part_stride_bytes, uint32_t n_namespaces,
                     lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes, bool fresh, uint32_t call_index, bool scan,
                     int sm_count, cudaStream_t s, int* cuda_err, const uint32_t** d_counters_out, bool first_pdl);
-int launch_place_publish(const lwse_place_out* d_cur, lwse_place_out* d_prev, uint32_t n, uint32_t* h_rows,
-                         lwse_place_out* h_outs, uint32_t capacity, uint32_t* d_count, uint32_t* d_ticket,
-                         const uint32_t* d_rounds, uint32_t* h_words, uint32_t seq, cudaStream_t s, int* cuda_err);
+int launch_place_diff(const lwse_place_out* d_cur, lwse_place_out* d_prev, uint32_t n, uint32_t* d_rows,
+                      lwse_place_out* d_outs, uint32_t capacity, uint32_t* d_count, cudaStream_t s, int* cuda_err);
 // lwse_ds_kernels.cu
 int launch_ds_sweep(const lwse_ds_tables* t, int sm_count, cudaStream_t s, int* cuda_err);
 // lwse_sha1_kernels.cu
@@ -174,6 +182,8 @@ struct lwse_engine {
   DevBuf arena_mirror, stage_mirror; // device copies of the two: a tick with many patches moves them with one DMA
                                      // copy per buffer (SM reads of host memory are latency-bound: ~6 GB/s measured)
   PinBuf chg;                        // change lists: [lws rows | lws out | group rows | group out | place rows | place out]
+  DevBuf chg_dev;                    // the same layout in device memory: the kernels append here, a publish kernel copies out
+  uint32_t last_changed[2] = {0, 0}; // rows the previous tick reported (sweep lists, placement list): sizes the publish grid
   PinBuf tickw;                      // [0] lws changes [1] group changes [2] sweep seq | [4] place changes [5] rounds [6] place seq
   size_t chg_off[6] = {};
   uint32_t rn_lws = 0, rn_groups = 0, rn_reqs = 0, rn_namespaces = 0;
@@ -371,7 +381,7 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
                       &e->ds_role_out, &e->ds_revrole_out, &e->sha_bytes, &e->sha_offsets, &e->sha_digests, &e->sha_ints,
                       &e->r_lws, &e->r_groups, &e->r_pst, &e->r_pid, &e->r_lws_out, &e->r_group_out, &e->r_scan,
                       &e->r_counts, &e->r_occ, &e->r_preq, &e->r_pout, &e->r_pout_prev, &e->h_counts_dev, &e->place_ns_scratch,
-                      &e->arena_mirror, &e->stage_mirror};
+                      &e->arena_mirror, &e->stage_mirror, &e->chg_dev};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&e->arena, &e->stage, &e->chg, &e->tickw};
     for (PinBuf* b : pins) b->release();
@@ -587,6 +597,7 @@ static int reserve_change_lists(lwse_engine* e) {
     off += align256(sizes[k] + 16);
   }
   LWSE_CUDA(e, e->chg.reserve(off));
+  LWSE_CUDA(e, e->chg_dev.reserve(off));
   LWSE_CUDA(e, e->tickw.reserve(256));
   return LWSE_OK;
 }
@@ -1343,7 +1354,8 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
   if (seq == 0) seq = ++e->tick_seq;
   volatile uint32_t* hw = static_cast<volatile uint32_t*>(e->tickw.h);
   uint32_t* hw_dev = static_cast<uint32_t*>(e->tickw.d);
-  uint8_t* chg_d = static_cast<uint8_t*>(e->chg.d);
+  uint8_t* chg_d = static_cast<uint8_t*>(e->chg.d);      // the pinned lists, as the device sees them
+  uint8_t* chg_v = static_cast<uint8_t*>(e->chg_dev.p);  // the device-memory lists the kernels append to
   const bool do_place = (flags & LWSE_TICK_PLACE) && e->r_place_loaded && e->rn_reqs > 0;
   const bool do_sweep = !(flags & LWSE_TICK_NO_SWEEP) && (e->rn_lws || e->rn_groups);
   // Patches go where their readers run: the placement request table is read only by the round on
@@ -1397,11 +1409,17 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
                         (lwse_place_out*)e->r_pout.p, nullptr, e->side_stream, 1, e->rn_reqs, 0, false, form, /*first_pdl=*/false);
     }
     if (rc != LWSE_OK) return rc;
-    int launched = lwse::launch_place_publish(
-        (const lwse_place_out*)e->r_pout.p, (lwse_place_out*)e->r_pout_prev.p, e->rn_reqs,
-        reinterpret_cast<uint32_t*>(chg_d + e->chg_off[4]), reinterpret_cast<lwse_place_out*>(chg_d + e->chg_off[5]),
-        e->rn_reqs, (uint32_t*)e->r_counts.p + 4, (uint32_t*)e->r_counts.p + 5, e->place_rounds_ptr, hw_dev + 4, seq,
-        e->side_stream, &cuda_err);
+    int launched = lwse::launch_place_diff((const lwse_place_out*)e->r_pout.p, (lwse_place_out*)e->r_pout_prev.p, e->rn_reqs,
+                                           reinterpret_cast<uint32_t*>(chg_v + e->chg_off[4]),
+                                           reinterpret_cast<lwse_place_out*>(chg_v + e->chg_off[5]), e->rn_reqs,
+                                           (uint32_t*)e->r_counts.p + 4, e->side_stream, &cuda_err);
+    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+    e->launches += (uint64_t)launched;
+    const lwse::PublishListHost pl[1] = {{reinterpret_cast<const uint32_t*>(chg_v + e->chg_off[4]), chg_v + e->chg_off[5],
+                                          reinterpret_cast<uint32_t*>(chg_d + e->chg_off[4]), chg_d + e->chg_off[5],
+                                          (uint32_t*)e->r_counts.p + 4, e->rn_reqs, (uint32_t)sizeof(lwse_place_out)}};
+    launched = lwse::launch_publish(pl, 1, e->place_rounds_ptr, hw_dev + 4, 2, seq, (uint32_t*)e->r_counts.p + 5,
+                                    e->last_changed[1], e->side_stream, &cuda_err);
     if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
     e->launches += (uint64_t)launched;
   }
@@ -1419,37 +1437,36 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
     d.group_out = (lwse_group_out*)e->r_group_out.p;
     d.flags = flags & LWSE_SWEEP_GANG;
     lwse::SweepChangeLists cl;
-    cl.lws_rows = reinterpret_cast<uint32_t*>(chg_d + e->chg_off[0]);
-    cl.lws_out = reinterpret_cast<lwse_lws_out*>(chg_d + e->chg_off[1]);
+    cl.lws_rows = reinterpret_cast<uint32_t*>(chg_v + e->chg_off[0]);
+    cl.lws_out = reinterpret_cast<lwse_lws_out*>(chg_v + e->chg_off[1]);
     cl.lws_capacity = e->rn_lws;
-    cl.group_rows = reinterpret_cast<uint32_t*>(chg_d + e->chg_off[2]);
-    cl.group_out = reinterpret_cast<lwse_group_out*>(chg_d + e->chg_off[3]);
+    cl.group_rows = reinterpret_cast<uint32_t*>(chg_v + e->chg_off[2]);
+    cl.group_out = reinterpret_cast<lwse_group_out*>(chg_v + e->chg_off[3]);
     cl.group_capacity = e->rn_groups;
     cl.counts = (uint32_t*)e->r_counts.p;
-    cl.host_words = hw_dev;
-    cl.seq = seq;
     int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes, e->r_scan.p, e->sm_count, s,
                                           &cuda_err, &cl, nullptr, /*first_pdl=*/!wrote);
     if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
     e->launches += (uint64_t)launched;
-    published = e->rn_lws > 0;  // the LWS pass's last CTA raises the sequence word
+    // the change lists (device memory) go to the pinned lists the caller reads; the last CTA raises the sequence word
+    const lwse::PublishListHost pl[2] = {
+        {cl.lws_rows, cl.lws_out, reinterpret_cast<uint32_t*>(chg_d + e->chg_off[0]), chg_d + e->chg_off[1],
+         (uint32_t*)e->r_counts.p + 0, e->rn_lws, (uint32_t)sizeof(lwse_lws_out)},
+        {cl.group_rows, cl.group_out, reinterpret_cast<uint32_t*>(chg_d + e->chg_off[2]), chg_d + e->chg_off[3],
+         (uint32_t*)e->r_counts.p + 1, e->rn_groups, (uint32_t)sizeof(lwse_group_out)}};
+    launched = lwse::launch_publish(pl, 2, nullptr, hw_dev, 2, seq, (uint32_t*)e->r_counts.p + 2, e->last_changed[0], s, &cuda_err);
+    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+    e->launches += (uint64_t)launched;
+    published = true;
   }
   // ---- the tick's only wait ----
   cudaError_t werr = cudaSuccess;
   bool ok = true;
   if (published) {
     ok = wait_word(hw + 2, seq, s, &werr);
-  } else if (do_sweep || wrote) {
+  } else if (wrote) {
     werr = cudaStreamSynchronize(s);
     ok = werr == cudaSuccess;
-    if (ok && do_sweep) {  // (no LWS rows: fetch the group pass's counter the slow way)
-      uint32_t c[2] = {0, 0};
-      werr = cudaMemcpy(c, e->r_counts.p, 8, cudaMemcpyDeviceToHost);
-      if (werr == cudaSuccess) werr = cudaMemset(e->r_counts.p, 0, 8);
-      ok = werr == cudaSuccess;
-      hw[0] = c[0];
-      hw[1] = c[1];
-    }
   }
   if (ok && do_place) ok = wait_word(hw + 6, seq, e->side_stream, &werr);
   if (ok && !do_place && wrote_side) {
@@ -1464,6 +1481,8 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
   out->n_groups = do_sweep ? hw[1] : 0u;
   out->n_place = do_place ? hw[4] : 0u;
   out->rounds = do_place ? hw[5] : 0u;
+  e->last_changed[0] = out->n_lws + out->n_groups;
+  e->last_changed[1] = out->n_place;
   return LWSE_OK;
 }
 

@@ -176,7 +176,9 @@ int launch_ident_prefetch(const uint8_t* d_state, uint64_t n_pods, const lwse_po
 // group pass
 // --------------------------------------------------------------------------
 // Optional change list: result rows that differ from what the output table held before.  The
-// list may live in mapped host memory (lwse_resident_tick): writers fence at system scope.
+// lists live in device memory; a tick's publish kernel moves them to the host in one coalesced
+// pass (a system-scope fence per changed row — the first version wrote rows straight into mapped
+// host memory — cost 20 us per thousand rows).
 struct ChangeList {
   uint32_t* rows;   // nullptr = off
   void* outs;       // packed result rows
@@ -199,7 +201,6 @@ __device__ __forceinline__ void emit_if_changed(const ChangeList& c, uint4* slot
         c.rows[i] = row;
 #pragma unroll
         for (int k = 0; k < N; k++) reinterpret_cast<uint4*>(c.outs)[(size_t)i * N + k] = v[k];
-        __threadfence_system();  // the list may be host memory read right after the tick's flag
       }
     }
   }
@@ -716,16 +717,6 @@ __global__ void __launch_bounds__(kFusedThreads, 3) group_fused_kernel(const Gro
 // --------------------------------------------------------------------------
 // LWS-level pass
 // --------------------------------------------------------------------------
-// A tick's last kernel tells the host that the results are in (lwse_resident_tick): the last
-// CTA copies the change-list counters to mapped host memory and then raises the sequence
-// number the host spins on — no stream synchronize on the critical path.
-struct TickPublish {
-  uint32_t* host_words;      // mapped host memory: [0] lws changes, [1] group changes, [2] sequence; nullptr = off
-  uint32_t* device_counts;   // [0] lws, [1] groups (reset here for the next tick)
-  uint32_t* ticket;          // device: CTA completion counter
-  uint32_t seq;
-};
-
 struct LwsSweepArgs {
   const lwse_lws_rec* lws;
   const uint8_t* gflag8;  // one flag byte per group (written by the group pass)
@@ -734,7 +725,6 @@ struct LwsSweepArgs {
   uint32_t n_groups;
   uint32_t sweep_flags;
   ChangeList changes;
-  TickPublish publish;
 };
 
 __device__ __forceinline__ int32_t want_replicas(int32_t lws_replicas, int32_t surge, int32_t mu,
@@ -770,7 +760,6 @@ __device__ __forceinline__ int32_t highest_lane(uint64_t m) { return (63 - __clz
 template <int W>
 __global__ void __launch_bounds__(256) lws_sweep_kernel(const LwsSweepArgs a) {
   constexpr uint32_t kTilesPerBlock = 256 / W;
-  __shared__ uint32_t s_last;
   const uint32_t lane = threadIdx.x & (W - 1);
   const uint32_t n_tiles = gridDim.x * kTilesPerBlock;
   const uint64_t* words = reinterpret_cast<const uint64_t*>(a.gflag8);
@@ -950,25 +939,6 @@ __global__ void __launch_bounds__(256) lws_sweep_kernel(const LwsSweepArgs a) {
       emit_if_changed<2>(a.changes, reinterpret_cast<uint4*>(a.out + i), i, v);
     }
   }
-  if (a.publish.host_words != nullptr) {
-    if (!waited) pdl_wait_prior();  // a CTA without rows still has to see the group pass's counter
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(a.publish.ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
-    __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-      __threadfence();
-      const uint32_t nl = __ldcg(a.publish.device_counts + 0), ng = __ldcg(a.publish.device_counts + 1);
-      a.publish.device_counts[0] = 0u;  // ready for the next tick (stream-ordered)
-      a.publish.device_counts[1] = 0u;
-      *a.publish.ticket = 0u;
-      volatile uint32_t* hw = a.publish.host_words;
-      hw[0] = nl;
-      hw[1] = ng;
-      __threadfence_system();
-      hw[2] = a.publish.seq;
-    }
-  }
 }
 
 // --------------------------------------------------------------------------
@@ -1041,9 +1011,7 @@ struct SweepChangeLists {  // device (or mapped host) pointers; all null = off
   uint32_t* group_rows = nullptr;
   lwse_group_out* group_out = nullptr;
   uint32_t group_capacity = 0;
-  uint32_t* counts = nullptr;  // device: [0] lws, [1] groups, [2] ticket; zeroed by the caller
-  uint32_t* host_words = nullptr;  // mapped host: the LWS pass publishes the counts and `seq` there
-  uint32_t seq = 0;
+  uint32_t* counts = nullptr;  // device: [0] lws, [1] groups; zeroed by the caller (a tick's publish kernel resets them)
 };
 
 // first_pdl: the sweep's first kernel may start before the previous kernel on the stream has
@@ -1118,9 +1086,8 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
     launches++;
   }
   if (t->n_lws && !(t->flags & LWSE_SWEEP_SKIP_LWS_PASS)) {
-    LwsSweepArgs a{t->lws, gflag8, t->lws_out, t->n_lws, t->n_groups, t->flags, ChangeList{}, TickPublish{}};
+    LwsSweepArgs a{t->lws, gflag8, t->lws_out, t->n_lws, t->n_groups, t->flags, ChangeList{}};
     if (cl && cl->lws_rows) a.changes = ChangeList{cl->lws_rows, cl->lws_out, cl->counts + 0, cl->lws_capacity};
-    if (cl && cl->host_words) a.publish = TickPublish{cl->host_words, cl->counts, cl->counts + 2, cl->seq};
     switch (pick_tile(t->n_groups, t->n_lws)) {
       case 1: e = launch_lws<1>(a, sm_count, s); break;
       case 2: e = launch_lws<2>(a, sm_count, s); break;
@@ -1133,6 +1100,98 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
     launches++;
   }
   return launches;
+}
+
+// --------------------------------------------------------------------------
+// tick: change lists to the host
+// --------------------------------------------------------------------------
+// The last kernel of each branch of a tick (lwse_resident_tick).  The sweep / placement kernels
+// appended the changed rows to device-memory lists; this kernel copies the used part of up to
+// three lists into pinned, mapped host memory with coalesced stores, every writing thread fences
+// ONCE at system scope, and the last CTA publishes the counts and then the sequence word the host
+// spins on — no stream synchronize, no copy-engine launch on the critical path.
+struct PublishList {
+  const uint32_t* src_rows;
+  const uint4* src_outs;
+  uint32_t* dst_rows;   // mapped host
+  uint4* dst_outs;      // mapped host
+  uint32_t* count;      // device counter (reset here)
+  uint32_t capacity;
+  uint32_t out_vec;     // uint4 per result row
+};
+struct PublishArgs {
+  PublishList list[3];
+  uint32_t n_lists;
+  const uint32_t* extra;   // nullable: one more device word to publish (the placement round counter)
+  uint32_t* host_words;    // mapped host: [k] = count of list k, [n_lists] = extra, then the sequence word at [seq_slot]
+  uint32_t seq_slot;
+  uint32_t seq;
+  uint32_t* ticket;
+};
+
+__global__ void __launch_bounds__(256) publish_lists_kernel(const PublishArgs a) {
+  __shared__ uint32_t s_last;
+  pdl_wait_prior();  // every producer kernel of this branch has completed: lists and counters are final
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  bool wrote = false;
+  uint32_t counts[3] = {0, 0, 0};
+  for (uint32_t k = 0; k < a.n_lists; k++) {
+    const PublishList& l = a.list[k];
+    counts[k] = __ldcg(l.count);
+    const uint32_t n = min(counts[k], l.capacity);
+    for (uint32_t i = gtid; i < n; i += gsize) l.dst_rows[i] = __ldcg(l.src_rows + i);
+    for (uint32_t i = gtid; i < n * l.out_vec; i += gsize) l.dst_outs[i] = __ldcg(l.src_outs + i);
+    wrote |= gtid < n * l.out_vec;
+  }
+  if (wrote) __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    volatile uint32_t* hw = a.host_words;
+    for (uint32_t k = 0; k < a.n_lists; k++) {
+      hw[k] = counts[k];
+      *a.list[k].count = 0u;  // ready for the next tick (stream-ordered)
+    }
+    if (a.extra != nullptr) hw[a.n_lists] = __ldcg(a.extra);
+    *a.ticket = 0u;
+    __threadfence_system();
+    hw[a.seq_slot] = a.seq;
+  }
+}
+
+struct PublishListHost {
+  const uint32_t* src_rows;
+  const void* src_outs;
+  uint32_t* dst_rows;
+  void* dst_outs;
+  uint32_t* count;
+  uint32_t capacity;
+  uint32_t out_bytes;
+};
+
+int launch_publish(const PublishListHost* lists, int n_lists, const uint32_t* d_extra, uint32_t* h_words, uint32_t seq_slot,
+                   uint32_t seq, uint32_t* d_ticket, uint32_t expected_rows, cudaStream_t s, int* cuda_err) {
+  *cuda_err = 0;
+  PublishArgs a{};
+  for (int k = 0; k < n_lists && k < 3; k++)
+    a.list[k] = PublishList{lists[k].src_rows, static_cast<const uint4*>(lists[k].src_outs), lists[k].dst_rows,
+                            static_cast<uint4*>(lists[k].dst_outs), lists[k].count, lists[k].capacity, lists[k].out_bytes / 16u};
+  a.n_lists = (uint32_t)n_lists;
+  a.extra = d_extra;
+  a.host_words = h_words;
+  a.seq_slot = seq_slot;
+  a.seq = seq;
+  a.ticket = d_ticket;
+  // a few CTAs for the usual few thousand rows; more when the previous tick reported many
+  unsigned grid = expected_rows / 1024u + 4u;
+  if (grid > 64u) grid = 64u;
+  const cudaError_t e = launch_pdl(publish_lists_kernel, dim3(grid), dim3(256), 0, s, g_pdl, a);
+  if (e != cudaSuccess) {
+    *cuda_err = (int)e;
+    return -1;
+  }
+  return 1;
 }
 
 // --------------------------------------------------------------------------

@@ -584,25 +584,21 @@ int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, cons
 // tick: which placement rows changed
 // --------------------------------------------------------------------------
 // Runs right after the placement kernel of a resident tick (programmatically dependent on it):
-// result rows that differ from the previous tick's go to the change list in mapped host memory,
-// the previous-result table is brought up to date, and the last CTA publishes the count, the
-// number of rounds and the tick's sequence number for the host to spin on.
-struct PlacePublishArgs {
+// result rows that differ from the previous tick's are appended to a device-memory change list
+// and the previous-result table is brought up to date.  The tick's publish kernel
+// (lwse_lws_kernels.cu) then moves the list to the host.
+struct PlaceDiffArgs {
   const lwse_place_out* cur;
   lwse_place_out* prev;
   uint32_t n;
-  uint32_t* rows;        // mapped host
-  lwse_place_out* outs;  // mapped host
+  uint32_t* rows;        // device list
+  lwse_place_out* outs;
   uint32_t capacity;
-  uint32_t* d_count;     // device counter (reset here)
-  uint32_t* ticket;
-  const uint32_t* rounds;  // the placement kernel's round counter
-  uint32_t* host_words;    // mapped host: [0] changed rows, [1] rounds, [2] sequence
-  uint32_t seq;
+  uint32_t* d_count;
 };
 
-__global__ void __launch_bounds__(256) place_publish_kernel(const PlacePublishArgs a) {
-  __shared__ uint32_t s_last;
+__global__ void __launch_bounds__(256) place_diff_kernel(const PlaceDiffArgs a) {
+  pdl_launch_dependents();
   pdl_wait_prior();
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += gridDim.x * blockDim.x) {
     const uint4 v = __ldcg(reinterpret_cast<const uint4*>(a.cur + r));
@@ -612,37 +608,20 @@ __global__ void __launch_bounds__(256) place_publish_kernel(const PlacePublishAr
       if (i < a.capacity) {
         a.rows[i] = r;
         *reinterpret_cast<uint4*>(a.outs + i) = v;
-        __threadfence_system();
       }
       *reinterpret_cast<uint4*>(a.prev + r) = v;
     }
   }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    __threadfence();
-    const uint32_t n = __ldcg(a.d_count);
-    *a.d_count = 0u;
-    *a.ticket = 0u;
-    volatile uint32_t* hw = a.host_words;
-    hw[0] = n;
-    hw[1] = __ldcg(a.rounds);
-    __threadfence_system();
-    hw[2] = a.seq;
-  }
 }
 
-int launch_place_publish(const lwse_place_out* d_cur, lwse_place_out* d_prev, uint32_t n, uint32_t* h_rows,
-                         lwse_place_out* h_outs, uint32_t capacity, uint32_t* d_count, uint32_t* d_ticket,
-                         const uint32_t* d_rounds, uint32_t* h_words, uint32_t seq, cudaStream_t s, int* cuda_err) {
+int launch_place_diff(const lwse_place_out* d_cur, lwse_place_out* d_prev, uint32_t n, uint32_t* d_rows,
+                      lwse_place_out* d_outs, uint32_t capacity, uint32_t* d_count, cudaStream_t s, int* cuda_err) {
   *cuda_err = 0;
-  PlacePublishArgs a{d_cur, d_prev, n, h_rows, h_outs, capacity, d_count, d_ticket, d_rounds, h_words, seq};
+  PlaceDiffArgs a{d_cur, d_prev, n, d_rows, d_outs, capacity, d_count};
   unsigned grid = (n + 255u) / 256u;
   if (grid < 1u) grid = 1u;
   if (grid > 148u * 4u) grid = 148u * 4u;
-  const cudaError_t e = launch_pdl(place_publish_kernel, dim3(grid), dim3(256), 0, s, true, a);
+  const cudaError_t e = launch_pdl(place_diff_kernel, dim3(grid), dim3(256), 0, s, true, a);
   if (e != cudaSuccess) {
     *cuda_err = (int)e;
     return -1;
