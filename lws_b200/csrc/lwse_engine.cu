@@ -33,7 +33,7 @@ struct PublishListHost {
   uint32_t capacity;
   uint32_t out_bytes;
 };
-int launch_publish(const PublishListHost* lists, int n_lists, const uint32_t* d_extra, uint32_t* h_words, uint32_t seq_slot,
+int launch_publish(const PublishListHost* lists, const uint32_t* d_extra, uint32_t* h_words, uint32_t seq_slot,
                    uint32_t seq, uint32_t* d_ticket, uint32_t expected_rows, cudaStream_t s, int* cuda_err);
 int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
                      void* scratch, int sm_count, cudaStream_t s, int* cuda_err, const SweepChangeLists* cl,
@@ -65,12 +65,20 @@ int launch_place(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, cons
                  bool after_push);
 size_t place_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces);
 size_t place_ns_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces);
+struct PlaceNsChanges {  // a tick's placement change list (device memory); prev == null: off
+  lwse_place_out* prev;
+  uint32_t* rows;
+  lwse_place_out* outs;
+  uint32_t* count;
+  uint32_t capacity;
+};
 bool place_ns_supported(uint32_t n_nodes, uint32_t n_domains);
 int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, const uint32_t* d_node_order, uint32_t n_nodes,
                     uint32_t n_usable, uint32_t n_domains, const lwse_place_req* d_reqs, uint32_t n_reqs,
                     const uint32_t* d_occupancy, uint32_t n_parts, uint64_t part_stride_bytes, uint32_t n_namespaces,
                     lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes, bool fresh, uint32_t call_index, bool scan,
-                    int sm_count, cudaStream_t s, int* cuda_err, const uint32_t** d_counters_out, bool first_pdl);
+                    int sm_count, cudaStream_t s, int* cuda_err, const uint32_t** d_counters_out, bool first_pdl,
+                    const PlaceNsChanges* changes);
 int launch_place_diff(const lwse_place_out* d_cur, lwse_place_out* d_prev, uint32_t n, uint32_t* d_rows,
                       lwse_place_out* d_outs, uint32_t capacity, uint32_t* d_count, cudaStream_t s, int* cuda_err);
 // lwse_ds_kernels.cu
@@ -174,7 +182,7 @@ struct lwse_engine {
   uint32_t ident_hint_events = 0;    // event pods the previous host sweep of that table visited
   // resident tables (lwse_resident_*)
   DevBuf r_lws, r_groups, r_pst, r_pid, r_lws_out, r_group_out, r_scan;
-  DevBuf r_counts;                   // [0] lws changes, [1] group changes, [2] sweep ticket, [4] place changes, [5] place ticket
+  DevBuf r_counts;                   // [0] lws changes, [1] group changes, [2] publish ticket, [4] place changes
   DevBuf r_occ;                      // scheduled pods per node of the resident identity column
   DevBuf r_preq, r_pout, r_pout_prev;  // resident placement requests / results of this and the previous tick
   PinBuf arena;                      // patch arena handed to the caller
@@ -184,7 +192,7 @@ struct lwse_engine {
   PinBuf chg;                        // change lists: [lws rows | lws out | group rows | group out | place rows | place out]
   DevBuf chg_dev;                    // the same layout in device memory: the kernels append here, a publish kernel copies out
   uint32_t last_changed[2] = {0, 0}; // rows the previous tick reported (sweep lists, placement list): sizes the publish grid
-  PinBuf tickw;                      // [0] lws changes [1] group changes [2] sweep seq | [4] place changes [5] rounds [6] place seq
+  PinBuf tickw;                      // [0] lws changes [1] group changes [2] place changes [3] placement rounds [4] sequence word
   size_t chg_off[6] = {};
   uint32_t rn_lws = 0, rn_groups = 0, rn_reqs = 0, rn_namespaces = 0;
   uint64_t rn_pods = 0;
@@ -889,7 +897,8 @@ static const int g_place_form_env = [] {  // LWSE_PLACE_FORM=general|grouped|sca
 // namespace.  `first_pdl`: nothing on the stream right before writes the request table.
 static int place_grouped_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs, const uint32_t* d_occupancy,
                                 uint32_t n_parts, uint64_t part_stride_bytes, uint32_t n_namespaces, lwse_place_out* d_out,
-                                bool scan, uint32_t* rounds_out, uint32_t* scans_out, cudaStream_t s, bool first_pdl) {
+                                bool scan, uint32_t* rounds_out, uint32_t* scans_out, cudaStream_t s, bool first_pdl,
+                                const lwse::PlaceNsChanges* changes = nullptr) {
   const size_t scratch = lwse::place_ns_scratch_bytes(e->n_nodes, e->n_domains, n_reqs, n_namespaces);
   const void* before = e->place_ns_scratch.p;
   LWSE_CUDA(e, e->place_ns_scratch.reserve(scratch));
@@ -905,12 +914,12 @@ static int place_grouped_locked(lwse_engine* e, const lwse_place_req* d_reqs, ui
                                        (const uint32_t*)e->node_order.p, e->n_nodes, e->n_usable, e->n_domains, d_reqs, n_reqs,
                                        d_occupancy, n_parts, part_stride_bytes, n_namespaces, d_out, e->place_ns_scratch.p,
                                        scratch, fresh, e->place_ns_calls++, scan, e->sm_count, s, &cuda_err, &counters,
-                                       first_pdl && !fresh);
+                                       first_pdl && !fresh, changes);
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
   e->place_rounds_ptr = counters;
   e->place_scans_ptr = counters + 3;
-  if (eager) {
+  if (eager && !changes) {  // (a tick — `changes` — returns only after the host has seen the round complete)
     LWSE_CUDA(e, cudaEventRecord(e->ev_place, s));
     e->place_pending = true;
   }
@@ -927,14 +936,17 @@ static int place_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n
                         const uint32_t* d_occupancy, uint32_t n_namespaces, lwse_place_out* d_out,
                         uint32_t* rounds_out, cudaStream_t s, uint32_t n_parts, uint32_t reqs_per_part,
                         uint64_t part_stride_bytes, bool after_push = false, uint32_t form = kFormGeneral,
-                        bool first_pdl = false) {
+                        bool first_pdl = false, const lwse::PlaceNsChanges* changes = nullptr, bool* diffed = nullptr) {
   if ((n_reqs && (!d_reqs || !d_out)) || n_namespaces == 0) return LWSE_ERR_INVALID_ARG;
   if (e->n_nodes == 0 || e->n_domains == 0) return LWSE_ERR_NOT_READY;
   if (g_place_form_env == 0) form = kFormGeneral;
   if (g_place_form_env == 2 && form != kFormGeneral) form = kFormScan;
-  if (form != kFormGeneral && n_parts <= 1 && lwse::place_ns_supported(e->n_nodes, e->n_domains))
+  if (diffed) *diffed = false;
+  if (form != kFormGeneral && n_parts <= 1 && lwse::place_ns_supported(e->n_nodes, e->n_domains)) {
+    if (diffed) *diffed = changes != nullptr;
     return place_grouped_locked(e, d_reqs, n_reqs, d_occupancy, 1, 0, n_namespaces, d_out, form == kFormScan, rounds_out, nullptr,
-                                s, first_pdl);
+                                s, first_pdl, changes);
+  }
   const size_t scratch = lwse::place_scratch_bytes(e->n_nodes, e->n_domains, n_reqs, n_namespaces);
   const void* before = e->place_scratch.p;
   LWSE_CUDA(e, e->place_scratch.reserve(scratch));
@@ -1152,7 +1164,8 @@ LWSE_API int lwse_reconcile_exchanged_device(lwse_engine* e, const lwse_lws_tabl
 // ranks' counters.  Enqueued on `ps`.  lagged: read the previous step's snapshot (see the kernel file).
 static int shared_occupancy_place_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs,
                                          const uint32_t* d_local_occ, uint32_t n_namespaces, lwse_place_out* d_out,
-                                         uint32_t form, bool lagged, cudaStream_t ps) {
+                                         uint32_t form, bool lagged, cudaStream_t ps,
+                                         const lwse::PlaceNsChanges* changes = nullptr) {
   const uint64_t step = ++e->xch_step;
   const uint64_t read_step = (lagged && step > 1) ? step - 1 : step;
   int cuda_err = 0;
@@ -1166,7 +1179,7 @@ static int shared_occupancy_place_locked(lwse_engine* e, const lwse_place_req* d
   const uint32_t* occ_parts = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(e->xch.p) + (read_step % 3ull) * e->xch_half);
   if (form != kFormGeneral && lwse::place_ns_supported(e->n_nodes, e->n_domains))
     return place_grouped_locked(e, d_reqs, n_reqs, occ_parts, e->xch_world, e->xch_stride, n_namespaces, d_out,
-                                form == kFormScan, nullptr, nullptr, ps, /*first_pdl=*/false);
+                                form == kFormScan, nullptr, nullptr, ps, /*first_pdl=*/false, changes);
   return LWSE_ERR_UNSUPPORTED;  // the shared-occupancy form needs a request table grouped by namespace
 }
 
@@ -1358,17 +1371,7 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
   uint8_t* chg_v = static_cast<uint8_t*>(e->chg_dev.p);  // the device-memory lists the kernels append to
   const bool do_place = (flags & LWSE_TICK_PLACE) && e->r_place_loaded && e->rn_reqs > 0;
   const bool do_sweep = !(flags & LWSE_TICK_NO_SWEEP) && (e->rn_lws || e->rn_groups);
-  // Patches go where their readers run: the placement request table is read only by the round on
-  // the side stream, everything else by the sweep on the engine's stream — the (long) round then
-  // starts behind its own few rows instead of behind the whole scatter.  Identity-row patches move
-  // occupancy counts, which the round reads: with those in the tick it forks behind the main scatter.
-  constexpr uint32_t kSideTables = 1u << LWSE_TABLE_PLACE_REQS;
-  bool has_ident = false, has_side = false;
-  for (uint32_t i = 0; i < n_segs; i++) {
-    if (!segs) return LWSE_ERR_INVALID_ARG;
-    if (segs[i].n && segs[i].table == LWSE_TABLE_POD_IDENT) has_ident = true;
-    if (segs[i].n && segs[i].table == LWSE_TABLE_PLACE_REQS) has_side = true;
-  }
+  if (n_segs && !segs) return LWSE_ERR_INVALID_ARG;
   {
     const size_t ub = stage_bytes_upper_bound(segs, n_segs);
     if (ub > e->stage.cap) {  // rare: only segments outside the arena are staged
@@ -1384,47 +1387,16 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
       }
     }
   }
-  bool wrote = false, wrote_side = false;
-  size_t stage_used = 0;
-  int rc = apply_patches_locked(e, segs, n_segs, &wrote, ~kSideTables, s, 0, &stage_used);
+  // One scatter applies every segment (one DMA copy of the arena span when the set is large); the
+  // placement round forks behind it on the side stream while the sweep runs on the engine's stream,
+  // and ONE publish kernel behind the join copies all change lists out and raises the word.
+  bool wrote = false;
+  int rc = apply_patches_locked(e, segs, n_segs, &wrote, 0xFFFFFFFFu, s, 0, nullptr);
   if (rc != LWSE_OK) return rc;
   int cuda_err = 0;
-  if (do_place || has_side) {
-    if (has_ident) {  // the round reads the occupancy counters the main scatter just moved
-      LWSE_CUDA(e, cudaEventRecord(e->ev_fork, s));
-      LWSE_CUDA(e, cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
-    }
-    rc = apply_patches_locked(e, segs, n_segs, &wrote_side, kSideTables, e->side_stream, stage_used, nullptr);
-    if (rc != LWSE_OK) return rc;
-  }
-  if (do_place) {
-    const uint32_t form = !e->r_place_grouped ? kFormGeneral : (flags & LWSE_SWEEP_PLACE_SCAN) ? kFormScan : kFormGrouped;
-    if (flags & LWSE_TICK_SHARED_OCCUPANCY) {  // multi-rank: this rank's counters go to the peers, the round sees the sum
-      if (!e->xch_connected) return LWSE_ERR_NOT_READY;
-      rc = shared_occupancy_place_locked(e, (const lwse_place_req*)e->r_preq.p, e->rn_reqs, (const uint32_t*)e->r_occ.p,
-                                         e->rn_namespaces, (lwse_place_out*)e->r_pout.p, form,
-                                         (flags & LWSE_EXCHANGE_LAGGED) != 0, e->side_stream);
-    } else {
-      rc = place_locked(e, (const lwse_place_req*)e->r_preq.p, e->rn_reqs, (const uint32_t*)e->r_occ.p, e->rn_namespaces,
-                        (lwse_place_out*)e->r_pout.p, nullptr, e->side_stream, 1, e->rn_reqs, 0, false, form, /*first_pdl=*/false);
-    }
-    if (rc != LWSE_OK) return rc;
-    int launched = lwse::launch_place_diff((const lwse_place_out*)e->r_pout.p, (lwse_place_out*)e->r_pout_prev.p, e->rn_reqs,
-                                           reinterpret_cast<uint32_t*>(chg_v + e->chg_off[4]),
-                                           reinterpret_cast<lwse_place_out*>(chg_v + e->chg_off[5]), e->rn_reqs,
-                                           (uint32_t*)e->r_counts.p + 4, e->side_stream, &cuda_err);
-    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
-    e->launches += (uint64_t)launched;
-    const lwse::PublishListHost pl[1] = {{reinterpret_cast<const uint32_t*>(chg_v + e->chg_off[4]), chg_v + e->chg_off[5],
-                                          reinterpret_cast<uint32_t*>(chg_d + e->chg_off[4]), chg_d + e->chg_off[5],
-                                          (uint32_t*)e->r_counts.p + 4, e->rn_reqs, (uint32_t)sizeof(lwse_place_out)}};
-    launched = lwse::launch_publish(pl, 1, e->place_rounds_ptr, hw_dev + 4, 2, seq, (uint32_t*)e->r_counts.p + 5,
-                                    e->last_changed[1], e->side_stream, &cuda_err);
-    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
-    e->launches += (uint64_t)launched;
-  }
-  bool published = false;
-  if (do_sweep) {
+  if (do_place && wrote) LWSE_CUDA(e, cudaEventRecord(e->ev_fork, s));
+  lwse::PublishListHost pl[3] = {};
+  if (do_sweep) {  // enqueued first: the engine's stream is the longer chain's head start
     lwse_lws_tables d{};
     d.lws = (const lwse_lws_rec*)e->r_lws.p;
     d.n_lws = e->rn_lws;
@@ -1448,39 +1420,68 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
                                           &cuda_err, &cl, nullptr, /*first_pdl=*/!wrote);
     if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
     e->launches += (uint64_t)launched;
-    // the change lists (device memory) go to the pinned lists the caller reads; the last CTA raises the sequence word
-    const lwse::PublishListHost pl[2] = {
-        {cl.lws_rows, cl.lws_out, reinterpret_cast<uint32_t*>(chg_d + e->chg_off[0]), chg_d + e->chg_off[1],
-         (uint32_t*)e->r_counts.p + 0, e->rn_lws, (uint32_t)sizeof(lwse_lws_out)},
-        {cl.group_rows, cl.group_out, reinterpret_cast<uint32_t*>(chg_d + e->chg_off[2]), chg_d + e->chg_off[3],
-         (uint32_t*)e->r_counts.p + 1, e->rn_groups, (uint32_t)sizeof(lwse_group_out)}};
-    launched = lwse::launch_publish(pl, 2, nullptr, hw_dev, 2, seq, (uint32_t*)e->r_counts.p + 2, e->last_changed[0], s, &cuda_err);
+    pl[0] = {cl.lws_rows, cl.lws_out, reinterpret_cast<uint32_t*>(chg_d + e->chg_off[0]), chg_d + e->chg_off[1],
+             (uint32_t*)e->r_counts.p + 0, e->rn_lws, (uint32_t)sizeof(lwse_lws_out)};
+    pl[1] = {cl.group_rows, cl.group_out, reinterpret_cast<uint32_t*>(chg_d + e->chg_off[2]), chg_d + e->chg_off[3],
+             (uint32_t*)e->r_counts.p + 1, e->rn_groups, (uint32_t)sizeof(lwse_group_out)};
+  }
+  if (do_place) {
+    cudaStream_t ps = e->side_stream;
+    if (wrote) LWSE_CUDA(e, cudaStreamWaitEvent(ps, e->ev_fork, 0));
+    const uint32_t form = !e->r_place_grouped ? kFormGeneral : (flags & LWSE_SWEEP_PLACE_SCAN) ? kFormScan : kFormGrouped;
+    // the namespace kernels append the changed rows themselves; the general form gets a diff kernel
+    const lwse::PlaceNsChanges changes{(lwse_place_out*)e->r_pout_prev.p, reinterpret_cast<uint32_t*>(chg_v + e->chg_off[4]),
+                                       reinterpret_cast<lwse_place_out*>(chg_v + e->chg_off[5]), (uint32_t*)e->r_counts.p + 4,
+                                       e->rn_reqs};
+    bool diffed = false;
+    if (flags & LWSE_TICK_SHARED_OCCUPANCY) {  // multi-rank: this rank's counters go to the peers, the round sees the sum
+      if (!e->xch_connected) return LWSE_ERR_NOT_READY;
+      rc = shared_occupancy_place_locked(e, (const lwse_place_req*)e->r_preq.p, e->rn_reqs, (const uint32_t*)e->r_occ.p,
+                                         e->rn_namespaces, (lwse_place_out*)e->r_pout.p, form,
+                                         (flags & LWSE_EXCHANGE_LAGGED) != 0, ps, &changes);
+      diffed = rc == LWSE_OK;
+    } else {
+      rc = place_locked(e, (const lwse_place_req*)e->r_preq.p, e->rn_reqs, (const uint32_t*)e->r_occ.p, e->rn_namespaces,
+                        (lwse_place_out*)e->r_pout.p, nullptr, ps, 1, e->rn_reqs, 0, false, form, /*first_pdl=*/false, &changes,
+                        &diffed);
+    }
+    if (rc != LWSE_OK) return rc;
+    if (!diffed) {
+      int launched = lwse::launch_place_diff((const lwse_place_out*)e->r_pout.p, changes.prev, e->rn_reqs, changes.rows,
+                                             changes.outs, changes.capacity, changes.count, ps, &cuda_err);
+      if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+      e->launches += (uint64_t)launched;
+    }
+    LWSE_CUDA(e, cudaEventRecord(e->ev_join, ps));
+    LWSE_CUDA(e, cudaStreamWaitEvent(s, e->ev_join, 0));
+    pl[2] = {changes.rows, changes.outs, reinterpret_cast<uint32_t*>(chg_d + e->chg_off[4]), chg_d + e->chg_off[5], changes.count,
+             e->rn_reqs, (uint32_t)sizeof(lwse_place_out)};
+  }
+  const bool published = do_sweep || do_place;
+  if (published) {
+    int launched = lwse::launch_publish(pl, do_place ? e->place_rounds_ptr : nullptr, hw_dev, 4, seq, (uint32_t*)e->r_counts.p + 2,
+                                        e->last_changed[0] + e->last_changed[1], s, &cuda_err);
     if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
     e->launches += (uint64_t)launched;
-    published = true;
   }
   // ---- the tick's only wait ----
   cudaError_t werr = cudaSuccess;
   bool ok = true;
   if (published) {
-    ok = wait_word(hw + 2, seq, s, &werr);
+    ok = wait_word(hw + 4, seq, s, &werr);
   } else if (wrote) {
     werr = cudaStreamSynchronize(s);
-    ok = werr == cudaSuccess;
-  }
-  if (ok && do_place) ok = wait_word(hw + 6, seq, e->side_stream, &werr);
-  if (ok && !do_place && wrote_side) {
-    werr = cudaStreamSynchronize(e->side_stream);
     ok = werr == cudaSuccess;
   }
   if (!ok) {
     const cudaError_t a = cudaStreamSynchronize(s), b = cudaStreamSynchronize(e->side_stream);
     return fail_cuda(e, werr != cudaSuccess ? werr : a != cudaSuccess ? a : b != cudaSuccess ? b : cudaErrorUnknown);
   }
+  if (do_place) e->place_pending = false;  // the publish kernel ran behind the join: the round is complete
   out->n_lws = do_sweep ? hw[0] : 0u;
   out->n_groups = do_sweep ? hw[1] : 0u;
-  out->n_place = do_place ? hw[4] : 0u;
-  out->rounds = do_place ? hw[5] : 0u;
+  out->n_place = do_place ? hw[2] : 0u;
+  out->rounds = do_place ? hw[3] : 0u;
   e->last_changed[0] = out->n_lws + out->n_groups;
   e->last_changed[1] = out->n_place;
   return LWSE_OK;

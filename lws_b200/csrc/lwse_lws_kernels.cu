@@ -1105,55 +1105,64 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
 // --------------------------------------------------------------------------
 // tick: change lists to the host
 // --------------------------------------------------------------------------
-// The last kernel of each branch of a tick (lwse_resident_tick).  The sweep / placement kernels
-// appended the changed rows to device-memory lists; this kernel copies the used part of up to
-// three lists into pinned, mapped host memory with coalesced stores, every writing thread fences
-// ONCE at system scope, and the last CTA publishes the counts and then the sequence word the host
+// The last kernel of a tick (lwse_resident_tick).  The sweep / placement kernels appended the
+// changed rows to device-memory lists; this kernel copies the used part of up to three lists into
+// pinned, mapped host memory with coalesced stores and then raises the sequence word the host
 // spins on — no stream synchronize, no copy-engine launch on the critical path.
+// Ordering: a system-scope fence costs microseconds and fences from many threads queue up behind
+// each other (one per writing thread measured 15-25 us for this kernel), so there is exactly ONE:
+// every CTA orders its stores with bar.sync + a gpu-scope fence before it takes a ticket, the last
+// CTA acquires with a gpu-scope fence, writes the counts, fences once at system scope (cumulative:
+// it covers everything that happens-before it, other CTAs' stores included) and stores the word.
 struct PublishList {
   const uint32_t* src_rows;
   const uint4* src_outs;
   uint32_t* dst_rows;   // mapped host
   uint4* dst_outs;      // mapped host
-  uint32_t* count;      // device counter (reset here)
+  uint32_t* count;      // device counter (reset here); null = list not in this tick
   uint32_t capacity;
   uint32_t out_vec;     // uint4 per result row
 };
 struct PublishArgs {
   PublishList list[3];
-  uint32_t n_lists;
   const uint32_t* extra;   // nullable: one more device word to publish (the placement round counter)
-  uint32_t* host_words;    // mapped host: [k] = count of list k, [n_lists] = extra, then the sequence word at [seq_slot]
+  uint32_t* host_words;    // mapped host: [k] = count of list k, [3] = extra, then the sequence word at [seq_slot]
   uint32_t seq_slot;
   uint32_t seq;
   uint32_t* ticket;
+  uint32_t fence_each;     // A/B: every CTA fences at system scope as well
 };
 
 __global__ void __launch_bounds__(256) publish_lists_kernel(const PublishArgs a) {
   __shared__ uint32_t s_last;
-  pdl_wait_prior();  // every producer kernel of this branch has completed: lists and counters are final
+  pdl_wait_prior();  // every producer kernel of the tick has completed: lists and counters are final
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
-  bool wrote = false;
   uint32_t counts[3] = {0, 0, 0};
-  for (uint32_t k = 0; k < a.n_lists; k++) {
+#pragma unroll
+  for (uint32_t k = 0; k < 3; k++) {
     const PublishList& l = a.list[k];
+    if (l.count == nullptr) continue;
     counts[k] = __ldcg(l.count);
     const uint32_t n = min(counts[k], l.capacity);
     for (uint32_t i = gtid; i < n; i += gsize) l.dst_rows[i] = __ldcg(l.src_rows + i);
     for (uint32_t i = gtid; i < n * l.out_vec; i += gsize) l.dst_outs[i] = __ldcg(l.src_outs + i);
-    wrote |= gtid < n * l.out_vec;
   }
-  if (wrote) __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
+  if (threadIdx.x == 0) {
+    if (a.fence_each) __threadfence_system(); else __threadfence();
+    s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
+  }
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
+    __threadfence();
     volatile uint32_t* hw = a.host_words;
-    for (uint32_t k = 0; k < a.n_lists; k++) {
+#pragma unroll
+    for (uint32_t k = 0; k < 3; k++) {
+      if (a.list[k].count == nullptr) continue;
       hw[k] = counts[k];
       *a.list[k].count = 0u;  // ready for the next tick (stream-ordered)
     }
-    if (a.extra != nullptr) hw[a.n_lists] = __ldcg(a.extra);
+    if (a.extra != nullptr) hw[3] = __ldcg(a.extra);
     *a.ticket = 0u;
     __threadfence_system();
     hw[a.seq_slot] = a.seq;
@@ -1165,27 +1174,32 @@ struct PublishListHost {
   const void* src_outs;
   uint32_t* dst_rows;
   void* dst_outs;
-  uint32_t* count;
+  uint32_t* count;   // null = skip this slot
   uint32_t capacity;
   uint32_t out_bytes;
 };
 
-int launch_publish(const PublishListHost* lists, int n_lists, const uint32_t* d_extra, uint32_t* h_words, uint32_t seq_slot,
+// lists[0..2]: the three slots (host_words[k] receives the count of slot k).
+int launch_publish(const PublishListHost* lists, const uint32_t* d_extra, uint32_t* h_words, uint32_t seq_slot,
                    uint32_t seq, uint32_t* d_ticket, uint32_t expected_rows, cudaStream_t s, int* cuda_err) {
   *cuda_err = 0;
   PublishArgs a{};
-  for (int k = 0; k < n_lists && k < 3; k++)
+  for (int k = 0; k < 3; k++)
     a.list[k] = PublishList{lists[k].src_rows, static_cast<const uint4*>(lists[k].src_outs), lists[k].dst_rows,
                             static_cast<uint4*>(lists[k].dst_outs), lists[k].count, lists[k].capacity, lists[k].out_bytes / 16u};
-  a.n_lists = (uint32_t)n_lists;
   a.extra = d_extra;
   a.host_words = h_words;
   a.seq_slot = seq_slot;
   a.seq = seq;
   a.ticket = d_ticket;
-  // a few CTAs for the usual few thousand rows; more when the previous tick reported many
-  unsigned grid = expected_rows / 1024u + 4u;
-  if (grid > 64u) grid = 64u;
+  static const bool fence_each = [] {
+    const char* v = getenv("LWSE_PUBLISH_FENCE_EACH");
+    return v && atoi(v) != 0;
+  }();
+  a.fence_each = fence_each ? 1u : 0u;
+  // one CTA for the usual few thousand rows; more when the previous tick reported many
+  unsigned grid = expected_rows / 2048u + 1u;
+  if (grid > 32u) grid = 32u;
   const cudaError_t e = launch_pdl(publish_lists_kernel, dim3(grid), dim3(256), 0, s, g_pdl, a);
   if (e != cudaSuccess) {
     *cuda_err = (int)e;

@@ -11,17 +11,28 @@
 //                           (a warp per domain over its run of the static domain-sorted index:
 //                           no atomics), and the namespace index of the request table
 //                           (ns_first[v] = first request of namespace v; order violations counted).
-//   place_ns_kernel         one CTA per namespace.  The node-word table and the capacities are
-//                           staged with TMA (cp.async.bulk.tensor.2d / cp.async.bulk + mbarrier,
-//                           issued by one thread while the others clear the holder table), the
-//                           holder table lives in shared memory, claims are 64-bit shared-memory
-//                           atomicMin, rounds are separated by __syncthreads() — no grid or
-//                           cluster barrier, no L2 round trip per domain.  Deferred acceptance
-//                           runs to ITS OWN fixed point per namespace.
-//   scan form               the same kernel brute-forcing every (request x node) pair from the
-//                           staged table instead of the two-level (domain, then node) search:
+//   place_ns_kernel         one CTA per namespace.  The capacities and the domain index are staged
+//                           with cp.async.bulk + mbarrier (issued by one thread while the others
+//                           clear the holder table and take the pinned claims), the holder table
+//                           lives in shared memory, claims are 64-bit shared-memory atomicMin,
+//                           rounds are separated by __syncthreads() — no grid or cluster barrier,
+//                           no L2 round trip per domain.  Deferred acceptance runs to ITS OWN
+//                           fixed point per namespace.
+//     two-level form        512 threads.  After the pinned claims the CTA compacts the CANDIDATE
+//                           domains — no pinned holder (a pinned key beats every unpinned key) and
+//                           capacity left — into a list {domain, free}; the unpinned holder table
+//                           is indexed by list position, so a (request, round) search is two
+//                           coalesced shared-memory streams over the candidates (a fourth of the
+//                           domains on C3) and one read of the chosen domain's (free | node) run.
+//                           16 KB + 36 B per domain of shared memory: no staging of the node
+//                           table, and the sweep kernels keep the SMs' shared memory.
+//     scan form             256 threads; the node-word table and the node order are staged whole
+//                           with TMA (cp.async.bulk.tensor.2d through a CUtensorMap + cp.async.bulk)
+//                           and every (request x node) pair is scored from shared memory:
 //                           feasibility + both rendezvous hashes per pair, lexicographic arg-max
 //                           (domain score, lower domain, node score, lower node) — identical rows.
+//   Inside a tick both forms also append the result rows that differ from the previous tick's to
+//   the device change list (PlaceNsArgs::prev …) — no separate diff kernel.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -38,6 +49,7 @@ struct PlaceNsArgs {
   const uint32_t* dom_first;   // static index (lwse_upload_nodes)
   const uint32_t* node_order;
   uint32_t* g_words;     // condensed node words in domain-sorted position, padded with zeros to whole rows of 256
+  uint32_t* g_nodes2;    // the same positions: free slots (4 bits) | node index — the two-level form's level 2
   uint32_t* g_dom_free;  // n_domains (+ padding)
   uint32_t* ns_first;    // n_namespaces + 1
   uint32_t* unpinned;    // n_reqs: namespace v's live unpinned requests at [ns_first[v], …)
@@ -50,6 +62,12 @@ struct PlaceNsArgs {
   uint32_t scan;        // 1 = brute-force (request x node) form
   uint32_t stage_words; // the word table fits shared memory and is staged
   uint32_t use_tensor_map;
+  // a tick's change list (all null / 0 = off): rows that differ from `prev` are appended, `prev` is updated
+  lwse_place_out* prev;
+  uint32_t* chg_rows;
+  lwse_place_out* chg_outs;
+  uint32_t* chg_count;
+  uint32_t chg_capacity;
 };
 
 __device__ __forceinline__ uint32_t mix32n(uint32_t x) {
@@ -98,6 +116,7 @@ __global__ void __launch_bounds__(256) place_condense_kernel(const PlaceNsArgs a
       const uint32_t cap = nr.w & 0xFFFFu, occ = occupancy_sum(a, n);
       const uint32_t fr = cap > occ ? cap - occ : 0u;
       a.g_words[i] = (min(fr, 15u) << 28) | d;
+      a.g_nodes2[i] = (min(fr, 15u) << 28) | n;
       sum += fr;
     }
     sum = __reduce_add_sync(0xFFFFFFFFu, sum);
@@ -123,8 +142,19 @@ __global__ void __launch_bounds__(256) place_condense_kernel(const PlaceNsArgs a
       for (uint32_t v = min(b, a.n_namespaces) + 1u; v <= a.n_namespaces; v++) a.ns_first[v] = a.n_reqs;
     if (b >= a.n_namespaces) {  // no such namespace: never takes part in a round
       const bool pinned = hi.w != LWSE_NONE;
-      store_row(a.out + i, LWSE_NONE, pinned ? hi.w : LWSE_NONE,
-                (pinned ? LWSE_PLACE_PINNED : 0u) | LWSE_PLACE_UNSCHEDULABLE, 0u);
+      const uint4 row = make_uint4(LWSE_NONE, pinned ? hi.w : LWSE_NONE, (pinned ? LWSE_PLACE_PINNED : 0u) | LWSE_PLACE_UNSCHEDULABLE, 0u);
+      *reinterpret_cast<uint4*>(a.out + i) = row;
+      if (a.prev != nullptr) {
+        const uint4 o = __ldcg(reinterpret_cast<const uint4*>(a.prev + i));
+        if (row.x != o.x || row.y != o.y || row.z != o.z || row.w != o.w) {
+          const uint32_t k = atomicAdd(a.chg_count, 1u);
+          if (k < a.chg_capacity) {
+            a.chg_rows[k] = i;
+            *reinterpret_cast<uint4*>(a.chg_outs + k) = row;
+          }
+          *reinterpret_cast<uint4*>(a.prev + i) = row;
+        }
+      }
     }
   }
   if (gtid < 8u) a.next_counters[gtid] = 0u;
@@ -135,14 +165,16 @@ __global__ void __launch_bounds__(256) place_condense_kernel(const PlaceNsArgs a
 // --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-constexpr uint32_t kNsThreads = 256;  // two CTAs share an SM (one wave for a few hundred namespaces)
-constexpr uint32_t kNsKeep = 4;       // requests per thread kept in registers between the claim and the result pass
-constexpr uint32_t kNsCache = 256;    // unpinned requests of a namespace whose state lives in shared memory
+constexpr uint32_t kNsScanThreads = 256;  // scan form: two CTAs (2 x ~100 KB of staged tables) share an SM
+constexpr uint32_t kNsThreads = 512;      // two-level form: 16 warps, a warp per unpinned request and round
+constexpr uint32_t kNsKeep = 2;           // requests per thread kept in registers between the claim and the result pass
+constexpr uint32_t kNsCache = 256;        // unpinned requests of a namespace whose state lives in shared memory
 
 // An unpinned request across the rounds (shared memory; written by the one warp that owns it).
+// cur: what it proposed to last — a domain (scan form) or a candidate slot (two-level form).
 struct NsReq {
   unsigned long long key;
-  uint32_t r, key_lo, key_hi, size, cur_dom, dead;
+  uint32_t r, key_lo, key_hi, size, cur, dead;
 };
 
 __device__ __forceinline__ void mbar_wait(unsigned long long* mbar) {
@@ -158,16 +190,33 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
                : "memory");
 }
 
+// A tick's change list: a result row that differs from the previous tick's is appended (and the
+// previous-tick copy brought up to date) by the thread that produced it.
+__device__ __forceinline__ void diff_row(const PlaceNsArgs& a, uint32_t r, const uint4 v) {
+  if (a.prev == nullptr) return;
+  const uint4 o = __ldcg(reinterpret_cast<const uint4*>(a.prev + r));
+  if (v.x != o.x || v.y != o.y || v.z != o.z || v.w != o.w) {
+    const uint32_t i = atomicAdd(a.chg_count, 1u);
+    if (i < a.chg_capacity) {
+      a.chg_rows[i] = r;
+      *reinterpret_cast<uint4*>(a.chg_outs + i) = v;
+    }
+    *reinterpret_cast<uint4*>(a.prev + r) = v;
+  }
+}
+
 template <bool kScan>
-__global__ void __launch_bounds__(kNsThreads, 2)
+__global__ void __launch_bounds__(kScan ? kNsScanThreads : kNsThreads, 2)
     place_ns_kernel(const PlaceNsArgs a, const __grid_constant__ CUtensorMap words_map) {
   extern __shared__ uint8_t s_dyn[];
   // layout (from a 128-byte aligned base: the TMA destination):
-  //   [words: word_rows x 256 u32] [node order: word_rows x 256 u32]      (staged when they fit)
-  //   [dom_free: n_domains u32] [dom_first: n_domains + 1 u32] [holder: n_domains u64]
+  //   scan form, when they fit:  [words: word_rows x 256 u32] [node order: word_rows x 256 u32]
+  //   [dom_free: n_domains u32] [dom_first: n_domains + 1 u32] [holder by domain: n_domains u64]
+  //   two-level form:            [candidates: n_domains x {domain, free}] [holder by candidate: n_domains u64]
+  //                              [slot of domain: n_domains u32]
   //   [request cache: kNsCache x 32 B] [mbarrier]
   uint8_t* s_raw = s_dyn + ((128u - (smem_u32(s_dyn) & 127u)) & 127u);
-  const uint32_t table_bytes = a.stage_words ? a.word_rows * 1024u : 0u;
+  const uint32_t table_bytes = (kScan && a.stage_words) ? a.word_rows * 1024u : 0u;
   const uint32_t free_bytes = ((a.n_domains * 4u) + 15u) & ~15u;
   const uint32_t first_bytes = (((a.n_domains + 1u) * 4u) + 15u) & ~15u;
   uint32_t* s_words = reinterpret_cast<uint32_t*>(s_raw);
@@ -175,29 +224,32 @@ __global__ void __launch_bounds__(kNsThreads, 2)
   uint32_t* s_free = reinterpret_cast<uint32_t*>(s_raw + 2u * table_bytes);
   uint32_t* s_first = reinterpret_cast<uint32_t*>(s_raw + 2u * table_bytes + free_bytes);
   unsigned long long* s_hold = reinterpret_cast<unsigned long long*>(s_raw + 2u * table_bytes + free_bytes + first_bytes);
-  NsReq* s_req = reinterpret_cast<NsReq*>(s_hold + a.n_domains);
+  uint2* s_cand = reinterpret_cast<uint2*>(s_hold + a.n_domains);
+  unsigned long long* s_holdc = reinterpret_cast<unsigned long long*>(s_cand + (kScan ? 0u : a.n_domains));
+  uint32_t* s_slot = reinterpret_cast<uint32_t*>(s_holdc + (kScan ? 0u : a.n_domains));
+  NsReq* s_req = reinterpret_cast<NsReq*>(reinterpret_cast<uint8_t*>(s_slot) + (kScan ? 0u : free_bytes));
   unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_req + kNsCache);
-  __shared__ uint32_t s_n_unp, s_unsettled[3];
+  __shared__ uint32_t s_n_unp, s_n_cand, s_unsettled[3];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, n_warps = blockDim.x >> 5;
-  const uint32_t* words = a.stage_words ? s_words : a.g_words;
-  const uint32_t* order = a.stage_words ? s_order : a.node_order;
+  const uint32_t* words = table_bytes ? s_words : a.g_words;
+  const uint32_t* order = table_bytes ? s_order : a.node_order;
 
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_mbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  // (no early griddepcontrol.launch_dependents: the tick's publish kernel would only park its CTAs
-  // on SMs the concurrent sweep wants; it still launches ahead and starts the moment this grid ends)
+  // (no early griddepcontrol.launch_dependents: a dependent would only park its CTAs on SMs the
+  // concurrent sweep wants; it still launches ahead and starts the moment this grid ends)
   pdl_wait_prior();  // the condense kernel's tables (and the request table a tick's scatter patched)
   if (tid == 0) {
-    // TMA: the node-word table (a 2D tensor of 256-word rows), the node order, the capacity vector
-    // and the domain index land in shared memory while the other threads clear the holder table
-    // and take the pinned claims; one mbarrier collects the bytes
+    // TMA: the capacity vector and the domain index — and, scan form, the node-word table (a 2D
+    // tensor of 256-word rows) and the node order — land in shared memory while the other threads
+    // clear the holder table and take the pinned claims; one mbarrier collects the bytes
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(s_mbar)),
                  "r"(2u * table_bytes + free_bytes + first_bytes)
                  : "memory");
-    if (a.stage_words) {
+    if (table_bytes) {
       if (a.use_tensor_map) {
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
                          smem_u32(s_words)),
@@ -217,6 +269,7 @@ __global__ void __launch_bounds__(kNsThreads, 2)
     const uint32_t first = __ldcg(a.ns_first + ns), last = __ldcg(a.ns_first + ns + 1u);
     if (tid == 0) {
       s_n_unp = 0u;
+      s_n_cand = 0u;
       s_unsettled[0] = s_unsettled[1] = s_unsettled[2] = 0u;
     }
     for (uint32_t d = tid; d < a.n_domains; d += blockDim.x) s_hold[d] = ~0ull;
@@ -229,7 +282,7 @@ __global__ void __launch_bounds__(kNsThreads, 2)
     uint32_t k_dom[kNsKeep];
 #pragma unroll
     for (uint32_t j = 0; j < kNsKeep; j++) {  // all request loads of the thread in flight together
-      const uint32_t r = first + tid + j * kNsThreads;
+      const uint32_t r = first + tid + j * blockDim.x;
       if (r < last) {
         k_lo[j] = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r));
         k_hi[j] = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r) + 1);
@@ -240,8 +293,11 @@ __global__ void __launch_bounds__(kNsThreads, 2)
       uint32_t d = LWSE_NONE;
       if (leader == LWSE_NONE) {
         const bool dead = (int32_t)hi.z < 1;
-        store_row(a.out + r, LWSE_NONE, LWSE_NONE, dead ? LWSE_PLACE_UNSCHEDULABLE : 0u, 0u);
-        if (!dead) {
+        const uint4 row = make_uint4(LWSE_NONE, LWSE_NONE, dead ? LWSE_PLACE_UNSCHEDULABLE : 0u, 0u);
+        *reinterpret_cast<uint4*>(a.out + r) = row;
+        if (dead) {
+          diff_row(a, r, row);
+        } else {
           const uint32_t k = atomicAdd(&s_n_unp, 1u);
           a.unpinned[first + k] = r;
           if (k < kNsCache) {
@@ -251,7 +307,7 @@ __global__ void __launch_bounds__(kNsThreads, 2)
             q.key_lo = lo.z;
             q.key_hi = lo.w;
             q.size = hi.z;
-            q.cur_dom = LWSE_NONE;
+            q.cur = LWSE_NONE;
             q.dead = 0u;
             s_req[k] = q;
           }
@@ -269,23 +325,25 @@ __global__ void __launch_bounds__(kNsThreads, 2)
       if (hi.w == LWSE_NONE) return;
       uint32_t flags = LWSE_PLACE_PINNED;
       if (d != LWSE_NONE) flags |= s_hold[d] == ns_place_key(u64_of(lo.x, lo.y), r, true) ? LWSE_PLACE_PLACED : LWSE_PLACE_CONFLICT;
-      store_row(a.out + r, d, hi.w, flags, 0u);
+      const uint4 row = make_uint4(d, hi.w, flags, 0u);
+      *reinterpret_cast<uint4*>(a.out + r) = row;
+      diff_row(a, r, row);
     };
 #pragma unroll
     for (uint32_t j = 0; j < kNsKeep; j++) {
-      const uint32_t r = first + tid + j * kNsThreads;
+      const uint32_t r = first + tid + j * blockDim.x;
       if (r < last) k_dom[j] = claim(r, k_lo[j], k_hi[j]);
     }
-    for (uint32_t r = first + tid + kNsKeep * kNsThreads; r < last; r += kNsThreads)  // big namespaces: the rest, unkept
+    for (uint32_t r = first + tid + kNsKeep * blockDim.x; r < last; r += blockDim.x)  // big namespaces: the rest, unkept
       claim(r, ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r)), ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r) + 1));
     __syncthreads();
     // results of the pinned requests: final from here on (pinned keys are below every unpinned key)
 #pragma unroll
     for (uint32_t j = 0; j < kNsKeep; j++) {
-      const uint32_t r = first + tid + j * kNsThreads;
+      const uint32_t r = first + tid + j * blockDim.x;
       if (r < last) result(r, k_lo[j], k_hi[j], k_dom[j]);
     }
-    for (uint32_t r = first + tid + kNsKeep * kNsThreads; r < last; r += kNsThreads) {
+    for (uint32_t r = first + tid + kNsKeep * blockDim.x; r < last; r += blockDim.x) {
       const uint4 lo = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r)), hi = ldg_keep(reinterpret_cast<const uint4*>(a.reqs + r) + 1);
       uint32_t d = LWSE_NONE;
       if (hi.w != LWSE_NONE && hi.w < a.n_nodes) {
@@ -303,6 +361,23 @@ __global__ void __launch_bounds__(kNsThreads, 2)
     if (!staged) {  // the first namespace with work waits for the staged tables
       mbar_wait(s_mbar);
       staged = true;
+    }
+    uint32_t n_cand = 0;
+    if constexpr (!kScan) {
+      // The domains an unpinned request can ever win: no pinned holder (a pinned key is below every
+      // unpinned key) and capacity left.  The rounds look at this list only; the holder table of
+      // the unpinned claims is indexed by the list position.
+      for (uint32_t d = tid; d < a.n_domains; d += blockDim.x) {
+        const uint32_t fr = s_free[d];
+        if (s_hold[d] == ~0ull && fr != 0u) {
+          const uint32_t c = atomicAdd(&s_n_cand, 1u);
+          s_cand[c] = make_uint2(d, fr);
+          s_holdc[c] = ~0ull;
+          s_slot[d] = c;
+        }
+      }
+      __syncthreads();
+      n_cand = s_n_cand;
     }
 
     // ---- deferred-acceptance rounds of this namespace, one warp per request ----
@@ -326,37 +401,45 @@ __global__ void __launch_bounds__(kNsThreads, 2)
           q.key_lo = lo.z;
           q.key_hi = lo.w;
           q.size = hi.z;
-          q.cur_dom = o.x;
+          q.cur = o.x;
+          if (!kScan && o.x != LWSE_NONE) q.cur = s_slot[o.x];
           q.dead = (o.z & LWSE_PLACE_UNSCHEDULABLE) ? 1u : 0u;
         }
         __syncwarp();  // every lane has its copy before lane 0 updates the cache entry below
         if (q.dead) continue;  // warp-uniform
         const unsigned long long key = q.key;
         const uint32_t key_lo = q.key_lo, key_hi = q.key_hi, size = q.size, r = q.r;
-        if (q.cur_dom != LWSE_NONE && s_hold[q.cur_dom] == key) continue;  // still holds what it proposed to
+        if (q.cur != LWSE_NONE && (kScan ? s_hold[q.cur] : s_holdc[q.cur]) == key) continue;  // still holds what it proposed to
         scans++;
-        uint32_t H = 0, best_d = LWSE_NONE, best_n = LWSE_NONE;
+        uint32_t H = 0, best_d = LWSE_NONE, best_n = LWSE_NONE, best_c = LWSE_NONE;
         if constexpr (!kScan) {
-          // Level 1 — the domain, from shared memory (holders change under our feet during a round;
-          // a stale reading can only make a proposal fail: holder keys only decrease).
-          uint32_t my_hi = 0, my_d = LWSE_NONE;
-          for (uint32_t d = lane; d < a.n_domains; d += 32u) {
-            const uint32_t h = (s_free[d] >= size && s_hold[d] >= key) ? (mix32n(key_lo ^ (d * 0x9E3779B1u)) | 1u) : 0u;
-            if (h > my_hi) {  // ascending d per lane: ties keep the lower domain
+          // Level 1 — the domain, over the candidate list in shared memory (holders change under
+          // our feet during a round; a stale reading can only make a proposal fail: holder keys
+          // only decrease).
+          uint32_t my_hi = 0, my_d = LWSE_NONE, my_c = LWSE_NONE;
+#pragma unroll 4
+          for (uint32_t c = lane; c < n_cand; c += 32u) {
+            const uint2 cd = s_cand[c];
+            const unsigned long long hk = s_holdc[c];
+            const uint32_t h = (cd.y >= size && hk >= key) ? (mix32n(key_lo ^ (cd.x * 0x9E3779B1u)) | 1u) : 0u;
+            if (h > my_hi || (h == my_hi && h != 0u && cd.x < my_d)) {  // ties keep the lower domain
               my_hi = h;
-              my_d = d;
+              my_d = cd.x;
+              my_c = c;
             }
           }
           H = __reduce_max_sync(0xFFFFFFFFu, my_hi);
           if (H != 0u) {
             best_d = __reduce_min_sync(0xFFFFFFFFu, my_hi == H ? my_d : LWSE_NONE);
-            // Level 2 — the node: the domain's run of the sorted words.
+            const uint32_t owner = __ffs(__ballot_sync(0xFFFFFFFFu, my_hi == H && my_d == best_d)) - 1u;
+            best_c = __shfl_sync(0xFFFFFFFFu, my_c, (int)owner);
+            // Level 2 — the node: the domain's run of the condensed (free | node) words.
             const uint32_t f2 = s_first[best_d], l2 = s_first[best_d + 1u];
             uint32_t my_lo = 0, my_n = LWSE_NONE;
             for (uint32_t i = f2 + lane; i < l2; i += 32u) {
-              const uint32_t w = words[i];
+              const uint32_t w = __ldcg(a.g_nodes2 + i);
               if ((w >> 28) == 0u) continue;
-              const uint32_t n = order[i];
+              const uint32_t n = w & 0x0FFFFFFFu;
               const uint32_t l = ((w >> 28) << 28) | (mix32n(key_hi ^ (n * 0x85EBCA77u)) >> 4);
               if (l > my_lo || (l == my_lo && n < my_n)) {
                 my_lo = l;
@@ -392,6 +475,7 @@ __global__ void __launch_bounds__(kNsThreads, 2)
             const uint32_t L = __reduce_max_sync(0xFFFFFFFFu, in ? my_lo : 0u);
             best_n = __reduce_min_sync(0xFFFFFFFFu, (in && my_lo == L && L != 0u) ? my_n : LWSE_NONE);
           }
+          best_c = best_d;
         }
         if (lane == 0) {
           if (H == 0u || best_n == LWSE_NONE) {  // nothing feasible now, and the feasible set only shrinks
@@ -399,10 +483,10 @@ __global__ void __launch_bounds__(kNsThreads, 2)
             if (cached) s_req[k].dead = 1u;
           } else {
             store_row(a.out + r, best_d, best_n, LWSE_PLACE_PLACED, H);
-            if (cached) s_req[k].cur_dom = best_d;
+            if (cached) s_req[k].cur = best_c;
             // A claim on an empty domain settles at once; any other outcome leaves somebody without
             // a domain who proposes again next round: count it.
-            const unsigned long long old = atomicMin(s_hold + best_d, key);
+            const unsigned long long old = atomicMin((kScan ? s_hold : s_holdc) + best_c, key);
             if (old != ~0ull) atomicAdd(unsettled_ctr, 1u);
           }
         }
@@ -414,6 +498,13 @@ __global__ void __launch_bounds__(kNsThreads, 2)
       if (unsettled == 0u || round > n_unp + 2u) break;
     }
     if (tid == 0) atomicMax(a.counters + 0, round + 1u);
+    // a tick's change list: the rows of the unpinned requests are final now
+    if (a.prev != nullptr) {
+      for (uint32_t k = tid; k < n_unp; k += blockDim.x) {
+        const uint32_t r = k < kNsCache ? s_req[k].r : __ldcg(a.unpinned + first + k);
+        diff_row(a, r, __ldcg(reinterpret_cast<const uint4*>(a.out + r)));
+      }
+    }
     __syncthreads();
   }
   if (!staged) mbar_wait(s_mbar);  // never leave a bulk copy in flight behind a CTA that exits
@@ -422,11 +513,19 @@ __global__ void __launch_bounds__(kNsThreads, 2)
 // --------------------------------------------------------------------------
 // launcher
 // --------------------------------------------------------------------------
+struct PlaceNsChanges {  // a tick's change list (device memory); prev == null: off
+  lwse_place_out* prev;
+  uint32_t* rows;
+  lwse_place_out* outs;
+  uint32_t* count;
+  uint32_t capacity;
+};
+
 static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 
-// scratch: [words (rows x 1 KB)] [dom_free] [ns_first] [unpinned] [counters: 2 blocks of 8 words]
+// scratch: [words (rows x 1 KB)] [nodes2 (same)] [dom_free] [ns_first] [unpinned] [counters: 2 blocks of 8 words]
 struct NsLayout {
-  size_t words, dom_free, ns_first, unpinned, counters, total;
+  size_t words, nodes2, dom_free, ns_first, unpinned, counters, total;
   uint32_t word_rows;
 };
 static NsLayout ns_layout(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs, uint32_t n_namespaces) {
@@ -435,6 +534,8 @@ static NsLayout ns_layout(uint32_t n_nodes, uint32_t n_domains, uint32_t n_reqs,
   if (l.word_rows == 0) l.word_rows = 1;
   size_t off = 0;
   l.words = off;
+  off += up256((size_t)l.word_rows * 1024);
+  l.nodes2 = off;
   off += up256((size_t)l.word_rows * 1024);
   l.dom_free = off;
   off += up256((size_t)n_domains * 4 + 16);
@@ -451,13 +552,17 @@ size_t place_ns_scratch_bytes(uint32_t n_nodes, uint32_t n_domains, uint32_t n_r
   return ns_layout(n_nodes, n_domains, n_reqs, n_namespaces).total;
 }
 
-// shared memory the namespace kernel needs when it stages the word table / when it does not
-static size_t ns_smem_bytes(uint32_t word_rows, uint32_t n_domains, bool stage) {
-  return (stage ? (size_t)word_rows * 2048 : 0) + (((size_t)n_domains * 4 + 15) & ~(size_t)15) +
-         ((((size_t)n_domains + 1) * 4 + 15) & ~(size_t)15) + (size_t)n_domains * 8 + 256 * 32 + 16 + 128;
+// shared memory of the namespace kernel: the scan form with / without the staged word table, the
+// two-level form (candidate list, holder table by candidate, slot of domain)
+static size_t ns_smem_bytes(uint32_t word_rows, uint32_t n_domains, bool scan, bool stage) {
+  const size_t free_bytes = ((size_t)n_domains * 4 + 15) & ~(size_t)15;
+  const size_t base = free_bytes + ((((size_t)n_domains + 1) * 4 + 15) & ~(size_t)15) + (size_t)n_domains * 8 + 256 * 32 + 16 + 128;
+  if (scan) return base + (stage ? (size_t)word_rows * 2048 : 0);
+  return base + (size_t)n_domains * 16 + free_bytes;
 }
 bool place_ns_supported(uint32_t n_nodes, uint32_t n_domains) {
-  return ns_smem_bytes((n_nodes + 255u) / 256u, n_domains, false) <= 200u * 1024u && n_domains < (1u << 28);
+  return ns_smem_bytes((n_nodes + 255u) / 256u, n_domains, false, false) <= 200u * 1024u && n_domains < (1u << 28) &&
+         n_nodes < (1u << 28);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -487,7 +592,8 @@ int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, c
                     uint32_t n_usable, uint32_t n_domains, const lwse_place_req* d_reqs, uint32_t n_reqs,
                     const uint32_t* d_occupancy, uint32_t n_parts, uint64_t part_stride_bytes, uint32_t n_namespaces,
                     lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes, bool fresh, uint32_t call_index, bool scan,
-                    int sm_count, cudaStream_t s, int* cuda_err, const uint32_t** d_counters_out, bool first_pdl) {
+                    int sm_count, cudaStream_t s, int* cuda_err, const uint32_t** d_counters_out, bool first_pdl,
+                    const PlaceNsChanges* changes) {
   *cuda_err = 0;
   const NsLayout l = ns_layout(n_nodes, n_domains, n_reqs, n_namespaces);
   if (scratch_bytes < l.total || n_reqs > 0xFFFFFFu) {
@@ -508,6 +614,7 @@ int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, c
   a.dom_first = d_dom_first;
   a.node_order = d_node_order;
   a.g_words = reinterpret_cast<uint32_t*>(base + l.words);
+  a.g_nodes2 = reinterpret_cast<uint32_t*>(base + l.nodes2);
   a.g_dom_free = reinterpret_cast<uint32_t*>(base + l.dom_free);
   a.ns_first = reinterpret_cast<uint32_t*>(base + l.ns_first);
   a.unpinned = reinterpret_cast<uint32_t*>(base + l.unpinned);
@@ -523,11 +630,18 @@ int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, c
   a.word_rows = l.word_rows;
   a.scan = scan ? 1u : 0u;
   if (d_counters_out) *d_counters_out = a.counters;
+  if (changes && changes->prev) {
+    a.prev = changes->prev;
+    a.chg_rows = changes->rows;
+    a.chg_outs = changes->outs;
+    a.chg_count = changes->count;
+    a.chg_capacity = changes->capacity;
+  }
 
   // does the word table fit next to the holder table?  (227 KB of shared memory per CTA)
-  const size_t with_words = ns_smem_bytes(l.word_rows, n_domains, true);
-  a.stage_words = with_words <= 100u * 1024u ? 1u : 0u;  // two CTAs per SM keep their tables side by side
-  const size_t smem = a.stage_words ? with_words : ns_smem_bytes(l.word_rows, n_domains, false);
+  const size_t with_words = ns_smem_bytes(l.word_rows, n_domains, true, true);
+  a.stage_words = (scan && with_words <= 100u * 1024u) ? 1u : 0u;  // two CTAs per SM keep their tables side by side
+  const size_t smem = ns_smem_bytes(l.word_rows, n_domains, scan, a.stage_words != 0);
   // the tensor map of the word table: re-encoded when the scratch moved
   static thread_local CUtensorMap map;
   static thread_local void* map_for = nullptr;
@@ -563,7 +677,7 @@ int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, c
       if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
       attr_set[scan ? 1 : 0] = smem;
     }
-    e = launch_pdl(kern, dim3(grid), dim3(kNsThreads), smem, s, true, a, map);
+    e = launch_pdl(kern, dim3(grid), dim3(scan ? kNsScanThreads : kNsThreads), smem, s, true, a, map);
     if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
   }
   return 2;

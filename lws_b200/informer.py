@@ -177,8 +177,14 @@ class IncrementalEncoder:
 
         put(R.TABLE_LWS, self.lws, sl.lws_row, lws_row)
         put(R.TABLE_GROUPS, self.groups, sl.group_base, grp)
-        put(R.TABLE_POD_STATE, self.pod_state, sl.pod_base, t.pod_state)
-        put(R.TABLE_POD_IDENT, self.pod_ident, sl.pod_base, t.pod_ident)
+        # the pod columns are written over the WHOLE slot range: rows a shrinking object no longer
+        # references go back to zero (the engine counts node occupancy over every identity row)
+        pst = R.aligned_empty(sl.pod_cap, R.POD_STATE)
+        pst[:npod] = t.pod_state
+        pid = R.aligned_empty(sl.pod_cap, R.POD_IDENT)
+        pid[:npod] = t.pod_ident
+        put(R.TABLE_POD_STATE, self.pod_state, sl.pod_base, pst)
+        put(R.TABLE_POD_IDENT, self.pod_ident, sl.pod_base, pid)
         put(R.TABLE_PLACE_REQS, self.reqs, sl.req_base, reqs)
 
     def _relocate(self, key, ng: int, npod: int) -> bool:
@@ -191,6 +197,7 @@ class IncrementalEncoder:
             return False
         # the vacated request rows must stop claiming: they are rewritten as inert by the diff below
         self._vacated_reqs = (sl.req_base, sl.group_cap, self._ns_id(key[0]))
+        self._vacated_pods = (sl.pod_base, sl.pod_cap)  # and the vacated pod rows must stop occupying nodes
         self.slots[key] = Slots(sl.lws_row, self.g_end, gcap, self.p_end, pcap, self.r_end)
         self.g_end, self.p_end, self.r_end = self.g_end + gcap, self.p_end + pcap, self.r_end + gcap
         return True
@@ -243,6 +250,7 @@ class IncrementalEncoder:
         patches._pending = {}
         for key in sorted(self.dirty):
             self._vacated_reqs = None
+            self._vacated_pods = None
             self._write_object(key, self._encode_object(key), patches)
             if self._vacated_reqs is not None:
                 base, cap, ns = self._vacated_reqs
@@ -257,6 +265,17 @@ class IncrementalEncoder:
                     patches._pending.setdefault(R.TABLE_PLACE_REQS, ([], []))
                     patches._pending[R.TABLE_PLACE_REQS][0].extend((diff + base).tolist())
                     patches._pending[R.TABLE_PLACE_REQS][1].append(inert[diff].copy())
+            if self._vacated_pods is not None:
+                base, cap = self._vacated_pods
+                for table_id, table in ((R.TABLE_POD_STATE, self.pod_state), (R.TABLE_POD_IDENT, self.pod_ident)):
+                    cur = table[base: base + cap]
+                    used = np.flatnonzero(np.ascontiguousarray(cur).view(np.uint8).reshape(cap, -1).any(axis=1))
+                    if len(used):
+                        zeros = R.aligned_empty(len(used), table.dtype)
+                        cur[used] = zeros
+                        patches._pending.setdefault(table_id, ([], []))
+                        patches._pending[table_id][0].extend((used + base).tolist())
+                        patches._pending[table_id][1].append(zeros)
         self.dirty.clear()
         for table_id in (R.TABLE_LWS, R.TABLE_GROUPS, R.TABLE_POD_STATE, R.TABLE_POD_IDENT, R.TABLE_PLACE_REQS):
             if table_id in patches._pending:

@@ -60,6 +60,9 @@ def test_event_stream_equals_fresh_encode(seed):
         (want_l, want_g), fresh = fresh_results(world, "zone")
         got_l, got_g = resident_results(enc, mirror)
         assert got_l == want_l, f"tick {tick}"
+        # node occupancy counted over EVERY identity row of the slotted table (what the engine does)
+        # = the fresh encode's: rows an object vacated were patched back to zero
+        assert np.array_equal(R.occupancy_of(mirror[3], len(enc.node_rec)), R.occupancy_of(fresh.pod_ident, len(fresh.nodes))), f"tick {tick}"
         # group rows: compare what both have; a fresh encode has exactly the referenced rows
         assert got_g.keys() == want_g.keys(), f"tick {tick}"
         for k in want_g:
