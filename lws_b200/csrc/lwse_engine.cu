@@ -698,7 +698,7 @@ static bool values_in_place(const lwse_engine* e, const lwse_patch_seg& g, uint3
 // stream); `stage_base`: where in the staging buffer this call may put copies.
 static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_segs, bool* wrote,
                                 uint32_t tables = 0xFFFFFFFFu, cudaStream_t s = nullptr, size_t stage_base = 0,
-                                size_t* stage_used = nullptr) {
+                                size_t* stage_used = nullptr, long dma_min_bytes = 0) {
   *wrote = false;
   if (stage_used) *stage_used = stage_base;
   if (n_segs == 0) return LWSE_OK;
@@ -792,7 +792,8 @@ static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint
     }();
     size_t total = 0;
     for (int k = 0; k < n_sc; k++) total += (size_t)sc[k].n * (4u + sc[k].row_bytes);
-    if (dma_threshold >= 0 && total >= (size_t)dma_threshold) {
+    const long dma_from = dma_threshold < 0 ? -1 : (dma_min_bytes > dma_threshold ? dma_min_bytes : dma_threshold);
+    if (dma_from >= 0 && total >= (size_t)dma_from) {
       struct Span { const PinBuf* pin; DevBuf* mirror; uintptr_t lo, hi; } spans[2] = {
           {&e->arena, &e->arena_mirror, UINTPTR_MAX, 0}, {&e->stage, &e->stage_mirror, UINTPTR_MAX, 0}};
       auto touch = [&](const void* dptr, size_t bytes) {
@@ -1387,16 +1388,37 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
       }
     }
   }
-  // One scatter applies every segment (one DMA copy of the arena span when the set is large); the
-  // placement round forks behind it on the side stream while the sweep runs on the engine's stream,
-  // and ONE publish kernel behind the join copies all change lists out and raises the word.
-  bool wrote = false;
-  int rc = apply_patches_locked(e, segs, n_segs, &wrote, 0xFFFFFFFFu, s, 0, nullptr);
+  // Patches go where their readers run: the placement request table is read only by the round on
+  // the side stream, everything else by the sweep on the engine's stream — the round then starts
+  // behind its own few rows (read in place over PCIe: no copy-engine launch) while the copy engine
+  // still moves the pod patches, and is mostly done when the sweep needs the SMs.  Identity-row
+  // patches move occupancy counts, which the round reads: with those in the tick it forks behind
+  // the main scatter.  ONE publish kernel behind the join copies all change lists out.
+  constexpr uint32_t kSideTables = 1u << LWSE_TABLE_PLACE_REQS;
+  bool has_ident = false, has_side = false;
+  for (uint32_t i = 0; i < n_segs; i++) {
+    if (segs[i].n && segs[i].table == LWSE_TABLE_POD_IDENT) has_ident = true;
+    if (segs[i].n && segs[i].table == LWSE_TABLE_PLACE_REQS) has_side = true;
+  }
+  bool wrote = false, wrote_side = false;
+  size_t stage_used = 0;
+  int rc = apply_patches_locked(e, segs, n_segs, &wrote, ~kSideTables, s, 0, &stage_used);
   if (rc != LWSE_OK) return rc;
   int cuda_err = 0;
-  if (do_place && wrote) LWSE_CUDA(e, cudaEventRecord(e->ev_fork, s));
+  cudaStream_t ps = e->side_stream;
+  if (has_side) {
+    if (has_ident && wrote) {
+      LWSE_CUDA(e, cudaEventRecord(e->ev_fork, s));
+      LWSE_CUDA(e, cudaStreamWaitEvent(ps, e->ev_fork, 0));
+    }
+    rc = apply_patches_locked(e, segs, n_segs, &wrote_side, kSideTables, ps, stage_used, nullptr, /*dma_min_bytes=*/65536);
+    if (rc != LWSE_OK) return rc;
+  } else if (do_place && has_ident && wrote) {
+    LWSE_CUDA(e, cudaEventRecord(e->ev_fork, s));
+    LWSE_CUDA(e, cudaStreamWaitEvent(ps, e->ev_fork, 0));
+  }
   lwse::PublishListHost pl[3] = {};
-  if (do_sweep) {  // enqueued first: the engine's stream is the longer chain's head start
+  auto enqueue_sweep = [&]() -> int {
     lwse_lws_tables d{};
     d.lws = (const lwse_lws_rec*)e->r_lws.p;
     d.n_lws = e->rn_lws;
@@ -1424,10 +1446,9 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
              (uint32_t*)e->r_counts.p + 0, e->rn_lws, (uint32_t)sizeof(lwse_lws_out)};
     pl[1] = {cl.group_rows, cl.group_out, reinterpret_cast<uint32_t*>(chg_d + e->chg_off[2]), chg_d + e->chg_off[3],
              (uint32_t*)e->r_counts.p + 1, e->rn_groups, (uint32_t)sizeof(lwse_group_out)};
-  }
-  if (do_place) {
-    cudaStream_t ps = e->side_stream;
-    if (wrote) LWSE_CUDA(e, cudaStreamWaitEvent(ps, e->ev_fork, 0));
+    return LWSE_OK;
+  };
+  auto enqueue_place = [&]() -> int {
     const uint32_t form = !e->r_place_grouped ? kFormGeneral : (flags & LWSE_SWEEP_PLACE_SCAN) ? kFormScan : kFormGrouped;
     // the namespace kernels append the changed rows themselves; the general form gets a diff kernel
     const lwse::PlaceNsChanges changes{(lwse_place_out*)e->r_pout_prev.p, reinterpret_cast<uint32_t*>(chg_v + e->chg_off[4]),
@@ -1452,10 +1473,27 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
       if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
       e->launches += (uint64_t)launched;
     }
-    LWSE_CUDA(e, cudaEventRecord(e->ev_join, ps));
-    LWSE_CUDA(e, cudaStreamWaitEvent(s, e->ev_join, 0));
     pl[2] = {changes.rows, changes.outs, reinterpret_cast<uint32_t*>(chg_d + e->chg_off[4]), chg_d + e->chg_off[5], changes.count,
              e->rn_reqs, (uint32_t)sizeof(lwse_place_out)};
+    return LWSE_OK;
+  };
+  // Enqueue order: with patches in flight the engine's stream is busy for ~15 us (copy + scatter),
+  // so the round's three launches go first; without, the sweep's.
+  if (wrote && do_place) {
+    rc = enqueue_place();
+    if (rc != LWSE_OK) return rc;
+  }
+  if (do_sweep) {
+    rc = enqueue_sweep();
+    if (rc != LWSE_OK) return rc;
+  }
+  if (!wrote && do_place) {
+    rc = enqueue_place();
+    if (rc != LWSE_OK) return rc;
+  }
+  if (do_place || wrote_side) {
+    LWSE_CUDA(e, cudaEventRecord(e->ev_join, ps));
+    LWSE_CUDA(e, cudaStreamWaitEvent(s, e->ev_join, 0));
   }
   const bool published = do_sweep || do_place;
   if (published) {

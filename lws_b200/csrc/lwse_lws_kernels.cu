@@ -1110,10 +1110,11 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
 // pinned, mapped host memory with coalesced stores and then raises the sequence word the host
 // spins on — no stream synchronize, no copy-engine launch on the critical path.
 // Ordering: a system-scope fence costs microseconds and fences from many threads queue up behind
-// each other (one per writing thread measured 15-25 us for this kernel), so there is exactly ONE:
-// every CTA orders its stores with bar.sync + a gpu-scope fence before it takes a ticket, the last
-// CTA acquires with a gpu-scope fence, writes the counts, fences once at system scope (cumulative:
-// it covers everything that happens-before it, other CTAs' stores included) and stores the word.
+// each other (one per writing thread measured 15-25 us for this kernel), so there is exactly ONE.
+// Usual case, one CTA: bar.sync, then thread 0 writes the counts, fences at system scope (cumulative:
+// it covers what happens-before it, the other threads' stores included) and stores the word.
+// Several CTAs (many changed rows): every CTA orders its stores with bar.sync + a gpu-scope fence
+// before it takes a ticket, the last CTA acquires with a gpu-scope fence and does the same.
 struct PublishList {
   const uint32_t* src_rows;
   const uint4* src_outs;
@@ -1133,28 +1134,48 @@ struct PublishArgs {
   uint32_t fence_each;     // A/B: every CTA fences at system scope as well
 };
 
-__global__ void __launch_bounds__(256) publish_lists_kernel(const PublishArgs a) {
+constexpr uint32_t kPublishThreads = 1024;
+
+__global__ void __launch_bounds__(kPublishThreads) publish_lists_kernel(const PublishArgs a) {
   __shared__ uint32_t s_last;
   pdl_wait_prior();  // every producer kernel of the tick has completed: lists and counters are final
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
-  uint32_t counts[3] = {0, 0, 0};
+  // the counts and each thread's first elements are requested together (the lists' memory is valid
+  // up to the capacity): one L2 round trip instead of two before the first store leaves
+  uint32_t counts[3] = {0, 0, 0}, row0[3] = {0, 0, 0};
+  uint4 out0[3];
+#pragma unroll
+  for (uint32_t k = 0; k < 3; k++) {
+    const PublishList& l = a.list[k];
+    out0[k] = make_uint4(0, 0, 0, 0);
+    if (l.count == nullptr) continue;
+    counts[k] = __ldcg(l.count);
+    if (gtid < l.capacity) row0[k] = __ldcg(l.src_rows + gtid);
+    if (gtid < l.capacity * l.out_vec) out0[k] = __ldcg(l.src_outs + gtid);
+  }
 #pragma unroll
   for (uint32_t k = 0; k < 3; k++) {
     const PublishList& l = a.list[k];
     if (l.count == nullptr) continue;
-    counts[k] = __ldcg(l.count);
     const uint32_t n = min(counts[k], l.capacity);
-    for (uint32_t i = gtid; i < n; i += gsize) l.dst_rows[i] = __ldcg(l.src_rows + i);
-    for (uint32_t i = gtid; i < n * l.out_vec; i += gsize) l.dst_outs[i] = __ldcg(l.src_outs + i);
+    if (gtid < n) l.dst_rows[gtid] = row0[k];
+    if (gtid < n * l.out_vec) l.dst_outs[gtid] = out0[k];
+    for (uint32_t i = gtid + gsize; i < n; i += gsize) l.dst_rows[i] = __ldcg(l.src_rows + i);
+#pragma unroll 4
+    for (uint32_t i = gtid + gsize; i < n * l.out_vec; i += gsize) l.dst_outs[i] = __ldcg(l.src_outs + i);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    if (a.fence_each) __threadfence_system(); else __threadfence();
-    s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
+  bool last = true;
+  if (gridDim.x > 1) {
+    if (threadIdx.x == 0) {
+      if (a.fence_each) __threadfence_system(); else __threadfence();
+      s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
+    }
+    __syncthreads();
+    last = s_last != 0u;
+    if (last && threadIdx.x == 0) __threadfence();
   }
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    __threadfence();
+  if (last && threadIdx.x == 0) {
     volatile uint32_t* hw = a.host_words;
 #pragma unroll
     for (uint32_t k = 0; k < 3; k++) {
@@ -1197,10 +1218,10 @@ int launch_publish(const PublishListHost* lists, const uint32_t* d_extra, uint32
     return v && atoi(v) != 0;
   }();
   a.fence_each = fence_each ? 1u : 0u;
-  // one CTA for the usual few thousand rows; more when the previous tick reported many
-  unsigned grid = expected_rows / 2048u + 1u;
+  // ONE CTA for the usual few thousand rows (no ticket stage then); more when the previous tick reported many
+  unsigned grid = expected_rows / 8192u + 1u;
   if (grid > 32u) grid = 32u;
-  const cudaError_t e = launch_pdl(publish_lists_kernel, dim3(grid), dim3(256), 0, s, g_pdl, a);
+  const cudaError_t e = launch_pdl(publish_lists_kernel, dim3(grid), dim3(kPublishThreads), 0, s, g_pdl, a);
   if (e != cudaSuccess) {
     *cuda_err = (int)e;
     return -1;
