@@ -198,6 +198,7 @@ struct lwse_engine {
   uint64_t rn_pods = 0;
   bool r_loaded = false, r_place_loaded = false;
   uint32_t tick_seq = 0;
+  int tick_order = 0;                // LWSE_TICK_ORDER (A/B of the tick's enqueue order, see tick_locked)
   uint32_t* h_counts = nullptr;      // pinned, 2 words
   DevBuf h_counts_dev;               // event-pod count of the host entry point's sweep
   bool no_zero_copy = false;         // LWSE_NO_ZERO_COPY=1: always upload the identity column
@@ -366,6 +367,9 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
   {
     const char* v = getenv("LWSE_NO_ZERO_COPY");
     e->no_zero_copy = v && atoi(v) != 0;
+    const char* o = getenv("LWSE_TICK_ORDER");
+    e->tick_order = o ? atoi(o) : 0;
+    if (e->tick_order < 0 || e->tick_order > 2) e->tick_order = 0;
   }
   *out = e;
   return LWSE_OK;
@@ -696,9 +700,31 @@ static bool values_in_place(const lwse_engine* e, const lwse_patch_seg& g, uint3
 // `tables`: bit t set = apply the segments of lwse_table t (a tick applies the placement request
 // patches on the side stream, where the round that reads them runs, and the rest on the engine's
 // stream); `stage_base`: where in the staging buffer this call may put copies.
+struct ScatterPlan {  // a prepared scatter launch (apply_patches_locked with `defer`): the copy is enqueued, the kernel is not
+  lwse::ScatterSegHost sc[LWSE_TICK_MAX_SEGS];
+  int n = 0;
+  bool recount = false;
+};
+
+static int launch_scatter_plan(lwse_engine* e, const ScatterPlan& p, cudaStream_t s) {
+  int cuda_err = 0;
+  if (p.n) {
+    int launched = lwse::launch_scatter(p.sc, p.n, e->n_nodes ? (uint32_t*)e->r_occ.p : nullptr, e->n_nodes, s, true, &cuda_err);
+    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+    e->launches += (uint64_t)launched;
+  }
+  if (p.recount && e->n_nodes) {
+    int launched = lwse::launch_occupancy((const lwse_pod_ident*)e->r_pid.p, e->rn_pods, (uint32_t*)e->r_occ.p, e->n_nodes,
+                                          e->sm_count, s, &cuda_err);
+    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+    e->launches += (uint64_t)launched;
+  }
+  return LWSE_OK;
+}
+
 static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_segs, bool* wrote,
                                 uint32_t tables = 0xFFFFFFFFu, cudaStream_t s = nullptr, size_t stage_base = 0,
-                                size_t* stage_used = nullptr, long dma_min_bytes = 0) {
+                                size_t* stage_used = nullptr, long dma_min_bytes = 0, ScatterPlan* defer = nullptr) {
   *wrote = false;
   if (stage_used) *stage_used = stage_base;
   if (n_segs == 0) return LWSE_OK;
@@ -726,7 +752,8 @@ static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint
     LWSE_CUDA(e, cudaStreamSynchronize(e->side_stream));
     LWSE_CUDA(e, e->stage.reserve(need));
   }
-  lwse::ScatterSegHost sc[LWSE_TICK_MAX_SEGS];
+  ScatterPlan plan;
+  lwse::ScatterSegHost* sc = plan.sc;
   int n_sc = 0;
   size_t cursor = stage_base;
   bool recount = false;
@@ -781,7 +808,6 @@ static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint
     }
     sc[n_sc++] = lwse::ScatterSegHost{base, rows, d_rows, d_vals, g.n, rb, g.table == LWSE_TABLE_POD_IDENT};
   }
-  int cuda_err = 0;
   if (n_sc) {
     // Few patch bytes: the scatter kernel reads them in place over PCIe (one round trip, no copy
     // launch).  Many: one DMA copy per pinned buffer of the span this call uses, then the kernel
@@ -827,18 +853,15 @@ static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint
         }
       }
     }
-    int launched = lwse::launch_scatter(sc, n_sc, e->n_nodes ? (uint32_t*)e->r_occ.p : nullptr, e->n_nodes, s, true, &cuda_err);
-    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
-    e->launches += (uint64_t)launched;
   }
-  if (recount && e->n_nodes) {
-    int launched = lwse::launch_occupancy((const lwse_pod_ident*)e->r_pid.p, e->rn_pods, (uint32_t*)e->r_occ.p, e->n_nodes,
-                                          e->sm_count, s, &cuda_err);
-    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
-    e->launches += (uint64_t)launched;
-  }
+  plan.n = n_sc;
+  plan.recount = recount;
   if (stage_used) *stage_used = cursor;
-  return LWSE_OK;
+  if (defer) {
+    *defer = plan;
+    return LWSE_OK;
+  }
+  return launch_scatter_plan(e, plan, s);
 }
 
 // bytes of staging the segments of a tick need in the worst case (nothing in the arena)
@@ -1402,21 +1425,34 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
   }
   bool wrote = false, wrote_side = false;
   size_t stage_used = 0;
-  int rc = apply_patches_locked(e, segs, n_segs, &wrote, ~kSideTables, s, 0, &stage_used);
-  if (rc != LWSE_OK) return rc;
+  int rc = LWSE_OK;
   int cuda_err = 0;
   cudaStream_t ps = e->side_stream;
-  if (has_side) {
-    if (has_ident && wrote) {
+  // Enqueue order (every call costs 1.5-3 us of host time, and the copy of the pod patches is the
+  // head of the critical path):
+  //   0 (default)  copy of the pod patches; the round's launches on the side stream while the copy
+  //                engine works; then the scatter and the sweep behind the copy
+  //   1            the round's launches first, then copy + scatter + sweep (segments in the arena only)
+  //   2            copy + scatter, the round, the sweep
+  // With identity patches the round forks behind the main scatter (it reads the occupancy counters).
+  bool all_in_place = true;
+  for (uint32_t i = 0; i < n_segs; i++)
+    if (segs[i].n && !(segs[i].flags & LWSE_PATCH_RANGE) && (!rows_in_place(e, segs[i]) || !e->arena.holds(segs[i].values, 1)))
+      all_in_place = false;
+  int order = has_ident ? 2 : e->tick_order;
+  if (order == 1 && !all_in_place) order = 0;  // (the two calls share the staging buffer: main part first)
+  ScatterPlan main_plan;
+  auto apply_main = [&](bool defer) -> int {
+    return apply_patches_locked(e, segs, n_segs, &wrote, ~kSideTables, s, 0, &stage_used, 0, defer ? &main_plan : nullptr);
+  };
+  auto apply_side = [&]() -> int {
+    if (has_ident && wrote && (has_side || do_place)) {
       LWSE_CUDA(e, cudaEventRecord(e->ev_fork, s));
       LWSE_CUDA(e, cudaStreamWaitEvent(ps, e->ev_fork, 0));
     }
-    rc = apply_patches_locked(e, segs, n_segs, &wrote_side, kSideTables, ps, stage_used, nullptr, /*dma_min_bytes=*/65536);
-    if (rc != LWSE_OK) return rc;
-  } else if (do_place && has_ident && wrote) {
-    LWSE_CUDA(e, cudaEventRecord(e->ev_fork, s));
-    LWSE_CUDA(e, cudaStreamWaitEvent(ps, e->ev_fork, 0));
-  }
+    if (!has_side) return LWSE_OK;
+    return apply_patches_locked(e, segs, n_segs, &wrote_side, kSideTables, ps, stage_used, nullptr, /*dma_min_bytes=*/65536);
+  };
   lwse::PublishListHost pl[3] = {};
   auto enqueue_sweep = [&]() -> int {
     lwse_lws_tables d{};
@@ -1477,20 +1513,26 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
              e->rn_reqs, (uint32_t)sizeof(lwse_place_out)};
     return LWSE_OK;
   };
-  // Enqueue order: with patches in flight the engine's stream is busy for ~15 us (copy + scatter),
-  // so the round's three launches go first; without, the sweep's.
-  if (wrote && do_place) {
-    rc = enqueue_place();
-    if (rc != LWSE_OK) return rc;
+  if (order == 1) {
+    rc = apply_side();
+    if (rc == LWSE_OK && do_place) rc = enqueue_place();
+    if (rc == LWSE_OK) rc = apply_main(false);
+    if (rc == LWSE_OK && do_sweep) rc = enqueue_sweep();
+  } else if (order == 0) {
+    rc = apply_main(true);
+    if (rc == LWSE_OK) rc = apply_side();
+    if (rc == LWSE_OK && do_place && wrote) rc = enqueue_place();
+    if (rc == LWSE_OK) rc = launch_scatter_plan(e, main_plan, s);
+    if (rc == LWSE_OK && do_sweep) rc = enqueue_sweep();
+    if (rc == LWSE_OK && do_place && !wrote) rc = enqueue_place();
+  } else {
+    rc = apply_main(false);
+    if (rc == LWSE_OK) rc = apply_side();
+    if (rc == LWSE_OK && do_place && wrote) rc = enqueue_place();
+    if (rc == LWSE_OK && do_sweep) rc = enqueue_sweep();
+    if (rc == LWSE_OK && do_place && !wrote) rc = enqueue_place();
   }
-  if (do_sweep) {
-    rc = enqueue_sweep();
-    if (rc != LWSE_OK) return rc;
-  }
-  if (!wrote && do_place) {
-    rc = enqueue_place();
-    if (rc != LWSE_OK) return rc;
-  }
+  if (rc != LWSE_OK) return rc;
   if (do_place || wrote_side) {
     LWSE_CUDA(e, cudaEventRecord(e->ev_join, ps));
     LWSE_CUDA(e, cudaStreamWaitEvent(s, e->ev_join, 0));

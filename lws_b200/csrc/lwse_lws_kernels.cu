@@ -1168,12 +1168,13 @@ __global__ void __launch_bounds__(kPublishThreads) publish_lists_kernel(const Pu
   bool last = true;
   if (gridDim.x > 1) {
     if (threadIdx.x == 0) {
-      if (a.fence_each) __threadfence_system(); else __threadfence();
-      s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
+      if (a.fence_each) __threadfence_system();
+      uint32_t t;  // release at gpu scope: the CTA's stores (ordered before this by bar.sync) happen-before the ticket
+      asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(t) : "l"(a.ticket) : "memory");
+      s_last = t == gridDim.x - 1u ? 1u : 0u;
     }
     __syncthreads();
     last = s_last != 0u;
-    if (last && threadIdx.x == 0) __threadfence();
   }
   if (last && threadIdx.x == 0) {
     volatile uint32_t* hw = a.host_words;
@@ -1185,8 +1186,10 @@ __global__ void __launch_bounds__(kPublishThreads) publish_lists_kernel(const Pu
     }
     if (a.extra != nullptr) hw[3] = __ldcg(a.extra);
     *a.ticket = 0u;
-    __threadfence_system();
-    hw[a.seq_slot] = a.seq;
+    // release at system scope (fence.acq_rel.sys + store; __threadfence_system() is the heavier
+    // fence.sc.sys + L1 invalidate): everything that happens-before this store is visible to the
+    // host thread that observes the word
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.host_words + a.seq_slot), "r"(a.seq) : "memory");
   }
 }
 
