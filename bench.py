@@ -739,8 +739,27 @@ def run_ours(args):
         reps = (reps + len(plan) - 1) // len(plan) * len(plan)  # whole cycles: every rank ends on the same set
         sec, last = wall(tick_step, reps, warm=len(plan))
         changed = state["rows"]
+
+        def pipelined(n_ticks, ap=ap, state=state):
+            """The same ticks through lwse_resident_tick_submit / _wait, two in flight: while the GPU
+            sweeps tick k the copy engine moves the patches of tick k+1; every tick's results are
+            waited for and read inside the timed region."""
+            barrier()
+            t0 = time.perf_counter()
+            eng.resident_tick_submit(ap.ticks[state["i"] % len(ap.ticks)])
+            state["i"] += 1
+            for _ in range(n_ticks - 1):
+                eng.resident_tick_submit(ap.ticks[state["i"] % len(ap.ticks)])
+                state["i"] += 1
+                r = eng.resident_tick_wait()
+            r = eng.resident_tick_wait()
+            state["rows_pipelined"] = (r["n_lws"], r["n_groups"], r["n_place"])
+            return (time.perf_counter() - t0) / n_ticks
+
+        pipelined(len(plan))  # warm-up
+        sec_pipe = pipelined(reps)
         d2h = changed[0] * (4 + R.LWS_OUT.itemsize) + changed[1] * (4 + R.GROUP_OUT.itemsize) + changed[2] * (4 + R.PLACE_OUT.itemsize) + 28
-        e2e_variants[name] = {"ms_per_step": sec * 1e3, "h2d_bytes_per_step": int(np.mean(ap.h2d_bytes)),
+        e2e_variants[name] = {"ms_per_step": sec * 1e3, "pipelined_ms_per_step": sec_pipe * 1e3, "h2d_bytes_per_step": int(np.mean(ap.h2d_bytes)),
                               "d2h_bytes_per_step": int(d2h), "changed_rows_last_step": {"lws": changed[0], "groups": changed[1], "placement": changed[2]},
                               "pod_rows_per_step": int(len(plan[0].pod_rows)), "request_rows_per_step": int(len(plan[0].req_rows)),
                               "placement_rounds": int(last["rounds"])}
@@ -762,7 +781,8 @@ def run_ours(args):
             mirror = {"ticks_replayed": state["i"], "sweep_equals_oracle": bool(ok), "placement_equals_spec_oracle": pl_ok}
             if not ok or pl_ok is False:
                 raise SystemExit(f"bench.py[{rank}]: resident tick differs from the oracle after {state['i']} ticks: {mirror}")
-    e2e_tick_s = e2e_variants["churn_1pct"]["ms_per_step"] * 1e-3
+    e2e_tick_s = e2e_variants["churn_1pct"]["pipelined_ms_per_step"] * 1e-3  # the headline: two ticks in flight
+    e2e_serial_s = e2e_variants["churn_1pct"]["ms_per_step"] * 1e-3           # one tick at a time (its latency)
 
     # ---- end to end (2): full handover through the stateless host entry point ----
     full = None
@@ -796,13 +816,13 @@ def run_ours(args):
         if int(xerr.item()) != 0:
             raise SystemExit(f"bench.py[{rank}]: a peer-exchange wait timed out")
     # ---- max over ranks ----
-    stats = torch.tensor([ms_step, ms_group, e2e_tick_s * 1e3, ms_scan, ms_lws, ms_place, ms_sweep, ms_fused],
+    stats = torch.tensor([ms_step, ms_group, e2e_tick_s * 1e3, ms_scan, ms_lws, ms_place, ms_sweep, ms_fused, e2e_serial_s * 1e3],
                          dtype=torch.float64, device=dev)
     groups = torch.tensor([float(n_grp)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(groups, op=dist.ReduceOp.SUM)
-    ms_step, ms_group, e2e_ms, ms_scan, ms_lws, ms_place, ms_sweep, ms_fused = [float(x) for x in stats.tolist()]
+    ms_step, ms_group, e2e_ms, ms_scan, ms_lws, ms_place, ms_sweep, ms_fused, e2e_serial_ms = [float(x) for x in stats.tolist()]
     total_groups = float(groups.item())
 
     if rank == 0:
@@ -861,10 +881,14 @@ def run_ours(args):
                                 "one lwse_reconcile_shared_device call per tick and rank: sweep of the shard ∥ (occupancy push, placement round over the rank's namespaces)"),
                        "l2": f"inputs rotate over {copies} resident copies ({copies * algo_bytes / 1e6:.0f} MB > L2)"},
             "e2e": {"value": total_groups / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "latency_ms_per_step": e2e_serial_ms,
                     "h2d_bytes_per_step": tick["h2d_bytes_per_step"], "d2h_bytes_per_step": tick["d2h_bytes_per_step"],
-                    "api": "lwse_resident_tick: per step the watch-event churn (row patches written into the engine's pinned "
-                           "arena, read by the scatter kernel over PCIe) in, full sweep + placement round, changed result rows "
-                           "(written by the kernels into pinned change lists) out; host wall clock around the call",
+                    "api": "lwse_resident_tick_submit / _wait, two ticks in flight (the work queue keeps flowing: while the GPU "
+                           "sweeps tick k the copy engine moves the patches of tick k+1).  Per step, all inside the timed region: "
+                           "the watch-event churn (row patches in the engine's pinned arena) copied host->device and scattered, "
+                           "full sweep + placement round, the changed result rows copied by the publish kernel into pinned change "
+                           "lists, the host waits for every tick's sequence word and reads its counts.  latency_ms_per_step = the "
+                           "same ticks one at a time through lwse_resident_tick (submit + wait)",
                     "churn": {"pod_state_rows": CHURN, "placement_requests": CHURN_REQS},
                     "timing": "host wall clock (time.perf_counter) around the calls, max over ranks",
                     "variants": e2e_variants, "full_handover": full, "oracle_check": mirror},

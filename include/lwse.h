@@ -466,6 +466,16 @@ LWSE_API int lwse_resident_arena(lwse_engine* e, uint64_t min_bytes, void** base
 LWSE_API int lwse_resident_place_load(lwse_engine* e, const lwse_place_req* reqs, uint32_t n_reqs,
                                       uint32_t n_namespaces);
 LWSE_API int lwse_resident_tick(lwse_engine* e, lwse_tick* t);
+/* The same tick in two halves, for callers that keep the work queue flowing: _submit enqueues a
+ * tick and returns at once, _wait blocks (spins on the tick's sequence word) for the OLDEST
+ * submitted tick and fills t's outputs.  At most two ticks are in flight (a third _submit returns
+ * LWSE_ERR_NOT_READY): while the GPU sweeps tick k the copy engine already moves the patches of
+ * tick k+1.  Rules: the patch segments of a tick in flight stay untouched in the arena until its
+ * _wait returned (use two arena regions alternately); a tick's output views stay valid until the
+ * second _submit after its _wait; every other lwse_resident_* call first waits for (and drops the
+ * results of) the ticks in flight.  lwse_resident_tick == _submit + _wait. */
+LWSE_API int lwse_resident_tick_submit(lwse_engine* e, const lwse_tick* t);
+LWSE_API int lwse_resident_tick_wait(lwse_engine* e, lwse_tick* t);
 /* Every placement row of the last tick with LWSE_TICK_PLACE / the occupancy counters the engine
  * maintains (n_nodes words). */
 LWSE_API int lwse_resident_place_outputs(lwse_engine* e, lwse_place_out* out);

@@ -198,6 +198,14 @@ struct lwse_engine {
   uint64_t rn_pods = 0;
   bool r_loaded = false, r_place_loaded = false;
   uint32_t tick_seq = 0;
+  // ticks in flight (lwse_resident_tick_submit / _wait): two slots of pinned change lists and words
+  struct TickSlot {
+    uint32_t seq = 0;
+    bool do_sweep = false, do_place = false, published = false, wrote = false;
+  } tslot[2];
+  uint64_t t_submitted = 0, t_waited = 0;
+  size_t chg_bytes = 0;              // one slot of `chg`
+  cudaEvent_t ev_pub = nullptr;      // behind the previous tick's publish kernel: the next tick's side stream starts there
   int tick_order = 0;                // LWSE_TICK_ORDER (A/B of the tick's enqueue order, see tick_locked)
   uint32_t* h_counts = nullptr;      // pinned, 2 words
   DevBuf h_counts_dev;               // event-pod count of the host entry point's sweep
@@ -272,6 +280,8 @@ int check_lws_tables(const lwse_lws_tables* t) {
 
 extern "C" {
 
+static int drain_ticks_locked(lwse_engine* e);  // waits for (and drops the results of) every tick in flight
+
 LWSE_API uint32_t lwse_abi_version(void) { return LWSE_ABI_VERSION; }
 
 LWSE_API const char* lwse_strerror(int status) {
@@ -343,6 +353,7 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
       create_side_stream(&e->side_stream) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_pub, cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->hist_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_hist, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_place, cudaEventDisableTiming) != cudaSuccess ||
@@ -351,6 +362,7 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
     (void)cudaGetLastError();
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->ev_pub) cudaEventDestroy(e->ev_pub);
     if (e->ev_hist) cudaEventDestroy(e->ev_hist);
     if (e->ev_place) cudaEventDestroy(e->ev_place);
     if (e->hist_stream) cudaStreamDestroy(e->hist_stream);
@@ -404,6 +416,7 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
     cudaStreamDestroy(e->hist_stream);
     cudaEventDestroy(e->ev_fork);
     cudaEventDestroy(e->ev_join);
+    if (e->ev_pub) cudaEventDestroy(e->ev_pub);
     cudaStreamDestroy(e->side_stream);
     cudaStreamDestroy(e->stream);
   }
@@ -608,7 +621,8 @@ static int reserve_change_lists(lwse_engine* e) {
     e->chg_off[k] = off;
     off += align256(sizes[k] + 16);
   }
-  LWSE_CUDA(e, e->chg.reserve(off));
+  e->chg_bytes = off;
+  LWSE_CUDA(e, e->chg.reserve(2 * off));  // two ticks may be in flight: the host reads one slot while the next tick fills the other
   LWSE_CUDA(e, e->chg_dev.reserve(off));
   LWSE_CUDA(e, e->tickw.reserve(256));
   return LWSE_OK;
@@ -621,6 +635,10 @@ LWSE_API int lwse_resident_load(lwse_engine* e, const lwse_lws_tables* h) {
   if (h->n_pods > 0xFFFFFFFFull) return LWSE_ERR_UNSUPPORTED;
   std::lock_guard<std::mutex> lock(e->mu);
   DeviceGuard guard(e->device);
+  {
+    const int drc = drain_ticks_locked(e);
+    if (drc != LWSE_OK) return drc;
+  }
   cudaStream_t s = e->stream;
   const size_t b_lws = (size_t)h->n_lws * sizeof(lwse_lws_rec), b_grp = (size_t)h->n_groups * sizeof(lwse_group_rec);
   const size_t b_pst = (size_t)h->n_pods * sizeof(lwse_pod_state), b_pid = (size_t)h->n_pods * sizeof(lwse_pod_ident);
@@ -663,7 +681,13 @@ LWSE_API int lwse_resident_arena(lwse_engine* e, uint64_t min_bytes, void** base
   if (!e || !base_out) return LWSE_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(e->mu);
   DeviceGuard guard(e->device);
-  LWSE_CUDA(e, cudaStreamSynchronize(e->stream));  // nothing may still be reading a buffer that is replaced
+  const size_t want_arena = min_bytes ? (size_t)min_bytes : ((size_t)8 << 20);
+  if (want_arena > e->arena.cap) {  // growing replaces the buffer: nothing may still be reading it
+    const int drc = drain_ticks_locked(e);
+    if (drc != LWSE_OK) return drc;
+    LWSE_CUDA(e, cudaStreamSynchronize(e->stream));
+    LWSE_CUDA(e, cudaStreamSynchronize(e->side_stream));
+  }
   LWSE_CUDA(e, e->arena.reserve(min_bytes ? (size_t)min_bytes : ((size_t)8 << 20)));
   *base_out = e->arena.h;
   if (bytes_out) *bytes_out = e->arena.cap;
@@ -879,6 +903,10 @@ LWSE_API int lwse_resident_patch(lwse_engine* e, lwse_table which, const uint32_
   if (!e->r_loaded) return LWSE_ERR_NOT_READY;
   if (n == 0) return LWSE_OK;
   DeviceGuard guard(e->device);
+  {
+    const int drc = drain_ticks_locked(e);
+    if (drc != LWSE_OK) return drc;
+  }
   lwse_patch_seg seg{};
   seg.table = (uint32_t)which;
   seg.n = n;
@@ -1336,6 +1364,11 @@ LWSE_API int lwse_resident_place_load(lwse_engine* e, const lwse_place_req* reqs
   std::lock_guard<std::mutex> lock(e->mu);
   if (!e->r_loaded || e->n_nodes == 0 || e->n_domains == 0) return LWSE_ERR_NOT_READY;
   DeviceGuard guard(e->device);
+  {
+    const int drc = drain_ticks_locked(e);
+    if (drc != LWSE_OK) return drc;
+    LWSE_CUDA(e, cudaStreamSynchronize(e->side_stream));
+  }
   cudaStream_t s = e->stream;
   const size_t b_req = (size_t)n_reqs * sizeof(lwse_place_req), b_out = (size_t)n_reqs * sizeof(lwse_place_out);
   LWSE_CUDA(e, e->r_preq.reserve(b_req + 16));
@@ -1385,13 +1418,16 @@ struct TickCounts {
   uint32_t n_lws = 0, n_groups = 0, n_place = 0, rounds = 0;
 };
 
-static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_segs, uint32_t flags, TickCounts* out) {
+// Enqueue one tick (nothing waits): slot = t_submitted & 1.  At most two ticks are in flight.
+static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_segs, uint32_t flags) {
+  if (e->t_submitted - e->t_waited >= 2) return LWSE_ERR_NOT_READY;  // wait for the oldest tick first
+  const bool in_flight = e->t_submitted != e->t_waited;
+  const uint32_t slot = (uint32_t)(e->t_submitted & 1u);
   cudaStream_t s = e->stream;
   uint32_t seq = ++e->tick_seq;
   if (seq == 0) seq = ++e->tick_seq;
-  volatile uint32_t* hw = static_cast<volatile uint32_t*>(e->tickw.h);
-  uint32_t* hw_dev = static_cast<uint32_t*>(e->tickw.d);
-  uint8_t* chg_d = static_cast<uint8_t*>(e->chg.d);      // the pinned lists, as the device sees them
+  uint32_t* hw_dev = static_cast<uint32_t*>(e->tickw.d) + slot * 16u;
+  uint8_t* chg_d = static_cast<uint8_t*>(e->chg.d) + slot * e->chg_bytes;  // the pinned lists of this slot, as the device sees them
   uint8_t* chg_v = static_cast<uint8_t*>(e->chg_dev.p);  // the device-memory lists the kernels append to
   const bool do_place = (flags & LWSE_TICK_PLACE) && e->r_place_loaded && e->rn_reqs > 0;
   const bool do_sweep = !(flags & LWSE_TICK_NO_SWEEP) && (e->rn_lws || e->rn_groups);
@@ -1441,6 +1477,18 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
       all_in_place = false;
   int order = has_ident ? 2 : e->tick_order;
   if (order == 1 && !all_in_place) order = 0;  // (the two calls share the staging buffer: main part first)
+  if (in_flight) {
+    // a tick is still running.  Its DMA may still read the staging buffer: segments outside the arena
+    // wait for it.  Its publish kernel (the last thing on the engine's stream) still has to copy and
+    // reset the placement change list the side stream appends to: the side stream starts behind it.
+    if (!all_in_place) {
+      LWSE_CUDA(e, cudaStreamSynchronize(s));
+      LWSE_CUDA(e, cudaStreamSynchronize(ps));
+    } else if (do_place || has_side) {
+      LWSE_CUDA(e, cudaEventRecord(e->ev_pub, s));
+      LWSE_CUDA(e, cudaStreamWaitEvent(ps, e->ev_pub, 0));
+    }
+  }
   ScatterPlan main_plan;
   auto apply_main = [&](bool defer) -> int {
     return apply_patches_locked(e, segs, n_segs, &wrote, ~kSideTables, s, 0, &stage_used, 0, defer ? &main_plan : nullptr);
@@ -1544,38 +1592,50 @@ static int tick_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_se
     if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
     e->launches += (uint64_t)launched;
   }
-  // ---- the tick's only wait ----
-  cudaError_t werr = cudaSuccess;
-  bool ok = true;
-  if (published) {
-    ok = wait_word(hw + 4, seq, s, &werr);
-  } else if (wrote) {
-    werr = cudaStreamSynchronize(s);
-    ok = werr == cudaSuccess;
-  }
-  if (!ok) {
-    const cudaError_t a = cudaStreamSynchronize(s), b = cudaStreamSynchronize(e->side_stream);
-    return fail_cuda(e, werr != cudaSuccess ? werr : a != cudaSuccess ? a : b != cudaSuccess ? b : cudaErrorUnknown);
-  }
-  if (do_place) e->place_pending = false;  // the publish kernel ran behind the join: the round is complete
-  out->n_lws = do_sweep ? hw[0] : 0u;
-  out->n_groups = do_sweep ? hw[1] : 0u;
-  out->n_place = do_place ? hw[2] : 0u;
-  out->rounds = do_place ? hw[3] : 0u;
-  e->last_changed[0] = out->n_lws + out->n_groups;
-  e->last_changed[1] = out->n_place;
+  lwse_engine::TickSlot& ts = e->tslot[slot];
+  ts.seq = seq;
+  ts.do_sweep = do_sweep;
+  ts.do_place = do_place;
+  ts.published = published;
+  ts.wrote = wrote || wrote_side;
+  e->t_submitted++;
   return LWSE_OK;
 }
 
-LWSE_API int lwse_resident_tick(lwse_engine* e, lwse_tick* t) {
-  if (!e || !t || (t->n_segs && !t->segs)) return LWSE_ERR_INVALID_ARG;
-  std::lock_guard<std::mutex> lock(e->mu);
-  if (!e->r_loaded) return LWSE_ERR_NOT_READY;
-  DeviceGuard guard(e->device);
-  TickCounts c;
-  const int rc = tick_locked(e, t->segs, t->n_segs, t->flags, &c);
-  if (rc != LWSE_OK) return rc;
-  const uint8_t* base = static_cast<const uint8_t*>(e->chg.h);
+// The oldest tick in flight: spin on its sequence word (the tick's only wait), report its counts.
+static int tick_wait_locked(lwse_engine* e, TickCounts* out, uint32_t* slot_out) {
+  if (e->t_submitted == e->t_waited) return LWSE_ERR_NOT_READY;
+  const uint32_t slot = (uint32_t)(e->t_waited & 1u);
+  const lwse_engine::TickSlot ts = e->tslot[slot];
+  cudaStream_t s = e->stream;
+  volatile uint32_t* hw = static_cast<volatile uint32_t*>(e->tickw.h) + slot * 16u;
+  cudaError_t werr = cudaSuccess;
+  bool ok = true;
+  if (ts.published) {
+    ok = wait_word(hw + 4, ts.seq, s, &werr);
+  } else if (ts.wrote) {
+    werr = cudaStreamSynchronize(s);
+    ok = werr == cudaSuccess;
+  }
+  e->t_waited++;
+  if (!ok) {
+    const cudaError_t a = cudaStreamSynchronize(s), b = cudaStreamSynchronize(e->side_stream);
+    e->t_waited = e->t_submitted;  // whatever else was in flight died with it
+    return fail_cuda(e, werr != cudaSuccess ? werr : a != cudaSuccess ? a : b != cudaSuccess ? b : cudaErrorUnknown);
+  }
+  if (ts.do_place && e->t_submitted == e->t_waited) e->place_pending = false;  // the publish kernel ran behind the join: the round is complete
+  out->n_lws = ts.do_sweep ? hw[0] : 0u;
+  out->n_groups = ts.do_sweep ? hw[1] : 0u;
+  out->n_place = ts.do_place ? hw[2] : 0u;
+  out->rounds = ts.do_place ? hw[3] : 0u;
+  e->last_changed[0] = out->n_lws + out->n_groups;
+  e->last_changed[1] = out->n_place;
+  if (slot_out) *slot_out = slot;
+  return LWSE_OK;
+}
+
+static void fill_tick_outputs(const lwse_engine* e, uint32_t slot, const TickCounts& c, lwse_tick* t) {
+  const uint8_t* base = static_cast<const uint8_t*>(e->chg.h) + slot * e->chg_bytes;
   t->lws_rows = reinterpret_cast<const uint32_t*>(base + e->chg_off[0]);
   t->lws_out = reinterpret_cast<const lwse_lws_out*>(base + e->chg_off[1]);
   t->group_rows = reinterpret_cast<const uint32_t*>(base + e->chg_off[2]);
@@ -1586,6 +1646,53 @@ LWSE_API int lwse_resident_tick(lwse_engine* e, lwse_tick* t) {
   t->n_groups = c.n_groups;
   t->n_place = c.n_place;
   t->place_rounds = c.rounds;
+}
+
+// Every tick in flight is waited for (its results are dropped): the synchronous entry points call this first.
+static int drain_ticks_locked(lwse_engine* e) {
+  while (e->t_submitted != e->t_waited) {
+    TickCounts c;
+    const int rc = tick_wait_locked(e, &c, nullptr);
+    if (rc != LWSE_OK) return rc;
+  }
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_resident_tick(lwse_engine* e, lwse_tick* t) {
+  if (!e || !t || (t->n_segs && !t->segs)) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->r_loaded) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  int rc = drain_ticks_locked(e);
+  if (rc != LWSE_OK) return rc;
+  rc = tick_submit_locked(e, t->segs, t->n_segs, t->flags);
+  if (rc != LWSE_OK) return rc;
+  TickCounts c;
+  uint32_t slot = 0;
+  rc = tick_wait_locked(e, &c, &slot);
+  if (rc != LWSE_OK) return rc;
+  fill_tick_outputs(e, slot, c, t);
+  return LWSE_OK;
+}
+
+LWSE_API int lwse_resident_tick_submit(lwse_engine* e, const lwse_tick* t) {
+  if (!e || !t || (t->n_segs && !t->segs)) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->r_loaded) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  return tick_submit_locked(e, t->segs, t->n_segs, t->flags);
+}
+
+LWSE_API int lwse_resident_tick_wait(lwse_engine* e, lwse_tick* t) {
+  if (!e || !t) return LWSE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->r_loaded) return LWSE_ERR_NOT_READY;
+  DeviceGuard guard(e->device);
+  TickCounts c;
+  uint32_t slot = 0;
+  const int rc = tick_wait_locked(e, &c, &slot);
+  if (rc != LWSE_OK) return rc;
+  fill_tick_outputs(e, slot, c, t);
   return LWSE_OK;
 }
 
@@ -1598,13 +1705,16 @@ LWSE_API int lwse_resident_sweep(lwse_engine* e, uint32_t flags, lwse_changes* c
   if (!e->r_loaded) return LWSE_ERR_NOT_READY;
   DeviceGuard guard(e->device);
   TickCounts c;
-  const int rc = tick_locked(e, nullptr, 0, flags & LWSE_SWEEP_GANG, &c);
+  uint32_t slot = 0;
+  int rc = drain_ticks_locked(e);
+  if (rc == LWSE_OK) rc = tick_submit_locked(e, nullptr, 0, flags & LWSE_SWEEP_GANG);
+  if (rc == LWSE_OK) rc = tick_wait_locked(e, &c, &slot);
   if (rc != LWSE_OK || !ch) return rc;
   ch->n_lws = c.n_lws;
   ch->n_groups = c.n_groups;
   const uint32_t nl = c.n_lws < ch->lws_capacity ? c.n_lws : ch->lws_capacity;
   const uint32_t ng = c.n_groups < ch->group_capacity ? c.n_groups : ch->group_capacity;
-  const uint8_t* base = static_cast<const uint8_t*>(e->chg.h);
+  const uint8_t* base = static_cast<const uint8_t*>(e->chg.h) + slot * e->chg_bytes;
   if (nl) {
     memcpy(ch->lws_rows, base + e->chg_off[0], (size_t)nl * 4);
     memcpy(ch->lws_out, base + e->chg_off[1], (size_t)nl * sizeof(lwse_lws_out));

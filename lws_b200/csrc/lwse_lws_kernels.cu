@@ -208,6 +208,8 @@ __device__ __forceinline__ void emit_if_changed(const ChangeList& c, uint4* slot
   for (int k = 0; k < N; k++) stg_stream(slot + k, v[k]);
 }
 
+constexpr uint32_t kSweepWaitAtTop = 1u << 31;  // internal bit of GroupSweepArgs::sweep_flags
+
 struct GroupSweepArgs {
   const lwse_lws_rec* lws;
   const lwse_group_rec* groups;
@@ -564,6 +566,9 @@ __global__ void __launch_bounds__(kFusedThreads, 3) group_fused_kernel(const Gro
   const uint32_t g = blockIdx.x * kFusedThreads + tid;
   const bool valid = g < a.n_groups;
   pdl_launch_dependents();
+  // behind a kernel that WRITES the input tables (a tick's patch scatter): launched programmatically
+  // dependent all the same — the launch latency overlaps the scatter — and nothing is read before it is done
+  if (a.sweep_flags & kSweepWaitAtTop) pdl_wait_prior();
 
   // ---- 1. rows ----
   uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, cc = ca, cd = ca, L = ca;
@@ -1057,7 +1062,9 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
     if (cl && cl->group_rows) a.changes = ChangeList{cl->group_rows, cl->group_out, cl->counts + 1, cl->group_capacity};
     const uint32_t grid = (t->n_groups + kFusedThreads - 1) / kFusedThreads;
     // (a memset / occupancy kernel right before: an ordinary launch orders behind it)
-    e = launch_pdl(group_fused_kernel, dim3(grid), dim3(kFusedThreads), 0, s, g_pdl && first_pdl && !t->node_occupancy, a);
+    const bool pdl = g_pdl && !t->node_occupancy;
+    if (pdl && !first_pdl) a.sweep_flags |= kSweepWaitAtTop;
+    e = launch_pdl(group_fused_kernel, dim3(grid), dim3(kFusedThreads), 0, s, pdl, a);
     if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
     launches++;
   }

@@ -37,6 +37,8 @@ SYMBOLS = {
     "lwse_resident_arena": ([C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)], C.c_int),
     "lwse_resident_place_load": ([C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32], C.c_int),
     "lwse_resident_tick": ([C.c_void_p, C.POINTER(R.Tick)], C.c_int),
+    "lwse_resident_tick_submit": ([C.c_void_p, C.POINTER(R.Tick)], C.c_int),
+    "lwse_resident_tick_wait": ([C.c_void_p, C.POINTER(R.Tick)], C.c_int),
     "lwse_resident_place_outputs": ([C.c_void_p, C.c_void_p], C.c_int),
     "lwse_resident_occupancy": ([C.c_void_p, C.c_void_p], C.c_int),
     "lwse_place_host": (
@@ -320,7 +322,21 @@ class Engine:
         """One tick: patches in, changed result rows out (views of engine-owned pinned memory,
         valid until the next resident call).  → dict of numpy views."""
         self._check(lib().lwse_resident_tick(self._h, C.byref(tick)))
+        return self._tick_views(tick)
 
+    def resident_tick_submit(self, tick: "R.Tick"):
+        """Enqueue a tick and return (at most two in flight); its patch segments stay untouched in the
+        arena until the matching ``resident_tick_wait``."""
+        self._check(lib().lwse_resident_tick_submit(self._h, C.byref(tick)))
+
+    def resident_tick_wait(self, tick: "R.Tick" = None):
+        """Wait for the OLDEST submitted tick → the same dict as ``resident_tick`` (views valid until
+        the second submit after this call)."""
+        tick = tick if tick is not None else R.Tick()
+        self._check(lib().lwse_resident_tick_wait(self._h, C.byref(tick)))
+        return self._tick_views(tick)
+
+    def _tick_views(self, tick: "R.Tick"):
         def view(ptr, n, dtype):
             if not ptr or n == 0:
                 return np.zeros(0, dtype=dtype)

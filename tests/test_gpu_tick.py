@@ -87,6 +87,63 @@ def test_ticks_match_the_oracle(engine, in_arena):
         prev = now
 
 
+def test_pipelined_ticks_report_what_serial_ticks_report(engine):
+    """lwse_resident_tick_submit / _wait with two ticks in flight: every tick's change lists (copied
+    at wait time, while the NEXT tick is already running) equal the oracle's diff of consecutive
+    states, and a third submit without a wait is refused."""
+    import oracle
+    from lws_b200.engine import LwseError
+
+    p = synth.profile("fuzz", 0.5)
+    p.n_namespaces = 3
+    t = synth.make(p, seed=47)
+    reqs = t.place_requests()
+    engine.upload_nodes(t.nodes, t.n_domains)
+    engine.resident_load(t.lws, t.groups, t.pod_state, t.pod_ident)
+    engine.resident_place_load(reqs, t.n_namespaces)
+    occ = R.occupancy_of(t.pod_ident, len(t.nodes))
+    flags = t.flags | R.TICK_PLACE
+    m_pst, m_grp, m_req = t.pod_state.copy(), t.groups.copy(), reqs.copy()
+
+    def oracle_now():
+        lo, go, _ = oracle.sweep_lws(t.lws, m_grp, m_pst, t.pod_ident, t.nodes, flags=t.flags)
+        return lo, go, oracle.place(t.nodes, occ, t.n_domains, t.n_namespaces, m_req)
+
+    states = [oracle_now()]
+    engine.resident_tick(engine.make_tick((), flags))
+    plan = churn.make_plan(t, reqs, states[0][2], 0.03, 0.05, n_sets=6, seed=9)
+    ticks = churn.ArenaPlan(engine, plan, flags).ticks  # six disjoint arena regions
+    n = 12
+    for k in range(n):
+        churn.apply_to_mirror(plan[k % len(plan)], m_pst, m_grp, m_req)
+        states.append(oracle_now())
+
+    def check(k, res):
+        before, after = states[k], states[k + 1]
+        res = {key: (v.copy() if isinstance(v, np.ndarray) else v) for key, v in res.items()}
+        _check_changes(res, "lws", before[0], after[0])
+        _check_changes(res, "group", before[1], after[1])
+        _check_changes(res, "place", before[2], after[2])
+
+    engine.resident_tick_submit(ticks[0])
+    for k in range(1, n):
+        engine.resident_tick_submit(ticks[k % len(ticks)])
+        if k == 3:  # two in flight: the third is refused, nothing is lost
+            with pytest.raises(LwseError):
+                engine.resident_tick_submit(ticks[(k + 1) % len(ticks)])
+        check(k - 1, engine.resident_tick_wait())
+    check(n - 1, engine.resident_tick_wait())
+    with pytest.raises(LwseError):
+        engine.resident_tick_wait()
+    g_lo, g_go = engine.resident_outputs()
+    assert g_lo.tobytes() == states[-1][0].tobytes() and g_go.tobytes() == states[-1][1].tobytes()
+    assert engine.resident_place_outputs().tobytes() == states[-1][2].tobytes()
+    # a synchronous call with a tick in flight drains it first
+    engine.resident_tick_submit(ticks[0])
+    again = engine.resident_tick(engine.make_tick((), flags))
+    assert (again["n_lws"], again["n_groups"], again["n_place"]) == (0, 0, 0)
+
+
 def test_range_patch_and_identity_patches_keep_the_occupancy(engine):
     import oracle
 
