@@ -98,3 +98,37 @@ func (e *Engine) Tick(segs []C.lwse_patch_seg, flags uint32) (TickResult, error)
 		Rounds:    uint32(t.place_rounds),
 	}, nil
 }
+
+// Submit enqueues a tick and returns at once; Wait blocks for the OLDEST submitted tick.  At most
+// two ticks are in flight: the sweeper goroutine writes the next batch of watch-event patches into
+// the other half of the arena and submits it while the GPU still works on the previous one.
+// The patch bytes of a submitted tick must stay untouched until its Wait returned.
+func (e *Engine) Submit(segs []C.lwse_patch_seg, flags uint32) error {
+	var t C.lwse_tick
+	if len(segs) > 0 {
+		t.segs = (*C.lwse_patch_seg)(unsafe.Pointer(&segs[0]))
+		t.n_segs = C.uint32_t(len(segs))
+	}
+	t.flags = C.uint32_t(flags)
+	return e.check(C.lwse_resident_tick_submit(e.h, &t))
+}
+
+func (e *Engine) Wait() (TickResult, error) {
+	var t C.lwse_tick
+	if err := e.check(C.lwse_resident_tick_wait(e.h, &t)); err != nil {
+		return TickResult{}, err
+	}
+	return tickResult(&t), nil
+}
+
+func tickResult(t *C.lwse_tick) TickResult {
+	return TickResult{
+		LwsRows:   unsafe.Slice((*uint32)(unsafe.Pointer(t.lws_rows)), int(t.n_lws)),
+		LwsOut:    unsafe.Slice((*C.lwse_lws_out)(unsafe.Pointer(t.lws_out)), int(t.n_lws)),
+		GroupRows: unsafe.Slice((*uint32)(unsafe.Pointer(t.group_rows)), int(t.n_groups)),
+		GroupOut:  unsafe.Slice((*C.lwse_group_out)(unsafe.Pointer(t.group_out)), int(t.n_groups)),
+		PlaceRows: unsafe.Slice((*uint32)(unsafe.Pointer(t.place_rows)), int(t.n_place)),
+		PlaceOut:  unsafe.Slice((*C.lwse_place_out)(unsafe.Pointer(t.place_out)), int(t.n_place)),
+		Rounds:    uint32(t.place_rounds),
+	}
+}

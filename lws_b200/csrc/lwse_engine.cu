@@ -1471,10 +1471,15 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
   //   1            the round's launches first, then copy + scatter + sweep (segments in the arena only)
   //   2            copy + scatter, the round, the sweep
   // With identity patches the round forks behind the main scatter (it reads the occupancy counters).
-  bool all_in_place = true;
-  for (uint32_t i = 0; i < n_segs; i++)
-    if (segs[i].n && !(segs[i].flags & LWSE_PATCH_RANGE) && (!rows_in_place(e, segs[i]) || !e->arena.holds(segs[i].values, 1)))
-      all_in_place = false;
+  bool all_in_place = true;  // no segment needs the staging buffer
+  for (uint32_t i = 0; i < n_segs; i++) {
+    if (!segs[i].n || (segs[i].flags & LWSE_PATCH_RANGE)) continue;
+    void* tb;
+    uint64_t trows;
+    uint32_t rb = 0;
+    if (!resident_table(e, segs[i].table, &tb, &trows, &rb)) return LWSE_ERR_INVALID_ARG;
+    if (!rows_in_place(e, segs[i]) || !values_in_place(e, segs[i], rb)) all_in_place = false;
+  }
   int order = has_ident ? 2 : e->tick_order;
   if (order == 1 && !all_in_place) order = 0;  // (the two calls share the staging buffer: main part first)
   if (in_flight) {
