@@ -565,10 +565,12 @@ __global__ void __launch_bounds__(kFusedThreads, 3) group_fused_kernel(const Gro
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t g = blockIdx.x * kFusedThreads + tid;
   const bool valid = g < a.n_groups;
-  pdl_launch_dependents();
-  // behind a kernel that WRITES the input tables (a tick's patch scatter): launched programmatically
-  // dependent all the same — the launch latency overlaps the scatter — and nothing is read before it is done
+  // Behind a kernel that WRITES the input tables (a tick's patch scatter) the kernel is launched
+  // programmatically dependent all the same — the launch latency overlaps the scatter — and waits
+  // here, before its first read.  Its own dependent (the LWS pass reads LWS rows BEFORE its wait) may
+  // only be released after that: it must not start while the scatter still writes.
   if (a.sweep_flags & kSweepWaitAtTop) pdl_wait_prior();
+  pdl_launch_dependents();
 
   // ---- 1. rows ----
   uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, cc = ca, cd = ca, L = ca;
@@ -1300,7 +1302,9 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const __grid_constant
       const uint4 v = static_cast<const uint4*>(sg.values)[j];
       uint4* dst = static_cast<uint4*>(sg.table) + (uint64_t)r * pieces + piece;
       if (sg.is_ident && a.occupancy != nullptr) {
-        const uint32_t old = dst->w;
+        // (through L2 only: a line of the table cached in this SM's L1 would be stale for the sweep
+        // kernel, which may already be resident — programmatic dependent launch — and reads after us)
+        const uint32_t old = __ldcg(&dst->w);
         if (old != v.w) {
           if ((old & LWSE_PODID_SCHEDULED) && (old >> LWSE_PODID_NODE_SHIFT) < a.n_nodes)
             atomicSub(a.occupancy + (old >> LWSE_PODID_NODE_SHIFT), 1u);
