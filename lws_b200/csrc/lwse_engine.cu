@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 #include <new>
 
@@ -34,10 +35,11 @@ struct PublishListHost {
   uint32_t out_bytes;
 };
 int launch_publish(const PublishListHost* lists, const uint32_t* d_extra, uint32_t* h_words, uint32_t seq_slot,
-                   uint32_t seq, uint32_t* d_ticket, uint32_t expected_rows, cudaStream_t s, int* cuda_err);
+                   uint32_t seq, uint32_t* d_ticket, uint32_t expected_rows, cudaStream_t s, int* cuda_err,
+                   uint32_t* d_seq_counter, uint32_t* d_clear, uint32_t n_clear, bool pdl);
 int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
                      void* scratch, int sm_count, cudaStream_t s, int* cuda_err, const SweepChangeLists* cl,
-                     uint32_t* d_event_count = nullptr, bool first_pdl = true);
+                     uint32_t* d_event_count = nullptr, int first_mode = 1);
 size_t lws_sweep_scratch_bytes(uint64_t n_pods, uint32_t n_groups);
 struct ScatterSegHost {
   void* table;
@@ -50,6 +52,9 @@ struct ScatterSegHost {
 };
 int launch_scatter(const ScatterSegHost* segs, int n_segs, uint32_t* d_occupancy, uint32_t n_nodes, cudaStream_t s,
                    bool pdl, int* cuda_err);
+size_t scatter_desc_bytes();
+bool write_scatter_desc(void* h_desc, const ScatterSegHost* segs, int n_segs, uint32_t* d_occupancy, uint32_t n_nodes);
+int launch_scatter_desc(const void* d_desc, int sm_count, cudaStream_t s, bool pdl, int* cuda_err);
 int launch_ident_prefetch(const uint8_t* d_state, uint64_t n_pods, const lwse_pod_ident* mapped_host_ident,
                           lwse_pod_ident* d_ident, int sm_count, cudaStream_t s, int* cuda_err);
 int launch_occupancy(const lwse_pod_ident* d_ident, uint64_t n_pods, uint32_t* d_occupancy, uint32_t n_nodes, int sm_count,
@@ -198,6 +203,7 @@ struct lwse_engine {
   uint64_t rn_pods = 0;
   bool r_loaded = false, r_place_loaded = false;
   uint32_t tick_seq = 0;
+  uint32_t tick_seq_prev = 0;        // the number of the last tick enqueued (what the device counter holds after it ran)
   // ticks in flight (lwse_resident_tick_submit / _wait): two slots of pinned change lists and words
   struct TickSlot {
     uint32_t seq = 0;
@@ -205,6 +211,21 @@ struct lwse_engine {
   } tslot[2];
   uint64_t t_submitted = 0, t_waited = 0;
   size_t chg_bytes = 0;              // one slot of `chg`
+  // a tick replayed as a CUDA graph (one cudaGraphLaunch instead of ~10 launches of 2-4 us each)
+  struct TickGraph {
+    cudaGraphExec_t exec = nullptr;
+    uint32_t seen = 0;      // eager ticks with this key so far (the first one lets every buffer settle)
+    uint32_t kernels = 0;   // kernel nodes (launch accounting)
+    bool failed = false;    // capture or instantiation failed once: this key stays eager
+  };
+  std::unordered_map<uint32_t, TickGraph> tick_graphs;
+  PinBuf tdesc;                      // 2 slots x 1 KB: [main scatter descriptor | side scatter descriptor] of the tick of that parity
+  DevBuf tdesc_dev;                  // device copy (the copy node at the root of a tick graph fills it)
+  DevBuf seq_dev;                    // device copy of tick_seq (the publish kernel counts replayed ticks itself)
+  cudaStream_t copy_stream = nullptr;  // the patch copy of a replayed tick: overlaps the previous tick's kernels
+  cudaEvent_t ev_dma = nullptr;
+  int use_graph = 1;                 // LWSE_TICK_GRAPH=0: always enqueue kernel by kernel
+  uint64_t graph_ticks = 0;
   cudaEvent_t ev_pub = nullptr;      // behind the previous tick's publish kernel: the next tick's side stream starts there
   int tick_order = 0;                // LWSE_TICK_ORDER (A/B of the tick's enqueue order, see tick_locked)
   uint32_t* h_counts = nullptr;      // pinned, 2 words
@@ -250,6 +271,14 @@ int fail_cuda(lwse_engine* e, cudaError_t err) {
   } while (0)
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Tick graphs freeze device pointers and sizes in their kernel nodes: whatever reallocates or
+// resizes a resident buffer drops them (the next ticks re-capture).
+void invalidate_tick_graphs(lwse_engine* e) {
+  for (auto& kv : e->tick_graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  e->tick_graphs.clear();
+}
 
 struct DeviceGuard {
   int prev = -1;
@@ -354,6 +383,8 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_pub, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_dma, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->hist_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_hist, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_place, cudaEventDisableTiming) != cudaSuccess ||
@@ -363,6 +394,8 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->ev_pub) cudaEventDestroy(e->ev_pub);
+    if (e->ev_dma) cudaEventDestroy(e->ev_dma);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->ev_hist) cudaEventDestroy(e->ev_hist);
     if (e->ev_place) cudaEventDestroy(e->ev_place);
     if (e->hist_stream) cudaStreamDestroy(e->hist_stream);
@@ -382,6 +415,8 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
     const char* o = getenv("LWSE_TICK_ORDER");
     e->tick_order = o ? atoi(o) : 0;
     if (e->tick_order < 0 || e->tick_order > 2) e->tick_order = 0;
+    const char* g = getenv("LWSE_TICK_GRAPH");
+    e->use_graph = g ? atoi(g) : 1;
   }
   *out = e;
   return LWSE_OK;
@@ -394,6 +429,10 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
     cudaStreamSynchronize(e->stream);
     cudaStreamSynchronize(e->side_stream);
     cudaStreamSynchronize(e->hist_stream);  // its copies target h_rounds, freed below
+    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+    for (auto& kv : e->tick_graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    e->tick_graphs.clear();
     for (uint32_t p = 0; p < e->xch_world; p++)
       if (e->xch_connected && p != e->xch_rank && e->xch_peer[p]) cudaIpcCloseMemHandle(e->xch_peer[p]);
     e->xch.release();
@@ -405,9 +444,9 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
                       &e->ds_role_out, &e->ds_revrole_out, &e->sha_bytes, &e->sha_offsets, &e->sha_digests, &e->sha_ints,
                       &e->r_lws, &e->r_groups, &e->r_pst, &e->r_pid, &e->r_lws_out, &e->r_group_out, &e->r_scan,
                       &e->r_counts, &e->r_occ, &e->r_preq, &e->r_pout, &e->r_pout_prev, &e->h_counts_dev, &e->place_ns_scratch,
-                      &e->arena_mirror, &e->stage_mirror, &e->chg_dev};
+                      &e->arena_mirror, &e->stage_mirror, &e->chg_dev, &e->tdesc_dev, &e->seq_dev};
     for (DevBuf* b : bufs) b->release();
-    PinBuf* pins[] = {&e->arena, &e->stage, &e->chg, &e->tickw};
+    PinBuf* pins[] = {&e->arena, &e->stage, &e->chg, &e->tickw, &e->tdesc};
     for (PinBuf* b : pins) b->release();
     if (e->ev_place) cudaEventDestroy(e->ev_place);
     if (e->h_rounds) cudaFreeHost(e->h_rounds);
@@ -417,6 +456,8 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
     cudaEventDestroy(e->ev_fork);
     cudaEventDestroy(e->ev_join);
     if (e->ev_pub) cudaEventDestroy(e->ev_pub);
+    if (e->ev_dma) cudaEventDestroy(e->ev_dma);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     cudaStreamDestroy(e->side_stream);
     cudaStreamDestroy(e->stream);
   }
@@ -433,6 +474,11 @@ LWSE_API int lwse_upload_nodes(lwse_engine* e, const lwse_node_rec* nodes, uint3
   if (n_nodes > LWSE_POD_NODE_MAX) return LWSE_ERR_UNSUPPORTED;
   std::lock_guard<std::mutex> lock(e->mu);
   DeviceGuard guard(e->device);
+  {
+    const int drc = drain_ticks_locked(e);
+    if (drc != LWSE_OK) return drc;
+    invalidate_tick_graphs(e);
+  }
   LWSE_CUDA(e, e->nodes.reserve((size_t)n_nodes * sizeof(lwse_node_rec) + 16));
   // Static index for the placement round: the usable nodes (schedulable, labelled with a
   // topology domain) in domain order — a counting sort, done once per node-table upload.
@@ -613,6 +659,7 @@ static size_t align256(size_t v) { return (v + 255u) & ~(size_t)255u; }
 
 // (re)allocate the pinned change lists for the resident tables' sizes
 static int reserve_change_lists(lwse_engine* e) {
+  invalidate_tick_graphs(e);  // called by both resident loads: table pointers and sizes change
   size_t off = 0;
   const size_t sizes[6] = {(size_t)e->rn_lws * 4,       (size_t)e->rn_lws * sizeof(lwse_lws_out),
                            (size_t)e->rn_groups * 4,    (size_t)e->rn_groups * sizeof(lwse_group_out),
@@ -728,6 +775,10 @@ struct ScatterPlan {  // a prepared scatter launch (apply_patches_locked with `d
   lwse::ScatterSegHost sc[LWSE_TICK_MAX_SEGS];
   int n = 0;
   bool recount = false;
+  // with `plan_only`: nothing was enqueued at all; the arena span [lo, hi) still has to be copied
+  // to the mirror (dma), or — staged segments, range segments — the plan cannot be replayed (eager_only)
+  bool dma = false, eager_only = false;
+  size_t lo = 0, hi = 0;
 };
 
 static int launch_scatter_plan(lwse_engine* e, const ScatterPlan& p, cudaStream_t s) {
@@ -748,7 +799,8 @@ static int launch_scatter_plan(lwse_engine* e, const ScatterPlan& p, cudaStream_
 
 static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_segs, bool* wrote,
                                 uint32_t tables = 0xFFFFFFFFu, cudaStream_t s = nullptr, size_t stage_base = 0,
-                                size_t* stage_used = nullptr, long dma_min_bytes = 0, ScatterPlan* defer = nullptr) {
+                                size_t* stage_used = nullptr, long dma_min_bytes = 0, ScatterPlan* defer = nullptr,
+                                bool plan_only = false) {
   *wrote = false;
   if (stage_used) *stage_used = stage_base;
   if (n_segs == 0) return LWSE_OK;
@@ -807,6 +859,10 @@ static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint
       }
     }
     if (g.flags & LWSE_PATCH_RANGE) {  // one DMA copy straight into the table
+      if (plan_only) {
+        plan.eager_only = true;
+        continue;
+      }
       LWSE_CUDA(e, cudaMemcpyAsync(static_cast<uint8_t*>(base) + (size_t)g.first_row * rb, g.values, (size_t)g.n * rb,
                                    cudaMemcpyHostToDevice, s));
       if (g.table == LWSE_TABLE_POD_IDENT) recount = true;
@@ -817,6 +873,7 @@ static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint
     if (rows_in_place(e, g)) {
       d_rows = e->arena.dev_of(g.rows);
     } else {
+      if (plan_only) plan.eager_only = true;
       uint8_t* dst = static_cast<uint8_t*>(e->stage.h) + cursor;
       memcpy(dst, g.rows, (size_t)g.n * 4);
       d_rows = reinterpret_cast<const uint32_t*>(static_cast<uint8_t*>(e->stage.d) + cursor);
@@ -825,6 +882,7 @@ static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint
     if (values_in_place(e, g, rb)) {
       d_vals = e->arena.dev_of(static_cast<const uint8_t*>(g.values));
     } else {
+      if (plan_only) plan.eager_only = true;
       uint8_t* dst = static_cast<uint8_t*>(e->stage.h) + cursor;
       memcpy(dst, g.values, (size_t)g.n * rb);
       d_vals = static_cast<uint8_t*>(e->stage.d) + cursor;
@@ -864,10 +922,21 @@ static int apply_patches_locked(lwse_engine* e, const lwse_patch_seg* segs, uint
         if (sp.mirror->cap < sp.pin->cap) {  // (first use, or the pinned buffer grew)
           LWSE_CUDA(e, cudaStreamSynchronize(e->stream));
           LWSE_CUDA(e, cudaStreamSynchronize(e->side_stream));
+          LWSE_CUDA(e, cudaStreamSynchronize(e->copy_stream));
           LWSE_CUDA(e, sp.mirror->reserve(sp.pin->cap));
         }
-        LWSE_CUDA(e, cudaMemcpyAsync(static_cast<uint8_t*>(sp.mirror->p) + sp.lo, static_cast<const uint8_t*>(sp.pin->h) + sp.lo,
-                                     sp.hi - sp.lo, cudaMemcpyHostToDevice, s));
+        if (plan_only) {
+          if (sp.pin == &e->stage) {
+            plan.eager_only = true;
+          } else {
+            plan.dma = true;
+            plan.lo = sp.lo;
+            plan.hi = sp.hi;
+          }
+        } else {
+          LWSE_CUDA(e, cudaMemcpyAsync(static_cast<uint8_t*>(sp.mirror->p) + sp.lo, static_cast<const uint8_t*>(sp.pin->h) + sp.lo,
+                                       sp.hi - sp.lo, cudaMemcpyHostToDevice, s));
+        }
         const uintptr_t d0 = reinterpret_cast<uintptr_t>(sp.pin->d), m0 = reinterpret_cast<uintptr_t>(sp.mirror->p);
         for (int k = 0; k < n_sc; k++) {
           uintptr_t a = reinterpret_cast<uintptr_t>(sc[k].rows);
@@ -959,6 +1028,7 @@ static int place_grouped_locked(lwse_engine* e, const lwse_place_req* d_reqs, ui
   memcpy(e->place_ns_geometry, geometry, sizeof(geometry));
   cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
   const bool eager = cudaStreamIsCapturing(s, &capturing) == cudaSuccess && capturing == cudaStreamCaptureStatusNone;
+  if (fresh && eager) invalidate_tick_graphs(e);  // (their kernel nodes hold the old scratch pointers)
   if (eager && e->place_pending) LWSE_CUDA(e, cudaStreamWaitEvent(s, e->ev_place, 0));
   int cuda_err = 0;
   const uint32_t* counters = nullptr;
@@ -1231,7 +1301,7 @@ static int shared_occupancy_place_locked(lwse_engine* e, const lwse_place_req* d
   const uint32_t* occ_parts = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(e->xch.p) + (read_step % 3ull) * e->xch_half);
   if (form != kFormGeneral && lwse::place_ns_supported(e->n_nodes, e->n_domains))
     return place_grouped_locked(e, d_reqs, n_reqs, occ_parts, e->xch_world, e->xch_stride, n_namespaces, d_out,
-                                form == kFormScan, nullptr, nullptr, ps, /*first_pdl=*/false, changes);
+                                form == kFormScan, nullptr, nullptr, ps, /*first_pdl=*/true, changes);  // behind the push kernel
   return LWSE_ERR_UNSUPPORTED;  // the shared-occupancy form needs a request table grouped by namespace
 }
 
@@ -1424,14 +1494,18 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
   const bool in_flight = e->t_submitted != e->t_waited;
   const uint32_t slot = (uint32_t)(e->t_submitted & 1u);
   cudaStream_t s = e->stream;
-  uint32_t seq = ++e->tick_seq;
-  if (seq == 0) seq = ++e->tick_seq;
   uint32_t* hw_dev = static_cast<uint32_t*>(e->tickw.d) + slot * 16u;
   uint8_t* chg_d = static_cast<uint8_t*>(e->chg.d) + slot * e->chg_bytes;  // the pinned lists of this slot, as the device sees them
   uint8_t* chg_v = static_cast<uint8_t*>(e->chg_dev.p);  // the device-memory lists the kernels append to
   const bool do_place = (flags & LWSE_TICK_PLACE) && e->r_place_loaded && e->rn_reqs > 0;
   const bool do_sweep = !(flags & LWSE_TICK_NO_SWEEP) && (e->rn_lws || e->rn_groups);
   if (n_segs && !segs) return LWSE_ERR_INVALID_ARG;
+  // sequence numbers count the ticks that end in a publish kernel (the device counts the same ones)
+  uint32_t seq = 0;
+  if (do_sweep || do_place) {
+    seq = ++e->tick_seq;
+    if (seq == 0) seq = ++e->tick_seq;
+  }
   {
     const size_t ub = stage_bytes_upper_bound(segs, n_segs);
     if (ub > e->stage.cap) {  // rare: only segments outside the arena are staged
@@ -1507,6 +1581,8 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
     return apply_patches_locked(e, segs, n_segs, &wrote_side, kSideTables, ps, stage_used, nullptr, /*dma_min_bytes=*/65536);
   };
   lwse::PublishListHost pl[3] = {};
+  int sweep_first_mode = -1;      // -1: 2 behind this tick's scatter kernel, else 1 (see launch_lws_sweep)
+  bool place_first_pdl = true;    // the round's first kernel follows a kernel on the side stream
   auto enqueue_sweep = [&]() -> int {
     lwse_lws_tables d{};
     d.lws = (const lwse_lws_rec*)e->r_lws.p;
@@ -1528,7 +1604,7 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
     cl.group_capacity = e->rn_groups;
     cl.counts = (uint32_t*)e->r_counts.p;
     int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes, e->r_scan.p, e->sm_count, s,
-                                          &cuda_err, &cl, nullptr, /*first_pdl=*/!wrote);
+                                          &cuda_err, &cl, nullptr, sweep_first_mode >= 0 ? sweep_first_mode : (wrote ? 2 : 1));
     if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
     e->launches += (uint64_t)launched;
     pl[0] = {cl.lws_rows, cl.lws_out, reinterpret_cast<uint32_t*>(chg_d + e->chg_off[0]), chg_d + e->chg_off[1],
@@ -1552,7 +1628,7 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
       diffed = rc == LWSE_OK;
     } else {
       rc = place_locked(e, (const lwse_place_req*)e->r_preq.p, e->rn_reqs, (const uint32_t*)e->r_occ.p, e->rn_namespaces,
-                        (lwse_place_out*)e->r_pout.p, nullptr, ps, 1, e->rn_reqs, 0, false, form, /*first_pdl=*/false, &changes,
+                        (lwse_place_out*)e->r_pout.p, nullptr, ps, 1, e->rn_reqs, 0, false, form, place_first_pdl, &changes,
                         &diffed);
     }
     if (rc != LWSE_OK) return rc;
@@ -1566,6 +1642,145 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
              e->rn_reqs, (uint32_t)sizeof(lwse_place_out)};
     return LWSE_OK;
   };
+  // ---- replay as a CUDA graph --------------------------------------------------------------
+  // Enqueueing a tick kernel by kernel costs ~10 runtime calls of 2-4 us each (launches with
+  // attributes and 200-400 bytes of parameters): more host time than the GPU needs for the tick.
+  // A tick whose patches lie in the arena is therefore replayed as ONE graph per (shape of the
+  // tick, slot): what changes from tick to tick — the scatter segments — travels as a 1 KB
+  // descriptor block (pinned slot -> device, a copy node at the root of the graph), the sequence
+  // number is counted on the device, and the patch bytes go to the mirror on the copy stream
+  // (outside the graph: the copy of tick k+1 overlaps the kernels of tick k).
+  bool any_range = false;
+  for (uint32_t i = 0; i < n_segs; i++)
+    if (segs[i].n && (segs[i].flags & LWSE_PATCH_RANGE)) any_range = true;
+  const bool graph_ok = e->use_graph && all_in_place && !any_range && !(flags & LWSE_TICK_SHARED_OCCUPANCY) &&
+                        (do_sweep || do_place) && !(has_side && !do_place) &&
+                        (!do_place || (e->r_place_grouped && g_place_form_env != 0 && lwse::place_ns_supported(e->n_nodes, e->n_domains)));
+  if (graph_ok) {
+    const uint32_t big_pub = (e->last_changed[0] + e->last_changed[1]) >= 8192u ? 1u : 0u;
+    bool has_main = false;
+    for (uint32_t i = 0; i < n_segs; i++)
+      if (segs[i].n && segs[i].table != LWSE_TABLE_PLACE_REQS) has_main = true;
+    const uint32_t key = (has_main ? 1u : 0u) | (has_side ? 2u : 0u) | (has_ident ? 4u : 0u) | (do_sweep ? 8u : 0u) |
+                         (do_place ? 16u : 0u) | ((flags & LWSE_SWEEP_GANG) ? 32u : 0u) |
+                         ((flags & LWSE_SWEEP_PLACE_SCAN) ? 64u : 0u) | (big_pub << 7) | (slot << 8);
+    lwse_engine::TickGraph& tg = e->tick_graphs[key];
+    bool replay = !tg.failed && tg.seen >= 1;  // the first tick of a shape runs eagerly: every buffer settles
+    tg.seen++;
+    ScatterPlan gp_main, gp_side;
+    if (replay) {
+      bool w1 = false, w2 = false;
+      rc = apply_patches_locked(e, segs, n_segs, &w1, ~kSideTables, s, 0, nullptr, 0, &gp_main, /*plan_only=*/true);
+      if (rc == LWSE_OK && has_side)
+        rc = apply_patches_locked(e, segs, n_segs, &w2, kSideTables, ps, 0, nullptr, /*dma_min_bytes=*/65536, &gp_side, true);
+      if (rc != LWSE_OK) return rc;
+      if (gp_main.eager_only || gp_side.eager_only || gp_main.recount || gp_side.recount || gp_side.dma) replay = false;
+      if (do_place && !e->r_place_grouped) replay = false;  // (a patch moved a request to another namespace)
+    }
+    const size_t desc_bytes = 1024;
+    if (replay && (lwse::scatter_desc_bytes() > desc_bytes / 2 || e->tdesc.reserve(2 * desc_bytes) != cudaSuccess ||
+                   e->tdesc_dev.reserve(2 * desc_bytes) != cudaSuccess || e->seq_dev.reserve(64) != cudaSuccess)) {
+      (void)cudaGetLastError();
+      replay = false;
+    }
+    if (replay) {
+      uint8_t* h_desc = static_cast<uint8_t*>(e->tdesc.h) + slot * desc_bytes;
+      uint8_t* d_desc = static_cast<uint8_t*>(e->tdesc_dev.p) + slot * desc_bytes;
+      uint32_t* occ = e->n_nodes ? (uint32_t*)e->r_occ.p : nullptr;
+      if (!lwse::write_scatter_desc(h_desc, gp_main.sc, gp_main.n, occ, e->n_nodes) ||
+          !lwse::write_scatter_desc(h_desc + desc_bytes / 2, gp_side.sc, gp_side.n, occ, e->n_nodes))
+        replay = false;
+      if (replay && !tg.exec) {
+        // ---- capture: the same enqueue functions, on capturing streams ----
+        // (the device sequence counter has to hold the number of the last tick before the first replay)
+        cudaError_t ce = cudaMemcpyAsync(e->seq_dev.p, &e->tick_seq_prev, 4, cudaMemcpyHostToDevice, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ps);
+        if (ce != cudaSuccess) return fail_cuda(e, ce);
+        const uint64_t launches_before = e->launches;
+        int crc = LWSE_OK;
+        ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);
+        if (ce == cudaSuccess) {
+          auto cap = [&](cudaError_t x) { if (crc == LWSE_OK && x != cudaSuccess) { ce = x; crc = LWSE_ERR_CUDA; } };
+          cap(cudaMemcpyAsync(d_desc, h_desc, desc_bytes, cudaMemcpyHostToDevice, s));
+          auto fork = [&]() {
+            cap(cudaEventRecord(e->ev_fork, s));
+            cap(cudaStreamWaitEvent(ps, e->ev_fork, 0));
+          };
+          auto scatter = [&](const uint8_t* d, cudaStream_t st) {
+            if (crc != LWSE_OK) return;
+            int err = 0;
+            // (an ordinary launch: its predecessor in the graph is a copy node or an event, not a kernel)
+            const int launched = lwse::launch_scatter_desc(d, e->sm_count, st, /*pdl=*/false, &err);
+            if (launched < 0) cap((cudaError_t)err); else e->launches += (uint64_t)launched;
+          };
+          if (do_place && !has_ident) fork();
+          if (has_main) scatter(d_desc, s);
+          if (do_place && has_ident) fork();  // the round reads the occupancy counters the main scatter moves
+          sweep_first_mode = has_main ? 2 : 0;  // behind the scatter kernel: waits at its top; behind the copy node: ordinary
+          place_first_pdl = has_side;           // behind the side scatter kernel, else behind an event
+          if (do_place) {
+            if (has_side) scatter(d_desc + desc_bytes / 2, ps);
+            if (crc == LWSE_OK) crc = enqueue_place();
+          }
+          if (crc == LWSE_OK && do_sweep) crc = enqueue_sweep();
+          if (do_place) {
+            cap(cudaEventRecord(e->ev_join, ps));
+            cap(cudaStreamWaitEvent(s, e->ev_join, 0));
+          }
+          if (crc == LWSE_OK) {
+            int err = 0;
+            const int launched = lwse::launch_publish(pl, do_place ? e->place_rounds_ptr : nullptr, hw_dev, 4, /*seq=*/0u,
+                                                      (uint32_t*)e->r_counts.p + 2, big_pub ? 0xFFFFFFFFu : 0u, s, &err,
+                                                      (uint32_t*)e->seq_dev.p,
+                                                      do_place ? const_cast<uint32_t*>(e->place_rounds_ptr) : nullptr, 8u,
+                                                      /*pdl=*/!do_place);  // (behind the join event: an ordinary launch)
+            if (launched < 0) cap((cudaError_t)err); else e->launches += (uint64_t)launched;
+          }
+          cudaGraph_t graph = nullptr;
+          const cudaError_t ee = cudaStreamEndCapture(s, &graph);
+          if (ee != cudaSuccess || graph == nullptr) cap(ee != cudaSuccess ? ee : cudaErrorUnknown);
+          if (crc == LWSE_OK) cap(cudaGraphInstantiate(&tg.exec, graph, 0));
+          if (graph) cudaGraphDestroy(graph);
+        } else {
+          crc = LWSE_ERR_CUDA;
+        }
+        tg.kernels = (uint32_t)(e->launches - launches_before);
+        e->launches = launches_before;
+        if (crc != LWSE_OK || !tg.exec) {  // this shape stays eager; the streams are usable again after EndCapture
+          (void)cudaGetLastError();
+          if (tg.exec) cudaGraphExecDestroy(tg.exec);
+          tg.exec = nullptr;
+          tg.failed = true;
+          replay = false;
+          sweep_first_mode = -1;
+          place_first_pdl = true;
+          pl[0] = pl[1] = pl[2] = lwse::PublishListHost{};
+        }
+      }
+    }
+    if (replay) {
+      if (gp_main.dma) {  // the patch bytes: arena span -> mirror, on the copy stream
+        LWSE_CUDA(e, cudaMemcpyAsync(static_cast<uint8_t*>(e->arena_mirror.p) + gp_main.lo,
+                                     static_cast<const uint8_t*>(e->arena.h) + gp_main.lo, gp_main.hi - gp_main.lo,
+                                     cudaMemcpyHostToDevice, e->copy_stream));
+        LWSE_CUDA(e, cudaEventRecord(e->ev_dma, e->copy_stream));
+        LWSE_CUDA(e, cudaStreamWaitEvent(s, e->ev_dma, 0));
+      }
+      LWSE_CUDA(e, cudaGraphLaunch(tg.exec, s));
+      e->launches += tg.kernels;
+      e->graph_ticks++;
+      e->tick_seq_prev = seq;
+      lwse_engine::TickSlot& gts = e->tslot[slot];
+      gts.seq = seq;
+      gts.do_sweep = do_sweep;
+      gts.do_place = do_place;
+      gts.published = true;
+      gts.wrote = has_main || has_side;
+      e->t_submitted++;
+      return LWSE_OK;
+    }
+  }
   if (order == 1) {
     rc = apply_side();
     if (rc == LWSE_OK && do_place) rc = enqueue_place();
@@ -1593,10 +1808,12 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
   const bool published = do_sweep || do_place;
   if (published) {
     int launched = lwse::launch_publish(pl, do_place ? e->place_rounds_ptr : nullptr, hw_dev, 4, seq, (uint32_t*)e->r_counts.p + 2,
-                                        e->last_changed[0] + e->last_changed[1], s, &cuda_err);
+                                        e->last_changed[0] + e->last_changed[1], s, &cuda_err, (uint32_t*)e->seq_dev.p, nullptr, 0,
+                                        /*pdl=*/true);
     if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
     e->launches += (uint64_t)launched;
   }
+  if (seq != 0) e->tick_seq_prev = seq;
   lwse_engine::TickSlot& ts = e->tslot[slot];
   ts.seq = seq;
   ts.do_sweep = do_sweep;

@@ -23,6 +23,7 @@
 //
 // All of them are integer/compare kernels bound by HBM traffic.
 #include <cstdlib>
+#include <cstring>
 
 #include "lwse_device.cuh"
 
@@ -1026,7 +1027,14 @@ struct SweepChangeLists {  // device (or mapped host) pointers; all null = off
 // kernel WRITES the input tables (the patch scatter of a tick).
 int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
                      void* scratch, int sm_count, cudaStream_t s, int* cuda_err, const SweepChangeLists* cl,
-                     uint32_t* d_event_count, bool first_pdl) {
+                     uint32_t* d_event_count, int first_mode) {
+  // first_mode — how the sweep's FIRST kernel is launched:
+  //   0  an ordinary launch (its predecessor is a copy, a memset, an event: nothing to overlap with)
+  //   1  programmatically dependent, input tables read before griddepcontrol.wait (the predecessor
+  //      kernel does not write them)
+  //   2  programmatically dependent, waits at its top (the predecessor kernel — a tick's patch
+  //      scatter — WRITES the input tables)
+  const bool first_pdl = first_mode == 1;
   *cuda_err = 0;
   int launches = 0;
   cudaError_t e = cudaSuccess;
@@ -1064,8 +1072,8 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
     if (cl && cl->group_rows) a.changes = ChangeList{cl->group_rows, cl->group_out, cl->counts + 1, cl->group_capacity};
     const uint32_t grid = (t->n_groups + kFusedThreads - 1) / kFusedThreads;
     // (a memset / occupancy kernel right before: an ordinary launch orders behind it)
-    const bool pdl = g_pdl && !t->node_occupancy;
-    if (pdl && !first_pdl) a.sweep_flags |= kSweepWaitAtTop;
+    const bool pdl = g_pdl && !t->node_occupancy && first_mode != 0;
+    if (pdl && first_mode == 2) a.sweep_flags |= kSweepWaitAtTop;
     e = launch_pdl(group_fused_kernel, dim3(grid), dim3(kFusedThreads), 0, s, pdl, a);
     if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
     launches++;
@@ -1141,6 +1149,12 @@ struct PublishArgs {
   uint32_t seq;
   uint32_t* ticket;
   uint32_t fence_each;     // A/B: every CTA fences at system scope as well
+  // graph replay (frozen parameters): seq == 0 -> the sequence number is the device counter + 1 (the
+  // host counts the same ticks); a tick launched eagerly stores its number there.  clear: device
+  // words zeroed after `extra` was read (the placement counters a replayed round accumulates into).
+  uint32_t* seq_counter;
+  uint32_t* clear;
+  uint32_t n_clear;
 };
 
 constexpr uint32_t kPublishThreads = 1024;
@@ -1194,11 +1208,20 @@ __global__ void __launch_bounds__(kPublishThreads) publish_lists_kernel(const Pu
       *a.list[k].count = 0u;  // ready for the next tick (stream-ordered)
     }
     if (a.extra != nullptr) hw[3] = __ldcg(a.extra);
+    for (uint32_t k = 0; k < a.n_clear; k++) a.clear[k] = 0u;
+    uint32_t seq = a.seq;
+    if (a.seq_counter != nullptr) {
+      if (seq == 0u) {
+        seq = *a.seq_counter + 1u;
+        if (seq == 0u) seq = 1u;  // (0 is never a sequence number: lwse_engine::tick_seq skips it the same way)
+      }
+      *a.seq_counter = seq;
+    }
     *a.ticket = 0u;
     // release at system scope (fence.acq_rel.sys + store; __threadfence_system() is the heavier
     // fence.sc.sys + L1 invalidate): everything that happens-before this store is visible to the
     // host thread that observes the word
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.host_words + a.seq_slot), "r"(a.seq) : "memory");
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.host_words + a.seq_slot), "r"(seq) : "memory");
   }
 }
 
@@ -1214,7 +1237,8 @@ struct PublishListHost {
 
 // lists[0..2]: the three slots (host_words[k] receives the count of slot k).
 int launch_publish(const PublishListHost* lists, const uint32_t* d_extra, uint32_t* h_words, uint32_t seq_slot,
-                   uint32_t seq, uint32_t* d_ticket, uint32_t expected_rows, cudaStream_t s, int* cuda_err) {
+                   uint32_t seq, uint32_t* d_ticket, uint32_t expected_rows, cudaStream_t s, int* cuda_err,
+                   uint32_t* d_seq_counter, uint32_t* d_clear, uint32_t n_clear, bool pdl) {
   *cuda_err = 0;
   PublishArgs a{};
   for (int k = 0; k < 3; k++)
@@ -1225,6 +1249,9 @@ int launch_publish(const PublishListHost* lists, const uint32_t* d_extra, uint32
   a.seq_slot = seq_slot;
   a.seq = seq;
   a.ticket = d_ticket;
+  a.seq_counter = d_seq_counter;
+  a.clear = d_clear;
+  a.n_clear = d_clear ? n_clear : 0u;
   static const bool fence_each = [] {
     const char* v = getenv("LWSE_PUBLISH_FENCE_EACH");
     return v && atoi(v) != 0;
@@ -1233,7 +1260,7 @@ int launch_publish(const PublishListHost* lists, const uint32_t* d_extra, uint32
   // ONE CTA for the usual few thousand rows (no ticket stage then); more when the previous tick reported many
   unsigned grid = expected_rows / 8192u + 1u;
   if (grid > 32u) grid = 32u;
-  const cudaError_t e = launch_pdl(publish_lists_kernel, dim3(grid), dim3(kPublishThreads), 0, s, g_pdl, a);
+  const cudaError_t e = launch_pdl(publish_lists_kernel, dim3(grid), dim3(kPublishThreads), 0, s, g_pdl && pdl, a);
   if (e != cudaSuccess) {
     *cuda_err = (int)e;
     return -1;
@@ -1266,9 +1293,7 @@ struct ScatterArgs {
   uint32_t n_nodes;
 };
 
-__global__ void __launch_bounds__(256) scatter_rows_kernel(const __grid_constant__ ScatterArgs a) {
-  pdl_launch_dependents();
-  pdl_wait_prior();  // the tables may still be read by the previous tick's kernels
+__device__ __forceinline__ void scatter_body(const ScatterArgs& a) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.total_work; i += gridDim.x * blockDim.x) {
     int k = 0;
 #pragma unroll
@@ -1317,6 +1342,26 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const __grid_constant
   }
 }
 
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const __grid_constant__ ScatterArgs a) {
+  pdl_launch_dependents();
+  pdl_wait_prior();  // the tables may still be read by the previous tick's kernels
+  scatter_body(a);
+}
+
+// The same kernel for a tick replayed as a CUDA graph: kernel parameters are frozen in a graph, so
+// the segment descriptors of THIS tick come from device memory (a 1 KB copy node at the root of the
+// graph brings them from the pinned slot the host just wrote).
+__global__ void __launch_bounds__(256) scatter_rows_desc_kernel(const ScatterArgs* __restrict__ desc) {
+  __shared__ ScatterArgs s_a;
+  pdl_launch_dependents();
+  pdl_wait_prior();
+  static_assert(sizeof(ScatterArgs) % 4 == 0, "copied word by word");
+  for (uint32_t i = threadIdx.x; i < sizeof(ScatterArgs) / 4u; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&s_a)[i] = __ldcg(reinterpret_cast<const uint32_t*>(desc) + i);
+  __syncthreads();
+  scatter_body(s_a);
+}
+
 struct ScatterSegHost {
   void* table;
   uint64_t table_rows;
@@ -1327,32 +1372,59 @@ struct ScatterSegHost {
   bool is_ident;
 };
 
-int launch_scatter(const ScatterSegHost* segs, int n_segs, uint32_t* d_occupancy, uint32_t n_nodes, cudaStream_t s,
-                   bool pdl, int* cuda_err) {
-  *cuda_err = 0;
+// Segment list -> kernel arguments.  false: more than kMaxScatterSegs segments, a row width the kernel
+// does not handle, or more than 2^32 work items.
+static bool fill_scatter_args(const ScatterSegHost* segs, int n_segs, uint32_t* d_occupancy, uint32_t n_nodes, ScatterArgs* out) {
   ScatterArgs a{};
   uint64_t work = 0;
   int k = 0;
   for (int i = 0; i < n_segs; i++) {
     if (segs[i].n == 0) continue;
-    if (k >= kMaxScatterSegs || (segs[i].row_bytes != 1u && (segs[i].row_bytes & 15u))) {
-      *cuda_err = (int)cudaErrorInvalidValue;
-      return -1;
-    }
+    if (k >= kMaxScatterSegs || (segs[i].row_bytes != 1u && (segs[i].row_bytes & 15u))) return false;
     a.seg[k] = ScatterSeg{segs[i].table, segs[i].rows, segs[i].values, segs[i].table_rows, segs[i].n,
                           segs[i].row_bytes, (uint32_t)work, segs[i].is_ident ? 1u : 0u};
     work += segs[i].row_bytes == 1u ? ((uint64_t)segs[i].n + 3u) / 4u : (uint64_t)segs[i].n * (segs[i].row_bytes >> 4);
     k++;
   }
-  if (k == 0) return 0;
-  if (work > 0xFFFFFFFFull) {
-    *cuda_err = (int)cudaErrorInvalidValue;
-    return -1;
-  }
+  if (work > 0xFFFFFFFFull) return false;
   a.n_segs = (uint32_t)k;
   a.total_work = (uint32_t)work;
   a.occupancy = d_occupancy;
   a.n_nodes = n_nodes;
+  *out = a;
+  return true;
+}
+
+// Graph form: the descriptor block (scatter_desc_bytes() bytes, written by write_scatter_desc into a
+// pinned slot and copied to d_desc by a node of the graph) and a fixed grid.
+size_t scatter_desc_bytes() { return sizeof(ScatterArgs); }
+bool write_scatter_desc(void* h_desc, const ScatterSegHost* segs, int n_segs, uint32_t* d_occupancy, uint32_t n_nodes) {
+  ScatterArgs a{};
+  if (!fill_scatter_args(segs, n_segs, d_occupancy, n_nodes, &a)) return false;
+  memcpy(h_desc, &a, sizeof(a));
+  return true;
+}
+int launch_scatter_desc(const void* d_desc, int sm_count, cudaStream_t s, bool pdl, int* cuda_err) {
+  *cuda_err = 0;
+  const cudaError_t e = launch_pdl(scatter_rows_desc_kernel, dim3((unsigned)sm_count * 4u), dim3(256), 0, s, pdl && g_pdl,
+                                   static_cast<const ScatterArgs*>(d_desc));
+  if (e != cudaSuccess) {
+    *cuda_err = (int)e;
+    return -1;
+  }
+  return 1;
+}
+
+int launch_scatter(const ScatterSegHost* segs, int n_segs, uint32_t* d_occupancy, uint32_t n_nodes, cudaStream_t s,
+                   bool pdl, int* cuda_err) {
+  *cuda_err = 0;
+  ScatterArgs a{};
+  if (!fill_scatter_args(segs, n_segs, d_occupancy, n_nodes, &a)) {
+    *cuda_err = (int)cudaErrorInvalidValue;
+    return -1;
+  }
+  if (a.n_segs == 0) return 0;
+  const uint64_t work = a.total_work;
   uint64_t grid = (work + 255) / 256;
   if (grid > 148ull * 16ull) grid = 148ull * 16ull;
   const cudaError_t e = launch_pdl(scatter_rows_kernel, dim3((unsigned)grid), dim3(256), 0, s, pdl && g_pdl, a);

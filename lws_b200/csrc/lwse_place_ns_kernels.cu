@@ -664,10 +664,10 @@ int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, c
     uint64_t grid = (threads + 255) / 256;
     if (grid < 1) grid = 1;
     if (grid > (uint64_t)sm_count * 8u) grid = (uint64_t)sm_count * 8u;
-    // programmatically dependent whatever runs before it (the kernel waits at its top, before its first
-    // read): behind a tick's scatter kernel the launch latency overlaps the scatter
-    (void)first_pdl;
-    e = launch_pdl(place_condense_kernel, dim3((unsigned)grid), dim3(256), 0, s, true, a);
+    // first_pdl: the predecessor on the stream is a kernel — programmatically dependent then (the
+    // kernel waits at its top, before its first read, so this is safe even behind a tick's scatter
+    // kernel, whose tail the launch latency overlaps); behind a copy / memset / event an ordinary launch
+    e = launch_pdl(place_condense_kernel, dim3((unsigned)grid), dim3(256), 0, s, first_pdl, a);
     if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
   }
   {
