@@ -219,7 +219,7 @@ struct lwse_engine {
     bool failed = false;    // capture or instantiation failed once: this key stays eager
   };
   std::unordered_map<uint32_t, TickGraph> tick_graphs;
-  PinBuf tdesc;                      // 2 slots x 1 KB: [main scatter descriptor | side scatter descriptor] of the tick of that parity
+  PinBuf tdesc;                      // 2 slots x 512 B: the scatter's segment descriptors of the tick of that parity
   DevBuf tdesc_dev;                  // device copy (the copy node at the root of a tick graph fills it)
   DevBuf seq_dev;                    // device copy of tick_seq (the publish kernel counts replayed ticks itself)
   cudaStream_t copy_stream = nullptr;  // the patch copy of a replayed tick: overlaps the previous tick's kernels
@@ -1488,6 +1488,10 @@ struct TickCounts {
   uint32_t n_lws = 0, n_groups = 0, n_place = 0, rounds = 0;
 };
 
+static inline uint8_t* d_desc_of(lwse_engine* e, uint32_t slot, size_t desc_bytes) {
+  return static_cast<uint8_t*>(e->tdesc_dev.p) + slot * desc_bytes;
+}
+
 // Enqueue one tick (nothing waits): slot = t_submitted & 1.  At most two ticks are in flight.
 static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32_t n_segs, uint32_t flags) {
   if (e->t_submitted - e->t_waited >= 2) return LWSE_ERR_NOT_READY;  // wait for the oldest tick first
@@ -1646,10 +1650,11 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
   // Enqueueing a tick kernel by kernel costs ~10 runtime calls of 2-4 us each (launches with
   // attributes and 200-400 bytes of parameters): more host time than the GPU needs for the tick.
   // A tick whose patches lie in the arena is therefore replayed as ONE graph per (shape of the
-  // tick, slot): what changes from tick to tick — the scatter segments — travels as a 1 KB
-  // descriptor block (pinned slot -> device, a copy node at the root of the graph), the sequence
-  // number is counted on the device, and the patch bytes go to the mirror on the copy stream
-  // (outside the graph: the copy of tick k+1 overlaps the kernels of tick k).
+  // tick, slot):   scatter -> { fused -> LWS pass  ||  condense -> namespace kernel } -> publish.
+  // What changes from tick to tick travels outside the graph, on the copy stream, so that the
+  // copies of tick k+1 overlap the kernels of tick k: the patch bytes (arena span -> mirror) and
+  // the scatter's segment descriptors (a 512-byte block, pinned slot -> device).  The sequence
+  // number is counted on the device.
   bool any_range = false;
   for (uint32_t i = 0; i < n_segs; i++)
     if (segs[i].n && (segs[i].flags & LWSE_PATCH_RANGE)) any_range = true;
@@ -1658,27 +1663,25 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
                         (!do_place || (e->r_place_grouped && g_place_form_env != 0 && lwse::place_ns_supported(e->n_nodes, e->n_domains)));
   if (graph_ok) {
     const uint32_t big_pub = (e->last_changed[0] + e->last_changed[1]) >= 8192u ? 1u : 0u;
-    bool has_main = false;
+    bool has_patches = false;
     for (uint32_t i = 0; i < n_segs; i++)
-      if (segs[i].n && segs[i].table != LWSE_TABLE_PLACE_REQS) has_main = true;
-    const uint32_t key = (has_main ? 1u : 0u) | (has_side ? 2u : 0u) | (has_ident ? 4u : 0u) | (do_sweep ? 8u : 0u) |
-                         (do_place ? 16u : 0u) | ((flags & LWSE_SWEEP_GANG) ? 32u : 0u) |
-                         ((flags & LWSE_SWEEP_PLACE_SCAN) ? 64u : 0u) | (big_pub << 7) | (slot << 8);
+      if (segs[i].n) has_patches = true;
+    const uint32_t key = (has_patches ? 1u : 0u) | (do_sweep ? 8u : 0u) | (do_place ? 16u : 0u) |
+                         ((flags & LWSE_SWEEP_GANG) ? 32u : 0u) | ((flags & LWSE_SWEEP_PLACE_SCAN) ? 64u : 0u) | (big_pub << 7) |
+                         (slot << 8);
     lwse_engine::TickGraph& tg = e->tick_graphs[key];
     bool replay = !tg.failed && tg.seen >= 1;  // the first tick of a shape runs eagerly: every buffer settles
     tg.seen++;
-    ScatterPlan gp_main, gp_side;
+    ScatterPlan gp;
     if (replay) {
-      bool w1 = false, w2 = false;
-      rc = apply_patches_locked(e, segs, n_segs, &w1, ~kSideTables, s, 0, nullptr, 0, &gp_main, /*plan_only=*/true);
-      if (rc == LWSE_OK && has_side)
-        rc = apply_patches_locked(e, segs, n_segs, &w2, kSideTables, ps, 0, nullptr, /*dma_min_bytes=*/65536, &gp_side, true);
+      bool w = false;  // one plan for every table: one scatter launch behind one copy of the arena span
+      rc = apply_patches_locked(e, segs, n_segs, &w, 0xFFFFFFFFu, s, 0, nullptr, 0, &gp, /*plan_only=*/true);
       if (rc != LWSE_OK) return rc;
-      if (gp_main.eager_only || gp_side.eager_only || gp_main.recount || gp_side.recount || gp_side.dma) replay = false;
+      if (gp.eager_only || gp.recount) replay = false;
       if (do_place && !e->r_place_grouped) replay = false;  // (a patch moved a request to another namespace)
     }
-    const size_t desc_bytes = 1024;
-    if (replay && (lwse::scatter_desc_bytes() > desc_bytes / 2 || e->tdesc.reserve(2 * desc_bytes) != cudaSuccess ||
+    const size_t desc_bytes = 512;
+    if (replay && (lwse::scatter_desc_bytes() > desc_bytes || e->tdesc.reserve(2 * desc_bytes) != cudaSuccess ||
                    e->tdesc_dev.reserve(2 * desc_bytes) != cudaSuccess || e->seq_dev.reserve(64) != cudaSuccess)) {
       (void)cudaGetLastError();
       replay = false;
@@ -1686,9 +1689,7 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
     if (replay) {
       uint8_t* h_desc = static_cast<uint8_t*>(e->tdesc.h) + slot * desc_bytes;
       uint8_t* d_desc = static_cast<uint8_t*>(e->tdesc_dev.p) + slot * desc_bytes;
-      uint32_t* occ = e->n_nodes ? (uint32_t*)e->r_occ.p : nullptr;
-      if (!lwse::write_scatter_desc(h_desc, gp_main.sc, gp_main.n, occ, e->n_nodes) ||
-          !lwse::write_scatter_desc(h_desc + desc_bytes / 2, gp_side.sc, gp_side.n, occ, e->n_nodes))
+      if (has_patches && !lwse::write_scatter_desc(h_desc, gp.sc, gp.n, e->n_nodes ? (uint32_t*)e->r_occ.p : nullptr, e->n_nodes))
         replay = false;
       if (replay && !tg.exec) {
         // ---- capture: the same enqueue functions, on capturing streams ----
@@ -1702,27 +1703,18 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
         ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);
         if (ce == cudaSuccess) {
           auto cap = [&](cudaError_t x) { if (crc == LWSE_OK && x != cudaSuccess) { ce = x; crc = LWSE_ERR_CUDA; } };
-          cap(cudaMemcpyAsync(d_desc, h_desc, desc_bytes, cudaMemcpyHostToDevice, s));
-          auto fork = [&]() {
+          if (has_patches) {  // the graph's first node: an ordinary launch
+            int err = 0;
+            const int launched = lwse::launch_scatter_desc(d_desc, e->sm_count, s, /*pdl=*/false, &err);
+            if (launched < 0) cap((cudaError_t)err); else e->launches += (uint64_t)launched;
+          }
+          if (do_place) {  // the round forks behind the scatter (it reads the request rows and the occupancy counters)
             cap(cudaEventRecord(e->ev_fork, s));
             cap(cudaStreamWaitEvent(ps, e->ev_fork, 0));
-          };
-          auto scatter = [&](const uint8_t* d, cudaStream_t st) {
-            if (crc != LWSE_OK) return;
-            int err = 0;
-            // (an ordinary launch: its predecessor in the graph is a copy node or an event, not a kernel)
-            const int launched = lwse::launch_scatter_desc(d, e->sm_count, st, /*pdl=*/false, &err);
-            if (launched < 0) cap((cudaError_t)err); else e->launches += (uint64_t)launched;
-          };
-          if (do_place && !has_ident) fork();
-          if (has_main) scatter(d_desc, s);
-          if (do_place && has_ident) fork();  // the round reads the occupancy counters the main scatter moves
-          sweep_first_mode = has_main ? 2 : 0;  // behind the scatter kernel: waits at its top; behind the copy node: ordinary
-          place_first_pdl = has_side;           // behind the side scatter kernel, else behind an event
-          if (do_place) {
-            if (has_side) scatter(d_desc + desc_bytes / 2, ps);
+            place_first_pdl = false;  // (behind an event: an ordinary launch)
             if (crc == LWSE_OK) crc = enqueue_place();
           }
+          sweep_first_mode = has_patches ? 2 : 0;  // behind the scatter kernel: waits at its top; first node: ordinary
           if (crc == LWSE_OK && do_sweep) crc = enqueue_sweep();
           if (do_place) {
             cap(cudaEventRecord(e->ev_join, ps));
@@ -1747,22 +1739,24 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
         }
         tg.kernels = (uint32_t)(e->launches - launches_before);
         e->launches = launches_before;
+        sweep_first_mode = -1;
+        place_first_pdl = true;
         if (crc != LWSE_OK || !tg.exec) {  // this shape stays eager; the streams are usable again after EndCapture
           (void)cudaGetLastError();
           if (tg.exec) cudaGraphExecDestroy(tg.exec);
           tg.exec = nullptr;
           tg.failed = true;
           replay = false;
-          sweep_first_mode = -1;
-          place_first_pdl = true;
           pl[0] = pl[1] = pl[2] = lwse::PublishListHost{};
         }
       }
     }
     if (replay) {
-      if (gp_main.dma) {  // the patch bytes: arena span -> mirror, on the copy stream
-        LWSE_CUDA(e, cudaMemcpyAsync(static_cast<uint8_t*>(e->arena_mirror.p) + gp_main.lo,
-                                     static_cast<const uint8_t*>(e->arena.h) + gp_main.lo, gp_main.hi - gp_main.lo,
+      if (has_patches) {  // patch bytes (arena span -> mirror) and the descriptor block, on the copy stream
+        if (gp.dma)
+          LWSE_CUDA(e, cudaMemcpyAsync(static_cast<uint8_t*>(e->arena_mirror.p) + gp.lo, static_cast<const uint8_t*>(e->arena.h) + gp.lo,
+                                       gp.hi - gp.lo, cudaMemcpyHostToDevice, e->copy_stream));
+        LWSE_CUDA(e, cudaMemcpyAsync(d_desc_of(e, slot, desc_bytes), static_cast<uint8_t*>(e->tdesc.h) + slot * desc_bytes, desc_bytes,
                                      cudaMemcpyHostToDevice, e->copy_stream));
         LWSE_CUDA(e, cudaEventRecord(e->ev_dma, e->copy_stream));
         LWSE_CUDA(e, cudaStreamWaitEvent(s, e->ev_dma, 0));
@@ -1776,7 +1770,7 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
       gts.do_sweep = do_sweep;
       gts.do_place = do_place;
       gts.published = true;
-      gts.wrote = has_main || has_side;
+      gts.wrote = has_patches;
       e->t_submitted++;
       return LWSE_OK;
     }
