@@ -224,7 +224,7 @@ struct lwse_engine {
   DevBuf seq_dev;                    // device copy of tick_seq (the publish kernel counts replayed ticks itself)
   cudaStream_t copy_stream = nullptr;  // the patch copy of a replayed tick: overlaps the previous tick's kernels
   cudaEvent_t ev_dma = nullptr;
-  int use_graph = 1;                 // LWSE_TICK_GRAPH=0: always enqueue kernel by kernel
+  int use_graph = 1;                 // LWSE_TICK_GRAPH: 0 never, 1 when a tick is in flight (default), 2 always
   uint64_t graph_ticks = 0;
   cudaEvent_t ev_pub = nullptr;      // behind the previous tick's publish kernel: the next tick's side stream starts there
   int tick_order = 0;                // LWSE_TICK_ORDER (A/B of the tick's enqueue order, see tick_locked)
@@ -1658,7 +1658,11 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
   bool any_range = false;
   for (uint32_t i = 0; i < n_segs; i++)
     if (segs[i].n && (segs[i].flags & LWSE_PATCH_RANGE)) any_range = true;
-  const bool graph_ok = e->use_graph && all_in_place && !any_range && !(flags & LWSE_TICK_SHARED_OCCUPANCY) &&
+  // (LWSE_TICK_GRAPH: 1 = replay when the previous tick is still in flight — the pipelined use, where the
+  //  host's enqueue time is what limits the rate; a lone tick is faster kernel by kernel, because its
+  //  round starts while the copy engine still moves the pod patches; 2 = always; 0 = never)
+  const bool graph_ok = (e->use_graph >= 2 || (e->use_graph == 1 && in_flight)) && all_in_place && !any_range &&
+                        !(flags & LWSE_TICK_SHARED_OCCUPANCY) &&
                         (do_sweep || do_place) && !(has_side && !do_place) &&
                         (!do_place || (e->r_place_grouped && g_place_form_env != 0 && lwse::place_ns_supported(e->n_nodes, e->n_domains)));
   if (graph_ok) {

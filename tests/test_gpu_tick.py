@@ -34,6 +34,23 @@ def _check_changes(res, prefix, before, after):
 
 @pytest.mark.parametrize("in_arena", [True, False])
 def test_ticks_match_the_oracle(engine, in_arena):
+    _ticks_match_the_oracle(engine, in_arena)
+
+
+def test_graph_replayed_ticks_match_the_oracle(monkeypatch):
+    """LWSE_TICK_GRAPH=2: every eligible tick — also a lone one — is replayed as a CUDA graph (scatter
+    descriptors through the pinned slot, device-side sequence counter).  Same checks, every tick."""
+    from lws_b200.engine import Engine
+
+    monkeypatch.setenv("LWSE_TICK_GRAPH", "2")
+    e = Engine(0)
+    try:
+        _ticks_match_the_oracle(e, True, n_ticks=14)
+    finally:
+        e.close()
+
+
+def _ticks_match_the_oracle(engine, in_arena, n_ticks=9):
     import oracle
 
     p = synth.profile("fuzz", 0.5)
@@ -72,7 +89,7 @@ def test_ticks_match_the_oracle(engine, in_arena):
             if len(ps.req_rows):
                 segs.append((R.TABLE_PLACE_REQS, ps.req_rows, ps.req_vals))
             ticks.append(engine.make_tick(segs, flags))
-    for k in range(9):
+    for k in range(n_ticks):
         ps = plan[k % len(plan)]
         churn.apply_to_mirror(ps, m_pst, m_grp, m_req)
         now = oracle_now()
