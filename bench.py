@@ -219,7 +219,7 @@ def cpu_oracle_rate(t, threads, min_seconds=1.0, max_reps=50):
     return len(t.groups) * reps / dt, dt / reps, reps
 
 
-def churn_plan(t, reqs, place_out, frac_pods=CHURN, frac_reqs=CHURN_REQS, n_sets=4):
+def churn_plan(t, reqs, place_out, frac_pods=CHURN, frac_reqs=CHURN_REQS, n_sets=4, patch_groups=True):
     """The tick-by-tick event stream both arms digest (same seed: same events)."""
     from lws_b200 import churn
     from lws_b200 import records as R
@@ -227,7 +227,7 @@ def churn_plan(t, reqs, place_out, frac_pods=CHURN, frac_reqs=CHURN_REQS, n_sets
     if frac_pods <= 0:
         return [churn.PatchSet(np.zeros(0, np.uint32), R.aligned_empty(0, R.POD_STATE))]
     return churn.make_plan(t, reqs if len(reqs) else None, place_out if len(reqs) else None, frac_pods,
-                           frac_reqs if len(reqs) else 0.0, n_sets=n_sets, seed=11)
+                           frac_reqs if len(reqs) else 0.0, n_sets=n_sets, seed=11, patch_groups=patch_groups)
 
 
 def run_reference(args):
@@ -720,7 +720,7 @@ def run_ours(args):
                                  ("churn_100pct", 1.0, CHURN_REQS), ("no_churn", 0.0, 0.0)):
         if name != "churn_1pct" and world > 1:
             continue
-        plan = churn_plan(t, reqs, base_place, frac_p, frac_r)
+        plan = churn_plan(t, reqs, base_place, frac_p, frac_r, patch_groups=not (args.scaling == "strong" and world > 1))
         # every variant starts from the loaded tables
         eng.resident_load(t.lws, t.groups, t.pod_state, t.pod_ident)
         if n_req:

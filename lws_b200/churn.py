@@ -51,10 +51,13 @@ def _toggle_states(vals: np.ndarray, rng) -> np.ndarray:
 
 
 def make_plan(t, reqs: np.ndarray | None, place_out: np.ndarray | None, frac_pods: float, frac_reqs: float = 0.0,
-              n_sets: int = 4, seed: int = 7) -> list[PatchSet]:
+              n_sets: int = 4, seed: int = 7, patch_groups: bool = True) -> list[PatchSet]:
     """Patch sets for tables ``t`` (a ``synth.Tables``).  Applied in order, cyclically, they keep
     mirror tables on the host consistent: every set's values are computed from the state the
-    previous sets leave behind (the plan simulates the run once)."""
+    previous sets leave behind (the plan simulates the run once).
+    ``patch_groups=False``: the request table is sharded differently from the group table (strong
+    scaling: placement by namespace owner, sweep by UID hash) — a scheduling event then patches the
+    request row here and the group row on the rank that sweeps the group (not generated)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     n_pods = len(t.pod_state)
     state = t.pod_state.copy()
@@ -100,13 +103,15 @@ def make_plan(t, reqs: np.ndarray | None, place_out: np.ndarray | None, frac_pod
             cur_reqs["leader_node"][rr] = new_nodes
             rv = R.aligned_empty(len(rr), R.PLACE_REQ)
             rv[:] = cur_reqs[rr]
-            gr = cur_reqs["group"][rr].astype(np.uint32)
-            groups["leader_node"][gr] = new_nodes
-            gv = R.aligned_empty(len(gr), R.GROUP_REC)
-            gv[:] = groups[gr]
-            ps.req_rows, ps.req_vals, ps.grp_rows, ps.grp_vals = rr, rv, gr, gv
-            dg = np.concatenate([dg, gr])
-            dl = np.concatenate([dl, groups["lws_index"][gr]])
+            ps.req_rows, ps.req_vals = rr, rv
+            if patch_groups:
+                gr = cur_reqs["group"][rr].astype(np.uint32)
+                groups["leader_node"][gr] = new_nodes
+                gv = R.aligned_empty(len(gr), R.GROUP_REC)
+                gv[:] = groups[gr]
+                ps.grp_rows, ps.grp_vals = gr, gv
+                dg = np.concatenate([dg, gr])
+                dl = np.concatenate([dl, groups["lws_index"][gr]])
         ps.dirty_groups = np.unique(dg).astype(np.uint32)
         ps.dirty_lws = np.unique(dl).astype(np.uint32)
         sets.append(ps)
