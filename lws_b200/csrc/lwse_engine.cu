@@ -76,6 +76,7 @@ struct PlaceNsChanges {  // a tick's placement change list (device memory); prev
   lwse_place_out* outs;
   uint32_t* count;
   uint32_t capacity;
+  int tick_slot;  // see lwse_place_ns_kernels.cu
 };
 bool place_ns_supported(uint32_t n_nodes, uint32_t n_domains);
 int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, const uint32_t* d_node_order, uint32_t n_nodes,
@@ -187,7 +188,7 @@ struct lwse_engine {
   uint32_t ident_hint_events = 0;    // event pods the previous host sweep of that table visited
   // resident tables (lwse_resident_*)
   DevBuf r_lws, r_groups, r_pst, r_pid, r_lws_out, r_group_out, r_scan;
-  DevBuf r_counts;                   // [0] lws changes, [1] group changes, [2] publish ticket, [4] place changes
+  DevBuf r_counts;                   // per tick slot (16 words): [0] lws changes, [1] group changes, [2] publish ticket, [4] place changes
   DevBuf r_occ;                      // scheduled pods per node of the resident identity column
   DevBuf r_preq, r_pout, r_pout_prev;  // resident placement requests / results of this and the previous tick
   PinBuf arena;                      // patch arena handed to the caller
@@ -217,6 +218,8 @@ struct lwse_engine {
     uint32_t seen = 0;      // eager ticks with this key so far (the first one lets every buffer settle)
     uint32_t kernels = 0;   // kernel nodes (launch accounting)
     bool failed = false;    // capture or instantiation failed once: this key stays eager
+    bool place_ns = false;  // its round runs the namespace kernels (counters in the slot's block)
+    const uint32_t* rounds_ptr = nullptr;  // where its round counts
   };
   std::unordered_map<uint32_t, TickGraph> tick_graphs;
   PinBuf tdesc;                      // 2 slots x 512 B: the scatter's segment descriptors of the tick of that parity
@@ -224,6 +227,9 @@ struct lwse_engine {
   DevBuf seq_dev;                    // device copy of tick_seq (the publish kernel counts replayed ticks itself)
   cudaStream_t copy_stream = nullptr;  // the patch copy of a replayed tick: overlaps the previous tick's kernels
   cudaEvent_t ev_dma = nullptr;
+  cudaStream_t pub_stream = nullptr;   // the publish kernels: tick k+1 starts while tick k's changed rows travel to the host
+  cudaEvent_t ev_done = nullptr;       // behind the last kernel of a tick on the engine's stream (both branches joined)
+  bool tick_place_ns = false;          // the last enqueue_place() ran the namespace kernels (their counters are per slot)
   int use_graph = 1;                 // LWSE_TICK_GRAPH: 0 never, 1 when a tick is in flight (default), 2 always
   uint64_t graph_ticks = 0;
   cudaEvent_t ev_pub = nullptr;      // behind the previous tick's publish kernel: the next tick's side stream starts there
@@ -385,6 +391,8 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
       cudaEventCreateWithFlags(&e->ev_pub, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_dma, cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->pub_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->hist_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_hist, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_place, cudaEventDisableTiming) != cudaSuccess ||
@@ -396,6 +404,8 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
     if (e->ev_pub) cudaEventDestroy(e->ev_pub);
     if (e->ev_dma) cudaEventDestroy(e->ev_dma);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->ev_done) cudaEventDestroy(e->ev_done);
+    if (e->pub_stream) cudaStreamDestroy(e->pub_stream);
     if (e->ev_hist) cudaEventDestroy(e->ev_hist);
     if (e->ev_place) cudaEventDestroy(e->ev_place);
     if (e->hist_stream) cudaStreamDestroy(e->hist_stream);
@@ -430,6 +440,7 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
     cudaStreamSynchronize(e->side_stream);
     cudaStreamSynchronize(e->hist_stream);  // its copies target h_rounds, freed below
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+    if (e->pub_stream) cudaStreamSynchronize(e->pub_stream);
     for (auto& kv : e->tick_graphs)
       if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     e->tick_graphs.clear();
@@ -458,6 +469,8 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
     if (e->ev_pub) cudaEventDestroy(e->ev_pub);
     if (e->ev_dma) cudaEventDestroy(e->ev_dma);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->ev_done) cudaEventDestroy(e->ev_done);
+    if (e->pub_stream) cudaStreamDestroy(e->pub_stream);
     cudaStreamDestroy(e->side_stream);
     cudaStreamDestroy(e->stream);
   }
@@ -660,6 +673,7 @@ static size_t align256(size_t v) { return (v + 255u) & ~(size_t)255u; }
 // (re)allocate the pinned change lists for the resident tables' sizes
 static int reserve_change_lists(lwse_engine* e) {
   invalidate_tick_graphs(e);  // called by both resident loads: table pointers and sizes change
+  LWSE_CUDA(e, cudaStreamSynchronize(e->pub_stream));  // (a publish kernel may still be copying out of the lists)
   size_t off = 0;
   const size_t sizes[6] = {(size_t)e->rn_lws * 4,       (size_t)e->rn_lws * sizeof(lwse_lws_out),
                            (size_t)e->rn_groups * 4,    (size_t)e->rn_groups * sizeof(lwse_group_out),
@@ -670,7 +684,7 @@ static int reserve_change_lists(lwse_engine* e) {
   }
   e->chg_bytes = off;
   LWSE_CUDA(e, e->chg.reserve(2 * off));  // two ticks may be in flight: the host reads one slot while the next tick fills the other
-  LWSE_CUDA(e, e->chg_dev.reserve(off));
+  LWSE_CUDA(e, e->chg_dev.reserve(2 * off));  // per tick slot: tick k+1 appends while tick k's lists are published
   LWSE_CUDA(e, e->tickw.reserve(256));
   return LWSE_OK;
 }
@@ -697,9 +711,9 @@ LWSE_API int lwse_resident_load(lwse_engine* e, const lwse_lws_tables* h) {
   LWSE_CUDA(e, e->r_lws_out.reserve(b_lo + 16));
   LWSE_CUDA(e, e->r_group_out.reserve(b_go + 16));
   LWSE_CUDA(e, e->r_scan.reserve(lwse::lws_sweep_scratch_bytes(h->n_pods, h->n_groups)));
-  LWSE_CUDA(e, e->r_counts.reserve(64));
+  LWSE_CUDA(e, e->r_counts.reserve(128));  // 64 bytes per tick slot
   LWSE_CUDA(e, e->r_occ.reserve((size_t)e->n_nodes * 4 + 16));
-  LWSE_CUDA(e, cudaMemsetAsync(e->r_counts.p, 0, 64, s));
+  LWSE_CUDA(e, cudaMemsetAsync(e->r_counts.p, 0, 128, s));
   if (b_lws) LWSE_CUDA(e, cudaMemcpyAsync(e->r_lws.p, h->lws, b_lws, cudaMemcpyHostToDevice, s));
   if (b_grp) LWSE_CUDA(e, cudaMemcpyAsync(e->r_groups.p, h->groups, b_grp, cudaMemcpyHostToDevice, s));
   if (b_pst) LWSE_CUDA(e, cudaMemcpyAsync(e->r_pst.p, h->pod_state, b_pst, cudaMemcpyHostToDevice, s));
@@ -1500,7 +1514,8 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
   cudaStream_t s = e->stream;
   uint32_t* hw_dev = static_cast<uint32_t*>(e->tickw.d) + slot * 16u;
   uint8_t* chg_d = static_cast<uint8_t*>(e->chg.d) + slot * e->chg_bytes;  // the pinned lists of this slot, as the device sees them
-  uint8_t* chg_v = static_cast<uint8_t*>(e->chg_dev.p);  // the device-memory lists the kernels append to
+  uint8_t* chg_v = static_cast<uint8_t*>(e->chg_dev.p) + slot * e->chg_bytes;  // the device-memory lists (of this slot) the kernels append to
+  uint32_t* cnt = static_cast<uint32_t*>(e->r_counts.p) + slot * 16u;          // and their counters
   const bool do_place = (flags & LWSE_TICK_PLACE) && e->r_place_loaded && e->rn_reqs > 0;
   const bool do_sweep = !(flags & LWSE_TICK_NO_SWEEP) && (e->rn_lws || e->rn_groups);
   if (n_segs && !segs) return LWSE_ERR_INVALID_ARG;
@@ -1567,10 +1582,12 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
     if (!all_in_place) {
       LWSE_CUDA(e, cudaStreamSynchronize(s));
       LWSE_CUDA(e, cudaStreamSynchronize(ps));
-    } else if (do_place || has_side) {
-      LWSE_CUDA(e, cudaEventRecord(e->ev_pub, s));
-      LWSE_CUDA(e, cudaStreamWaitEvent(ps, e->ev_pub, 0));
     }
+    // the general placement kernel keeps its counters in two alternating scratch halves (a call resets
+    // the half the next one uses): its round may not start before the previous tick's publish kernel
+    // has read them.  (The namespace kernels count in the tick slot's own block.)
+    if (do_place && !(e->r_place_grouped && g_place_form_env != 0 && lwse::place_ns_supported(e->n_nodes, e->n_domains)))
+      LWSE_CUDA(e, cudaStreamWaitEvent(ps, e->ev_pub, 0));
   }
   ScatterPlan main_plan;
   auto apply_main = [&](bool defer) -> int {
@@ -1606,23 +1623,22 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
     cl.group_rows = reinterpret_cast<uint32_t*>(chg_v + e->chg_off[2]);
     cl.group_out = reinterpret_cast<lwse_group_out*>(chg_v + e->chg_off[3]);
     cl.group_capacity = e->rn_groups;
-    cl.counts = (uint32_t*)e->r_counts.p;
+    cl.counts = cnt;
     int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes, e->r_scan.p, e->sm_count, s,
                                           &cuda_err, &cl, nullptr, sweep_first_mode >= 0 ? sweep_first_mode : (wrote ? 2 : 1));
     if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
     e->launches += (uint64_t)launched;
     pl[0] = {cl.lws_rows, cl.lws_out, reinterpret_cast<uint32_t*>(chg_d + e->chg_off[0]), chg_d + e->chg_off[1],
-             (uint32_t*)e->r_counts.p + 0, e->rn_lws, (uint32_t)sizeof(lwse_lws_out)};
+             cnt + 0, e->rn_lws, (uint32_t)sizeof(lwse_lws_out)};
     pl[1] = {cl.group_rows, cl.group_out, reinterpret_cast<uint32_t*>(chg_d + e->chg_off[2]), chg_d + e->chg_off[3],
-             (uint32_t*)e->r_counts.p + 1, e->rn_groups, (uint32_t)sizeof(lwse_group_out)};
+             cnt + 1, e->rn_groups, (uint32_t)sizeof(lwse_group_out)};
     return LWSE_OK;
   };
   auto enqueue_place = [&]() -> int {
     const uint32_t form = !e->r_place_grouped ? kFormGeneral : (flags & LWSE_SWEEP_PLACE_SCAN) ? kFormScan : kFormGrouped;
     // the namespace kernels append the changed rows themselves; the general form gets a diff kernel
     const lwse::PlaceNsChanges changes{(lwse_place_out*)e->r_pout_prev.p, reinterpret_cast<uint32_t*>(chg_v + e->chg_off[4]),
-                                       reinterpret_cast<lwse_place_out*>(chg_v + e->chg_off[5]), (uint32_t*)e->r_counts.p + 4,
-                                       e->rn_reqs};
+                                       reinterpret_cast<lwse_place_out*>(chg_v + e->chg_off[5]), cnt + 4, e->rn_reqs, (int)slot};
     bool diffed = false;
     if (flags & LWSE_TICK_SHARED_OCCUPANCY) {  // multi-rank: this rank's counters go to the peers, the round sees the sum
       if (!e->xch_connected) return LWSE_ERR_NOT_READY;
@@ -1644,6 +1660,22 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
     }
     pl[2] = {changes.rows, changes.outs, reinterpret_cast<uint32_t*>(chg_d + e->chg_off[4]), chg_d + e->chg_off[5], changes.count,
              e->rn_reqs, (uint32_t)sizeof(lwse_place_out)};
+    e->tick_place_ns = diffed;
+    return LWSE_OK;
+  };
+  // The tick's last step, on the publish stream: behind everything the tick enqueued on the engine's
+  // stream (both branches joined there), so the NEXT tick's kernels do not wait for the copy of this
+  // tick's changed rows to the host.  Lists, counters and the round's counter block are per slot.
+  auto enqueue_publish = [&]() -> int {
+    LWSE_CUDA(e, cudaEventRecord(e->ev_done, s));
+    LWSE_CUDA(e, cudaStreamWaitEvent(e->pub_stream, e->ev_done, 0));
+    const bool ns_counters = do_place && e->tick_place_ns;
+    int launched = lwse::launch_publish(pl, do_place ? e->place_rounds_ptr : nullptr, hw_dev, 4, seq, cnt + 2,
+                                        e->last_changed[0] + e->last_changed[1], e->pub_stream, &cuda_err, nullptr,
+                                        ns_counters ? const_cast<uint32_t*>(e->place_rounds_ptr) : nullptr, 8u, /*pdl=*/false);
+    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
+    e->launches += (uint64_t)launched;
+    LWSE_CUDA(e, cudaEventRecord(e->ev_pub, e->pub_stream));
     return LWSE_OK;
   };
   // ---- replay as a CUDA graph --------------------------------------------------------------
@@ -1666,13 +1698,11 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
                         (do_sweep || do_place) && !(has_side && !do_place) &&
                         (!do_place || (e->r_place_grouped && g_place_form_env != 0 && lwse::place_ns_supported(e->n_nodes, e->n_domains)));
   if (graph_ok) {
-    const uint32_t big_pub = (e->last_changed[0] + e->last_changed[1]) >= 8192u ? 1u : 0u;
     bool has_patches = false;
     for (uint32_t i = 0; i < n_segs; i++)
       if (segs[i].n) has_patches = true;
     const uint32_t key = (has_patches ? 1u : 0u) | (do_sweep ? 8u : 0u) | (do_place ? 16u : 0u) |
-                         ((flags & LWSE_SWEEP_GANG) ? 32u : 0u) | ((flags & LWSE_SWEEP_PLACE_SCAN) ? 64u : 0u) | (big_pub << 7) |
-                         (slot << 8);
+                         ((flags & LWSE_SWEEP_GANG) ? 32u : 0u) | ((flags & LWSE_SWEEP_PLACE_SCAN) ? 64u : 0u) | (slot << 8);
     lwse_engine::TickGraph& tg = e->tick_graphs[key];
     bool replay = !tg.failed && tg.seen >= 1;  // the first tick of a shape runs eagerly: every buffer settles
     tg.seen++;
@@ -1697,9 +1727,7 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
         replay = false;
       if (replay && !tg.exec) {
         // ---- capture: the same enqueue functions, on capturing streams ----
-        // (the device sequence counter has to hold the number of the last tick before the first replay)
-        cudaError_t ce = cudaMemcpyAsync(e->seq_dev.p, &e->tick_seq_prev, 4, cudaMemcpyHostToDevice, s);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        cudaError_t ce = cudaStreamSynchronize(s);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(ps);
         if (ce != cudaSuccess) return fail_cuda(e, ce);
         const uint64_t launches_before = e->launches;
@@ -1724,15 +1752,6 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
             cap(cudaEventRecord(e->ev_join, ps));
             cap(cudaStreamWaitEvent(s, e->ev_join, 0));
           }
-          if (crc == LWSE_OK) {
-            int err = 0;
-            const int launched = lwse::launch_publish(pl, do_place ? e->place_rounds_ptr : nullptr, hw_dev, 4, /*seq=*/0u,
-                                                      (uint32_t*)e->r_counts.p + 2, big_pub ? 0xFFFFFFFFu : 0u, s, &err,
-                                                      (uint32_t*)e->seq_dev.p,
-                                                      do_place ? const_cast<uint32_t*>(e->place_rounds_ptr) : nullptr, 8u,
-                                                      /*pdl=*/!do_place);  // (behind the join event: an ordinary launch)
-            if (launched < 0) cap((cudaError_t)err); else e->launches += (uint64_t)launched;
-          }
           cudaGraph_t graph = nullptr;
           const cudaError_t ee = cudaStreamEndCapture(s, &graph);
           if (ee != cudaSuccess || graph == nullptr) cap(ee != cudaSuccess ? ee : cudaErrorUnknown);
@@ -1752,6 +1771,9 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
           tg.failed = true;
           replay = false;
           pl[0] = pl[1] = pl[2] = lwse::PublishListHost{};
+        } else {
+          tg.place_ns = e->tick_place_ns;
+          tg.rounds_ptr = e->place_rounds_ptr;
         }
       }
     }
@@ -1769,6 +1791,21 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
       e->launches += tg.kernels;
       e->graph_ticks++;
       e->tick_seq_prev = seq;
+      if (!pl[0].count && do_sweep) {  // (replayed without capturing: the lists the graph's kernels append to)
+        pl[0] = {reinterpret_cast<uint32_t*>(chg_v + e->chg_off[0]), chg_v + e->chg_off[1], reinterpret_cast<uint32_t*>(chg_d + e->chg_off[0]),
+                 chg_d + e->chg_off[1], cnt + 0, e->rn_lws, (uint32_t)sizeof(lwse_lws_out)};
+        pl[1] = {reinterpret_cast<uint32_t*>(chg_v + e->chg_off[2]), chg_v + e->chg_off[3], reinterpret_cast<uint32_t*>(chg_d + e->chg_off[2]),
+                 chg_d + e->chg_off[3], cnt + 1, e->rn_groups, (uint32_t)sizeof(lwse_group_out)};
+      }
+      if (!pl[2].count && do_place)
+        pl[2] = {reinterpret_cast<uint32_t*>(chg_v + e->chg_off[4]), chg_v + e->chg_off[5], reinterpret_cast<uint32_t*>(chg_d + e->chg_off[4]),
+                 chg_d + e->chg_off[5], cnt + 4, e->rn_reqs, (uint32_t)sizeof(lwse_place_out)};
+      if (do_place) {
+        e->tick_place_ns = tg.place_ns;
+        e->place_rounds_ptr = tg.rounds_ptr;
+      }
+      rc = enqueue_publish();
+      if (rc != LWSE_OK) return rc;
       lwse_engine::TickSlot& gts = e->tslot[slot];
       gts.seq = seq;
       gts.do_sweep = do_sweep;
@@ -1805,11 +1842,8 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
   }
   const bool published = do_sweep || do_place;
   if (published) {
-    int launched = lwse::launch_publish(pl, do_place ? e->place_rounds_ptr : nullptr, hw_dev, 4, seq, (uint32_t*)e->r_counts.p + 2,
-                                        e->last_changed[0] + e->last_changed[1], s, &cuda_err, (uint32_t*)e->seq_dev.p, nullptr, 0,
-                                        /*pdl=*/true);
-    if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
-    e->launches += (uint64_t)launched;
+    rc = enqueue_publish();
+    if (rc != LWSE_OK) return rc;
   }
   if (seq != 0) e->tick_seq_prev = seq;
   lwse_engine::TickSlot& ts = e->tslot[slot];

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) place_condense_kernel(const PlaceNsArgs a
       }
     }
   }
-  if (gtid < 8u) a.next_counters[gtid] = 0u;
+  if (gtid < 8u && a.next_counters != nullptr) a.next_counters[gtid] = 0u;
 }
 
 // --------------------------------------------------------------------------
@@ -519,6 +519,8 @@ struct PlaceNsChanges {  // a tick's change list (device memory); prev == null: 
   lwse_place_out* outs;
   uint32_t* count;
   uint32_t capacity;
+  int tick_slot;  // 0 / 1: the round's counters live in the tick slot's own block, which the tick's publish
+                  // kernel clears after reading (two ticks may be in flight); -1: the two alternating blocks
 };
 
 static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
@@ -618,8 +620,16 @@ int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, c
   a.g_dom_free = reinterpret_cast<uint32_t*>(base + l.dom_free);
   a.ns_first = reinterpret_cast<uint32_t*>(base + l.ns_first);
   a.unpinned = reinterpret_cast<uint32_t*>(base + l.unpinned);
-  a.counters = reinterpret_cast<uint32_t*>(base + l.counters) + (call_index & 1u) * 8u;
-  a.next_counters = reinterpret_cast<uint32_t*>(base + l.counters) + ((call_index + 1u) & 1u) * 8u;
+  // counters: 256 bytes = 8 blocks of 8 words.  Blocks 0 / 1 alternate between calls (a call clears the
+  // block the next one uses); blocks 2 / 3 belong to the tick slots.
+  const int tick_slot = (changes && changes->prev) ? changes->tick_slot : -1;
+  if (tick_slot >= 0) {
+    a.counters = reinterpret_cast<uint32_t*>(base + l.counters) + (2u + (uint32_t)(tick_slot & 1)) * 8u;
+    a.next_counters = nullptr;
+  } else {
+    a.counters = reinterpret_cast<uint32_t*>(base + l.counters) + (call_index & 1u) * 8u;
+    a.next_counters = reinterpret_cast<uint32_t*>(base + l.counters) + ((call_index + 1u) & 1u) * 8u;
+  }
   a.n_nodes = n_nodes;
   a.n_usable = n_usable;
   a.n_domains = n_domains;
