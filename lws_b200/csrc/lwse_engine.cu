@@ -76,7 +76,8 @@ struct PlaceNsChanges {  // a tick's placement change list (device memory); prev
   lwse_place_out* outs;
   uint32_t* count;
   uint32_t capacity;
-  int tick_slot;  // see lwse_place_ns_kernels.cu
+  int tick_slot;    // see lwse_place_ns_kernels.cu
+  void* mid_event;
 };
 bool place_ns_supported(uint32_t n_nodes, uint32_t n_domains);
 int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, const uint32_t* d_node_order, uint32_t n_nodes,
@@ -229,6 +230,7 @@ struct lwse_engine {
   cudaEvent_t ev_dma = nullptr;
   cudaStream_t pub_stream = nullptr;   // the publish kernels: tick k+1 starts while tick k's changed rows travel to the host
   cudaEvent_t ev_done = nullptr;       // behind the last kernel of a tick on the engine's stream (both branches joined)
+  cudaEvent_t ev_mid = nullptr;        // (graph capture) between the condense and the namespace kernel
   bool tick_place_ns = false;          // the last enqueue_place() ran the namespace kernels (their counters are per slot)
   int use_graph = 1;                 // LWSE_TICK_GRAPH: 0 never, 1 when a tick is in flight (default), 2 always
   uint64_t graph_ticks = 0;
@@ -393,6 +395,7 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
       cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->pub_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_mid, cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->hist_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_hist, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_place, cudaEventDisableTiming) != cudaSuccess ||
@@ -405,6 +408,7 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
     if (e->ev_dma) cudaEventDestroy(e->ev_dma);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->ev_done) cudaEventDestroy(e->ev_done);
+    if (e->ev_mid) cudaEventDestroy(e->ev_mid);
     if (e->pub_stream) cudaStreamDestroy(e->pub_stream);
     if (e->ev_hist) cudaEventDestroy(e->ev_hist);
     if (e->ev_place) cudaEventDestroy(e->ev_place);
@@ -470,6 +474,7 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
     if (e->ev_dma) cudaEventDestroy(e->ev_dma);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->ev_done) cudaEventDestroy(e->ev_done);
+    if (e->ev_mid) cudaEventDestroy(e->ev_mid);
     if (e->pub_stream) cudaStreamDestroy(e->pub_stream);
     cudaStreamDestroy(e->side_stream);
     cudaStreamDestroy(e->stream);
@@ -1604,6 +1609,7 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
   lwse::PublishListHost pl[3] = {};
   int sweep_first_mode = -1;      // -1: 2 behind this tick's scatter kernel, else 1 (see launch_lws_sweep)
   bool place_first_pdl = true;    // the round's first kernel follows a kernel on the side stream
+  void* place_mid_event = nullptr;  // (graph capture) recorded between the condense and the namespace kernel
   auto enqueue_sweep = [&]() -> int {
     lwse_lws_tables d{};
     d.lws = (const lwse_lws_rec*)e->r_lws.p;
@@ -1638,7 +1644,8 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
     const uint32_t form = !e->r_place_grouped ? kFormGeneral : (flags & LWSE_SWEEP_PLACE_SCAN) ? kFormScan : kFormGrouped;
     // the namespace kernels append the changed rows themselves; the general form gets a diff kernel
     const lwse::PlaceNsChanges changes{(lwse_place_out*)e->r_pout_prev.p, reinterpret_cast<uint32_t*>(chg_v + e->chg_off[4]),
-                                       reinterpret_cast<lwse_place_out*>(chg_v + e->chg_off[5]), cnt + 4, e->rn_reqs, (int)slot};
+                                       reinterpret_cast<lwse_place_out*>(chg_v + e->chg_off[5]), cnt + 4, e->rn_reqs, (int)slot,
+                                       place_mid_event};
     bool diffed = false;
     if (flags & LWSE_TICK_SHARED_OCCUPANCY) {  // multi-rank: this rank's counters go to the peers, the round sees the sum
       if (!e->xch_connected) return LWSE_ERR_NOT_READY;
@@ -1744,9 +1751,16 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
             cap(cudaEventRecord(e->ev_fork, s));
             cap(cudaStreamWaitEvent(ps, e->ev_fork, 0));
             place_first_pdl = false;  // (behind an event: an ordinary launch)
+            // The fused sweep kernel fills every SM (3 CTAs of 256 x 77 registers) the moment it starts
+            // and the namespace kernel's CTAs (512 x 53 registers) then wait for CTAs to retire: hold
+            // the sweep back until the (short) condense kernel is done, so that both reach the SMs together.
+            place_mid_event = do_sweep ? (void*)e->ev_mid : nullptr;
             if (crc == LWSE_OK) crc = enqueue_place();
+            if (do_sweep && e->tick_place_ns) cap(cudaStreamWaitEvent(s, e->ev_mid, 0));
+            place_mid_event = nullptr;
           }
-          sweep_first_mode = has_patches ? 2 : 0;  // behind the scatter kernel: waits at its top; first node: ordinary
+          // behind the scatter kernel alone: programmatic, waits at its top; behind an event / first node: ordinary
+          sweep_first_mode = (has_patches && !(do_place && e->tick_place_ns)) ? 2 : 0;
           if (crc == LWSE_OK && do_sweep) crc = enqueue_sweep();
           if (do_place) {
             cap(cudaEventRecord(e->ev_join, ps));

@@ -521,6 +521,8 @@ struct PlaceNsChanges {  // a tick's change list (device memory); prev == null: 
   uint32_t capacity;
   int tick_slot;  // 0 / 1: the round's counters live in the tick slot's own block, which the tick's publish
                   // kernel clears after reading (two ticks may be in flight); -1: the two alternating blocks
+  void* mid_event;  // cudaEvent_t or null: recorded between the condense and the namespace kernel (a tick graph
+                    // holds the sweep back until then, so that both branches reach the SMs together)
 };
 
 static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
@@ -679,6 +681,10 @@ int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, c
     // kernel, whose tail the launch latency overlaps); behind a copy / memset / event an ordinary launch
     e = launch_pdl(place_condense_kernel, dim3((unsigned)grid), dim3(256), 0, s, first_pdl, a);
     if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
+    if (changes && changes->mid_event) {
+      e = cudaEventRecord(static_cast<cudaEvent_t>(changes->mid_event), s);
+      if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
+    }
   }
   {
     unsigned grid = n_namespaces < (unsigned)sm_count * 2u ? n_namespaces : (unsigned)sm_count * 2u;

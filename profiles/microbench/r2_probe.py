@@ -65,6 +65,28 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
 show(prof, "resident ticks x3 (1 % churn)")
 
+# two ticks in flight (submit / wait): graph replay after the first few
+e.resident_tick_submit(ap.ticks[0])
+for k in range(1, 12):
+    e.resident_tick_submit(ap.ticks[k % 4])
+    e.resident_tick_wait()
+e.resident_tick_wait()
+t0 = time.perf_counter()
+e.resident_tick_submit(ap.ticks[0])
+for k in range(1, 200):
+    e.resident_tick_submit(ap.ticks[k % 4])
+    e.resident_tick_wait()
+e.resident_tick_wait()
+print("pipelined tick wall us", (time.perf_counter() - t0) / 200 * 1e6)
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    e.resident_tick_submit(ap.ticks[0])
+    for k in range(1, 4):
+        e.resident_tick_submit(ap.ticks[k % 4])
+        e.resident_tick_wait()
+    e.resident_tick_wait()
+    torch.cuda.synchronize()
+show(prof, "pipelined resident ticks x4 (1 % churn, two in flight)", limit=80)
+
 keep = []
 def pinned(a):
     ten = torch.empty(max(a.nbytes, 16), dtype=torch.uint8).pin_memory()
