@@ -830,7 +830,8 @@ def run_ours(args):
         ev = t.event_pods()
         words = (n_pod + 31) // 32
         group_rows = n_grp * (R.GROUP_REC.itemsize + R.GROUP_OUT.itemsize + 1) + n_lws * 16
-        fused_on = n_pod <= 256 * max(n_grp, 1)  # the engine's rule (lwse_lws_kernels.cu launch_lws_sweep)
+        avg_pods = (n_pod + max(n_grp, 1) - 1) // max(n_grp, 1)
+        fused_on = 16 <= avg_pods <= 256  # the engine's rule (lwse_lws_kernels.cu launch_lws_sweep)
         passes = {
             # algorithmic bytes per launch: rows read once + rows written once.  A sweep is the fused
             # scan + group kernel followed by the LWS pass (small groups); the three-kernel form

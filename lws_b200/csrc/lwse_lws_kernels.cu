@@ -1051,9 +1051,16 @@ int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uin
     const char* v = getenv("LWSE_NO_FUSE");
     return v && atoi(v) != 0;
   }();
-  // scan + group pass in one kernel: small groups (the pod window of 256 consecutive groups has to
-  // fit the CTA's bitmap window of 65 536 pods), both passes wanted.
-  const bool fused = group_pass && avg_pods <= 256 && !no_fuse && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN);
+  // scan + group pass in one kernel: mid-sized groups, both passes wanted.  Upper bound: the pod
+  // window of 256 consecutive groups has to fit the CTA's bitmap window of 65 536 pods.  Lower bound:
+  // with a handful of pods per group a CTA of 256 groups streams only 2-4 KB of state and the
+  // kernel is all per-group work — on C5 (1.65 M groups x 8 pods) the fused kernel measured 86 us
+  // against 4.7 + 47.8 us for the scan and the group pass as two kernels.
+  static const uint64_t fuse_min_pods = [] {
+    const char* v = getenv("LWSE_FUSE_MIN_PODS");
+    return v ? (uint64_t)atol(v) : (uint64_t)16;
+  }();
+  const bool fused = group_pass && avg_pods <= 256 && avg_pods >= fuse_min_pods && !no_fuse && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN);
   if (t->node_occupancy && n_nodes && !(t->flags & LWSE_SWEEP_SKIP_POD_SCAN)) {
     e = cudaMemsetAsync(t->node_occupancy, 0, (size_t)n_nodes * sizeof(uint32_t), s);
     if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
