@@ -148,7 +148,8 @@ def test_device_pointer_entry(engine):
     engine.sweep_lws_device(d_lws, len(t.lws), d_grp, len(t.groups), d_pst, d_pid, len(t.pod_state), d_lo, d_go,
                             d_occ, flags=t.flags, stream=stream)
     torch.cuda.synchronize()
-    assert engine.launch_count - before == 3
+    # occupancy count + pod scan + group pass + LWS pass (C5's 8-pod groups are below the fused kernel's threshold)
+    assert engine.launch_count - before == 4
     want = oracle.sweep_lws(t.lws, t.groups, t.pod_state, t.pod_ident, t.nodes, flags=t.flags, want_occupancy=True)
     assert_same(d_lo.cpu().numpy().view(R.LWS_OUT), want[0], "lws_out")
     assert_same(d_go.cpu().numpy().view(R.GROUP_OUT), want[1], "group_out")
