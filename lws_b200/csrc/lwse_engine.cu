@@ -36,7 +36,7 @@ struct PublishListHost {
 };
 int launch_publish(const PublishListHost* lists, const uint32_t* d_extra, uint32_t* h_words, uint32_t seq_slot,
                    uint32_t seq, uint32_t* d_ticket, uint32_t expected_rows, cudaStream_t s, int* cuda_err,
-                   uint32_t* d_seq_counter, uint32_t* d_clear, uint32_t n_clear, bool pdl);
+                   uint32_t* d_clear, uint32_t n_clear, bool pdl);
 int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
                      void* scratch, int sm_count, cudaStream_t s, int* cuda_err, const SweepChangeLists* cl,
                      uint32_t* d_event_count = nullptr, int first_mode = 1);
@@ -205,7 +205,6 @@ struct lwse_engine {
   uint64_t rn_pods = 0;
   bool r_loaded = false, r_place_loaded = false;
   uint32_t tick_seq = 0;
-  uint32_t tick_seq_prev = 0;        // the number of the last tick enqueued (what the device counter holds after it ran)
   // ticks in flight (lwse_resident_tick_submit / _wait): two slots of pinned change lists and words
   struct TickSlot {
     uint32_t seq = 0;
@@ -225,7 +224,6 @@ struct lwse_engine {
   std::unordered_map<uint32_t, TickGraph> tick_graphs;
   PinBuf tdesc;                      // 2 slots x 512 B: the scatter's segment descriptors of the tick of that parity
   DevBuf tdesc_dev;                  // device copy (the copy node at the root of a tick graph fills it)
-  DevBuf seq_dev;                    // device copy of tick_seq (the publish kernel counts replayed ticks itself)
   cudaStream_t copy_stream = nullptr;  // the patch copy of a replayed tick: overlaps the previous tick's kernels
   cudaEvent_t ev_dma = nullptr;
   cudaStream_t pub_stream = nullptr;   // the publish kernels: tick k+1 starts while tick k's changed rows travel to the host
@@ -459,7 +457,7 @@ LWSE_API void lwse_destroy(lwse_engine* e) {
                       &e->ds_role_out, &e->ds_revrole_out, &e->sha_bytes, &e->sha_offsets, &e->sha_digests, &e->sha_ints,
                       &e->r_lws, &e->r_groups, &e->r_pst, &e->r_pid, &e->r_lws_out, &e->r_group_out, &e->r_scan,
                       &e->r_counts, &e->r_occ, &e->r_preq, &e->r_pout, &e->r_pout_prev, &e->h_counts_dev, &e->place_ns_scratch,
-                      &e->arena_mirror, &e->stage_mirror, &e->chg_dev, &e->tdesc_dev, &e->seq_dev};
+                      &e->arena_mirror, &e->stage_mirror, &e->chg_dev, &e->tdesc_dev};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&e->arena, &e->stage, &e->chg, &e->tickw, &e->tdesc};
     for (PinBuf* b : pins) b->release();
@@ -1678,7 +1676,7 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
     LWSE_CUDA(e, cudaStreamWaitEvent(e->pub_stream, e->ev_done, 0));
     const bool ns_counters = do_place && e->tick_place_ns;
     int launched = lwse::launch_publish(pl, do_place ? e->place_rounds_ptr : nullptr, hw_dev, 4, seq, cnt + 2,
-                                        e->last_changed[0] + e->last_changed[1], e->pub_stream, &cuda_err, nullptr,
+                                        e->last_changed[0] + e->last_changed[1], e->pub_stream, &cuda_err,
                                         ns_counters ? const_cast<uint32_t*>(e->place_rounds_ptr) : nullptr, 8u, /*pdl=*/false);
     if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
     e->launches += (uint64_t)launched;
@@ -1689,11 +1687,11 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
   // Enqueueing a tick kernel by kernel costs ~10 runtime calls of 2-4 us each (launches with
   // attributes and 200-400 bytes of parameters): more host time than the GPU needs for the tick.
   // A tick whose patches lie in the arena is therefore replayed as ONE graph per (shape of the
-  // tick, slot):   scatter -> { fused -> LWS pass  ||  condense -> namespace kernel } -> publish.
+  // tick, slot):   scatter -> condense -> { fused -> LWS pass  ||  namespace kernel }.
   // What changes from tick to tick travels outside the graph, on the copy stream, so that the
   // copies of tick k+1 overlap the kernels of tick k: the patch bytes (arena span -> mirror) and
-  // the scatter's segment descriptors (a 512-byte block, pinned slot -> device).  The sequence
-  // number is counted on the device.
+  // the scatter's segment descriptors (a 512-byte block, pinned slot -> device).  The publish
+  // kernel follows on the publish stream, launched with the tick's sequence number.
   bool any_range = false;
   for (uint32_t i = 0; i < n_segs; i++)
     if (segs[i].n && (segs[i].flags & LWSE_PATCH_RANGE)) any_range = true;
@@ -1723,7 +1721,7 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
     }
     const size_t desc_bytes = 512;
     if (replay && (lwse::scatter_desc_bytes() > desc_bytes || e->tdesc.reserve(2 * desc_bytes) != cudaSuccess ||
-                   e->tdesc_dev.reserve(2 * desc_bytes) != cudaSuccess || e->seq_dev.reserve(64) != cudaSuccess)) {
+                   e->tdesc_dev.reserve(2 * desc_bytes) != cudaSuccess)) {
       (void)cudaGetLastError();
       replay = false;
     }
@@ -1804,7 +1802,6 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
       LWSE_CUDA(e, cudaGraphLaunch(tg.exec, s));
       e->launches += tg.kernels;
       e->graph_ticks++;
-      e->tick_seq_prev = seq;
       if (!pl[0].count && do_sweep) {  // (replayed without capturing: the lists the graph's kernels append to)
         pl[0] = {reinterpret_cast<uint32_t*>(chg_v + e->chg_off[0]), chg_v + e->chg_off[1], reinterpret_cast<uint32_t*>(chg_d + e->chg_off[0]),
                  chg_d + e->chg_off[1], cnt + 0, e->rn_lws, (uint32_t)sizeof(lwse_lws_out)};
@@ -1859,7 +1856,6 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
     rc = enqueue_publish();
     if (rc != LWSE_OK) return rc;
   }
-  if (seq != 0) e->tick_seq_prev = seq;
   lwse_engine::TickSlot& ts = e->tslot[slot];
   ts.seq = seq;
   ts.do_sweep = do_sweep;

@@ -1156,10 +1156,7 @@ struct PublishArgs {
   uint32_t seq;
   uint32_t* ticket;
   uint32_t fence_each;     // A/B: every CTA fences at system scope as well
-  // graph replay (frozen parameters): seq == 0 -> the sequence number is the device counter + 1 (the
-  // host counts the same ticks); a tick launched eagerly stores its number there.  clear: device
-  // words zeroed after `extra` was read (the placement counters a replayed round accumulates into).
-  uint32_t* seq_counter;
+  // clear: device words zeroed after `extra` was read (the tick slot's block of placement counters)
   uint32_t* clear;
   uint32_t n_clear;
 };
@@ -1216,19 +1213,11 @@ __global__ void __launch_bounds__(kPublishThreads) publish_lists_kernel(const Pu
     }
     if (a.extra != nullptr) hw[3] = __ldcg(a.extra);
     for (uint32_t k = 0; k < a.n_clear; k++) a.clear[k] = 0u;
-    uint32_t seq = a.seq;
-    if (a.seq_counter != nullptr) {
-      if (seq == 0u) {
-        seq = *a.seq_counter + 1u;
-        if (seq == 0u) seq = 1u;  // (0 is never a sequence number: lwse_engine::tick_seq skips it the same way)
-      }
-      *a.seq_counter = seq;
-    }
     *a.ticket = 0u;
     // release at system scope (fence.acq_rel.sys + store; __threadfence_system() is the heavier
     // fence.sc.sys + L1 invalidate): everything that happens-before this store is visible to the
     // host thread that observes the word
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.host_words + a.seq_slot), "r"(seq) : "memory");
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.host_words + a.seq_slot), "r"(a.seq) : "memory");
   }
 }
 
@@ -1245,7 +1234,7 @@ struct PublishListHost {
 // lists[0..2]: the three slots (host_words[k] receives the count of slot k).
 int launch_publish(const PublishListHost* lists, const uint32_t* d_extra, uint32_t* h_words, uint32_t seq_slot,
                    uint32_t seq, uint32_t* d_ticket, uint32_t expected_rows, cudaStream_t s, int* cuda_err,
-                   uint32_t* d_seq_counter, uint32_t* d_clear, uint32_t n_clear, bool pdl) {
+                   uint32_t* d_clear, uint32_t n_clear, bool pdl) {
   *cuda_err = 0;
   PublishArgs a{};
   for (int k = 0; k < 3; k++)
@@ -1256,7 +1245,6 @@ int launch_publish(const PublishListHost* lists, const uint32_t* d_extra, uint32
   a.seq_slot = seq_slot;
   a.seq = seq;
   a.ticket = d_ticket;
-  a.seq_counter = d_seq_counter;
   a.clear = d_clear;
   a.n_clear = d_clear ? n_clear : 0u;
   static const bool fence_each = [] {

@@ -55,3 +55,27 @@ def test_c3_profile_is_feasible_and_conflict_free():
     assert not (out["flags"][pinned] & R.PLACE_CONFLICT).any()
     assert 0.02 < (~pinned).mean() < 0.09
     assert ((out["flags"][~pinned] & R.PLACE_PLACED) != 0).mean() > 0.95
+
+
+def test_plan_for_a_request_table_sharded_by_namespace_owner():
+    """Strong scaling: the rank's request table (namespaces it owns) refers to groups of OTHER ranks' sweep
+    shards — the plan then patches request rows only (patch_groups=False) and stays self-consistent."""
+    import oracle
+    from lws_b200 import distributed as D
+
+    t = synth.make("C3", 0.03, seed=synth.SEED)
+    world, rank = 4, 1
+    s_lws, s_grp, s_pst, s_pid, lrows, _ = D.shard_lws_tables(t.lws, t.groups, t.pod_state, t.pod_ident, world)[rank]
+    reqs, n_ns, _ = D.requests_of_rank(t.place_requests(), world, rank)
+    shard = synth.Tables(profile=t.profile, lws=s_lws, groups=s_grp, pod_state=s_pst, pod_ident=s_pid, nodes=t.nodes,
+                         n_domains=t.n_domains, flags=t.flags, ns_of_lws=t.ns_of_lws[lrows], n_namespaces=n_ns)
+    assert int(reqs["group"].max()) >= len(s_grp)  # global group rows: not indices into the shard
+    po = oracle.place(t.nodes, R.occupancy_of(t.pod_ident, len(t.nodes)), t.n_domains, n_ns, reqs)
+    plan = churn.make_plan(shard, reqs, po, 0.01, 0.02, n_sets=4, seed=11, patch_groups=False)
+    m_pst, m_grp, m_req = s_pst.copy(), s_grp.copy(), reqs.copy()
+    for ps in plan:
+        assert len(ps.grp_rows) == 0 and len(ps.req_rows) > 0 and len(ps.pod_rows) > 0
+        churn.apply_to_mirror(ps, m_pst, m_grp, m_req)
+    assert m_grp.tobytes() == s_grp.tobytes()
+    # sets 0/1 and 2/3 are scheduling events and their undo: the request table is back where it started
+    assert m_req.tobytes() == reqs.tobytes()
