@@ -79,13 +79,18 @@ struct PlaceNsChanges {  // a tick's placement change list (device memory); prev
   int tick_slot;    // see lwse_place_ns_kernels.cu
   void* mid_event;
 };
+struct PlaceNsExchange {
+  const unsigned long long* step_ctr;
+  uint64_t half_bytes;
+  bool lagged;
+};
 bool place_ns_supported(uint32_t n_nodes, uint32_t n_domains);
 int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, const uint32_t* d_node_order, uint32_t n_nodes,
                     uint32_t n_usable, uint32_t n_domains, const lwse_place_req* d_reqs, uint32_t n_reqs,
                     const uint32_t* d_occupancy, uint32_t n_parts, uint64_t part_stride_bytes, uint32_t n_namespaces,
                     lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes, bool fresh, uint32_t call_index, bool scan,
                     int sm_count, cudaStream_t s, int* cuda_err, const uint32_t** d_counters_out, bool first_pdl,
-                    const PlaceNsChanges* changes);
+                    const PlaceNsChanges* changes, const PlaceNsExchange* xch);
 int launch_place_diff(const lwse_place_out* d_cur, lwse_place_out* d_prev, uint32_t n, uint32_t* d_rows,
                       lwse_place_out* d_outs, uint32_t capacity, uint32_t* d_count, cudaStream_t s, int* cuda_err);
 // lwse_ds_kernels.cu
@@ -99,7 +104,8 @@ int launch_subgroup_keys(const uint8_t* d_bytes, const uint32_t* d_offsets, uint
 // lwse_exchange_kernels.cu
 int launch_exchange_push(const void* d_local_part, uint8_t* const* d_peer_base, void* d_local_base,
                          uint64_t part_bytes, uint64_t part_stride, uint64_t half_bytes, uint64_t flags_offset,
-                         uint64_t step, uint64_t wait_step, uint32_t world, uint32_t rank, cudaStream_t s, int* cuda_err);
+                         uint64_t step, uint64_t wait_step, uint32_t world, uint32_t rank, cudaStream_t s, int* cuda_err,
+                         bool lagged);
 }  // namespace lwse
 
 
@@ -1036,7 +1042,7 @@ static const int g_place_form_env = [] {  // LWSE_PLACE_FORM=general|grouped|sca
 static int place_grouped_locked(lwse_engine* e, const lwse_place_req* d_reqs, uint32_t n_reqs, const uint32_t* d_occupancy,
                                 uint32_t n_parts, uint64_t part_stride_bytes, uint32_t n_namespaces, lwse_place_out* d_out,
                                 bool scan, uint32_t* rounds_out, uint32_t* scans_out, cudaStream_t s, bool first_pdl,
-                                const lwse::PlaceNsChanges* changes = nullptr) {
+                                const lwse::PlaceNsChanges* changes = nullptr, const lwse::PlaceNsExchange* xch = nullptr) {
   const size_t scratch = lwse::place_ns_scratch_bytes(e->n_nodes, e->n_domains, n_reqs, n_namespaces);
   const void* before = e->place_ns_scratch.p;
   LWSE_CUDA(e, e->place_ns_scratch.reserve(scratch));
@@ -1053,7 +1059,7 @@ static int place_grouped_locked(lwse_engine* e, const lwse_place_req* d_reqs, ui
                                        (const uint32_t*)e->node_order.p, e->n_nodes, e->n_usable, e->n_domains, d_reqs, n_reqs,
                                        d_occupancy, n_parts, part_stride_bytes, n_namespaces, d_out, e->place_ns_scratch.p,
                                        scratch, fresh, e->place_ns_calls++, scan, e->sm_count, s, &cuda_err, &counters,
-                                       first_pdl && !fresh, changes);
+                                       first_pdl && !fresh, changes, xch);
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
   e->place_rounds_ptr = counters;
@@ -1279,7 +1285,7 @@ LWSE_API int lwse_reconcile_exchanged_device(lwse_engine* e, const lwse_lws_tabl
   int cuda_err = 0;
   int launched = lwse::launch_exchange_push(d_local_part, (uint8_t* const*)e->xch_peers_dev.p, e->xch.p, e->xch_stride,
                                             e->xch_stride, e->xch_half, e->xch_flags_off, step, step, e->xch_world,
-                                            e->xch_rank, e->side_stream, &cuda_err);
+                                            e->xch_rank, e->side_stream, &cuda_err, false);
   if (launched < 0) {
     rc = fail_cuda(e, (cudaError_t)cuda_err);
   } else {
@@ -1305,20 +1311,27 @@ static int shared_occupancy_place_locked(lwse_engine* e, const lwse_place_req* d
                                          const uint32_t* d_local_occ, uint32_t n_namespaces, lwse_place_out* d_out,
                                          uint32_t form, bool lagged, cudaStream_t ps,
                                          const lwse::PlaceNsChanges* changes = nullptr) {
-  const uint64_t step = ++e->xch_step;
+  // While a tick graph is being captured the step is not a parameter: the push kernel takes it from
+  // the device counter every push advances (and the condense kernel the blocks to sum from the same
+  // counter), so that the replayed nodes follow the step; the replay itself advances e->xch_step.
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  const bool eager = cudaStreamIsCapturing(ps, &capturing) == cudaSuccess && capturing == cudaStreamCaptureStatusNone;
+  const uint64_t step = eager ? ++e->xch_step : 0ull;
   const uint64_t read_step = (lagged && step > 1) ? step - 1 : step;
   int cuda_err = 0;
   int launched = lwse::launch_exchange_push(d_local_occ, (uint8_t* const*)e->xch_peers_dev.p, e->xch.p,
                                             e->xch_reqs_off,  // the occupancy block of a part: n_nodes counters, 16-byte padded
                                             e->xch_stride, e->xch_half, e->xch_flags_off, step, read_step, e->xch_world,
-                                            e->xch_rank, ps, &cuda_err);
+                                            e->xch_rank, ps, &cuda_err, lagged);
   if (launched < 0) return fail_cuda(e, (cudaError_t)cuda_err);
   e->launches += (uint64_t)launched;
   if (n_reqs == 0) return LWSE_OK;
-  const uint32_t* occ_parts = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(e->xch.p) + (read_step % 3ull) * e->xch_half);
+  const lwse::PlaceNsExchange xch{reinterpret_cast<const unsigned long long*>(static_cast<const uint8_t*>(e->xch.p) + e->xch_flags_off +
+                                                                              (uint64_t)e->xch_world * 8u + 16u),
+                                  e->xch_half, lagged};
   if (form != kFormGeneral && lwse::place_ns_supported(e->n_nodes, e->n_domains))
-    return place_grouped_locked(e, d_reqs, n_reqs, occ_parts, e->xch_world, e->xch_stride, n_namespaces, d_out,
-                                form == kFormScan, nullptr, nullptr, ps, /*first_pdl=*/true, changes);  // behind the push kernel
+    return place_grouped_locked(e, d_reqs, n_reqs, static_cast<const uint32_t*>(e->xch.p), e->xch_world, e->xch_stride, n_namespaces,
+                                d_out, form == kFormScan, nullptr, nullptr, ps, /*first_pdl=*/true, changes, &xch);  // behind the push kernel
   return LWSE_ERR_UNSUPPORTED;  // the shared-occupancy form needs a request table grouped by namespace
 }
 
@@ -1698,8 +1711,9 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
   // (LWSE_TICK_GRAPH: 1 = replay when the previous tick is still in flight — the pipelined use, where the
   //  host's enqueue time is what limits the rate; a lone tick is faster kernel by kernel, because its
   //  round starts while the copy engine still moves the pod patches; 2 = always; 0 = never)
+  const bool shared_occ = (flags & LWSE_TICK_SHARED_OCCUPANCY) != 0;
   const bool graph_ok = (e->use_graph >= 2 || (e->use_graph == 1 && in_flight)) && all_in_place && !any_range &&
-                        !(flags & LWSE_TICK_SHARED_OCCUPANCY) &&
+                        (!shared_occ || (do_place && e->xch_connected)) &&
                         (do_sweep || do_place) && !(has_side && !do_place) &&
                         (!do_place || (e->r_place_grouped && g_place_form_env != 0 && lwse::place_ns_supported(e->n_nodes, e->n_domains)));
   if (graph_ok) {
@@ -1707,7 +1721,8 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
     for (uint32_t i = 0; i < n_segs; i++)
       if (segs[i].n) has_patches = true;
     const uint32_t key = (has_patches ? 1u : 0u) | (do_sweep ? 8u : 0u) | (do_place ? 16u : 0u) |
-                         ((flags & LWSE_SWEEP_GANG) ? 32u : 0u) | ((flags & LWSE_SWEEP_PLACE_SCAN) ? 64u : 0u) | (slot << 8);
+                         ((flags & LWSE_SWEEP_GANG) ? 32u : 0u) | ((flags & LWSE_SWEEP_PLACE_SCAN) ? 64u : 0u) | (slot << 8) |
+                         (shared_occ ? 512u : 0u) | ((shared_occ && (flags & LWSE_EXCHANGE_LAGGED)) ? 1024u : 0u);
     lwse_engine::TickGraph& tg = e->tick_graphs[key];
     bool replay = !tg.failed && tg.seen >= 1;  // the first tick of a shape runs eagerly: every buffer settles
     tg.seen++;
@@ -1802,6 +1817,7 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
       LWSE_CUDA(e, cudaGraphLaunch(tg.exec, s));
       e->launches += tg.kernels;
       e->graph_ticks++;
+      if (shared_occ) e->xch_step++;  // (the replayed push kernel advanced the device counter by one)
       if (!pl[0].count && do_sweep) {  // (replayed without capturing: the lists the graph's kernels append to)
         pl[0] = {reinterpret_cast<uint32_t*>(chg_v + e->chg_off[0]), chg_v + e->chg_off[1], reinterpret_cast<uint32_t*>(chg_d + e->chg_off[0]),
                  chg_d + e->chg_off[1], cnt + 0, e->rn_lws, (uint32_t)sizeof(lwse_lws_out)};

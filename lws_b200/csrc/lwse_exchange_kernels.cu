@@ -30,7 +30,10 @@ struct ExchangeArgs {
   uint32_t* ticket;                // local: CTA completion counter
   uint32_t* error;                 // local: set to 1 when the wait timed out
   uint64_t part_bytes, part_stride, half_bytes, flags_offset;
-  uint64_t step, wait_step;
+  uint64_t step, wait_step;        // step == 0: this launch is a node of a replayed graph — the step is the
+                                   // device counter + 1 (the host counts the same calls), lagged as below
+  unsigned long long* step_ctr;    // local: the step of the last push (every launch stores its step there)
+  uint32_t lagged;
   uint32_t world, rank;
   uint64_t timeout_ns;
 };
@@ -47,8 +50,13 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __global__ void __launch_bounds__(256) exchange_push_kernel(const ExchangeArgs a) {
   __shared__ uint32_t s_last;
   pdl_launch_dependents();  // the placement round may take its SMs now; it waits for this grid to complete
+  uint64_t step = a.step, wait_step = a.wait_step;
+  if (step == 0ull) {  // (every CTA reads the counter before the last one — the last to finish — advances it)
+    step = *reinterpret_cast<volatile unsigned long long*>(a.step_ctr) + 1ull;
+    wait_step = (a.lagged && step > 1ull) ? step - 1ull : step;
+  }
   const uint64_t n_vec = a.part_bytes >> 4;
-  const uint64_t dst_off = (a.step % 3ull) * a.half_bytes + (uint64_t)a.rank * a.part_stride;
+  const uint64_t dst_off = (step % 3ull) * a.half_bytes + (uint64_t)a.rank * a.part_stride;
   // every peer's copy of this rank's part: the loads of the local part are shared by all targets
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint4 v = __ldg(a.local_part + i);
@@ -61,14 +69,17 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const ExchangeArgs a
   if (!s_last) return;
   // last CTA: every CTA's stores are out (each fenced before taking its ticket)
   __threadfence_system();
-  if (threadIdx.x == 0) *a.ticket = 0u;  // ready for the next launch (stream-ordered)
+  if (threadIdx.x == 0) {
+    *a.ticket = 0u;  // ready for the next launch (stream-ordered)
+    *a.step_ctr = step;
+  }
   if (threadIdx.x < a.world) {
     unsigned long long* peer_flags = reinterpret_cast<unsigned long long*>(a.peer_base[threadIdx.x] + a.flags_offset);
-    st_release_sys(peer_flags + a.rank, a.step);
+    st_release_sys(peer_flags + a.rank, step);
     // … and wait for source threadIdx.x to have pushed this step here
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (ld_acquire_sys(a.flags + threadIdx.x) < a.wait_step) {
+    while (ld_acquire_sys(a.flags + threadIdx.x) < wait_step) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (t - t0 > a.timeout_ns) {  // a peer is gone: do not hang the GPU, report
@@ -81,7 +92,8 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const ExchangeArgs a
 
 int launch_exchange_push(const void* d_local_part, uint8_t* const* d_peer_base, void* d_local_base,
                          uint64_t part_bytes, uint64_t part_stride, uint64_t half_bytes, uint64_t flags_offset,
-                         uint64_t step, uint64_t wait_step, uint32_t world, uint32_t rank, cudaStream_t s, int* cuda_err) {
+                         uint64_t step, uint64_t wait_step, uint32_t world, uint32_t rank, cudaStream_t s, int* cuda_err,
+                         bool lagged) {
   *cuda_err = 0;
   ExchangeArgs a{};
   uint8_t* base = static_cast<uint8_t*>(d_local_base);
@@ -90,6 +102,8 @@ int launch_exchange_push(const void* d_local_part, uint8_t* const* d_peer_base, 
   a.flags = reinterpret_cast<unsigned long long*>(base + flags_offset);
   a.ticket = reinterpret_cast<uint32_t*>(base + flags_offset + (uint64_t)world * 8u);
   a.error = a.ticket + 1;
+  a.step_ctr = reinterpret_cast<unsigned long long*>(base + flags_offset + (uint64_t)world * 8u + 16u);
+  a.lagged = lagged ? 1u : 0u;
   a.part_bytes = part_bytes;
   a.part_stride = part_stride;
   a.half_bytes = half_bytes;

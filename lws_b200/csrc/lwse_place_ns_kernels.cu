@@ -68,6 +68,11 @@ struct PlaceNsArgs {
   lwse_place_out* chg_outs;
   uint32_t* chg_count;
   uint32_t chg_capacity;
+  // multi-rank ticks: `occupancy` is the base of the exchange buffers; the blocks to sum are those of
+  // step (lagged ? step - 1 : step) where step = *xch_step (the push kernel right before stored it)
+  const unsigned long long* xch_step;
+  uint64_t xch_half_bytes;
+  uint32_t xch_lagged;
 };
 
 __device__ __forceinline__ uint32_t mix32n(uint32_t x) {
@@ -84,11 +89,11 @@ __device__ __forceinline__ unsigned long long ns_place_key(unsigned long long pr
          (unsigned long long)(index & 0xFFFFFFu);
 }
 
-__device__ __forceinline__ uint32_t occupancy_sum(const PlaceNsArgs& a, uint32_t n) {
-  if (!a.occupancy) return 0u;
+__device__ __forceinline__ uint32_t occupancy_sum(const PlaceNsArgs& a, const uint32_t* base, uint32_t n) {
+  if (!base) return 0u;
   uint32_t occ = 0;
   for (uint32_t p = 0; p < a.n_parts; p++)
-    occ += ldg_keep_u32(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(a.occupancy) +
+    occ += ldg_keep_u32(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(base) +
                                                            (uint64_t)p * a.part_stride_bytes) + n);
   return occ;
 }
@@ -106,6 +111,12 @@ __global__ void __launch_bounds__(256) place_condense_kernel(const PlaceNsArgs a
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
   pdl_launch_dependents();  // the namespace kernel may load its requests meanwhile; it waits before the tables below
   pdl_wait_prior();         // the previous call's namespace kernel may still read the tables written here
+  const uint32_t* occ_base = a.occupancy;
+  if (a.xch_step != nullptr && occ_base != nullptr) {
+    const unsigned long long step = *reinterpret_cast<const volatile unsigned long long*>(a.xch_step);
+    const unsigned long long read_step = (a.xch_lagged && step > 1ull) ? step - 1ull : step;
+    occ_base = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(occ_base) + (read_step % 3ull) * a.xch_half_bytes);
+  }
   // A. a warp per domain: its nodes are a run of the sorted index
   for (uint32_t d = gwarp; d < a.n_domains; d += n_warps) {
     const uint32_t first = ldg_keep_u32(a.dom_first + d), last = ldg_keep_u32(a.dom_first + d + 1u);
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__(256) place_condense_kernel(const PlaceNsArgs a
     for (uint32_t i = first + lane; i < last; i += 32u) {
       const uint32_t n = ldg_keep_u32(a.node_order + i);
       const uint4 nr = ldg_keep(reinterpret_cast<const uint4*>(a.nodes + n));
-      const uint32_t cap = nr.w & 0xFFFFu, occ = occupancy_sum(a, n);
+      const uint32_t cap = nr.w & 0xFFFFu, occ = occupancy_sum(a, occ_base, n);
       const uint32_t fr = cap > occ ? cap - occ : 0u;
       a.g_words[i] = (min(fr, 15u) << 28) | d;
       a.g_nodes2[i] = (min(fr, 15u) << 28) | n;
@@ -525,6 +536,12 @@ struct PlaceNsChanges {  // a tick's change list (device memory); prev == null: 
                     // holds the sweep back until then, so that both branches reach the SMs together)
 };
 
+struct PlaceNsExchange {  // multi-rank: d_occupancy is the base of the exchange buffers (see PlaceNsArgs::xch_step)
+  const unsigned long long* step_ctr;
+  uint64_t half_bytes;
+  bool lagged;
+};
+
 static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 
 // scratch: [words (rows x 1 KB)] [nodes2 (same)] [dom_free] [ns_first] [unpinned] [counters: 2 blocks of 8 words]
@@ -597,7 +614,7 @@ int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, c
                     const uint32_t* d_occupancy, uint32_t n_parts, uint64_t part_stride_bytes, uint32_t n_namespaces,
                     lwse_place_out* d_out, void* d_scratch, size_t scratch_bytes, bool fresh, uint32_t call_index, bool scan,
                     int sm_count, cudaStream_t s, int* cuda_err, const uint32_t** d_counters_out, bool first_pdl,
-                    const PlaceNsChanges* changes) {
+                    const PlaceNsChanges* changes, const PlaceNsExchange* xch) {
   *cuda_err = 0;
   const NsLayout l = ns_layout(n_nodes, n_domains, n_reqs, n_namespaces);
   if (scratch_bytes < l.total || n_reqs > 0xFFFFFFu) {
@@ -641,6 +658,11 @@ int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, c
   a.part_stride_bytes = part_stride_bytes;
   a.word_rows = l.word_rows;
   a.scan = scan ? 1u : 0u;
+  if (xch && xch->step_ctr) {
+    a.xch_step = xch->step_ctr;
+    a.xch_half_bytes = xch->half_bytes;
+    a.xch_lagged = xch->lagged ? 1u : 0u;
+  }
   if (d_counters_out) *d_counters_out = a.counters;
   if (changes && changes->prev) {
     a.prev = changes->prev;
