@@ -199,6 +199,70 @@ def test_range_patch_and_identity_patches_keep_the_occupancy(engine):
     assert np.array_equal(engine.resident_occupancy(), R.occupancy_of(m_pid, len(t.nodes)))
 
 
+def test_watch_events_pipelined_through_the_arena(engine):
+    """The informer's patch segments written into alternating halves of the engine's arena and submitted
+    with two ticks in flight (the later ones replayed as graphs): the final resident state equals the
+    oracle on a fresh encode of the same objects, by name — sweep rows, occupancy, placement rows."""
+    import oracle
+    from informer_world import World, make_world, outputs_by_name
+    from lws_b200 import encoder, informer
+
+    items, cluster = make_world(5, n_lws=24, n_nodes=40)
+    world = World(items, cluster, 6)
+    enc = informer.IncrementalEncoder(list(world.items.values()), world.cluster(), "zone")
+    lws, groups, pst, pid, reqs = enc.full_tables()
+    engine.upload_nodes(enc.node_rec, len(enc.domain_values))
+    engine.resident_load(lws, groups, pst, pid)
+    engine.resident_place_load(reqs, enc.n_namespaces)
+    flags = R.SWEEP_GANG | R.TICK_PLACE
+    engine.resident_tick(engine.make_tick((), flags))
+    half = 1 << 20
+    arena = engine.resident_arena(2 * half)
+
+    def in_arena(segments, which):
+        cursor, out = which * half, []
+        for table, rows, vals in segments:
+            views = []
+            for a in (np.ascontiguousarray(rows, dtype=np.uint32), np.ascontiguousarray(vals)):
+                cursor = (cursor + 255) // 256 * 256
+                v = arena[cursor: cursor + a.nbytes].view(a.dtype)
+                v[...] = a
+                cursor += a.nbytes
+                views.append(v)
+            out.append((table, views[0], views[1]))
+        assert cursor <= (which + 1) * half
+        return out
+
+    n_ticks, in_flight = 24, 0
+    for tick in range(n_ticks):
+        for _ in range(int(world.rng.integers(1, 6))):
+            world.step(enc)
+        patches = enc.flush()
+        assert not enc.needs_reload
+        t = engine.make_tick(in_arena(patches.segments, tick & 1), flags)
+        if in_flight == 2:  # the tick that used this half of the arena two ticks ago
+            engine.resident_tick_wait()
+            in_flight -= 1
+        engine.resident_tick_submit(t)
+        in_flight += 1
+    while in_flight:
+        engine.resident_tick_wait()
+        in_flight -= 1
+    names = {sl.lws_row: key for key, sl in enc.slots.items()}
+    g_lo, g_go = engine.resident_outputs()
+    got_l, got_g = outputs_by_name(enc.lws[: enc.n_lws], enc.groups, g_lo, g_go, names)
+    fresh_items = list(world.items.values())
+    ft = encoder.encode_lws(fresh_items, world.cluster(), "zone")
+    w_lo, w_go, w_occ = oracle.sweep_lws(ft.lws, ft.groups, ft.pod_state, ft.pod_ident, ft.nodes, flags=R.SWEEP_GANG,
+                                         want_occupancy=True)
+    want_l, want_g = outputs_by_name(ft.lws, ft.groups, w_lo, w_go,
+                                     {i: (it.lws.namespace, it.lws.name) for i, it in enumerate(fresh_items)})
+    assert got_l == want_l and got_g == want_g
+    assert np.array_equal(engine.resident_occupancy(), w_occ)
+    want_p = oracle.place(enc.node_rec, w_occ, len(enc.domain_values), enc.n_namespaces, enc.reqs)
+    assert engine.resident_place_outputs().tobytes() == want_p.tobytes()
+
+
 def test_ds_sweep_c4_full_size(engine):
     """BASELINE.json configs[3]: 50k two-role DisaggregatedSets, every output against the oracle."""
     import oracle
