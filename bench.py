@@ -797,8 +797,10 @@ def run_ours(args):
 
         def handover():
             if n_req:
+                # (the encoder emits the request table grouped by namespace: promised, checked on the device)
                 return eng.reconcile_host(h["lws"], h["groups"], h["pst"], h["pid"], h["reqs"], h["occ"], n_ns,
-                                          flags=t.flags, out=(h["lo"], h["go"]), place_out=h["po"])[2]
+                                          flags=t.flags | (R.SWEEP_PLACE_GROUPED if grouped else 0), out=(h["lo"], h["go"]),
+                                          place_out=h["po"])[2]
             eng.sweep_lws_host(h["lws"], h["groups"], h["pst"], h["pid"], flags=t.flags, out=(h["lo"], h["go"]))
 
         sec, _ = wall(handover, max(10, args.e2e_steps // 10))

@@ -555,7 +555,10 @@ LWSE_API int lwse_reconcile_device(lwse_engine* e, const lwse_lws_tables* d, con
 
 /* The same tick from host tables: lwse_sweep_lws_host(host) and lwse_place_host(reqs, …) in one
  * call, the placement round solved on the side stream while the sweep's tables are uploaded;
- * returns when all results are in the caller's buffers.  n_reqs == 0: sweep only. */
+ * returns when all results are in the caller's buffers.  n_reqs == 0: sweep only.
+ * host->flags & LWSE_SWEEP_PLACE_GROUPED: the request table is grouped by namespace — the call then
+ * skips its own pass over the table (it is checked on the device instead: LWSE_ERR_BAD_TABLE when
+ * the promise does not hold; without the flag the call finds out itself). */
 LWSE_API int lwse_reconcile_host(lwse_engine* e, const lwse_lws_tables* host, const lwse_place_req* reqs,
                                  uint32_t n_reqs, const uint32_t* occupancy, uint32_t n_namespaces,
                                  lwse_place_out* place_out);

@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -572,7 +573,10 @@ LWSE_API int lwse_sweep_lws_device(lwse_engine* e, const lwse_lws_tables* t, voi
 
 // lwse_sweep_lws_host with the engine locked and its device current; returns after the results
 // are in the caller's tables (stream synchronized — the only synchronize of the call).
-static int sweep_host_locked(lwse_engine* e, const lwse_lws_tables* h) {
+// `after_uploads` (optional): called once the table uploads are enqueued and before the sweep is —
+// lwse_reconcile_host enqueues its placement branch there, so that the copy engine starts on the
+// big tables at once instead of behind the host-side preparation of the round.
+static int sweep_host_locked(lwse_engine* e, const lwse_lws_tables* h, const std::function<int()>* after_uploads = nullptr) {
   cudaStream_t s = e->stream;
   const size_t b_lws = (size_t)h->n_lws * sizeof(lwse_lws_rec);
   const size_t b_grp = (size_t)h->n_groups * sizeof(lwse_group_rec);
@@ -643,6 +647,10 @@ static int sweep_host_locked(lwse_engine* e, const lwse_lws_tables* h) {
   }
   if (b_grp) LWSE_CUDA(e, cudaMemcpyAsync(e->groups.p, h->groups, b_grp, cudaMemcpyHostToDevice, s));
   if (b_lws) LWSE_CUDA(e, cudaMemcpyAsync(e->lws.p, h->lws, b_lws, cudaMemcpyHostToDevice, s));
+  if (after_uploads) {
+    const int arc = (*after_uploads)();
+    if (arc != LWSE_OK) return arc;
+  }
   if (prefetching) LWSE_CUDA(e, cudaStreamWaitEvent(s, e->ev_join, 0));
   int launched = lwse::launch_lws_sweep(&d, (const lwse_node_rec*)e->nodes.p, e->n_nodes, e->scan_scratch.p, e->sm_count,
                                         s, &cuda_err, nullptr, counted ? (uint32_t*)e->h_counts_dev.p : nullptr,
@@ -1427,8 +1435,14 @@ LWSE_API int lwse_reconcile_host(lwse_engine* e, const lwse_lws_tables* h, const
   if (rc != LWSE_OK) return rc;
   std::lock_guard<std::mutex> lock(e->mu);
   DeviceGuard guard(e->device);
-  if (n_reqs) {
-    if (e->n_nodes == 0 || e->n_domains == 0) return LWSE_ERR_NOT_READY;
+  if (n_reqs && (e->n_nodes == 0 || e->n_domains == 0)) return LWSE_ERR_NOT_READY;
+  // LWSE_SWEEP_PLACE_GROUPED: the caller promises a request table grouped by namespace (the encoder
+  // emits it that way) — no host pass over the table; the condense kernel counts order violations
+  // and a broken promise comes back as LWSE_ERR_BAD_TABLE.
+  const bool promised = n_reqs && (h->flags & LWSE_SWEEP_PLACE_GROUPED) && lwse::place_ns_supported(e->n_nodes, e->n_domains);
+  bool check_order = false;
+  const std::function<int()> place_branch = [&]() -> int {
+    if (!n_reqs) return LWSE_OK;
     cudaStream_t ps = e->side_stream;
     LWSE_CUDA(e, e->place_reqs.reserve((size_t)n_reqs * sizeof(lwse_place_req) + 16));
     LWSE_CUDA(e, e->place_out.reserve((size_t)n_reqs * sizeof(lwse_place_out) + 16));
@@ -1439,18 +1453,23 @@ LWSE_API int lwse_reconcile_host(lwse_engine* e, const lwse_lws_tables* h, const
       LWSE_CUDA(e, cudaMemcpyAsync(e->place_occ.p, occupancy, (size_t)e->n_nodes * 4, cudaMemcpyHostToDevice, ps));
     else
       LWSE_CUDA(e, cudaMemsetAsync(e->place_occ.p, 0, (size_t)e->n_nodes * 4, ps));
-    const uint32_t form = grouped_by_namespace(reqs, n_reqs)
-                              ? ((h->flags & LWSE_SWEEP_PLACE_SCAN) ? kFormScan : kFormGrouped) : kFormGeneral;
-    rc = place_locked(e, (const lwse_place_req*)e->place_reqs.p, n_reqs, (const uint32_t*)e->place_occ.p, n_namespaces,
-                      (lwse_place_out*)e->place_out.p, nullptr, ps, 1, n_reqs, 0, false, form);
-    if (rc == LWSE_OK)
-      LWSE_CUDA(e, cudaMemcpyAsync(place_out, e->place_out.p, (size_t)n_reqs * sizeof(lwse_place_out),
-                                   cudaMemcpyDeviceToHost, ps));
-  }
-  const int rc_sweep = rc == LWSE_OK ? sweep_host_locked(e, h) : rc;
+    const bool grouped = promised || grouped_by_namespace(reqs, n_reqs);
+    const uint32_t form = grouped ? ((h->flags & LWSE_SWEEP_PLACE_SCAN) ? kFormScan : kFormGrouped) : kFormGeneral;
+    const int prc = place_locked(e, (const lwse_place_req*)e->place_reqs.p, n_reqs, (const uint32_t*)e->place_occ.p, n_namespaces,
+                                 (lwse_place_out*)e->place_out.p, nullptr, ps, 1, n_reqs, 0, false, form);
+    if (prc != LWSE_OK) return prc;
+    if (promised && g_place_form_env != 0 && e->place_scans_ptr != nullptr) {  // (the namespace kernels ran: their counter block)
+      LWSE_CUDA(e, cudaMemcpyAsync(e->h_rounds + 8, e->place_rounds_ptr + 2, 4, cudaMemcpyDeviceToHost, ps));
+      check_order = true;
+    }
+    LWSE_CUDA(e, cudaMemcpyAsync(place_out, e->place_out.p, (size_t)n_reqs * sizeof(lwse_place_out), cudaMemcpyDeviceToHost, ps));
+    return LWSE_OK;
+  };
+  const int rc_sweep = sweep_host_locked(e, h, &place_branch);
   if (n_reqs) {
     const cudaError_t pe = cudaStreamSynchronize(e->side_stream);
     if (rc_sweep == LWSE_OK && pe != cudaSuccess) return fail_cuda(e, pe);
+    if (rc_sweep == LWSE_OK && check_order && e->h_rounds[8] != 0u) return LWSE_ERR_BAD_TABLE;
   }
   return rc_sweep;
 }

@@ -360,6 +360,27 @@ def test_reconcile_host_one_call(engine):
     lo, go, po = engine.reconcile_host(t.lws, t.groups, t.pod_state, t.pod_ident, reqs[:0], None, 1, flags=t.flags)
     same(lo, want_lo, "lws_out")
     assert len(po) == 0
+    # LWSE_SWEEP_PLACE_GROUPED: the caller promises the grouping, the call skips its own pass over the table …
+    from lws_b200.engine import LwseError
+
+    t3 = synth.make("C3", 0.02)
+    reqs3 = t3.place_requests()
+    assert bool(np.all(np.diff(reqs3["ns"].astype(np.int64)) >= 0)) and t3.n_namespaces > 1
+    engine.upload_nodes(t3.nodes, t3.n_domains)
+    w_lo, w_go, occ3 = oracle.sweep_lws(t3.lws, t3.groups, t3.pod_state, t3.pod_ident, t3.nodes, flags=t3.flags, want_occupancy=True)
+    lo, go, po = engine.reconcile_host(t3.lws, t3.groups, t3.pod_state, t3.pod_ident, reqs3, occ3, t3.n_namespaces,
+                                       flags=t3.flags | R.SWEEP_PLACE_GROUPED)
+    same(lo, w_lo, "lws_out")
+    same(po, oracle.place(t3.nodes, occ3, t3.n_domains, t3.n_namespaces, reqs3), "place_out (promised grouping)")
+    # … and a broken promise is found on the device
+    bad = reqs3[::-1].copy()
+    assert not bool(np.all(np.diff(bad["ns"].astype(np.int64)) >= 0))
+    with pytest.raises(LwseError):
+        engine.reconcile_host(t3.lws, t3.groups, t3.pod_state, t3.pod_ident, bad, occ3, t3.n_namespaces,
+                              flags=t3.flags | R.SWEEP_PLACE_GROUPED)
+    # without the flag the same table takes the general kernel: fine
+    lo, go, po = engine.reconcile_host(t3.lws, t3.groups, t3.pod_state, t3.pod_ident, bad, occ3, t3.n_namespaces, flags=t3.flags)
+    same(po, oracle.place(t3.nodes, occ3, t3.n_domains, t3.n_namespaces, bad), "place_out (ungrouped, general kernel)")
 
 
 def test_peer_exchange_degenerate_world_of_one():
