@@ -403,11 +403,14 @@ LWSE_API int lwse_resident_outputs(lwse_engine* e, lwse_lws_out* lws_out, lwse_g
  * Watch events in (as row patches), actions out (the result rows that changed), ONE call:
  *   patches -> scatter kernel -> fused pod scan + group pass -> LWS pass     (engine stream)
  *           \-> placement round over the resident request table            (side stream)
- * The patch rows / values are read by the GPU where the host wrote them when they lie in the
- * engine's arena (pinned, mapped memory: lwse_resident_arena) — no staging copy; the kernels
- * write the changed result rows straight into pinned, mapped result buffers and the last CTA of
- * each branch raises a sequence word the call spins on: no stream synchronize, no device->host
- * copy on the critical path.  Replaces, per reconcile pass, the informer-cache reads of
+ * The patch rows / values are consumed where the host wrote them when they lie in the engine's
+ * arena (pinned, mapped memory: lwse_resident_arena) — no staging copy (large sets go to a device
+ * mirror with one copy-engine transfer, small ones are read in place over PCIe); the kernels
+ * append the changed result rows to device lists, a publish kernel copies them into pinned,
+ * mapped result buffers and raises a sequence word the call spins on: no stream synchronize, no
+ * device->host copy-engine launch on the path.  A tick that follows one still in flight is
+ * replayed as one CUDA graph (LWSE_TICK_GRAPH=0 turns that off).  Replaces, per reconcile pass, the
+ * informer-cache reads of
  * leaderworkerset_controller.go:421,584,598 and pod_controller.go:348 (List) for every object. */
 
 typedef struct lwse_place_req lwse_place_req; /* defined below (Placement) */
