@@ -335,6 +335,23 @@ def add_tpu_variables(pod: dict, size: int) -> Optional[str]:
     return None
 
 
+KubeGroupNameAnnotationKey = "scheduling.k8s.io/group-name"  # volcano.sh/apis v1.12.1 scheduling/v1beta1
+
+
+def volcano_inject_pod_group_metadata(pod: dict) -> Optional[str]:
+    """VolcanoProvider.InjectPodGroupMetadata (pkg/schedulerprovider/volcano_provider.go:103-109): the pod's
+    PodGroup is ``GetPodGroupName(lws, groupIndex, revision)`` = "<lws>-<group index>-<revision key>"
+    (interface.go:35, :49-51).  Go writes into ``pod.Annotations`` without a nil check: a pod without
+    annotations panics there — reported as an error string here."""
+    md = _md(pod)
+    labels = md.get("labels") or {}
+    if md.get("annotations") is None:
+        return "assignment to entry in nil map"
+    md["annotations"][KubeGroupNameAnnotationKey] = "%s-%s-%s" % (
+        labels.get(api.SetNameLabelKey, ""), labels.get(api.GroupIndexLabelKey, ""), labels.get(api.RevisionKey, ""))
+    return None
+
+
 def default_batch(pods: Sequence[dict], sha1_batch: Callable[[list], "np.ndarray"],
                   inject_pod_group_metadata: Optional[Callable[[dict], Optional[str]]] = None) -> list[Optional[str]]:
     """The whole of ``PodWebhook.Default`` (pod_webhook.go:83-178) over a batch of admission requests

@@ -143,3 +143,22 @@ def test_defaulting_entry(case):
 def test_the_fixture_is_the_whole_range():
     assert GOLD["source"] == "test/integration/webhooks/pod_test.go:265-868" and len(GOLD["cases"]) == 20
     assert sum(len(c["checks"]) for c in GOLD["cases"]) == 36
+
+
+def test_gang_scheduling_entry_adds_the_pod_group_annotation():
+    """test/integration/webhooks/pod_test.go:913-935 ("should add pod group annotation when creating a lws pod"),
+    with the Volcano provider configured (pod_webhook.go:159-164 → volcano_provider.go:103-109): the pod's
+    annotation scheduling.k8s.io/group-name is "<lws>-<group index>-<revision>" = "test-0-1"."""
+    pod = {"metadata": {"name": "test-pod-0", "namespace": NAMESPACE,
+                        "labels": {api.SetNameLabelKey: "test", api.GroupIndexLabelKey: "0", api.RevisionKey: "1"},
+                        "annotations": {api.SizeAnnotationKey: "2"}},
+           "spec": resolve({"$chain": [["MakeLeaderPodSpec"]]})}
+    assert W.default_batch([pod], sha1_batch, inject_pod_group_metadata=W.volcano_inject_pod_group_metadata) == [None]
+    assert pod["metadata"]["annotations"][W.KubeGroupNameAnnotationKey] == "test-0-1"
+    # no provider configured: no annotation (schedulerProvider == nil, pod_webhook.go:159)
+    pod2 = {"metadata": {"name": "test-pod-0", "namespace": NAMESPACE,
+                         "labels": {api.SetNameLabelKey: "test", api.GroupIndexLabelKey: "0", api.RevisionKey: "1"},
+                         "annotations": {api.SizeAnnotationKey: "2"}},
+            "spec": resolve({"$chain": [["MakeLeaderPodSpec"]]})}
+    assert W.default_batch([pod2], sha1_batch) == [None]
+    assert W.KubeGroupNameAnnotationKey not in pod2["metadata"]["annotations"]
