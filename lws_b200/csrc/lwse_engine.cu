@@ -1731,33 +1731,24 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
   //  host's enqueue time is what limits the rate; a lone tick is faster kernel by kernel, because its
   //  round starts while the copy engine still moves the pod patches; 2 = always; 0 = never)
   const bool shared_occ = (flags & LWSE_TICK_SHARED_OCCUPANCY) != 0;
-  const bool graph_base = e->use_graph >= 1 && all_in_place && !any_range && (!shared_occ || (do_place && e->xch_connected)) &&
-                          (do_sweep || do_place) && !(has_side && !do_place) &&
-                          (!do_place || (e->r_place_grouped && g_place_form_env != 0 && lwse::place_ns_supported(e->n_nodes, e->n_domains)));
-  const bool full_graph = graph_base && (e->use_graph >= 2 || in_flight);
-  bool has_main = false;
-  for (uint32_t i = 0; i < n_segs; i++)
-    if (segs[i].n && segs[i].table != LWSE_TABLE_PLACE_REQS) has_main = true;
-  // A lone tick (nothing in flight) with pod patches: HYBRID — the round is enqueued kernel by kernel on
-  // the side stream, where it starts at once and runs while the copy engine still moves the pod
-  // patches, and only the sweep branch (scatter -> fused -> LWS pass) is a graph behind the copy:
-  // four launches less on the host, the same overlap on the device.
-  const bool hybrid = graph_base && !full_graph && e->use_graph == 1 && do_sweep && do_place && has_main && !has_ident && !shared_occ;
-  if (full_graph || hybrid) {
-    bool has_patches = hybrid;
+  const bool graph_ok = (e->use_graph >= 2 || (e->use_graph == 1 && in_flight)) && all_in_place && !any_range &&
+                        (!shared_occ || (do_place && e->xch_connected)) &&
+                        (do_sweep || do_place) && !(has_side && !do_place) &&
+                        (!do_place || (e->r_place_grouped && g_place_form_env != 0 && lwse::place_ns_supported(e->n_nodes, e->n_domains)));
+  if (graph_ok) {
+    bool has_patches = false;
     for (uint32_t i = 0; i < n_segs; i++)
       if (segs[i].n) has_patches = true;
     const uint32_t key = (has_patches ? 1u : 0u) | (do_sweep ? 8u : 0u) | (do_place ? 16u : 0u) |
                          ((flags & LWSE_SWEEP_GANG) ? 32u : 0u) | ((flags & LWSE_SWEEP_PLACE_SCAN) ? 64u : 0u) | (slot << 8) |
-                         (shared_occ ? 512u : 0u) | ((shared_occ && (flags & LWSE_EXCHANGE_LAGGED)) ? 1024u : 0u) |
-                         (hybrid ? 2048u : 0u);
+                         (shared_occ ? 512u : 0u) | ((shared_occ && (flags & LWSE_EXCHANGE_LAGGED)) ? 1024u : 0u);
     lwse_engine::TickGraph& tg = e->tick_graphs[key];
     bool replay = !tg.failed && tg.seen >= 1;  // the first tick of a shape runs eagerly: every buffer settles
     tg.seen++;
     ScatterPlan gp;
     if (replay) {
-      bool w = false;  // one plan for every table (hybrid: all but the request table): one scatter behind one copy of the arena span
-      rc = apply_patches_locked(e, segs, n_segs, &w, hybrid ? ~kSideTables : 0xFFFFFFFFu, s, 0, nullptr, 0, &gp, /*plan_only=*/true);
+      bool w = false;  // one plan for every table: one scatter launch behind one copy of the arena span
+      rc = apply_patches_locked(e, segs, n_segs, &w, 0xFFFFFFFFu, s, 0, nullptr, 0, &gp, /*plan_only=*/true);
       if (rc != LWSE_OK) return rc;
       if (gp.eager_only || gp.recount) replay = false;
       if (do_place && !e->r_place_grouped) replay = false;  // (a patch moved a request to another namespace)
@@ -1788,7 +1779,7 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
             const int launched = lwse::launch_scatter_desc(d_desc, e->sm_count, s, /*pdl=*/false, &err);
             if (launched < 0) cap((cudaError_t)err); else e->launches += (uint64_t)launched;
           }
-          if (do_place && !hybrid) {  // the round forks behind the scatter (it reads the request rows and the occupancy counters)
+          if (do_place) {  // the round forks behind the scatter (it reads the request rows and the occupancy counters)
             cap(cudaEventRecord(e->ev_fork, s));
             cap(cudaStreamWaitEvent(ps, e->ev_fork, 0));
             place_first_pdl = false;  // (behind an event: an ordinary launch)
@@ -1801,9 +1792,9 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
             place_mid_event = nullptr;
           }
           // behind the scatter kernel alone: programmatic, waits at its top; behind an event / first node: ordinary
-          sweep_first_mode = (has_patches && (hybrid || !(do_place && e->tick_place_ns))) ? 2 : 0;
+          sweep_first_mode = (has_patches && !(do_place && e->tick_place_ns)) ? 2 : 0;
           if (crc == LWSE_OK && do_sweep) crc = enqueue_sweep();
-          if (do_place && !hybrid) {
+          if (do_place) {
             cap(cudaEventRecord(e->ev_join, ps));
             cap(cudaStreamWaitEvent(s, e->ev_join, 0));
           }
@@ -1842,16 +1833,7 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
         LWSE_CUDA(e, cudaEventRecord(e->ev_dma, e->copy_stream));
         LWSE_CUDA(e, cudaStreamWaitEvent(s, e->ev_dma, 0));
       }
-      if (hybrid) {  // the round, kernel by kernel, while the copy engine works
-        rc = apply_side();
-        if (rc == LWSE_OK) rc = enqueue_place();
-        if (rc != LWSE_OK) return rc;
-      }
       LWSE_CUDA(e, cudaGraphLaunch(tg.exec, s));
-      if (hybrid) {
-        LWSE_CUDA(e, cudaEventRecord(e->ev_join, ps));
-        LWSE_CUDA(e, cudaStreamWaitEvent(s, e->ev_join, 0));
-      }
       e->launches += tg.kernels;
       e->graph_ticks++;
       if (shared_occ) e->xch_step++;  // (the replayed push kernel advanced the device counter by one)
@@ -1864,7 +1846,7 @@ static int tick_submit_locked(lwse_engine* e, const lwse_patch_seg* segs, uint32
       if (!pl[2].count && do_place)
         pl[2] = {reinterpret_cast<uint32_t*>(chg_v + e->chg_off[4]), chg_v + e->chg_off[5], reinterpret_cast<uint32_t*>(chg_d + e->chg_off[4]),
                  chg_d + e->chg_off[5], cnt + 4, e->rn_reqs, (uint32_t)sizeof(lwse_place_out)};
-      if (do_place && !hybrid) {
+      if (do_place) {
         e->tick_place_ns = tg.place_ns;
         e->place_rounds_ptr = tg.rounds_ptr;
       }
