@@ -280,3 +280,37 @@ def test_n_role_default_config():  # planner_test.go:1057-1069: surge 1, unavail
         _, role_out, _ = oracle.sweep_ds(t.ds, t.roles, t.revroles)
         direct = oracle.ds_compute_next_step([2] * n, [2] * n, [0] * n, [2] * n, [1] * n, [0] * n)
         assert [int(role_out[i]["next_new"]) for i in range(n)] == direct[1] == [1] * n
+
+
+def test_fresh_deployment_and_scaling_without_rolling_update():
+    """pkg/controllers/disaggregatedset/disaggregatedset_controller_test.go:70-102 (TestFreshDeploymentNoRollingUpdate)
+    and :104-140 (TestScalingWithoutRollingUpdate): no old revision → the simple path of Reconcile
+    (disaggregatedset_controller.go:95-112): the target revision's LWS go straight to spec.replicas."""
+    roles = [api.DisaggregatedRoleSpec("prefill", 3, None), api.DisaggregatedRoleSpec("decode", 2, None)]
+    t = encoder.encode_ds([encoder.DsItem(api.DisaggregatedSet("fresh-deploy", roles=roles), "rev", [])])
+    ds_out, role_out, rr = oracle.sweep_ds(t.ds, t.roles, t.revroles)
+    assert not ds_out[0]["flags"] & R.DOUT_ROLLING and not ds_out[0]["flags"] & R.DOUT_BAD_TABLE
+    assert [int(x) for x in rr[-2:]] == [3, 2]  # prefill LWS created with 3 replicas, decode with 2
+    roles = [api.DisaggregatedRoleSpec("prefill", 5, None), api.DisaggregatedRoleSpec("decode", 4, None)]
+    t = encoder.encode_ds([encoder.DsItem(api.DisaggregatedSet("scale-test", roles=roles), "rev",
+                                          [_child("prefill", "rev", 3, 1.0), _child("decode", "rev", 2, 1.0)])])
+    ds_out, role_out, rr = oracle.sweep_ds(t.ds, t.roles, t.revroles)
+    assert not ds_out[0]["flags"] & R.DOUT_ROLLING
+    assert [int(x) for x in rr[-2:]] == [5, 4]  # "prefill replicas should be scaled to 5", "decode … to 4"
+
+
+@pytest.mark.parametrize("annotations,want", [  # lws_manager_test.go:51-101 TestParseInitialReplicasAnnotation
+    ({}, -1), ({"other-key": "value"}, -1), ({api.DSInitialReplicasAnnotationKey: "not-a-number"}, -1),
+    ({api.DSInitialReplicasAnnotationKey: "5"}, 5), ({api.DSInitialReplicasAnnotationKey: "0"}, 0)])
+def test_parse_initial_replicas_annotation(annotations, want):
+    assert encoder.get_initial_replicas(api.ChildLWS("r", "x", 3, annotations=dict(annotations))) == want
+
+
+@pytest.mark.parametrize("replicas,want", [(None, 1), (5, 5), (0, 0)])  # lws_manager_test.go:103-138 TestGetLWSReplicas
+def test_lws_replicas_nil_is_one(replicas, want):
+    """getLWSReplicas (utils.go:160-165): nil spec.replicas counts as 1 — in the record row and in the sums."""
+    t = encoder.encode_ds([encoder.DsItem(_ds((4, 4)), "new", [
+        api.ChildLWS("prefill", "old", replicas, 0, 1.0, {}), _child("decode", "old", 2, 1.0),
+        _child("prefill", "new", 0, 2.0), _child("decode", "new", 0, 2.0)])])
+    assert int(t.revroles[0]["replicas"]) == want
+    assert bool(int(t.revroles[0]["flags"]) & R.RR_REPLICAS_NIL) == (replicas is None)
