@@ -66,6 +66,14 @@ def main():
                                      "cases": G.table_entries(tpu, "func TestAddTPUVariablesSkip(")}
     out["add_tpu_variables_subgroup"] = {"source": "pkg/utils/accelerators/tpu_test.go:348-588",
                                          "cases": G.table_entries(tpu, "func TestAddTPUVariablesSubGroup(")}
+    out["get_containers_requesting_tpus"] = {"source": "pkg/utils/accelerators/tpu_test.go:590-656",
+                                             "cases": G.table_entries(tpu, "func TestGetContainersRequestingTPUs(")}
+    out["get_container_requesting_tpus"] = {"source": "pkg/utils/accelerators/tpu_test.go:658-704",
+                                            "cases": G.table_entries(tpu, "func TestGetContainerRequestingTPUs(")}
+    out["pod_requests_tpus"] = {"source": "pkg/utils/accelerators/tpu_test.go:706-756",
+                                "cases": G.table_entries(tpu, "func TestPodRequestsTPUs(")}
+    out["get_env_var_if_in_container"] = {"source": "pkg/utils/pod/pod_utils_test.go:188-256",
+                                          "cases": G.table_entries(rd("pkg/utils/pod/pod_utils_test.go"), "func TestGetEnvVarIfInContainer(")}
     out["wrappers"] = {"source": "test/wrappers/wrappers.go", "functions": wrapper_literals(rd("test/wrappers/wrappers.go"))}
     path = os.path.join(HERE, "webhook_vectors.json")
     json.dump(out, open(path, "w"), indent=1, sort_keys=True)

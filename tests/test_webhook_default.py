@@ -2,7 +2,9 @@
 tests/golden/extract_webhook_vectors.py into tests/golden/webhook_vectors.json:
   pkg/webhooks/pod_webhook_test.go:66-169 (SetExclusiveAffinities), :171-270 (exclusiveAffinityApplied),
   pkg/utils/pod/pod_utils_test.go:103-186 (AddLWSVariables),
-  pkg/utils/accelerators/tpu_test.go:34-293, :295-346, :348-588 (AddTPUVariables, …Skip, …SubGroup)."""
+  pkg/utils/accelerators/tpu_test.go:34-293, :295-346, :348-588 (AddTPUVariables, …Skip, …SubGroup),
+  :590-656, :658-704, :706-756 (getContainersRequestingTPUs, getContainerRequestingTPUs, PodRequestsTPUs),
+  pkg/utils/pod/pod_utils_test.go:188-256 (getEnvVarValueIfInContainer)."""
 import copy
 import hashlib
 import json
@@ -153,6 +155,46 @@ def test_add_tpu_variables_skip(case):
     pod = resolve(case["pod"])
     before = copy.deepcopy(pod)
     assert W.add_tpu_variables(pod, 2) is None and pod["spec"] == before["spec"]  # nothing is injected twice
+
+
+@pytest.mark.parametrize("case", GOLD["get_containers_requesting_tpus"]["cases"], ids=lambda c: c["name"])
+def test_get_containers_requesting_tpus(case):
+    """tpu_test.go:590-656: only the count is checked there; the order (containers, then init containers) by :658-704."""
+    got = W.containers_requesting_tpus(resolve(case["podSpec"]) or {})
+    assert len(got) == case["expectedNumContainer"]
+
+
+def _comparable_container(c):
+    """cmp.Diff over corev1.Container: quantities compare by value ("4" == 4), absent == empty."""
+    if c is None:
+        return None
+    out = {k: v for k, v in c.items() if v not in (None, [], {})}
+    res = {part: {k: str(q) for k, q in qs.items()} for part, qs in (out.get("resources") or {}).items() if qs}
+    if res:
+        out["resources"] = res
+    return out
+
+
+@pytest.mark.parametrize("case", GOLD["get_container_requesting_tpus"]["cases"], ids=lambda c: c["name"])
+def test_get_container_requesting_tpus(case):
+    """tpu_test.go:658-704; getContainerRequestingTPUs (tpu.go:91-97) is the first of containers_requesting_tpus."""
+    got = W.containers_requesting_tpus(resolve(case["podSpec"]))
+    first = got[0] if got else None
+    assert _comparable_container(first) == _comparable_container(resolve(case["expectedContainer"]))
+
+
+@pytest.mark.parametrize("case", GOLD["pod_requests_tpus"]["cases"], ids=lambda c: c["name"])
+def test_pod_requests_tpus(case):
+    """tpu_test.go:706-756"""
+    assert W.pod_requests_tpus(resolve(case["podSpec"]) or {}) is case["expected"]
+
+
+@pytest.mark.parametrize("case", GOLD["get_env_var_if_in_container"]["cases"], ids=lambda c: c["name"])
+def test_get_env_var_value_if_in_container(case):
+    """pod_utils_test.go:188-256"""
+    found, value = W.get_env_var_value_if_in_container(case["container"], case["envVarName"])
+    assert found is case["expectEnvVar"]
+    assert value == case["expectedEnvValue"]
 
 
 def test_default_batch_end_to_end():
