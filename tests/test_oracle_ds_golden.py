@@ -314,3 +314,39 @@ def test_lws_replicas_nil_is_one(replicas, want):
         _child("prefill", "new", 0, 2.0), _child("decode", "new", 0, 2.0)])])
     assert int(t.revroles[0]["replicas"]) == want
     assert bool(int(t.revroles[0]["flags"]) & R.RR_REPLICAS_NIL) == (replicas is None)
+
+
+INITIAL_STATE = json.load(open(os.path.join(HERE, "golden", "ds_initial_state_vectors.json")))["cases"]
+
+
+@pytest.mark.parametrize("case", INITIAL_STATE, ids=[c["name"] for c in INITIAL_STATE])
+def test_compute_initial_replica_state(case):
+    """pkg/utils/disaggregatedset/utils_test.go:177-412 TestComputeInitialReplicaState (extracted by
+    tests/golden/extract_ds_initial_state_vectors.py): ComputeInitialReplicaState (utils.go:55-81) sums, per
+    role, the initial-replicas annotation of the old LeaderWorkerSets — spec.replicas when the annotation is
+    absent or unparsable, 1 when that is nil too.  Here the rule is split between the encoder (the record row:
+    replicas with nil → 1, initial_replicas or -1) and the planner-state sum every implementation applies to the
+    rows (oracle/lwse_oracle_ds.c:394, lwse_ds_kernels.cu): each list element becomes the child of its own old
+    revision, and the per-role sum over the encoded rows must be the reference's total."""
+    assert api.DSRoleLabelKey == "disaggregatedset.x-k8s.io/role"
+    children = []
+    for i, lws in enumerate(case["lwsList"]):
+        md = lws.get("metadata") or {}
+        role = (md.get("labels") or {}).get(api.DSRoleLabelKey, "")
+        if role == "":
+            continue  # utils.go:61-63
+        children.append(api.ChildLWS(role, f"old-{i}", (lws.get("spec") or {}).get("replicas"), 0, float(i + 1),
+                                     dict(md.get("annotations") or {})))
+    t = encoder.encode_ds([encoder.DsItem(_ds((4, 4)), "new", children)])
+    names = t.role_names[0]
+    n = len(names)
+    got = {name: 0 for name in names}
+    rows = t.revroles
+    assert len(rows) % n == 0
+    for k, row in enumerate(rows):
+        if not int(row["flags"]) & R.RR_EXISTS:
+            continue
+        init = int(row["initial_replicas"])
+        got[names[k % n]] += init if init >= 0 else int(row["replicas"])
+    for role, want in case["want"].items():
+        assert got.get(role, 0) == want
