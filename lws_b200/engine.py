@@ -435,11 +435,19 @@ class Engine:
         return rounds.value if want_rounds else None
 
     # --------------------------------------------------------------------- DS
-    def sweep_ds_host(self, ds, roles, revroles):
+    def sweep_ds_host(self, ds, roles, revroles, out=None):
+        """lwse_sweep_ds_host: host tables in, host result rows out.  `out` = (ds_out, role_out, revrole_out)
+        arrays to fill instead of fresh ones (page-locked tables and outputs copy at PCIe speed; pageable ones
+        are staged by the driver)."""
         assert ds.dtype == R.DS_REC and roles.dtype == R.DS_ROLE_REC and revroles.dtype == R.DS_REVROLE_REC
-        ds_out = R.aligned_empty(len(ds), R.DS_OUT)
-        role_out = R.aligned_empty(len(roles), R.DS_ROLE_OUT)
-        revrole_out = R.aligned_empty(len(revroles), R.DS_REVROLE_OUT)
+        if out is None:
+            ds_out = R.aligned_empty(len(ds), R.DS_OUT)
+            role_out = R.aligned_empty(len(roles), R.DS_ROLE_OUT)
+            revrole_out = R.aligned_empty(len(revroles), R.DS_REVROLE_OUT)
+        else:
+            ds_out, role_out, revrole_out = out
+            assert ds_out.dtype == R.DS_OUT and role_out.dtype == R.DS_ROLE_OUT and revrole_out.dtype == R.DS_REVROLE_OUT
+            assert len(ds_out) == len(ds) and len(role_out) == len(roles) and len(revrole_out) == len(revroles)
         t = R.DsTables(
             R.ptr(ds), len(ds), R.ptr(roles), len(roles), R.ptr(revroles), len(revroles),
             R.ptr(ds_out), R.ptr(role_out), R.ptr(revrole_out),

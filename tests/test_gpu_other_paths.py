@@ -148,6 +148,14 @@ def test_ds_sweep_matches_oracle(engine, kw):
     same(got[0], want[0], "ds_out")
     same(got[1], want[1], "role_out")
     same(got[2], want[2], "revrole_out")
+    # the caller's own result arrays (bench.py hands page-locked ones in)
+    out = (np.full(len(t.ds), 0x5A, np.uint8).repeat(R.DS_OUT.itemsize).view(R.DS_OUT),
+           np.full(len(t.roles), 0x5A, np.uint8).repeat(R.DS_ROLE_OUT.itemsize).view(R.DS_ROLE_OUT),
+           np.full(len(t.revroles), 0x5A5A5A5A, R.DS_REVROLE_OUT))
+    back = engine.sweep_ds_host(t.ds, t.roles, t.revroles, out=out)
+    assert all(a is b for a, b in zip(back, out))
+    for a, b, what in zip(out, want, ("ds_out", "role_out", "revrole_out")):
+        same(a, b, what + " (caller's arrays)")
     flags = want[0]["flags"]
     if kw["n_ds"] >= 1000:  # the generator reaches every branch
         for bit in (R.DOUT_ROLLING, R.DOUT_INIT, R.DOUT_STABLE, R.DOUT_STEP, R.DOUT_NEW_READY):
