@@ -38,6 +38,8 @@ struct PublishListHost {
 int launch_publish(const PublishListHost* lists, const uint32_t* d_extra, uint32_t* h_words, uint32_t seq_slot,
                    uint32_t seq, uint32_t* d_ticket, uint32_t expected_rows, cudaStream_t s, int* cuda_err,
                    uint32_t* d_clear, uint32_t n_clear, bool pdl);
+cudaError_t set_sweep_carveout(int pct);
+cudaError_t set_place_ns_carveout(int pct);
 int launch_lws_sweep(const lwse_lws_tables* t, const lwse_node_rec* d_nodes, uint32_t n_nodes,
                      void* scratch, int sm_count, cudaStream_t s, int* cuda_err, const SweepChangeLists* cl,
                      uint32_t* d_event_count = nullptr, int first_mode = 1);
@@ -436,6 +438,12 @@ LWSE_API int lwse_create(const lwse_config* cfg, lwse_engine** out) {
     if (e->tick_order < 0 || e->tick_order > 2) e->tick_order = 0;
     const char* g = getenv("LWSE_TICK_GRAPH");
     e->use_graph = g ? atoi(g) : 1;
+    const char* c = getenv("LWSE_SMEM_CARVEOUT");  // percent of the maximum shared memory, every tick kernel alike
+    if (c && atoi(c) >= 0 && atoi(c) <= 100) {
+      (void)lwse::set_sweep_carveout(atoi(c));
+      (void)lwse::set_place_ns_carveout(atoi(c));
+      (void)cudaGetLastError();
+    }
   }
   *out = e;
   return LWSE_OK;

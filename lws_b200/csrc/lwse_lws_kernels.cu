@@ -556,7 +556,12 @@ struct DirectBits {
   }
 };
 
-__global__ void __launch_bounds__(kFusedThreads, 3) group_fused_kernel(const GroupSweepArgs a) {
+#ifdef LWSE_FUSED_MAXNREG  // build-time experiment switch, see lwse_place_ns_kernels.cu
+#define LWSE_FUSED_BOUNDS __maxnreg__(LWSE_FUSED_MAXNREG)
+#else
+#define LWSE_FUSED_BOUNDS __launch_bounds__(kFusedThreads, 3)
+#endif
+__global__ void LWSE_FUSED_BOUNDS group_fused_kernel(const GroupSweepArgs a) {
   __shared__ uint32_t s_pend[kWinWords], s_ev[kWinWords];
   __shared__ uint32_t s_pair[kPairCap];  // tid << 16 | pod index relative to the window start
   __shared__ uint4 s_ctx4[kFusedThreads];
@@ -1443,6 +1448,28 @@ int launch_occupancy(const lwse_pod_ident* d_ident, uint64_t n_pods, uint32_t* d
   e = cudaGetLastError();
   if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
   return 1;
+}
+
+// LWSE_SMEM_CARVEOUT (experiment switch, engine creation): one preferred shared-memory carveout (percent of the
+// SM's maximum) for every kernel of a tick, so that CTAs of the sweep and of the placement round never ask the SM
+// for different L1 / shared-memory splits.
+cudaError_t set_sweep_carveout(int pct) {
+  cudaError_t e = cudaSuccess;
+  auto set = [&](const void* k) {
+    const cudaError_t r = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (r != cudaSuccess) e = r;
+  };
+  set((const void*)group_fused_kernel);
+  set((const void*)lws_sweep_kernel<1>);
+  set((const void*)lws_sweep_kernel<2>);
+  set((const void*)lws_sweep_kernel<4>);
+  set((const void*)lws_sweep_kernel<8>);
+  set((const void*)lws_sweep_kernel<16>);
+  set((const void*)lws_sweep_kernel<32>);
+  set((const void*)scatter_rows_kernel);
+  set((const void*)scatter_rows_desc_kernel);
+  set((const void*)publish_lists_kernel);
+  return e;
 }
 
 }  // namespace lwse

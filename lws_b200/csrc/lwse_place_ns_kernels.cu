@@ -216,8 +216,16 @@ __device__ __forceinline__ void diff_row(const PlaceNsArgs& a, uint32_t r, const
   }
 }
 
+// Register budget: LWSE_NS_MAXNREG (build-time experiment switch) caps the kernel with __maxnreg__ instead of
+// __launch_bounds__ (the two cannot be combined) so that a CTA of this kernel and CTAs of the sweep fit one SM's
+// register file side by side in a tick.
+#ifdef LWSE_NS_MAXNREG
+#define LWSE_NS_BOUNDS __maxnreg__(LWSE_NS_MAXNREG)
+#else
+#define LWSE_NS_BOUNDS __launch_bounds__(kScan ? kNsScanThreads : kNsThreads, 2)
+#endif
 template <bool kScan>
-__global__ void __launch_bounds__(kScan ? kNsScanThreads : kNsThreads, 2)
+__global__ void LWSE_NS_BOUNDS
     place_ns_kernel(const PlaceNsArgs a, const __grid_constant__ CUtensorMap words_map) {
   extern __shared__ uint8_t s_dyn[];
   // layout (from a 128-byte aligned base: the TMA destination):
@@ -722,6 +730,18 @@ int launch_place_ns(const lwse_node_rec* d_nodes, const uint32_t* d_dom_first, c
     if (e != cudaSuccess) { *cuda_err = (int)e; return -1; }
   }
   return 2;
+}
+
+cudaError_t set_place_ns_carveout(int pct) {  // see set_sweep_carveout (lwse_lws_kernels.cu)
+  cudaError_t e = cudaSuccess;
+  auto set = [&](const void* k) {
+    const cudaError_t r = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (r != cudaSuccess) e = r;
+  };
+  set((const void*)place_condense_kernel);
+  set((const void*)place_ns_kernel<false>);
+  set((const void*)place_ns_kernel<true>);
+  return e;
 }
 
 }  // namespace lwse
